@@ -1,0 +1,215 @@
+"""Seeded synthetic inputs shared by the pinning script, the tests and the bench.
+
+ORACLE / TEST INFRASTRUCTURE.  All draws come from CPU ``torch.Generator``s so the same tensors are produced in
+the build container and on the GPU box (same image, same torch).
+"""
+from __future__ import annotations
+
+import random
+from typing import List
+
+import torch
+
+from . import sd_modules as sdm
+from . import comat_ref as R
+
+
+def case_key(case: dict) -> str:
+    return ",".join(f"{k}={case[k]}" for k in sorted(case))
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def random_prob_maps(g, n, res, T=77, sharp=2.0):
+    """(n,res,res,T) rows summing to 1 over T — what a cross-attention softmax stores."""
+    return torch.softmax(torch.randn(n, res, res, T, generator=g) * sharp, dim=-1)
+
+
+def random_mask(g, size=512, empty=False):
+    """(1,1,size,size) bool: union of 1-2 axis-aligned rectangles covering 5-40 %."""
+    m = torch.zeros(1, 1, size, size, dtype=torch.bool)
+    if empty:
+        return m
+    for _ in range(int(torch.randint(1, 3, (1,), generator=g))):
+        h = int(torch.randint(size // 5, size * 6 // 10, (1,), generator=g))
+        w = int(torch.randint(size // 5, size * 6 // 10, (1,), generator=g))
+        y = int(torch.randint(0, size - h, (1,), generator=g))
+        x = int(torch.randint(0, size - w, (1,), generator=g))
+        m[..., y:y + h, x:x + w] = True
+    return m
+
+
+def random_words(g, n_words, T=77, max_tok=3, lo=1, hi=40):
+    words = []
+    perm = (torch.randperm(hi - lo, generator=g) + lo).tolist()
+    for _ in range(n_words):
+        k = int(torch.randint(1, max_tok + 1, (1,), generator=g))
+        words.append([perm.pop() for _ in range(k)])
+    return words
+
+
+# ------------------------------------------------------------------ layer loss (tc_loss_utils.py:66-173)
+LAYER_LOSS_CASES = [
+    dict(seed=1, res=8, heads=8, n_maps=1, n_words=1, empty=-1, msize=512),
+    dict(seed=2, res=16, heads=8, n_maps=3, n_words=3, empty=1, msize=512),
+    dict(seed=3, res=32, heads=8, n_maps=3, n_words=2, empty=-1, msize=512),
+    dict(seed=4, res=64, heads=8, n_maps=3, n_words=3, empty=-1, msize=512),
+    dict(seed=5, res=16, heads=20, n_maps=5, n_words=1, empty=-1, msize=512),   # SDXL-like head count
+    dict(seed=6, res=16, heads=8, n_maps=2, n_words=0, empty=-1, msize=512),    # W == 0 -> python zeros
+    dict(seed=7, res=8, heads=4, n_maps=2, n_words=2, empty=-1, msize=64),      # tiny-pipeline geometry
+]
+
+
+def layer_loss_inputs(seed, res, heads, n_maps, n_words, empty, msize):
+    g = _gen(seed)
+    maps = [random_prob_maps(g, heads, res) for _ in range(n_maps)]
+    masks = [random_mask(g, msize, empty=(i == empty)) for i in range(n_words)]
+    words = random_words(g, n_words)
+    return maps, masks, words, res
+
+
+# ------------------------------------------------------------------ mask loss (gsam_interface.py:140-228)
+MASK_LOSS_CASES = [
+    dict(seed=11, B=2, heads=8, layers="mid_8,up_16,up_32", n_t=2, msize=512),
+    dict(seed=12, B=3, heads=4, layers="up_8,up_16", n_t=1, msize=128),
+]
+_NOUNS = ["dog", "cat", "table", "sky", "car", "apple", "hat", "dog"]      # 'sky' is in the stop list; 'dog' repeats
+
+
+def mask_loss_inputs(seed, B, heads, layers, n_t, msize):
+    g = _gen(seed)
+    layer_ls = layers.split(",")
+    n_per = {"mid": 1, "up": 3, "down": 2}
+    attn_dict = {}
+    for ti in range(n_t):
+        d = {}
+        for ly in layer_ls:
+            place, res = ly.split("_")
+            d[ly] = [random_prob_maps(g, B * heads, int(res)) for _ in range(n_per[place])]
+        attn_dict[str(951 - 100 * ti)] = d
+    subtrees, idx2wp, masks_by_sample = [], [], []
+    rr = random.Random(seed)
+    for b in range(B):
+        n_groups = rr.randint(0 if b == B - 1 else 1, 3)
+        pos = list(range(1, 30))
+        rr.shuffle(pos)
+        groups, wp = [], {}
+        for _ in range(n_groups):
+            noun = rr.choice(_NOUNS)
+            npos = [pos.pop()] if rr.random() < 0.7 else [pos.pop(), pos.pop()]
+            if len(npos) == 1:
+                wp[npos[0]] = noun
+            else:
+                wp[npos[0]], wp[npos[1]] = noun[:2], noun[2:]
+            mods = []
+            for _ in range(rr.randint(0, 2)):
+                p = pos.pop()
+                wp[p] = "big"
+                mods.append(p)
+            groups.append(mods + [npos if len(npos) > 1 else npos[0]])
+        subtrees.append(groups)
+        idx2wp.append(wp)
+        _, attrs = R.words_from_subtrees(groups, wp, None)
+        # one mask per *surviving* noun is what get_mask returns; generate generously, slice later
+        masks_by_sample.append([random_mask(g, msize, empty=(rr.random() < 0.1)) for _ in range(max(1, len(attrs)))])
+    # masks must line up with the nouns that survive update_nouns_attributes: recompute with the restated filter
+    for b in range(B):
+        nouns, attrs = R.words_from_subtrees(subtrees[b], idx2wp[b], update_nouns_attributes)
+        masks_by_sample[b] = masks_by_sample[b][: max(1, len(nouns))]
+    return attn_dict, subtrees, idx2wp, masks_by_sample, layer_ls, B
+
+
+_INVALID_NOUNS = set(
+    "scene surface area atmosphere noise place kitchen dream interior exterior meal background bathroom room scent "
+    "street hillside mountain sky sea ocean lost language skill one night day morning space environment conditions "
+    "field shore restroom party grass snow meadow water shadow waves song cycle sunlight mysteries wall salon range "
+    "cry speech tone thing about activity air advertisement airport also".split())
+
+
+def update_nouns_attributes(nouns, attributes):
+    """Restated gsam_interface.py:232-261: drop nouns that occur more than once, then stop-listed nouns
+    (also when the noun minus its last character — a plural — is stop-listed)."""
+    keep = [(n, a) for n, a in zip(nouns, attributes) if nouns.count(n) == 1]
+    keep = [(n, a) for n, a in keep if n not in _INVALID_NOUNS and n[:-1] not in _INVALID_NOUNS]
+    return [n for n, _ in keep], [a for _, a in keep]
+
+
+# ------------------------------------------------------------------ pipeline (tiny geometry)
+PIPELINE_CASES = [
+    dict(seed=21, B=2, S=4, K=2, hw=32, rank=4),
+    dict(seed=22, B=1, S=5, K=1, hw=32, rank=4, rescale=0.7),
+]
+
+
+def make_tiny_unet(seed, rank=4, sdxl=False, up_std=0.05, width=32, ctx=64):
+    torch.manual_seed(seed)
+    unet = sdm.UNet2DConditionModel(**sdm.tiny_unet_config(sdxl=sdxl, width=width, cross_attention_dim=ctx))
+    unet.requires_grad_(False)
+    if rank:
+        sdm.install_lora(unet, rank, up_std=up_std, seed=seed + 1)
+    return unet
+
+
+def make_tiny_vae(seed, sdxl=False):
+    torch.manual_seed(seed)
+    vae = sdm.AutoencoderKL(block_out_channels=(32, 32, 64, 64), scaling_factor=0.13025 if sdxl else 0.18215)
+    vae.requires_grad_(False)
+    return vae
+
+
+def pipeline_world(seed, B, S, K, hw, rank, rescale=0.0, sdxl=False):
+    g = _gen(seed)
+    rr = random.Random(seed)
+    steps, attrcon = R.select_training_steps(S, K, rr, 2)
+    return dict(
+        make_unet=lambda: make_tiny_unet(seed, rank, sdxl),
+        vae=make_tiny_vae(seed + 5, sdxl),
+        prompt_embeds=torch.randn(B, 77, 64, generator=g),
+        null_embeds=torch.randn(1, 77, 64, generator=g).expand(B, -1, -1).contiguous(),
+        latents=torch.randn(B, 4, hw, hw, generator=g),
+        training_steps=steps, attrcon_steps=attrcon,
+        train_layer_ls=["up_8", "up_16", "up_32"],
+    )
+
+
+# ------------------------------------------------------------------ BLIP
+BLIP_CASES = [dict(seed=31, B=2, size=254, L=9), dict(seed=32, B=3, size=190, L=14)]
+
+
+def blip_token_batch(g, B, L_mean, vocab=30524):
+    """[CLS] + 'a photography of' stand-in ids + random wordpieces + [SEP], right-padded with 0."""
+    rows = []
+    for _ in range(B):
+        L = int(torch.clamp(torch.randn((), generator=g) * 4 + L_mean, 4, 40).round())
+        body = torch.randint(1000, 30000, (L,), generator=g)
+        rows.append(torch.cat([torch.tensor([101, 1037, 5855, 1997]), body, torch.tensor([102])]))
+    T = max(len(r) for r in rows)
+    ids = torch.zeros(B, T, dtype=torch.long)
+    mask = torch.zeros(B, T, dtype=torch.long)
+    for i, r in enumerate(rows):
+        ids[i, : len(r)] = r
+        mask[i, : len(r)] = 1
+    return ids, mask
+
+
+def blip_inputs(seed, B, size, L):
+    g = _gen(seed)
+    model = R.make_blip(large=False, seed=seed)
+    images = torch.rand(B, 3, size, size, generator=g)
+    ids, mask = blip_token_batch(g, B, L)
+    return model, images, ids, mask
+
+
+# ------------------------------------------------------------------ GAN
+GAN_CASES = [dict(seed=41, B=2, S=20, hw=16)]
+
+
+def gan_world(seed, B, S, hw):
+    g = _gen(seed)
+    d_unet = make_tiny_unet(seed, rank=4)
+    torch.manual_seed(seed + 3)
+    head = torch.nn.Sequential(torch.nn.Linear(4, 1))
+    return dict(d_unet=d_unet, head=head, fake=torch.randn(B, 4, hw, hw, generator=g),
+                real=torch.randn(B, 4, hw, hw, generator=g), null=torch.randn(B, 77, 64, generator=g))
