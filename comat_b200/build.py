@@ -1,0 +1,81 @@
+"""Build libcomat_b200.so (the C-ABI product library) with nvcc for sm_100a, in-tree.
+
+The library links only cudart (static) — no torch, no libcuda link-time dependency (driver entry points such as
+cuTensorMapEncodeTiled are resolved at run time through cudaGetDriverEntryPoint), so it loads on a CPU-only box
+for the symbol check and travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import glob
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libcomat_b200.so")
+STAMP = os.path.join(HERE, ".libcomat_b200.stamp")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found — comat_b200 has no CPU fallback and cannot be built without the CUDA toolkit")
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "comat_b200.h")]:
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    procs = []
+    objs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [nvcc, *flags, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"[comat_b200.build] nvcc failed for {src}:\n{out}\n")
+        elif verbose or "warning" in out.lower():
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-cudart", "static", "-Xlinker", "--no-undefined", "-ldl", "-lrt", "-lpthread"]
+    subprocess.check_call(cmd)
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

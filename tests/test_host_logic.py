@@ -1,0 +1,98 @@
+"""CPU: host-side logic of the product package + C-ABI library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import comat_ref as R
+from oracle import fixtures as FX
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from comat_b200 import build
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    hdr = open(os.path.join(ROOT, "include", "comat_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(comat_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 7
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/comat_b200.h but not exported"
+    lib.comat_version.restype = ctypes.c_int
+    assert lib.comat_version() >= 100
+    lib.comat_strerror.restype = ctypes.c_char_p
+    assert lib.comat_strerror(-1) == b"invalid argument"
+
+
+def test_product_has_no_cpu_fallback():
+    from comat_b200 import _lib, attn_loss
+    with pytest.raises(_lib.ComatError):
+        attn_loss.mask_resize_any(torch.zeros(1, 8, 8, dtype=torch.uint8), 4)
+
+
+def test_product_does_not_import_oracle():
+    import subprocess, sys
+    code = ("import sys; import comat_b200, comat_b200.attn_loss, comat_b200._lib; "
+            "bad=[m for m in sys.modules if m=='oracle' or m.startswith('oracle.')]; assert not bad, bad")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "comat_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_noun_filter_matches_oracle():
+    from comat_b200 import attn_loss
+    nouns = ["dog", "cat", "dog", "sky", "waves", "skys", "apple"]
+    attrs = [[1], [2, 3], [4], [5], [6], [7], [8, 9]]
+    assert attn_loss.update_nouns_attributes(nouns, attrs) == FX.update_nouns_attributes(nouns, attrs) == (["cat", "apple"], [[2, 3], [8, 9]])
+    st = [[3, [4, 5]], [7], []]
+    wp = {3: "big", 4: "ap", 5: "ple", 7: "sea"}
+    assert attn_loss.words_from_subtrees(st, wp) == (["apple"], [[3, 4, 5]])
+    assert R.words_from_subtrees(st, wp, FX.update_nouns_attributes) == (["apple"], [[3, 4, 5]])
+
+
+def _aa_any_emulation(mask, res):
+    """python emulation of comat_mask_resize_any (csrc/attnmap_loss.cu) — validates the window rule against torchvision."""
+    import math
+    H, W = mask.shape
+    out = torch.zeros(res, res)
+
+    def win(o, scale, n):
+        support = scale if scale >= 1 else 1.0
+        inv = 1.0 / scale if scale >= 1 else 1.0
+        c = scale * (o + 0.5)
+        lo, hi = max(int(c - support + 0.5), 0), min(int(c + support + 0.5), n)
+        return [j for j in range(lo, hi) if 1.0 - abs((j - c + 0.5) * inv) > 0]
+    sy, sx = H / res, W / res
+    for y in range(res):
+        ys = win(y, sy, H)
+        for x in range(res):
+            xs = win(x, sx, W)
+            out[y, x] = float(mask[ys][:, xs].any())
+    return out
+
+
+@pytest.mark.parametrize("size,res", [(512, 8), (512, 64), (64, 8), (96, 16), (100, 16)])
+def test_mask_resize_rule_matches_torchvision(size, res):
+    g = torch.Generator().manual_seed(size + res)
+    m = FX.random_mask(g, size)
+    m[0, 0, 3, 5] = True
+    ref = R.resize_mask(m, res)[0]
+    assert torch.equal(_aa_any_emulation(m[0, 0], res), ref)
+    single = torch.zeros(1, 1, size, size, dtype=torch.bool)
+    single[0, 0, size // 2, size // 2] = True
+    assert torch.equal(_aa_any_emulation(single[0, 0], res), R.resize_mask(single, res)[0])
+
+
+def test_select_training_steps():
+    import random
+    steps, attr = R.select_training_steps(20, 5, random.Random(0), 2)
+    assert len(steps) == 5 and steps[1] - steps[0] == 4 and all(a in steps for a in attr)
+    steps, _ = R.select_training_steps(50, 5, random.Random(1), 2)
+    assert steps[-1] <= 49 and steps[1] - steps[0] == 10

@@ -1,0 +1,128 @@
+"""CPU: the oracle restatement reproduces the golden vectors generated from the reference's own code
+(oracle/pin_against_reference.py).  Inputs are regenerated from seeds (oracle/fixtures.py)."""
+import pytest
+import torch
+
+from oracle import comat_ref as R
+from oracle import fixtures as FX
+from oracle import sd_modules as sdm
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    return (a - b).abs().max().item() / max(1e-12, b.abs().max().item())
+
+
+def test_param_totals_match_published():
+    # the only upstream-anchored structural check available offline
+    with torch.device("meta"):
+        assert sdm.count_params(sdm.UNet2DConditionModel(**sdm.SD15_UNET_CONFIG)) == 859_520_964
+        assert sdm.count_params(sdm.UNet2DConditionModel(**sdm.SDXL_UNET_CONFIG)) == 2_567_463_684
+        assert sdm.count_params(sdm.AutoencoderKL()) == 49_490_199
+        u = sdm.UNet2DConditionModel(**sdm.SD15_UNET_CONFIG)
+        x = sdm.UNet2DConditionModel(**sdm.SDXL_UNET_CONFIG)
+    assert len(u.attn_processors) == 32 and len(x.attn_processors) == 140
+
+
+def test_lora_param_totals():
+    with torch.device("meta"):
+        u = sdm.UNet2DConditionModel(**sdm.SD15_UNET_CONFIG)
+        n = 0
+        for name in u.attn_processors:
+            m = u.get_submodule(name.rsplit(".", 1)[0])
+            for lin in (m.to_q, m.to_k, m.to_v, m.to_out[0]):
+                n += 128 * (lin.in_features + lin.out_features)
+    assert n == 25_509_888  # 25.51 M
+
+
+def test_ddpm_timesteps_and_coefficients():
+    s = sdm.DDPMScheduler()
+    s.set_timesteps(20)
+    assert s.timesteps.tolist() == [951 - 50 * i for i in range(20)]
+    s.set_timesteps(50)
+    assert s.timesteps[0].item() == 981 and s.timesteps[-1].item() == 1
+    x = torch.randn(2, 4, 8, 8)
+    out = s.step(torch.zeros_like(x), 1, x, variance_noise=torch.zeros_like(x))   # t=1 -> prev_t<0 -> alpha_prev=1
+    assert torch.isfinite(out.prev_sample).all()
+
+
+@pytest.mark.parametrize("case", FX.LAYER_LOSS_CASES, ids=FX.case_key)
+def test_layer_loss_golden(case, golden):
+    g = golden("layer_loss")[FX.case_key(case)]
+    maps, masks, words, res = FX.layer_loss_inputs(**case)
+    maps = [m.requires_grad_(True) for m in maps]
+    d = R.grounding_loss_by_layer(masks, words, res, maps)
+    assert rel(d["token_loss"], g["token_loss"]) < 1e-6 and rel(d["pixel_loss"], g["pixel_loss"]) < 1e-6
+    assert [float(R.resize_mask(m, res).sum()) for m in masks] == g["mask_resized_sum"]
+    if words:
+        (d["token_loss"] + 0.5 * d["pixel_loss"]).backward()
+        for m, l2, probe in zip(maps, g["grad_l2"], g["grad_probe"]):
+            assert rel(m.grad.double().norm(), l2) < 1e-5
+            assert rel(m.grad.flatten()[:: max(1, m.grad.numel() // 64)][:64], probe) < 1e-5
+
+
+@pytest.mark.parametrize("case", FX.MASK_LOSS_CASES, ids=FX.case_key)
+def test_mask_loss_golden(case, golden):
+    g = golden("mask_loss")[FX.case_key(case)]
+    attn_dict, subtrees, idx2wp, masks_by_sample, layers, B = FX.mask_loss_inputs(**case)
+    words, masks = [], []
+    for b in range(B):
+        nouns, attrs = R.words_from_subtrees(subtrees[b], idx2wp[b], FX.update_nouns_attributes)
+        words.append(attrs)
+        masks.append(masks_by_sample[b] if nouns else None)
+    assert words == g["words"]
+    tok, pix = R.mask_loss(attn_dict, words, masks, layers, torch.zeros(1))
+    assert rel(tok, g["token_loss"]) < 1e-6 and rel(pix, g["pixel_loss"]) < 1e-6
+
+
+@pytest.mark.parametrize("case", FX.BLIP_CASES, ids=FX.case_key)
+def test_blip_score_golden(case, golden):
+    g = golden("blip_score")[FX.case_key(case)]
+    model, images, ids, mask = FX.blip_inputs(**case)
+    images.requires_grad_(True)
+    r = R.blip_score(model, images, ids, mask, 4)
+    assert rel(r, g["reward"]) < 1e-5
+    (-r).backward()
+    assert rel(images.grad.double().norm(), g["grad_l2"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", FX.GAN_CASES, ids=FX.case_key)
+def test_gan_golden(case, golden):
+    g = golden("gan")[FX.case_key(case)]
+    w = FX.gan_world(**case)
+    w["d_unet"].eval()
+    gl = R.d_forward(w["d_unet"], w["head"], sdm.DDPMScheduler(), w["fake"], w["null"], case["S"], "G")
+    dl = R.d_forward(w["d_unet"], w["head"], sdm.DDPMScheduler(), w["fake"], w["null"], case["S"], "D", w["real"])
+    assert rel(gl, g["G_loss"]) < 1e-5 and rel(dl, g["D_loss"]) < 1e-5
+
+
+@pytest.mark.parametrize("case", FX.PIPELINE_CASES[:1], ids=FX.case_key)
+def test_pipeline_golden(case, golden):
+    g = golden("pipeline")[FX.case_key(case)]
+    w = FX.pipeline_world(**case)
+    unet = w["make_unet"]()
+    ctrl = R.AttentionStore(w["train_layer_ls"])
+    assert R.register_attention_control(unet, ctrl) == g["num_att_layers"] == 32
+    gen = torch.Generator().manual_seed(case["seed"] + 77)
+    noises = [torch.randn(w["latents"].shape, generator=gen) for _ in range(case["S"])]
+    image, lat, attn = R.rollout(unet, w["vae"], sdm.DDPMScheduler(), w["prompt_embeds"], w["null_embeds"],
+                                 w["latents"].clone(), noises, case["S"], w["training_steps"], 7.5,
+                                 case.get("rescale", 0.0), w["attrcon_steps"], ctrl, return_latents=True)
+    assert sorted(attn.keys()) == g["timesteps"]
+    assert {k: len(v) for k, v in next(iter(attn.values())).items()} == g["keyset"]
+    assert rel(lat, g["latents"]) < 1e-4
+    assert rel(image.double().mean(), g["image_mean"]) < 1e-4
+
+
+@pytest.mark.needs_reference
+def test_reference_hook_captures_expected_keys_on_restated_unet():
+    """The reference's own register_attention_control must hook the restated UNet (SURVEY 8c checks 2-4)."""
+    from oracle import ref_shim
+    tca = ref_shim.import_reference("attn_utils.tc_attn_utils")
+    with torch.device("meta"):
+        u = sdm.UNet2DConditionModel(**sdm.SD15_UNET_CONFIG)
+        x = sdm.UNet2DConditionModel(**sdm.SDXL_UNET_CONFIG)
+    for m, n in ((u, 32), (x, 140)):
+        c = tca.AttentionStore(["mid_8", "up_16"])
+        tca.register_attention_control(m, c)
+        assert c.num_att_layers == n
