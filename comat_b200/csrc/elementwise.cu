@@ -1,0 +1,519 @@
+// HBM-bound normalisation / activation / rearrangement kernels of the UNet, VAE and BLIP paths (fwd + bwd).
+// All activations are 16-bit (fp16 or bf16) row-major [rows, C] (images are NHWC), statistics and math in fp32.
+// Base weights are frozen on this path (training_utils/pipeline.py:66-71), so no gamma/beta gradients are produced.
+#include "common.cuh"
+
+namespace comat {
+
+template <typename T>
+struct Vec8 {
+  uint4 u;
+  __device__ __forceinline__ void load(const T* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(T* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ __forceinline__ float get(int i) const { return to_f32<T>(reinterpret_cast<const T*>(&u)[i]); }
+  __device__ __forceinline__ void set(int i, float v) { reinterpret_cast<T*>(&u)[i] = from_f32<T>(v); }
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad(float x) {
+  const float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+// ============================================================================================== GroupNorm
+// x: (n, HW, C), G groups, cpg = C/G.  Pass 1: per-(n, chunk) partial sums of (a, b) per group, where
+//   stats  pass: a = x,          b = x^2
+//   bwd    pass: a = dy*gamma*act'(.), b = a * xhat
+// Pass 2 (apply) consumes the chunk-reduced sums.  Two passes => x is read twice (algorithmic minimum for a
+// normalisation whose statistics span the whole image) and written once.
+constexpr int GN_THREADS = 256;
+
+template <typename T, int MODE>   // MODE 0: stats of x ; MODE 1: backward sums
+__global__ void __launch_bounds__(512) gn_partial_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const float* __restrict__ mean_rstd, float* __restrict__ part,
+                                                                int HW, int C, int G, int chunks, int silu) {
+  extern __shared__ float sm[];   // [2*C]
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int vcols = C / 8;
+  const int rows_par = blockDim.x / vcols;
+  const int v = threadIdx.x % vcols, pr = threadIdx.x / vcols;
+  const int cpg = C / G;
+  const int p_begin = (int)((long long)HW * chunk / chunks), p_end = (int)((long long)HW * (chunk + 1) / chunks);
+  float sa[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sa[i] = sb[i] = 0.f;
+  if (pr < rows_par) {
+    float g8[8], b8[8], mu[8], rs[8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = v * 8 + i, gidx = c / cpg;
+        g8[i] = gamma[c]; b8[i] = beta[c];
+        mu[i] = mean_rstd[((size_t)n * G + gidx) * 2]; rs[i] = mean_rstd[((size_t)n * G + gidx) * 2 + 1];
+      }
+    }
+    for (int p = p_begin + pr; p < p_end; p += rows_par) {
+      const size_t off = ((size_t)n * HW + p) * C + v * 8;
+      Vec8<T> xv; xv.load(x + off);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float f = xv.get(i); sa[i] += f; sb[i] += f * f; }
+      } else {
+        Vec8<T> dv; dv.load(dy + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xv.get(i) - mu[i]) * rs[i];
+          float d = dv.get(i);
+          if (silu) d *= silu_grad(xh * g8[i] + b8[i]);
+          const float a = d * g8[i];
+          sa[i] += a; sb[i] += a * xh;
+        }
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  if (pr < rows_par) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(&sm[v * 8 + i], sa[i]); atomicAdd(&sm[C + v * 8 + i], sb[i]); }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sm[c]; b += sm[C + c]; }
+    float* o = part + (((size_t)n * chunks + chunk) * G + g) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+// reduce chunk partials -> (mean, rstd) [MODE 0] or (sum_a, sum_b) [MODE 1]
+__global__ void gn_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nG, int G, int chunks, float inv_cnt,
+                                 float eps, int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nG) return;
+  const int n = i / G, g = i % G;
+  float a = 0.f, b = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const float* p = part + (((size_t)n * chunks + c) * G + g) * 2;
+    a += p[0]; b += p[1];
+  }
+  if (mode == 0) {
+    const float mean = a * inv_cnt;
+    const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+    out[i * 2] = mean; out[i * 2 + 1] = rsqrtf(var + eps);
+  } else {
+    out[i * 2] = a * inv_cnt; out[i * 2 + 1] = b * inv_cnt;
+  }
+}
+
+template <typename T, int MODE>   // MODE 0: y = [silu](xhat*gamma+beta) ; MODE 1: dx
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ mean_rstd, const float* __restrict__ sums,
+                                                       long long total_vec, int HW, int C, int G, int silu) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int vcols = C / 8;
+  const int v = (int)(idx % vcols);
+  const long long row = idx / vcols;
+  const int n = (int)(row / HW);
+  const int cpg = C / G;
+  const size_t off = (size_t)row * C + v * 8;
+  Vec8<T> xv; xv.load(x + off);
+  Vec8<T> dv;
+  if (MODE == 1) dv.load(dy + off);
+  Vec8<T> o;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = v * 8 + i, g = c / cpg;
+    const float mu = mean_rstd[((size_t)n * G + g) * 2], rs = mean_rstd[((size_t)n * G + g) * 2 + 1];
+    const float xh = (xv.get(i) - mu) * rs;
+    if (MODE == 0) {
+      float y = xh * gamma[c] + beta[c];
+      if (silu) y = silu_f(y);
+      o.set(i, y);
+    } else {
+      float d = dv.get(i);
+      if (silu) d *= silu_grad(xh * gamma[c] + beta[c]);
+      const float a = d * gamma[c];
+      const float m1 = sums[((size_t)n * G + g) * 2], m2 = sums[((size_t)n * G + g) * 2 + 1];
+      o.set(i, rs * (a - m1 - xh * m2));
+    }
+  }
+  o.store(out + off);
+}
+
+// ============================================================================================== LayerNorm (one warp per row)
+template <typename T, int MODE>   // 0 fwd (saves mean,rstd) ; 1 bwd
+__global__ void __launch_bounds__(256) ln_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
+                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 float* __restrict__ mean_rstd, long long rows, int C, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int vcols = C / 8;
+  const T* xr = x + (size_t)row * C;
+  constexpr int MAXV = 8;   // up to C = 2048
+  Vec8<T> xv[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int v = lane + k * 32;
+    if (v < vcols) {
+      xv[k].load(xr + v * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += xv[k].get(i);
+    }
+  }
+  float mean, rstd;
+  if (MODE == 0) {
+    mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int v = lane + k * 32;
+      if (v < vcols) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = xv[k].get(i) - mean; q += d * d; }
+      }
+    }
+    rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (lane == 0) { mean_rstd[row * 2] = mean; mean_rstd[row * 2 + 1] = rstd; }
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int v = lane + k * 32;
+      if (v < vcols) {
+        Vec8<T> o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.set(i, (xv[k].get(i) - mean) * rstd * gamma[v * 8 + i] + beta[v * 8 + i]);
+        o.store(out + (size_t)row * C + v * 8);
+      }
+    }
+  } else {
+    mean = mean_rstd[row * 2]; rstd = mean_rstd[row * 2 + 1];
+    Vec8<T> dv[MAXV];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int v = lane + k * 32;
+      if (v < vcols) {
+        dv[k].load(dy + (size_t)row * C + v * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = dv[k].get(i) * gamma[v * 8 + i];
+          m1 += a; m2 += a * (xv[k].get(i) - mean) * rstd;
+        }
+      }
+    }
+    m1 = warp_sum(m1) / (float)C; m2 = warp_sum(m2) / (float)C;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int v = lane + k * 32;
+      if (v < vcols) {
+        Vec8<T> o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = dv[k].get(i) * gamma[v * 8 + i];
+          const float xh = (xv[k].get(i) - mean) * rstd;
+          o.set(i, rstd * (a - m1 - xh * m2));
+        }
+        o.store(out + (size_t)row * C + v * 8);
+      }
+    }
+  }
+}
+
+// ============================================================================================== GEGLU  (hidden * gelu(gate))
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ hg, const T* __restrict__ dy, T* __restrict__ out,
+                                                    long long rows, int Ch) {   // hg: [rows, 2*Ch] ; out fwd [rows,Ch], bwd [rows,2*Ch]
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vcols = Ch / 8;
+  if (idx >= rows * vcols) return;
+  const long long row = idx / vcols;
+  const int v = (int)(idx % vcols);
+  Vec8<T> h, g;
+  h.load(hg + (size_t)row * 2 * Ch + v * 8);
+  g.load(hg + (size_t)row * 2 * Ch + Ch + v * 8);
+  if (MODE == 0) {
+    Vec8<T> o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.set(i, h.get(i) * gelu_f(g.get(i)));
+    o.store(out + (size_t)row * Ch + v * 8);
+  } else {
+    Vec8<T> d, oh, og;
+    d.load(dy + (size_t)row * Ch + v * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gi = g.get(i), di = d.get(i);
+      oh.set(i, di * gelu_f(gi));
+      og.set(i, di * h.get(i) * gelu_grad(gi));
+    }
+    oh.store(out + (size_t)row * 2 * Ch + v * 8);
+    og.store(out + (size_t)row * 2 * Ch + Ch + v * 8);
+  }
+}
+
+// ============================================================================================== unary / binary elementwise
+// op: 0 silu  1 silu_bwd(x, dy)  2 gelu  3 gelu_bwd(x, dy)  4 add(x, y)  5 scale(x)*alpha  6 axpby: alpha*x + beta*y
+template <typename T>
+__global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, long long nvec,
+                                                 int op, float alpha, float beta) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nvec) return;
+  Vec8<T> a, b, o;
+  a.load(x + idx * 8);
+  if (y != nullptr) b.load(y + idx * 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float xa = a.get(i), yb = (y != nullptr) ? b.get(i) : 0.f;
+    float r;
+    switch (op) {
+      case 0: r = silu_f(xa); break;
+      case 1: r = yb * silu_grad(xa); break;
+      case 2: r = gelu_f(xa); break;
+      case 3: r = yb * gelu_grad(xa); break;
+      case 4: r = xa + yb; break;
+      case 5: r = xa * alpha; break;
+      default: r = alpha * xa + beta * yb; break;
+    }
+    o.set(i, r);
+  }
+  o.store(out + idx * 8);
+}
+
+// ============================================================================================== spatial rearrangements (NHWC)
+// mode 0: nearest x2 upsample fwd (n,H,W,C)->(n,2H,2W,C)     mode 1: its backward (sum of the 2x2 block)
+// mode 2: space-to-depth (n,H,W,C)->(n,H/2,W/2,4C), channel block order (dy,dx)   mode 3: depth-to-space (inverse)
+template <typename T>
+__global__ void __launch_bounds__(256) spatial_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int H, int W, int C, int mode) {
+  // H, W are the dims of the *smaller* tensor for modes 0/1 and of the *larger* tensor for modes 2/3
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vcols = C / 8;
+  if (mode == 0 || mode == 1) {
+    if (mode == 0) {
+      const long long total = (long long)n * 2 * H * 2 * W * vcols;
+      if (idx >= total) return;
+      const int v = (int)(idx % vcols);
+      long long r = idx / vcols;
+      const int x = (int)(r % (2 * W)); r /= 2 * W;
+      const int y = (int)(r % (2 * H));
+      const int b = (int)(r / (2 * H));
+      Vec8<T> t; t.load(in + (((size_t)b * H + y / 2) * W + x / 2) * C + v * 8);
+      t.store(out + (((size_t)b * 2 * H + y) * 2 * W + x) * C + v * 8);
+    } else {
+      const long long total = (long long)n * H * W * vcols;
+      if (idx >= total) return;
+      const int v = (int)(idx % vcols);
+      long long r = idx / vcols;
+      const int x = (int)(r % W); r /= W;
+      const int y = (int)(r % H);
+      const int b = (int)(r / H);
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          Vec8<T> t; t.load(in + (((size_t)b * 2 * H + 2 * y + dy) * 2 * W + 2 * x + dx) * C + v * 8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += t.get(i);
+        }
+      Vec8<T> o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.set(i, acc[i]);
+      o.store(out + (((size_t)b * H + y) * W + x) * C + v * 8);
+    }
+  } else {
+    const long long total = (long long)n * H * W * vcols;
+    if (idx >= total) return;
+    const int v = (int)(idx % vcols);
+    long long r = idx / vcols;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    const size_t big = (((size_t)b * H + y) * W + x) * C + v * 8;
+    const size_t small = (((size_t)b * (H / 2) + y / 2) * (W / 2) + x / 2) * (4 * C) + ((y & 1) * 2 + (x & 1)) * C + v * 8;
+    Vec8<T> t;
+    if (mode == 2) { t.load(in + big); t.store(out + small); }
+    else           { t.load(in + small); t.store(out + big); }
+  }
+}
+
+// 16-bit matrix transpose [R, Cc] -> [Cc, R] (LoRA wgrad operands), 32x32 tiles through padded smem
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int Cc, int ld_out) {
+  __shared__ T tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = by + j, c = bx + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = in[(size_t)r * Cc + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = bx + j, r = by + threadIdx.x;
+    if (r < R && c < Cc) out[(size_t)c * ld_out + r] = tile[threadIdx.x][j];
+  }
+}
+
+// fp32 <-> 16-bit casts with layout change for the 4-channel latents: NCHW fp32 -> NHWC 16-bit padded to Cpad channels
+template <typename T>
+__global__ void latent_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int n, int Cin, int HW, int Cpad, float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * HW * Cpad) return;
+  const int c = (int)(idx % Cpad);
+  const long long r = idx / Cpad;
+  const int p = (int)(r % HW), b = (int)(r / HW);
+  out[idx] = from_f32<T>(c < Cin ? in[((size_t)b * Cin + c) * HW + p] * scale : 0.f);
+}
+// NHWC 16-bit (first Cout of ld channels) -> NCHW fp32
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int n, int Cout, int HW, int ld, float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * Cout * HW) return;
+  const int p = (int)(idx % HW);
+  const long long r = idx / HW;
+  const int c = (int)(r % Cout), b = (int)(r / Cout);
+  out[idx] = to_f32<T>(in[((size_t)b * HW + p) * ld + c]) * scale;
+}
+
+// strided 2-D copy of 16-bit rows: dst[r, 0:cols] = src[r, 0:cols]  (torch.cat([hidden, skip], dim=1) in NHWC)
+__global__ void __launch_bounds__(256) copy2d_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long rows, int vcols,
+                                                     long long ld_src_v, long long ld_dst_v) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * vcols) return;
+  const long long r = idx / vcols;
+  const int v = (int)(idx % vcols);
+  dst[r * ld_dst_v + v] = src[r * ld_src_v + v];
+}
+
+}  // namespace comat
+
+using namespace comat;
+
+#define DISPATCH_T(dtype, ...)                                       \
+  if ((dtype) == COMAT_F16) { using T = __half; __VA_ARGS__; }       \
+  else if ((dtype) == COMAT_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+  else return COMAT_ERR_UNSUPPORTED;
+
+static inline int gn_threads(int C) { int v = C / 8; return v <= 256 ? 256 : ((v + 31) / 32) * 32; }
+static inline int gn_chunks(int n, int HW) {
+  int c = (2 * num_sms() + n - 1) / n;
+  if (c > HW / 16) c = HW / 16;
+  return c < 1 ? 1 : c;
+}
+
+extern "C" size_t comat_groupnorm_workspace_floats(int n, int HW, int G) { return (size_t)n * gn_chunks(n, HW) * G * 2 + (size_t)n * G * 2; }
+
+extern "C" int comat_groupnorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, float* ws,
+                                   int n, int HW, int C, int G, float eps, int silu, int dtype, void* stream) {
+  if (!x || !y || !gamma || !beta || !mean_rstd || !ws || C % 8 || C % G || C / 8 > 512) return COMAT_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = gn_chunks(n, HW);
+  const long long nvec = (long long)n * HW * (C / 8);
+  DISPATCH_T(dtype, {
+    gn_partial_kernel<T, 0><<<dim3(chunks, n), gn_threads(C), 2 * C * sizeof(float), st>>>((const T*)x, nullptr, gamma, beta, nullptr, ws, HW, C, G, chunks, 0);
+    gn_reduce_kernel<<<(n * G + 127) / 128, 128, 0, st>>>(ws, mean_rstd, n * G, G, chunks, 1.f / ((float)HW * (C / G)), eps, 0);
+    gn_apply_kernel<T, 0><<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, nullptr, nvec, HW, C, G, silu);
+  });
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+extern "C" int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* beta,
+                                   const float* mean_rstd, float* ws, int n, int HW, int C, int G, int silu, int dtype, void* stream) {
+  if (!x || !dy || !dx || !gamma || !beta || !mean_rstd || !ws || C % 8 || C % G || C / 8 > 512) return COMAT_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = gn_chunks(n, HW);
+  float* sums = ws + (size_t)n * chunks * G * 2;
+  const long long nvec = (long long)n * HW * (C / 8);
+  DISPATCH_T(dtype, {
+    gn_partial_kernel<T, 1><<<dim3(chunks, n), gn_threads(C), 2 * C * sizeof(float), st>>>((const T*)x, (const T*)dy, gamma, beta, mean_rstd, ws, HW, C, G, chunks, silu);
+    gn_reduce_kernel<<<(n * G + 127) / 128, 128, 0, st>>>(ws, sums, n * G, G, chunks, 1.f / ((float)HW * (C / G)), 0.f, 1);
+    gn_apply_kernel<T, 1><<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)dx, gamma, beta, mean_rstd, sums, nvec, HW, C, G, silu);
+  });
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+extern "C" int comat_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, long long rows,
+                                   int C, float eps, int dtype, void* stream) {
+  if (!x || !y || !gamma || !beta || !mean_rstd || C % 8 || C > 2048) return COMAT_ERR_INVALID;
+  DISPATCH_T(dtype, (ln_kernel<T, 0><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, rows, C, eps)));
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+extern "C" int comat_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* mean_rstd, long long rows,
+                                   int C, int dtype, void* stream) {
+  if (!x || !dy || !dx || !gamma || !mean_rstd || C % 8 || C > 2048) return COMAT_ERR_INVALID;
+  DISPATCH_T(dtype, (ln_kernel<T, 1><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, (T*)dx, gamma, nullptr, const_cast<float*>(mean_rstd), rows, C, 0.f)));
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+extern "C" int comat_geglu_fwd(const void* hg, void* out, long long rows, int Ch, int dtype, void* stream) {
+  if (!hg || !out || Ch % 8) return COMAT_ERR_INVALID;
+  const long long nv = rows * (Ch / 8);
+  DISPATCH_T(dtype, (geglu_kernel<T, 0><<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)hg, nullptr, (T*)out, rows, Ch)));
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+extern "C" int comat_geglu_bwd(const void* hg, const void* dy, void* dhg, long long rows, int Ch, int dtype, void* stream) {
+  if (!hg || !dy || !dhg || Ch % 8) return COMAT_ERR_INVALID;
+  const long long nv = rows * (Ch / 8);
+  DISPATCH_T(dtype, (geglu_kernel<T, 1><<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)hg, (const T*)dy, (T*)dhg, rows, Ch)));
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+extern "C" int comat_elementwise(const void* x, const void* y, void* out, long long numel, int op, float alpha, float beta, int dtype,
+                                 void* stream) {
+  if (!x || !out || numel % 8) return COMAT_ERR_INVALID;
+  const long long nv = numel / 8;
+  DISPATCH_T(dtype, (ew_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)y, (T*)out, nv, op, alpha, beta)));
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+extern "C" int comat_spatial(const void* in, void* out, int n, int H, int W, int C, int mode, int dtype, void* stream) {
+  if (!in || !out || C % 8 || mode < 0 || mode > 3) return COMAT_ERR_INVALID;
+  if ((mode >= 2) && ((H | W) & 1)) return COMAT_ERR_INVALID;
+  const long long total = (long long)n * H * W * (C / 8) * (mode == 0 ? 4 : 1);
+  DISPATCH_T(dtype, (spatial_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, (T*)out, n, H, W, C, mode)));
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+extern "C" int comat_transpose16(const void* in, void* out, int R, int Cc, int ld_out, void* stream) {
+  if (!in || !out || ld_out < R) return COMAT_ERR_INVALID;
+  transpose_kernel<__half><<<dim3((Cc + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, R, Cc, ld_out);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+extern "C" int comat_latent_to_nhwc(const float* in, void* out, int n, int Cin, int HW, int Cpad, float scale, int dtype, void* stream) {
+  if (!in || !out) return COMAT_ERR_INVALID;
+  const long long total = (long long)n * HW * Cpad;
+  DISPATCH_T(dtype, (latent_to_nhwc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (T*)out, n, Cin, HW, Cpad, scale)));
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+extern "C" int comat_nhwc_to_nchw_f32(const void* in, float* out, int n, int Cout, int HW, int ld, float scale, int dtype, void* stream) {
+  if (!in || !out) return COMAT_ERR_INVALID;
+  const long long total = (long long)n * Cout * HW;
+  DISPATCH_T(dtype, (nhwc_to_nchw_f32_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, out, n, Cout, HW, ld, scale)));
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+extern "C" int comat_copy2d16(const void* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst, void* stream) {
+  if (!src || !dst || cols % 8 || ld_src % 8 || ld_dst % 8 || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return COMAT_ERR_INVALID;
+  const long long nv = rows * (cols / 8);
+  copy2d_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, rows, cols / 8, ld_src / 8, ld_dst / 8);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}

@@ -1,0 +1,366 @@
+// Tensor-core GEMM / implicit-GEMM convolution for the UNet / VAE / BLIP hot path  (tcgen05 + TMEM + TMA).
+//
+//   out[m, n] = act(alpha * sum_k A[m, k] * B[n, k] + bias[n] + rowvec[m / rows_per_group, n]) + residual[m, n]
+//
+// replaces the cuBLAS / cuDNN calls behind diffusers' Linear / Conv2d / LoRACompatibleLinear modules
+// (ResBlock conv3x3, proj_in/out, attention projections + LoRA, GEGLU feed-forward, BLIP linears).
+//
+// * A is K-major 16-bit.  "plain" mode: a [M, K] matrix.  "conv" mode: an NHWC activation tensor read through a 4-D
+//   TMA tensor map — one (tap, 64-channel) slab per k-block at spatial offset (dh, dw); out-of-bounds rows are
+//   zero-filled by the TMA unit, which *is* the convolution's zero padding, so no im2col buffer ever exists.
+// * Up to two K-segments accumulate into the same TMEM accumulator: [x | x*down^T] against [W | up] fuses the LoRA
+//   branch (training_utils/pipeline.py:94-115) into the projection, and [hidden | skip] fuses the UNet's
+//   torch.cat([hidden, skip], dim=1) into the ResBlock's first convolution.
+// * B is the weight, [N, K_total] K-major (for conv: k = tap * c_total + channel).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2-5 = epilogue (tcgen05.ld -> registers -> fused bias / time-embedding / activation / residual -> global).
+// One 128 x BN output tile per CTA, 3-stage smem ring; two CTAs fit per SM so one CTA's epilogue overlaps the
+// other's main loop.
+#include "tc_common.cuh"
+
+namespace comat {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 x 16-bit = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+
+struct GemmKP {
+  int M, N;
+  int n_seg, seg_kblocks[2], seg_bkoff[2];
+  int conv, H, W, n_img, TW, TH, TN, tiles_w, tiles_h, n_taps, c_total;
+  int dh[9], dw[9];
+  float alpha;
+  const float* bias;
+  const float* rowvec;
+  int rows_per_group, act;
+  const void* residual;
+  long long res_ld;
+  void* out16;
+  long long out_ld;
+  float* out32;
+  long long out32_ld;
+  uint32_t idesc;
+  int is_bf16;
+};
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == 1) return x / (1.f + __expf(-x));                       // SiLU
+  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));  // exact GELU (F.gelu default)
+  return x;
+}
+
+template <int BN>
+constexpr int tmem_cols() { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512; }
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TILES = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = TILES;                       // full[STAGES], empty[STAGES], tmem_full
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
+  static constexpr int BIAS_OFF = TMEMPTR_OFF + 8;
+  static constexpr int TOTAL = BIAS_OFF + BN * 4 + 1024;      // +1024: manual alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmKP p) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::TMEMPTR_OFF);
+  float* s_bias = reinterpret_cast<float*>(smem + S::BIAS_OFF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int n0 = tile_n * BN;
+  const int kb_per_tap = p.seg_kblocks[0] + (p.n_seg > 1 ? p.seg_kblocks[1] : 0);
+  const int num_kb = p.n_taps * kb_per_tap;
+
+  // tile origin
+  int m0 = tile_m * BM, img0 = 0, h0 = 0, w0 = 0;
+  if (p.conv) {
+    const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
+    w0 = tw * p.TW; h0 = th * p.TH; img0 = tn * p.TN;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.n_seg > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, tmem_cols<BN>());
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += GEMM_THREADS - 64)
+      s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tap = 0; tap < p.n_taps; ++tap) {
+        for (int sg = 0; sg < p.n_seg; ++sg) {
+          const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
+          const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
+          const int nkb = p.seg_kblocks[sg];
+          for (int cb = 0; cb < nkb; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            unsigned char* sa = smem + stage * S::STAGE_BYTES;
+            unsigned char* sb = sa + S::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            if (p.conv) tma_load_4d(sa, mA, &full_bar[stage], cb * BK, w0 + p.dw[tap], h0 + p.dh[tap], img0);
+            else        tma_load_2d(sa, mA, &full_bar[stage], cb * BK, m0);
+            tma_load_2d(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+        const uint32_t sb = sa + S::A_BYTES;
+        const uint64_t da = make_kmajor_sw128_desc(sa);
+        const uint64_t db = make_kmajor_sw128_desc(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the (addr>>4) field
+          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);          // frees this smem stage when the MMAs above have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);                    // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // row inside the tile
+    long long m;                                 // global output row
+    bool row_ok;
+    if (p.conv) {
+      const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
+      const int n_i = img0 + tn, hh = h0 + th, ww = w0 + tw;
+      row_ok = (n_i < p.n_img) && (hh < p.H) && (ww < p.W);
+      m = ((long long)n_i * p.H + hh) * p.W + ww;
+    } else {
+      m = (long long)m0 + r;
+      row_ok = m < p.M;
+    }
+    const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * (long long)p.N : nullptr;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        const int ncol = min(32, p.N - (n0 + c0));
+        if (ncol > 0) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) * p.alpha + s_bias[c0 + j];
+            if (rv != nullptr && j < ncol) x += rv[n0 + c0 + j];
+            f[j] = act_apply(x, p.act);
+          }
+          if (p.residual != nullptr) {
+            const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
+            if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rp + j4 * 8);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (p.is_bf16) {
+                    f[j4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
+                    f[j4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                  } else {
+                    const __half2 h2 = *reinterpret_cast<const __half2*>(&w[e]);
+                    f[j4 * 8 + e * 2 + 0] += __low2float(h2);
+                    f[j4 * 8 + e * 2 + 1] += __high2float(h2);
+                  }
+                }
+              }
+            } else {
+              for (int j = 0; j < ncol; ++j) {
+                const uint16_t b = rp[j];
+                f[j] += p.is_bf16 ? __uint_as_float((uint32_t)b << 16) : __half2float(*reinterpret_cast<const __half*>(&b));
+              }
+            }
+          }
+          if (p.out16 != nullptr) {
+            uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n0 + c0;
+            if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = f[j4 * 8 + e * 2], b = f[j4 * 8 + e * 2 + 1];
+                  if (p.is_bf16) {
+                    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+                    w[e] = *reinterpret_cast<const uint32_t*>(&t);
+                  } else {
+                    const __half2 t = __floats2half2_rn(a, b);
+                    w[e] = *reinterpret_cast<const uint32_t*>(&t);
+                  }
+                }
+                *reinterpret_cast<uint4*>(op + j4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            } else {
+              for (int j = 0; j < ncol; ++j) {
+                if (p.is_bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(f[j]); op[j] = *reinterpret_cast<const uint16_t*>(&t); }
+                else           { const __half t = __float2half_rn(f[j]);           op[j] = *reinterpret_cast<const uint16_t*>(&t); }
+              }
+            }
+          }
+          if (p.out32 != nullptr) {
+            float* op = p.out32 + m * p.out32_ld + n0 + c0;
+            for (int j = 0; j < ncol; ++j) op[j] = f[j];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols<BN>());
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap* maps, const GemmKP& kp, dim3 grid, cudaStream_t st) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+}  // namespace comat
+
+using namespace comat;
+
+static int pick_bn(int N, int forced) {
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 160 || forced == 256) return forced;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0 || N > 1024) return 128;
+  if (N % 64 == 0 && N < 128) return 64;
+  return (N % 160) > (N % 128) || (N % 128 == 0) ? 128 : 160;
+}
+
+extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
+  if (!g || g->M <= 0 || g->N <= 0 || g->n_seg < 1 || g->n_seg > 2) return COMAT_ERR_INVALID;
+  if (g->dtype != COMAT_F16 && g->dtype != COMAT_BF16) return COMAT_ERR_UNSUPPORTED;
+  if (!g->out16 && !g->out32) return COMAT_ERR_INVALID;
+  GemmKP kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.M = g->M; kp.N = g->N; kp.n_seg = g->n_seg;
+  kp.alpha = g->alpha; kp.bias = g->bias; kp.rowvec = g->rowvec; kp.rows_per_group = g->rows_per_group > 0 ? g->rows_per_group : 1;
+  kp.act = g->act; kp.residual = g->residual; kp.res_ld = g->res_ld; kp.out16 = g->out16; kp.out_ld = g->out_ld;
+  kp.out32 = g->out32; kp.out32_ld = g->out32_ld; kp.is_bf16 = g->dtype == COMAT_BF16;
+  const int BN = pick_bn(g->N, g->force_bn);
+  kp.idesc = make_idesc_f16(BM, BN, kp.is_bf16 ? 1 : 0);
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  dim3 grid;
+  kp.conv = g->conv ? 1 : 0;
+  if (kp.conv) {
+    if (g->n_taps < 1 || g->n_taps > 9 || g->H <= 0 || g->W <= 0 || g->n_img <= 0) return COMAT_ERR_INVALID;
+    if ((long long)g->n_img * g->H * g->W != g->M) return COMAT_ERR_INVALID;
+    kp.H = g->H; kp.W = g->W; kp.n_img = g->n_img; kp.n_taps = g->n_taps; kp.c_total = g->c_total;
+    for (int t = 0; t < g->n_taps; ++t) { kp.dh[t] = g->tap_dh[t]; kp.dw[t] = g->tap_dw[t]; }
+    // spatial tile: 128 output pixels = TW x TH x TN
+    int TW = 1;
+    while (TW < g->W && TW < 128) TW <<= 1;            // power of two >= W, capped at 128
+    if (TW > 128) TW = 128;
+    int TH = 128 / TW, TN = 1;
+    if (TH > g->H) {                                   // small maps: several images per tile
+      int th = 1;
+      while (th < g->H) th <<= 1;
+      TH = th < 128 / TW ? th : 128 / TW;
+      TN = 128 / (TW * TH);
+    }
+    kp.TW = TW; kp.TH = TH; kp.TN = TN;
+    kp.tiles_w = (g->W + TW - 1) / TW; kp.tiles_h = (g->H + TH - 1) / TH;
+    const int tiles_n = (g->n_img + TN - 1) / TN;
+    grid = dim3(kp.tiles_w * kp.tiles_h * tiles_n, (g->N + BN - 1) / BN, 1);
+  } else {
+    kp.n_taps = 1; kp.c_total = 0;
+    grid = dim3((g->M + BM - 1) / BM, (g->N + BN - 1) / BN, 1);
+  }
+  for (int s = 0; s < g->n_seg; ++s) {
+    const int K = g->a_k[s];
+    if (K <= 0 || (K % 8) != 0 || !g->a[s] || !g->b[s]) return COMAT_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(g->a[s]) & 15) || (reinterpret_cast<uintptr_t>(g->b[s]) & 15)) return COMAT_ERR_INVALID;
+    if (kp.conv && (K % BK) != 0) return COMAT_ERR_UNSUPPORTED;   // channel slabs of 64
+    kp.seg_kblocks[s] = (K + BK - 1) / BK;
+    kp.seg_bkoff[s] = g->b_koff[s];
+    if (kp.conv) {
+      const uint64_t dims[4] = {(uint64_t)K, (uint64_t)g->W, (uint64_t)g->H, (uint64_t)g->n_img};
+      const uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)K * 2 * g->W, (uint64_t)K * 2 * g->W * g->H};
+      const uint32_t box[4] = {(uint32_t)BK, (uint32_t)kp.TW, (uint32_t)kp.TH, (uint32_t)kp.TN};
+      if (!make_tmap_16bit(&maps[s], g->a[s], 4, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    } else {
+      if ((g->a_ld[s] % 8) != 0) return COMAT_ERR_INVALID;
+      const uint64_t dims[2] = {(uint64_t)K, (uint64_t)g->M};
+      const uint64_t str[1] = {(uint64_t)g->a_ld[s] * 2};
+      const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+      if (!make_tmap_16bit(&maps[s], g->a[s], 2, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    }
+    {
+      if ((g->b_ld[s] % 8) != 0) return COMAT_ERR_INVALID;
+      const uint64_t kext = kp.conv ? (uint64_t)g->n_taps * g->c_total : (uint64_t)g->b_koff[s] + K;
+      const uint64_t dims[2] = {kext, (uint64_t)g->N};
+      const uint64_t str[1] = {(uint64_t)g->b_ld[s] * 2};
+      const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+      if (!make_tmap_16bit(&maps[2 + s], g->b[s], 2, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 32:  return launch_gemm<32, 4>(maps, kp, grid, st);
+    case 64:  return launch_gemm<64, 4>(maps, kp, grid, st);
+    case 128: return launch_gemm<128, 3>(maps, kp, grid, st);
+    case 160: return launch_gemm<160, 3>(maps, kp, grid, st);
+    case 256: return launch_gemm<256, 4>(maps, kp, grid, st);
+  }
+  return COMAT_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,553 @@
+"""Explicit forward/backward executor for the UNet / VAE-decoder hot path.
+
+No autograd tape inside the networks: every op launches hand-written kernels through the C ABI (comat_b200.ops) and,
+when a ``Tape`` is active, records a closure that launches the matching backward kernels.  The executor is plain
+Python issuing launches on the current stream, so a whole forward (and a whole backward) can be captured in a CUDA
+graph and replayed (engine.GraphedUNet) — CUDA graphs instead of a tracing compiler.
+
+Layout: activations are 16-bit NHWC ``(n, H, W, C)`` / token-major ``(n, L, C)``; statistics, softmax, losses and
+the latent chain are fp32.  Base weights are frozen (training_utils/pipeline.py:66-71): only data gradients and the
+LoRA A/B weight gradients (training_utils/pipeline.py:94-115, 123-143) are produced.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import attention as attn_ops
+from . import ops
+from . import unet_weights as UW
+
+
+class Var:
+    """value + accumulated gradient"""
+    __slots__ = ("v", "g", "needs_grad")
+
+    def __init__(self, v, needs_grad=True):
+        self.v, self.g, self.needs_grad = v, None, needs_grad
+
+
+class Tape:
+    def __init__(self):
+        self.ops = []
+
+    def record(self, fn):
+        self.ops.append(fn)
+
+    def backward(self):
+        for fn in reversed(self.ops):
+            fn()
+        self.ops = []
+
+
+def _acc(var: Var, g: torch.Tensor):
+    if not var.needs_grad:
+        return
+    var.g = g if var.g is None else ops.elementwise("add", var.g, g)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parameter containers
+# ------------------------------------------------------------------------------------------------------------
+class ConvW:
+    def __init__(self, conv: torch.nn.Conv2d, dtype, cin_pad: int = 0):
+        w = conv.weight.detach()
+        self.cout, self.cin = w.shape[0], w.shape[1]
+        self.k = w.shape[2]
+        self.stride = conv.stride[0]
+        self.bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+        self.cin_pad = cin_pad or self.cin
+        if self.k == 1:
+            self.w_f, self.taps_f = UW.to16(w.reshape(self.cout, self.cin), dtype), None
+            self.w_d = UW.to16(w.reshape(self.cout, self.cin).t(), dtype)
+            self.taps_d = None
+        elif self.stride == 1:
+            self.w_f, self.taps_f = UW.to16(UW.pack_conv3x3(w, self.cin_pad), dtype), UW.TAPS_3x3
+            wd = UW.pack_conv3x3_dgrad(w, UW.pad_channels(self.cout))
+            if self.cin_pad != self.cin:                      # padded input channels get (zero) gradient rows
+                wd = torch.cat([wd, wd.new_zeros(self.cin_pad - self.cin, wd.shape[1])], 0)
+            self.w_d, self.taps_d = UW.to16(wd, dtype), UW.TAPS_3x3
+        else:
+            wf, tf = UW.pack_conv_stride2(w)
+            wd, td = UW.pack_conv_stride2_dgrad(w)
+            self.w_f, self.taps_f, self.w_d, self.taps_d = UW.to16(wf, dtype), tf, UW.to16(wd, dtype), td
+
+
+class LinW:
+    def __init__(self, lin: torch.nn.Linear, dtype):
+        w = lin.weight.detach()
+        self.n, self.k = w.shape
+        self.w = UW.to16(w, dtype)               # [N, K]
+        self.wt = UW.to16(w.t(), dtype)          # [K, N]  (dgrad operand)
+        self.bias = lin.bias.detach().float().contiguous() if lin.bias is not None else None
+
+
+class LoRAW:
+    """fp32 master parameters (trainable) + per-step 16-bit operand copies.  y = W x + up(down(x))."""
+
+    def __init__(self, lora, dtype):
+        self.down = lora.down.weight        # (r, K) fp32 nn.Parameter
+        self.up = lora.up.weight            # (N, r) fp32 nn.Parameter
+        self.rank = self.down.shape[0]
+        self.dtype = dtype
+        self.g_down = None
+        self.g_up = None
+        self.refresh()
+
+    def refresh(self):
+        d, u = self.down.detach(), self.up.detach()
+        self.down16, self.up16 = d.to(self.dtype).contiguous(), u.to(self.dtype).contiguous()
+        self.down16_t, self.up16_t = d.t().to(self.dtype).contiguous(), u.t().to(self.dtype).contiguous()
+
+
+class NormW:
+    def __init__(self, m, groups=None):
+        self.gamma = m.weight.detach().float().contiguous()
+        self.beta = m.bias.detach().float().contiguous()
+        self.eps = m.eps
+        self.groups = groups
+
+
+# ------------------------------------------------------------------------------------------------------------
+# ops (forward + recorded backward)
+# ------------------------------------------------------------------------------------------------------------
+def conv(tape: Optional[Tape], xs: Sequence[Var], cw: ConvW, rowvec: Optional[torch.Tensor] = None,
+         residual: Optional[Var] = None) -> Var:
+    """conv3x3 (stride 1 or 2) / conv1x1 over one or two channel segments (torch.cat fused away), fused
+    + bias + per-sample time-embedding row vector + residual.  NHWC in/out."""
+    n, H, W = xs[0].v.shape[:3]
+    chans = [x.v.shape[-1] for x in xs]
+    koffs = [0, chans[0]] if len(xs) == 2 else [0]
+    res = residual.v if residual is not None else None
+    if cw.k == 1:
+        y = ops.gemm([x.v.reshape(n * H * W, c) for x, c in zip(xs, chans)], [cw.w_f] * len(xs), b_koff=koffs + [0],
+                     bias=cw.bias, rowvec=rowvec, rows_per_group=H * W, residual=res).reshape(n, H, W, cw.cout)
+    elif cw.stride == 1:
+        y = ops.gemm([x.v for x in xs], [cw.w_f] * len(xs), b_koff=koffs + [0], bias=cw.bias, rowvec=rowvec,
+                     rows_per_group=H * W, residual=res, conv_taps=cw.taps_f, c_total=sum(chans) if len(xs) == 2 else cw.cin_pad)
+    else:
+        xs2d = ops.spatial(xs[0].v, "s2d")
+        y = ops.gemm([xs2d], [cw.w_f], bias=cw.bias, conv_taps=cw.taps_f)
+    out = Var(y)
+    if tape is not None:
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            if residual is not None:
+                _acc(residual, dy)
+            if cw.k == 1:
+                dy2 = dy.reshape(-1, cw.cout)
+                off = 0
+                for x, c in zip(xs, chans):
+                    if x.needs_grad:
+                        g = ops.gemm([dy2], [cw.w_d[off:off + c]], residual=x.g.reshape(-1, c) if x.g is not None else None)
+                        x.g = g.reshape(x.v.shape)
+                    off += c
+            elif cw.stride == 1:
+                cop = UW.pad_channels(cw.cout)
+                dyp = dy if cop == cw.cout else torch.nn.functional.pad(dy, (0, cop - cw.cout))   # conv_out only (4 -> 64)
+                off = 0
+                for x, c in zip(xs, chans):
+                    if x.needs_grad:
+                        x.g = ops.gemm([dyp], [cw.w_d[off:off + c]], conv_taps=cw.taps_d, c_total=cop, residual=x.g)
+                    off += c
+            else:
+                if xs[0].needs_grad:
+                    g = ops.spatial(ops.gemm([dy], [cw.w_d], conv_taps=cw.taps_d), "d2s")
+                    _acc(xs[0], g)
+        tape.record(bwd)
+    return out
+
+
+def linear(tape, x: Var, lw: LinW, lora: Optional[LoRAW] = None, residual: Optional[Var] = None) -> Var:
+    """y = x W^T (+ (x down^T) up^T) + b (+ residual); token-major (.., K) -> (.., N)."""
+    xv = x.v
+    x2 = xv.reshape(-1, lw.k)
+    res = residual.v.reshape(-1, lw.n) if residual is not None else None
+    if lora is not None:
+        t = ops.gemm([x2], [lora.down16])
+        y = ops.gemm([x2, t], [lw.w, lora.up16], bias=lw.bias, residual=res)
+    else:
+        t = None
+        y = ops.gemm([x2], [lw.w], bias=lw.bias, residual=res)
+    out = Var(y.reshape(*xv.shape[:-1], lw.n))
+    if tape is not None:
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            dy2 = dy.reshape(-1, lw.n)
+            if residual is not None:
+                _acc(residual, dy)
+            if lora is not None:
+                u = ops.gemm([dy2], [lora.up16_t])                                   # dy . up      (M, r)
+                dyT, tT = ops.transpose16(dy2, 8), ops.transpose16(t, 8)
+                gu = ops.gemm([dyT], [tT], out_fp32=True)                            # d up   = dy^T t  (N, r)
+                uT, xT = ops.transpose16(u, 8), ops.transpose16(x2, 8)
+                gd = ops.gemm([uT], [xT], out_fp32=True)                             # d down = u^T x   (r, K)
+                lora.g_up = gu if lora.g_up is None else lora.g_up + gu
+                lora.g_down = gd if lora.g_down is None else lora.g_down + gd
+                if x.needs_grad:
+                    g = ops.gemm([dy2, u], [lw.wt, lora.down16_t], residual=x.g.reshape(-1, lw.k) if x.g is not None else None)
+                    x.g = g.reshape(xv.shape)
+            elif x.needs_grad:
+                g = ops.gemm([dy2], [lw.wt], residual=x.g.reshape(-1, lw.k) if x.g is not None else None)
+                x.g = g.reshape(xv.shape)
+        tape.record(bwd)
+    return out
+
+
+def groupnorm(tape, x: Var, nw: NormW, silu: bool) -> Var:
+    y, mr = ops.groupnorm_fwd(x.v, nw.gamma, nw.beta, nw.groups, nw.eps, silu)
+    out = Var(y)
+    if tape is not None:
+        def bwd():
+            if out.g is not None and x.needs_grad:
+                _acc(x, ops.groupnorm_bwd(x.v, out.g, nw.gamma, nw.beta, mr, nw.groups, silu))
+        tape.record(bwd)
+    return out
+
+
+def layernorm(tape, x: Var, nw: NormW) -> Var:
+    y, mr = ops.layernorm_fwd(x.v, nw.gamma, nw.beta, nw.eps)
+    out = Var(y)
+    if tape is not None:
+        def bwd():
+            if out.g is not None and x.needs_grad:
+                _acc(x, ops.layernorm_bwd(x.v, out.g, nw.gamma, mr))
+        tape.record(bwd)
+    return out
+
+
+def geglu(tape, hg: Var) -> Var:
+    out = Var(ops.geglu_fwd(hg.v))
+    if tape is not None:
+        def bwd():
+            if out.g is not None:
+                _acc(hg, ops.geglu_bwd(hg.v, out.g))
+        tape.record(bwd)
+    return out
+
+
+def upsample2x(tape, x: Var) -> Var:
+    out = Var(ops.spatial(x.v, "up2"))
+    if tape is not None:
+        def bwd():
+            if out.g is not None and x.needs_grad:
+                _acc(x, ops.spatial(out.g, "up2_bwd"))
+        tape.record(bwd)
+    return out
+
+
+def concat(tape, a: Var, b: Var) -> Var:
+    ca, cb = a.v.shape[-1], b.v.shape[-1]
+    out = Var(ops.concat_channels(a.v, b.v))
+    if tape is not None:
+        def bwd():
+            if out.g is None:
+                return
+            g = out.g
+            if a.needs_grad:
+                _acc(a, g[..., :ca].contiguous())
+            if b.needs_grad:
+                _acc(b, g[..., ca:].contiguous())
+        tape.record(bwd)
+    return out
+
+
+def attention(tape, q: Var, k: Var, v: Var, heads: int, export_probs: bool = False):
+    """softmax(scale q k^T) v per head; optionally exports the fp32 probabilities (n*heads, Lq, Lk) as a Var whose
+    gradient (from the attention-map loss) is added into the softmax backward (SURVEY 'hard parts')."""
+    o, probs, saved = attn_ops.attention_fwd(q.v, k.v, v.v, heads, export_probs, need_bwd=tape is not None)
+    out = Var(o)
+    pvar = Var(probs) if export_probs else None
+    if tape is not None:
+        def bwd():
+            if out.g is None and (pvar is None or pvar.g is None):
+                return
+            dq, dk, dv = attn_ops.attention_bwd(saved, out.g, pvar.g if pvar is not None else None)
+            _acc(q, dq)
+            _acc(k, dk)
+            _acc(v, dv)
+        tape.record(bwd)
+    return out, pvar
+
+
+# ------------------------------------------------------------------------------------------------------------
+# network executors built from diffusers-shaped modules (state-dict compatible with oracle/sd_modules.py or diffusers)
+# ------------------------------------------------------------------------------------------------------------
+class _Attn:
+    def __init__(self, m, dtype):
+        self.heads = m.heads
+        self.q, self.k, self.v, self.o = (LinW(l, dtype) for l in (m.to_q, m.to_k, m.to_v, m.to_out[0]))
+        self.loras = [LoRAW(l.lora_layer, dtype) if getattr(l, "lora_layer", None) is not None else None
+                      for l in (m.to_q, m.to_k, m.to_v, m.to_out[0])]
+        self.gn = NormW(m.group_norm, m.group_norm.num_groups) if m.group_norm is not None else None
+
+
+class _TBlock:
+    def __init__(self, m, dtype):
+        self.n1, self.n2, self.n3 = NormW(m.norm1), NormW(m.norm2), NormW(m.norm3)
+        self.a1, self.a2 = _Attn(m.attn1, dtype), _Attn(m.attn2, dtype)
+        self.ff1, self.ff2 = LinW(m.ff.net[0].proj, dtype), LinW(m.ff.net[2], dtype)
+
+
+class _Transformer:
+    def __init__(self, m, dtype):
+        self.gn = NormW(m.norm, m.norm.num_groups)
+        self.linear_proj = m.use_linear_projection
+        if self.linear_proj:
+            self.pin, self.pout = LinW(m.proj_in, dtype), LinW(m.proj_out, dtype)
+        else:
+            self.pin, self.pout = ConvW(m.proj_in, dtype), ConvW(m.proj_out, dtype)
+        self.blocks = [_TBlock(b, dtype) for b in m.transformer_blocks]
+
+
+class _Res:
+    def __init__(self, m, dtype):
+        self.n1, self.n2 = NormW(m.norm1, m.norm1.num_groups), NormW(m.norm2, m.norm2.num_groups)
+        self.c1, self.c2 = ConvW(m.conv1, dtype), ConvW(m.conv2, dtype)
+        self.temb = LinW(m.time_emb_proj, dtype) if m.time_emb_proj is not None else None
+        self.short = ConvW(m.conv_shortcut, dtype) if m.conv_shortcut is not None else None
+
+
+def _resnet(tape, r: _Res, x: Var, temb_act16, skip: Optional[Var] = None) -> Var:
+    """ResnetBlock2D.  ``skip``: the UNet skip tensor — GroupNorm spans the concatenation so it is
+    materialised once; the 1x1 shortcut reads the two segments directly."""
+    xin = concat(tape, x, skip) if skip is not None else x
+    h = groupnorm(tape, xin, r.n1, True)
+    rowvec = None
+    if r.temb is not None and temb_act16 is not None:
+        rowvec = ops.gemm([temb_act16], [r.temb.w], bias=r.temb.bias, out_fp32=True)     # (n, Cout) fp32, constant wrt params
+    h = conv(tape, [h], r.c1, rowvec=rowvec)
+    h = groupnorm(tape, h, r.n2, True)
+    sc = conv(tape, [xin], r.short) if r.short is not None else xin
+    return conv(tape, [h], r.c2, residual=sc)
+
+
+def _attn_layer(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, capture=None, place=None):
+    q = linear(tape, x, a.q, a.loras[0])
+    src = x if ctx is None else ctx
+    k = linear(tape, src, a.k, a.loras[1])
+    v = linear(tape, src, a.v, a.loras[2])
+    export = capture is not None and ctx is not None and capture.wants(place)
+    o, p = attention(tape, q, k, v, a.heads, export_probs=export)
+    if capture is not None:
+        capture.push(p, ctx is not None, place)
+    return linear(tape, o, a.o, a.loras[3], residual=residual)
+
+
+def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=None) -> Var:
+    n, H, W, C = x.v.shape
+    h = groupnorm(tape, x, t.gn, False)
+    if t.linear_proj:
+        h = linear(tape, _reshape(tape, h, (n, H * W, C)), t.pin)
+    else:
+        h = _reshape(tape, conv(tape, [h], t.pin), (n, H * W, t.pin.cout))
+    for b in t.blocks:
+        h = _attn_layer(tape, b.a1, layernorm(tape, h, b.n1), None, h, capture, place)
+        h = _attn_layer(tape, b.a2, layernorm(tape, h, b.n2), ctx, h, capture, place)
+        ff = geglu(tape, linear(tape, layernorm(tape, h, b.n3), b.ff1))
+        h = linear(tape, ff, b.ff2, residual=h)
+    if t.linear_proj:
+        return _reshape(tape, linear(tape, h, t.pout, residual=_reshape(tape, x, (n, H * W, C))), (n, H, W, C))
+    return conv(tape, [_reshape(tape, h, (n, H, W, h.v.shape[-1]))], t.pout, residual=x)
+
+
+def _reshape(tape, x: Var, shape) -> Var:
+    out = Var(x.v.reshape(shape), x.needs_grad)
+    if tape is not None:
+        def bwd():
+            if out.g is not None:
+                _acc(x, out.g.reshape(x.v.shape))
+        tape.record(bwd)
+    return out
+
+
+class AttnCapture:
+    """Product-side AttentionStore (attn_utils/tc_attn_utils.py:53-94): keeps the exported cross-attention
+    probability Vars of the requested places for one UNet pass."""
+
+    def __init__(self, train_layer_ls):
+        self.places = sorted({s.split("_")[0] for s in train_layer_ls})
+        self.reset()
+
+    def reset(self):
+        self.store = {"down": [], "mid": [], "up": []}
+        self.count = 0
+
+    def wants(self, place):
+        return place in self.places
+
+    def push(self, pvar, is_cross, place):
+        self.count += 1
+        if pvar is not None and is_cross and place in self.places:
+            self.store[place].append(pvar)
+
+    def attn_dict(self, reses=(64, 32, 16, 8), poses=("down", "mid", "up")):
+        """get_cross_attn_map_from_unet (tc_attn_utils.py:198-216) -> ({'up_16': [tensor (B*h,res,res,T)]}, same of Vars)"""
+        out, vars_ = {}, {}
+        for pos in poses:
+            for res in reses:
+                sel = [p for p in self.store[pos] if p.v.shape[1] == res * res]
+                if sel:
+                    out[f"{pos}_{res}"] = [p.v.reshape(-1, res, res, p.v.shape[-1]) for p in sel]
+                    vars_[f"{pos}_{res}"] = sel
+        return out, vars_
+
+
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """diffusers Timesteps(flip_sin_to_cos=True, freq_shift=0): [cos | sin]."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    arg = t.float()[:, None] * freqs[None]
+    return torch.cat([arg.cos(), arg.sin()], -1)
+
+
+class UNetEngine:
+    """UNet2DConditionModel executor (SD1.5 and SDXL geometries)."""
+
+    def __init__(self, unet: torch.nn.Module, dtype=torch.float16):
+        self.dtype = dtype
+        self.cfg = unet.config
+        self.te1, self.te2 = LinW(unet.time_embedding.linear_1, dtype), LinW(unet.time_embedding.linear_2, dtype)
+        self.tdim = unet.time_embedding.linear_1.in_features
+        self.sdxl = getattr(unet.config, "addition_embed_type", None) == "text_time"
+        if self.sdxl:
+            self.ae1, self.ae2 = LinW(unet.add_embedding.linear_1, dtype), LinW(unet.add_embedding.linear_2, dtype)
+            self.add_dim = unet.config.addition_time_embed_dim
+        self.conv_in = ConvW(unet.conv_in, dtype, cin_pad=64)
+        self.down = []
+        for blk in unet.down_blocks:
+            attns = [_Transformer(a, dtype) for a in blk.attentions] if hasattr(blk, "attentions") else None
+            ds = ConvW(blk.downsamplers[0].conv, dtype) if blk.downsamplers is not None else None
+            self.down.append(([_Res(r, dtype) for r in blk.resnets], attns, ds))
+        mb = unet.mid_block
+        self.mid = ([_Res(r, dtype) for r in mb.resnets], [_Transformer(a, dtype) for a in mb.attentions])
+        self.up = []
+        for blk in unet.up_blocks:
+            attns = [_Transformer(a, dtype) for a in blk.attentions] if hasattr(blk, "attentions") else None
+            us = ConvW(blk.upsamplers[0].conv, dtype) if blk.upsamplers is not None else None
+            self.up.append(([_Res(r, dtype) for r in blk.resnets], attns, us))
+        self.norm_out = NormW(unet.conv_norm_out, unet.conv_norm_out.num_groups)
+        self.conv_out = ConvW(unet.conv_out, dtype)
+        self.loras: List[LoRAW] = []
+        for blocks in [self.down, [(self.mid[0], self.mid[1], None)], self.up]:
+            for _, attns, _ in blocks:
+                for t in attns or []:
+                    for b in t.blocks:
+                        for a in (b.a1, b.a2):
+                            self.loras.extend(l for l in a.loras if l is not None)
+
+    # ---- LoRA plumbing
+    def refresh_lora(self):
+        for l in self.loras:
+            l.refresh()
+
+    def zero_lora_grads(self):
+        for l in self.loras:
+            l.g_down = l.g_up = None
+
+    def lora_params(self):
+        return [p for l in self.loras for p in (l.down, l.up)]
+
+    def lora_grads(self):
+        return [g for l in self.loras for g in (l.g_down, l.g_up)]
+
+    # ---- forward
+    def temb(self, t: torch.Tensor, n: int, added_cond=None):
+        """SiLU(time embedding) as 16-bit (n, 1280) — constant w.r.t. all trainable tensors."""
+        te = timestep_embedding(t.reshape(-1).expand(n).to(self.te1.w.device), self.tdim).to(self.dtype)
+        e = ops.gemm([ops.gemm([te], [self.te1.w], bias=self.te1.bias, act="silu")], [self.te2.w], bias=self.te2.bias, out_fp32=True)
+        if self.sdxl:
+            tid = added_cond["time_ids"].reshape(-1)
+            te2 = timestep_embedding(tid, self.add_dim).reshape(n, -1)
+            add = torch.cat([added_cond["text_embeds"].float(), te2], -1).to(self.dtype)
+            e = e + ops.gemm([ops.gemm([add], [self.ae1.w], bias=self.ae1.bias, act="silu")], [self.ae2.w], bias=self.ae2.bias, out_fp32=True)
+        return ops.elementwise("silu", e.to(self.dtype))
+
+    def forward(self, tape: Optional[Tape], x: Var, t: torch.Tensor, ctx: torch.Tensor, capture: Optional[AttnCapture] = None,
+                added_cond=None) -> Var:
+        """x: Var of NHWC 16-bit latents zero-padded to 64 channels (n, h, w, 64); ctx: (n, 77, D) 16-bit.
+        returns Var (n, h, w, 4)."""
+        n = x.v.shape[0]
+        temb = self.temb(t, n, added_cond)
+        cvar = Var(ctx, needs_grad=False)
+        h = conv(tape, [x], self.conv_in)
+        skips = [h]
+        for resnets, attns, ds in self.down:
+            for i, r in enumerate(resnets):
+                h = _resnet(tape, r, h, temb)
+                if attns is not None:
+                    h = _transformer(tape, attns[i], h, cvar, capture, "down")
+                skips.append(h)
+            if ds is not None:
+                h = conv(tape, [h], ds)
+                skips.append(h)
+        h = _resnet(tape, self.mid[0][0], h, temb)
+        h = _transformer(tape, self.mid[1][0], h, cvar, capture, "mid")
+        h = _resnet(tape, self.mid[0][1], h, temb)
+        for resnets, attns, us in self.up:
+            for i, r in enumerate(resnets):
+                h = _resnet(tape, r, h, temb, skip=skips.pop())
+                if attns is not None:
+                    h = _transformer(tape, attns[i], h, cvar, capture, "up")
+            if us is not None:
+                h = conv(tape, [upsample2x(tape, h)], us)
+        h = groupnorm(tape, h, self.norm_out, True)
+        return conv(tape, [h], self.conv_out)
+
+
+class VAEDecoderEngine:
+    """AutoencoderKL.decode executor (TrainableSDPipeline.py:220)."""
+
+    def __init__(self, vae: torch.nn.Module, dtype=torch.float16):
+        self.dtype = dtype
+        self.scaling_factor = vae.config.scaling_factor
+        self.pq = ConvW(vae.post_quant_conv, dtype, cin_pad=64)
+        d = vae.decoder
+        self.conv_in = ConvW(d.conv_in, dtype, cin_pad=64)
+        self.mid_res = [_Res(r, dtype) for r in d.mid_block.resnets]
+        self.mid_attn = _Attn(d.mid_block.attentions[0], dtype)
+        self.ups = []
+        for blk in d.up_blocks:
+            us = ConvW(blk.upsamplers[0].conv, dtype) if blk.upsamplers is not None else None
+            self.ups.append(([_Res(r, dtype) for r in blk.resnets], us))
+        self.norm_out = NormW(d.conv_norm_out, d.conv_norm_out.num_groups)
+        self.conv_out = ConvW(d.conv_out, dtype)
+
+    def forward(self, tape: Optional[Tape], z: Var) -> Var:
+        """z: Var NHWC 16-bit (n,h,w,64) = latents / scaling_factor zero-padded; returns (n, 8h, 8w, 3)."""
+        n, H, W, _ = z.v.shape
+        # post_quant_conv is 1x1 4->4: run on the padded tensor, then re-pad its 4 outputs to 64 for conv_in
+        pq = conv(tape, [z], self.pq_as_padded())
+        h = conv(tape, [pq], self.conv_in)
+        h = _resnet(tape, self.mid_res[0], h, None)
+        a = self.mid_attn
+        hn = _reshape(tape, groupnorm(tape, h, a.gn, False), (n, H * W, h.v.shape[-1]))
+        hr = _reshape(tape, h, (n, H * W, h.v.shape[-1]))
+        h = _reshape(tape, _attn_layer(tape, a, hn, None, hr), (n, H, W, h.v.shape[-1]))
+        h = _resnet(tape, self.mid_res[1], h, None)
+        for resnets, us in self.ups:
+            for r in resnets:
+                h = _resnet(tape, r, h, None)
+            if us is not None:
+                h = conv(tape, [upsample2x(tape, h)], us)
+        h = groupnorm(tape, h, self.norm_out, True)
+        return conv(tape, [h], self.conv_out)
+
+    def pq_as_padded(self) -> ConvW:
+        """post_quant_conv re-expressed as a 64->64 1x1 conv (zero rows/cols) so its output feeds conv_in directly."""
+        if not hasattr(self, "_pq64"):
+            cw = object.__new__(ConvW)
+            w = torch.zeros(64, 64, dtype=self.dtype, device=self.pq.w_f.device)
+            w[: self.pq.cout, : self.pq.cin] = self.pq.w_f[:, : self.pq.cin]
+            cw.cout, cw.cin, cw.k, cw.stride, cw.cin_pad = 64, 64, 1, 1, 64
+            cw.bias = torch.zeros(64, dtype=torch.float32, device=w.device)
+            cw.bias[: self.pq.cout] = self.pq.bias
+            cw.w_f, cw.taps_f, cw.w_d, cw.taps_d = w.contiguous(), None, w.t().contiguous(), None
+            self._pq64 = cw
+        return self._pq64

@@ -1,0 +1,272 @@
+"""Thin Python bindings of the C-ABI compute entry points (include/comat_b200.h).
+
+Tensors are torch CUDA tensors used purely as device memory + stream plumbing; every function here ends in a
+``comat_*`` C call on the current CUDA stream.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+class GemmParams(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("dtype", C.c_int32), ("n_seg", C.c_int32),
+                ("a", C.c_void_p * 2), ("a_ld", C.c_int64 * 2), ("a_k", C.c_int32 * 2),
+                ("b", C.c_void_p * 2), ("b_ld", C.c_int64 * 2), ("b_koff", C.c_int32 * 2),
+                ("conv", C.c_int32), ("n_img", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_taps", C.c_int32),
+                ("c_total", C.c_int32), ("tap_dh", C.c_int32 * 9), ("tap_dw", C.c_int32 * 9),
+                ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rows_per_group", C.c_int32),
+                ("act", C.c_int32), ("residual", C.c_void_p), ("res_ld", C.c_int64), ("out16", C.c_void_p),
+                ("out_ld", C.c_int64), ("out32", C.c_void_p), ("out32_ld", C.c_int64), ("force_bn", C.c_int32)]
+
+
+_lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
+
+ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2}
+TAPS_3x3 = [(dh, dw) for dh in (-1, 0, 1) for dw in (-1, 0, 1)]
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_koff: Sequence[int] = (0, 0),
+         bias: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_group: int = 1,
+         act=None, residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
+         out_fp32: bool = False, conv_taps=None, c_total: int = 0, force_bn: int = 0) -> torch.Tensor:
+    """out[m,n] = act(alpha * sum_s A_s[m,:] . B_s[n,:] + bias[n] + rowvec[m // rows_per_group, n]) + residual[m,n]
+
+    plain mode : A_s is (M, K_s) (last dim contiguous); B_s is (N, >=K_s) K-major.
+    conv mode  : ``conv_taps`` = [(dh, dw), ...]; A_s is NHWC (n, H, W, C_s) contiguous; B_s is (N, taps*c_total)
+                 with k = tap*c_total + b_koff[s] + c; returns (n, H, W, N).
+    """
+    a0 = a_segs[0]
+    _lib.require_cuda(a0)
+    dt = a0.dtype
+    if dt not in (torch.float16, torch.bfloat16):
+        raise _lib.ComatError("gemm: A must be fp16 or bf16")
+    p = GemmParams()
+    conv = conv_taps is not None
+    if conv:
+        n_img, H, W, _ = a0.shape
+        M = n_img * H * W
+        p.conv, p.n_img, p.H, p.W, p.n_taps = 1, n_img, H, W, len(conv_taps)
+        p.c_total = c_total if c_total else sum(a.shape[-1] for a in a_segs)
+        for i, (dh, dw) in enumerate(conv_taps):
+            p.tap_dh[i], p.tap_dw[i] = dh, dw
+    else:
+        M = a0.numel() // a0.shape[-1]
+    N = b_segs[0].shape[0]
+    p.M, p.N, p.dtype, p.n_seg = M, N, DT[dt], len(a_segs)
+    keep = []
+    koff_auto = 0
+    for s, (a, b) in enumerate(zip(a_segs, b_segs)):
+        if a.dtype != dt or b.dtype != dt:
+            raise _lib.ComatError("gemm: all operands must share the 16-bit dtype")
+        if conv:
+            a = a.contiguous()
+            p.a_ld[s] = a.shape[-1]
+        else:
+            a = a.reshape(-1, a.shape[-1])
+            if a.stride(-1) != 1:
+                a = a.contiguous()
+            p.a_ld[s] = a.stride(0) if a.shape[0] > 1 else a.shape[-1]
+        if b.stride(-1) != 1:
+            b = b.contiguous()
+        keep += [a, b]
+        p.a[s], p.a_k[s] = a.data_ptr(), a.shape[-1]
+        p.b[s], p.b_ld[s] = b.data_ptr(), b.stride(0)
+        p.b_koff[s] = b_koff[s]
+    p.alpha = alpha
+    if bias is not None:
+        bias = bias.float().contiguous()
+    if rowvec is not None:
+        rowvec = rowvec.float().contiguous()
+    p.bias, p.rowvec, p.rows_per_group, p.act = _p(bias), _p(rowvec), rows_per_group, ACT[act]
+    if residual is not None:
+        residual = residual.reshape(M, N) if residual.is_contiguous() else residual.contiguous().reshape(M, N)
+        if residual.dtype != dt:
+            raise _lib.ComatError("gemm: residual dtype mismatch")
+        p.residual, p.res_ld = residual.data_ptr(), residual.stride(0)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else dt, device=a0.device)
+    o2 = out.reshape(M, N) if out.dim() != 2 else out
+    if o2.stride(-1) != 1:
+        raise _lib.ComatError("gemm: out must have unit inner stride")
+    if o2.dtype == torch.float32:
+        p.out32, p.out32_ld = o2.data_ptr(), o2.stride(0)
+    else:
+        p.out16, p.out_ld = o2.data_ptr(), o2.stride(0)
+    p.force_bn = force_bn
+    _lib.check(_lib.lib().comat_gemm(C.byref(p), _lib.stream_ptr()), "gemm")
+    _lib.count_launch()
+    if conv:
+        return out.reshape(n_img, H, W, N) if out.dim() == 2 else out
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# normalisation / activation / rearrangement bindings
+# ------------------------------------------------------------------------------------------------------------
+_vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
+_lib.register_signature("comat_groupnorm_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp])
+_lib.register_signature("comat_groupnorm_bwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
+_lib.register_signature("comat_layernorm_fwd", [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp])
+_lib.register_signature("comat_layernorm_bwd", [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp])
+_lib.register_signature("comat_geglu_fwd", [_vp, _vp, _ll, _i, _i, _vp])
+_lib.register_signature("comat_geglu_bwd", [_vp, _vp, _vp, _ll, _i, _i, _vp])
+_lib.register_signature("comat_elementwise", [_vp, _vp, _vp, _ll, _i, _f, _f, _i, _vp])
+_lib.register_signature("comat_spatial", [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
+_lib.register_signature("comat_transpose16", [_vp, _vp, _i, _i, _i, _vp])
+_lib.register_signature("comat_copy2d16", [_vp, _vp, _ll, _i, _ll, _ll, _vp])
+_lib.register_signature("comat_latent_to_nhwc", [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp])
+_lib.register_signature("comat_nhwc_to_nchw_f32", [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp])
+
+
+def _gn_ws(n, HW, G, dev):
+    L = _lib.lib()
+    L.comat_groupnorm_workspace_floats.restype = _sz
+    L.comat_groupnorm_workspace_floats.argtypes = [_i, _i, _i]
+    return torch.empty(int(L.comat_groupnorm_workspace_floats(n, HW, G)), dtype=torch.float32, device=dev)
+
+
+def _call(name, *args, launches=1):
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+    _lib.count_launch(launches)
+
+
+def groupnorm_fwd(x, gamma, beta, G, eps, silu):
+    """x: (n, HW, C) or (n, H, W, C) 16-bit contiguous -> (y, mean_rstd)"""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    n, C_ = x.shape[0], x.shape[-1]
+    HW = x.numel() // (n * C_)
+    y = torch.empty_like(x)
+    mr = torch.empty(n * G * 2, dtype=torch.float32, device=x.device)
+    _call("comat_groupnorm_fwd", x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mr.data_ptr(),
+          _gn_ws(n, HW, G, x.device).data_ptr(), n, HW, C_, G, eps, int(silu), DT[x.dtype], _lib.stream_ptr(), launches=3)
+    return y, mr
+
+
+def groupnorm_bwd(x, dy, gamma, beta, mr, G, silu):
+    x, dy = x.contiguous(), dy.contiguous()
+    n, C_ = x.shape[0], x.shape[-1]
+    HW = x.numel() // (n * C_)
+    dx = torch.empty_like(x)
+    _call("comat_groupnorm_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mr.data_ptr(),
+          _gn_ws(n, HW, G, x.device).data_ptr(), n, HW, C_, G, int(silu), DT[x.dtype], _lib.stream_ptr(), launches=3)
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    y = torch.empty_like(x)
+    mr = torch.empty(rows * 2, dtype=torch.float32, device=x.device)
+    _call("comat_layernorm_fwd", x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mr.data_ptr(), rows, C_, eps,
+          DT[x.dtype], _lib.stream_ptr())
+    return y, mr
+
+
+def layernorm_bwd(x, dy, gamma, mr):
+    x, dy = x.contiguous(), dy.contiguous()
+    C_ = x.shape[-1]
+    dx = torch.empty_like(x)
+    _call("comat_layernorm_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(), mr.data_ptr(), x.numel() // C_, C_,
+          DT[x.dtype], _lib.stream_ptr())
+    return dx
+
+
+def geglu_fwd(hg):
+    _lib.require_cuda(hg)
+    hg = hg.contiguous()
+    Ch = hg.shape[-1] // 2
+    out = torch.empty(*hg.shape[:-1], Ch, dtype=hg.dtype, device=hg.device)
+    _call("comat_geglu_fwd", hg.data_ptr(), out.data_ptr(), hg.numel() // (2 * Ch), Ch, DT[hg.dtype], _lib.stream_ptr())
+    return out
+
+
+def geglu_bwd(hg, dy):
+    hg, dy = hg.contiguous(), dy.contiguous()
+    Ch = hg.shape[-1] // 2
+    d = torch.empty_like(hg)
+    _call("comat_geglu_bwd", hg.data_ptr(), dy.data_ptr(), d.data_ptr(), hg.numel() // (2 * Ch), Ch, DT[hg.dtype], _lib.stream_ptr())
+    return d
+
+
+EW = {"silu": 0, "silu_bwd": 1, "gelu": 2, "gelu_bwd": 3, "add": 4, "scale": 5, "axpby": 6}
+
+
+def elementwise(op, x, y=None, alpha=1.0, beta=1.0):
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    y = y.contiguous() if y is not None else None
+    out = torch.empty_like(x)
+    _call("comat_elementwise", x.data_ptr(), _p(y), out.data_ptr(), x.numel(), EW[op], alpha, beta, DT[x.dtype], _lib.stream_ptr())
+    return out
+
+
+def spatial(x, mode):
+    """mode: 'up2' (n,H,W,C)->(n,2H,2W,C) | 'up2_bwd' | 's2d' (n,H,W,C)->(n,H/2,W/2,4C) | 'd2s'"""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    n, H, W, C_ = x.shape
+    if mode == "up2":
+        out, args = torch.empty(n, 2 * H, 2 * W, C_, dtype=x.dtype, device=x.device), (n, H, W, C_, 0)
+    elif mode == "up2_bwd":
+        out, args = torch.empty(n, H // 2, W // 2, C_, dtype=x.dtype, device=x.device), (n, H // 2, W // 2, C_, 1)
+    elif mode == "s2d":
+        out, args = torch.empty(n, H // 2, W // 2, 4 * C_, dtype=x.dtype, device=x.device), (n, H, W, C_, 2)
+    else:
+        out, args = torch.empty(n, 2 * H, 2 * W, C_ // 4, dtype=x.dtype, device=x.device), (n, 2 * H, 2 * W, C_ // 4, 3)
+    _call("comat_spatial", x.data_ptr(), out.data_ptr(), *args, DT[x.dtype], _lib.stream_ptr())
+    return out
+
+
+def transpose16(x, pad_to=1):
+    """(R, Cc) -> (Cc, R'), R' = R rounded up to ``pad_to`` (extra columns zero) so the result can be a K-major GEMM operand."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    R, Cc = x.shape
+    Rp = (R + pad_to - 1) // pad_to * pad_to
+    out = (torch.zeros if Rp != R else torch.empty)(Cc, Rp, dtype=x.dtype, device=x.device)
+    _call("comat_transpose16", x.data_ptr(), out.data_ptr(), R, Cc, Rp, _lib.stream_ptr())
+    return out
+
+
+def concat_channels(a, b):
+    """torch.cat([a, b], dim=-1) for NHWC 16-bit tensors (two strided row copies)."""
+    _lib.require_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    rows = a.numel() // Ca
+    out = torch.empty(*a.shape[:-1], Ca + Cb, dtype=a.dtype, device=a.device)
+    _call("comat_copy2d16", a.data_ptr(), out.data_ptr(), rows, Ca, Ca, Ca + Cb, _lib.stream_ptr())
+    _call("comat_copy2d16", b.data_ptr(), out.data_ptr() + 2 * Ca, rows, Cb, Cb, Ca + Cb, _lib.stream_ptr())
+    return out
+
+
+def latent_to_nhwc(x_nchw_f32, dtype, cpad=64, scale=1.0):
+    _lib.require_cuda(x_nchw_f32)
+    x = x_nchw_f32.float().contiguous()
+    n, Cin, H, W = x.shape
+    out = torch.empty(n, H, W, cpad, dtype=dtype, device=x.device)
+    _call("comat_latent_to_nhwc", x.data_ptr(), out.data_ptr(), n, Cin, H * W, cpad, scale, DT[dtype], _lib.stream_ptr())
+    return out
+
+
+def nhwc_to_nchw_f32(x, cout, scale=1.0):
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    n, H, W, ld = x.shape
+    out = torch.empty(n, cout, H, W, dtype=torch.float32, device=x.device)
+    _call("comat_nhwc_to_nchw_f32", x.data_ptr(), out.data_ptr(), n, cout, H * W, ld, scale, DT[x.dtype], _lib.stream_ptr())
+    return out

@@ -85,6 +85,84 @@ int comat_attnmap_loss_bwd(const comat_attnmap_plan* plan, const float* grad2, c
  * in: u8 (n, in_h, in_w)  out: f32 (n, res, res) of 0/1. */
 int comat_mask_resize_any(const uint8_t* in, float* out, int n, int in_h, int in_w, int res, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMEM + TMA), 16-bit in, fp32 accumulate:
+ *     out[m,n] = act(alpha * sum_k A[m,k] * B[n,k] + bias[n] + rowvec[m / rows_per_group, n]) + residual[m,n]
+ * Replaces the library calls behind diffusers Linear / Conv2d / LoRACompatibleLinear on the UNet, VAE and BLIP
+ * paths (reference call sites: TrainableSDPipeline.py:144-150 `self.unet(...)`, :220 `self.vae.decode`,
+ * concept_mat_utils/caption_blip.py:57 `self.model(**inputs)`, LoRA: training_utils/pipeline.py:94-115).
+ *   plain mode : A = [M, a_k] row-major with leading dimension a_ld.
+ *   conv mode  : A = NHWC activation (n_img, H, W, a_k) dense; k-blocks iterate (tap, segment, 64-channel slab),
+ *                tap t reads the input at spatial offset (tap_dh[t], tap_dw[t]); out-of-range pixels are zero
+ *                (TMA out-of-bounds fill == the convolution's zero padding).  M must equal n_img*H*W, a_k % 64 == 0.
+ *   n_seg = 2  : two K-segments accumulate into one output — [x | x.down^T] x [W | up] (LoRA) or
+ *                [hidden | skip] x W (torch.cat fused away).  b_koff[s] = column of B where segment s starts
+ *                (conv: inside each tap's block of c_total channels).
+ *   B          : [N, b_ld] row-major (K-major) 16-bit weights.
+ * All base pointers 16-byte aligned, a_ld/b_ld/a_k multiples of 8.  act: 0 none, 1 SiLU, 2 GELU(erf).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t M, N;
+  int32_t dtype;            /* COMAT_F16 or COMAT_BF16 (A, B, residual, out16) */
+  int32_t n_seg;
+  const void* a[2];
+  int64_t a_ld[2];
+  int32_t a_k[2];
+  const void* b[2];
+  int64_t b_ld[2];
+  int32_t b_koff[2];
+  int32_t conv, n_img, H, W, n_taps, c_total;
+  int32_t tap_dh[9], tap_dw[9];
+  float alpha;
+  const float* bias;
+  const float* rowvec;
+  int32_t rows_per_group;
+  int32_t act;
+  const void* residual;
+  int64_t res_ld;
+  void* out16;
+  int64_t out_ld;
+  float* out32;
+  int64_t out32_ld;
+  int32_t force_bn;         /* 0 = auto; else 32/64/128/160/256 (tuning / tests) */
+} comat_gemm_params;
+
+int comat_gemm(const comat_gemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HBM-bound normalisation / activation / rearrangement kernels (16-bit activations, fp32 statistics).
+ * Replace aten group_norm / silu / layer_norm / gelu / interpolate / cat launched by diffusers' ResnetBlock2D,
+ * Transformer2DModel, BasicTransformerBlock, GEGLU, Upsample2D/Downsample2D.
+ * Activations are row-major [rows, C]; images are NHWC (n, H*W, C).  dtype = COMAT_F16 / COMAT_BF16.
+ * Base weights are frozen on this path (training_utils/pipeline.py:66-71): no gamma/beta gradients.
+ * ------------------------------------------------------------------------------------------------------------ */
+size_t comat_groupnorm_workspace_floats(int n, int HW, int G);
+/* y = [silu](GroupNorm(x)); saves (mean, rstd) per (n, group) in mean_rstd[n*G*2] */
+int comat_groupnorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, float* ws,
+                        int n, int HW, int C, int G, float eps, int silu, int dtype, void* stream);
+int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* beta,
+                        const float* mean_rstd, float* ws, int n, int HW, int C, int G, int silu, int dtype, void* stream);
+int comat_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, long long rows,
+                        int C, float eps, int dtype, void* stream);
+int comat_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* mean_rstd, long long rows,
+                        int C, int dtype, void* stream);
+/* GEGLU: hg = [hidden | gate] (rows, 2*Ch) -> out = hidden * gelu(gate) (rows, Ch); bwd writes d[hidden | gate] */
+int comat_geglu_fwd(const void* hg, void* out, long long rows, int Ch, int dtype, void* stream);
+int comat_geglu_bwd(const void* hg, const void* dy, void* dhg, long long rows, int Ch, int dtype, void* stream);
+/* op: 0 silu(x) 1 silu'(x)*y 2 gelu(x) 3 gelu'(x)*y 4 x+y 5 alpha*x 6 alpha*x+beta*y ; numel % 8 == 0 */
+int comat_elementwise(const void* x, const void* y, void* out, long long numel, int op, float alpha, float beta, int dtype,
+                      void* stream);
+/* mode 0: nearest x2 upsample (n,H,W,C)->(n,2H,2W,C); 1: its backward (H,W = small dims);
+ * mode 2: space-to-depth (n,H,W,C)->(n,H/2,W/2,4C) (channel block = (y&1)*2+(x&1)); 3: inverse (H,W = large dims) */
+int comat_spatial(const void* in, void* out, int n, int H, int W, int C, int mode, int dtype, void* stream);
+/* 16-bit (R, Cc) -> (Cc, ld_out >= R) */
+int comat_transpose16(const void* in, void* out, int R, int Cc, int ld_out, void* stream);
+int comat_copy2d16(const void* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst, void* stream);
+/* fp32 NCHW latents -> 16-bit NHWC zero-padded to Cpad channels (x scale), and back (first Cout of ld channels) */
+int comat_latent_to_nhwc(const float* in, void* out, int n, int Cin, int HW, int Cpad, float scale, int dtype, void* stream);
+int comat_nhwc_to_nchw_f32(const void* in, float* out, int n, int Cout, int HW, int ld, float scale, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

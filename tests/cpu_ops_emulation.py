@@ -1,0 +1,148 @@
+"""TEST INFRASTRUCTURE: a torch (CPU, fp32/fp64) emulation of the *semantics* of the C-ABI ops in comat_b200/ops.py.
+
+It exists so the host-side executor logic (tape, backward formulas, weight packing, segment/tap bookkeeping) can be
+verified against the oracle in the CPU-only build container.  It is never imported by the product; tests install it
+with ``monkeypatch`` and the product still has no CPU path.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_group=1, act=None, residual=None, alpha=1.0,
+         out=None, out_fp32=False, conv_taps=None, c_total=0, force_bn=0):
+    a0 = a_segs[0]
+    N = b_segs[0].shape[0]
+    if conv_taps is not None:
+        n, H, W, _ = a0.shape
+        M = n * H * W
+        ct = c_total if c_total else sum(a.shape[-1] for a in a_segs)
+        acc = torch.zeros(n, H, W, N, dtype=torch.float64)
+        for s, (a, b) in enumerate(zip(a_segs, b_segs)):
+            C = a.shape[-1]
+            ap = F.pad(a.double(), (0, 0, 2, 2, 2, 2))
+            for t, (dh, dw) in enumerate(conv_taps):
+                k0 = t * ct + b_koff[s]
+                acc += ap[:, 2 + dh:2 + dh + H, 2 + dw:2 + dw + W, :] @ b[:, k0:k0 + C].double().t()
+        acc = acc.reshape(M, N)
+    else:
+        M = a0.numel() // a0.shape[-1]
+        acc = torch.zeros(M, N, dtype=torch.float64)
+        for s, (a, b) in enumerate(zip(a_segs, b_segs)):
+            K = a.shape[-1]
+            acc += a.reshape(M, K).double() @ b[:, b_koff[s]:b_koff[s] + K].double().t()
+    y = acc * alpha
+    if bias is not None:
+        y = y + bias.double()
+    if rowvec is not None:
+        y = y + rowvec.double().repeat_interleave(rows_per_group, 0)
+    if act == "silu":
+        y = F.silu(y)
+    elif act == "gelu":
+        y = F.gelu(y)
+    if residual is not None:
+        y = y + residual.reshape(M, N).double()
+    y = y.to(torch.float32 if out_fp32 else a0.dtype)
+    if conv_taps is not None:
+        return y.reshape(n, H, W, N)
+    return y
+
+
+def groupnorm_fwd(x, gamma, beta, G, eps, silu):
+    n, C = x.shape[0], x.shape[-1]
+    xf = x.double().reshape(n, -1, G, C // G)
+    mean = xf.mean((1, 3), keepdim=True)
+    var = xf.var((1, 3), unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    y = ((xf - mean) * rstd).reshape(n, -1, C) * gamma.double() + beta.double()
+    if silu:
+        y = F.silu(y)
+    return y.reshape(x.shape).to(x.dtype), (mean, rstd, eps)
+
+
+def groupnorm_bwd(x, dy, gamma, beta, mr, G, silu):
+    xr = x.double().requires_grad_(True)
+    y, _ = groupnorm_fwd(xr, gamma, beta, G, mr[2], silu)
+    return torch.autograd.grad(y, xr, dy.double())[0].to(x.dtype)
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    return F.layer_norm(x.double(), (x.shape[-1],), gamma.double(), beta.double(), eps).to(x.dtype), eps
+
+
+def layernorm_bwd(x, dy, gamma, mr):
+    xr = x.double().requires_grad_(True)
+    y = F.layer_norm(xr, (x.shape[-1],), gamma.double(), torch.zeros_like(gamma).double(), mr)
+    return torch.autograd.grad(y, xr, dy.double())[0].to(x.dtype)
+
+
+def geglu_fwd(hg):
+    h, g = hg.chunk(2, -1)
+    return (h.double() * F.gelu(g.double())).to(hg.dtype)
+
+
+def geglu_bwd(hg, dy):
+    r = hg.double().requires_grad_(True)
+    h, g = r.chunk(2, -1)
+    return torch.autograd.grad(h * F.gelu(g), r, dy.double())[0].to(hg.dtype)
+
+
+def elementwise(op, x, y=None, alpha=1.0, beta=1.0):
+    xd = x.double()
+    yd = y.double() if y is not None else None
+    if op == "silu":
+        r = F.silu(xd)
+    elif op == "silu_bwd":
+        xr = xd.requires_grad_(True)
+        r = torch.autograd.grad(F.silu(xr), xr, yd)[0]
+    elif op == "gelu":
+        r = F.gelu(xd)
+    elif op == "add":
+        r = xd + yd
+    elif op == "scale":
+        r = xd * alpha
+    elif op == "axpby":
+        r = alpha * xd + beta * yd
+    else:
+        raise NotImplementedError(op)
+    return r.to(x.dtype)
+
+
+def spatial(x, mode):
+    n, H, W, C = x.shape
+    if mode == "up2":
+        return x.repeat_interleave(2, 1).repeat_interleave(2, 2)
+    if mode == "up2_bwd":
+        return x.reshape(n, H // 2, 2, W // 2, 2, C).sum((2, 4))
+    if mode == "s2d":
+        return x.reshape(n, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(n, H // 2, W // 2, 4 * C)
+    return x.reshape(n, H, W, 2, 2, C // 4).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * H, 2 * W, C // 4)
+
+
+def transpose16(x, pad_to=1):
+    R, Cc = x.shape
+    Rp = (R + pad_to - 1) // pad_to * pad_to
+    out = x.new_zeros(Cc, Rp)
+    out[:, :R] = x.t()
+    return out
+
+
+def concat_channels(a, b):
+    return torch.cat([a, b], -1)
+
+
+def latent_to_nhwc(x, dtype, cpad=64, scale=1.0):
+    n, C, H, W = x.shape
+    out = torch.zeros(n, H, W, cpad, dtype=dtype)
+    out[..., :C] = (x * scale).permute(0, 2, 3, 1).to(dtype)
+    return out
+
+
+def nhwc_to_nchw_f32(x, cout, scale=1.0):
+    return (x[..., :cout].float() * scale).permute(0, 3, 1, 2).contiguous()
+
+
+def install(monkeypatch):
+    from comat_b200 import ops
+    for name in ("gemm", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
+                 "elementwise", "spatial", "transpose16", "concat_channels", "latent_to_nhwc", "nhwc_to_nchw_f32"):
+        monkeypatch.setattr(ops, name, globals()[name])

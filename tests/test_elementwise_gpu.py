@@ -1,0 +1,108 @@
+"""GPU parity: normalisation / activation / rearrangement kernels vs plain PyTorch fp32 references (fwd + bwd)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.2e-2)])
+@pytest.mark.parametrize("n,HW,C,silu,eps", [(2, 4096, 320, True, 1e-5), (3, 1024, 640, False, 1e-6), (2, 256, 1920, True, 1e-5),
+                                             (2, 64, 2560, True, 1e-5), (1, 16384, 128, True, 1e-6), (2, 64, 32, True, 1e-5)])
+def test_groupnorm(n, HW, C, silu, eps, dtype, tol):
+    from comat_b200 import ops
+    torch.manual_seed(C)
+    x = (torch.randn(n, HW, C, device="cuda") * 1.5 + 0.3).to(dtype)
+    g, b = torch.randn(C, device="cuda") * 0.2 + 1, torch.randn(C, device="cuda") * 0.1
+    dy = torch.randn(n, HW, C, device="cuda").to(dtype)
+    y, mr = ops.groupnorm_fwd(x, g, b, 32, eps, silu)
+    dx = ops.groupnorm_bwd(x, dy, g, b, mr, 32, silu)
+    xr = x.float().requires_grad_(True)
+    yr = F.group_norm(xr.permute(0, 2, 1), 32, g, b, eps).permute(0, 2, 1)
+    if silu:
+        yr = F.silu(yr)
+    yr.backward(dy.float())
+    assert rel(y.float(), yr) < tol
+    assert rel(dx.float(), xr.grad) < 2 * tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.2e-2)])
+@pytest.mark.parametrize("rows,C", [(8192, 320), (1000, 640), (577 * 2, 1024), (77, 768), (300, 1280)])
+def test_layernorm(rows, C, dtype, tol):
+    from comat_b200 import ops
+    torch.manual_seed(C)
+    x = (torch.randn(rows, C, device="cuda") * 2 - 0.5).to(dtype)
+    g, b = torch.randn(C, device="cuda") * 0.2 + 1, torch.randn(C, device="cuda") * 0.1
+    dy = torch.randn(rows, C, device="cuda").to(dtype)
+    y, mr = ops.layernorm_fwd(x, g, b, 1e-5)
+    dx = ops.layernorm_bwd(x, dy, g, mr)
+    xr = x.float().requires_grad_(True)
+    yr = F.layer_norm(xr, (C,), g, b, 1e-5)
+    yr.backward(dy.float())
+    assert rel(y.float(), yr) < tol and rel(dx.float(), xr.grad) < 2 * tol
+
+
+def test_geglu_and_unary():
+    from comat_b200 import ops
+    torch.manual_seed(0)
+    for dtype, tol in ((torch.float16, 2e-3), (torch.bfloat16, 1.2e-2)):
+        hg = torch.randn(1000, 2 * 1280, device="cuda").to(dtype)
+        dy = torch.randn(1000, 1280, device="cuda").to(dtype)
+        out = ops.geglu_fwd(hg)
+        d = ops.geglu_bwd(hg, dy)
+        r = hg.float().requires_grad_(True)
+        h, g = r.chunk(2, -1)
+        ref = h * F.gelu(g)
+        ref.backward(dy.float())
+        assert rel(out.float(), ref) < tol and rel(d.float(), r.grad) < 2 * tol
+        x = torch.randn(64, 1280, device="cuda").to(dtype)
+        y = torch.randn(64, 1280, device="cuda").to(dtype)
+        assert rel(ops.elementwise("silu", x).float(), F.silu(x.float())) < tol
+        xr = x.float().requires_grad_(True)
+        F.silu(xr).backward(y.float())
+        assert rel(ops.elementwise("silu_bwd", x, y).float(), xr.grad) < 2 * tol
+        assert rel(ops.elementwise("add", x, y).float(), x.float() + y.float()) < tol
+        assert rel(ops.elementwise("axpby", x, y, 0.5, -2.0).float(), 0.5 * x.float() - 2 * y.float()) < tol
+
+
+def test_spatial_and_layout():
+    from comat_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 12, 64, device="cuda").half()
+    up = ops.spatial(x, "up2")
+    ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    g = torch.randn_like(up)
+    assert rel(ops.spatial(g, "up2_bwd").float(), g.float().reshape(2, 8, 2, 12, 2, 64).sum((2, 4))) < 2e-3
+    s = ops.spatial(x, "s2d")
+    ref = x.reshape(2, 4, 2, 6, 2, 64).permute(0, 1, 3, 2, 4, 5).reshape(2, 4, 6, 256)
+    assert torch.equal(s, ref)
+    assert torch.equal(ops.spatial(s, "d2s"), x)
+    a = torch.randn(300, 320, device="cuda").half()
+    assert torch.equal(ops.transpose16(a), a.t().contiguous())
+    b = torch.randn(2, 8, 12, 128, device="cuda").half()
+    assert torch.equal(ops.concat_channels(x, b), torch.cat([x, b], -1))
+    lat = torch.randn(3, 4, 16, 16, device="cuda")
+    nh = ops.latent_to_nhwc(lat, torch.float16, 64, 2.0)
+    assert nh.shape == (3, 16, 16, 64) and float(nh[..., 4:].abs().max()) == 0
+    assert rel(nh[..., :4].float(), (2.0 * lat).permute(0, 2, 3, 1)) < 1e-3
+    back = ops.nhwc_to_nchw_f32(nh, 4, 0.5)
+    assert rel(back, lat) < 1e-3
+
+
+def test_stride2_conv_via_space_to_depth():
+    """Downsample2D (conv3x3 stride 2 pad 1) == 2x2-tap conv over the space-to-depth input with rearranged weights."""
+    from comat_b200 import ops, unet_weights
+    torch.manual_seed(0)
+    x = torch.randn(2, 32, 32, 64, device="cuda").half()
+    w = (torch.randn(128, 64, 3, 3, device="cuda") / 24).half()
+    bias = torch.randn(128, device="cuda")
+    wk, taps = unet_weights.pack_conv_stride2(w)
+    out = ops.gemm([ops.spatial(x, "s2d")], [wk], bias=bias, conv_taps=taps)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert rel(out.float(), ref) < 2e-3

@@ -1,0 +1,74 @@
+"""CPU: executor logic (tape, backward formulas, packing, segments) vs the oracle, with the C-ABI ops replaced by a
+torch emulation of their semantics (tests/cpu_ops_emulation.py — test infrastructure only)."""
+import pytest
+import torch
+
+from oracle import sd_modules as sdm
+from tests import cpu_ops_emulation as EMU
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _tiny(sdxl=False):
+    torch.manual_seed(3)
+    unet = sdm.UNet2DConditionModel(**sdm.tiny_unet_config(sdxl=sdxl, width=64, cross_attention_dim=64))
+    unet.requires_grad_(False)
+    sdm.install_lora(unet, 8, up_std=0.05, seed=4)
+    return unet
+
+
+@pytest.mark.parametrize("sdxl", [False, True])
+def test_unet_executor_matches_oracle(monkeypatch, sdxl):
+    EMU.install(monkeypatch)
+    from comat_b200 import engine as E, ops
+    unet = _tiny(sdxl)
+    dtype = torch.float32
+    eng = E.UNetEngine(unet, dtype)
+    g = torch.Generator().manual_seed(0)
+    n, hw = 2, 16
+    x = torch.randn(n, 4, hw, hw, generator=g)
+    ctx = torch.randn(n, 77, 64, generator=g)
+    added = dict(text_embeds=torch.randn(n, 16, generator=g), time_ids=torch.tensor([[512., 512, 0, 0, 512, 512]] * n)) if sdxl else None
+    t = torch.tensor(951)
+    dy = torch.randn(n, 4, hw, hw, generator=g)
+    xr = x.clone().requires_grad_(True)
+    params = [p for p in unet.parameters() if p.requires_grad]
+    kw = dict(added_cond_kwargs=added) if sdxl else {}
+    out_ref = unet(xr, t, ctx, return_dict=False, **kw)[0]
+    grads_ref = torch.autograd.grad(out_ref, [xr] + params, dy)
+    cap = E.AttnCapture(["up_8", "up_16"])
+    tape = E.Tape()
+    xv = E.Var(ops.latent_to_nhwc(x, dtype, 64))
+    out = eng.forward(tape, xv, t, ctx, capture=cap, added_cond=added)
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), out_ref) < 1e-4
+    assert cap.count == len(unet.attn_processors)
+    out.g = dy.permute(0, 2, 3, 1).contiguous()
+    tape.backward()
+    assert rel(ops.nhwc_to_nchw_f32(xv.g, 4), grads_ref[0]) < 1e-4
+    eg = eng.lora_grads()
+    assert len(eg) == len(params)
+    assert max(rel(a, b) for a, b in zip(eg, grads_ref[1:])) < 1e-3
+
+
+def test_vae_executor_matches_oracle(monkeypatch):
+    EMU.install(monkeypatch)
+    from comat_b200 import engine as E, ops
+    torch.manual_seed(5)
+    vae = sdm.AutoencoderKL(block_out_channels=(64, 64, 128, 128))
+    vae.requires_grad_(False)
+    eng = E.VAEDecoderEngine(vae, torch.float32)
+    z = torch.randn(1, 4, 8, 8)
+    zr = z.clone().requires_grad_(True)
+    ref = vae.decode(zr / vae.config.scaling_factor, return_dict=False)[0]
+    dy = torch.randn_like(ref)
+    gref = torch.autograd.grad(ref, zr, dy)[0]
+    tape = E.Tape()
+    zv = E.Var(ops.latent_to_nhwc(z, torch.float32, 64, 1.0 / vae.config.scaling_factor))
+    out = eng.forward(tape, zv)
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 3), ref) < 1e-4
+    out.g = dy.permute(0, 2, 3, 1).contiguous()
+    tape.backward()
+    assert rel(ops.nhwc_to_nchw_f32(zv.g, 4, 1.0 / vae.config.scaling_factor), gref) < 1e-4

@@ -1,0 +1,93 @@
+"""GPU parity: tcgen05 GEMM / implicit-GEMM conv (through the C ABI) vs a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item(), ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 160, 64, 0), (256, 320, 320, 0), (1000, 320, 768, 0), (4096, 1280, 640, 0),
+                                      (77, 640, 768, 0), (300, 128, 128, 0), (512, 30524 // 4 * 4, 768, 128),
+                                      (130, 4, 320, 0), (256, 96, 200, 0), (512, 512, 1024, 256), (384, 64, 64, 64)])
+def test_plain_gemm(M, N, K, bn, dtype):
+    from comat_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").to(dtype)
+    b = (torch.randn(N, K, device="cuda") / K ** 0.5).to(dtype)
+    out = ops.gemm([a], [b], force_bn=bn)
+    ref = a.float() @ b.float().t()
+    l2, mx = _rel(out.float(), ref)
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2
+    assert l2 < tol and mx < 4 * tol, (l2, mx)
+
+
+def test_gemm_identity_pattern_exact():
+    """small integers are exact in fp16/fp32: any descriptor / swizzle / row-mapping slip shows up as a wrong integer."""
+    from comat_b200 import ops
+    M, N, K = 256, 160, 128
+    a = torch.randint(-3, 4, (M, K), device="cuda").half()
+    b = torch.randint(-3, 4, (N, K), device="cuda").half()
+    out = ops.gemm([a], [b], out_fp32=True)
+    ref = a.float() @ b.float().t()
+    assert torch.equal(out, ref), (out - ref).abs().nonzero()[:8]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_epilogue_bias_rowvec_act_residual_and_lora_segment(dtype):
+    from comat_b200 import ops
+    torch.manual_seed(0)
+    M, N, K, r = 2 * 1024, 320, 320, 128
+    x = torch.randn(M, K, device="cuda").to(dtype)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(dtype)
+    down = (torch.randn(r, K, device="cuda") / r).to(dtype)
+    up = (torch.randn(N, r, device="cuda") * 0.05).to(dtype)
+    bias = torch.randn(N, device="cuda")
+    temb = torch.randn(2, N, device="cuda")
+    res = torch.randn(M, N, device="cuda").to(dtype)
+    t = ops.gemm([x], [down])                                   # x . down^T
+    for act, fn in (("none", lambda v: v), ("silu", F.silu), ("gelu", F.gelu)):
+        out = ops.gemm([x, t], [w, up], bias=bias, rowvec=temb, rows_per_group=1024, act=act, residual=res, alpha=0.5)
+        ref = fn(0.5 * (x.float() @ w.float().t() + t.float() @ up.float().t()) + bias + temb.repeat_interleave(1024, 0)) + res.float()
+        l2, mx = _rel(out.float(), ref)
+        assert l2 < (3e-3 if dtype == torch.float16 else 1.5e-2), (act, l2, mx)
+
+
+@pytest.mark.parametrize("n,H,W,C,Cout", [(2, 64, 64, 320, 320), (3, 32, 32, 640, 320), (2, 16, 16, 1280, 640), (3, 8, 8, 1280, 1280),
+                                          (1, 128, 128, 128, 128), (1, 256, 256, 64, 32), (2, 24, 40, 64, 64)])
+def test_conv3x3_implicit_gemm(n, H, W, C, Cout):
+    from comat_b200 import ops
+    torch.manual_seed(H + C)
+    dtype = torch.float16
+    x = torch.randn(n, H, W, C, device="cuda").to(dtype)
+    w = (torch.randn(Cout, C, 3, 3, device="cuda") / (9 * C) ** 0.5).to(dtype)
+    bias = torch.randn(Cout, device="cuda")
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()        # k = (kh*3+kw)*C + c
+    out = ops.gemm([x], [wk], bias=bias, conv_taps=ops.TAPS_3x3)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    l2, mx = _rel(out.float(), ref)
+    assert l2 < 2e-3, (l2, mx)
+
+
+def test_conv_with_concat_segments_and_1x1():
+    from comat_b200 import ops
+    torch.manual_seed(1)
+    dtype = torch.float16
+    n, H, W, C1, C2, Cout = 2, 32, 32, 640, 320, 640
+    h = torch.randn(n, H, W, C1, device="cuda").to(dtype)
+    s = torch.randn(n, H, W, C2, device="cuda").to(dtype)
+    w = (torch.randn(Cout, C1 + C2, 3, 3, device="cuda") / (9 * (C1 + C2)) ** 0.5).to(dtype)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * (C1 + C2)).contiguous()
+    out = ops.gemm([h, s], [wk, wk], b_koff=(0, C1), conv_taps=ops.TAPS_3x3, c_total=C1 + C2)
+    ref = F.conv2d(torch.cat([h, s], -1).float().permute(0, 3, 1, 2), w.float(), None, padding=1).permute(0, 2, 3, 1)
+    l2, mx = _rel(out.float(), ref)
+    assert l2 < 2e-3, (l2, mx)
+    w1 = (torch.randn(Cout, C1 + C2, device="cuda") / (C1 + C2) ** 0.5).to(dtype)
+    out1 = ops.gemm([h.reshape(-1, C1), s.reshape(-1, C2)], [w1, w1], b_koff=(0, C1))
+    ref1 = torch.cat([h, s], -1).reshape(-1, C1 + C2).float() @ w1.float().t()
+    assert _rel(out1.float(), ref1)[0] < 2e-3
