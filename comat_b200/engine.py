@@ -94,6 +94,7 @@ class LoRAW:
         self.dtype = dtype
         self.g_down = None
         self.g_up = None
+        self.wgrad = True
         self.refresh()
 
     def refresh(self):
@@ -184,12 +185,13 @@ def linear(tape, x: Var, lw: LinW, lora: Optional[LoRAW] = None, residual: Optio
                 _acc(residual, dy)
             if lora is not None:
                 u = ops.gemm([dy2], [lora.up16_t])                                   # dy . up      (M, r)
-                dyT, tT = ops.transpose16(dy2, 8), ops.transpose16(t, 8)
-                gu = ops.gemm([dyT], [tT], out_fp32=True)                            # d up   = dy^T t  (N, r)
-                uT, xT = ops.transpose16(u, 8), ops.transpose16(x2, 8)
-                gd = ops.gemm([uT], [xT], out_fp32=True)                             # d down = u^T x   (r, K)
-                lora.g_up = gu if lora.g_up is None else lora.g_up + gu
-                lora.g_down = gd if lora.g_down is None else lora.g_down + gd
+                if lora.wgrad:
+                    dyT, tT = ops.transpose16(dy2, 8), ops.transpose16(t, 8)
+                    gu = ops.gemm([dyT], [tT], out_fp32=True)                        # d up   = dy^T t  (N, r)
+                    uT, xT = ops.transpose16(u, 8), ops.transpose16(x2, 8)
+                    gd = ops.gemm([uT], [xT], out_fp32=True)                         # d down = u^T x   (r, K)
+                    lora.g_up = gu if lora.g_up is None else lora.g_up + gu
+                    lora.g_down = gd if lora.g_down is None else lora.g_down + gd
                 if x.needs_grad:
                     g = ops.gemm([dy2, u], [lw.wt, lora.down16_t], residual=x.g.reshape(-1, lw.k) if x.g is not None else None)
                     x.g = g.reshape(xv.shape)
@@ -446,6 +448,10 @@ class UNetEngine:
     def refresh_lora(self):
         for l in self.loras:
             l.refresh()
+
+    def set_lora_wgrad(self, flag: bool):
+        for l in self.loras:
+            l.wgrad = flag
 
     def zero_lora_grads(self):
         for l in self.loras:

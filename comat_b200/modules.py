@@ -1,0 +1,159 @@
+"""diffusers-shaped callables backed by the explicit executors (comat_b200/engine.py).
+
+``EngineUNet`` / ``EngineVAE`` expose exactly the surface the reference pipelines call —
+``unet(x, t, encoder_hidden_states=..., added_cond_kwargs=..., return_dict=False)[0]`` (TrainableSDPipeline.py:144-150)
+and ``vae.decode(z, return_dict=False)[0]`` (:220) — so they drop into ``TrainableSDPipeline`` unchanged.  Each call is ONE
+node in torch's autograd graph (plumbing for the latent chain); inside it the forward and backward are our own kernels
+driven by an explicit tape.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import engine as E
+from . import ops
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod: "EngineUNet", x, t, ehs, added, capture, n_lora, *lora_params):
+        eng = mod.engine
+        tape = E.Tape()
+        xv = E.Var(ops.latent_to_nhwc(x, eng.dtype, 64), needs_grad=ctx.needs_input_grad[1])
+        out = eng.forward(tape, xv, t, ehs.to(eng.dtype), capture=capture, added_cond=added)
+        eps = ops.nhwc_to_nchw_f32(out.v, mod.out_channels)
+        pvars = []
+        if capture is not None:
+            for place in ("down", "mid", "up"):
+                pvars.extend(capture.store[place])
+        ctx.tape, ctx.xv, ctx.out, ctx.pvars, ctx.mod = tape, xv, out, pvars, mod
+        ctx.x_dtype = x.dtype
+        ctx.wgrad = bool(mod.train_lora and any(p.requires_grad for p in lora_params))
+        return (eps.to(x.dtype), *[p.v for p in pvars])
+
+    @staticmethod
+    def backward(ctx, g_eps, *g_probs):
+        eng = ctx.mod.engine
+        ctx.out.g = g_eps.float().permute(0, 2, 3, 1).contiguous().to(eng.dtype)
+        for p, g in zip(ctx.pvars, g_probs):
+            if g is not None:
+                p.g = g.contiguous().float()
+        eng.zero_lora_grads()
+        eng.set_lora_wgrad(ctx.wgrad)
+        ctx.tape.backward()
+        gx = None
+        if ctx.needs_input_grad[1] and ctx.xv.g is not None:
+            gx = ops.nhwc_to_nchw_f32(ctx.xv.g, ctx.mod.in_channels).to(ctx.x_dtype)
+        lg = eng.lora_grads() if ctx.wgrad else [None] * len(eng.lora_grads())
+        ctx.tape = ctx.xv = ctx.out = ctx.pvars = None
+        return (None, gx, None, None, None, None, None, *lg)
+
+
+class EngineUNet(torch.nn.Module):
+    """Wraps a diffusers-shaped UNet2DConditionModel (parameters + LoRA layers live there, state-dict compatible) and
+    executes it with the B200 kernels."""
+
+    def __init__(self, unet: torch.nn.Module, dtype=torch.float16, train_lora: bool = True):
+        super().__init__()
+        self.ref = unet                       # parameter owner (LoRA fp32 masters are trained in place)
+        self.config = unet.config
+        self.engine = E.UNetEngine(unet, dtype)
+        self.in_channels = unet.config.in_channels
+        self.out_channels = unet.config.out_channels
+        self.train_lora = train_lora
+        self.capture: Optional[E.AttnCapture] = None
+        self.last_probs = None
+        self._dtype = dtype
+
+    @property
+    def dtype(self):
+        return torch.float32                  # interface dtype of latents / embeddings (fp32 chain, SURVEY 'numerics')
+
+    @property
+    def device(self):
+        return self.engine.te1.w.device
+
+    def lora_parameters(self):
+        return self.engine.lora_params()
+
+    def refresh_lora(self):
+        """call after every optimiser step: re-materialise the 16-bit LoRA operands from the fp32 masters."""
+        self.engine.refresh_lora()
+
+    def enable_gradient_checkpointing(self):
+        pass                                  # never recomputes: activations of K steps fit in 180 GB
+
+    def forward(self, sample, timestep, encoder_hidden_states, cross_attention_kwargs=None, added_cond_kwargs=None,
+                return_dict=False):
+        t = timestep if torch.is_tensor(timestep) else torch.tensor(timestep, device=sample.device)
+        params = self.engine.lora_params()
+        want_grad = torch.is_grad_enabled() and (sample.requires_grad or (self.train_lora and any(p.requires_grad for p in params)))
+        capture = self.capture
+        if capture is not None:
+            capture.reset()
+        if want_grad:
+            outs = _UNetFn.apply(self, sample, t, encoder_hidden_states, added_cond_kwargs, capture, len(params), *params)
+            eps, probs = outs[0], outs[1:]
+        else:
+            eng = self.engine
+            out = eng.forward(None, E.Var(ops.latent_to_nhwc(sample, eng.dtype, 64), False), t,
+                              encoder_hidden_states.to(eng.dtype), capture=capture, added_cond=added_cond_kwargs)
+            eps = ops.nhwc_to_nchw_f32(out.v, self.out_channels).to(sample.dtype)
+            probs = ()
+        if capture is not None:
+            # re-point the captured Vars' values at the autograd-visible tensors so losses differentiate through them
+            i = 0
+            for place in ("down", "mid", "up"):
+                for p in capture.store[place]:
+                    if i < len(probs):
+                        p.v = probs[i]
+                    i += 1
+        if not return_dict:
+            return (eps,)
+        return SimpleNamespace(sample=eps)
+
+
+class _VAEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod: "EngineVAE", z):
+        eng = mod.engine
+        tape = E.Tape()
+        zv = E.Var(ops.latent_to_nhwc(z, eng.dtype, 64))
+        out = eng.forward(tape, zv)
+        ctx.tape, ctx.zv, ctx.out, ctx.mod, ctx.zdtype = tape, zv, out, mod, z.dtype
+        return ops.nhwc_to_nchw_f32(out.v, 3).to(z.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.mod.engine
+        ctx.out.g = g.float().permute(0, 2, 3, 1).contiguous().to(eng.dtype)
+        ctx.tape.backward()
+        gz = ops.nhwc_to_nchw_f32(ctx.zv.g, 4).to(ctx.zdtype)
+        ctx.tape = ctx.zv = ctx.out = None
+        return None, gz
+
+
+class EngineVAE(torch.nn.Module):
+    def __init__(self, vae: torch.nn.Module, dtype=torch.float16):
+        super().__init__()
+        self.ref = vae
+        self.config = vae.config
+        self.engine = E.VAEDecoderEngine(vae, dtype)
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    def decode(self, z, return_dict=False):
+        if torch.is_grad_enabled() and z.requires_grad:
+            x = _VAEFn.apply(self, z)
+        else:
+            eng = self.engine
+            out = eng.forward(None, E.Var(ops.latent_to_nhwc(z, eng.dtype, 64), False))
+            x = ops.nhwc_to_nchw_f32(out.v, 3).to(z.dtype)
+        if not return_dict:
+            return (x,)
+        return SimpleNamespace(sample=x)

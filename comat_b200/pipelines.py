@@ -1,0 +1,218 @@
+"""Drop-in pipelines: same class names and ``forward`` keyword surface as the reference
+(TrainableSDPipeline.py:16-225 / :427-846, AttrConcenTrainableSDPipeline.py:28-279,
+AttrConcenTrainableSDXLPipeline.py:20-496), running the in-step DDPM rollout on the B200 executors.
+
+The pipelines are written from the reference's *behaviour* (gradient windows, CFG, DDPM step, attrcon split,
+SDXL quirks) — not its code — and add two keyword-only conveniences the parity tests need: ``noises`` (pre-drawn DDPM
+variance noise per step instead of the global RNG) and ``added_cond_kwargs`` passthrough.  Text encoding,
+spaCy parsing and GSAM masks are out of scope: prompts enter as ``prompt_embeds``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import engine as E
+from .modules import EngineUNet, EngineVAE
+from .scheduler import DDPMScheduler, rescale_noise_cfg
+
+
+class TrainableSDPipeline:
+    """SD1.5 differentiable sampler (TrainableSDPipeline.py:16-225)."""
+
+    is_sdxl = False
+
+    def __init__(self, vae: EngineVAE, unet: EngineUNet, scheduler: Optional[DDPMScheduler] = None, text_encoder=None,
+                 tokenizer=None, **_ignored):
+        self.vae, self.unet = vae, unet
+        self.scheduler = scheduler or DDPMScheduler()
+        self.text_encoder, self.tokenizer = text_encoder, tokenizer
+        self.controller: Optional[E.AttnCapture] = None
+        self.attn_dict: Dict[str, Dict[str, List[torch.Tensor]]] = {}
+
+    @property
+    def _execution_device(self):
+        return self.unet.device
+
+    def to(self, *a, **k):
+        return self
+
+    # -- prompt encoding is "next" scope: only the pre-computed-embedding path is implemented
+    def encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt=None,
+                      prompt_embeds=None, negative_prompt_embeds=None, lora_scale=None, clip_skip=None):
+        if prompt_embeds is None:
+            if self.text_encoder is None or self.tokenizer is None:
+                raise NotImplementedError("text encoders are outside the hot-path scope: pass prompt_embeds "
+                                          "(TrainableSDPipeline.py:227-424 is 'next' in SURVEY 8f)")
+            ids = self.tokenizer(prompt, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
+                                 return_tensors="pt").input_ids.to(device)
+            prompt_embeds = self.text_encoder(ids)[0]
+        prompt_embeds = prompt_embeds.to(device=device, dtype=torch.float32)
+        b, L, D = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, D)
+        if do_classifier_free_guidance:
+            if negative_prompt_embeds is None:
+                raise NotImplementedError("pass negative_prompt_embeds (the trainer always does, training_script.py:513-525)")
+            negative_prompt_embeds = negative_prompt_embeds.to(device=device, dtype=torch.float32)
+            negative_prompt_embeds = negative_prompt_embeds.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, D)
+        return prompt_embeds, negative_prompt_embeds
+
+    def prepare_latents(self, batch_size, num_channels, height, width, dtype, device, generator, latents=None):
+        shape = (batch_size, num_channels, height // 8, width // 8)
+        if latents is None:
+            latents = torch.randn(shape, generator=generator, dtype=dtype, device=generator.device if generator is not None else device)
+        return latents.to(device) * self.scheduler.init_noise_sigma
+
+    # ------------------------------------------------------------------------------------------------
+    def _unet(self, x, t, embeds, added):
+        return self.unet(x, t, encoder_hidden_states=embeds, added_cond_kwargs=added, return_dict=False)[0]
+
+    def _attrcon_forward(self, latents, t, prompt_embeds, added=None):
+        """AttrConcenTrainableSDPipeline.py:239-279: conditional half with attention capture, then the unconditional half."""
+        h = latents.shape[0] // 2
+        split = (lambda d, s: None if d is None else {k: v[s] for k, v in d.items()})
+        self.unet.capture = self.controller
+        try:
+            n_c = self._unet(latents[h:], t, prompt_embeds[h:], split(added, slice(h, None)))
+            maps, _ = self.controller.attn_dict()
+            self.attn_dict[str(int(t))] = maps
+        finally:
+            self.unet.capture = None
+        n_u = self._unet(latents[:h], t, prompt_embeds[:h], split(added, slice(0, h)))
+        return torch.cat([n_u, n_c], 0)
+
+    def forward(self, prompt=None, height: int = 512, width: int = 512, training_timesteps: Sequence[int] = (),
+                early_exit: bool = False, detach_gradient: bool = True, train_text_encoder: bool = False,
+                double_laststep: bool = False, bp_on_trained: bool = False, fast_training: bool = False,
+                num_inference_steps: int = 50, guidance_scale: float = 7.5, negative_prompt=None,
+                num_images_per_prompt: int = 1, eta: float = 0.0, generator=None, latents=None, prompt_embeds=None,
+                negative_prompt_embeds=None, output_type: str = "image", callback=None, callback_steps: int = 1,
+                cross_attention_kwargs=None, guidance_rescale: float = 0.0, return_latents: bool = False,
+                return_timestamped_latents: bool = False, return_early: bool = False, D_timesteps=None, batch=None,
+                attrcon_train_steps=None, *, noises=None, added_cond_kwargs=None, **sdxl_kwargs):
+        if double_laststep or fast_training or return_timestamped_latents:
+            raise NotImplementedError("double_laststep / fast_training / return_timestamped_latents are dead branches under "
+                                      "the trainer's constants (training_script.py:558-567; SURVEY A.2)")
+        batch_size = len(prompt) if isinstance(prompt, (list, tuple)) else (1 if isinstance(prompt, str) else prompt_embeds.shape[0])
+        device = self._execution_device
+        cfg = guidance_scale > 1.0
+        T = list(training_timesteps)
+        prev = torch.is_grad_enabled()
+        try:
+            torch.set_grad_enabled(False)
+            prompt_embeds, negative_prompt_embeds = self.encode_prompt(
+                prompt, device, num_images_per_prompt, cfg, negative_prompt, prompt_embeds=prompt_embeds,
+                negative_prompt_embeds=negative_prompt_embeds)
+            embeds = torch.cat([negative_prompt_embeds, prompt_embeds]) if cfg else prompt_embeds
+            added = self._added_cond(batch_size * num_images_per_prompt, height, width, cfg, added_cond_kwargs, sdxl_kwargs)
+            self.scheduler.set_timesteps(num_inference_steps, device=device)
+            timesteps = self.scheduler.timesteps
+            latents = self.prepare_latents(batch_size * num_images_per_prompt, 4, height, width, torch.float32, device,
+                                           generator, latents)
+            attr = T if attrcon_train_steps is None else list(attrcon_train_steps)
+            use_attr = self.controller is not None and attrcon_train_steps is not None
+            for i, t in enumerate(timesteps):
+                torch.set_grad_enabled(len(T) == 0 or i > min(T))                       # TrainableSDPipeline.py:133
+                x_in = torch.cat([latents] * 2) if cfg else latents
+                torch.set_grad_enabled(i in T)                                          # :138
+                detach = detach_gradient and not (i in T and bp_on_trained)             # :140-145
+                if self.is_sdxl:
+                    detach = True                                                       # :809
+                x_in = x_in.detach() if detach else x_in
+                if i in T and bp_on_trained and use_attr and i in attr:                 # AttrConcen...:159-167
+                    eps = self._attrcon_forward(x_in, t, embeds, added)
+                else:
+                    eps = self._unet(x_in, t, embeds, added)
+                if cfg:
+                    e_u, e_c = eps.chunk(2)
+                    eps = e_u + guidance_scale * (e_c - e_u)                            # :155-157
+                    if guidance_rescale > 0.0:
+                        eps = rescale_noise_cfg(eps, e_c, guidance_rescale)             # :159-161
+                torch.set_grad_enabled(len(T) == 0 or i >= min(T))                      # :163
+                out = self.scheduler.step(eps, t, latents, generator=generator,
+                                          variance_noise=None if noises is None else noises[i])
+                latents = out.prev_sample
+                if callback is not None and i % callback_steps == 0:
+                    callback(i, t, latents)
+                if len(T) > 0 and i == max(T) and early_exit:
+                    latents = out.pred_original_sample
+                    break
+            torch.set_grad_enabled(True)
+            if output_type == "latent":
+                return latents
+            image = self.vae.decode(latents / self.vae.config.scaling_factor, return_dict=False)[0]
+            if self.is_sdxl and return_latents:
+                return image, latents                                                   # un-rescaled: :838-840 (quirk kept)
+            image = image / 2 + 0.5                                                     # :223 (unclamped)
+            return (image, latents) if return_latents else image
+        finally:
+            torch.set_grad_enabled(prev)
+
+    def _added_cond(self, n, height, width, cfg, added_cond_kwargs, sdxl_kwargs):
+        return added_cond_kwargs
+
+
+class TrainableSDXLPipeline(TrainableSDPipeline):
+    """SDXL twin (TrainableSDPipeline.py:427-846): UNet input always detached, pooled-text + time-id conditioning."""
+
+    is_sdxl = True
+
+    def _get_add_time_ids(self, original_size, crops_coords_top_left, target_size, dtype=torch.float32):
+        add_time_ids = list(original_size + crops_coords_top_left + target_size)        # :428-449
+        want = self.unet.ref.add_embedding.linear_1.in_features
+        have = self.unet.config.addition_time_embed_dim * len(add_time_ids) + self._pooled_dim
+        if want != have:
+            raise ValueError(f"Model expects an added time embedding vector of length {want}, but a vector of {have} was created.")
+        return torch.tensor([add_time_ids], dtype=dtype)
+
+    def _added_cond(self, n, height, width, cfg, added_cond_kwargs, kw):
+        if added_cond_kwargs is not None:
+            return added_cond_kwargs
+        pooled, neg_pooled = kw.get("pooled_prompt_embeds"), kw.get("negative_pooled_prompt_embeds")
+        if pooled is None:
+            raise NotImplementedError("pass pooled_prompt_embeds (text encoders are outside the hot-path scope)")
+        self._pooled_dim = pooled.shape[-1]
+        osz = kw.get("original_size") or (height, width)
+        tsz = kw.get("target_size") or (height, width)
+        ids = self._get_add_time_ids(tuple(osz), tuple(kw.get("crops_coords_top_left", (0, 0))), tuple(tsz)).to(pooled.device)
+        ids = ids.repeat(n, 1)
+        if cfg:
+            pooled = torch.cat([neg_pooled, pooled], 0)
+            ids = torch.cat([ids, ids], 0)
+        return {"text_embeds": pooled.float(), "time_ids": ids.float()}
+
+
+class AttrConcenTrainableSDPipeline(TrainableSDPipeline):
+    """Adds cross-attention capture on ``attrcon_train_steps`` (AttrConcenTrainableSDPipeline.py:28-279).  The spaCy
+    noun/attribute alignment (:281-338) is out of scope: token-index lists are inputs to the loss."""
+
+
+class AttrConcenTrainableSDXLPipeline(TrainableSDXLPipeline):
+    """SDXL twin (AttrConcenTrainableSDXLPipeline.py:20-496)."""
+
+
+def register_attention_control(pipeline_or_unet, controller: E.AttnCapture):
+    """Product-side equivalent of attn_utils/tc_attn_utils.py:96-196: instead of monkey-patching every Attention.forward,
+    the cross-attention kernel exports P for the controller's places.  Returns the hooked attention-layer count."""
+    unet = getattr(pipeline_or_unet, "unet", pipeline_or_unet)
+    n = 0
+    for blocks in (unet.engine.down, [(unet.engine.mid[0], unet.engine.mid[1], None)], unet.engine.up):
+        for _, attns, _ in blocks:
+            for t in attns or []:
+                n += 2 * len(t.blocks)
+    controller.num_att_layers = n
+    if hasattr(pipeline_or_unet, "unet"):
+        pipeline_or_unet.controller = controller
+    return n
+
+
+AttentionStore = E.AttnCapture
+
+
+def get_cross_attn_map_from_unet(attention_store: E.AttnCapture, is_training_sd21=False, reses=(64, 32, 16, 8),
+                                 poses=("down", "mid", "up")):
+    """tc_attn_utils.py:198-216."""
+    if is_training_sd21:
+        reses = [int(1.5 * r) for r in reses]
+    return attention_store.attn_dict(reses, poses)[0]

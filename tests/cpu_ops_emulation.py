@@ -60,9 +60,10 @@ def groupnorm_fwd(x, gamma, beta, G, eps, silu):
 
 
 def groupnorm_bwd(x, dy, gamma, beta, mr, G, silu):
-    xr = x.double().requires_grad_(True)
-    y, _ = groupnorm_fwd(xr, gamma, beta, G, mr[2], silu)
-    return torch.autograd.grad(y, xr, dy.double())[0].to(x.dtype)
+    with torch.enable_grad():
+        xr = x.detach().double().requires_grad_(True)
+        y, _ = groupnorm_fwd(xr, gamma, beta, G, mr[2], silu)
+        return torch.autograd.grad(y, xr, dy.double())[0].to(x.dtype)
 
 
 def layernorm_fwd(x, gamma, beta, eps):
@@ -70,9 +71,10 @@ def layernorm_fwd(x, gamma, beta, eps):
 
 
 def layernorm_bwd(x, dy, gamma, mr):
-    xr = x.double().requires_grad_(True)
-    y = F.layer_norm(xr, (x.shape[-1],), gamma.double(), torch.zeros_like(gamma).double(), mr)
-    return torch.autograd.grad(y, xr, dy.double())[0].to(x.dtype)
+    with torch.enable_grad():
+        xr = x.detach().double().requires_grad_(True)
+        y = F.layer_norm(xr, (x.shape[-1],), gamma.double(), torch.zeros_like(gamma).double(), mr)
+        return torch.autograd.grad(y, xr, dy.double())[0].to(x.dtype)
 
 
 def geglu_fwd(hg):
@@ -81,9 +83,10 @@ def geglu_fwd(hg):
 
 
 def geglu_bwd(hg, dy):
-    r = hg.double().requires_grad_(True)
-    h, g = r.chunk(2, -1)
-    return torch.autograd.grad(h * F.gelu(g), r, dy.double())[0].to(hg.dtype)
+    with torch.enable_grad():
+        r = hg.detach().double().requires_grad_(True)
+        h, g = r.chunk(2, -1)
+        return torch.autograd.grad(h * F.gelu(g), r, dy.double())[0].to(hg.dtype)
 
 
 def elementwise(op, x, y=None, alpha=1.0, beta=1.0):
@@ -92,8 +95,9 @@ def elementwise(op, x, y=None, alpha=1.0, beta=1.0):
     if op == "silu":
         r = F.silu(xd)
     elif op == "silu_bwd":
-        xr = xd.requires_grad_(True)
-        r = torch.autograd.grad(F.silu(xr), xr, yd)[0]
+        with torch.enable_grad():
+            xr = xd.detach().requires_grad_(True)
+            r = torch.autograd.grad(F.silu(xr), xr, yd)[0]
     elif op == "gelu":
         r = F.gelu(xd)
     elif op == "add":
