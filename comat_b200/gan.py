@@ -1,0 +1,66 @@
+"""Fidelity-preservation GAN: the discriminator is a second (LoRA'd) SD1.5 UNet + a per-pixel Linear(4,1) head.
+
+Mirrors ``D_sd`` (training_utils/gan_sdxl.py:6-155) and ``load_discriminator`` (training_utils/gan_sd_model.py:8-14):
+``D_sd_pipeline_forward(training_latents, side='G'|'D', **kwargs)`` with the same kwargs the trainer passes
+(``negative_prompt_embeds``, ``num_inference_steps``, ``batch``).  The UNet runs on the B200 executor.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .modules import EngineUNet
+from .scheduler import DDPMScheduler
+
+
+class D_sd(torch.nn.Module):
+    def __init__(self, unet: EngineUNet, mlp: torch.nn.Module = None, scheduler: DDPMScheduler = None):
+        super().__init__()
+        self.unet = unet
+        self.mlp = mlp if mlp is not None else torch.nn.Sequential(torch.nn.Linear(4, 1))    # gan_sdxl.py:31-34 (fp32)
+        self.mlp.to(device=unet.device, dtype=torch.float32)
+        self.ori_scheduler = scheduler or DDPMScheduler()
+        self.D_parameters = None
+
+    def get_trainable_parameters(self):
+        self.D_parameters = list(self.unet.lora_parameters()) + list(self.mlp.parameters())   # gan_sdxl.py:37-40
+        return self.D_parameters
+
+    def set_D_sd_pipeline_lora(self, requires_grad=True):
+        for p in self.D_parameters or self.get_trainable_parameters():
+            p.requires_grad = requires_grad
+
+    def get_D_gt_noise(self, device, **kwargs):
+        return kwargs["batch"]["latents"].to(device, dtype=torch.float32)                     # gan_sdxl.py:46-48
+
+    def D_sd_pipeline_forward(self, training_latents, side="G", **kwargs):
+        device = training_latents.device
+        self.ori_scheduler.set_timesteps(kwargs["num_inference_steps"], device=device)
+        t = self.ori_scheduler.timesteps[-1]                                                  # "its own step" (=1)
+        null = kwargs["negative_prompt_embeds"]
+        if side == "G":                                                                       # gan_sdxl.py:52-89
+            self.set_D_sd_pipeline_lora(False)
+            x, cond = training_latents, null
+        elif side == "D":                                                                     # gan_sdxl.py:92-132
+            self.set_D_sd_pipeline_lora(True)
+            with torch.no_grad():
+                real = self.get_D_gt_noise(device, **kwargs)
+            x = torch.cat([training_latents.detach(), real])
+            cond = torch.cat([null, null])
+        else:
+            raise ValueError(side)
+        eps = self.unet(x, t, encoder_hidden_states=cond, return_dict=False)[0]
+        pred = self.mlp(eps.permute(0, 2, 3, 1).float())
+        target = torch.ones_like(pred)
+        if side == "D":
+            target[: target.shape[0] // 2] = 0
+        return F.binary_cross_entropy_with_logits(pred, target)
+
+
+def load_discriminator(args, unet: EngineUNet):
+    """gan_sd_model.py:8-14 keeps the reference quirk: the arch string has 'gan' stripped and only 'sd_1_5' resolves
+    (the default 'gan_sd_1_5' -> '_sd_1_5' resolves to nothing -> None)."""
+    name = args.gan_model_arch.replace("gan", "")
+    if name == "sd_1_5":
+        return D_sd(unet)
+    return None

@@ -29,6 +29,7 @@ class GemmParams(C.Structure):
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
 
 ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2}
+PROFILE = None      # bench.py sets {"flops": 0.0, "events": []} for one instrumented step (per-launch CUDA events)
 TAPS_3x3 = [(dh, dw) for dh in (-1, 0, 1) for dw in (-1, 0, 1)]
 
 
@@ -104,8 +105,15 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
     else:
         p.out16, p.out_ld = o2.data_ptr(), o2.stride(0)
     p.force_bn = force_bn
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(_lib.lib().comat_gemm(C.byref(p), _lib.stream_ptr()), "gemm")
     _lib.count_launch()
+    if PROFILE is not None:
+        e1.record()
+        PROFILE["events"].append((e0, e1))
+        PROFILE["flops"] += 2.0 * M * N * sum(a.shape[-1] for a in a_segs) * (len(conv_taps) if conv else 1)
     if conv:
         return out.reshape(n_img, H, W, N) if out.dim() == 2 else out
     return out

@@ -1,0 +1,158 @@
+"""Random-init weights at the real geometries + synthetic batches — there is no Hub / dataset access.
+
+Used by bench.py, smoke() and the GPU tests.  Everything is seeded; weights are created directly on the device.
+"""
+from __future__ import annotations
+
+import random
+from types import SimpleNamespace
+from typing import Dict
+
+import torch
+
+from . import containers as Cn
+
+
+def build_sd15(device, dtype=torch.float16, rank=128, seed=42, lora_up_std=0.0, tiny=False):
+    """(unet, vae) parameter containers at SD1.5 geometry (859.5 M + 49.5 M params), random init, LoRA installed."""
+    torch.manual_seed(seed)
+    with torch.device(device):
+        if tiny:
+            unet = Cn.UNet2DConditionModel(block_out_channels=(64, 128, 256, 256), heads=4, cross_attention_dim=64)
+            vae = Cn.AutoencoderKL(block_out_channels=(64, 64, 128, 128))
+        else:
+            unet = Cn.UNet2DConditionModel()
+            vae = Cn.AutoencoderKL()
+    unet.requires_grad_(False)
+    vae.requires_grad_(False)
+    unet.install_lora(rank, up_std=lora_up_std)
+    return unet, vae
+
+
+def build_sdxl_unet(device, rank=128, seed=42, tiny=False):
+    torch.manual_seed(seed)
+    with torch.device(device):
+        if tiny:
+            unet = Cn.UNet2DConditionModel(**{**Cn.SDXL_UNET, "block_out_channels": (64, 128, 256), "heads": (2, 4, 8),
+                                              "cross_attention_dim": 64, "transformer_layers": (1, 1, 2),
+                                              "addition_time_embed_dim": 8, "projection_class_embeddings_input_dim": 64})
+        else:
+            unet = Cn.UNet2DConditionModel(**Cn.SDXL_UNET)
+    unet.requires_grad_(False)
+    unet.install_lora(rank)
+    return unet
+
+
+def build_blip(device, dtype=torch.float16, seed=0, large=True, label_smoothing=0.1):
+    """Random-init HF BlipForConditionalGeneration at blip-image-captioning-large geometry: the parameter
+    container for the captioner.  Non-degenerate vision init (default initializer_range 1e-10 kills image gradients).
+    label_smoothing 0.1 follows the transformers==4.31.0 pin (requirements.txt:1)."""
+    from transformers import BlipConfig, BlipForConditionalGeneration
+    if large:
+        vis = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16)
+        txt = dict(hidden_size=768, encoder_hidden_size=1024, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12)
+    else:
+        vis = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2)
+        txt = dict(hidden_size=128, encoder_hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2)
+    vis.update(image_size=384, patch_size=16, initializer_range=0.02, attention_dropout=0.0)
+    txt.update(vocab_size=30524, max_position_embeddings=512, label_smoothing=label_smoothing, hidden_dropout_prob=0.0,
+               attention_probs_dropout_prob=0.0, bos_token_id=30522, pad_token_id=0, sep_token_id=102)
+    cfg = BlipConfig(vision_config=vis, text_config=txt)
+    cfg.label_smoothing = label_smoothing
+    torch.manual_seed(seed)
+    m = BlipForConditionalGeneration(cfg)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.startswith("vision_model") and p.ndim >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    m.eval().requires_grad_(False)
+    return m.to(device=device, dtype=dtype)
+
+
+def random_mask(g, size=512, empty=False):
+    m = torch.zeros(1, 1, size, size, dtype=torch.bool)
+    if empty:
+        return m
+    for _ in range(int(torch.randint(1, 3, (1,), generator=g))):
+        h = int(torch.randint(size // 5, size * 6 // 10, (1,), generator=g))
+        w = int(torch.randint(size // 5, size * 6 // 10, (1,), generator=g))
+        y = int(torch.randint(0, size - h, (1,), generator=g))
+        x = int(torch.randint(0, size - w, (1,), generator=g))
+        m[..., y:y + h, x:x + w] = True
+    return m
+
+
+def synthetic_batch(B: int, seed: int, ctx_dim: int = 768, res: int = 512, attrcon: bool = True, gan: bool = True,
+                    pinned: bool = False) -> Dict:
+    """Host-side batch (what a dataloader would hand over): prompt / null embeddings, BLIP token ids, attribute token
+    lists + per-word masks, 'real' latents for the discriminator."""
+    g = torch.Generator().manual_seed(seed)
+    rr = random.Random(seed)
+    lat = res // 8
+    b: Dict = {
+        "prompt_embeds": torch.randn(B, 77, ctx_dim, generator=g),
+        "null_embeds": torch.randn(1, 77, ctx_dim, generator=g).expand(B, -1, -1).contiguous(),
+    }
+    rows = []
+    for _ in range(B):
+        L = max(4, min(40, round(rr.gauss(14, 4))))
+        rows.append([101, 1037, 5855, 1997] + [rr.randrange(1000, 30000) for _ in range(L)] + [102])
+    T = max(len(r) for r in rows)
+    ids = torch.zeros(B, T, dtype=torch.long)
+    am = torch.zeros(B, T, dtype=torch.long)
+    for i, r in enumerate(rows):
+        ids[i, :len(r)] = torch.tensor(r)
+        am[i, :len(r)] = 1
+    b["blip"] = {"input_ids": ids, "attention_mask": am}
+    if attrcon:
+        words, masks = [], []
+        for _ in range(B):
+            nw = rr.randint(1, 3)
+            pos = rr.sample(range(1, 40), 9)
+            ws = []
+            for _ in range(nw):
+                k = rr.randint(1, 3)
+                ws.append([pos.pop() for _ in range(k)])
+            words.append(ws)
+            masks.append(torch.cat([random_mask(g, res, empty=(rr.random() < 0.1)) for _ in range(nw)]))   # (nw,1,res,res)
+        b["words"], b["masks_host"] = words, masks
+    if gan:
+        b["gan_null_embeds"] = b["null_embeds"].clone()
+        b["real_latents"] = torch.randn(B, 4, lat, lat, generator=g)
+    if pinned:
+        for k, v in list(b.items()):
+            if torch.is_tensor(v):
+                b[k] = v.pin_memory()
+        b["blip"] = {k: v.pin_memory() for k, v in b["blip"].items()}
+        if attrcon:
+            b["masks_host"] = [m.pin_memory() for m in b["masks_host"]]
+    return b
+
+
+def batch_to_device(b: Dict, device) -> (Dict, int):
+    """H2D copy of one step's inputs (non_blocking from pinned memory); returns (device batch, bytes copied)."""
+    out, nbytes = {}, 0
+    for k, v in b.items():
+        if torch.is_tensor(v):
+            out[k] = v.to(device, non_blocking=True)
+            nbytes += v.numel() * v.element_size()
+        elif k == "blip":
+            out[k] = {kk: vv.to(device, non_blocking=True) for kk, vv in v.items()}
+            nbytes += sum(vv.numel() * vv.element_size() for vv in v.values())
+        elif k == "masks_host":
+            dm = [m.to(device, non_blocking=True) for m in v]
+            nbytes += sum(m.numel() * m.element_size() for m in v)
+            out["masks"] = [[m[i:i + 1] for i in range(m.shape[0])] for m in dm]
+        else:
+            out[k] = v
+    return out, nbytes
+
+
+def default_args(**over):
+    from .arguments import parse_args
+    a = parse_args([])
+    for k, v in over.items():
+        setattr(a, k, v)
+    a.do_classifier_free_guidance = a.cfg_scale > 1.0
+    return a

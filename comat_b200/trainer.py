@@ -1,0 +1,122 @@
+"""One CoMat optimiser step — the body of ``Trainer.train``'s hot loop (training_script.py:556-694) on the B200 path.
+
+Behavioural mirror (same step selection, loss assembly, clip / AdamW hyper-parameters, D update), with the host
+synchronisations removed: no ``.item()`` / ``accelerator.gather`` per scalar — logs are returned as
+device tensors — and the DDP bucketed all-reduce (C2/C3) replaced by ONE NCCL all-reduce of the flat LoRA-gradient
+buffer per optimiser, folded with 1/world into the fused clip+AdamW kernel.
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, Optional
+
+import torch
+
+from . import attn_loss
+from .optim import FlatAdamW
+
+
+class CoMatTrainer:
+    def __init__(self, args, pipeline, caption_model, D=None, rng: Optional[random.Random] = None, process_group=None):
+        self.args, self.pipeline, self.caption_model, self.D = args, pipeline, caption_model, D
+        self.rng = rng or random.Random(args.seed)
+        self.G_parameters = list(pipeline.unet.lora_parameters())                 # training_utils/pipeline.py:123-143
+        self.optimizer = FlatAdamW(self.G_parameters, lr=args.learning_rate, betas=(args.adam_beta1, args.adam_beta2),
+                                   weight_decay=args.adam_weight_decay, eps=args.adam_epsilon,
+                                   max_grad_norm=args.max_grad_norm, process_group=process_group)
+        self.D_optimizer = None
+        if D is not None:
+            self.D_parameters = D.get_trainable_parameters()
+            self.D_optimizer = FlatAdamW(self.D_parameters, lr=args.learning_rate_D, betas=(args.adam_beta1_D, args.adam_beta2_D),
+                                         weight_decay=args.adam_weight_decay, eps=args.adam_epsilon,
+                                         max_grad_norm=args.max_grad_norm_D, process_group=process_group)
+            D.unet.refresh_lora()
+        pipeline.unet.refresh_lora()
+        self.attrcon = "attrcon" in args.pretrain_model_name
+        self.train_layer_ls = getattr(args, "train_layer_ls", None) or (
+            ["mid_8", "up_16", "up_32", "up_64"] if "sdxl" not in args.pretrain_model_name else ["mid_16", "up_16", "up_32"])
+        self.global_step = 0
+
+    # -- training_script.py:563-566, :589-590
+    def select_steps(self):
+        a = self.args
+        interval = a.total_step // a.K
+        max_start = a.total_step - interval * (a.K - 1) - 1
+        start = self.rng.randint(0, max_start)
+        steps = list(range(start, a.total_step, interval))
+        attr = self.rng.choices(steps, k=min(a.attrcon_train_steps, len(steps))) if self.attrcon else None
+        return steps, attr
+
+    def g_losses(self, batch: Dict) -> Dict[str, torch.Tensor]:
+        """forward part of the G step: rollout -> reward / GAN / attention losses -> total ``loss``."""
+        a, pipe = self.args, self.pipeline
+        steps, attr = batch.get("training_steps"), batch.get("attrcon_steps")
+        if steps is None:
+            steps, attr = self.select_steps()
+        kwargs = dict(prompt=batch.get("text"), prompt_embeds=batch["prompt_embeds"], height=a.resolution, width=a.resolution,
+                      training_timesteps=steps, detach_gradient=True, train_text_encoder=False,
+                      num_inference_steps=a.total_step, guidance_scale=a.cfg_scale, guidance_rescale=a.cfg_rescale,
+                      negative_prompt_embeds=batch["null_embeds"] if a.do_classifier_free_guidance else None,
+                      early_exit=False, return_latents=bool(a.gan_loss), latents=batch.get("init_latents"),
+                      noises=batch.get("noises"))
+        if self.attrcon:
+            kwargs["attrcon_train_steps"] = attr
+        if pipe.is_sdxl:
+            kwargs.update(pooled_prompt_embeds=batch["pooled_prompt_embeds"],
+                          negative_pooled_prompt_embeds=batch.get("pooled_null_embeds"))
+            out = pipe.forward(**kwargs)
+        else:
+            out = pipe.forward(bp_on_trained=True, double_laststep=False, fast_training=False, **kwargs)
+        image, training_latents = out if a.gan_loss else (out, None)
+        off = a.resolution // 224                                                   # :606-611
+        ox, oy = batch.get("crop") or (self.rng.randint(0, off), self.rng.randint(0, off))
+        size = a.resolution - off
+        rewards = self.caption_model(image[:, :, ox:ox + size, oy:oy + size], batch.get("text"), batch=batch.get("blip"))
+        logs = {k: v.detach() for k, v in rewards.items()}
+        loss = -rewards["total"].mean()                                              # :618
+        if a.gan_loss:
+            g = self.D.D_sd_pipeline_forward(training_latents, side="G", negative_prompt_embeds=batch["gan_null_embeds"],
+                                             num_inference_steps=a.total_step)
+            loss = loss + a.gan_loss_weight * g                                      # :620-625
+            logs["G_loss"] = g.detach()
+        if self.attrcon and pipe.attn_dict:
+            tok, pix = attn_loss.get_mask_loss(pipe.attn_dict, batch["words"], batch["masks"], self.train_layer_ls)
+            loss = loss + a.mask_token_loss_weight * tok + a.mask_pixel_loss_weight * pix     # :639-640
+            logs["token_loss"], logs["pixel_loss"] = tok.detach(), pix.detach()
+            pipe.attn_dict = {}                                                      # :642
+        if image.requires_grad:
+            norm_holder = {}
+
+            def record_grad(grad):                                                   # :644-651, without the host sync
+                n = grad.norm(2)
+                norm_holder["reward_norm"] = n
+                return grad / (n / 1e4) if a.norm_grad else grad
+            image.register_hook(record_grad)
+            logs["_norm_holder"] = norm_holder
+        logs["loss"] = loss
+        logs["_image"], logs["_latents"] = image, training_latents
+        return logs
+
+    def train_step(self, batch: Dict) -> Dict[str, torch.Tensor]:
+        a = self.args
+        logs = self.g_losses(batch)
+        loss = logs["loss"]
+        self.optimizer.zero_grad()                                                   # :658
+        loss.backward()                                                              # :659
+        handle = self.optimizer.all_reduce()                                         # the only data-path collective
+        self.optimizer.step(handle)                                                  # :661-663 (clip folded in)
+        self.pipeline.unet.refresh_lora()
+        out = {k: v for k, v in logs.items() if not k.startswith("_")}
+        out["step_loss"] = loss.detach()
+        out.update(logs.get("_norm_holder", {}))
+        if a.gan_loss:                                                               # :679-694
+            d_loss = self.D.D_sd_pipeline_forward(logs["_latents"].detach(), side="D", negative_prompt_embeds=batch["gan_null_embeds"],
+                                                  num_inference_steps=a.total_step, batch={"latents": batch["real_latents"]})
+            self.D_optimizer.zero_grad()
+            d_loss.backward()
+            h = self.D_optimizer.all_reduce()
+            self.D_optimizer.step(h)
+            self.D.unet.refresh_lora()
+            out["D_loss"] = d_loss.detach()
+        self.global_step += 1
+        return out

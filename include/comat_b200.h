@@ -163,6 +163,18 @@ int comat_copy2d16(const void* src, void* dst, long long rows, int cols, long lo
 int comat_latent_to_nhwc(const float* in, void* out, int n, int Cin, int HW, int Cpad, float scale, int dtype, void* stream);
 int comat_nhwc_to_nchw_f32(const void* in, float* out, int n, int Cout, int HW, int ld, float scale, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused clip + AdamW over ONE flat fp32 buffer (all LoRA A/B matrices), consuming the all-reduced gradient.
+ * Replaces accelerator.clip_grad_norm_ + torch.optim.AdamW.step (training_script.py:661-664, :692-694).
+ *   comat_grad_sumsq : out[0] = sum g^2 (device scalar, no host sync); partial = >= 1024 floats of scratch.
+ *   comat_adamw_clip : g' = g * grad_scale * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)); then torch-AdamW math
+ *                      (decoupled weight decay, bias correction by `step` >= 1).  max_norm <= 0 disables clipping.
+ * ------------------------------------------------------------------------------------------------------------ */
+int comat_grad_sumsq(const float* g, long long n, float* partial, float* out, void* stream);
+int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, float max_norm, float grad_scale, const float* sumsq,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif
