@@ -12,21 +12,58 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-IMPL = "torch"
+import ctypes as C
+
+from . import _lib
+
+IMPL = "native"          # forward: tcgen05 kernel when the shape is covered; backward: library path for now (round 1)
 LIBRARY_CALLS = 0
+NATIVE_HEAD_DIMS = (16, 32, 40, 64, 80, 160)
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+_lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp])
+_DT = {torch.float16: 1, torch.bfloat16: 2}
+
+
+def native_supported(q, k, heads, export_probs):
+    d = q.shape[-1] // heads
+    return (q.is_cuda and q.dtype in _DT and d in NATIVE_HEAD_DIMS and (not export_probs or k.shape[1] <= 128))
+
+
+def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False):
+    """tcgen05 fused attention forward (csrc/attention.cu).  returns (o, probs | None, lse | None)"""
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    n, Lq, Cq = q.shape
+    Lk = k.shape[1]
+    d = Cq // heads
+    L = _lib.lib()
+    L.comat_attention_workspace_bytes.restype = C.c_size_t
+    L.comat_attention_workspace_bytes.argtypes = [_i, _i, _i, _i]
+    ws = torch.empty(int(L.comat_attention_workspace_bytes(n, Lk, heads, d)), dtype=torch.uint8, device=q.device)
+    o = torch.empty_like(q)
+    probs = torch.empty(n * heads, Lq, Lk, dtype=torch.float32, device=q.device) if export_probs else None
+    lse = torch.empty(n * heads, Lq, dtype=torch.float32, device=q.device) if need_lse else None
+    _lib.check(L.comat_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                     None if probs is None else probs.data_ptr(), None if lse is None else lse.data_ptr(),
+                                     ws.data_ptr(), n, Lq, Lk, heads, d, float(d) ** -0.5, _DT[q.dtype], _lib.stream_ptr()),
+               "attention_fwd")
+    _lib.count_launch(2)
+    return o, probs, lse
 
 
 def _split(x, heads):
-    n, L, C = x.shape
-    return x.reshape(n, L, heads, C // heads).permute(0, 2, 1, 3)        # (n, h, L, d)
+    n, L, Cc = x.shape
+    return x.reshape(n, L, heads, Cc // heads).permute(0, 2, 1, 3)        # (n, h, L, d)
 
 
 def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
     """q: (n, Lq, C), k/v: (n, Lk, C) 16-bit.  returns (o (n, Lq, C), probs fp32 (n*heads, Lq, Lk) | None, saved)"""
     global LIBRARY_CALLS
+    if IMPL == "native" and native_supported(q, k, heads, export_probs):
+        o, probs, _ = attention_fwd_native(q, k, v, heads, export_probs)
+        return o, probs, ((q, k, v, heads, export_probs) if need_bwd else None)
     LIBRARY_CALLS += 1
-    n, Lq, C = q.shape
-    d = C // heads
+    n, Lq, Cc = q.shape
+    d = Cc // heads
     qh, kh, vh = _split(q, heads), _split(k, heads), _split(v, heads)
     probs = None
     if export_probs:
@@ -36,7 +73,7 @@ def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
         o = torch.matmul(p.to(q.dtype), vh)
     else:
         o = F.scaled_dot_product_attention(qh, kh, vh)
-    o = o.permute(0, 2, 1, 3).reshape(n, Lq, C).contiguous()
+    o = o.permute(0, 2, 1, 3).reshape(n, Lq, Cc).contiguous()
     saved = (q, k, v, heads, export_probs) if need_bwd else None
     return o, probs, saved
 
@@ -45,15 +82,15 @@ def attention_bwd(saved, do, dprobs):
     global LIBRARY_CALLS
     LIBRARY_CALLS += 1
     q, k, v, heads, export = saved
-    n, Lq, C = q.shape
-    d = C // heads
+    n, Lq, Cc = q.shape
+    d = Cc // heads
     with torch.enable_grad():
         q_, k_, v_ = (t.detach().requires_grad_(True) for t in (q, k, v))
         qh, kh, vh = _split(q_, heads), _split(k_, heads), _split(v_, heads)
         if export:
             s = torch.matmul(qh.float(), kh.float().transpose(-1, -2)) * d ** -0.5
             p = s.softmax(-1)
-            o = torch.matmul(p.to(q.dtype), vh).permute(0, 2, 1, 3).reshape(n, Lq, C)
+            o = torch.matmul(p.to(q.dtype), vh).permute(0, 2, 1, 3).reshape(n, Lq, Cc)
             outs, grads = [], []
             if do is not None:
                 outs.append(o); grads.append(do)
@@ -61,6 +98,6 @@ def attention_bwd(saved, do, dprobs):
                 outs.append(p.reshape(n * heads, Lq, -1)); grads.append(dprobs)
             dq, dk, dv = torch.autograd.grad(outs, (q_, k_, v_), grads)
         else:
-            o = F.scaled_dot_product_attention(qh, kh, vh).permute(0, 2, 1, 3).reshape(n, Lq, C)
+            o = F.scaled_dot_product_attention(qh, kh, vh).permute(0, 2, 1, 3).reshape(n, Lq, Cc)
             dq, dk, dv = torch.autograd.grad(o, (q_, k_, v_), do)
     return dq.contiguous(), dk.contiguous(), dv.contiguous()

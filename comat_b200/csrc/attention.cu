@@ -1,0 +1,358 @@
+// Fused multi-head attention forward on tcgen05:  O = softmax(scale * Q K^T) V  per (sample, head), flash-style
+// (online softmax over 128-key tiles; S and the per-tile P.V product live in TMEM), with
+//   * optional export of the normalised fp32 probabilities when all keys fit one tile (UNet cross-attention, 77 text
+//     tokens): this is the tensor the reference's hooked Attention.forward hands to AttentionStore
+//     (attn_utils/tc_attn_utils.py:126-145, :60-68) — written once, never re-read by this kernel;
+//   * the log-sum-exp per row saved for the backward pass.
+// Replaces F.scaled_dot_product_attention / baddbmm+softmax+bmm of diffusers' Attention and HF BLIP's eager attention.
+//
+// Layout: q (n, Lq, H*d), k (n, Lk, H*d) 16-bit token-major (the projection GEMMs' natural output); V is consumed as
+// V^T (n*H, d, Lk_pad) K-major (tiny pre-pass `kv_transpose`), so every MMA operand is a K-major 128B-swizzled tile.
+// Head dims that are not multiples of 64 (40, 80, 160) are handled by a 3-D tensor map {d, H, rows}: the TMA box is 64
+// wide and elements past d are out-of-bounds -> zero-filled, so no padded copies of Q/K exist.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 softmax / epilogue
+// (one thread per query row: row max / sum need no shuffles).
+#include "tc_common.cuh"
+
+namespace comat {
+
+constexpr int ATT_BM = 128;   // queries per CTA
+constexpr int ATT_BN = 128;   // keys per tile
+constexpr int ATT_THREADS = 192;
+
+struct AttnKP {
+  int Lq, Lk, H, d;
+  int n_kv_tiles;
+  float scale_log2;    // scale * log2(e)
+  float scale;
+  void* out;           // (n, Lq, H*d) 16-bit
+  float* probs;        // (n*H, Lq, Lk) fp32 or null (requires n_kv_tiles == 1)
+  float* lse;          // (n*H, Lq) fp32 or null
+  long long out_ld;    // H*d
+  uint32_t idesc_qk, idesc_pv;
+  int is_bf16;
+};
+
+template <int D>
+struct AttnCfg {
+  static constexpr int NKC = (D + 63) / 64;                 // 64-wide d chunks of Q / K
+  static constexpr int DN = (D + 15) / 16 * 16;             // P.V MMA N (output columns)
+  static constexpr int KSTEPS_QK = (D + 15) / 16;           // 16-wide k-steps actually issued
+  static constexpr int Q_BYTES = NKC * ATT_BM * 128;
+  static constexpr int K_BYTES = NKC * ATT_BN * 128;
+  static constexpr int VT_BYTES = 2 * DN * 128;             // two 64-key halves, DN rows of 128 B
+  static constexpr int KV_STAGE = K_BYTES + ((VT_BYTES + 1023) / 1024) * 1024;
+  static constexpr int P_BYTES = 2 * ATT_BM * 128;          // two 64-key halves
+  static constexpr int STAGES = (D > 128) ? 1 : 2;
+  static constexpr int BAR_OFF = Q_BYTES + STAGES * KV_STAGE + P_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int TMEM_COLS = (128 + DN) <= 256 ? 256 : 512;
+  static constexpr int O_COL = 128;                         // S at columns [0,128), O tile at [128, 128+DN)
+};
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+template <int D, typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmVt, const AttnKP p) {
+  using Cf = AttnCfg<D>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sKV = smem + Cf::Q_BYTES;
+  unsigned char* sP = sKV + Cf::STAGES * Cf::KV_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cf::BAR_OFF);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // STAGES
+  uint64_t* kv_empty = bars + 3;      // STAGES
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * ATT_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int NT = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < Cf::STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, Cf::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cf::Q_BYTES);
+      for (int c = 0; c < Cf::NKC; ++c) tma_load_3d(sQ + c * ATT_BM * 128, &tmQ, q_full, c * 64, h, b * p.Lq + m0);
+      int stage = 0, phase = 0;
+      for (int j = 0; j < NT; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        unsigned char* sK = sKV + stage * Cf::KV_STAGE;
+        unsigned char* sV = sK + Cf::K_BYTES;
+        mbar_expect_tx(&kv_full[stage], Cf::K_BYTES + Cf::VT_BYTES);
+        for (int c = 0; c < Cf::NKC; ++c) tma_load_3d(sK + c * ATT_BN * 128, &tmK, &kv_full[stage], c * 64, h, b * p.Lk + j * ATT_BN);
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_2d(sV + hf * Cf::DN * 128, &tmVt, &kv_full[stage], j * ATT_BN + hf * 64, (b * p.H + h) * p.d);
+        if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      auto issue_qk = [&](int stage) {
+        const uint32_t aK = smem_u32(sKV + stage * Cf::KV_STAGE);
+#pragma unroll
+        for (int ks = 0; ks < Cf::KSTEPS_QK; ++ks) {
+          const uint32_t off = (uint32_t)(ks / 4) * (ATT_BM * 128) + (uint32_t)(ks % 4) * 32;
+          umma_f16(tmem_base, make_kmajor_sw128_desc(aQ + off), make_kmajor_sw128_desc(aK + off), p.idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_qk(0);
+      int stage = 0, phase = 0;
+      for (int j = 0; j < NT; ++j) {
+        mbar_wait(p_full, j & 1);                 // P_j is in smem (and S_j has been fully read)
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sKV + stage * Cf::KV_STAGE + Cf::K_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < ATT_BN / 16; ++ks) {
+          const uint32_t offp = (uint32_t)(ks / 4) * (ATT_BM * 128) + (uint32_t)(ks % 4) * 32;
+          const uint32_t offv = (uint32_t)(ks / 4) * (Cf::DN * 128) + (uint32_t)(ks % 4) * 32;
+          umma_f16(tmem_base + Cf::O_COL, make_kmajor_sw128_desc(aP + offp), make_kmajor_sw128_desc(aV + offv), p.idesc_pv,
+                   ks > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[stage]);
+        if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
+        if (j + 1 < NT) {
+          mbar_wait(&kv_full[stage], phase);
+          tc_fence_after();
+          issue_qk(stage);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- softmax + epilogue: thread = query row ----------------
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const bool row_ok = (m0 + r) < p.Lq;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[Cf::DN];
+#pragma unroll
+    for (int i = 0; i < Cf::DN; ++i) o[i] = 0.f;
+    float m_used = 0.f;
+
+    for (int j = 0; j < NT; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kvalid = min(ATT_BN, p.Lk - j * ATT_BN);
+      // pass 1: row max
+      float mt = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+        if (c0 >= kvalid) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < kvalid) mt = fmaxf(mt, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_run, mt);
+      const float alpha = exp2f((m_run - m_new) * p.scale_log2);     // exp2(-inf) = 0 on the first tile
+      const float mneg = m_new * p.scale_log2;
+      // pass 2: p = exp2(s*sl2 - m*sl2), row sum, 16-bit P into swizzled smem (K-major, two 64-key halves)
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+        uint32_t v[32];
+        if (c0 < kvalid) {
+          tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+          tmem_ld_wait();
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0 = 0.f, e1 = 0.f;
+          if (c0 + i < kvalid) e0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - mneg);
+          if (c0 + i + 1 < kvalid) e1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - mneg);
+          lsum += e0 + e1;
+          pk[i / 2] = pack2<T>(e0, e1);
+        }
+        // 32 keys = 4 x 16-byte chunks of row r in half (c0/64): chunk index cc = (c0%64)/8 + q
+        unsigned char* base = sP + (c0 / 64) * (ATT_BM * 128) + (r / 8) * 1024 + (r % 8) * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cc = (c0 % 64) / 8 + q;
+          *reinterpret_cast<uint4*>(base + ((cc ^ (r % 8)) * 16)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      m_used = m_new;
+      tc_fence_before();
+      fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(p_full);
+      // accumulate O
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < Cf::DN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(trow + (uint32_t)(Cf::O_COL + c0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c0 + i] = o[c0 + i] * alpha + __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+    }
+    const float inv_l = 1.f / l_run;
+    if (row_ok) {
+      T* op = reinterpret_cast<T*>(p.out) + ((size_t)b * p.Lq + m0 + r) * p.out_ld + (size_t)h * p.d;
+      if constexpr (D % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < D; i += 8) {
+          uint4 u;
+          u.x = pack2<T>(o[i] * inv_l, o[i + 1] * inv_l); u.y = pack2<T>(o[i + 2] * inv_l, o[i + 3] * inv_l);
+          u.z = pack2<T>(o[i + 4] * inv_l, o[i + 5] * inv_l); u.w = pack2<T>(o[i + 6] * inv_l, o[i + 7] * inv_l);
+          *reinterpret_cast<uint4*>(op + i) = u;
+        }
+      } else {
+        for (int i = 0; i < D; ++i) op[i] = from_f32<T>(o[i] * inv_l);
+      }
+      if (p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.Lq + m0 + r] = m_used * p.scale + logf(l_run);
+    }
+    if (p.probs != nullptr) {
+      // single-tile case: S is still in TMEM; write softmax(S) as fp32 (n*H, Lq, Lk)
+      if (row_ok) {
+        float* pp = p.probs + (((size_t)b * p.H + h) * p.Lq + m0 + r) * p.Lk;
+        const float mneg = m_used * p.scale_log2;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.Lk; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Lk) pp[c0 + i] = exp2f(__uint_as_float(v[i]) * p.scale_log2 - mneg) * inv_l;
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cf::TMEM_COLS); }
+}
+
+// V (n, Lk, H*d) -> V^T (n*H, d, Lpad) with zero padding of keys >= Lk  (K-major B operand of P.V)
+template <typename T>
+__global__ void kv_transpose_kernel(const T* __restrict__ v, T* __restrict__ vt, int Lk, int H, int d, int Lpad) {
+  __shared__ T tile[32][33];
+  const int bh = blockIdx.z, b = bh / H, h = bh % H;
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int key = k0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (key < Lk && c < d) ? v[((size_t)b * Lk + key) * (H * d) + h * d + c] : from_f32<T>(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, key = k0 + threadIdx.x;
+    if (c < d && key < Lpad) vt[((size_t)bh * d + c) * Lpad + key] = tile[threadIdx.x][j];
+  }
+}
+
+template <int D, typename T>
+static int launch_attn(const CUtensorMap* maps, const AttnKP& kp, dim3 grid, cudaStream_t st) {
+  using Cf = AttnCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    COMAT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::TOTAL));
+    configured = true;
+  }
+  attn_fwd_kernel<D, T><<<grid, ATT_THREADS, Cf::TOTAL, st>>>(maps[0], maps[1], maps[2], kp);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+}  // namespace comat
+using namespace comat;
+
+extern "C" size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d) {
+  const int Lpad = (Lk + 127) / 128 * 128;
+  return (size_t)n * H * d * Lpad * 2 + 256;
+}
+
+extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
+                                   int n, int Lq, int Lk, int H, int d, float scale, int dtype, void* stream) {
+  if (!q || !k || !v || !out || !workspace || n <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return COMAT_ERR_INVALID;
+  if (d != 40 && d != 64 && d != 80 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
+  if (dtype != COMAT_F16 && dtype != COMAT_BF16) return COMAT_ERR_UNSUPPORTED;
+  if (probs && Lk > ATT_BN) return COMAT_ERR_UNSUPPORTED;
+  if (((H * d) % 8) != 0 || (d % 8) != 0) return COMAT_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Lpad = (Lk + 127) / 128 * 128;
+  void* vt = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  {
+    dim3 g((Lpad + 31) / 32, (d + 31) / 32, n * H), blk(32, 8);
+    kv_transpose_kernel<__half><<<g, blk, 0, st>>>((const __half*)v, (__half*)vt, Lk, H, d, Lpad);
+  }
+  AttnKP kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.Lq = Lq; kp.Lk = Lk; kp.H = H; kp.d = d; kp.n_kv_tiles = (Lk + ATT_BN - 1) / ATT_BN;
+  kp.scale = scale; kp.scale_log2 = scale * 1.4426950408889634f;
+  kp.out = out; kp.probs = probs; kp.lse = lse; kp.out_ld = (long long)H * d; kp.is_bf16 = dtype == COMAT_BF16;
+  const int fmt = kp.is_bf16 ? 1 : 0;
+  const int DN = (d + 15) / 16 * 16;
+  kp.idesc_qk = make_idesc_f16(ATT_BM, ATT_BN, fmt);
+  kp.idesc_pv = make_idesc_f16(ATT_BM, DN, fmt);
+  CUtensorMap maps[3];
+  {
+    const uint64_t dq[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * Lq};
+    const uint64_t sq[2] = {(uint64_t)d * 2, (uint64_t)H * d * 2};
+    const uint32_t bq[3] = {64, 1, (uint32_t)ATT_BM};
+    if (!make_tmap_16bit(&maps[0], q, 3, dq, sq, bq)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    const uint64_t dk[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * Lk};
+    const uint32_t bk[3] = {64, 1, (uint32_t)ATT_BN};
+    if (!make_tmap_16bit(&maps[1], k, 3, dk, sq, bk)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    const uint64_t dv[2] = {(uint64_t)Lpad, (uint64_t)n * H * d};
+    const uint64_t sv[1] = {(uint64_t)Lpad * 2};
+    const uint32_t bv[2] = {64, (uint32_t)DN};
+    if (!make_tmap_16bit(&maps[2], vt, 2, dv, sv, bv)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+  }
+  dim3 grid((Lq + ATT_BM - 1) / ATT_BM, H, n);
+#define ATT_CASE(DD)                                                                      \
+  case DD:                                                                                \
+    return kp.is_bf16 ? launch_attn<DD, __nv_bfloat16>(maps, kp, grid, st) : launch_attn<DD, __half>(maps, kp, grid, st);
+  switch (d) {
+    ATT_CASE(16) ATT_CASE(32) ATT_CASE(40) ATT_CASE(64) ATT_CASE(80) ATT_CASE(160)
+  }
+#undef ATT_CASE
+  return COMAT_ERR_UNSUPPORTED;
+}

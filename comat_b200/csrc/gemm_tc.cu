@@ -42,12 +42,19 @@ struct GemmKP {
   long long out32_ld;
   uint32_t idesc;
   int is_bf16;
+  int tma_store;     // 1: epilogue stages 16-bit tiles in (free) pipeline smem and writes them with TMA bulk tensor stores
 };
 
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == 1) return x / (1.f + __expf(-x));                       // SiLU
   if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));  // exact GELU (F.gelu default)
   return x;
+}
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
+  if (is_bf16) { const __nv_bfloat162 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&t); }
+  const __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
 }
 
 template <int BN>
@@ -68,7 +75,8 @@ struct GemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmKP p) {
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
   using S = GemmSmem<BN, STAGES>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -181,9 +189,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (row_ok) {
-        const int ncol = min(32, p.N - (n0 + c0));
-        if (ncol > 0) {
+      const int ncol = min(32, p.N - (n0 + c0));
+      if (p.tma_store || (row_ok && ncol > 0)) {
+        {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -191,7 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (rv != nullptr && j < ncol) x += rv[n0 + c0 + j];
             f[j] = act_apply(x, p.act);
           }
-          if (p.residual != nullptr) {
+          if (p.residual != nullptr && row_ok && ncol > 0) {
             const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
             if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
@@ -217,23 +225,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
             }
           }
-          if (p.out16 != nullptr) {
+          if (p.out16 != nullptr && !p.tma_store) {
             uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n0 + c0;
             if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 uint32_t w[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float a = f[j4 * 8 + e * 2], b = f[j4 * 8 + e * 2 + 1];
-                  if (p.is_bf16) {
-                    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-                    w[e] = *reinterpret_cast<const uint32_t*>(&t);
-                  } else {
-                    const __half2 t = __floats2half2_rn(a, b);
-                    w[e] = *reinterpret_cast<const uint32_t*>(&t);
-                  }
-                }
+                for (int e = 0; e < 4; ++e) w[e] = pack16(f[j4 * 8 + e * 2], f[j4 * 8 + e * 2 + 1], p.is_bf16);
                 *reinterpret_cast<uint4*>(op + j4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
               }
             } else {
@@ -243,7 +242,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
             }
           }
-          if (p.out32 != nullptr) {
+          if (p.tma_store) {
+            // panel (c0/32): [128 rows][64 B], 64B-swizzled (16B chunk q of row r lives at q ^ ((r>>1)&3))
+            unsigned char* prow = smem + (c0 / 32) * 8192 + r * 64;
+            const int sw = (r >> 1) & 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack16(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1], p.is_bf16);
+              *reinterpret_cast<uint4*>(prow + ((q ^ sw) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          if (p.out32 != nullptr && row_ok) {
             float* op = p.out32 + m * p.out32_ld + n0 + c0;
             for (int j = 0; j < ncol; ++j) op[j] = f[j];
           }
@@ -251,6 +262,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
     tc_fence_before();
+    if (p.tma_store) {
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the 4 epilogue warps only
+      if (warp == 2 && lane == 0) {
+#pragma unroll 1
+        for (int pn = 0; pn < BN / 32; ++pn) {
+          if (n0 + pn * 32 >= p.N) break;
+          if (p.conv) tma_store_4d(&tmO, smem + pn * 8192, n0 + pn * 32, w0, h0, img0);
+          else        tma_store_2d(&tmO, smem + pn * 8192, n0 + pn * 32, m0);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();                                 // smem must stay valid until the stores have read it
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -267,7 +292,7 @@ static int launch_gemm(const CUtensorMap* maps, const GemmKP& kp, dim3 grid, cud
     COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
+  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -298,7 +323,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   kp.out32 = g->out32; kp.out32_ld = g->out32_ld; kp.is_bf16 = g->dtype == COMAT_BF16;
   const int BN = pick_bn(g->N, g->force_bn);
   kp.idesc = make_idesc_f16(BM, BN, kp.is_bf16 ? 1 : 0);
-  CUtensorMap maps[4];
+  CUtensorMap maps[5];
   memset(maps, 0, sizeof(maps));
   dim3 grid;
   kp.conv = g->conv ? 1 : 0;
@@ -353,6 +378,26 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
       const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
       if (!make_tmap_16bit(&maps[2 + s], g->b[s], 2, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
     }
+  }
+  // TMA-store epilogue (default): needs a 16-bit output with 16-byte aligned base and row pitch
+  static int epi_mode = -1;
+  if (epi_mode < 0) { const char* e = getenv("COMAT_GEMM_EPILOGUE"); epi_mode = (e && !strcmp(e, "direct")) ? 0 : 1; }
+  kp.tma_store = 0;
+  if (epi_mode == 1 && g->out16 && !g->out32 && (g->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(g->out16) & 15) == 0 &&
+      (!kp.conv || g->out_ld == g->N)) {
+    bool ok;
+    if (kp.conv) {
+      const uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->W, (uint64_t)g->H, (uint64_t)g->n_img};
+      const uint64_t str[3] = {(uint64_t)g->out_ld * 2, (uint64_t)g->out_ld * 2 * g->W, (uint64_t)g->out_ld * 2 * g->W * g->H};
+      const uint32_t box[4] = {32u, (uint32_t)kp.TW, (uint32_t)kp.TH, (uint32_t)kp.TN};
+      ok = make_tmap_16bit(&maps[4], g->out16, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    } else {
+      const uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
+      const uint64_t str[1] = {(uint64_t)g->out_ld * 2};
+      const uint32_t box[2] = {32u, (uint32_t)BM};
+      ok = make_tmap_16bit(&maps[4], g->out16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    }
+    kp.tma_store = ok ? 1 : 0;
   }
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {

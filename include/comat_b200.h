@@ -175,6 +175,20 @@ int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, 
                      float eps, float weight_decay, int step, float max_norm, float grad_scale, const float* sumsq,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused multi-head attention forward (tcgen05, flash-style):  out = softmax(scale * q k^T) v  per (sample, head).
+ * Replaces the hooked Attention.forward arithmetic (attn_utils/tc_attn_utils.py:126-145: baddbmm + softmax + bmm) and
+ * F.scaled_dot_product_attention inside diffusers' Attention / HF BLIP attention.
+ *   q (n, Lq, H*d), k/v (n, Lk, H*d), out (n, Lq, H*d): 16-bit token-major.  d in {16, 32, 40, 64, 80, 160}.
+ *   probs : optional fp32 (n*H, Lq, Lk) export of the normalised probabilities (Lk <= 128) — the tensor AttentionStore
+ *           clones for the attention-map loss (tc_attn_utils.py:60-68); null to skip.
+ *   lse   : optional fp32 (n*H, Lq) log-sum-exp (saved for backward); null to skip.
+ *   workspace: comat_attention_workspace_bytes() bytes (V^T staging).
+ * ------------------------------------------------------------------------------------------------------------ */
+size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d);
+int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
+                        int n, int Lq, int Lk, int H, int d, float scale, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
