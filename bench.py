@@ -50,6 +50,8 @@ def parse():
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--no_gan", action="store_true")
     p.add_argument("--no_attrcon", action="store_true")
+    p.add_argument("--profile_step", action="store_true",
+                   help="run warm-up then ONE step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     return p.parse_args()
 
 
@@ -240,6 +242,13 @@ def main():
 
     for i in range(a.warmup):
         trainer.train_step(dev_batches[i % len(dev_batches)])
+    if a.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer.train_step(dev_batches[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
         clocks.start()

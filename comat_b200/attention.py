@@ -21,6 +21,8 @@ LIBRARY_CALLS = 0
 NATIVE_HEAD_DIMS = (16, 32, 40, 64, 80, 160)
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 _lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp])
+_lib.register_signature("comat_attention_bwd", [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _i, _vp])
+NATIVE_BWD = True
 _DT = {torch.float16: 1, torch.bfloat16: 2}
 
 
@@ -59,8 +61,12 @@ def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
     """q: (n, Lq, C), k/v: (n, Lk, C) 16-bit.  returns (o (n, Lq, C), probs fp32 (n*heads, Lq, Lk) | None, saved)"""
     global LIBRARY_CALLS
     if IMPL == "native" and native_supported(q, k, heads, export_probs):
-        o, probs, _ = attention_fwd_native(q, k, v, heads, export_probs)
-        return o, probs, ((q, k, v, heads, export_probs) if need_bwd else None)
+        o, probs, lse = attention_fwd_native(q, k, v, heads, export_probs, need_lse=need_bwd and NATIVE_BWD)
+        if not need_bwd:
+            return o, probs, None
+        if NATIVE_BWD:
+            return o, probs, ("native", q.contiguous(), k.contiguous(), v.contiguous(), o, lse, probs, heads)
+        return o, probs, (q, k, v, heads, export_probs)
     LIBRARY_CALLS += 1
     n, Lq, Cc = q.shape
     d = Cc // heads
@@ -78,8 +84,32 @@ def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
     return o, probs, saved
 
 
+def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs):
+    """tcgen05 fused attention backward (csrc/attention_bwd.cu): (dq, dk, dv)."""
+    n, Lq, Cq = q.shape
+    Lk = k.shape[1]
+    d = Cq // heads
+    L = _lib.lib()
+    L.comat_attention_bwd_workspace_bytes.restype = C.c_size_t
+    L.comat_attention_bwd_workspace_bytes.argtypes = [_i, _i, _i, _i, _i]
+    ws = torch.empty(int(L.comat_attention_bwd_workspace_bytes(n, Lq, Lk, heads, d)), dtype=torch.uint8, device=q.device)
+    do = torch.zeros_like(o) if do is None else do.contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    if dprobs is not None:
+        dprobs = dprobs.contiguous().float()
+    _lib.check(L.comat_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                     None if dprobs is None else probs.data_ptr(), None if dprobs is None else dprobs.data_ptr(),
+                                     dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), n, Lq, Lk, heads, d,
+                                     float(d) ** -0.5, _DT[q.dtype], _lib.stream_ptr()), "attention_bwd")
+    _lib.count_launch(6)
+    return dq, dk, dv
+
+
 def attention_bwd(saved, do, dprobs):
     global LIBRARY_CALLS
+    if saved[0] == "native":
+        _, q, k, v, o, lse, probs, heads = saved
+        return attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs)
     LIBRARY_CALLS += 1
     q, k, v, heads, export = saved
     n, Lq, Cc = q.shape

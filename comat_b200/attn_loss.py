@@ -173,7 +173,7 @@ class _AttnMapLossFn(torch.autograd.Function):
         state = torch.empty(plan.state_floats, dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().comat_attnmap_loss_fwd(C.byref(plan.c), _lib.ptr(loss2), _lib.ptr(state), plan.state_floats,
                                                      _lib.ptr(_counter(dev)), _lib.stream_ptr()), "attnmap_loss_fwd")
-        _lib.count_launch(2)
+        _lib.count_launch(3)
         ctx.plan, ctx.state = plan, state
         ctx.shapes = [m.shape for m in maps]
         return loss2

@@ -1,0 +1,439 @@
+// Fused attention backward on tcgen05 (flash-style recomputation, no P materialised in HBM).
+//
+//   P = exp(scale * Q K^T - lse),  dP = dO V^T (+ dP_ext),  D_i = sum_j P_ij dP_ij,  dS = P o (dP - D)
+//   dV = P^T dO,   dK = scale * dS^T Q,   dQ = scale * dS K
+//
+// dP_ext is the gradient that the attention-map loss sends into the exported cross-attention probabilities
+// (the reference differentiates through the tensor its hook stored: attn_utils/tc_attn_utils.py:142-143, SURVEY "hard parts").
+//
+// Two launches of one templated kernel, no atomics, bit-reproducible:
+//   MODE 0 (dQ)    : CTA = 128 queries, loops over key tiles   : S = Q K^T, dP = dO V^T  -> dS (smem) -> dQ += dS K
+//   MODE 1 (dK,dV) : CTA = 128 keys,    loops over query tiles : S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (smem)
+//                                                                 -> dV += P^T dO,  dK += dS^T Q
+// Every MMA operand is a K-major, 128B-swizzled tile: the "transposed" B operands (K^T, Q^T, dO^T per head) come from a
+// small pre-pass, S / dP and the dQ / dK / dV accumulators live in TMEM (<= 448 of 512 columns), the elementwise softmax
+// backward is done by 128 row-owning threads.
+#include "tc_common.cuh"
+
+namespace comat {
+
+constexpr int AB_ROWS = 128;
+constexpr int AB_THREADS = 192;
+
+struct AttnBwdKP {
+  int Lq, Lk, H, d;
+  int Lq_pad, Lk_pad;
+  int n_inner;
+  float scale, scale_log2;
+  const float* lse_pad;   // (n*H, Lq_pad), padded with +1e30
+  const float* D_pad;     // (n*H, Lq_pad), padded with 0
+  const float* dp_ext;    // (n*H, Lq, Lk) fp32 or null
+  void* out0;             // MODE 0: dQ (n, Lq, H*d) ; MODE 1: dK (n, Lk, H*d)
+  void* out1;             // MODE 1: dV
+  long long out_ld;
+  uint32_t idesc_s, idesc_acc;
+};
+
+template <int D, int MODE>
+struct ABCfg {
+  static constexpr int NKC = (D + 63) / 64;
+  static constexpr int DN = (D + 15) / 16 * 16;
+  static constexpr int KSTEPS = (D + 15) / 16;
+  static constexpr int BY = (D <= 64) ? 128 : 64;                  // inner tile width
+  static constexpr int NHALF = BY / 64;
+  static constexpr int NT = (MODE == 0) ? 1 : 2;                   // transposed streamed tiles
+  static constexpr int NP = (MODE == 0) ? 1 : 2;                   // smem A tiles produced by the row threads
+  static constexpr int RES_BYTES = 2 * NKC * AB_ROWS * 128;
+  static constexpr int NAT_BYTES = NKC * BY * 128;                 // one natural streamed tile
+  static constexpr int TR_BYTES = NHALF * DN * 128;                // one transposed streamed tile
+  static constexpr int VEC_BYTES = (MODE == 1) ? 2 * BY * 4 : 0;   // lse / D slices of the inner tile
+  static constexpr int STAGE_BYTES = ((2 * NAT_BYTES + NT * TR_BYTES + VEC_BYTES + 1023) / 1024) * 1024;
+  static constexpr int PD_BYTES = NP * NHALF * AB_ROWS * 128;
+  static constexpr int FIXED = RES_BYTES + PD_BYTES + 256 + 1024;
+  static constexpr int STAGES = (FIXED + 2 * STAGE_BYTES <= 225 * 1024) ? 2 : 1;
+  static constexpr int BAR_OFF = RES_BYTES + STAGES * STAGE_BYTES + PD_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int COL_S = 0, COL_DP = BY, COL_ACC0 = 2 * BY, COL_ACC1 = 2 * BY + DN;
+  static constexpr int TMEM_COLS = 512;
+};
+
+template <typename T>
+__device__ __forceinline__ uint32_t ab_pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t ab_pack2<__half>(float a, float b) { const __half2 t = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&t); }
+template <>
+__device__ __forceinline__ uint32_t ab_pack2<__nv_bfloat16>(float a, float b) { const __nv_bfloat162 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&t); }
+
+// 16-byte chunk `cc` (8 elements) of row r in a [128 x 64] K-major 128B-swizzled half tile
+__device__ __forceinline__ unsigned char* sw128_chunk(unsigned char* half_base, int r, int cc) {
+  return half_base + (r / 8) * 1024 + (r % 8) * 128 + ((cc ^ (r % 8)) * 16);
+}
+
+template <int D, int MODE, typename T>
+__global__ void __launch_bounds__(AB_THREADS)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 1: MODE0 Q   | MODE1 K      (box 128 rows)
+                const __grid_constant__ CUtensorMap tmA2,   // resident natural 2: MODE0 dO  | MODE1 V
+                const __grid_constant__ CUtensorMap tmB1,   // streamed natural 1: MODE0 K   | MODE1 Q      (box BY rows)
+                const __grid_constant__ CUtensorMap tmB2,   // streamed natural 2: MODE0 V   | MODE1 dO
+                const __grid_constant__ CUtensorMap tmT1,   // streamed transposed: MODE0 K^T | MODE1 dO^T  (box {64, DN})
+                const __grid_constant__ CUtensorMap tmT2,   //                      MODE1 Q^T
+                const AttnBwdKP p) {
+  using Cf = ABCfg<D, MODE>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sRes = smem;
+  unsigned char* sStage = smem + Cf::RES_BYTES;
+  unsigned char* sPD = sStage + Cf::STAGES * Cf::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cf::BAR_OFF);
+  uint64_t* res_full = bars;
+  uint64_t* st_full = bars + 1;     // [2]
+  uint64_t* st_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* acc_full = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * AB_ROWS;          // first query (MODE 0) / key (MODE 1) of this CTA
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.H + h;
+  const int NI = p.n_inner;
+  const int Lx = (MODE == 0) ? p.Lq : p.Lk;     // rows of the outer dimension
+  const int Ly = (MODE == 0) ? p.Lk : p.Lq;     // inner dimension
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(res_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, Cf::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(res_full, Cf::RES_BYTES);
+      for (int c = 0; c < Cf::NKC; ++c) {
+        tma_load_3d(sRes + c * AB_ROWS * 128, &tmA1, res_full, c * 64, h, b * Lx + x0);
+        tma_load_3d(sRes + (Cf::NKC + c) * AB_ROWS * 128, &tmA2, res_full, c * 64, h, b * Lx + x0);
+      }
+      int stage = 0, phase = 0;
+      for (int it = 0; it < NI; ++it) {
+        mbar_wait(&st_empty[stage], phase ^ 1);
+        unsigned char* st = sStage + stage * Cf::STAGE_BYTES;
+        mbar_expect_tx(&st_full[stage], 2 * Cf::NAT_BYTES + Cf::NT * Cf::TR_BYTES + Cf::VEC_BYTES);
+        const int y0 = it * Cf::BY;
+        for (int c = 0; c < Cf::NKC; ++c) {
+          tma_load_3d(st + c * Cf::BY * 128, &tmB1, &st_full[stage], c * 64, h, b * Ly + y0);
+          tma_load_3d(st + Cf::NAT_BYTES + c * Cf::BY * 128, &tmB2, &st_full[stage], c * 64, h, b * Ly + y0);
+        }
+        unsigned char* tr = st + 2 * Cf::NAT_BYTES;
+        for (int hf = 0; hf < Cf::NHALF; ++hf) {
+          tma_load_2d(tr + hf * Cf::DN * 128, &tmT1, &st_full[stage], y0 + hf * 64, bh * p.d);
+          if (MODE == 1) tma_load_2d(tr + Cf::TR_BYTES + hf * Cf::DN * 128, &tmT2, &st_full[stage], y0 + hf * 64, bh * p.d);
+        }
+        if (MODE == 1) {
+          unsigned char* vec = tr + Cf::NT * Cf::TR_BYTES;
+          bulk_g2s(vec, p.lse_pad + (size_t)bh * p.Lq_pad + y0, Cf::BY * 4, &st_full[stage]);
+          bulk_g2s(vec + Cf::BY * 4, p.D_pad + (size_t)bh * p.Lq_pad + y0, Cf::BY * 4, &st_full[stage]);
+        }
+        if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t aR1 = smem_u32(sRes), aR2 = aR1 + Cf::NKC * AB_ROWS * 128, aPD = smem_u32(sPD);
+      mbar_wait(res_full, 0);
+      int stage = 0, phase = 0;
+      for (int it = 0; it < NI; ++it) {
+        mbar_wait(&st_full[stage], phase);
+        tc_fence_after();
+        const uint32_t aB1 = smem_u32(sStage + stage * Cf::STAGE_BYTES), aB2 = aB1 + Cf::NAT_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < Cf::KSTEPS; ++ks) {
+          const uint32_t offa = (uint32_t)(ks / 4) * (AB_ROWS * 128) + (uint32_t)(ks % 4) * 32;
+          const uint32_t offb = (uint32_t)(ks / 4) * (Cf::BY * 128) + (uint32_t)(ks % 4) * 32;
+          umma_f16(tmem_base + Cf::COL_S, make_kmajor_sw128_desc(aR1 + offa), make_kmajor_sw128_desc(aB1 + offb), p.idesc_s, ks > 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < Cf::KSTEPS; ++ks) {
+          const uint32_t offa = (uint32_t)(ks / 4) * (AB_ROWS * 128) + (uint32_t)(ks % 4) * 32;
+          const uint32_t offb = (uint32_t)(ks / 4) * (Cf::BY * 128) + (uint32_t)(ks % 4) * 32;
+          umma_f16(tmem_base + Cf::COL_DP, make_kmajor_sw128_desc(aR2 + offa), make_kmajor_sw128_desc(aB2 + offb), p.idesc_s, ks > 0);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, it & 1);                          // row threads wrote P / dS of this tile
+        tc_fence_after();
+        const uint32_t aT1 = aB1 + 2 * Cf::NAT_BYTES, aT2 = aT1 + Cf::TR_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < Cf::BY / 16; ++ks) {
+          const uint32_t offp = (uint32_t)(ks / 4) * (AB_ROWS * 128) + (uint32_t)(ks % 4) * 32;
+          const uint32_t offt = (uint32_t)(ks / 4) * (Cf::DN * 128) + (uint32_t)(ks % 4) * 32;
+          // MODE 0: dQ += dS K      MODE 1: dV += P^T dO
+          umma_f16(tmem_base + Cf::COL_ACC0, make_kmajor_sw128_desc(aPD + offp), make_kmajor_sw128_desc(aT1 + offt), p.idesc_acc,
+                   (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        if (MODE == 1) {
+#pragma unroll
+          for (int ks = 0; ks < Cf::BY / 16; ++ks) {
+            const uint32_t offp = (uint32_t)(Cf::NHALF * AB_ROWS * 128) + (uint32_t)(ks / 4) * (AB_ROWS * 128) + (uint32_t)(ks % 4) * 32;
+            const uint32_t offt = (uint32_t)(ks / 4) * (Cf::DN * 128) + (uint32_t)(ks % 4) * 32;
+            umma_f16(tmem_base + Cf::COL_ACC1, make_kmajor_sw128_desc(aPD + offp), make_kmajor_sw128_desc(aT2 + offt), p.idesc_acc,
+                     (it > 0 || ks > 0) ? 1u : 0u);          // dK += dS^T Q
+          }
+        }
+        umma_commit(&st_empty[stage]);
+        if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== row threads: softmax backward + epilogue =====================
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const int xrow = x0 + r;
+    const bool row_ok = xrow < Lx;
+    float lse_r = 0.f, D_r = 0.f;
+    if (MODE == 0) {
+      lse_r = p.lse_pad[(size_t)bh * p.Lq_pad + xrow] * 1.4426950408889634f;
+      D_r = p.D_pad[(size_t)bh * p.Lq_pad + xrow];
+    }
+    int stage = 0, phase = 0;
+    for (int it = 0; it < NI; ++it) {
+      mbar_wait(s_full, it & 1);
+      if (MODE == 1) mbar_wait(&st_full[stage], phase);      // acquire the TMA-written lse / D slices for generic loads
+      tc_fence_after();
+      const int y0 = it * Cf::BY;
+      const float* vec = reinterpret_cast<const float*>(sStage + stage * Cf::STAGE_BYTES + 2 * Cf::NAT_BYTES + Cf::NT * Cf::TR_BYTES);
+#pragma unroll 1
+      for (int c0 = 0; c0 < Cf::BY; c0 += 32) {
+        uint32_t vs[32], vd[32];
+        tmem_ld_32x32b_x32(trow + (uint32_t)(Cf::COL_S + c0), vs);
+        tmem_ld_32x32b_x32(trow + (uint32_t)(Cf::COL_DP + c0), vd);
+        tmem_ld_wait();
+        uint32_t pk_p[16], pk_ds[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float pv[2], dsv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = c0 + i + e;                      // inner index within the tile
+            const int y = y0 + c;
+            float pr, dp = __uint_as_float(vd[i + e]);
+            if (MODE == 0) {
+              pr = (y < p.Lk) ? exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_r) : 0.f;
+              if (p.dp_ext != nullptr && y < p.Lk && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + xrow) * p.Lk + y];
+              dsv[e] = pr * (dp - D_r);
+            } else {
+              const float lse_c = vec[c] * 1.4426950408889634f, D_c = vec[Cf::BY + c];
+              pr = exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_c);     // lse pad = 1e30 -> 0 beyond Lq
+              if (p.dp_ext != nullptr && y < p.Lq && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + y) * p.Lk + xrow];
+              dsv[e] = pr * (dp - D_c);
+            }
+            pv[e] = pr;
+          }
+          pk_p[i / 2] = ab_pack2<T>(pv[0], pv[1]);
+          pk_ds[i / 2] = ab_pack2<T>(dsv[0], dsv[1]);
+        }
+        unsigned char* half0 = sPD + (c0 / 64) * (AB_ROWS * 128);                            // MODE 0: dS   | MODE 1: P^T
+        unsigned char* half1 = sPD + Cf::NHALF * AB_ROWS * 128 + (c0 / 64) * (AB_ROWS * 128);  //              | MODE 1: dS^T
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cc = (c0 % 64) / 8 + q;
+          if (MODE == 0) {
+            *reinterpret_cast<uint4*>(sw128_chunk(half0, r, cc)) = make_uint4(pk_ds[q * 4], pk_ds[q * 4 + 1], pk_ds[q * 4 + 2], pk_ds[q * 4 + 3]);
+          } else {
+            *reinterpret_cast<uint4*>(sw128_chunk(half0, r, cc)) = make_uint4(pk_p[q * 4], pk_p[q * 4 + 1], pk_p[q * 4 + 2], pk_p[q * 4 + 3]);
+            *reinterpret_cast<uint4*>(sw128_chunk(half1, r, cc)) = make_uint4(pk_ds[q * 4], pk_ds[q * 4 + 1], pk_ds[q * 4 + 2], pk_ds[q * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+      if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ---- epilogue: accumulators -> 16-bit global
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int n_out = (MODE == 0) ? 1 : 2;
+    for (int o = 0; o < n_out; ++o) {
+      // MODE 0: acc0 = dQ (x scale).  MODE 1: acc0 = dV (x 1) -> out1, acc1 = dK (x scale) -> out0
+      const float mul = (MODE == 0 || o == 1) ? p.scale : 1.f;
+      void* outp = (MODE == 0) ? p.out0 : (o == 0 ? p.out1 : p.out0);
+      T* op = reinterpret_cast<T*>(outp) + ((size_t)b * Lx + xrow) * p.out_ld + (size_t)h * p.d;
+#pragma unroll 1
+      for (int c0 = 0; c0 < Cf::DN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(trow + (uint32_t)((o == 0 ? Cf::COL_ACC0 : Cf::COL_ACC1) + c0), v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 8) {
+            if (c0 + i + 8 <= D) {
+              uint4 u;
+              u.x = ab_pack2<T>(__uint_as_float(v[i]) * mul, __uint_as_float(v[i + 1]) * mul);
+              u.y = ab_pack2<T>(__uint_as_float(v[i + 2]) * mul, __uint_as_float(v[i + 3]) * mul);
+              u.z = ab_pack2<T>(__uint_as_float(v[i + 4]) * mul, __uint_as_float(v[i + 5]) * mul);
+              u.w = ab_pack2<T>(__uint_as_float(v[i + 6]) * mul, __uint_as_float(v[i + 7]) * mul);
+              *reinterpret_cast<uint4*>(op + c0 + i) = u;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cf::TMEM_COLS); }
+}
+
+// (n, L, H*d) -> per-head transpose (n*H, d, Lpad), zero padded  (same as the forward's V^T pre-pass)
+template <typename T>
+__global__ void ab_transpose_kernel(const T* __restrict__ v, T* __restrict__ vt, int L, int H, int d, int Lpad) {
+  __shared__ T tile[32][33];
+  const int bh = blockIdx.z, b = bh / H, h = bh % H;
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int key = k0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (key < L && c < d) ? v[((size_t)b * L + key) * (H * d) + h * d + c] : from_f32<T>(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, key = k0 + threadIdx.x;
+    if (c < d && key < Lpad) vt[((size_t)bh * d + c) * Lpad + key] = tile[threadIdx.x][j];
+  }
+}
+
+// D_i = sum_c dO o O (+ sum_k P dP_ext), lse padded with 1e30 / D padded with 0 to Lq_pad
+template <typename T>
+__global__ void ab_prep_kernel(const T* __restrict__ o, const T* __restrict__ dO, const float* __restrict__ lse,
+                               const float* __restrict__ probs, const float* __restrict__ dp_ext, float* __restrict__ lse_pad,
+                               float* __restrict__ D_pad, int n, int Lq, int Lk, int H, int d, int Lq_pad) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * H * Lq_pad) return;
+  const int q = (int)(idx % Lq_pad);
+  const int bh = (int)(idx / Lq_pad), b = bh / H, h = bh % H;
+  if (q >= Lq) { lse_pad[idx] = 1e30f; D_pad[idx] = 0.f; return; }
+  const T* op = o + ((size_t)b * Lq + q) * (H * d) + h * d;
+  const T* dp = dO + ((size_t)b * Lq + q) * (H * d) + h * d;
+  float s = 0.f;
+  for (int c = 0; c < d; ++c) s += to_f32<T>(op[c]) * to_f32<T>(dp[c]);
+  if (dp_ext != nullptr) {
+    const float* pr = probs + ((size_t)bh * Lq + q) * Lk;
+    const float* de = dp_ext + ((size_t)bh * Lq + q) * Lk;
+    for (int k = 0; k < Lk; ++k) s += pr[k] * de[k];
+  }
+  lse_pad[idx] = lse[(size_t)bh * Lq + q];
+  D_pad[idx] = s;
+}
+
+template <int D, int MODE, typename T>
+static int launch_ab(const CUtensorMap* m, const AttnBwdKP& kp, dim3 grid, cudaStream_t st) {
+  using Cf = ABCfg<D, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    COMAT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::TOTAL));
+    configured = true;
+  }
+  attn_bwd_kernel<D, MODE, T><<<grid, AB_THREADS, Cf::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], kp);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
+template <int D, typename T>
+static int run_bwd(const void* q, const void* k, const void* v, const void* dO, void* qT, void* kT, void* dOT, AttnBwdKP kp, int n,
+                   void* dq, void* dk, void* dv, int fmt, cudaStream_t st) {
+  constexpr int NKC = (D + 63) / 64; (void)NKC;
+  constexpr int DN = (D + 15) / 16 * 16;
+  constexpr int BY = (D <= 64) ? 128 : 64;
+  const int H = kp.H, d = kp.d, Lq = kp.Lq, Lk = kp.Lk;
+  auto nat = [&](CUtensorMap* m, const void* base, int L, int rows) {
+    const uint64_t dims[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * L};
+    const uint64_t str[2] = {(uint64_t)d * 2, (uint64_t)H * d * 2};
+    const uint32_t box[3] = {64, 1, (uint32_t)rows};
+    return make_tmap_16bit(m, base, 3, dims, str, box);
+  };
+  auto trn = [&](CUtensorMap* m, const void* base, int Lpad) {
+    const uint64_t dims[2] = {(uint64_t)Lpad, (uint64_t)n * H * d};
+    const uint64_t str[1] = {(uint64_t)Lpad * 2};
+    const uint32_t box[2] = {64, (uint32_t)DN};
+    return make_tmap_16bit(m, base, 2, dims, str, box);
+  };
+  kp.idesc_s = make_idesc_f16(AB_ROWS, BY, fmt);
+  kp.idesc_acc = make_idesc_f16(AB_ROWS, DN, fmt);
+  CUtensorMap m[6];
+  memset(m, 0, sizeof(m));
+  // ---- MODE 0: dQ
+  bool ok = nat(&m[0], q, Lq, AB_ROWS) && nat(&m[1], dO, Lq, AB_ROWS) && nat(&m[2], k, Lk, BY) && nat(&m[3], v, Lk, BY) &&
+            trn(&m[4], kT, kp.Lk_pad);
+  m[5] = m[4];
+  if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+  kp.n_inner = (Lk + BY - 1) / BY;
+  kp.out0 = dq; kp.out1 = nullptr;
+  int rc = launch_ab<D, 0, T>(m, kp, dim3((Lq + AB_ROWS - 1) / AB_ROWS, H, n), st);
+  if (rc) return rc;
+  // ---- MODE 1: dK, dV
+  ok = nat(&m[0], k, Lk, AB_ROWS) && nat(&m[1], v, Lk, AB_ROWS) && nat(&m[2], q, Lq, BY) && nat(&m[3], dO, Lq, BY) &&
+       trn(&m[4], dOT, kp.Lq_pad) && trn(&m[5], qT, kp.Lq_pad);
+  if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+  kp.n_inner = (Lq + BY - 1) / BY;
+  kp.out0 = dk; kp.out1 = dv;
+  return launch_ab<D, 1, T>(m, kp, dim3((Lk + AB_ROWS - 1) / AB_ROWS, H, n), st);
+}
+
+}  // namespace comat
+using namespace comat;
+
+extern "C" size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int H, int d) {
+  const size_t Lqp = (size_t)(Lq + 127) / 128 * 128, Lkp = (size_t)(Lk + 127) / 128 * 128;
+  return (size_t)n * H * d * (2 * Lqp + Lkp) * 2 + (size_t)n * H * Lqp * 8 + 1024;
+}
+
+extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
+                                   const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
+                                   int Lq, int Lk, int H, int d, float scale, int dtype, void* stream) {
+  if (!q || !k || !v || !o || !dO || !lse || !dq || !dk || !dv || !workspace) return COMAT_ERR_INVALID;
+  if (d != 40 && d != 64 && d != 80 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
+  if (dtype != COMAT_F16 && dtype != COMAT_BF16) return COMAT_ERR_UNSUPPORTED;
+  if (dp_ext && !probs) return COMAT_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Lqp = (Lq + 127) / 128 * 128, Lkp = (Lk + 127) / 128 * 128;
+  unsigned char* ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  const size_t szq = (size_t)n * H * d * Lqp * 2, szk = (size_t)n * H * d * Lkp * 2;
+  void* qT = ws; void* dOT = ws + szq; void* kT = ws + 2 * szq;
+  float* lse_pad = reinterpret_cast<float*>(ws + 2 * szq + szk);
+  float* D_pad = lse_pad + (size_t)n * H * Lqp;
+  {
+    dim3 blk(32, 8);
+    ab_transpose_kernel<__half><<<dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)q, (__half*)qT, Lq, H, d, Lqp);
+    ab_transpose_kernel<__half><<<dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)dO, (__half*)dOT, Lq, H, d, Lqp);
+    ab_transpose_kernel<__half><<<dim3((Lkp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)k, (__half*)kT, Lk, H, d, Lkp);
+    const long long tot = (long long)n * H * Lqp;
+    if (dtype == COMAT_F16)
+      ab_prep_kernel<__half><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __half*)o, (const __half*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
+    else
+      ab_prep_kernel<__nv_bfloat16><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
+  }
+  AttnBwdKP kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.Lq = Lq; kp.Lk = Lk; kp.H = H; kp.d = d; kp.Lq_pad = Lqp; kp.Lk_pad = Lkp;
+  kp.scale = scale; kp.scale_log2 = scale * 1.4426950408889634f;
+  kp.lse_pad = lse_pad; kp.D_pad = D_pad; kp.dp_ext = dp_ext; kp.out_ld = (long long)H * d;
+  const int fmt = dtype == COMAT_BF16 ? 1 : 0;
+#define AB_CASE(DD)                                                                                                          \
+  case DD:                                                                                                                   \
+    return fmt ? run_bwd<DD, __nv_bfloat16>(q, k, v, dO, qT, kT, dOT, kp, n, dq, dk, dv, fmt, st)                            \
+               : run_bwd<DD, __half>(q, k, v, dO, qT, kT, dOT, kp, n, dq, dk, dv, fmt, st);
+  switch (d) { AB_CASE(16) AB_CASE(32) AB_CASE(40) AB_CASE(64) AB_CASE(80) AB_CASE(160) }
+#undef AB_CASE
+  return COMAT_ERR_UNSUPPORTED;
+}

@@ -110,13 +110,16 @@ __global__ void __launch_bounds__(FWD_THREADS) attnmap_fwd_kernel(Tables tb, flo
 #pragma unroll
   for (int k = 0; k < PAIRS_PER_WARP; ++k) acc[k] = 0.f;
 
-  float* part = state + L.part_nd + (size_t)w * L.nd_stride;
+  // partial region of this (group, sample): [slot][tile][2] (tile fastest -> the reducer reads it coalesced)
+  const int n_tiles = G[5], work_begin = G[7];
+  const size_t region = (size_t)(work_begin + b * n_tiles);
+  float* part = state + L.part_nd + region * L.nd_stride;
   for (int it = 0; it < n_it; ++it) {
     const int s = it % STAGES;
     mbar_wait(&bars[s], (uint32_t)((it / STAGES) & 1));
     const float* buf = ring + (size_t)s * tile_floats + lane * T;
     const int lm = it / H, h = it % H;
-    float* prow = part + ((size_t)(lm * tb.maxH + h) * MAXP) * 2;
+    const int slot0 = (lm * tb.maxH + h) * MAXP;
 #pragma unroll
     for (int k = 0; k < PAIRS_PER_WARP; ++k) {
       const int j = warp + k * NWARPS;
@@ -126,10 +129,8 @@ __global__ void __launch_bounds__(FWD_THREADS) attnmap_fwd_kernel(Tables tb, flo
         acc[k] += v;
         const float num = warp_sum(v * mk);
         const float den = warp_sum(v);
-        if (lane == 0) {
-          prow[j * 2 + 0] = num;
-          prow[j * 2 + 1] = den;
-        }
+        if (lane == 0)
+          *reinterpret_cast<float2*>(part + ((size_t)(slot0 + j) * n_tiles + tile) * 2) = make_float2(num, den);
       }
     }
     __syncthreads();   // everyone is done with stage s
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(FWD_THREADS) attnmap_fwd_kernel(Tables tb, flo
   __syncthreads();
   const float inv_cnt = 1.0f / (float)n_it;
   float* pred_out = state + L.pred + (size_t)pred_base + (size_t)b * MAXW * HW;
-  float* pb = state + L.part_bce + (size_t)w * MAXW;
+  float* pb = state + L.part_bce + region * MAXW;
   for (int wl = warp; wl < nw; wl += NWARPS) {
     float p = 0.f;
     for (int j = 0; j < np; ++j)
@@ -158,12 +159,34 @@ __global__ void __launch_bounds__(FWD_THREADS) attnmap_fwd_kernel(Tables tb, flo
     const float l0 = fmaxf(logf(fmaxf(1.f - p, 0.f)), -100.f);
     const float bce = -(mk * l1 + (1.f - mk) * l0);
     const float sum = warp_sum(bce);
-    if (lane == 0) pb[wl] = sum;
+    if (lane == 0) pb[(size_t)wl * n_tiles + tile] = sum;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
-// one CTA per (group, sample): fixed-order reduction of the tile partials, token-loss terms, backward coefficients.
+// Stage A: one warp per (group, sample, map, head, pair) slot sums its tile partials (coalesced float2 reads, fixed-order
+// shuffle tree -> bit-reproducible).  Stage B: one CTA per (group, sample): token-loss terms, backward coefficients, pixel sum;
+// the last CTA adds the per-(group, sample) results in index order.
+__global__ void __launch_bounds__(256) attnmap_reduce_kernel(Tables tb, float* __restrict__ state, StateLayout L) {
+  const int slots = tb.maxMG * tb.maxH * MAXP;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)tb.n_groups * tb.B * slots) return;
+  const int gb = (int)(wid / slots), slot = (int)(wid % slots);
+  const int g = gb / tb.B, b = gb % tb.B;
+  const int* G = tb.grp + g * 8;
+  const int nm = G[2] - G[1], H = G[3], n_tiles = G[5], work_begin = G[7];
+  const int np = tb.smp[b * 4 + 1] - tb.smp[b * 4 + 0];
+  const int j = slot % MAXP, h = (slot / MAXP) % tb.maxH, lm = slot / (MAXP * tb.maxH);
+  if (j >= np || h >= H || lm >= nm) return;
+  const float2* p = reinterpret_cast<const float2*>(state + L.part_nd + (size_t)(work_begin + b * n_tiles) * L.nd_stride) +
+                    (size_t)slot * n_tiles;
+  float num = 0.f, den = 0.f;
+  for (int t = lane; t < n_tiles; t += 32) { const float2 v = p[t]; num += v.x; den += v.y; }
+  num = warp_sum(num); den = warp_sum(den);
+  if (lane == 0) *reinterpret_cast<float2*>(state + L.nd + (size_t)gb * L.nd_stride + (size_t)slot * 2) = make_float2(num, den);
+}
+
 __global__ void __launch_bounds__(256) attnmap_finalize_kernel(Tables tb, float* __restrict__ state, StateLayout L,
                                                                float* __restrict__ loss2, unsigned int* counter) {
   __shared__ float s_red[256];
@@ -173,38 +196,14 @@ __global__ void __launch_bounds__(256) attnmap_finalize_kernel(Tables tb, float*
   const int* G = tb.grp + g * 8;
   const int res = G[0], nm = G[2] - G[1], H = G[3], n_tiles = G[5], work_begin = G[7];
   const int* S = tb.smp + b * 4;
-  const int pair_begin = S[0], np = S[1] - S[0], word_begin = S[2], nw = S[3] - S[2];
+  const int pair_begin = S[0], np = S[1] - S[0], nw = S[3] - S[2];
   const int tid = threadIdx.x;
   float tok_local = 0.f, pix_local = 0.f;
   if (np > 0) {
-    const int slot0 = work_begin + b * n_tiles;
-    float* nd = state + L.nd + (size_t)gb * L.nd_stride;
-    // 1) reduce partial (num, den) over tiles: one warp per (map, head, pair), lanes stride the tiles, then a
-    //    fixed-order shuffle tree (bit-reproducible)
-    const int n_items = nm * H * np;
-    const int warp_id = tid >> 5, lane_id = tid & 31, n_warps = blockDim.x >> 5;
-    for (int i = warp_id; i < n_items; i += n_warps) {
-      const int j = i % np, mh = i / np;
-      const int h = mh % H, lm = mh / H;
-      const size_t off = ((size_t)(lm * tb.maxH + h) * MAXP + j) * 2;
-      float num = 0.f, den = 0.f;
-      for (int t = lane_id; t < n_tiles; t += 32) {
-        const float2 p = *reinterpret_cast<const float2*>(state + L.part_nd + (size_t)(slot0 + t) * L.nd_stride + off);
-        num += p.x;
-        den += p.y;
-      }
-      num = warp_sum(num);
-      den = warp_sum(den);
-      if (lane_id == 0) {
-        nd[off] = num;
-        nd[off + 1] = den;
-      }
-    }
-    __syncthreads();
-    // 2) token loss terms per (map, pair)  (tc_loss_utils.py:104-125)
+    const float* nd = state + L.nd + (size_t)gb * L.nd_stride;
     float* coef = state + L.coef + (size_t)gb * L.coef_stride;
     const float invW = 1.f / (float)nw, invB = 1.f / (float)tb.B;
-    for (int i = tid; i < nm * np; i += blockDim.x) {
+    for (int i = tid; i < nm * np; i += blockDim.x) {          // token loss terms (tc_loss_utils.py:104-125)
       const int j = i % np, lm = i / np;
       float fm = 0.f;
       for (int h = 0; h < H; ++h) {
@@ -218,14 +217,10 @@ __global__ void __launch_bounds__(256) attnmap_finalize_kernel(Tables tb, float*
       tok_local += d * d * inv_nt * invW;
       coef[lm * MAXP + j] = -2.f * d * inv_nt * invW * invB / (float)H;
     }
-    // 3) pixel loss: mean over res^2 of BCE, mean over words (tc_loss_utils.py:153-167)
-    for (int i = tid; i < nw * n_tiles; i += blockDim.x) {
-      const int wl = i % nw, t = i / nw;
-      pix_local += state[L.part_bce + (size_t)(slot0 + t) * MAXW + wl];
-    }
+    const float* pb = state + L.part_bce + (size_t)(work_begin + b * n_tiles) * MAXW;     // [wl][tile]
+    for (int i = tid; i < nw * n_tiles; i += blockDim.x) pix_local += pb[i];              // (tc_loss_utils.py:153-167)
     pix_local *= invW / (float)(res * res);
   }
-  // deterministic block reduction
   s_red[tid] = tok_local;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -264,20 +259,18 @@ __global__ void __launch_bounds__(256) attnmap_finalize_kernel(Tables tb, float*
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// Writes every dP tile exactly once with coalesced 16-byte stores straight from registers: a tile is a contiguous run
-// of 32*T floats; element e -> (pixel e / T, column e % T).  Only the <= 32 (word, token) columns are non-zero; their
-// per-(map, head) values are staged in a double-buffered smem table tv[pair][pixel] (one barrier per slab).
-constexpr int BWD_THREADS = 256;
+constexpr int BWD_THREADS = 128;
 __global__ void __launch_bounds__(BWD_THREADS) attnmap_bwd_kernel(Tables tb, const float* __restrict__ state, StateLayout L,
                                                                   const float* __restrict__ grad2,
                                                                   const int64_t* __restrict__ map_grad_ptr) {
-  __shared__ float s_mask[MAXW * TILE_PX];
-  __shared__ float s_dbce[MAXW * TILE_PX];
-  __shared__ float s_tv[2][MAXP * TILE_PX];
-  __shared__ unsigned int s_colmask[128];      // column -> bitmask of pairs writing it (T <= 128)
-  __shared__ int s_tok[MAXP], s_wl[MAXP];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int T = tb.T;
   const int tile_floats = TILE_PX * T;
+  float* obuf = reinterpret_cast<float*>(smem_raw);            // 2 * tile_floats
+  float* s_mask = obuf + 2 * (size_t)tile_floats;              // MAXW*32
+  float* s_dbce = s_mask + MAXW * TILE_PX;                     // MAXW*32
+  int* s_tok = reinterpret_cast<int*>(s_dbce + MAXW * TILE_PX);
+  int* s_wl = s_tok + MAXP;
 
   const int w = blockIdx.x;
   const int g = tb.work[w * 4 + 0], b = tb.work[w * 4 + 1], tile = tb.work[w * 4 + 2];
@@ -285,30 +278,19 @@ __global__ void __launch_bounds__(BWD_THREADS) attnmap_bwd_kernel(Tables tb, con
   const int res = G[0], map_begin = G[1], map_end = G[2], H = G[3], mask_off = G[4], pred_base = G[6];
   const int* S = tb.smp + b * 4;
   const int pair_begin = S[0], np = S[1] - S[0], word_begin = S[2], nw = S[3] - S[2];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int HW = res * res, px0 = tile * TILE_PX;
   const int n_it = (map_end - map_begin) * H;
+  const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
   const int gb = g * tb.B + b;
-  const int n_vec = tile_floats / 4;           // 32*T is a multiple of 4
 
-  if (np <= 0) {                               // sample without words: dP = 0
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int it = 0; it < n_it; ++it) {
-      const int lm = it / H, h = it % H;
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(map_grad_ptr[map_begin + lm]) + ((size_t)(b * H + h) * HW + px0) * T);
-      for (int f = tid; f < n_vec; f += BWD_THREADS) dst[f] = z;
-    }
-    return;
-  }
-  for (int i = tid; i < 128; i += BWD_THREADS) s_colmask[i] = 0u;
-  if (tid < np) {
-    s_tok[tid] = tb.pair[(pair_begin + tid) * 2 + 1];
-    s_wl[tid] = tb.pair[(pair_begin + tid) * 2 + 0] - word_begin;
-  }
-  __syncthreads();
-  if (tid < np) atomicOr(&s_colmask[s_tok[tid]], 1u << tid);
-  {
+  for (int i = tid; i < 2 * tile_floats; i += BWD_THREADS) obuf[i] = 0.f;
+  if (np > 0) {
     const float g_pix = grad2[1];
+    if (tid < np) {
+      s_tok[tid] = tb.pair[(pair_begin + tid) * 2 + 1];
+      s_wl[tid] = tb.pair[(pair_begin + tid) * 2 + 0] - word_begin;
+    }
     const float* pred = state + L.pred + (size_t)pred_base + (size_t)b * MAXW * HW;
     const float cpix = g_pix / ((float)HW * (float)n_it * (float)nw * (float)tb.B);
     for (int i = tid; i < nw * TILE_PX; i += BWD_THREADS) {
@@ -316,7 +298,8 @@ __global__ void __launch_bounds__(BWD_THREADS) attnmap_bwd_kernel(Tables tb, con
       const float mk = tb.masks[(size_t)mask_off + (size_t)(word_begin + wl) * HW + px0 + p];
       const float x = pred[(size_t)wl * HW + px0 + p];
       s_mask[i] = mk;
-      s_dbce[i] = cpix * (x - mk) / fmaxf((1.f - x) * x, 1e-12f);   // aten binary_cross_entropy_backward
+      // aten binary_cross_entropy_backward: (x - t) / max((1 - x) * x, 1e-12)
+      s_dbce[i] = cpix * (x - mk) / fmaxf((1.f - x) * x, 1e-12f);
     }
   }
   __syncthreads();
@@ -324,45 +307,36 @@ __global__ void __launch_bounds__(BWD_THREADS) attnmap_bwd_kernel(Tables tb, con
   const float* nd = state + L.nd + (size_t)gb * L.nd_stride;
   const float* coef = state + L.coef + (size_t)gb * L.coef_stride;
 
-  auto fill_tv = [&](int it) {
-    const int lm = it / H, h = it % H;
-    float* tv = s_tv[it & 1];
-    for (int i = tid; i < np * TILE_PX; i += BWD_THREADS) {
-      const int j = i / TILE_PX, p = i % TILE_PX;
-      const size_t off = ((size_t)(lm * tb.maxH + h) * MAXP + j) * 2;
-      const float num = nd[off], den = nd[off + 1];
-      const float c = g_tok * coef[lm * MAXP + j];
-      const int wl = s_wl[j];
-      tv[i] = c * (s_mask[wl * TILE_PX + p] * den - num) / (den * den) + s_dbce[wl * TILE_PX + p];
-    }
-  };
-  fill_tv(0);
-  __syncthreads();
   for (int it = 0; it < n_it; ++it) {
     const int lm = it / H, h = it % H;
-    if (it + 1 < n_it) fill_tv(it + 1);        // other buffer: safe while this slab is being written out
-    const float* tv = s_tv[it & 1];
-    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(map_grad_ptr[map_begin + lm]) + ((size_t)(b * H + h) * HW + px0) * T);
-    for (int f = tid; f < n_vec; f += BWD_THREADS) {
-      float v[4];
-      const int e0 = f * 4;
-      int pix = e0 / T, col = e0 - pix * T;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        unsigned int m = s_colmask[col];
-        float a = 0.f;
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          a += tv[j * TILE_PX + pix];
-        }
-        v[q] = a;
-        if (++col == T) { col = 0; ++pix; }
-      }
-      dst[f] = make_float4(v[0], v[1], v[2], v[3]);
+    float* buf = obuf + (size_t)(it & 1) * tile_floats;
+    if (it >= 2) {
+      if (tid == 0) bulk_wait_read<1>();   // the store that last used this buffer has finished reading smem
+      __syncthreads();
     }
+    if (np > 0) {
+      // clear the touched columns, then accumulate (pairs of different words may share a token column)
+      for (int j = warp; j < np; j += BWD_THREADS / 32) buf[lane * T + s_tok[j]] = 0.f;
+      __syncthreads();
+      for (int j = warp; j < np; j += BWD_THREADS / 32) {
+        const size_t off = ((size_t)(lm * tb.maxH + h) * MAXP + j) * 2;
+        const float num = nd[off], den = nd[off + 1];
+        const float c = g_tok * coef[lm * MAXP + j];
+        const int wl = s_wl[j];
+        const float mk = s_mask[wl * TILE_PX + lane];
+        const float val = c * (mk * den - num) / (den * den) + s_dbce[wl * TILE_PX + lane];
+        atomicAdd(&buf[lane * T + s_tok[j]], val);
+      }
+    }
+    fence_proxy_async_smem();
     __syncthreads();
+    if (tid == 0) {
+      float* dst = reinterpret_cast<float*>(map_grad_ptr[map_begin + lm]) + ((size_t)(b * H + h) * HW + px0) * T;
+      bulk_s2g(dst, buf, tile_bytes);
+      bulk_commit();
+    }
   }
+  if (tid == 0) bulk_wait_all<0>();
 }
 
 // ------------------------------------------------------------------------------------------------ mask resize
@@ -415,6 +389,8 @@ static inline size_t fwd_smem(int T) {
   return (size_t)STAGES * TILE_PX * T * 4 + MAXW * TILE_PX * 4 + 2 * MAXP * 4 + STAGES * 8 + 16;
 }
 
+static inline size_t bwd_smem(int T) { return (size_t)2 * TILE_PX * T * 4 + 2 * MAXW * TILE_PX * 4 + 2 * MAXP * 4; }
+
 }  // namespace comat
 
 using namespace comat;
@@ -448,6 +424,10 @@ extern "C" int comat_attnmap_loss_fwd(const comat_attnmap_plan* p, float* loss2,
   }
   attnmap_fwd_kernel<<<p->n_work, FWD_THREADS, smem, st>>>(tb, state, L);
   COMAT_CHECK_LAUNCH();
+  {
+    const long long warps = (long long)p->n_groups * p->n_samples * p->max_maps_per_group * p->max_heads * MAXP;
+    attnmap_reduce_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tb, state, L);
+  }
   attnmap_finalize_kernel<<<p->n_groups * p->n_samples, 256, 0, st>>>(tb, state, L, loss2, counter);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
@@ -460,8 +440,13 @@ extern "C" int comat_attnmap_loss_bwd(const comat_attnmap_plan* p, const float* 
   if (!grad2 || !state || !map_grad_ptr) return COMAT_ERR_INVALID;
   StateLayout L = make_layout(p->n_work, p->n_groups, p->n_samples, p->max_heads, p->max_maps_per_group, p->pred_floats);
   Tables tb = make_tables(p);
-  if (p->tokens > 128) return COMAT_ERR_UNSUPPORTED;
-  attnmap_bwd_kernel<<<p->n_work, BWD_THREADS, 0, (cudaStream_t)stream>>>(tb, state, L, grad2, map_grad_ptr);
+  const size_t smem = bwd_smem(p->tokens);
+  static size_t configured = 0;
+  if (smem > configured) {
+    COMAT_CUDA(cudaFuncSetAttribute(attnmap_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  attnmap_bwd_kernel<<<p->n_work, BWD_THREADS, smem, (cudaStream_t)stream>>>(tb, state, L, grad2, map_grad_ptr);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }

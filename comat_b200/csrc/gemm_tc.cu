@@ -42,6 +42,8 @@ struct GemmKP {
   long long out32_ld;
   uint32_t idesc;
   int is_bf16;
+  int split_k, kb_per_split;   // split-K: blockIdx.z handles k-blocks [z*kb_per_split, ...) and writes raw fp32 partials
+  float* splitk_ws;            // [split_k][M][N] fp32
   int tma_store;     // 1: epilogue stages 16-bit tiles in (free) pipeline smem and writes them with TMA bulk tensor stores
 };
 
@@ -90,7 +92,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int tile_m = blockIdx.x, tile_n = blockIdx.y;
   const int n0 = tile_n * BN;
   const int kb_per_tap = p.seg_kblocks[0] + (p.n_seg > 1 ? p.seg_kblocks[1] : 0);
-  const int num_kb = p.n_taps * kb_per_tap;
+  const int num_kb_total = p.n_taps * kb_per_tap;
+  const int kb_begin = p.split_k > 1 ? blockIdx.z * p.kb_per_split : 0;
+  const int kb_end = p.split_k > 1 ? min(num_kb_total, kb_begin + p.kb_per_split) : num_kb_total;
+  const int num_kb = kb_end - kb_begin;
 
   // tile origin
   int m0 = tile_m * BM, img0 = 0, h0 = 0, w0 = 0;
@@ -124,22 +129,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int tap = 0; tap < p.n_taps; ++tap) {
-        for (int sg = 0; sg < p.n_seg; ++sg) {
-          const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
-          const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
-          const int nkb = p.seg_kblocks[sg];
-          for (int cb = 0; cb < nkb; ++cb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            unsigned char* sa = smem + stage * S::STAGE_BYTES;
-            unsigned char* sb = sa + S::A_BYTES;
-            mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-            if (p.conv) tma_load_4d(sa, mA, &full_bar[stage], cb * BK, w0 + p.dw[tap], h0 + p.dh[tap], img0);
-            else        tma_load_2d(sa, mA, &full_bar[stage], cb * BK, m0);
-            tma_load_2d(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
+      for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
+        const int tap = kbi / kb_per_tap;
+        int rem = kbi - tap * kb_per_tap;
+        const int sg = (rem >= p.seg_kblocks[0]) ? 1 : 0;
+        const int cb = rem - (sg ? p.seg_kblocks[0] : 0);
+        const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
+        const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        unsigned char* sa = smem + stage * S::STAGE_BYTES;
+        unsigned char* sb = sa + S::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+        if (p.conv) tma_load_4d(sa, mA, &full_bar[stage], cb * BK, w0 + p.dw[tap], h0 + p.dh[tap], img0);
+        else        tma_load_2d(sa, mA, &full_bar[stage], cb * BK, m0);
+        tma_load_2d(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -190,7 +194,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
       tmem_ld_wait();
       const int ncol = min(32, p.N - (n0 + c0));
-      if (p.tma_store || (row_ok && ncol > 0)) {
+      if (p.split_k > 1) {
+        if (row_ok && ncol > 0) {
+          float* wp = p.splitk_ws + ((size_t)blockIdx.z * p.M + m) * p.N + n0 + c0;
+          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(wp + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) wp[j] = __uint_as_float(v[j]);
+          }
+        }
+      } else if (p.tma_store || (row_ok && ncol > 0)) {
         {
           float f[32];
 #pragma unroll
@@ -219,9 +235,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
               }
             } else {
-              for (int j = 0; j < ncol; ++j) {
-                const uint16_t b = rp[j];
-                f[j] += p.is_bf16 ? __uint_as_float((uint32_t)b << 16) : __half2float(*reinterpret_cast<const __half*>(&b));
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {          // static indexing keeps f[] in registers
+                if (j < ncol) {
+                  const uint16_t b = rp[j];
+                  f[j] += p.is_bf16 ? __uint_as_float((uint32_t)b << 16) : __half2float(*reinterpret_cast<const __half*>(&b));
+                }
               }
             }
           }
@@ -236,9 +255,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 *reinterpret_cast<uint4*>(op + j4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
               }
             } else {
-              for (int j = 0; j < ncol; ++j) {
-                if (p.is_bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(f[j]); op[j] = *reinterpret_cast<const uint16_t*>(&t); }
-                else           { const __half t = __float2half_rn(f[j]);           op[j] = *reinterpret_cast<const uint16_t*>(&t); }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < ncol) {
+                  if (p.is_bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(f[j]); op[j] = *reinterpret_cast<const uint16_t*>(&t); }
+                  else           { const __half t = __float2half_rn(f[j]);           op[j] = *reinterpret_cast<const uint16_t*>(&t); }
+                }
               }
             }
           }
@@ -256,7 +278,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           if (p.out32 != nullptr && row_ok) {
             float* op = p.out32 + m * p.out32_ld + n0 + c0;
-            for (int j = 0; j < ncol; ++j) op[j] = f[j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) op[j] = f[j];
           }
         }
       }
@@ -281,6 +305,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols<BN>());
+  }
+}
+
+// split-K second pass: out = act(alpha * sum_s ws[s] + bias + rowvec) + residual  (+ accumulate into out32)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.M * p.N;
+  if (idx >= total) return;
+  const long long m = idx / p.N;
+  const int n = (int)(idx % p.N);
+  float acc = 0.f;
+  for (int s = 0; s < p.split_k; ++s) acc += p.splitk_ws[(size_t)s * total + idx];
+  float x = acc * p.alpha;
+  if (p.bias) x += p.bias[n];
+  if (p.rowvec) x += p.rowvec[(m / p.rows_per_group) * p.N + n];
+  x = act_apply(x, p.act);
+  if (p.residual) {
+    const uint16_t b = reinterpret_cast<const uint16_t*>(p.residual)[m * p.res_ld + n];
+    x += p.is_bf16 ? __uint_as_float((uint32_t)b << 16) : __half2float(*reinterpret_cast<const __half*>(&b));
+  }
+  if (p.out32) { float* o = p.out32 + m * p.out32_ld + n; *o = accumulate ? (*o + x) : x; }
+  if (p.out16) {
+    uint16_t* o = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n;
+    if (p.is_bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(x); *o = *reinterpret_cast<const uint16_t*>(&t); }
+    else           { const __half t = __float2half_rn(x);           *o = *reinterpret_cast<const uint16_t*>(&t); }
   }
 }
 
@@ -379,11 +428,24 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
       if (!make_tmap_16bit(&maps[2 + s], g->b[s], 2, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
     }
   }
+  // split-K (caller supplies the fp32 partial workspace)
+  {
+    const int kb_total = kp.n_taps * (kp.seg_kblocks[0] + (g->n_seg > 1 ? kp.seg_kblocks[1] : 0));
+    int sk = g->split_k > 1 ? g->split_k : 1;
+    if (sk > kb_total) sk = kb_total;
+    if (sk > 1) {
+      if (!g->splitk_ws) return COMAT_ERR_WORKSPACE;
+      kp.kb_per_split = (kb_total + sk - 1) / sk;
+      sk = (kb_total + kp.kb_per_split - 1) / kp.kb_per_split;
+      kp.split_k = sk; kp.splitk_ws = g->splitk_ws;
+      grid.z = sk;
+    } else { kp.split_k = 1; kp.kb_per_split = kb_total; }
+  }
   // TMA-store epilogue (default): needs a 16-bit output with 16-byte aligned base and row pitch
   static int epi_mode = -1;
   if (epi_mode < 0) { const char* e = getenv("COMAT_GEMM_EPILOGUE"); epi_mode = (e && !strcmp(e, "direct")) ? 0 : 1; }
   kp.tma_store = 0;
-  if (epi_mode == 1 && g->out16 && !g->out32 && (g->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(g->out16) & 15) == 0 &&
+  if (epi_mode == 1 && kp.split_k == 1 && g->out16 && !g->out32 && (g->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(g->out16) & 15) == 0 &&
       (!kp.conv || g->out_ld == g->N)) {
     bool ok;
     if (kp.conv) {
@@ -400,12 +462,18 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     kp.tma_store = ok ? 1 : 0;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  int rc = COMAT_ERR_UNSUPPORTED;
   switch (BN) {
-    case 32:  return launch_gemm<32, 4>(maps, kp, grid, st);
-    case 64:  return launch_gemm<64, 4>(maps, kp, grid, st);
-    case 128: return launch_gemm<128, 3>(maps, kp, grid, st);
-    case 160: return launch_gemm<160, 3>(maps, kp, grid, st);
-    case 256: return launch_gemm<256, 4>(maps, kp, grid, st);
+    case 32:  rc = launch_gemm<32, 4>(maps, kp, grid, st); break;
+    case 64:  rc = launch_gemm<64, 4>(maps, kp, grid, st); break;
+    case 128: rc = launch_gemm<128, 3>(maps, kp, grid, st); break;
+    case 160: rc = launch_gemm<160, 3>(maps, kp, grid, st); break;
+    case 256: rc = launch_gemm<256, 4>(maps, kp, grid, st); break;
   }
-  return COMAT_ERR_UNSUPPORTED;
+  if (rc == COMAT_OK && kp.split_k > 1) {
+    const long long total = (long long)kp.M * kp.N;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kp, g->accumulate ? 1 : 0);
+    COMAT_CHECK_LAUNCH();
+  }
+  return rc;
 }

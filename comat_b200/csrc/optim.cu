@@ -78,3 +78,46 @@ extern "C" int comat_adamw_clip(float* p, const float* g, float* m, float* v, lo
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused classifier-free guidance + DDPM ancestral step on the fp32 latent chain (TrainableSDPipeline.py:155-167):
+//   x_prev = c_x * x + c_eps * (e_u + s * (e_c - e_u)) + sigma * z        (epsilon prediction folded into c_x, c_eps)
+// replaces ~10 aten launches per sampler step; backward is the matching linear map.
+namespace comat {
+__global__ void __launch_bounds__(256) cfg_ddpm_fwd_kernel(const float* __restrict__ eps2, const float* __restrict__ x,
+                                                           const float* __restrict__ z, float* __restrict__ out, long long n,
+                                                           float s, float c_eps, float c_x, float sigma, int cfg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float e = cfg ? (eps2[i] + s * (eps2[n + i] - eps2[i])) : eps2[i];
+  float r = c_x * x[i] + c_eps * e;
+  if (z != nullptr) r += sigma * z[i];
+  out[i] = r;
+}
+__global__ void __launch_bounds__(256) cfg_ddpm_bwd_kernel(const float* __restrict__ g, float* __restrict__ d_eps2,
+                                                           float* __restrict__ dx, long long n, float s, float c_eps, float c_x, int cfg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  if (dx != nullptr) dx[i] = c_x * gi;
+  if (d_eps2 != nullptr) {
+    if (cfg) { d_eps2[i] = c_eps * (1.f - s) * gi; d_eps2[n + i] = c_eps * s * gi; }
+    else d_eps2[i] = c_eps * gi;
+  }
+}
+}  // namespace comat
+
+extern "C" int comat_cfg_ddpm_step_fwd(const float* eps, const float* x, const float* noise, float* out, long long n, float guidance,
+                                       float c_eps, float c_x, float sigma, int cfg, void* stream) {
+  if (!eps || !x || !out || n <= 0) return COMAT_ERR_INVALID;
+  comat::cfg_ddpm_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(eps, x, noise, out, n, guidance, c_eps, c_x, sigma, cfg);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+extern "C" int comat_cfg_ddpm_step_bwd(const float* grad_out, float* d_eps, float* dx, long long n, float guidance, float c_eps,
+                                       float c_x, int cfg, void* stream) {
+  if (!grad_out || n <= 0) return COMAT_ERR_INVALID;
+  comat::cfg_ddpm_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, d_eps, dx, n, guidance, c_eps, c_x, cfg);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}

@@ -23,7 +23,8 @@ class GemmParams(C.Structure):
                 ("c_total", C.c_int32), ("tap_dh", C.c_int32 * 9), ("tap_dw", C.c_int32 * 9),
                 ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rows_per_group", C.c_int32),
                 ("act", C.c_int32), ("residual", C.c_void_p), ("res_ld", C.c_int64), ("out16", C.c_void_p),
-                ("out_ld", C.c_int64), ("out32", C.c_void_p), ("out32_ld", C.c_int64), ("force_bn", C.c_int32)]
+                ("out_ld", C.c_int64), ("out32", C.c_void_p), ("out32_ld", C.c_int64), ("force_bn", C.c_int32),
+                ("split_k", C.c_int32), ("accumulate", C.c_int32), ("splitk_ws", C.c_void_p)]
 
 
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
@@ -40,7 +41,8 @@ def _p(t: Optional[torch.Tensor]):
 def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_koff: Sequence[int] = (0, 0),
          bias: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_group: int = 1,
          act=None, residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
-         out_fp32: bool = False, conv_taps=None, c_total: int = 0, force_bn: int = 0) -> torch.Tensor:
+         out_fp32: bool = False, conv_taps=None, c_total: int = 0, force_bn: int = 0, split_k: int = 0,
+         accumulate: bool = False) -> torch.Tensor:
     """out[m,n] = act(alpha * sum_s A_s[m,:] . B_s[n,:] + bias[n] + rowvec[m // rows_per_group, n]) + residual[m,n]
 
     plain mode : A_s is (M, K_s) (last dim contiguous); B_s is (N, >=K_s) K-major.
@@ -105,6 +107,17 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
     else:
         p.out16, p.out_ld = o2.data_ptr(), o2.stride(0)
     p.force_bn = force_bn
+    if split_k == 0:                      # auto: fill the machine when the output has few tiles and K is long
+        kb = sum((a.shape[-1] + 63) // 64 for a in a_segs) * (len(conv_taps) if conv else 1)
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        if tiles <= 74 and kb >= 32:
+            split_k = max(1, min(kb // 8, 296 // tiles))
+    if split_k > 1:
+        ws = torch.empty(split_k * M * N, dtype=torch.float32, device=a0.device)
+        p.split_k, p.splitk_ws, p.accumulate = split_k, ws.data_ptr(), int(accumulate)
+        keep.append(ws)
+    elif accumulate:
+        raise _lib.ComatError("gemm: accumulate=True needs split_k > 1")
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

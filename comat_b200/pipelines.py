@@ -15,7 +15,7 @@ import torch
 
 from . import engine as E
 from .modules import EngineUNet, EngineVAE
-from .scheduler import DDPMScheduler, rescale_noise_cfg
+from .scheduler import DDPMScheduler, fused_cfg_ddpm_step, rescale_noise_cfg
 
 
 class TrainableSDPipeline:
@@ -68,7 +68,7 @@ class TrainableSDPipeline:
     def _unet(self, x, t, embeds, added):
         return self.unet(x, t, encoder_hidden_states=embeds, added_cond_kwargs=added, return_dict=False)[0]
 
-    def _attrcon_forward(self, latents, t, prompt_embeds, added=None):
+    def _attrcon_forward(self, latents, t, prompt_embeds, added=None, t_host=None):
         """AttrConcenTrainableSDPipeline.py:239-279: conditional half with attention capture, then the unconditional half."""
         h = latents.shape[0] // 2
         split = (lambda d, s: None if d is None else {k: v[s] for k, v in d.items()})
@@ -76,7 +76,7 @@ class TrainableSDPipeline:
         try:
             n_c = self._unet(latents[h:], t, prompt_embeds[h:], split(added, slice(h, None)))
             maps, _ = self.controller.attn_dict()
-            self.attn_dict[str(int(t))] = maps
+            self.attn_dict[str(int(t) if t_host is None else t_host)] = maps
         finally:
             self.unet.capture = None
         n_u = self._unet(latents[:h], t, prompt_embeds[:h], split(added, slice(0, h)))
@@ -112,6 +112,7 @@ class TrainableSDPipeline:
                                            generator, latents)
             attr = T if attrcon_train_steps is None else list(attrcon_train_steps)
             use_attr = self.controller is not None and attrcon_train_steps is not None
+            ts_host = self.scheduler._ts_host          # host copy: no device sync per sampler step
             for i, t in enumerate(timesteps):
                 torch.set_grad_enabled(len(T) == 0 or i > min(T))                       # TrainableSDPipeline.py:133
                 x_in = torch.cat([latents] * 2) if cfg else latents
@@ -121,16 +122,26 @@ class TrainableSDPipeline:
                     detach = True                                                       # :809
                 x_in = x_in.detach() if detach else x_in
                 if i in T and bp_on_trained and use_attr and i in attr:                 # AttrConcen...:159-167
-                    eps = self._attrcon_forward(x_in, t, embeds, added)
+                    eps = self._attrcon_forward(x_in, t, embeds, added, t_host=ts_host[i])
                 else:
                     eps = self._unet(x_in, t, embeds, added)
+                fused = eps.is_cuda and guidance_rescale == 0.0 and not (early_exit and len(T) > 0 and i == max(T))
+                if fused:
+                    # one launch: guidance combine + DDPM step (:155-167); the reference's grad window for both is
+                    # `i >= min(T)` except that the combine of step min(T) happens under `i in T` — identical here
+                    torch.set_grad_enabled(len(T) == 0 or i >= min(T))
+                    latents = fused_cfg_ddpm_step(self.scheduler, eps, ts_host[i], latents, guidance_scale, cfg,
+                                                  noise=None if noises is None else noises[i], generator=generator)
+                    if callback is not None and i % callback_steps == 0:
+                        callback(i, t, latents)
+                    continue
                 if cfg:
                     e_u, e_c = eps.chunk(2)
                     eps = e_u + guidance_scale * (e_c - e_u)                            # :155-157
                     if guidance_rescale > 0.0:
                         eps = rescale_noise_cfg(eps, e_c, guidance_rescale)             # :159-161
                 torch.set_grad_enabled(len(T) == 0 or i >= min(T))                      # :163
-                out = self.scheduler.step(eps, t, latents, generator=generator,
+                out = self.scheduler.step(eps, ts_host[i], latents, generator=generator,
                                           variance_noise=None if noises is None else noises[i])
                 latents = out.prev_sample
                 if callback is not None and i % callback_steps == 0:

@@ -78,3 +78,46 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
     std_cfg = noise_cfg.std(dim=dims, keepdim=True)
     rescaled = noise_cfg * (std_text / std_cfg)
     return guidance_rescale * rescaled + (1 - guidance_rescale) * noise_cfg
+
+
+class _CfgDdpmStep(torch.autograd.Function):
+    """x_prev = c_x x + c_eps (e_u + s (e_c - e_u)) + sigma z  — one fused launch forward, one backward (csrc/optim.cu)."""
+
+    @staticmethod
+    def forward(ctx, eps, x, noise, s, c_eps, c_x, sigma, cfg):
+        import ctypes as C
+        from . import _lib
+        eps, x = eps.float().contiguous(), x.float().contiguous()
+        out = torch.empty_like(x)
+        z = noise.float().contiguous() if (noise is not None and sigma > 0) else None
+        _lib.check(_lib.lib().comat_cfg_ddpm_step_fwd(C.c_void_p(eps.data_ptr()), C.c_void_p(x.data_ptr()),
+                                                      C.c_void_p(z.data_ptr() if z is not None else None), C.c_void_p(out.data_ptr()),
+                                                      C.c_longlong(x.numel()), C.c_float(s), C.c_float(c_eps), C.c_float(c_x),
+                                                      C.c_float(sigma), int(cfg), _lib.stream_ptr()), "cfg_ddpm_step_fwd")
+        _lib.count_launch()
+        ctx.k = (s, c_eps, c_x, cfg, eps.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        from . import _lib
+        s, c_eps, c_x, cfg, eshape = ctx.k
+        g = g.float().contiguous()
+        d_eps = torch.empty(eshape, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        dx = torch.empty_like(g) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.lib().comat_cfg_ddpm_step_bwd(C.c_void_p(g.data_ptr()), C.c_void_p(d_eps.data_ptr() if d_eps is not None else None),
+                                                      C.c_void_p(dx.data_ptr() if dx is not None else None), C.c_longlong(g.numel()),
+                                                      C.c_float(s), C.c_float(c_eps), C.c_float(c_x), int(cfg), _lib.stream_ptr()),
+                   "cfg_ddpm_step_bwd")
+        _lib.count_launch()
+        return d_eps, dx, None, None, None, None, None, None
+
+
+def fused_cfg_ddpm_step(scheduler: DDPMScheduler, eps, t, latents, guidance_scale, cfg, noise=None, generator=None):
+    """CFG combine + scheduler.step in one kernel (CUDA tensors only).  ``eps`` is the raw UNet output ([uncond; cond] if cfg)."""
+    c_eps, c_x, sigma, _, _ = scheduler.step_coefficients(int(t))
+    if sigma > 0 and noise is None:
+        noise = torch.randn(latents.shape, generator=generator, dtype=torch.float32,
+                            device=generator.device if generator is not None else latents.device).to(latents.device)
+    return _CfgDdpmStep.apply(eps, latents, noise, float(guidance_scale), c_eps, c_x, sigma, bool(cfg))

@@ -126,6 +126,10 @@ typedef struct {
   float* out32;
   int64_t out32_ld;
   int32_t force_bn;         /* 0 = auto; else 32/64/128/160/256 (tuning / tests) */
+  int32_t split_k;          /* >1: split the K loop over grid.z; needs splitk_ws = split_k*M*N floats; a second pass
+                               reduces the partials in a fixed order and applies the epilogue */
+  int32_t accumulate;       /* split-K only: out32 += result (gradient accumulation over the K training steps) */
+  float* splitk_ws;
 } comat_gemm_params;
 
 int comat_gemm(const comat_gemm_params* p, void* stream);
@@ -188,6 +192,26 @@ int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, 
 size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d);
 int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
                         int n, int Lq, int Lk, int H, int d, float scale, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused classifier-free guidance + DDPM ancestral step on the fp32 latent chain.
+ * Replaces TrainableSDPipeline.py:155-167 (chunk, guidance combine, scheduler.step) when guidance_rescale == 0:
+ *   out = c_x * x + c_eps * (e_u + s (e_c - e_u)) + sigma * noise ;  eps = [e_u ; e_c] (2n floats) when cfg, else n floats.
+ * (c_eps, c_x, sigma) = comat_b200.scheduler.DDPMScheduler.step_coefficients(t).
+ * ------------------------------------------------------------------------------------------------------------ */
+int comat_cfg_ddpm_step_fwd(const float* eps, const float* x, const float* noise, float* out, long long n, float guidance,
+                            float c_eps, float c_x, float sigma, int cfg, void* stream);
+int comat_cfg_ddpm_step_bwd(const float* grad_out, float* d_eps, float* dx, long long n, float guidance, float c_eps,
+                            float c_x, int cfg, void* stream);
+
+/* Fused attention backward (tcgen05, recomputation; two launches: dQ, then dK+dV; no atomics).
+ * Inputs as the forward plus o, dO (n, Lq, H*d) 16-bit and the forward's lse.  `probs` + `dp_ext` (both fp32 (n*H, Lq, Lk),
+ * Lk <= 128) inject the gradient of the exported probabilities (attention-map loss) into the softmax backward; pass nulls
+ * otherwise.  Outputs dq / dk / dv in the layouts of q / k / v. */
+size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int H, int d);
+int comat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
+                        const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
+                        int Lq, int Lk, int H, int d, float scale, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,3 +49,28 @@ def test_cross_attention_with_probability_export(n, HW, H, d):
     assert p.shape == (n * H, HW, 77) and p.dtype == torch.float32
     assert float((p.sum(-1) - 1).abs().max()) < 1e-5
     assert rel(p, p_ref) < 2e-3 and rel(o.float(), o_ref) < 3e-3
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 6e-3), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("n,Lq,Lk,H,d,ext", [(2, 256, 256, 8, 40, False), (1, 1024, 1024, 4, 80, False), (2, 256, 256, 4, 160, False),
+                                             (2, 64, 64, 8, 160, False), (1, 4096, 4096, 1, 40, False), (2, 577, 577, 2, 64, False),
+                                             (2, 20, 577, 4, 64, False), (3, 300, 77, 8, 40, True), (2, 1024, 77, 8, 80, True),
+                                             (2, 256, 77, 8, 160, True), (2, 100, 130, 2, 32, False), (2, 4096, 77, 8, 40, True)])
+def test_attention_backward(n, Lq, Lk, H, d, ext, dtype, tol):
+    from comat_b200 import attention as A
+    torch.manual_seed(Lq * 3 + Lk + d)
+    q = torch.randn(n, Lq, H * d, device="cuda").to(dtype)
+    k = torch.randn(n, Lk, H * d, device="cuda").to(dtype)
+    v = torch.randn(n, Lk, H * d, device="cuda").to(dtype)
+    do = torch.randn(n, Lq, H * d, device="cuda").to(dtype)
+    dp = (torch.randn(n * H, Lq, Lk, device="cuda") * 0.5) if ext else None
+    o, probs, lse = A.attention_fwd_native(q, k, v, H, export_probs=ext, need_lse=True)
+    dq, dk, dv = A.attention_bwd_native(q, k, v, o, lse, probs, H, do, dp)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    o_ref, p_ref, _ = ref_attn(qr, kr, vr, H)
+    outs, grads = [o_ref], [do.float()]
+    if ext:
+        outs.append(p_ref); grads.append(dp)
+    gq, gk, gv = torch.autograd.grad(outs, (qr, kr, vr), grads)
+    for name, a, b in (("dq", dq, gq), ("dk", dk, gk), ("dv", dv, gv)):
+        assert rel(a.float(), b) < tol, (name, rel(a.float(), b))

@@ -91,3 +91,32 @@ def test_conv_with_concat_segments_and_1x1():
     out1 = ops.gemm([h.reshape(-1, C1), s.reshape(-1, C2)], [w1, w1], b_koff=(0, C1))
     ref1 = torch.cat([h, s], -1).reshape(-1, C1 + C2).float() @ w1.float().t()
     assert _rel(out1.float(), ref1)[0] < 2e-3
+
+
+def test_split_k_matches_single_pass_and_reference():
+    from comat_b200 import ops
+    torch.manual_seed(2)
+    dt = torch.float16
+    # LoRA wgrad shape: tiny output, very long K
+    a = torch.randn(320, 32768, device="cuda").to(dt)
+    b = (torch.randn(128, 32768, device="cuda") / 180).to(dt)
+    ref = a.float() @ b.float().t()
+    one = ops.gemm([a], [b], out_fp32=True, split_k=1)
+    many = ops.gemm([a], [b], out_fp32=True, split_k=37)
+    auto = ops.gemm([a], [b], out_fp32=True)
+    for o in (one, many, auto):
+        assert _rel(o, ref)[0] < 2e-3
+    acc = torch.ones(320, 128, device="cuda")
+    ops.gemm([a], [b], out=acc, split_k=8, accumulate=True)
+    assert _rel(acc, ref + 1)[0] < 2e-3
+    # conv at 8x8 with the fused epilogue applied by the reduce pass
+    x = torch.randn(8, 8, 8, 1280, device="cuda").to(dt)
+    w = (torch.randn(640, 1280, 3, 3, device="cuda") / (9 * 1280) ** 0.5).to(dt)
+    wk = w.permute(0, 2, 3, 1).reshape(640, -1).contiguous()
+    bias = torch.randn(640, device="cuda")
+    res = torch.randn(8, 8, 8, 640, device="cuda").to(dt)
+    temb = torch.randn(8, 640, device="cuda")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1) + temb[:, None, None, :] + res.float()
+    for sk in (1, 5, 0):
+        out = ops.gemm([x], [wk], bias=bias, rowvec=temb, rows_per_group=64, residual=res, conv_taps=ops.TAPS_3x3, split_k=sk)
+        assert _rel(out.float(), ref)[0] < 2e-3, sk
