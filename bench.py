@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--no_gan", action="store_true")
     p.add_argument("--no_attrcon", action="store_true")
+    p.add_argument("--no_graphs", action="store_true", help="disable CUDA-graph replay of the no-grad UNet forwards")
     p.add_argument("--profile_step", action="store_true",
                    help="run warm-up then ONE step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     return p.parse_args()
@@ -201,12 +202,14 @@ def main():
         layers = ["up_8", "up_16", "up_32"] if a.tiny else ["mid_8", "up_16", "up_32", "up_64"]
         args.train_layer_ls = layers
         register_attention_control(pipe, AttentionStore(layers))
-    blip = Blip(synthetic.build_blip(dev, dt, large=not a.tiny))
+    from comat_b200.blip_engine import BlipEngine
+    blip = Blip(BlipEngine(synthetic.build_blip(dev, dt, large=not a.tiny), dt))
     cap = CaptionModelWrapper(["Blip"], [1.0], blip)
     D = None
     if gan:
         d_unet, _ = synthetic.build_sd15(dev, dt, rank=rank_lora, seed=43, tiny=a.tiny)
         D = D_sd(EngineUNet(d_unet, dt))
+    pipe.unet.use_graphs = not a.no_graphs
     trainer = CoMatTrainer(args, pipe, cap, D, process_group=None)
     ctx_dim = 64 if a.tiny else 768
     host_batches = [synthetic.synthetic_batch(a.batch, 1000 * rank + i, ctx_dim, args.resolution, attrcon, gan, pinned=True)
@@ -282,7 +285,7 @@ def main():
                 "config": {"workload": ("TINY-DEBUG " if a.tiny else "") + "SD1.5 512^2 full CoMat (BLIP concept-match + attention-map "
                            "token/pixel loss on 2 attrcon steps + GAN G/D), S=%d DDPM steps, K=%d, batch %d/GPU, LoRA r=%d, cfg 7.5 "
                            "(BASELINE configs[1])" % (a.total_step, a.K, a.batch, rank_lora),
-                           "global_batch": a.batch * world, "parallelism": f"dp{world}",
+                           "global_batch": a.batch * world, "parallelism": f"dp{world}", "cuda_graphs": not a.no_graphs,
                            "l2_policy": "inputs rotate over 4 batches; per-step working set (weights 7 GB + activations > 50 GB) exceeds the 126 MB L2",
                            "samples_per_sec": value * a.batch * world,
                            "library_calls_per_step": lib_calls / a.steps,

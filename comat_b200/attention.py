@@ -18,10 +18,10 @@ from . import _lib
 
 IMPL = "native"          # forward: tcgen05 kernel when the shape is covered; backward: library path for now (round 1)
 LIBRARY_CALLS = 0
-NATIVE_HEAD_DIMS = (16, 32, 40, 64, 80, 160)
+NATIVE_HEAD_DIMS = (16, 32, 40, 64, 80, 128, 160)
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
-_lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp])
-_lib.register_signature("comat_attention_bwd", [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _i, _vp])
+_lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
+_lib.register_signature("comat_attention_bwd", [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
 NATIVE_BWD = True
 _DT = {torch.float16: 1, torch.bfloat16: 2}
 
@@ -31,7 +31,7 @@ def native_supported(q, k, heads, export_probs):
     return (q.is_cuda and q.dtype in _DT and d in NATIVE_HEAD_DIMS and (not export_probs or k.shape[1] <= 128))
 
 
-def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False):
+def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False, kv_lens=None, causal=False):
     """tcgen05 fused attention forward (csrc/attention.cu).  returns (o, probs | None, lse | None)"""
     q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
     n, Lq, Cq = q.shape
@@ -46,7 +46,8 @@ def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False):
     lse = torch.empty(n * heads, Lq, dtype=torch.float32, device=q.device) if need_lse else None
     _lib.check(L.comat_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
                                      None if probs is None else probs.data_ptr(), None if lse is None else lse.data_ptr(),
-                                     ws.data_ptr(), n, Lq, Lk, heads, d, float(d) ** -0.5, _DT[q.dtype], _lib.stream_ptr()),
+                                     ws.data_ptr(), n, Lq, Lk, heads, d, float(d) ** -0.5, _DT[q.dtype],
+                                     None if kv_lens is None else kv_lens.data_ptr(), int(causal), _lib.stream_ptr()),
                "attention_fwd")
     _lib.count_launch(2)
     return o, probs, lse
@@ -57,9 +58,43 @@ def _split(x, heads):
     return x.reshape(n, L, heads, Cc // heads).permute(0, 2, 1, 3)        # (n, h, L, d)
 
 
+def attention_unfused_fwd(q, k, v):
+    """single-head attention with a head dim beyond the fused kernel's TMEM budget (VAE mid-block: d = 512, 4096 tokens):
+    S = scale Q K^T and O = P V on the tcgen05 GEMM, row softmax in between.  returns (o, [P per sample])."""
+    from . import ops
+    n, L, d = q.shape
+    outs, ps = [], []
+    for b in range(n):
+        s = ops.gemm([q[b]], [k[b]], alpha=float(d) ** -0.5)                 # (Lq, Lk)
+        p = ops.softmax_rows(s)
+        outs.append(ops.gemm([p], [ops.transpose16(v[b], 8)]))               # P V : B operand = V^T (d, Lk)
+        ps.append(p)
+    return torch.stack(outs), ps
+
+
+def attention_unfused_bwd(q, k, v, ps, do):
+    from . import ops
+    n, L, d = q.shape
+    scale = float(d) ** -0.5
+    dq, dk, dv = [], [], []
+    for b in range(n):
+        p, g = ps[b], do[b].contiguous()
+        dv.append(ops.gemm([ops.transpose16(p, 8)], [ops.transpose16(g, 8)]))      # P^T dO
+        dp = ops.gemm([g], [v[b]])                                                  # dO V^T
+        ds = ops.softmax_rows(p, dp)
+        dq.append(ops.gemm([ds], [ops.transpose16(k[b], 8)], alpha=scale))          # dS K
+        dk.append(ops.gemm([ops.transpose16(ds, 8)], [ops.transpose16(q[b], 8)], alpha=scale))   # dS^T Q
+    return torch.stack(dq), torch.stack(dk), torch.stack(dv)
+
+
 def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
     """q: (n, Lq, C), k/v: (n, Lk, C) 16-bit.  returns (o (n, Lq, C), probs fp32 (n*heads, Lq, Lk) | None, saved)"""
     global LIBRARY_CALLS
+    if (IMPL == "native" and heads == 1 and not export_probs and q.is_cuda and q.dtype in _DT and q.shape[-1] > 160
+            and q.shape[-1] % 64 == 0 and k.shape[1] % 8 == 0 and k.shape[1] <= 8192):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, ps = attention_unfused_fwd(q, k, v)
+        return o, None, (("unfused", q, k, v, ps) if need_bwd else None)
     if IMPL == "native" and native_supported(q, k, heads, export_probs):
         o, probs, lse = attention_fwd_native(q, k, v, heads, export_probs, need_lse=need_bwd and NATIVE_BWD)
         if not need_bwd:
@@ -84,7 +119,7 @@ def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
     return o, probs, saved
 
 
-def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs):
+def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None, causal=False):
     """tcgen05 fused attention backward (csrc/attention_bwd.cu): (dq, dk, dv)."""
     n, Lq, Cq = q.shape
     Lk = k.shape[1]
@@ -100,13 +135,17 @@ def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs):
     _lib.check(L.comat_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
                                      None if dprobs is None else probs.data_ptr(), None if dprobs is None else dprobs.data_ptr(),
                                      dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), n, Lq, Lk, heads, d,
-                                     float(d) ** -0.5, _DT[q.dtype], _lib.stream_ptr()), "attention_bwd")
+                                     float(d) ** -0.5, _DT[q.dtype], None if kv_lens is None else kv_lens.data_ptr(), int(causal),
+                                     _lib.stream_ptr()), "attention_bwd")
     _lib.count_launch(6)
     return dq, dk, dv
 
 
 def attention_bwd(saved, do, dprobs):
     global LIBRARY_CALLS
+    if saved[0] == "unfused":
+        _, q, k, v, ps = saved
+        return attention_unfused_bwd(q, k, v, ps, do)
     if saved[0] == "native":
         _, q, k, v, o, lse, probs, heads = saved
         return attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs)

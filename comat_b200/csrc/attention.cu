@@ -32,6 +32,8 @@ struct AttnKP {
   long long out_ld;    // H*d
   uint32_t idesc_qk, idesc_pv;
   int is_bf16;
+  const int* kv_lens;  // per-sample number of valid keys (padding mask) or null
+  int causal;          // key index <= query index (BLIP text decoder self-attention)
 };
 
 template <int D>
@@ -172,12 +174,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < NT; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kvalid = min(ATT_BN, p.Lk - j * ATT_BN);
+      const int klen = (p.kv_lens != nullptr) ? min(p.Lk, p.kv_lens[b]) : p.Lk;
+      const int ktile = min(ATT_BN, klen - j * ATT_BN);                       // warp-uniform loop bound
+      const int kvalid = p.causal ? min(ktile, m0 + r - j * ATT_BN + 1) : ktile;   // per-row limit
       // pass 1: row max
       float mt = -INFINITY;
 #pragma unroll 1
       for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-        if (c0 >= kvalid) break;
+        if (c0 >= ktile) break;
         uint32_t v[32];
         tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -186,14 +190,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (c0 + i < kvalid) mt = fmaxf(mt, __uint_as_float(v[i]));
       }
       const float m_new = fmaxf(m_run, mt);
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);     // exp2(-inf) = 0 on the first tile
-      const float mneg = m_new * p.scale_log2;
+      const float alpha = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);   // exp2(-inf) = 0 on the first tile
+      const float mneg = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
       // pass 2: p = exp2(s*sl2 - m*sl2), row sum, 16-bit P into swizzled smem (K-major, two 64-key halves)
       float lsum = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
         uint32_t v[32];
-        if (c0 < kvalid) {
+        if (c0 < ktile) {
           tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
           tmem_ld_wait();
         }
@@ -310,9 +314,10 @@ extern "C" size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d) {
 }
 
 extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
-                                   int n, int Lq, int Lk, int H, int d, float scale, int dtype, void* stream) {
+                                   int n, int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal,
+                                   void* stream) {
   if (!q || !k || !v || !out || !workspace || n <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return COMAT_ERR_INVALID;
-  if (d != 40 && d != 64 && d != 80 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
+  if (d != 40 && d != 64 && d != 80 && d != 128 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
   if (dtype != COMAT_F16 && dtype != COMAT_BF16) return COMAT_ERR_UNSUPPORTED;
   if (probs && Lk > ATT_BN) return COMAT_ERR_UNSUPPORTED;
   if (((H * d) % 8) != 0 || (d % 8) != 0) return COMAT_ERR_INVALID;
@@ -327,6 +332,7 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
   memset(&kp, 0, sizeof(kp));
   kp.Lq = Lq; kp.Lk = Lk; kp.H = H; kp.d = d; kp.n_kv_tiles = (Lk + ATT_BN - 1) / ATT_BN;
   kp.scale = scale; kp.scale_log2 = scale * 1.4426950408889634f;
+  kp.kv_lens = kv_lens; kp.causal = causal;
   kp.out = out; kp.probs = probs; kp.lse = lse; kp.out_ld = (long long)H * d; kp.is_bf16 = dtype == COMAT_BF16;
   const int fmt = kp.is_bf16 ? 1 : 0;
   const int DN = (d + 15) / 16 * 16;
@@ -351,7 +357,7 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
   case DD:                                                                                \
     return kp.is_bf16 ? launch_attn<DD, __nv_bfloat16>(maps, kp, grid, st) : launch_attn<DD, __half>(maps, kp, grid, st);
   switch (d) {
-    ATT_CASE(16) ATT_CASE(32) ATT_CASE(40) ATT_CASE(64) ATT_CASE(80) ATT_CASE(160)
+    ATT_CASE(16) ATT_CASE(32) ATT_CASE(40) ATT_CASE(64) ATT_CASE(80) ATT_CASE(128) ATT_CASE(160)
   }
 #undef ATT_CASE
   return COMAT_ERR_UNSUPPORTED;

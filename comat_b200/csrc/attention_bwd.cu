@@ -32,6 +32,8 @@ struct AttnBwdKP {
   void* out1;             // MODE 1: dV
   long long out_ld;
   uint32_t idesc_s, idesc_acc;
+  const int* kv_lens;
+  int causal;
 };
 
 template <int D, int MODE>
@@ -206,6 +208,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       lse_r = p.lse_pad[(size_t)bh * p.Lq_pad + xrow] * 1.4426950408889634f;
       D_r = p.D_pad[(size_t)bh * p.Lq_pad + xrow];
     }
+    const int klen = (p.kv_lens != nullptr) ? min(p.Lk, p.kv_lens[b]) : p.Lk;
     int stage = 0, phase = 0;
     for (int it = 0; it < NI; ++it) {
       mbar_wait(s_full, it & 1);
@@ -229,12 +232,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
             const int y = y0 + c;
             float pr, dp = __uint_as_float(vd[i + e]);
             if (MODE == 0) {
-              pr = (y < p.Lk) ? exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_r) : 0.f;
+              const bool kv_ok = (y < klen) && (!p.causal || y <= xrow);
+              pr = kv_ok ? exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_r) : 0.f;
               if (p.dp_ext != nullptr && y < p.Lk && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + xrow) * p.Lk + y];
               dsv[e] = pr * (dp - D_r);
             } else {
               const float lse_c = vec[c] * 1.4426950408889634f, D_c = vec[Cf::BY + c];
-              pr = exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_c);     // lse pad = 1e30 -> 0 beyond Lq
+              const bool kv_ok = (xrow < klen) && (!p.causal || xrow <= y);
+              pr = kv_ok ? exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_c) : 0.f;   // lse pad = 1e30 -> 0 beyond Lq
               if (p.dp_ext != nullptr && y < p.Lq && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + y) * p.Lk + xrow];
               dsv[e] = pr * (dp - D_c);
             }
@@ -400,9 +405,9 @@ extern "C" size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int
 
 extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
                                    const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
-                                   int Lq, int Lk, int H, int d, float scale, int dtype, void* stream) {
+                                   int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal, void* stream) {
   if (!q || !k || !v || !o || !dO || !lse || !dq || !dk || !dv || !workspace) return COMAT_ERR_INVALID;
-  if (d != 40 && d != 64 && d != 80 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
+  if (d != 40 && d != 64 && d != 80 && d != 128 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
   if (dtype != COMAT_F16 && dtype != COMAT_BF16) return COMAT_ERR_UNSUPPORTED;
   if (dp_ext && !probs) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
@@ -427,13 +432,14 @@ extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, 
   memset(&kp, 0, sizeof(kp));
   kp.Lq = Lq; kp.Lk = Lk; kp.H = H; kp.d = d; kp.Lq_pad = Lqp; kp.Lk_pad = Lkp;
   kp.scale = scale; kp.scale_log2 = scale * 1.4426950408889634f;
+  kp.kv_lens = kv_lens; kp.causal = causal;
   kp.lse_pad = lse_pad; kp.D_pad = D_pad; kp.dp_ext = dp_ext; kp.out_ld = (long long)H * d;
   const int fmt = dtype == COMAT_BF16 ? 1 : 0;
 #define AB_CASE(DD)                                                                                                          \
   case DD:                                                                                                                   \
     return fmt ? run_bwd<DD, __nv_bfloat16>(q, k, v, dO, qT, kT, dOT, kp, n, dq, dk, dv, fmt, st)                            \
                : run_bwd<DD, __half>(q, k, v, dO, qT, kT, dOT, kp, n, dq, dk, dv, fmt, st);
-  switch (d) { AB_CASE(16) AB_CASE(32) AB_CASE(40) AB_CASE(64) AB_CASE(80) AB_CASE(160) }
+  switch (d) { AB_CASE(16) AB_CASE(32) AB_CASE(40) AB_CASE(64) AB_CASE(80) AB_CASE(128) AB_CASE(160) }
 #undef AB_CASE
   return COMAT_ERR_UNSUPPORTED;
 }

@@ -517,3 +517,90 @@ extern "C" int comat_copy2d16(const void* src, void* dst, long long rows, int co
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
+
+// ============================================================================================== row softmax (unfused attention)
+// Used for attention layers whose head dim exceeds the fused kernel's TMEM budget (the VAE decoder's single-head d=512
+// mid-block attention over 4096 tokens): S = Q K^T and O = P V run on the tcgen05 GEMM, this kernel is the softmax between.
+namespace comat {
+template <typename T, int MODE>   // 0: p = softmax(x) ; 1: ds = p * (dp - sum(p*dp))
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const T* __restrict__ x, const T* __restrict__ dp, T* __restrict__ out, int Ccols) {
+  __shared__ float sm[8];
+  const size_t row = blockIdx.x;
+  const T* xr = x + row * Ccols;
+  const int nv = Ccols / 8;
+  constexpr int MAXV = 4;                       // up to 8192 columns
+  Vec8<T> xv[MAXV], dv[MAXV];
+  float m = -INFINITY, s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int v = threadIdx.x + k * 256;
+    if (v < nv) {
+      xv[k].load(xr + v * 8);
+      if (MODE == 1) dv[k].load(dp + row * Ccols + v * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE == 0) m = fmaxf(m, xv[k].get(i));
+        else s += xv[k].get(i) * dv[k].get(i);
+      }
+    }
+  }
+  auto block_sum = [&](float v, bool is_max) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = sm[0];
+    for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, sm[i]) : r + sm[i];
+    return r;
+  };
+  if (MODE == 0) {
+    m = block_sum(m, true);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int v = threadIdx.x + k * 256;
+      if (v < nv) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += __expf(xv[k].get(i) - m);
+      }
+    }
+    s = block_sum(s, false);
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int v = threadIdx.x + k * 256;
+      if (v < nv) {
+        Vec8<T> o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.set(i, __expf(xv[k].get(i) - m) * inv);
+        o.store(out + row * Ccols + v * 8);
+      }
+    }
+  } else {
+    s = block_sum(s, false);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int v = threadIdx.x + k * 256;
+      if (v < nv) {
+        Vec8<T> o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.set(i, xv[k].get(i) * (dv[k].get(i) - s));
+        o.store(out + row * Ccols + v * 8);
+      }
+    }
+  }
+}
+}  // namespace comat
+
+extern "C" int comat_softmax_rows(const void* x, const void* dp, void* out, long long rows, int cols, int mode, int dtype, void* stream) {
+  if (!x || !out || cols % 8 || cols > 8192 || (mode == 1 && !dp)) return COMAT_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == COMAT_F16) {
+    if (mode == 0) comat::softmax_rows_kernel<__half, 0><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, nullptr, (__half*)out, cols);
+    else comat::softmax_rows_kernel<__half, 1><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, (const __half*)dp, (__half*)out, cols);
+  } else if (dtype == COMAT_BF16) {
+    if (mode == 0) comat::softmax_rows_kernel<__nv_bfloat16, 0><<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)out, cols);
+    else comat::softmax_rows_kernel<__nv_bfloat16, 1><<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dp, (__nv_bfloat16*)out, cols);
+  } else return COMAT_ERR_UNSUPPORTED;
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}

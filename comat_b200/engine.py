@@ -98,9 +98,14 @@ class LoRAW:
         self.refresh()
 
     def refresh(self):
+        """re-materialise the 16-bit operands IN PLACE (stable addresses: captured CUDA graphs keep reading them)."""
         d, u = self.down.detach(), self.up.detach()
-        self.down16, self.up16 = d.to(self.dtype).contiguous(), u.to(self.dtype).contiguous()
-        self.down16_t, self.up16_t = d.t().to(self.dtype).contiguous(), u.t().to(self.dtype).contiguous()
+        if getattr(self, "down16", None) is None:
+            self.down16, self.up16 = d.to(self.dtype).contiguous(), u.to(self.dtype).contiguous()
+            self.down16_t, self.up16_t = d.t().to(self.dtype).contiguous(), u.t().to(self.dtype).contiguous()
+        else:
+            self.down16.copy_(d); self.up16.copy_(u)
+            self.down16_t.copy_(d.t()); self.up16_t.copy_(u.t())
 
 
 class NormW:

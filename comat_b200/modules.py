@@ -52,6 +52,40 @@ class _UNetFn(torch.autograd.Function):
         return (None, gx, None, None, None, None, None, *lg)
 
 
+class _GraphedForward:
+    """One captured no-grad UNet forward (fixed shapes): ~700 launches replayed by a single cudaGraphLaunch.
+    CUDA graphs instead of a tracing compiler — the executor's Python runs once, at capture."""
+
+    def __init__(self, mod: "EngineUNet", sample, t, ehs):
+        from . import _lib
+        eng = mod.engine
+        self.x = torch.empty_like(sample)
+        self.t = torch.zeros((), dtype=torch.int64, device=sample.device)
+        self.ehs = torch.empty_like(ehs)
+        self.x.copy_(sample); self.t.copy_(t.reshape(())); self.ehs.copy_(ehs)
+
+        def run():
+            out = eng.forward(None, E.Var(ops.latent_to_nhwc(self.x, eng.dtype, 64), False), self.t, self.ehs.to(eng.dtype))
+            return ops.nhwc_to_nchw_f32(out.v, mod.out_channels)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()                                   # eager warm-up on the side stream (one-time attribute / entry-point setup)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCH_COUNT
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+        self.launches = _lib.LAUNCH_COUNT - l0
+
+    def __call__(self, sample, t, ehs):
+        from . import _lib
+        self.x.copy_(sample); self.t.copy_(t.reshape(())); self.ehs.copy_(ehs)
+        self.graph.replay()
+        _lib.count_launch(self.launches)
+        return self.out.clone()
+
+
 class EngineUNet(torch.nn.Module):
     """Wraps a diffusers-shaped UNet2DConditionModel (parameters + LoRA layers live there, state-dict compatible) and
     executes it with the B200 kernels."""
@@ -67,6 +101,8 @@ class EngineUNet(torch.nn.Module):
         self.capture: Optional[E.AttnCapture] = None
         self.last_probs = None
         self._dtype = dtype
+        self.use_graphs = False                # bench / trainer switch: CUDA-graph the no-grad forwards of the rollout
+        self._graphs = {}
 
     @property
     def dtype(self):
@@ -97,6 +133,12 @@ class EngineUNet(torch.nn.Module):
         if want_grad:
             outs = _UNetFn.apply(self, sample, t, encoder_hidden_states, added_cond_kwargs, capture, len(params), *params)
             eps, probs = outs[0], outs[1:]
+        elif self.use_graphs and capture is None and added_cond_kwargs is None and sample.is_cuda:
+            key = (tuple(sample.shape), tuple(encoder_hidden_states.shape), sample.dtype, encoder_hidden_states.dtype)
+            if key not in self._graphs:
+                self._graphs[key] = _GraphedForward(self, sample.detach(), t, encoder_hidden_states.detach())
+            eps = self._graphs[key](sample.detach(), t, encoder_hidden_states.detach()).to(sample.dtype)
+            probs = ()
         else:
             eng = self.engine
             out = eng.forward(None, E.Var(ops.latent_to_nhwc(sample, eng.dtype, 64), False), t,

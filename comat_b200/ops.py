@@ -291,3 +291,16 @@ def nhwc_to_nchw_f32(x, cout, scale=1.0):
     out = torch.empty(n, cout, H, W, dtype=torch.float32, device=x.device)
     _call("comat_nhwc_to_nchw_f32", x.data_ptr(), out.data_ptr(), n, cout, H * W, ld, scale, DT[x.dtype], _lib.stream_ptr())
     return out
+
+
+_lib.register_signature("comat_softmax_rows", [_vp, _vp, _vp, _ll, _i, _i, _i, _vp])
+
+
+def softmax_rows(x, dp=None):
+    """x (R, C) 16-bit -> softmax over C; with ``dp``: x are probabilities and the result is p * (dp - sum(p*dp))."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _call("comat_softmax_rows", x.data_ptr(), _p(dp.contiguous() if dp is not None else None), out.data_ptr(), x.shape[0], x.shape[1],
+          0 if dp is None else 1, DT[x.dtype], _lib.stream_ptr())
+    return out

@@ -162,6 +162,9 @@ int comat_elementwise(const void* x, const void* y, void* out, long long numel, 
 int comat_spatial(const void* in, void* out, int n, int H, int W, int C, int mode, int dtype, void* stream);
 /* 16-bit (R, Cc) -> (Cc, ld_out >= R) */
 int comat_transpose16(const void* in, void* out, int R, int Cc, int ld_out, void* stream);
+/* row softmax (mode 0: out = softmax(x)) and its backward (mode 1: out = x * (dp - sum(x*dp)), x = probabilities); 16-bit,
+ * cols % 8 == 0, cols <= 8192.  The softmax between the two GEMMs of an unfused attention (VAE mid-block, d = 512). */
+int comat_softmax_rows(const void* x, const void* dp, void* out, long long rows, int cols, int mode, int dtype, void* stream);
 int comat_copy2d16(const void* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst, void* stream);
 /* fp32 NCHW latents -> 16-bit NHWC zero-padded to Cpad channels (x scale), and back (first Cout of ld channels) */
 int comat_latent_to_nhwc(const float* in, void* out, int n, int Cin, int HW, int Cpad, float scale, int dtype, void* stream);
@@ -183,15 +186,16 @@ int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, 
  * Fused multi-head attention forward (tcgen05, flash-style):  out = softmax(scale * q k^T) v  per (sample, head).
  * Replaces the hooked Attention.forward arithmetic (attn_utils/tc_attn_utils.py:126-145: baddbmm + softmax + bmm) and
  * F.scaled_dot_product_attention inside diffusers' Attention / HF BLIP attention.
- *   q (n, Lq, H*d), k/v (n, Lk, H*d), out (n, Lq, H*d): 16-bit token-major.  d in {16, 32, 40, 64, 80, 160}.
+ *   q (n, Lq, H*d), k/v (n, Lk, H*d), out (n, Lq, H*d): 16-bit token-major.  d in {16, 32, 40, 64, 80, 128, 160}.
  *   probs : optional fp32 (n*H, Lq, Lk) export of the normalised probabilities (Lk <= 128) — the tensor AttentionStore
  *           clones for the attention-map loss (tc_attn_utils.py:60-68); null to skip.
  *   lse   : optional fp32 (n*H, Lq) log-sum-exp (saved for backward); null to skip.
  *   workspace: comat_attention_workspace_bytes() bytes (V^T staging).
  * ------------------------------------------------------------------------------------------------------------ */
 size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d);
+/* kv_lens: optional int32[n] valid-key counts (padding mask); causal != 0: key index <= query index. */
 int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
-                        int n, int Lq, int Lk, int H, int d, float scale, int dtype, void* stream);
+                        int n, int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused classifier-free guidance + DDPM ancestral step on the fp32 latent chain.
@@ -211,7 +215,25 @@ int comat_cfg_ddpm_step_bwd(const float* grad_out, float* d_eps, float* dx, long
 size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int H, int d);
 int comat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
                         const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
-                        int Lq, int Lk, int H, int d, float scale, int dtype, void* stream);
+                        int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal, void* stream);
+
+/* Separable table-driven 2-D resampling with a fused per-channel affine (fp32 NCHW):
+ *   out[b,c,oy,ox] = scale[c] * sum_{ky<yc[oy]} sum_{kx<xc[ox]} wy[oy*KY+ky] * wx[ox*KX+kx] * in[b,c,ys[oy]+ky,xs[ox]+kx] + shift[c]
+ * With aten's bicubic-antialias taps this is Resize(384, BICUBIC, antialias) + Normalize of caption_blip.py:33-36,45;
+ * with the transposed tables it is its backward.  scale / shift may be null. */
+int comat_resample2d(const float* in, float* out, const int* ys, const int* yc, const float* wy, const int* xs, const int* xc,
+                     const float* wx, const float* scale, const float* shift, int B, int C, int IH, int IW, int OH, int OW,
+                     int KY, int KX, void* stream);
+
+/* Cross-entropy with label smoothing, mean over rows whose label != ignore_index — the caption NLL of
+ * HF BlipTextLMHeadModel (modeling_blip_text.py:764-775) behind concept_mat_utils/caption_blip.py:57.
+ *   fwd : logits fp32 (R, ld >= V), labels int64 (R) -> row_stats (R,2) = {lse, row loss}, out2 = {mean loss, #valid rows}
+ *   bwd : dlogits16 (R, Vpad) 16-bit, zero padded = grad_out[0] / #valid * (softmax - (1-eps) onehot - eps/V) */
+int comat_ce_label_smooth_fwd(const float* logits, const long long* labels, float* row_stats, float* out2, int R, int V,
+                              long long ld, float eps, long long ignore_index, void* stream);
+int comat_ce_label_smooth_bwd(const float* logits, const long long* labels, const float* row_stats, const float* out2,
+                              const float* grad_out, void* dlogits16, int R, int V, int Vpad, long long ld, float eps,
+                              long long ignore_index, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

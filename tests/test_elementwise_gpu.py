@@ -106,3 +106,20 @@ def test_stride2_conv_via_space_to_depth():
     out = ops.gemm([ops.spatial(x, "s2d")], [wk], bias=bias, conv_taps=taps)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
     assert rel(out.float(), ref) < 2e-3
+
+
+def test_bicubic_aa_resize_normalize_fwd_bwd():
+    """concept_mat_utils/caption_blip.py:33-36,45 — native table-driven kernel vs aten upsample_bicubic2d_aa + Normalize."""
+    from comat_b200 import image_ops as IO
+    torch.manual_seed(0)
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    for size_in in (510, 254):
+        x = torch.rand(2, 3, size_in, size_in, device="cuda", requires_grad=True)
+        y = IO.resize_bicubic_aa_normalize(x, 384, mean, std)
+        g = torch.randn_like(y)
+        y.backward(g)
+        xr = x.detach().clone().requires_grad_(True)
+        ref = F.interpolate(xr, size=(384, 384), mode="bicubic", antialias=True, align_corners=False)
+        ref = (ref - torch.tensor(mean, device="cuda").view(1, 3, 1, 1)) / torch.tensor(std, device="cuda").view(1, 3, 1, 1)
+        ref.backward(g)
+        assert rel(y, ref) < 1e-5 and rel(x.grad, xr.grad) < 1e-5

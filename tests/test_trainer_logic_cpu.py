@@ -17,7 +17,15 @@ def rel(a, b):
 
 def _emulate_cuda_only(monkeypatch):
     EMU.install(monkeypatch)
-    from comat_b200 import attn_loss, optim
+    from comat_b200 import attn_loss, image_ops, optim
+    import torch.nn.functional as F
+
+    def resize_norm(images, size, mean, std):
+        x = F.interpolate(images.float(), size=(size, size), mode="bicubic", antialias=True, align_corners=False)
+        m = torch.tensor(mean).view(1, -1, 1, 1)
+        sd = torch.tensor(std).view(1, -1, 1, 1)
+        return (x - m) / sd
+    monkeypatch.setattr(image_ops, "resize_bicubic_aa_normalize", resize_norm)
 
     def get_mask_loss(attn_map, words, masks, layers, tokens=77):
         some = next(iter(next(iter(attn_map.values())).values()))[0]
