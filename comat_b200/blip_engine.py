@@ -24,6 +24,27 @@ _lib.register_signature("comat_ce_label_smooth_fwd", [_vp, _vp, _vp, _vp, _i, _i
 _lib.register_signature("comat_ce_label_smooth_bwd", [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _f, _ll, _i, _vp])
 
 
+def ce_fwd(logits, labels, V, eps):
+    """label-smoothed CE over fp32 logits (R, ld): returns (row_stats (R,2), out2 = {mean loss, #valid})."""
+    R = logits.shape[0]
+    stats = torch.empty(R, 2, dtype=torch.float32, device=logits.device)
+    out2 = torch.empty(2, dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.lib().comat_ce_label_smooth_fwd(logits.data_ptr(), labels.data_ptr(), stats.data_ptr(), out2.data_ptr(), R, V,
+                                                    logits.stride(0), eps, -100, _lib.stream_ptr()), "ce_fwd")
+    _lib.count_launch(2)
+    return stats, out2
+
+
+def ce_bwd(logits, labels, stats, out2, gout, V, Vpad, eps, dtype):
+    R = logits.shape[0]
+    d = torch.empty(R, Vpad, dtype=dtype, device=logits.device)
+    _lib.check(_lib.lib().comat_ce_label_smooth_bwd(logits.data_ptr(), labels.data_ptr(), stats.data_ptr(), out2.data_ptr(),
+                                                    gout.float().contiguous().data_ptr(), d.data_ptr(), R, V, Vpad, logits.stride(0), eps,
+                                                    -100, ops.DT[dtype], _lib.stream_ptr()), "ce_bwd")
+    _lib.count_launch()
+    return d
+
+
 def _gelu(tape, x: E.Var) -> E.Var:
     out = E.Var(ops.elementwise("gelu", x.v))
     if tape is not None:
@@ -185,21 +206,12 @@ class BlipEngine:
         R = B * (T - 1)
         logits = ops.gemm([t.v], [self.dec_w], bias=self.dec_b, out_fp32=True)              # (R, V) fp32
         lab = labels[:, 1:].contiguous().reshape(-1).to(torch.int64)
-        stats = torch.empty(R, 2, dtype=torch.float32, device=logits.device)
-        out2 = torch.empty(2, dtype=torch.float32, device=logits.device)
-        L = _lib.lib()
-        _lib.check(L.comat_ce_label_smooth_fwd(logits.data_ptr(), lab.data_ptr(), stats.data_ptr(), out2.data_ptr(), R, self.V,
-                                               logits.stride(0), self.eps_ls, -100, _lib.stream_ptr()), "ce_fwd")
-        _lib.count_launch(2)
+        stats, out2 = ce_fwd(logits, lab, self.V, self.eps_ls)
         loss = E.Var(out2[:1])
         if tape is not None:
             def bwd_ce():
                 gout = loss.g if loss.g is not None else torch.ones(1, device=logits.device)
-                d = torch.empty(R, self.Vpad, dtype=self.dtype, device=logits.device)
-                _lib.check(L.comat_ce_label_smooth_bwd(logits.data_ptr(), lab.data_ptr(), stats.data_ptr(), out2.data_ptr(),
-                                                       gout.float().contiguous().data_ptr(), d.data_ptr(), R, self.V, self.Vpad,
-                                                       logits.stride(0), self.eps_ls, -100, ops.DT[self.dtype], _lib.stream_ptr()), "ce_bwd")
-                _lib.count_launch()
+                d = ce_bwd(logits, lab, stats, out2, gout, self.V, self.Vpad, self.eps_ls, self.dtype)
                 E._acc(t, ops.gemm([d], [self.dec_wt]))                                       # (R, hid)
             tape.record(bwd_ce)
         return loss

@@ -170,45 +170,77 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int i = 0; i < Cf::DN; ++i) o[i] = 0.f;
     float m_used = 0.f;
+    const int klen = (p.kv_lens != nullptr) ? min(p.Lk, p.kv_lens[b]) : p.Lk;
 
     for (int j = 0; j < NT; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int klen = (p.kv_lens != nullptr) ? min(p.Lk, p.kv_lens[b]) : p.Lk;
       const int ktile = min(ATT_BN, klen - j * ATT_BN);                       // warp-uniform loop bound
       const int kvalid = p.causal ? min(ktile, m0 + r - j * ATT_BN + 1) : ktile;   // per-row limit
-      // pass 1: row max
+      // warp-uniform: every row of this warp sees all 128 keys of the tile -> predicate-free fast path
+      const bool full_w = (ktile == ATT_BN) && (!p.causal || (m0 + q4 * 32 - j * ATT_BN + 1 >= ATT_BN));
       float mt = -INFINITY;
+      if (full_w) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-        if (c0 >= ktile) break;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
-        tmem_ld_wait();
+        for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float m0_ = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1_ = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < kvalid) mt = fmaxf(mt, __uint_as_float(v[i]));
+          for (int i = 4; i < 32; i += 2) {
+            m0_ = fmaxf(m0_, __uint_as_float(v[i]));
+            m1_ = fmaxf(m1_, __uint_as_float(v[i + 1]));
+          }
+          mt = fmaxf(mt, fmaxf(m0_, m1_));
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+          if (c0 >= ktile) break;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < kvalid) mt = fmaxf(mt, __uint_as_float(v[i]));
+        }
       }
       const float m_new = fmaxf(m_run, mt);
-      const float alpha = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * p.scale_log2);   // exp2(-inf) = 0 on the first tile
+      const float alpha = (m_new == -INFINITY) ? 1.f : fast_exp2((m_run - m_new) * p.scale_log2);   // exp2(-inf) = 0 on the first tile
       const float mneg = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
       // pass 2: p = exp2(s*sl2 - m*sl2), row sum, 16-bit P into swizzled smem (K-major, two 64-key halves)
       float lsum = 0.f;
+      const float sl2 = p.scale_log2;
 #pragma unroll 1
       for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
         uint32_t v[32];
-        if (c0 < ktile) {
+        uint32_t pk[16];
+        if (full_w) {
           tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
           tmem_ld_wait();
-        }
-        uint32_t pk[16];
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0 = 0.f, e1 = 0.f;
-          if (c0 + i < kvalid) e0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - mneg);
-          if (c0 + i + 1 < kvalid) e1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - mneg);
-          lsum += e0 + e1;
-          pk[i / 2] = pack2<T>(e0, e1);
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), sl2, -mneg));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sl2, -mneg));
+            s0 += e0; s1 += e1;
+            pk[i / 2] = pack2<T>(e0, e1);
+          }
+          lsum += s0 + s1;
+        } else {
+          if (c0 < ktile) {
+            tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float e0 = 0.f, e1 = 0.f;
+            if (c0 + i < kvalid) e0 = fast_exp2(__uint_as_float(v[i]) * sl2 - mneg);
+            if (c0 + i + 1 < kvalid) e1 = fast_exp2(__uint_as_float(v[i + 1]) * sl2 - mneg);
+            lsum += e0 + e1;
+            pk[i / 2] = pack2<T>(e0, e1);
+          }
         }
         // 32 keys = 4 x 16-byte chunks of row r in half (c0/64): chunk index cc = (c0%64)/8 + q
         unsigned char* base = sP + (c0 / 64) * (ATT_BM * 128) + (r / 8) * 1024 + (r % 8) * 128;
@@ -254,18 +286,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.Lq + m0 + r] = m_used * p.scale + logf(l_run);
     }
     if (p.probs != nullptr) {
-      // single-tile case: S is still in TMEM; write softmax(S) as fp32 (n*H, Lq, Lk)
-      if (row_ok) {
-        float* pp = p.probs + (((size_t)b * p.H + h) * p.Lq + m0 + r) * p.Lk;
-        const float mneg = m_used * p.scale_log2;
+      // single-tile case: S is still in TMEM; write softmax(S) as fp32 (n*H, Lq, Lk).  tcgen05.ld is .sync.aligned: the whole
+      // warp executes the loads, only the stores are predicated on the row being valid.
+      float* pp = p.probs + (((size_t)b * p.H + h) * p.Lq + m0 + r) * p.Lk;
+      const float mneg = m_used * p.scale_log2;
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.Lk; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
-          tmem_ld_wait();
+      for (int c0 = 0; c0 < p.Lk; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Lk) pp[c0 + i] = exp2f(__uint_as_float(v[i]) * p.scale_log2 - mneg) * inv_l;
+            if (c0 + i < p.Lk) pp[c0 + i] = fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - mneg) * inv_l;
         }
       }
       tc_fence_before();

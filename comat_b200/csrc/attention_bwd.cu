@@ -25,7 +25,7 @@ struct AttnBwdKP {
   int Lq_pad, Lk_pad;
   int n_inner;
   float scale, scale_log2;
-  const float* lse_pad;   // (n*H, Lq_pad), padded with +1e30
+  const float* lse_pad;   // (n*H, Lq_pad), lse * log2(e), padded with +1e30
   const float* D_pad;     // (n*H, Lq_pad), padded with 0
   const float* dp_ext;    // (n*H, Lq, Lk) fp32 or null
   void* out0;             // MODE 0: dQ (n, Lq, H*d) ; MODE 1: dK (n, Lk, H*d)
@@ -205,7 +205,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
     const bool row_ok = xrow < Lx;
     float lse_r = 0.f, D_r = 0.f;
     if (MODE == 0) {
-      lse_r = p.lse_pad[(size_t)bh * p.Lq_pad + xrow] * 1.4426950408889634f;
+      lse_r = p.lse_pad[(size_t)bh * p.Lq_pad + xrow];      // already multiplied by log2(e) by the pre-pass
       D_r = p.D_pad[(size_t)bh * p.Lq_pad + xrow];
     }
     const int klen = (p.kv_lens != nullptr) ? min(p.Lk, p.kv_lens[b]) : p.Lk;
@@ -216,6 +216,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       tc_fence_after();
       const int y0 = it * Cf::BY;
       const float* vec = reinterpret_cast<const float*>(sStage + stage * Cf::STAGE_BYTES + 2 * Cf::NAT_BYTES + Cf::NT * Cf::TR_BYTES);
+      // warp-uniform: no external dP, no padding / causal edge inside this (warp, tile) -> predicate-free fast path
+      bool fast_w;
+      if (MODE == 0) fast_w = (p.dp_ext == nullptr) && (y0 + Cf::BY <= klen) && (!p.causal || (y0 + Cf::BY - 1 <= x0 + q4 * 32));
+      else           fast_w = (p.dp_ext == nullptr) && (x0 + q4 * 32 + 31 < klen) && (!p.causal || (x0 + q4 * 32 + 31 <= y0));
+      const float sl2 = p.scale_log2;
 #pragma unroll 1
       for (int c0 = 0; c0 < Cf::BY; c0 += 32) {
         uint32_t vs[32], vd[32];
@@ -223,30 +228,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
         tmem_ld_32x32b_x32(trow + (uint32_t)(Cf::COL_DP + c0), vd);
         tmem_ld_wait();
         uint32_t pk_p[16], pk_ds[16];
+        if (fast_w) {
+          if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2], dsv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = c0 + i + e;                      // inner index within the tile
-            const int y = y0 + c;
-            float pr, dp = __uint_as_float(vd[i + e]);
-            if (MODE == 0) {
-              const bool kv_ok = (y < klen) && (!p.causal || y <= xrow);
-              pr = kv_ok ? exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_r) : 0.f;
-              if (p.dp_ext != nullptr && y < p.Lk && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + xrow) * p.Lk + y];
-              dsv[e] = pr * (dp - D_r);
-            } else {
-              const float lse_c = vec[c] * 1.4426950408889634f, D_c = vec[Cf::BY + c];
-              const bool kv_ok = (xrow < klen) && (!p.causal || xrow <= y);
-              pr = kv_ok ? exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_c) : 0.f;   // lse pad = 1e30 -> 0 beyond Lq
-              if (p.dp_ext != nullptr && y < p.Lq && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + y) * p.Lk + xrow];
-              dsv[e] = pr * (dp - D_c);
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(vs[i]), sl2, -lse_r));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(vs[i + 1]), sl2, -lse_r));
+              pk_ds[i / 2] = ab_pack2<T>(p0 * (__uint_as_float(vd[i]) - D_r), p1 * (__uint_as_float(vd[i + 1]) - D_r));
             }
-            pv[e] = pr;
+          } else {
+            const float4* l4 = reinterpret_cast<const float4*>(vec + c0);
+            const float4* d4 = reinterpret_cast<const float4*>(vec + Cf::BY + c0);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 L = l4[i / 4], Dv = d4[i / 4];
+              const float p0 = fast_exp2(fmaf(__uint_as_float(vs[i]), sl2, -L.x));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(vs[i + 1]), sl2, -L.y));
+              const float p2 = fast_exp2(fmaf(__uint_as_float(vs[i + 2]), sl2, -L.z));
+              const float p3 = fast_exp2(fmaf(__uint_as_float(vs[i + 3]), sl2, -L.w));
+              pk_p[i / 2] = ab_pack2<T>(p0, p1);
+              pk_p[i / 2 + 1] = ab_pack2<T>(p2, p3);
+              pk_ds[i / 2] = ab_pack2<T>(p0 * (__uint_as_float(vd[i]) - Dv.x), p1 * (__uint_as_float(vd[i + 1]) - Dv.y));
+              pk_ds[i / 2 + 1] = ab_pack2<T>(p2 * (__uint_as_float(vd[i + 2]) - Dv.z), p3 * (__uint_as_float(vd[i + 3]) - Dv.w));
+            }
           }
-          pk_p[i / 2] = ab_pack2<T>(pv[0], pv[1]);
-          pk_ds[i / 2] = ab_pack2<T>(dsv[0], dsv[1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float pv[2], dsv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = c0 + i + e;                      // inner index within the tile
+              const int y = y0 + c;
+              float pr, dp = __uint_as_float(vd[i + e]);
+              if (MODE == 0) {
+                const bool kv_ok = (y < klen) && (!p.causal || y <= xrow);
+                pr = kv_ok ? fast_exp2(__uint_as_float(vs[i + e]) * sl2 - lse_r) : 0.f;
+                if (p.dp_ext != nullptr && y < p.Lk && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + xrow) * p.Lk + y];
+                dsv[e] = pr * (dp - D_r);
+              } else {
+                const float lse_c = vec[c], D_c = vec[Cf::BY + c];
+                const bool kv_ok = (xrow < klen) && (!p.causal || xrow <= y);
+                pr = kv_ok ? fast_exp2(__uint_as_float(vs[i + e]) * sl2 - lse_c) : 0.f;   // lse pad = 1e30 -> 0 beyond Lq
+                if (p.dp_ext != nullptr && y < p.Lq && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + y) * p.Lk + xrow];
+                dsv[e] = pr * (dp - D_c);
+              }
+              pv[e] = pr;
+            }
+            pk_p[i / 2] = ab_pack2<T>(pv[0], pv[1]);
+            pk_ds[i / 2] = ab_pack2<T>(dsv[0], dsv[1]);
+          }
         }
         unsigned char* half0 = sPD + (c0 / 64) * (AB_ROWS * 128);                            // MODE 0: dS   | MODE 1: P^T
         unsigned char* half1 = sPD + Cf::NHALF * AB_ROWS * 128 + (c0 / 64) * (AB_ROWS * 128);  //              | MODE 1: dS^T
@@ -337,7 +368,7 @@ __global__ void ab_prep_kernel(const T* __restrict__ o, const T* __restrict__ dO
     const float* de = dp_ext + ((size_t)bh * Lq + q) * Lk;
     for (int k = 0; k < Lk; ++k) s += pr[k] * de[k];
   }
-  lse_pad[idx] = lse[(size_t)bh * Lq + q];
+  lse_pad[idx] = lse[(size_t)bh * Lq + q] * 1.4426950408889634f;    // log2 units: p = exp2(s*scale*log2e - lse2)
   D_pad[idx] = s;
 }
 

@@ -43,6 +43,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 2^x on the SFU without the denormal / range fix-up code the compiler adds around exp2f()
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -33,6 +33,7 @@ struct GemmKP {
   float alpha;
   const float* bias;
   const float* rowvec;
+  long long rowvec_ld;
   int rows_per_group, act;
   const void* residual;
   long long res_ld;
@@ -184,7 +185,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       m = (long long)m0 + r;
       row_ok = m < p.M;
     }
-    const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * (long long)p.N : nullptr;
+    const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * p.rowvec_ld : nullptr;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -207,81 +208,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       } else if (p.tma_store || (row_ok && ncol > 0)) {
-        {
-          float f[32];
+        // lean epilogue: every runtime option is tested once per 32-column chunk (uniform branches), the element loops
+        // are straight FFMA / pack code; bias comes from smem as float4 (the first version spent ~19 instructions per
+        // element here and was instruction-issue bound: profiles/r01_gemm_k320_ncu.md)
+        float f[32];
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) * p.alpha + s_bias[c0 + j];
-            if (rv != nullptr && j < ncol) x += rv[n0 + c0 + j];
-            f[j] = act_apply(x, p.act);
-          }
-          if (p.residual != nullptr && row_ok && ncol > 0) {
-            const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
-            if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = b4[j / 4];
+          f[j] = fmaf(__uint_as_float(v[j]), p.alpha, bb.x);
+          f[j + 1] = fmaf(__uint_as_float(v[j + 1]), p.alpha, bb.y);
+          f[j + 2] = fmaf(__uint_as_float(v[j + 2]), p.alpha, bb.z);
+          f[j + 3] = fmaf(__uint_as_float(v[j + 3]), p.alpha, bb.w);
+        }
+        if (rv != nullptr) {
+          const float* rvc = rv + n0 + c0;
+          if (ncol == 32) {
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rp + j4 * 8);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (p.is_bf16) {
-                    f[j4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
-                    f[j4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-                  } else {
-                    const __half2 h2 = *reinterpret_cast<const __half2*>(&w[e]);
-                    f[j4 * 8 + e * 2 + 0] += __low2float(h2);
-                    f[j4 * 8 + e * 2 + 1] += __high2float(h2);
-                  }
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {          // static indexing keeps f[] in registers
-                if (j < ncol) {
-                  const uint16_t b = rp[j];
-                  f[j] += p.is_bf16 ? __uint_as_float((uint32_t)b << 16) : __half2float(*reinterpret_cast<const __half*>(&b));
-                }
-              }
-            }
-          }
-          if (p.out16 != nullptr && !p.tma_store) {
-            uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n0 + c0;
-            if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) w[e] = pack16(f[j4 * 8 + e * 2], f[j4 * 8 + e * 2 + 1], p.is_bf16);
-                *reinterpret_cast<uint4*>(op + j4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < ncol) {
-                  if (p.is_bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(f[j]); op[j] = *reinterpret_cast<const uint16_t*>(&t); }
-                  else           { const __half t = __float2half_rn(f[j]);           op[j] = *reinterpret_cast<const uint16_t*>(&t); }
-                }
-              }
-            }
-          }
-          if (p.tma_store) {
-            // panel (c0/32): [128 rows][64 B], 64B-swizzled (16B chunk q of row r lives at q ^ ((r>>1)&3))
-            unsigned char* prow = smem + (c0 / 32) * 8192 + r * 64;
-            const int sw = (r >> 1) & 3;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) w[e] = pack16(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1], p.is_bf16);
-              *reinterpret_cast<uint4*>(prow + ((q ^ sw) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-          if (p.out32 != nullptr && row_ok) {
-            float* op = p.out32 + m * p.out32_ld + n0 + c0;
+            for (int j = 0; j < 32; ++j) f[j] += rvc[j];
+          } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < ncol) op[j] = f[j];
+              if (j < ncol) f[j] += rvc[j];
           }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+        }
+        if (p.residual != nullptr && row_ok && ncol > 0) {
+          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
+          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+            uint4 u[4];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) u[j4] = *reinterpret_cast<const uint4*>(rp + j4 * 8);
+            if (p.is_bf16) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint32_t w[4] = {u[j4].x, u[j4].y, u[j4].z, u[j4].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f[j4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
+                  f[j4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint32_t w[4] = {u[j4].x, u[j4].y, u[j4].z, u[j4].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                  f[j4 * 8 + e * 2 + 0] += t.x;
+                  f[j4 * 8 + e * 2 + 1] += t.y;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {          // static indexing keeps f[] in registers
+              if (j < ncol) {
+                const uint16_t bv = rp[j];
+                f[j] += p.is_bf16 ? __uint_as_float((uint32_t)bv << 16) : __half2float(*reinterpret_cast<const __half*>(&bv));
+              }
+            }
+          }
+        }
+        uint32_t pk[16];
+        if (p.out16 != nullptr) {
+          if (p.is_bf16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&t); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&t); }
+          }
+        }
+        if (p.tma_store) {
+          // panel (c0/32): [128 rows][64 B], 64B-swizzled (16B chunk q of row r lives at q ^ ((r>>1)&3))
+          unsigned char* prow = smem + (c0 / 32) * 8192 + r * 64;
+          const int sw = (r >> 1) & 3;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(prow + ((q4 ^ sw) * 16)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+        } else if (p.out16 != nullptr) {
+          uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n0 + c0;
+          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(op + q4 * 8) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) op[j] = (uint16_t)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xFFFFu));
+          }
+        }
+        if (p.out32 != nullptr && row_ok) {
+          float* op = p.out32 + m * p.out32_ld + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncol) op[j] = f[j];
         }
       }
     }
@@ -319,7 +348,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int 
   for (int s = 0; s < p.split_k; ++s) acc += p.splitk_ws[(size_t)s * total + idx];
   float x = acc * p.alpha;
   if (p.bias) x += p.bias[n];
-  if (p.rowvec) x += p.rowvec[(m / p.rows_per_group) * p.N + n];
+  if (p.rowvec) x += p.rowvec[(m / p.rows_per_group) * p.rowvec_ld + n];
   x = act_apply(x, p.act);
   if (p.residual) {
     const uint16_t b = reinterpret_cast<const uint16_t*>(p.residual)[m * p.res_ld + n];
@@ -367,7 +396,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   GemmKP kp;
   memset(&kp, 0, sizeof(kp));
   kp.M = g->M; kp.N = g->N; kp.n_seg = g->n_seg;
-  kp.alpha = g->alpha; kp.bias = g->bias; kp.rowvec = g->rowvec; kp.rows_per_group = g->rows_per_group > 0 ? g->rows_per_group : 1;
+  kp.alpha = g->alpha; kp.bias = g->bias; kp.rowvec = g->rowvec; kp.rowvec_ld = g->rowvec_ld > 0 ? g->rowvec_ld : g->N; kp.rows_per_group = g->rows_per_group > 0 ? g->rows_per_group : 1;
   kp.act = g->act; kp.residual = g->residual; kp.res_ld = g->res_ld; kp.out16 = g->out16; kp.out_ld = g->out_ld;
   kp.out32 = g->out32; kp.out32_ld = g->out32_ld; kp.is_bf16 = g->dtype == COMAT_BF16;
   const int BN = pick_bn(g->N, g->force_bn);

@@ -328,7 +328,10 @@ def _resnet(tape, r: _Res, x: Var, temb_act16, skip: Optional[Var] = None) -> Va
     h = groupnorm(tape, xin, r.n1, True)
     rowvec = None
     if r.temb is not None and temb_act16 is not None:
-        rowvec = ops.gemm([temb_act16], [r.temb.w], bias=r.temb.bias, out_fp32=True)     # (n, Cout) fp32, constant wrt params
+        if isinstance(temb_act16, dict):                                                 # all projections done by one GEMM
+            rowvec = temb_act16[id(r)]
+        else:
+            rowvec = ops.gemm([temb_act16], [r.temb.w], bias=r.temb.bias, out_fp32=True)  # (n, Cout) fp32, constant wrt params
     h = conv(tape, [h], r.c1, rowvec=rowvec)
     h = groupnorm(tape, h, r.n2, True)
     sc = conv(tape, [xin], r.short) if r.short is not None else xin
@@ -441,6 +444,10 @@ class UNetEngine:
             self.up.append(([_Res(r, dtype) for r in blk.resnets], attns, us))
         self.norm_out = NormW(unet.conv_norm_out, unet.conv_norm_out.num_groups)
         self.conv_out = ConvW(unet.conv_out, dtype)
+        # every ResBlock's time_emb_proj applied by ONE GEMM per UNet call (22 tiny launches -> 1): concatenated weights
+        self._res_all = [r for rs, _, _ in self.down for r in rs] + list(self.mid[0]) + [r for rs, _, _ in self.up for r in rs]
+        self._temb_w = torch.cat([r.temb.w for r in self._res_all], 0).contiguous()
+        self._temb_b = torch.cat([r.temb.bias for r in self._res_all], 0).contiguous()
         self.loras: List[LoRAW] = []
         for blocks in [self.down, [(self.mid[0], self.mid[1], None)], self.up]:
             for _, attns, _ in blocks:
@@ -485,7 +492,12 @@ class UNetEngine:
         """x: Var of NHWC 16-bit latents zero-padded to 64 channels (n, h, w, 64); ctx: (n, 77, D) 16-bit.
         returns Var (n, h, w, 4)."""
         n = x.v.shape[0]
-        temb = self.temb(t, n, added_cond)
+        temb16 = self.temb(t, n, added_cond)
+        allp = ops.gemm([temb16], [self._temb_w], bias=self._temb_b, out_fp32=True)       # (n, sum Cout) fp32
+        temb, off = {}, 0
+        for r in self._res_all:
+            temb[id(r)] = allp[:, off:off + r.temb.n]
+            off += r.temb.n
         cvar = Var(ctx, needs_grad=False)
         h = conv(tape, [x], self.conv_in)
         skips = [h]

@@ -24,7 +24,7 @@ class GemmParams(C.Structure):
                 ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rows_per_group", C.c_int32),
                 ("act", C.c_int32), ("residual", C.c_void_p), ("res_ld", C.c_int64), ("out16", C.c_void_p),
                 ("out_ld", C.c_int64), ("out32", C.c_void_p), ("out32_ld", C.c_int64), ("force_bn", C.c_int32),
-                ("split_k", C.c_int32), ("accumulate", C.c_int32), ("splitk_ws", C.c_void_p)]
+                ("split_k", C.c_int32), ("accumulate", C.c_int32), ("splitk_ws", C.c_void_p), ("rowvec_ld", C.c_int64)]
 
 
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
@@ -90,7 +90,9 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
     if bias is not None:
         bias = bias.float().contiguous()
     if rowvec is not None:
-        rowvec = rowvec.float().contiguous()
+        if rowvec.dtype != torch.float32 or rowvec.stride(-1) != 1:
+            rowvec = rowvec.float().contiguous()
+        p.rowvec_ld = rowvec.stride(0) if rowvec.dim() == 2 and rowvec.shape[0] > 1 else rowvec.shape[-1]
     p.bias, p.rowvec, p.rows_per_group, p.act = _p(bias), _p(rowvec), rows_per_group, ACT[act]
     if residual is not None:
         residual = residual.reshape(M, N) if residual.is_contiguous() else residual.contiguous().reshape(M, N)

@@ -130,6 +130,8 @@ typedef struct {
                                reduces the partials in a fixed order and applies the epilogue */
   int32_t accumulate;       /* split-K only: out32 += result (gradient accumulation over the K training steps) */
   float* splitk_ws;
+  int64_t rowvec_ld;        /* row pitch of rowvec in floats (0 = N): lets all ResBlock time-embedding projections of a UNet call
+                               come from ONE GEMM whose output is sliced per block */
 } comat_gemm_params;
 
 int comat_gemm(const comat_gemm_params* p, void* stream);

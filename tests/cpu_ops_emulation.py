@@ -34,7 +34,7 @@ def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_grou
     if bias is not None:
         y = y + bias.double()
     if rowvec is not None:
-        y = y + rowvec.double().repeat_interleave(rows_per_group, 0)
+        y = y + rowvec.double().repeat_interleave(rows_per_group, 0)[:, :N]
     if act == "silu":
         y = F.silu(y)
     elif act == "gelu":
@@ -100,6 +100,10 @@ def elementwise(op, x, y=None, alpha=1.0, beta=1.0):
             r = torch.autograd.grad(F.silu(xr), xr, yd)[0]
     elif op == "gelu":
         r = F.gelu(xd)
+    elif op == "gelu_bwd":
+        with torch.enable_grad():
+            xr = xd.detach().requires_grad_(True)
+            r = torch.autograd.grad(F.gelu(xr), xr, yd)[0]
     elif op == "add":
         r = xd + yd
     elif op == "scale":
@@ -150,3 +154,76 @@ def install(monkeypatch):
     for name in ("gemm", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
                  "elementwise", "spatial", "transpose16", "concat_channels", "latent_to_nhwc", "nhwc_to_nchw_f32"):
         monkeypatch.setattr(ops, name, globals()[name])
+
+
+# ---- attention / CE / resize emulations (BLIP executor logic tests)
+def _ref_attn(q, k, v, heads, kv_lens=None, causal=False, dprobs=None):
+    n, Lq, C = q.shape
+    Lk = k.shape[1]
+    d = C // heads
+    sp = lambda x: x.double().reshape(n, x.shape[1], heads, d).permute(0, 2, 1, 3)
+    s = sp(q) @ sp(k).transpose(-1, -2) * d ** -0.5
+    ki = torch.arange(Lk)
+    mask = torch.ones(n, 1, Lq, Lk, dtype=torch.bool)
+    if kv_lens is not None:
+        mask = mask & (ki[None, None, None, :] < kv_lens[:, None, None, None])
+    if causal:
+        mask = mask & (ki[None, None, None, :] <= torch.arange(Lq)[None, None, :, None])
+    s = s.masked_fill(~mask, float("-inf"))
+    p = s.softmax(-1)
+    o = (p @ sp(v)).permute(0, 2, 1, 3).reshape(n, Lq, C)
+    return o, p.reshape(n * heads, Lq, Lk), torch.logsumexp(s, -1).reshape(n * heads, Lq)
+
+
+def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False, kv_lens=None, causal=False):
+    o, p, lse = _ref_attn(q, k, v, heads, kv_lens, causal)
+    return o.to(q.dtype), (p.float() if export_probs else None), (lse.float() if need_lse else None)
+
+
+def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None, causal=False):
+    with torch.enable_grad():
+        qr, kr, vr = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+        o_, p_, _ = _ref_attn(qr, kr, vr, heads, kv_lens, causal)
+        outs, gs = [o_], [do.double()]
+        if dprobs is not None:
+            outs.append(p_); gs.append(dprobs.double())
+        gq, gk, gv = torch.autograd.grad(outs, (qr, kr, vr), gs)
+    return gq.to(q.dtype), gk.to(q.dtype), gv.to(q.dtype)
+
+
+def ce_fwd(logits, labels, V, eps):
+    x = logits[:, :V].double()
+    lse = torch.logsumexp(x, -1)
+    valid = labels != -100
+    y = labels.clamp_min(0)
+    nll = lse - x.gather(1, y[:, None])[:, 0]
+    smooth = lse - x.mean(-1)
+    row = torch.where(valid, (1 - eps) * nll + eps * smooth, torch.zeros_like(nll))
+    cnt = valid.sum().double()
+    return torch.stack([lse, row], 1).float(), torch.stack([row.sum() / cnt, cnt]).float()
+
+
+def ce_bwd(logits, labels, stats, out2, gout, V, Vpad, eps, dtype):
+    x = logits[:, :V].double()
+    p = (x - stats[:, :1].double()).exp()
+    valid = (labels != -100)[:, None]
+    oh = torch.zeros_like(p).scatter_(1, labels.clamp_min(0)[:, None], 1.0)
+    g = float(gout.reshape(-1)[0]) / float(out2[1])
+    d = torch.where(valid, g * (p - (1 - eps) * oh - eps / V), torch.zeros_like(p))
+    out = torch.zeros(logits.shape[0], Vpad, dtype=dtype)
+    out[:, :V] = d.to(dtype)
+    return out
+
+
+def install_blip(monkeypatch):
+    install(monkeypatch)
+    from comat_b200 import attention, blip_engine, image_ops
+    monkeypatch.setattr(attention, "attention_fwd_native", attention_fwd_native)
+    monkeypatch.setattr(attention, "attention_bwd_native", attention_bwd_native)
+    monkeypatch.setattr(blip_engine, "ce_fwd", ce_fwd)
+    monkeypatch.setattr(blip_engine, "ce_bwd", ce_bwd)
+
+    def resize_norm(images, size, mean, std):
+        x = F.interpolate(images.float(), size=(size, size), mode="bicubic", antialias=True, align_corners=False)
+        return (x - torch.tensor(mean).view(1, -1, 1, 1)) / torch.tensor(std).view(1, -1, 1, 1)
+    monkeypatch.setattr(image_ops, "resize_bicubic_aa_normalize", resize_norm)
