@@ -32,7 +32,6 @@ sys.path.insert(0, ROOT)
 METRIC = "sd15_512_comat_train_steps_per_sec"
 UNIT = "train-steps/s"
 TFLOP_PER_STEP_CFG2 = 203.0          # SURVEY 8d / BASELINE.md section 3 (per GPU, B=4, S=20, K=5, GAN on)
-TFLOP_SAMPLE_CFG1 = 10.6             # config 1: B=1, S=2, K=1, concept-match only
 
 
 def parse():
@@ -99,9 +98,12 @@ def load_peaks():
 
 # --------------------------------------------------------------------------------------------------------------
 def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
-    """Times the oracle (plain PyTorch, fp32, eager) on the host cores for a config-1 step at full SD1.5 geometry:
-    B=1, S=2 DDPM steps, K=1 back-propagated step, cfg 7.5, concept-matching loss only."""
+    """Times the oracle (plain PyTorch, fp32, eager) on the host cores on a BOUNDED sample of the workload: SD1.5 at full geometry
+    (859.5 M-param UNet, VAE decoder, BLIP-large), B=1, S=2 DDPM steps, K=1 back-propagated step, cfg 7.5, concept-matching loss,
+    on a 32x32 latent (256^2 image) so one step is tens of seconds.  The sample's algorithmic FLOPs are counted with
+    torch.utils.flop_counter and the result is scaled to config-2 train-steps by FLOPs (203 TFLOP per config-2 step)."""
     import torch
+    from torch.utils.flop_counter import FlopCounterMode
     from oracle import comat_ref as R
     from oracle import sd_modules as sdm
     threads = threads or os.cpu_count()
@@ -111,10 +113,10 @@ def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
         unet = sdm.UNet2DConditionModel(**sdm.tiny_unet_config(width=64, cross_attention_dim=64))
         vae = sdm.AutoencoderKL(block_out_channels=(64, 64, 128, 128))
         blip = R.make_blip(large=False)
-        ctx, res = 64, 256
+        ctx, res = 64, 128
     else:
         unet, vae, blip = sdm.UNet2DConditionModel(**sdm.SD15_UNET_CONFIG), sdm.AutoencoderKL(), R.make_blip(large=True)
-        ctx, res = 768, 512
+        ctx, res = 768, 256
     unet.requires_grad_(False)
     vae.requires_grad_(False)
     params = sdm.install_lora(unet, 128 if not tiny else 8)
@@ -122,21 +124,31 @@ def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
     lat = res // 8
     batch = dict(prompt_embeds=torch.randn(1, 77, ctx, generator=g), null_embeds=torch.randn(1, 77, ctx, generator=g),
                  latents=torch.randn(1, 4, lat, lat, generator=g), noises=[torch.randn(1, 4, lat, lat, generator=g) for _ in range(2)],
-                 training_steps=[1], crop=(1, 1), blip_ids=torch.tensor([[101, 1037, 5855, 1997] + list(range(2000, 2014)) + [102]]),
+                 training_steps=[1], crop=(0, 0), blip_ids=torch.tensor([[101, 1037, 5855, 1997] + list(range(2000, 2014)) + [102]]),
                  blip_mask=torch.ones(1, 19, dtype=torch.long))
     cfg = dict(S=2, resolution=res)
     opt = torch.optim.AdamW(params, lr=5e-5)
-    times = []
+    times, flops = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
+        counter = FlopCounterMode(display=False) if flops is None else None
+        if counter is not None:
+            counter.__enter__()
         out = R.g_step_loss(unet, vae, sdm.DDPMScheduler(), blip, batch, cfg)
         opt.zero_grad()
         out["loss"].backward()
+        if counter is not None:
+            counter.__exit__(None, None, None)
+            flops = float(counter.get_total_flops())
         torch.nn.utils.clip_grad_norm_(params, 0.1)
         opt.step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return times, threads, float(out["loss"])
+    return times, threads, flops
+
+
+SAMPLE_DESC = ("SD1.5 full geometry (UNet 859.5 M, VAE decoder, BLIP-large), B=1, S=2, K=1, cfg 7.5, concept-match loss, 32x32 latent "
+               "(256^2 image), fp32 eager oracle")
 
 
 def run_reference(a):
@@ -146,18 +158,19 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    times, threads, _ = cpu_oracle_sample(steps=a.steps, warmup=min(a.warmup, 1), tiny=a.tiny)
+    times, threads, flops = cpu_oracle_sample(steps=a.steps, warmup=min(a.warmup, 1), tiny=a.tiny)
     total = sum(times)
     sample_sps = len(times) / total
-    value = sample_sps * (TFLOP_SAMPLE_CFG1 / TFLOP_PER_STEP_CFG2)
+    value = sample_sps * (flops / (TFLOP_PER_STEP_CFG2 * 1e12))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": min(a.warmup, 1), "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SD1.5 512^2 full CoMat, S=20, K=5, B=4 (BASELINE configs[1]) — CPU value extrapolated "
-                                   "by algorithmic FLOPs (203 / 10.6 TFLOP) from the bounded sample",
-                       "sample": "SD1.5 full geometry, B=1, S=2, K=1, cfg 7.5, concept-match loss only, fp32 eager (configs[0])"},
+            "config": {"workload": "SD1.5 512^2 full CoMat, S=20, K=5, B=4 (BASELINE configs[1]); CPU value = bounded sample scaled by "
+                                   "algorithmic FLOPs (%.2f TFLOP counted / 203 TFLOP per config-2 step)" % (flops / 1e12),
+                       "sample": ("TINY-DEBUG " if a.tiny else "") + SAMPLE_DESC},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{len(times)} config-1 steps, {total / len(times):.1f} s each, scaled x(10.6/203)"},
+                             "sample": f"{len(times)} sample steps of {total / len(times):.1f} s each ({flops / 1e12:.2f} TFLOP per sample step, "
+                                       f"{flops / 1e12 / (total / len(times)):.2f} TFLOP/s on {threads} threads)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -296,11 +309,11 @@ def main():
                 "losses": {k: float(v) for k, v in logs.items() if hasattr(v, "numel") and v.numel() == 1}}
         if not a.no_cpu_baseline:
             try:
-                times, threads, _ = cpu_oracle_sample(steps=1, warmup=0, tiny=a.tiny)
-                v = (1.0 / times[0]) * (TFLOP_SAMPLE_CFG1 / TFLOP_PER_STEP_CFG2)
+                times, threads, flops = cpu_oracle_sample(steps=1, warmup=0, tiny=a.tiny)
+                v = (1.0 / times[0]) * (flops / (TFLOP_PER_STEP_CFG2 * 1e12))
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                        "sample": f"1 config-1 step (SD1.5 full geometry, B=1, S=2, K=1, fp32 eager oracle) = {times[0]:.1f} s, "
-                                                  f"scaled by algorithmic FLOPs 10.6/203 to config-2 steps"}
+                                        "sample": f"1 step of [{SAMPLE_DESC}] = {times[0]:.1f} s, {flops / 1e12:.2f} TFLOP counted "
+                                                  f"({flops / 1e12 / times[0]:.2f} TFLOP/s), scaled by FLOPs to config-2 steps (203 TFLOP)"}
             except Exception as e:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
         print(json.dumps(line))

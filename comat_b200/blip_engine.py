@@ -228,13 +228,14 @@ class _BlipLossFn(torch.autograd.Function):
         tape = E.Tape() if need else None
         pv = E.Var(pix.to(eng.dtype).contiguous())
         loss = eng.caption_loss_tape(tape, pv, ids, mask, labels)
-        ctx.tape, ctx.pv, ctx.loss, ctx.dt = tape, pv, loss, pix.dtype
+        ctx.tape, ctx.pv, ctx.loss, ctx.dt, ctx.eng_dtype = tape, pv, loss, pix.dtype, eng.dtype
         return loss.v.reshape(()).clone()
 
     @staticmethod
     def backward(ctx, g):
-        ctx.loss.g = g.reshape(1).float().contiguous()
+        S = 16384.0 if ctx.eng_dtype == torch.float16 else 1.0   # static loss scaling: fp16 activation gradients of the frozen tower underflow otherwise
+        ctx.loss.g = (g.reshape(1).float() * S).contiguous()
         ctx.tape.backward()
-        gp = ctx.pv.g.to(ctx.dt) if ctx.pv.g is not None else None
+        gp = (ctx.pv.g.float() / S).to(ctx.dt) if ctx.pv.g is not None else None
         ctx.tape = ctx.pv = ctx.loss = None
         return None, gp, None, None, None

@@ -37,17 +37,20 @@ class _UNetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_eps, *g_probs):
         eng = ctx.mod.engine
-        ctx.out.g = g_eps.float().permute(0, 2, 3, 1).contiguous().to(eng.dtype)
+        S = ctx.mod.grad_scale          # static loss scaling of the fp16 backward (the reference relies on GradScaler, node8.yaml:8)
+        ctx.out.g = (g_eps.float() * S).permute(0, 2, 3, 1).contiguous().to(eng.dtype)
         for p, g in zip(ctx.pvars, g_probs):
             if g is not None:
-                p.g = g.contiguous().float()
+                p.g = (g.float() * S).contiguous()
         eng.zero_lora_grads()
         eng.set_lora_wgrad(ctx.wgrad)
         ctx.tape.backward()
         gx = None
         if ctx.needs_input_grad[1] and ctx.xv.g is not None:
-            gx = ops.nhwc_to_nchw_f32(ctx.xv.g, ctx.mod.in_channels).to(ctx.x_dtype)
+            gx = ops.nhwc_to_nchw_f32(ctx.xv.g, ctx.mod.in_channels, 1.0 / S).to(ctx.x_dtype)
         lg = eng.lora_grads() if ctx.wgrad else [None] * len(eng.lora_grads())
+        if ctx.wgrad and S != 1.0:
+            torch._foreach_mul_([g for g in lg if g is not None], 1.0 / S)
         ctx.tape = ctx.xv = ctx.out = ctx.pvars = None
         return (None, gx, None, None, None, None, None, *lg)
 
@@ -101,6 +104,7 @@ class EngineUNet(torch.nn.Module):
         self.capture: Optional[E.AttnCapture] = None
         self.last_probs = None
         self._dtype = dtype
+        self.grad_scale = 4096.0 if dtype == torch.float16 else 1.0   # power of two: exact scale / unscale around the 16-bit backward
         self.use_graphs = False                # bench / trainer switch: CUDA-graph the no-grad forwards of the rollout
         self._graphs = {}
 
@@ -171,9 +175,10 @@ class _VAEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         eng = ctx.mod.engine
-        ctx.out.g = g.float().permute(0, 2, 3, 1).contiguous().to(eng.dtype)
+        S = ctx.mod.grad_scale
+        ctx.out.g = (g.float() * S).permute(0, 2, 3, 1).contiguous().to(eng.dtype)
         ctx.tape.backward()
-        gz = ops.nhwc_to_nchw_f32(ctx.zv.g, 4).to(ctx.zdtype)
+        gz = ops.nhwc_to_nchw_f32(ctx.zv.g, 4, 1.0 / S).to(ctx.zdtype)
         ctx.tape = ctx.zv = ctx.out = None
         return None, gz
 
@@ -184,6 +189,7 @@ class EngineVAE(torch.nn.Module):
         self.ref = vae
         self.config = vae.config
         self.engine = E.VAEDecoderEngine(vae, dtype)
+        self.grad_scale = 4096.0 if dtype == torch.float16 else 1.0
 
     @property
     def dtype(self):
