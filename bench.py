@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--no_gan", action="store_true")
     p.add_argument("--no_attrcon", action="store_true")
     p.add_argument("--no_graphs", action="store_true", help="disable CUDA-graph replay of the no-grad UNet forwards")
+    p.add_argument("--kineto_step", default="", help="profile ONE step with torch.profiler (CUPTI) and write a per-kernel table to this path")
     p.add_argument("--profile_step", action="store_true",
                    help="run warm-up then ONE step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     return p.parse_args()
@@ -129,9 +130,9 @@ def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
     cfg = dict(S=2, resolution=res)
     opt = torch.optim.AdamW(params, lr=5e-5)
     times, flops = [], None
-    for i in range(warmup + steps):
+    for i in range(-1, warmup + steps):           # i == -1: untimed FLOP-counting pass (also warms oneDNN primitives)
         t0 = time.perf_counter()
-        counter = FlopCounterMode(display=False) if flops is None else None
+        counter = FlopCounterMode(display=False) if i < 0 else None
         if counter is not None:
             counter.__enter__()
         out = R.g_step_loss(unet, vae, sdm.DDPMScheduler(), blip, batch, cfg)
@@ -258,6 +259,20 @@ def main():
 
     for i in range(a.warmup):
         trainer.train_step(dev_batches[i % len(dev_batches)])
+    if a.kineto_step:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            trainer.train_step(dev_batches[0])
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        with open(a.kineto_step, "w") as fh:
+            fh.write(f"one train step, torch.profiler (CUPTI) device time per kernel; total {tot / 1e3:.1f} ms\n")
+            fh.write("| kernel | calls | total ms | share |\n|---|---:|---:|---:|\n")
+            for e in rows[:45]:
+                fh.write(f"| `{e.key[:100]}` | {e.count} | {e.device_time_total / 1e3:.2f} | {100 * e.device_time_total / tot:.1f} % |\n")
+        return 0
     if a.profile_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()

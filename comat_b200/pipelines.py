@@ -121,7 +121,7 @@ class TrainableSDPipeline:
                 if self.is_sdxl:
                     detach = True                                                       # :809
                 x_in = x_in.detach() if detach else x_in
-                if i in T and bp_on_trained and use_attr and i in attr:                 # AttrConcen...:159-167
+                if i in T and (bp_on_trained or self.is_sdxl) and use_attr and i in attr:   # AttrConcen...:159-167 / SDXL :404-412
                     eps = self._attrcon_forward(x_in, t, embeds, added, t_host=ts_host[i])
                 else:
                     eps = self._unet(x_in, t, embeds, added)
