@@ -107,7 +107,8 @@ def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
     from torch.utils.flop_counter import FlopCounterMode
     from oracle import comat_ref as R
     from oracle import sd_modules as sdm
-    threads = threads or os.cpu_count()
+    # the GPU box reports 128 cores; aten/oneDNN scale to ~32 threads there and collapse beyond (profiles/r01_host_cpu_thread_probe.log)
+    threads = threads or min(os.cpu_count() or 8, int(os.environ.get("COMAT_CPU_THREADS", "32")))
     torch.set_num_threads(threads)
     torch.manual_seed(42)
     if tiny:
@@ -317,8 +318,10 @@ def main():
                            "l2_policy": "inputs rotate over 4 batches; per-step working set (weights 7 GB + activations > 50 GB) exceeds the 126 MB L2",
                            "samples_per_sec": value * a.batch * world,
                            "library_calls_per_step": lib_calls / a.steps,
-                           "library_note": "attention softmax(QK^T)V, BLIP network and bicubic resize still run on aten/HF (bring-up); "
-                                           "all convs/linears/norms/losses/optimiser are comat_b200 kernels"},
+                           "library_note": ("0 = every conv / linear / attention (fwd+bwd) / norm / loss / resize / optimiser launch of the step "
+                                            "is a comat_b200 kernel; torch supplies memory, the fp32 latent-chain glue, "
+                                            "embedding gathers and layout permutes") if lib_calls == 0 else
+                                           "calls that fell back to aten/HF kernels (shapes the native kernels do not cover)"},
                 "e2e": {"value": a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof,
                 "losses": {k: float(v) for k, v in logs.items() if hasattr(v, "numel") and v.numel() == 1}}

@@ -182,15 +182,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float mt = -INFINITY;
       if (full_w) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-          uint32_t v[32];
+        for (int c0 = 0; c0 < ATT_BN; c0 += 64) {      // two TMEM loads in flight per wait
+          uint32_t v[32], w[32];
           tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+          tmem_ld_32x32b_x32(trow + (uint32_t)(c0 + 32), w);
           tmem_ld_wait();
-          float m0_ = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1_ = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+          float m0_ = fmaxf(__uint_as_float(v[0]), __uint_as_float(w[0])), m1_ = fmaxf(__uint_as_float(v[1]), __uint_as_float(w[1]));
 #pragma unroll
-          for (int i = 4; i < 32; i += 2) {
-            m0_ = fmaxf(m0_, __uint_as_float(v[i]));
-            m1_ = fmaxf(m1_, __uint_as_float(v[i + 1]));
+          for (int i = 2; i < 32; i += 2) {
+            m0_ = fmaxf(m0_, fmaxf(__uint_as_float(v[i]), __uint_as_float(w[i])));
+            m1_ = fmaxf(m1_, fmaxf(__uint_as_float(v[i + 1]), __uint_as_float(w[i + 1])));
           }
           mt = fmaxf(mt, fmaxf(m0_, m1_));
         }

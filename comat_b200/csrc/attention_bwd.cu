@@ -349,27 +349,46 @@ __global__ void ab_transpose_kernel(const T* __restrict__ v, T* __restrict__ vt,
   }
 }
 
-// D_i = sum_c dO o O (+ sum_k P dP_ext), lse padded with 1e30 / D padded with 0 to Lq_pad
+// D_i = sum_c dO o O (+ sum_k P dP_ext), lse (x log2 e) padded with 1e30 / D padded with 0 to Lq_pad.
+// One warp per (sample, query) row: lanes stride each head's d channels (coalesced), one shuffle reduction per head.
 template <typename T>
-__global__ void ab_prep_kernel(const T* __restrict__ o, const T* __restrict__ dO, const float* __restrict__ lse,
-                               const float* __restrict__ probs, const float* __restrict__ dp_ext, float* __restrict__ lse_pad,
-                               float* __restrict__ D_pad, int n, int Lq, int Lk, int H, int d, int Lq_pad) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n * H * Lq_pad) return;
-  const int q = (int)(idx % Lq_pad);
-  const int bh = (int)(idx / Lq_pad), b = bh / H, h = bh % H;
-  if (q >= Lq) { lse_pad[idx] = 1e30f; D_pad[idx] = 0.f; return; }
-  const T* op = o + ((size_t)b * Lq + q) * (H * d) + h * d;
-  const T* dp = dO + ((size_t)b * Lq + q) * (H * d) + h * d;
-  float s = 0.f;
-  for (int c = 0; c < d; ++c) s += to_f32<T>(op[c]) * to_f32<T>(dp[c]);
-  if (dp_ext != nullptr) {
-    const float* pr = probs + ((size_t)bh * Lq + q) * Lk;
-    const float* de = dp_ext + ((size_t)bh * Lq + q) * Lk;
-    for (int k = 0; k < Lk; ++k) s += pr[k] * de[k];
+__global__ void __launch_bounds__(256) ab_prep_kernel(const T* __restrict__ o, const T* __restrict__ dO, const float* __restrict__ lse,
+                                                      const float* __restrict__ probs, const float* __restrict__ dp_ext,
+                                                      float* __restrict__ lse_pad, float* __restrict__ D_pad, int n, int Lq, int Lk, int H,
+                                                      int d, int Lq_pad) {
+  __shared__ float s_acc[8][32];                       // per warp: up to 32 heads
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;   // row = b * Lq_pad + q
+  if (row >= (long long)n * Lq_pad) return;
+  const int q = (int)(row % Lq_pad), b = (int)(row / Lq_pad);
+  if (q >= Lq) {
+    for (int h = lane; h < H; h += 32) {
+      lse_pad[((size_t)b * H + h) * Lq_pad + q] = 1e30f;
+      D_pad[((size_t)b * H + h) * Lq_pad + q] = 0.f;
+    }
+    return;
   }
-  lse_pad[idx] = lse[(size_t)bh * Lq + q] * 1.4426950408889634f;    // log2 units: p = exp2(s*scale*log2e - lse2)
-  D_pad[idx] = s;
+  const int Cc = H * d;
+  const T* op = o + ((size_t)b * Lq + q) * Cc;
+  const T* dp = dO + ((size_t)b * Lq + q) * Cc;
+  for (int h = 0; h < H; ++h) {
+    float part = 0.f;
+    for (int c = lane; c < d; c += 32) part += to_f32<T>(op[h * d + c]) * to_f32<T>(dp[h * d + c]);
+    part = warp_sum(part);
+    if (lane == 0) s_acc[warp][h] = part;
+  }
+  __syncwarp();
+  for (int h = lane; h < H; h += 32) {
+    const size_t bh = (size_t)b * H + h;
+    float s = s_acc[warp][h];
+    if (dp_ext != nullptr) {
+      const float* pr = probs + (bh * Lq + q) * Lk;
+      const float* de = dp_ext + (bh * Lq + q) * Lk;
+      for (int k = 0; k < Lk; ++k) s += pr[k] * de[k];
+    }
+    lse_pad[bh * Lq_pad + q] = lse[bh * Lq + q] * 1.4426950408889634f;    // log2 units: p = exp2(s*scale*log2e - lse2)
+    D_pad[bh * Lq_pad + q] = s;
+  }
 }
 
 template <int D, int MODE, typename T>
@@ -453,11 +472,12 @@ extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, 
     ab_transpose_kernel<__half><<<dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)q, (__half*)qT, Lq, H, d, Lqp);
     ab_transpose_kernel<__half><<<dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)dO, (__half*)dOT, Lq, H, d, Lqp);
     ab_transpose_kernel<__half><<<dim3((Lkp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)k, (__half*)kT, Lk, H, d, Lkp);
-    const long long tot = (long long)n * H * Lqp;
+    const long long rows = (long long)n * Lqp;
+    if (H > 32) return COMAT_ERR_UNSUPPORTED;
     if (dtype == COMAT_F16)
-      ab_prep_kernel<__half><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __half*)o, (const __half*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
+      ab_prep_kernel<__half><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __half*)o, (const __half*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
     else
-      ab_prep_kernel<__nv_bfloat16><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
+      ab_prep_kernel<__nv_bfloat16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
   }
   AttnBwdKP kp;
   memset(&kp, 0, sizeof(kp));
