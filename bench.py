@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--no_gan", action="store_true")
     p.add_argument("--no_attrcon", action="store_true")
     p.add_argument("--no_graphs", action="store_true", help="disable CUDA-graph replay of the no-grad UNet forwards")
+    p.add_argument("--gemm_shapes", default="", help="write the per-shape GEMM table of the instrumented step to this path")
     p.add_argument("--kineto_step", default="", help="profile ONE step with torch.profiler (CUPTI) and write a per-kernel table to this path")
     p.add_argument("--profile_step", action="store_true",
                    help="run warm-up then ONE step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
@@ -241,6 +242,7 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         d2h = 0
+        th0 = time.perf_counter()
         e0.record()
         for i in range(n_steps):
             if host_inputs:
@@ -252,6 +254,7 @@ def main():
                 loss_host = logs["step_loss"].float().cpu()       # D2H read of the step's result
                 d2h = loss_host.numel() * 4
         e1.record()
+        timed.host_issue_s = (time.perf_counter() - th0) / n_steps    # time the host needed to enqueue a step (no sync inside)
         barrier()
         t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
         if world > 1:
@@ -263,9 +266,30 @@ def main():
     if a.kineto_step:
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()
+        if a.gemm_shapes:
+            ops.PROFILE = gp = {"flops": 0.0, "events": [], "keys_only": True}
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             trainer.train_step(dev_batches[0])
             torch.cuda.synchronize()
+        ops.PROFILE = None
+        if a.gemm_shapes:
+            # kernel durations (CUPTI) of the GEMM launches in issue order <-> the shapes ops.gemm recorded in the same order
+            # (only valid with --no_graphs: graph replays do not pass through ops.gemm)
+            kev = sorted((e for e in prof.events() if "gemm_tc_kernel" in e.name), key=lambda e: e.time_range.start)
+            by = {}
+            if len(kev) == len(gp["events"]):
+                for e, (_, _, key, fl) in zip(kev, gp["events"]):
+                    r = by.setdefault(key, [0, 0.0, 0.0])
+                    r[0] += 1
+                    r[1] += e.device_time_total * 1e-3
+                    r[2] += fl
+            with open(a.gemm_shapes, "w") as f:
+                f.write(f"GEMM launches of one train step by shape, CUPTI kernel durations ({len(kev)} kernels, {len(gp['events'])} calls)\n")
+                f.write("| M | N | K segs | taps | split_k | fp32 out | calls | total ms | us/call | TFLOP/s |\n|---|---|---|---|---|---|---:|---:|---:|---:|\n")
+                for key, r in sorted(by.items(), key=lambda kv: -kv[1][1]):
+                    f.write("| %d | %d | %s | %d | %d | %s | %d | %.2f | %.1f | %.0f |\n" % (
+                        key[0], key[1], "+".join(map(str, key[2])), key[3], key[4], key[5], r[0], r[1], 1e3 * r[1] / r[0],
+                        r[2] / max(r[1], 1e-9) / 1e9))
         rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
         tot = sum(e.device_time_total for e in rows)
         with open(a.kineto_step, "w") as fh:
@@ -273,6 +297,31 @@ def main():
             fh.write("| kernel | calls | total ms | share |\n|---|---:|---:|---:|\n")
             for e in rows[:45]:
                 fh.write(f"| `{e.key[:100]}` | {e.count} | {e.device_time_total / 1e3:.2f} | {100 * e.device_time_total / tot:.1f} % |\n")
+            # idle time between consecutive kernels on the device timeline: ~1-2 us gaps are back-to-back launches, long
+            # gaps mean the GPU waited for the host
+            try:
+                from torch.autograd import DeviceType
+                dev_ev = sorted(((e.time_range.start, e.time_range.end) for e in prof.events()
+                                 if e.device_type == DeviceType.CUDA and e.time_range.end > e.time_range.start), key=lambda t: t[0])
+                edges = [2, 5, 20, 100, 1000, 1e9]
+                cnt, tot_gap = [0] * len(edges), [0.0] * len(edges)
+                end = dev_ev[0][1]
+                for st, en in dev_ev[1:]:
+                    gap = st - end
+                    if gap > 0:
+                        k = next(i for i, e_ in enumerate(edges) if gap < e_)
+                        cnt[k] += 1
+                        tot_gap[k] += gap
+                    end = max(end, en)
+                span = (dev_ev[-1][1] - dev_ev[0][0]) / 1e3
+                fh.write(f"\ndevice timeline: {len(dev_ev)} kernels over {span:.1f} ms; idle gaps between consecutive kernels:\n")
+                fh.write("| gap (us) | count | total ms |\n|---|---:|---:|\n")
+                lo = 0
+                for e_, c_, t_ in zip(edges, cnt, tot_gap):
+                    fh.write(f"| {lo}-{e_ if e_ < 1e9 else 'inf'} | {c_} | {t_ / 1e3:.2f} |\n")
+                    lo = e_
+            except Exception as ex:  # profiler internals differ between torch versions
+                fh.write(f"\n(gap analysis unavailable: {ex!r})\n")
         return 0
     if a.profile_step:
         torch.cuda.synchronize()
@@ -287,6 +336,7 @@ def main():
     l0 = _lib.LAUNCH_COUNT
     lib0 = attention.LIBRARY_CALLS + caption.LIBRARY_CALLS + image_ops.LIBRARY_CALLS
     t_dev, _, logs = timed(a.steps, host_inputs=False)
+    host_issue_ms = 1e3 * timed.host_issue_s
     launches = _lib.LAUNCH_COUNT - l0
     lib_calls = attention.LIBRARY_CALLS + caption.LIBRARY_CALLS + image_ops.LIBRARY_CALLS - lib0
     t_e2e, d2h, _ = timed(a.steps, host_inputs=True)
@@ -297,7 +347,7 @@ def main():
     trainer.train_step(dev_batches[0])
     torch.cuda.synchronize()
     ops.PROFILE = None
-    gemm_s = sum(e0.elapsed_time(e1) for e0, e1 in prof["events"]) * 1e-3
+    gemm_s = sum(ev[0].elapsed_time(ev[1]) for ev in prof["events"]) * 1e-3
     sustained, burst, hbm, peak_src = load_peaks()
     step_s = t_dev / a.steps
     roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
@@ -309,7 +359,7 @@ def main():
     if rank == 0:
         value = a.steps / t_dev
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": 1e3 * t_dev / a.steps, "host_issue_ms_per_step": host_issue_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.dtype, "data": "synthetic",
                 "config": {"workload": ("TINY-DEBUG " if a.tiny else "") + "SD1.5 512^2 full CoMat (BLIP concept-match + attention-map "
                            "token/pixel loss on 2 attrcon steps + GAN G/D), S=%d DDPM steps, K=%d, batch %d/GPU, LoRA r=%d, cfg 7.5 "

@@ -43,6 +43,7 @@ struct GemmKP {
   long long out32_ld;
   uint32_t idesc;
   int is_bf16;
+  int tiles_m;                 // number of 128-row (or 128-pixel) output tiles
   int split_k, kb_per_split;   // split-K: blockIdx.z handles k-blocks [z*kb_per_split, ...) and writes raw fp32 partials
   float* splitk_ws;            // [split_k][M][N] fp32
   int tma_store;     // 1: epilogue stages 16-bit tiles in (free) pipeline smem and writes them with TMA bulk tensor stores
@@ -60,6 +61,134 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
+// One 32-column chunk of the epilogue for one accumulator row: v[] holds the raw fp32 accumulators of columns
+// [n0+c0, n0+c0+32) of tile row r (global row m).  zsplit = split-K slice (raw partial store), stage = smem staging tile
+// for the TMA-store path.  Every runtime option is tested once per chunk (uniform branches), the element loops are
+// straight FFMA / pack code; bias comes from smem as float4 (the first version spent ~19 instructions per element here
+// and was instruction-issue bound: profiles/r01_gemm_k320_ncu.md).
+__device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (&v)[32], int c0, int n0, long long m, bool row_ok,
+                                           const float* rv, const float* s_bias, int r, unsigned char* stage, int zsplit) {
+  const int ncol = min(32, p.N - (n0 + c0));
+  if (p.split_k > 1) {
+    if (row_ok && ncol > 0) {
+      float* wp = p.splitk_ws + ((size_t)zsplit * p.M + m) * p.N + n0 + c0;
+      if (ncol == 32 && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(wp + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) wp[j] = __uint_as_float(v[j]);
+      }
+    }
+  } else if (p.tma_store || (row_ok && ncol > 0)) {
+    // lean epilogue: every runtime option is tested once per 32-column chunk (uniform branches), the element loops
+    // are straight FFMA / pack code; bias comes from smem as float4 (the first version spent ~19 instructions per
+    // element here and was instruction-issue bound: profiles/r01_gemm_k320_ncu.md)
+    float f[32];
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = b4[j / 4];
+      f[j] = fmaf(__uint_as_float(v[j]), p.alpha, bb.x);
+      f[j + 1] = fmaf(__uint_as_float(v[j + 1]), p.alpha, bb.y);
+      f[j + 2] = fmaf(__uint_as_float(v[j + 2]), p.alpha, bb.z);
+      f[j + 3] = fmaf(__uint_as_float(v[j + 3]), p.alpha, bb.w);
+    }
+    if (rv != nullptr) {
+      const float* rvc = rv + n0 + c0;
+      if (ncol == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] += rvc[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) f[j] += rvc[j];
+      }
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+    } else if (p.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+    }
+    if (p.residual != nullptr && row_ok && ncol > 0) {
+      const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
+      if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+        uint4 u[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) u[j4] = *reinterpret_cast<const uint4*>(rp + j4 * 8);
+        if (p.is_bf16) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint32_t w[4] = {u[j4].x, u[j4].y, u[j4].z, u[j4].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[j4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
+              f[j4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint32_t w[4] = {u[j4].x, u[j4].y, u[j4].z, u[j4].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+              f[j4 * 8 + e * 2 + 0] += t.x;
+              f[j4 * 8 + e * 2 + 1] += t.y;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {          // static indexing keeps f[] in registers
+          if (j < ncol) {
+            const uint16_t bv = rp[j];
+            f[j] += p.is_bf16 ? __uint_as_float((uint32_t)bv << 16) : __half2float(*reinterpret_cast<const __half*>(&bv));
+          }
+        }
+      }
+    }
+    uint32_t pk[16];
+    if (p.out16 != nullptr) {
+      if (p.is_bf16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&t); }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&t); }
+      }
+    }
+    if (p.tma_store) {
+      // panel (c0/32): [128 rows][64 B], 64B-swizzled (16B chunk q of row r lives at q ^ ((r>>1)&3))
+      unsigned char* prow = stage + (c0 / 32) * 8192 + r * 64;
+      const int sw = (r >> 1) & 3;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+        *reinterpret_cast<uint4*>(prow + ((q4 ^ sw) * 16)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+    } else if (p.out16 != nullptr) {
+      uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n0 + c0;
+      if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(op + q4 * 8) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) op[j] = (uint16_t)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xFFFFu));
+      }
+    }
+    if (p.out32 != nullptr && row_ok) {
+      float* op = p.out32 + m * p.out32_ld + n0 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncol) op[j] = f[j];
+    }
+  }
+}
+
 template <int BN>
 constexpr int tmem_cols() { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512; }
 
@@ -71,7 +200,7 @@ struct GemmSmem {
   static constexpr int TILES = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = TILES;                       // full[STAGES], empty[STAGES], tmem_full
   static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
-  static constexpr int BIAS_OFF = TMEMPTR_OFF + 8;
+  static constexpr int BIAS_OFF = (TMEMPTR_OFF + 8 + 15) & ~15;     // float4-aligned
   static constexpr int TOTAL = BIAS_OFF + BN * 4 + 1024;      // +1024: manual alignment slack
 };
 
@@ -194,125 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
       tmem_ld_wait();
-      const int ncol = min(32, p.N - (n0 + c0));
-      if (p.split_k > 1) {
-        if (row_ok && ncol > 0) {
-          float* wp = p.splitk_ws + ((size_t)blockIdx.z * p.M + m) * p.N + n0 + c0;
-          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(wp + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) wp[j] = __uint_as_float(v[j]);
-          }
-        }
-      } else if (p.tma_store || (row_ok && ncol > 0)) {
-        // lean epilogue: every runtime option is tested once per 32-column chunk (uniform branches), the element loops
-        // are straight FFMA / pack code; bias comes from smem as float4 (the first version spent ~19 instructions per
-        // element here and was instruction-issue bound: profiles/r01_gemm_k320_ncu.md)
-        float f[32];
-        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = b4[j / 4];
-          f[j] = fmaf(__uint_as_float(v[j]), p.alpha, bb.x);
-          f[j + 1] = fmaf(__uint_as_float(v[j + 1]), p.alpha, bb.y);
-          f[j + 2] = fmaf(__uint_as_float(v[j + 2]), p.alpha, bb.z);
-          f[j + 3] = fmaf(__uint_as_float(v[j + 3]), p.alpha, bb.w);
-        }
-        if (rv != nullptr) {
-          const float* rvc = rv + n0 + c0;
-          if (ncol == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += rvc[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) f[j] += rvc[j];
-          }
-        }
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
-        } else if (p.act == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
-        }
-        if (p.residual != nullptr && row_ok && ncol > 0) {
-          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
-          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-            uint4 u[4];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) u[j4] = *reinterpret_cast<const uint4*>(rp + j4 * 8);
-            if (p.is_bf16) {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const uint32_t w[4] = {u[j4].x, u[j4].y, u[j4].z, u[j4].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  f[j4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
-                  f[j4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const uint32_t w[4] = {u[j4].x, u[j4].y, u[j4].z, u[j4].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-                  f[j4 * 8 + e * 2 + 0] += t.x;
-                  f[j4 * 8 + e * 2 + 1] += t.y;
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {          // static indexing keeps f[] in registers
-              if (j < ncol) {
-                const uint16_t bv = rp[j];
-                f[j] += p.is_bf16 ? __uint_as_float((uint32_t)bv << 16) : __half2float(*reinterpret_cast<const __half*>(&bv));
-              }
-            }
-          }
-        }
-        uint32_t pk[16];
-        if (p.out16 != nullptr) {
-          if (p.is_bf16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&t); }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { const __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&t); }
-          }
-        }
-        if (p.tma_store) {
-          // panel (c0/32): [128 rows][64 B], 64B-swizzled (16B chunk q of row r lives at q ^ ((r>>1)&3))
-          unsigned char* prow = smem + (c0 / 32) * 8192 + r * 64;
-          const int sw = (r >> 1) & 3;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(prow + ((q4 ^ sw) * 16)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-        } else if (p.out16 != nullptr) {
-          uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n0 + c0;
-          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              *reinterpret_cast<uint4*>(op + q4 * 8) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) op[j] = (uint16_t)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xFFFFu));
-          }
-        }
-        if (p.out32 != nullptr && row_ok) {
-          float* op = p.out32 + m * p.out32_ld + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) op[j] = f[j];
-        }
-      }
+      epilogue_chunk(p, v, c0, n0, m, row_ok, rv, s_bias, r, smem, blockIdx.z);
     }
     tc_fence_before();
     if (p.tma_store) {
@@ -334,6 +345,209 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols<BN>());
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant (default): one CTA per SM walks the (m-tile, n-tile, k-split) work list, n fastest so the CTAs
+// running at the same time share A rows through L2.  The TMA producer runs ahead across tile boundaries (deeper smem
+// ring than the one-tile kernel), the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
+// main loop of tile i+1, and the 16-bit output goes through a dedicated staging tile + TMA bulk tensor stores.
+// Measured motivation (profiles/r01_gemm_shapes_v3.md): K <= 640 shapes ran at 400-500 TFLOP/s in the one-tile kernel
+// because prologue + first-load latency + epilogue were serialised per tile, and single-wave long-K shapes were
+// latency-bound by a 3-stage ring.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct PersistSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TILES = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFF = TILES;                         // [(BN+31)/32 panels][128 rows][64 B]
+  static constexpr int STAGING_BYTES = ((BN + 31) / 32) * 8192;
+  static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;       // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int BIAS_OFF = (TMEMPTR_OFF + 8 + 15) & ~15;     // [2][BN] floats, float4-aligned
+  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;        // +1024: manual alignment slack
+};
+
+struct TileCoord {
+  int tile_n, z, m0, img0, h0, w0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int t, int tiles_n) {
+  TileCoord c;
+  const int per_z = p.tiles_m * tiles_n;
+  c.z = t / per_z;
+  const int r = t - c.z * per_z;
+  const int tile_m = r / tiles_n;
+  c.tile_n = r - tile_m * tiles_n;
+  c.m0 = tile_m * BM; c.img0 = 0; c.h0 = 0; c.w0 = 0;
+  if (p.conv) {
+    const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
+    c.w0 = tw * p.TW; c.h0 = th * p.TH; c.img0 = tn * p.TN;
+  }
+  return c;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                       const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                       const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
+  using S = PersistSmem<BN, STAGES>;
+  constexpr int ACC = tmem_cols<BN>();           // TMEM columns per accumulator buffer
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull = empty_bar + STAGES;          // [2] accumulator ready for the epilogue
+  uint64_t* tempty = tfull + 2;                  // [2] accumulator drained, MMA may overwrite
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::TMEMPTR_OFF);
+  float* s_bias = reinterpret_cast<float*>(smem + S::BIAS_OFF);
+  unsigned char* staging = smem + S::STAGING_OFF;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int total_tiles = p.tiles_m * tiles_n * p.split_k;
+  const int kb_per_tap = p.seg_kblocks[0] + (p.n_seg > 1 ? p.seg_kblocks[1] : 0);
+  const int num_kb_total = p.n_taps * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.n_seg > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
+    if (p.tma_store) tma_prefetch_desc(&tmO);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);      // one arrival per epilogue warp
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 2 * ACC);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer: streams k-blocks of tile after tile =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t, tiles_n);
+        const int n0 = c.tile_n * BN;
+        const int kb_begin = c.z * p.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+        int tap = kb_begin / kb_per_tap;
+        int rem = kb_begin - tap * kb_per_tap;
+        for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
+          const int sg = (rem >= p.seg_kblocks[0]) ? 1 : 0;
+          const int cb = rem - (sg ? p.seg_kblocks[0] : 0);
+          const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
+          const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * S::STAGE_BYTES;
+          unsigned char* sb = sa + S::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          if (p.conv) tma_load_4d(sa, mA, &full_bar[stage], cb * BK, c.w0 + p.dw[tap], c.h0 + p.dh[tap], c.img0);
+          else        tma_load_2d(sa, mA, &full_bar[stage], cb * BK, c.m0);
+          tma_load_2d(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++rem == kb_per_tap) { rem = 0; ++tap; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread), accumulator buffer it & 1 =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0, it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int z = t / (p.tiles_m * tiles_n);
+        const int kb_begin = z * p.kb_per_split;
+        const int num_kb = min(num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
+        const int acc = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);        // epilogue has drained this buffer (passes at once on first use)
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+          const uint64_t da = make_kmajor_sw128_desc(sa);
+          const uint64_t db = make_kmajor_sw128_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 64;             // 0..127
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileCoord c = decode_tile(p, t, tiles_n);
+      const int n0 = c.tile_n * BN;
+      const int acc = it & 1, aph = (it >> 1) & 1;
+      long long m;
+      bool row_ok;
+      if (p.conv) {
+        const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
+        const int n_i = c.img0 + tn, hh = c.h0 + th, ww = c.w0 + tw;
+        row_ok = (n_i < p.n_img) && (hh < p.H) && (ww < p.W);
+        m = ((long long)n_i * p.H + hh) * p.W + ww;
+      } else {
+        m = (long long)c.m0 + r;
+        row_ok = m < p.M;
+      }
+      const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * p.rowvec_ld : nullptr;
+      float* bias_buf = s_bias + (it & 1) * BN;
+      for (int i = et; i < BN; i += 128) bias_buf[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+      if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();   // previous tile's stores have read the staging tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+        tmem_ld_wait();
+        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator buffer free for tile it + 2
+      if (p.tma_store) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+#pragma unroll 1
+          for (int pn = 0; pn < (BN + 31) / 32; ++pn) {
+            if (n0 + pn * 32 >= p.N) break;
+            if (p.conv) tma_store_4d(&tmO, staging + pn * 8192, n0 + pn * 32, c.w0, c.h0, c.img0);
+            else        tma_store_2d(&tmO, staging + pn * 8192, n0 + pn * 32, c.m0);
+          }
+          bulk_commit();
+        }
+      }
+    }
+    if (p.tma_store && warp == 2 && lane == 0) bulk_wait_all<0>();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * ACC);
   }
 }
 
@@ -375,6 +589,21 @@ static int launch_gemm(const CUtensorMap* maps, const GemmKP& kp, dim3 grid, cud
   return COMAT_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_gemm_persist(const CUtensorMap* maps, const GemmKP& kp, int total_tiles, cudaStream_t st) {
+  using S = PersistSmem<BN, STAGES>;
+  static_assert(S::TOTAL <= 232448, "persistent GEMM smem budget");
+  static bool configured = false;
+  if (!configured) {
+    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  gemm_tc_persist_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
 }  // namespace comat
 
 using namespace comat;
@@ -399,7 +628,10 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   kp.alpha = g->alpha; kp.bias = g->bias; kp.rowvec = g->rowvec; kp.rowvec_ld = g->rowvec_ld > 0 ? g->rowvec_ld : g->N; kp.rows_per_group = g->rows_per_group > 0 ? g->rows_per_group : 1;
   kp.act = g->act; kp.residual = g->residual; kp.res_ld = g->res_ld; kp.out16 = g->out16; kp.out_ld = g->out_ld;
   kp.out32 = g->out32; kp.out32_ld = g->out32_ld; kp.is_bf16 = g->dtype == COMAT_BF16;
-  const int BN = pick_bn(g->N, g->force_bn);
+  int BN = pick_bn(g->N, g->force_bn);
+  // 256-wide tiles need 25 % less smem operand traffic per FLOP than 160-wide ones; take them when N divides and
+  // there are enough of them to fill the machine (profiles/r01_gemm_persist_vs_tile.md)
+  if (g->force_bn == 0 && (g->N % 256) == 0 && (long long)((g->M + BM - 1) / BM) * (g->N / 256) >= num_sms()) BN = 256;
   kp.idesc = make_idesc_f16(BM, BN, kp.is_bf16 ? 1 : 0);
   CUtensorMap maps[5];
   memset(maps, 0, sizeof(maps));
@@ -425,9 +657,11 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     kp.tiles_w = (g->W + TW - 1) / TW; kp.tiles_h = (g->H + TH - 1) / TH;
     const int tiles_n = (g->n_img + TN - 1) / TN;
     grid = dim3(kp.tiles_w * kp.tiles_h * tiles_n, (g->N + BN - 1) / BN, 1);
+    kp.tiles_m = (int)grid.x;
   } else {
     kp.n_taps = 1; kp.c_total = 0;
     grid = dim3((g->M + BM - 1) / BM, (g->N + BN - 1) / BN, 1);
+    kp.tiles_m = (int)grid.x;
   }
   for (int s = 0; s < g->n_seg; ++s) {
     const int K = g->a_k[s];
@@ -492,6 +726,26 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   }
   cudaStream_t st = (cudaStream_t)stream;
   int rc = COMAT_ERR_UNSUPPORTED;
+  // kernel choice (COMAT_GEMM_KERNEL=tile|persist forces one for A/B measurements): the persistent kernel wins when the
+  // per-tile prologue/epilogue dominates (short K) or when there is at most one wave of tiles (deeper ring covers the
+  // load latency); with long K and several waves two co-resident one-tile CTAs keep more loads in flight per SM.
+  static int kernel_mode = -1;
+  if (kernel_mode < 0) {
+    const char* e = getenv("COMAT_GEMM_KERNEL");
+    kernel_mode = (e && !strcmp(e, "tile")) ? 0 : (e && !strcmp(e, "persist")) ? 1 : 2;
+  }
+  const int total_tiles = (int)(grid.x * grid.y * grid.z);
+  const int kb_all = kp.n_taps * (kp.seg_kblocks[0] + (g->n_seg > 1 ? kp.seg_kblocks[1] : 0));
+  const bool use_persist = kernel_mode == 1 || (kernel_mode == 2 && (kb_all <= 24 || total_tiles <= num_sms()));
+  if (use_persist) {
+    switch (BN) {
+      case 32:  rc = launch_gemm_persist<32, 8>(maps, kp, total_tiles, st); break;
+      case 64:  rc = launch_gemm_persist<64, 8>(maps, kp, total_tiles, st); break;
+      case 128: rc = launch_gemm_persist<128, 6>(maps, kp, total_tiles, st); break;
+      case 160: rc = launch_gemm_persist<160, 5>(maps, kp, total_tiles, st); break;
+      case 256: rc = launch_gemm_persist<256, 3>(maps, kp, total_tiles, st); break;
+    }
+  } else
   switch (BN) {
     case 32:  rc = launch_gemm<32, 4>(maps, kp, grid, st); break;
     case 64:  rc = launch_gemm<64, 4>(maps, kp, grid, st); break;

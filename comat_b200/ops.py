@@ -120,15 +120,20 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         keep.append(ws)
     elif accumulate:
         raise _lib.ComatError("gemm: accumulate=True needs split_k > 1")
-    if PROFILE is not None:
+    if PROFILE is not None and "keys_only" not in PROFILE:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.check(_lib.lib().comat_gemm(C.byref(p), _lib.stream_ptr()), "gemm")
     _lib.count_launch()
     if PROFILE is not None:
-        e1.record()
-        PROFILE["events"].append((e0, e1))
-        PROFILE["flops"] += 2.0 * M * N * sum(a.shape[-1] for a in a_segs) * (len(conv_taps) if conv else 1)
+        if "keys_only" in PROFILE:
+            e0 = e1 = None
+        else:
+            e1.record()
+        fl = 2.0 * M * N * sum(a.shape[-1] for a in a_segs) * (len(conv_taps) if conv else 1)
+        PROFILE["events"].append((e0, e1, (M, N, tuple(a.shape[-1] for a in a_segs), len(conv_taps) if conv else 0, int(p.split_k),
+                                           bool(out_fp32)), fl))
+        PROFILE["flops"] += fl
     if conv:
         return out.reshape(n_img, H, W, N) if out.dim() == 2 else out
     return out

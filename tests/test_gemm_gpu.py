@@ -27,6 +27,27 @@ def test_plain_gemm(M, N, K, bn, dtype):
     assert l2 < tol and mx < 4 * tol, (l2, mx)
 
 
+@pytest.mark.parametrize("M,N,K,why", [
+    (40 * 128, 1024, 320, "auto BN=256, persistent (short K), several tiles per CTA"),
+    (300 * 128 + 17, 320, 192, "persistent, >2 tiles per CTA so both TMEM accumulator buffers wrap, ragged last m-tile"),
+    (200 * 128, 320, 2048, "long K, several waves: one-tile kernel"),
+    (640, 1280, 2560, "single wave, long K: persistent with the deep ring"),
+    (150 * 128, 96, 64, "one k-block per tile, N < tile width"),
+])
+def test_gemm_kernel_selection_paths(M, N, K, why):
+    """Both GEMM kernels (one-tile-per-CTA and persistent, see gemm_tc.cu) and the automatic 256-wide tile choice, each on a
+    shape the host heuristic routes to it; exact small-integer data so any tile / accumulator-buffer mix-up is a wrong integer."""
+    from comat_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randint(-2, 3, (M, K), device="cuda", generator=g).half()
+    b = torch.randint(-2, 3, (N, K), device="cuda", generator=g).half()
+    bias = torch.randint(-4, 5, (N,), device="cuda", generator=g).float()
+    out = ops.gemm([a], [b], bias=bias, out_fp32=False)
+    ref = a.float() @ b.float().t() + bias
+    assert ref.abs().max() < 2048            # exactly representable in fp16
+    assert torch.equal(out.float(), ref), (why, (out.float() - ref).abs().nonzero()[:8])
+
+
 def test_gemm_identity_pattern_exact():
     """small integers are exact in fp16/fp32: any descriptor / swizzle / row-mapping slip shows up as a wrong integer."""
     from comat_b200 import ops

@@ -35,7 +35,7 @@ def main():
         med, best = timeit(lambda i: ops.gemm([xs[i % nb]], [w], bias=bias, conv_taps=ops.TAPS_3x3, out=out))
         fl = 2.0 * n * H * H * C * 9 * Co
         res.append({"op": f"conv3x3 n{n} {H}x{H} {C}->{Co}", "ms": med * 1e3, "tflops_med": fl / med / 1e12, "tflops_best": fl / best / 1e12})
-    for (M, K, N) in [(32768, 320, 2560), (32768, 1280, 320), (8192, 640, 5120), (8192, 2560, 640), (2048, 1280, 10240), (32768, 320, 320), (4616, 1024, 4096), (8192, 8192, 8192), (32768, 320, 128), (616, 768, 320), (640, 128, 128)]:
+    for (M, K, N) in [(32768, 320, 2560), (32768, 1280, 320), (8192, 640, 5120), (8192, 2560, 640), (2048, 1280, 10240), (32768, 320, 320), (4616, 1024, 4096), (8192, 8192, 8192), (32768, 320, 128), (616, 768, 320), (640, 128, 128), (2048, 1280, 128), (2048, 1280, 1280), (8192, 640, 640)]:
         nb = max(2, int(2.6e8 // (M * K * 2)) + 1)
         xs = [torch.randn(M, K, device="cuda").to(dt) for _ in range(nb)]
         w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(dt)
