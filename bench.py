@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--no_gan", action="store_true")
     p.add_argument("--no_attrcon", action="store_true")
     p.add_argument("--no_graphs", action="store_true", help="disable CUDA-graph replay of the no-grad UNet forwards")
+    p.add_argument("--sync_debug", action="store_true", help="run ONE step with torch.cuda.set_sync_debug_mode('warn') and list the host-sync call sites")
     p.add_argument("--gemm_shapes", default="", help="write the per-shape GEMM table of the instrumented step to this path")
     p.add_argument("--kineto_step", default="", help="profile ONE step with torch.profiler (CUPTI) and write a per-kernel table to this path")
     p.add_argument("--profile_step", action="store_true",
@@ -263,6 +264,23 @@ def main():
 
     for i in range(a.warmup):
         trainer.train_step(dev_batches[i % len(dev_batches)])
+    if a.sync_debug:
+        import traceback, warnings
+        torch.cuda.synchronize()
+        seen = {}
+        def _show(message, category, filename, lineno, file=None, line=None):
+            st = [f for f in traceback.extract_stack() if "/comat_b200/" in f.filename or f.filename.endswith("bench.py")]
+            key = " <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in reversed(st[-4:]))
+            seen[key] = seen.get(key, 0) + 1
+        warnings.showwarning = _show
+        warnings.simplefilter("always")
+        torch.cuda.set_sync_debug_mode("warn")
+        trainer.train_step(dev_batches[0])
+        torch.cuda.set_sync_debug_mode("default")
+        torch.cuda.synchronize()
+        for k, v in sorted(seen.items(), key=lambda kv: -kv[1]):
+            print(f"SYNC x{v}: {k}")
+        return 0
     if a.kineto_step:
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()

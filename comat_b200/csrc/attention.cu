@@ -70,6 +70,7 @@ template <int D, typename T>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVt, const AttnKP p) {
+  pdl_grid_dependency_sync();
   using Cf = AttnCfg<D>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -312,6 +313,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // V (n, Lk, H*d) -> V^T (n*H, d, Lpad) with zero padding of keys >= Lk  (K-major B operand of P.V)
 template <typename T>
 __global__ void kv_transpose_kernel(const T* __restrict__ v, T* __restrict__ vt, int Lk, int H, int d, int Lpad) {
+  pdl_grid_dependency_sync();
   __shared__ T tile[32][33];
   const int bh = blockIdx.z, b = bh / H, h = bh % H;
   const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -334,7 +336,7 @@ static int launch_attn(const CUtensorMap* maps, const AttnKP& kp, dim3 grid, cud
     COMAT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::TOTAL));
     configured = true;
   }
-  attn_fwd_kernel<D, T><<<grid, ATT_THREADS, Cf::TOTAL, st>>>(maps[0], maps[1], maps[2], kp);
+  launch_k(attn_fwd_kernel<D, T>, grid, ATT_THREADS, Cf::TOTAL, st, maps[0], maps[1], maps[2], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -360,7 +362,7 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
   void* vt = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   {
     dim3 g((Lpad + 31) / 32, (d + 31) / 32, n * H), blk(32, 8);
-    kv_transpose_kernel<__half><<<g, blk, 0, st>>>((const __half*)v, (__half*)vt, Lk, H, d, Lpad);
+    launch_k(kv_transpose_kernel<__half>, g, blk, 0, st, (const __half*)v, (__half*)vt, Lk, H, d, Lpad);
   }
   AttnKP kp;
   memset(&kp, 0, sizeof(kp));

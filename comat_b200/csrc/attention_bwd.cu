@@ -80,6 +80,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
                 const __grid_constant__ CUtensorMap tmT1,   // streamed transposed: MODE0 K^T | MODE1 dO^T  (box {64, DN})
                 const __grid_constant__ CUtensorMap tmT2,   //                      MODE1 Q^T
                 const AttnBwdKP p) {
+  pdl_grid_dependency_sync();
   using Cf = ABCfg<D, MODE>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -335,6 +336,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
 // (n, L, H*d) -> per-head transpose (n*H, d, Lpad), zero padded  (same as the forward's V^T pre-pass)
 template <typename T>
 __global__ void ab_transpose_kernel(const T* __restrict__ v, T* __restrict__ vt, int L, int H, int d, int Lpad) {
+  pdl_grid_dependency_sync();
   __shared__ T tile[32][33];
   const int bh = blockIdx.z, b = bh / H, h = bh % H;
   const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(256) ab_prep_kernel(const T* __restrict__ o, c
                                                       const float* __restrict__ probs, const float* __restrict__ dp_ext,
                                                       float* __restrict__ lse_pad, float* __restrict__ D_pad, int n, int Lq, int Lk, int H,
                                                       int d, int Lq_pad) {
+  pdl_grid_dependency_sync();
   __shared__ float s_acc[8][32];                       // per warp: up to 32 heads
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;   // row = b * Lq_pad + q
@@ -399,7 +402,7 @@ static int launch_ab(const CUtensorMap* m, const AttnBwdKP& kp, dim3 grid, cudaS
     COMAT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::TOTAL));
     configured = true;
   }
-  attn_bwd_kernel<D, MODE, T><<<grid, AB_THREADS, Cf::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], kp);
+  launch_k(attn_bwd_kernel<D, MODE, T>, grid, AB_THREADS, Cf::TOTAL, st, m[0], m[1], m[2], m[3], m[4], m[5], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -469,15 +472,15 @@ extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, 
   float* D_pad = lse_pad + (size_t)n * H * Lqp;
   {
     dim3 blk(32, 8);
-    ab_transpose_kernel<__half><<<dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)q, (__half*)qT, Lq, H, d, Lqp);
-    ab_transpose_kernel<__half><<<dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)dO, (__half*)dOT, Lq, H, d, Lqp);
-    ab_transpose_kernel<__half><<<dim3((Lkp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st>>>((const __half*)k, (__half*)kT, Lk, H, d, Lkp);
+    launch_k(ab_transpose_kernel<__half>, dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st, (const __half*)q, (__half*)qT, Lq, H, d, Lqp);
+    launch_k(ab_transpose_kernel<__half>, dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st, (const __half*)dO, (__half*)dOT, Lq, H, d, Lqp);
+    launch_k(ab_transpose_kernel<__half>, dim3((Lkp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st, (const __half*)k, (__half*)kT, Lk, H, d, Lkp);
     const long long rows = (long long)n * Lqp;
     if (H > 32) return COMAT_ERR_UNSUPPORTED;
     if (dtype == COMAT_F16)
-      ab_prep_kernel<__half><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __half*)o, (const __half*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
+      launch_k(ab_prep_kernel<__half>, (unsigned)((rows + 7) / 8), 256, 0, st, (const __half*)o, (const __half*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
     else
-      ab_prep_kernel<__nv_bfloat16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
+      launch_k(ab_prep_kernel<__nv_bfloat16>, (unsigned)((rows + 7) / 8), 256, 0, st, (const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
   }
   AttnBwdKP kp;
   memset(&kp, 0, sizeof(kp));

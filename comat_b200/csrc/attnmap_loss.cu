@@ -57,6 +57,7 @@ struct Tables {
 
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(FWD_THREADS) attnmap_fwd_kernel(Tables tb, float* __restrict__ state, StateLayout L) {
+  pdl_grid_dependency_sync();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int T = tb.T;
   const int tile_floats = TILE_PX * T;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(FWD_THREADS) attnmap_fwd_kernel(Tables tb, flo
 // shuffle tree -> bit-reproducible).  Stage B: one CTA per (group, sample): token-loss terms, backward coefficients, pixel sum;
 // the last CTA adds the per-(group, sample) results in index order.
 __global__ void __launch_bounds__(256) attnmap_reduce_kernel(Tables tb, float* __restrict__ state, StateLayout L) {
+  pdl_grid_dependency_sync();
   const int slots = tb.maxMG * tb.maxH * MAXP;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(256) attnmap_reduce_kernel(Tables tb, float* _
 
 __global__ void __launch_bounds__(256) attnmap_finalize_kernel(Tables tb, float* __restrict__ state, StateLayout L,
                                                                float* __restrict__ loss2, unsigned int* counter) {
+  pdl_grid_dependency_sync();
   __shared__ float s_red[256];
   __shared__ bool s_last;
   const int gb = blockIdx.x;
@@ -263,6 +266,7 @@ constexpr int BWD_THREADS = 128;
 __global__ void __launch_bounds__(BWD_THREADS) attnmap_bwd_kernel(Tables tb, const float* __restrict__ state, StateLayout L,
                                                                   const float* __restrict__ grad2,
                                                                   const int64_t* __restrict__ map_grad_ptr) {
+  pdl_grid_dependency_sync();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int T = tb.T;
   const int tile_floats = TILE_PX * T;
@@ -353,6 +357,7 @@ __device__ __forceinline__ void aa_window(int o, float scale, int in_size, int& 
 }
 __global__ void mask_resize_any_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int n, int in_h, int in_w,
                                        int res) {
+  pdl_grid_dependency_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * res * res) return;
   const int x = idx % res, y = (idx / res) % res, i = idx / (res * res);
@@ -422,13 +427,13 @@ extern "C" int comat_attnmap_loss_fwd(const comat_attnmap_plan* p, float* loss2,
     COMAT_CUDA(cudaFuncSetAttribute(attnmap_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  attnmap_fwd_kernel<<<p->n_work, FWD_THREADS, smem, st>>>(tb, state, L);
+  launch_k(attnmap_fwd_kernel, p->n_work, FWD_THREADS, smem, st, tb, state, L);
   COMAT_CHECK_LAUNCH();
   {
     const long long warps = (long long)p->n_groups * p->n_samples * p->max_maps_per_group * p->max_heads * MAXP;
-    attnmap_reduce_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tb, state, L);
+    launch_k(attnmap_reduce_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, st, tb, state, L);
   }
-  attnmap_finalize_kernel<<<p->n_groups * p->n_samples, 256, 0, st>>>(tb, state, L, loss2, counter);
+  launch_k(attnmap_finalize_kernel, p->n_groups * p->n_samples, 256, 0, st, tb, state, L, loss2, counter);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -446,7 +451,7 @@ extern "C" int comat_attnmap_loss_bwd(const comat_attnmap_plan* p, const float* 
     COMAT_CUDA(cudaFuncSetAttribute(attnmap_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  attnmap_bwd_kernel<<<p->n_work, BWD_THREADS, smem, (cudaStream_t)stream>>>(tb, state, L, grad2, map_grad_ptr);
+  launch_k(attnmap_bwd_kernel, p->n_work, BWD_THREADS, smem, (cudaStream_t)stream, tb, state, L, grad2, map_grad_ptr);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -454,7 +459,7 @@ extern "C" int comat_attnmap_loss_bwd(const comat_attnmap_plan* p, const float* 
 extern "C" int comat_mask_resize_any(const uint8_t* in, float* out, int n, int in_h, int in_w, int res, void* stream) {
   if (!in || !out || n <= 0 || in_h <= 0 || in_w <= 0 || res <= 0) return COMAT_ERR_INVALID;
   const int total = n * res * res;
-  mask_resize_any_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, out, n, in_h, in_w, res);
+  launch_k(mask_resize_any_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, in, out, n, in_h, in_w, res);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }

@@ -19,6 +19,7 @@ __device__ __forceinline__ float block_reduce(float v, float* sm, bool is_max) {
 // one CTA per row: stats[r] = {lse, loss_row}
 __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                                       float* __restrict__ stats, int V, long long ld, float eps, long long ignore) {
+  pdl_grid_dependency_sync();
   __shared__ float sm[8];
   const int r = blockIdx.x;
   const float* x = logits + (size_t)r * ld;
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
 // out[0] = mean loss over non-ignored rows, out[1] = count (fixed-order sum)
 __global__ void ce_mean_kernel(const float* __restrict__ stats, const long long* __restrict__ labels, float* __restrict__ out, int R,
                                long long ignore) {
+  pdl_grid_dependency_sync();
   if (threadIdx.x != 0) return;
   float s = 0.f, c = 0.f;
   for (int r = 0; r < R; ++r)
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
                                                      const float* __restrict__ stats, const float* __restrict__ out2,
                                                      const float* __restrict__ gout, T* __restrict__ dlogits, int V, int Vpad, long long ld,
                                                      float eps, long long ignore) {
+  pdl_grid_dependency_sync();
   const int r = blockIdx.x;
   const long long y = labels[r];
   T* d = dlogits + (size_t)r * Vpad;
@@ -77,8 +80,8 @@ extern "C" int comat_ce_label_smooth_fwd(const float* logits, const long long* l
                                          long long ld, float eps, long long ignore_index, void* stream) {
   if (!logits || !labels || !row_stats || !out2 || R <= 0 || V <= 0) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  ce_rows_kernel<<<R, 256, 0, st>>>(logits, labels, row_stats, V, ld, eps, ignore_index);
-  ce_mean_kernel<<<1, 32, 0, st>>>(row_stats, labels, out2, R, ignore_index);
+  launch_k(ce_rows_kernel, R, 256, 0, st, logits, labels, row_stats, V, ld, eps, ignore_index);
+  launch_k(ce_mean_kernel, 1, 32, 0, st, row_stats, labels, out2, R, ignore_index);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -87,8 +90,8 @@ extern "C" int comat_ce_label_smooth_bwd(const float* logits, const long long* l
                                          long long ignore_index, int dtype, void* stream) {
   if (!logits || !labels || !row_stats || !out2 || !grad_out || !dlogits16 || Vpad < V) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == COMAT_F16) ce_bwd_kernel<__half><<<R, 256, 0, st>>>(logits, labels, row_stats, out2, grad_out, (__half*)dlogits16, V, Vpad, ld, eps, ignore_index);
-  else if (dtype == COMAT_BF16) ce_bwd_kernel<__nv_bfloat16><<<R, 256, 0, st>>>(logits, labels, row_stats, out2, grad_out, (__nv_bfloat16*)dlogits16, V, Vpad, ld, eps, ignore_index);
+  if (dtype == COMAT_F16) launch_k(ce_bwd_kernel<__half>, R, 256, 0, st, logits, labels, row_stats, out2, grad_out, (__half*)dlogits16, V, Vpad, ld, eps, ignore_index);
+  else if (dtype == COMAT_BF16) launch_k(ce_bwd_kernel<__nv_bfloat16>, R, 256, 0, st, logits, labels, row_stats, out2, grad_out, (__nv_bfloat16*)dlogits16, V, Vpad, ld, eps, ignore_index);
   else return COMAT_ERR_UNSUPPORTED;
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;

@@ -4,6 +4,8 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include "../../include/comat_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -29,6 +31,36 @@ extern "C" void comat_set_cuda_error(int e);
       return COMAT_ERR_CUDA;                                  \
     }                                                         \
   } while (0)
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel starts with pdl_grid_dependency_sync(): it lets the *next* kernel in the stream begin launching (its CTAs
+// become resident as ours drain, hiding launch latency and the tail of the last wave) and then waits until the
+// *previous* kernel has completed and flushed its memory.  Both instructions are no-ops for a kernel launched without the
+// programmatic-serialization attribute, so aten kernels interleaved in the stream keep ordinary stream semantics.
+// COMAT_PDL=0 launches everything without the attribute (A/B measurements).
+__device__ __forceinline__ void pdl_grid_dependency_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool comat_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("COMAT_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = comat_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors are picked up by COMAT_CHECK_LAUNCH()
+}
 
 namespace comat {
 

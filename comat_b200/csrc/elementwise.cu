@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(const T* __restrict__ x
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 const float* __restrict__ mean_rstd, float* __restrict__ part,
                                                                 int HW, int C, int G, int chunks, int silu) {
+  pdl_grid_dependency_sync();
   extern __shared__ float sm[];   // [2*C]
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int vcols = C / 8;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(const T* __restrict__ x
 // reduce chunk partials -> (mean, rstd) [MODE 0] or (sum_a, sum_b) [MODE 1]
 __global__ void gn_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nG, int G, int chunks, float inv_cnt,
                                  float eps, int mode) {
+  pdl_grid_dependency_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nG) return;
   const int n = i / G, g = i % G;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ mean_rstd, const float* __restrict__ sums,
                                                        long long total_vec, int HW, int C, int G, int silu) {
+  pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total_vec) return;
   const int vcols = C / 8;
@@ -153,6 +156,7 @@ template <typename T, int MODE>   // 0 fwd (saves mean,rstd) ; 1 bwd
 __global__ void __launch_bounds__(256) ln_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                  float* __restrict__ mean_rstd, long long rows, int C, float eps) {
+  pdl_grid_dependency_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -231,7 +235,8 @@ __global__ void __launch_bounds__(256) ln_kernel(const T* __restrict__ x, const 
 // ============================================================================================== GEGLU  (hidden * gelu(gate))
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ hg, const T* __restrict__ dy, T* __restrict__ out,
-                                                    long long rows, int Ch) {   // hg: [rows, 2*Ch] ; out fwd [rows,Ch], bwd [rows,2*Ch]
+                                                    long long rows, int Ch) {
+  pdl_grid_dependency_sync();   // hg: [rows, 2*Ch] ; out fwd [rows,Ch], bwd [rows,2*Ch]
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int vcols = Ch / 8;
   if (idx >= rows * vcols) return;
@@ -264,6 +269,7 @@ __global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ hg, co
 template <typename T>
 __global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, long long nvec,
                                                  int op, float alpha, float beta) {
+  pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nvec) return;
   Vec8<T> a, b, o;
@@ -292,6 +298,7 @@ __global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ x, const 
 // mode 2: space-to-depth (n,H,W,C)->(n,H/2,W/2,4C), channel block order (dy,dx)   mode 3: depth-to-space (inverse)
 template <typename T>
 __global__ void __launch_bounds__(256) spatial_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int H, int W, int C, int mode) {
+  pdl_grid_dependency_sync();
   // H, W are the dims of the *smaller* tensor for modes 0/1 and of the *larger* tensor for modes 2/3
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int vcols = C / 8;
@@ -347,6 +354,7 @@ __global__ void __launch_bounds__(256) spatial_kernel(const T* __restrict__ in, 
 // 16-bit matrix transpose [R, Cc] -> [Cc, R] (LoRA wgrad operands), 32x32 tiles through padded smem
 template <typename T>
 __global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int Cc, int ld_out) {
+  pdl_grid_dependency_sync();
   __shared__ T tile[32][33];
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += 8) {
@@ -363,6 +371,7 @@ __global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, 
 // fp32 <-> 16-bit casts with layout change for the 4-channel latents: NCHW fp32 -> NHWC 16-bit padded to Cpad channels
 template <typename T>
 __global__ void latent_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int n, int Cin, int HW, int Cpad, float scale) {
+  pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n * HW * Cpad) return;
   const int c = (int)(idx % Cpad);
@@ -373,6 +382,7 @@ __global__ void latent_to_nhwc_kernel(const float* __restrict__ in, T* __restric
 // NHWC 16-bit (first Cout of ld channels) -> NCHW fp32
 template <typename T>
 __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int n, int Cout, int HW, int ld, float scale) {
+  pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n * Cout * HW) return;
   const int p = (int)(idx % HW);
@@ -384,6 +394,7 @@ __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restr
 // strided 2-D copy of 16-bit rows: dst[r, 0:cols] = src[r, 0:cols]  (torch.cat([hidden, skip], dim=1) in NHWC)
 __global__ void __launch_bounds__(256) copy2d_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long rows, int vcols,
                                                      long long ld_src_v, long long ld_dst_v) {
+  pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * vcols) return;
   const long long r = idx / vcols;
@@ -416,9 +427,9 @@ extern "C" int comat_groupnorm_fwd(const void* x, void* y, const float* gamma, c
   const int chunks = gn_chunks(n, HW);
   const long long nvec = (long long)n * HW * (C / 8);
   DISPATCH_T(dtype, {
-    gn_partial_kernel<T, 0><<<dim3(chunks, n), gn_threads(C), 2 * C * sizeof(float), st>>>((const T*)x, nullptr, gamma, beta, nullptr, ws, HW, C, G, chunks, 0);
-    gn_reduce_kernel<<<(n * G + 127) / 128, 128, 0, st>>>(ws, mean_rstd, n * G, G, chunks, 1.f / ((float)HW * (C / G)), eps, 0);
-    gn_apply_kernel<T, 0><<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, nullptr, nvec, HW, C, G, silu);
+    launch_k(gn_partial_kernel<T, 0>, dim3(chunks, n), gn_threads(C), 2 * C * sizeof(float), st, (const T*)x, nullptr, gamma, beta, nullptr, ws, HW, C, G, chunks, 0);
+    launch_k(gn_reduce_kernel, (n * G + 127) / 128, 128, 0, st, ws, mean_rstd, n * G, G, chunks, 1.f / ((float)HW * (C / G)), eps, 0);
+    launch_k(gn_apply_kernel<T, 0>, (unsigned)((nvec + 255) / 256), 256, 0, st, (const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, nullptr, nvec, HW, C, G, silu);
   });
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
@@ -432,9 +443,9 @@ extern "C" int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, cons
   float* sums = ws + (size_t)n * chunks * G * 2;
   const long long nvec = (long long)n * HW * (C / 8);
   DISPATCH_T(dtype, {
-    gn_partial_kernel<T, 1><<<dim3(chunks, n), gn_threads(C), 2 * C * sizeof(float), st>>>((const T*)x, (const T*)dy, gamma, beta, mean_rstd, ws, HW, C, G, chunks, silu);
-    gn_reduce_kernel<<<(n * G + 127) / 128, 128, 0, st>>>(ws, sums, n * G, G, chunks, 1.f / ((float)HW * (C / G)), 0.f, 1);
-    gn_apply_kernel<T, 1><<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((const T*)x, (const T*)dy, (T*)dx, gamma, beta, mean_rstd, sums, nvec, HW, C, G, silu);
+    launch_k(gn_partial_kernel<T, 1>, dim3(chunks, n), gn_threads(C), 2 * C * sizeof(float), st, (const T*)x, (const T*)dy, gamma, beta, mean_rstd, ws, HW, C, G, chunks, silu);
+    launch_k(gn_reduce_kernel, (n * G + 127) / 128, 128, 0, st, ws, sums, n * G, G, chunks, 1.f / ((float)HW * (C / G)), 0.f, 1);
+    launch_k(gn_apply_kernel<T, 1>, (unsigned)((nvec + 255) / 256), 256, 0, st, (const T*)x, (const T*)dy, (T*)dx, gamma, beta, mean_rstd, sums, nvec, HW, C, G, silu);
   });
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
@@ -443,14 +454,14 @@ extern "C" int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, cons
 extern "C" int comat_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, long long rows,
                                    int C, float eps, int dtype, void* stream) {
   if (!x || !y || !gamma || !beta || !mean_rstd || C % 8 || C > 2048) return COMAT_ERR_INVALID;
-  DISPATCH_T(dtype, (ln_kernel<T, 0><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, rows, C, eps)));
+  DISPATCH_T(dtype, (launch_k(ln_kernel<T, 0>, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, (const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, rows, C, eps)));
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 extern "C" int comat_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* mean_rstd, long long rows,
                                    int C, int dtype, void* stream) {
   if (!x || !dy || !dx || !gamma || !mean_rstd || C % 8 || C > 2048) return COMAT_ERR_INVALID;
-  DISPATCH_T(dtype, (ln_kernel<T, 1><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, (T*)dx, gamma, nullptr, const_cast<float*>(mean_rstd), rows, C, 0.f)));
+  DISPATCH_T(dtype, (launch_k(ln_kernel<T, 1>, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, (T*)dx, gamma, nullptr, const_cast<float*>(mean_rstd), rows, C, 0.f)));
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -458,14 +469,14 @@ extern "C" int comat_layernorm_bwd(const void* x, const void* dy, void* dx, cons
 extern "C" int comat_geglu_fwd(const void* hg, void* out, long long rows, int Ch, int dtype, void* stream) {
   if (!hg || !out || Ch % 8) return COMAT_ERR_INVALID;
   const long long nv = rows * (Ch / 8);
-  DISPATCH_T(dtype, (geglu_kernel<T, 0><<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)hg, nullptr, (T*)out, rows, Ch)));
+  DISPATCH_T(dtype, (launch_k(geglu_kernel<T, 0>, (unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream, (const T*)hg, nullptr, (T*)out, rows, Ch)));
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 extern "C" int comat_geglu_bwd(const void* hg, const void* dy, void* dhg, long long rows, int Ch, int dtype, void* stream) {
   if (!hg || !dy || !dhg || Ch % 8) return COMAT_ERR_INVALID;
   const long long nv = rows * (Ch / 8);
-  DISPATCH_T(dtype, (geglu_kernel<T, 1><<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)hg, (const T*)dy, (T*)dhg, rows, Ch)));
+  DISPATCH_T(dtype, (launch_k(geglu_kernel<T, 1>, (unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream, (const T*)hg, (const T*)dy, (T*)dhg, rows, Ch)));
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -474,7 +485,7 @@ extern "C" int comat_elementwise(const void* x, const void* y, void* out, long l
                                  void* stream) {
   if (!x || !out || numel % 8) return COMAT_ERR_INVALID;
   const long long nv = numel / 8;
-  DISPATCH_T(dtype, (ew_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)y, (T*)out, nv, op, alpha, beta)));
+  DISPATCH_T(dtype, (launch_k(ew_kernel<T>, (unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream, (const T*)x, (const T*)y, (T*)out, nv, op, alpha, beta)));
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -483,14 +494,14 @@ extern "C" int comat_spatial(const void* in, void* out, int n, int H, int W, int
   if (!in || !out || C % 8 || mode < 0 || mode > 3) return COMAT_ERR_INVALID;
   if ((mode >= 2) && ((H | W) & 1)) return COMAT_ERR_INVALID;
   const long long total = (long long)n * H * W * (C / 8) * (mode == 0 ? 4 : 1);
-  DISPATCH_T(dtype, (spatial_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, (T*)out, n, H, W, C, mode)));
+  DISPATCH_T(dtype, (launch_k(spatial_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, (const T*)in, (T*)out, n, H, W, C, mode)));
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 
 extern "C" int comat_transpose16(const void* in, void* out, int R, int Cc, int ld_out, void* stream) {
   if (!in || !out || ld_out < R) return COMAT_ERR_INVALID;
-  transpose_kernel<__half><<<dim3((Cc + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, R, Cc, ld_out);
+  launch_k(transpose_kernel<__half>, dim3((Cc + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream, (const __half*)in, (__half*)out, R, Cc, ld_out);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -498,14 +509,14 @@ extern "C" int comat_transpose16(const void* in, void* out, int R, int Cc, int l
 extern "C" int comat_latent_to_nhwc(const float* in, void* out, int n, int Cin, int HW, int Cpad, float scale, int dtype, void* stream) {
   if (!in || !out) return COMAT_ERR_INVALID;
   const long long total = (long long)n * HW * Cpad;
-  DISPATCH_T(dtype, (latent_to_nhwc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (T*)out, n, Cin, HW, Cpad, scale)));
+  DISPATCH_T(dtype, (launch_k(latent_to_nhwc_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, in, (T*)out, n, Cin, HW, Cpad, scale)));
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 extern "C" int comat_nhwc_to_nchw_f32(const void* in, float* out, int n, int Cout, int HW, int ld, float scale, int dtype, void* stream) {
   if (!in || !out) return COMAT_ERR_INVALID;
   const long long total = (long long)n * Cout * HW;
-  DISPATCH_T(dtype, (nhwc_to_nchw_f32_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, out, n, Cout, HW, ld, scale)));
+  DISPATCH_T(dtype, (launch_k(nhwc_to_nchw_f32_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, (const T*)in, out, n, Cout, HW, ld, scale)));
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -513,7 +524,7 @@ extern "C" int comat_nhwc_to_nchw_f32(const void* in, float* out, int n, int Cou
 extern "C" int comat_copy2d16(const void* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst, void* stream) {
   if (!src || !dst || cols % 8 || ld_src % 8 || ld_dst % 8 || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return COMAT_ERR_INVALID;
   const long long nv = rows * (cols / 8);
-  copy2d_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, rows, cols / 8, ld_src / 8, ld_dst / 8);
+  launch_k(copy2d_kernel, (unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream, (const uint4*)src, (uint4*)dst, rows, cols / 8, ld_src / 8, ld_dst / 8);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -524,6 +535,7 @@ extern "C" int comat_copy2d16(const void* src, void* dst, long long rows, int co
 namespace comat {
 template <typename T, int MODE>   // 0: p = softmax(x) ; 1: ds = p * (dp - sum(p*dp))
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const T* __restrict__ x, const T* __restrict__ dp, T* __restrict__ out, int Ccols) {
+  pdl_grid_dependency_sync();
   __shared__ float sm[8];
   const size_t row = blockIdx.x;
   const T* xr = x + row * Ccols;
@@ -595,11 +607,11 @@ extern "C" int comat_softmax_rows(const void* x, const void* dp, void* out, long
   if (!x || !out || cols % 8 || cols > 8192 || (mode == 1 && !dp)) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == COMAT_F16) {
-    if (mode == 0) comat::softmax_rows_kernel<__half, 0><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, nullptr, (__half*)out, cols);
-    else comat::softmax_rows_kernel<__half, 1><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, (const __half*)dp, (__half*)out, cols);
+    if (mode == 0) launch_k(comat::softmax_rows_kernel<__half, 0>, (unsigned)rows, 256, 0, st, (const __half*)x, nullptr, (__half*)out, cols);
+    else launch_k(comat::softmax_rows_kernel<__half, 1>, (unsigned)rows, 256, 0, st, (const __half*)x, (const __half*)dp, (__half*)out, cols);
   } else if (dtype == COMAT_BF16) {
-    if (mode == 0) comat::softmax_rows_kernel<__nv_bfloat16, 0><<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)out, cols);
-    else comat::softmax_rows_kernel<__nv_bfloat16, 1><<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dp, (__nv_bfloat16*)out, cols);
+    if (mode == 0) launch_k(comat::softmax_rows_kernel<__nv_bfloat16, 0>, (unsigned)rows, 256, 0, st, (const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)out, cols);
+    else launch_k(comat::softmax_rows_kernel<__nv_bfloat16, 1>, (unsigned)rows, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dp, (__nv_bfloat16*)out, cols);
   } else return COMAT_ERR_UNSUPPORTED;
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;

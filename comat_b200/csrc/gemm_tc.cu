@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
+  pdl_grid_dependency_sync();
   using S = GemmSmem<BN, STAGES>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                        const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
+  pdl_grid_dependency_sync();
   using S = PersistSmem<BN, STAGES>;
   constexpr int ACC = tmem_cols<BN>();           // TMEM columns per accumulator buffer
   extern __shared__ unsigned char smem_dyn[];
@@ -553,6 +555,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
 
 // split-K second pass: out = act(alpha * sum_s ws[s] + bias + rowvec) + residual  (+ accumulate into out32)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int accumulate) {
+  pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)p.M * p.N;
   if (idx >= total) return;
@@ -584,7 +587,7 @@ static int launch_gemm(const CUtensorMap* maps, const GemmKP& kp, dim3 grid, cud
     COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  launch_k(gemm_tc_kernel<BN, STAGES>, grid, GEMM_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -599,7 +602,7 @@ static int launch_gemm_persist(const CUtensorMap* maps, const GemmKP& kp, int to
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  gemm_tc_persist_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  launch_k(gemm_tc_persist_kernel<BN, STAGES>, grid, GEMM_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -755,7 +758,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   }
   if (rc == COMAT_OK && kp.split_k > 1) {
     const long long total = (long long)kp.M * kp.N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kp, g->accumulate ? 1 : 0);
+    launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, kp, g->accumulate ? 1 : 0);
     COMAT_CHECK_LAUNCH();
   }
   return rc;

@@ -7,6 +7,7 @@
 namespace comat {
 
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  pdl_grid_dependency_sync();
   float s = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n4 = n / 4;
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   }
 }
 __global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  pdl_grid_dependency_sync();
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
   s = warp_sum(s);
@@ -38,6 +40,7 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, 
                                                          float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                          float wd, float bc1, float bc2_sqrt, float max_norm, float grad_scale,
                                                          const float* __restrict__ sumsq) {
+  pdl_grid_dependency_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float coef = grad_scale;
@@ -61,8 +64,8 @@ extern "C" int comat_grad_sumsq(const float* g, long long n, float* partial /* >
   if (!g || !partial || !out || n <= 0) return COMAT_ERR_INVALID;
   int blocks = num_sms() * 4;
   if (blocks > 1024) blocks = 1024;
-  sumsq_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, n, partial);
-  sumsq_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partial, blocks, out);
+  launch_k(sumsq_partial_kernel, blocks, 256, 0, (cudaStream_t)stream, g, n, partial);
+  launch_k(sumsq_final_kernel, 1, 32, 0, (cudaStream_t)stream, partial, blocks, out);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -73,7 +76,7 @@ extern "C" int comat_adamw_clip(float* p, const float* g, float* m, float* v, lo
   if (!p || !g || !m || !v || n <= 0 || step < 1 || (max_norm > 0.f && !sumsq)) return COMAT_ERR_INVALID;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  adamw_clip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+  launch_k(adamw_clip_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                                                   bc1, bc2s, max_norm, grad_scale, sumsq);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
@@ -87,6 +90,7 @@ namespace comat {
 __global__ void __launch_bounds__(256) cfg_ddpm_fwd_kernel(const float* __restrict__ eps2, const float* __restrict__ x,
                                                            const float* __restrict__ z, float* __restrict__ out, long long n,
                                                            float s, float c_eps, float c_x, float sigma, int cfg) {
+  pdl_grid_dependency_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float e = cfg ? (eps2[i] + s * (eps2[n + i] - eps2[i])) : eps2[i];
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(256) cfg_ddpm_fwd_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) cfg_ddpm_bwd_kernel(const float* __restrict__ g, float* __restrict__ d_eps2,
                                                            float* __restrict__ dx, long long n, float s, float c_eps, float c_x, int cfg) {
+  pdl_grid_dependency_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i];
@@ -110,14 +115,14 @@ __global__ void __launch_bounds__(256) cfg_ddpm_bwd_kernel(const float* __restri
 extern "C" int comat_cfg_ddpm_step_fwd(const float* eps, const float* x, const float* noise, float* out, long long n, float guidance,
                                        float c_eps, float c_x, float sigma, int cfg, void* stream) {
   if (!eps || !x || !out || n <= 0) return COMAT_ERR_INVALID;
-  comat::cfg_ddpm_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(eps, x, noise, out, n, guidance, c_eps, c_x, sigma, cfg);
+  launch_k(comat::cfg_ddpm_fwd_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, eps, x, noise, out, n, guidance, c_eps, c_x, sigma, cfg);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 extern "C" int comat_cfg_ddpm_step_bwd(const float* grad_out, float* d_eps, float* dx, long long n, float guidance, float c_eps,
                                        float c_x, int cfg, void* stream) {
   if (!grad_out || n <= 0) return COMAT_ERR_INVALID;
-  comat::cfg_ddpm_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, d_eps, dx, n, guidance, c_eps, c_x, cfg);
+  launch_k(comat::cfg_ddpm_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, grad_out, d_eps, dx, n, guidance, c_eps, c_x, cfg);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }

@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) resample2d_kernel(const float* __restrict
                                                          const int* __restrict__ xs, const int* __restrict__ xc, const float* __restrict__ wx,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          int BC, int C, int IH, int IW, int OH, int OW, int KY, int KX) {
+  pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)BC * OH * OW) return;
   const int ox = (int)(idx % OW), oy = (int)((idx / OW) % OH), bc = (int)(idx / ((long long)OW * OH));
@@ -36,7 +37,7 @@ extern "C" int comat_resample2d(const float* in, float* out, const int* ys, cons
                                 int KY, int KX, void* stream) {
   if (!in || !out || !ys || !yc || !wy || !xs || !xc || !wx || B <= 0 || C <= 0) return COMAT_ERR_INVALID;
   const long long total = (long long)B * C * OH * OW;
-  comat::resample2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, ys, yc, wy, xs, xc, wx, scale, shift,
+  launch_k(comat::resample2d_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, in, out, ys, yc, wy, xs, xc, wx, scale, shift,
                                                                                              B * C, C, IH, IW, OH, OW, KY, KX);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;

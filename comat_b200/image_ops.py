@@ -107,13 +107,24 @@ def _resample(x, ty, tx, OH, OW, scale, shift):
     return out
 
 
+_NORM_CONSTS = {}
+
+
+def _norm_consts(mean, std, dev):
+    """device copies of 1/std and -mean/std, made once (a torch.tensor(..., device=cuda) per call is a stream sync)"""
+    key = (mean, std, str(dev))
+    if key not in _NORM_CONSTS:
+        _NORM_CONSTS[key] = (torch.tensor([1.0 / s for s in std], dtype=torch.float32, device=dev),
+                             torch.tensor([-m / s for m, s in zip(mean, std)], dtype=torch.float32, device=dev))
+    return _NORM_CONSTS[key]
+
+
 class _ResizeNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, images, size, mean, std):
         B, Cc, IH, IW = images.shape
         dev = images.device
-        inv_std = torch.tensor([1.0 / s for s in std], dtype=torch.float32, device=dev)
-        shift = torch.tensor([-m / s for m, s in zip(mean, std)], dtype=torch.float32, device=dev)
+        inv_std, shift = _norm_consts(tuple(mean), tuple(std), dev)
         ctx.meta = (IH, IW, size, inv_std, images.dtype)
         return _resample(images, _tables("f", IH, size, dev), _tables("f", IW, size, dev), size, size, inv_std, shift)
 

@@ -35,7 +35,15 @@ class DDPMScheduler:
         ratio = self.config.num_train_timesteps // num_inference_steps
         ts = (torch.arange(0, num_inference_steps) * ratio).flip(0).to(torch.int64) + self.config.steps_offset
         self._ts_host = ts.tolist()
-        self.timesteps = ts.to(device) if device is not None else ts
+        if device is None:
+            self.timesteps = ts
+        else:
+            # one pageable H2D copy is a stream sync; the schedule only depends on (steps, device), so keep the device copy
+            key = (num_inference_steps, str(device))
+            cache = self.__dict__.setdefault("_ts_dev_cache", {})
+            if key not in cache:
+                cache[key] = ts.to(device)
+            self.timesteps = cache[key]
 
     def scale_model_input(self, sample, timestep=None):
         return sample
