@@ -67,10 +67,10 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
 }
 
 template <int D, typename T>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, (D <= 64) ? 2 : 1)     // d <= 64: two CTAs per SM (smem 112 KB, TMEM 256 columns each)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVt, const AttnKP p) {
-  pdl_grid_dependency_sync();
+  pdl_trigger();
   using Cf = AttnCfg<D>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -103,6 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                    // everything above touched no global memory
 
   if (warp == 0) {
     if (lane == 0) {
@@ -147,7 +148,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t offp = (uint32_t)(ks / 4) * (ATT_BM * 128) + (uint32_t)(ks % 4) * 32;
           const uint32_t offv = (uint32_t)(ks / 4) * (Cf::DN * 128) + (uint32_t)(ks % 4) * 32;
           umma_f16(tmem_base + Cf::O_COL, make_kmajor_sw128_desc(aP + offp), make_kmajor_sw128_desc(aV + offv), p.idesc_pv,
-                   ks > 0 ? 1u : 0u);
+                   (j > 0 || ks > 0) ? 1u : 0u);      // O accumulates in TMEM across key tiles
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[stage]);
@@ -162,87 +163,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
   } else {
     // ---------------- softmax + epilogue: thread = query row ----------------
+    // O accumulates in TMEM across key tiles (the P.V MMAs run with accumulate on); the running row maximum is only
+    // refreshed when some row of the warp grew by more than 2^8 (in the exp2 domain), so the TMEM read-scale-write of O
+    // is rare after the first tiles and exp2 arguments stay <= 8.  The 128 scores of a row are read from TMEM once and
+    // kept in registers for the max and the exponentials.
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const bool row_ok = (m0 + r) < p.Lq;
     float m_run = -INFINITY, l_run = 0.f;
-    float o[Cf::DN];
-#pragma unroll
-    for (int i = 0; i < Cf::DN; ++i) o[i] = 0.f;
-    float m_used = 0.f;
     const int klen = (p.kv_lens != nullptr) ? min(p.Lk, p.kv_lens[b]) : p.Lk;
+    const float sl2 = p.scale_log2;
 
     for (int j = 0; j < NT; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, j & 1);                   // S_j complete; the tensor pipe is in order, so P.V_{j-1} is complete too
       tc_fence_after();
-      const int ktile = min(ATT_BN, klen - j * ATT_BN);                       // warp-uniform loop bound
+      const int ktile = min(ATT_BN, klen - j * ATT_BN);                       // warp-uniform
       const int kvalid = p.causal ? min(ktile, m0 + r - j * ATT_BN + 1) : ktile;   // per-row limit
-      // warp-uniform: every row of this warp sees all 128 keys of the tile -> predicate-free fast path
+      // warp-uniform: every row of this warp sees all 128 keys of the tile -> no masking
       const bool full_w = (ktile == ATT_BN) && (!p.causal || (m0 + q4 * 32 - j * ATT_BN + 1 >= ATT_BN));
-      float mt = -INFINITY;
-      if (full_w) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < ATT_BN; c0 += 64) {      // two TMEM loads in flight per wait
-          uint32_t v[32], w[32];
-          tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
-          tmem_ld_32x32b_x32(trow + (uint32_t)(c0 + 32), w);
-          tmem_ld_wait();
-          float m0_ = fmaxf(__uint_as_float(v[0]), __uint_as_float(w[0])), m1_ = fmaxf(__uint_as_float(v[1]), __uint_as_float(w[1]));
+      float sv[ATT_BN];
 #pragma unroll
-          for (int i = 2; i < 32; i += 2) {
-            m0_ = fmaxf(m0_, fmaxf(__uint_as_float(v[i]), __uint_as_float(w[i])));
-            m1_ = fmaxf(m1_, fmaxf(__uint_as_float(v[i + 1]), __uint_as_float(w[i + 1])));
-          }
-          mt = fmaxf(mt, fmaxf(m0_, m1_));
-        }
-      } else {
-#pragma unroll 1
-        for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-          if (c0 >= ktile) break;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < kvalid) mt = fmaxf(mt, __uint_as_float(v[i]));
-        }
-      }
-      const float m_new = fmaxf(m_run, mt);
-      const float alpha = (m_new == -INFINITY) ? 1.f : fast_exp2((m_run - m_new) * p.scale_log2);   // exp2(-inf) = 0 on the first tile
-      const float mneg = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-      // pass 2: p = exp2(s*sl2 - m*sl2), row sum, 16-bit P into swizzled smem (K-major, two 64-key halves)
-      float lsum = 0.f;
-      const float sl2 = p.scale_log2;
-#pragma unroll 1
       for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
         uint32_t v[32];
-        uint32_t pk[16];
-        if (full_w) {
-          tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
-          tmem_ld_wait();
-          float s0 = 0.f, s1 = 0.f;
+        tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), sl2, -mneg));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sl2, -mneg));
-            s0 += e0; s1 += e1;
-            pk[i / 2] = pack2<T>(e0, e1);
-          }
-          lsum += s0 + s1;
-        } else {
-          if (c0 < ktile) {
-            tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+        for (int i = 0; i < 32; ++i) sv[c0 + i] = __uint_as_float(v[i]);
+      }
+      tmem_ld_wait();
+      if (!full_w) {
+#pragma unroll
+        for (int i = 0; i < ATT_BN; ++i)
+          if (i >= kvalid) sv[i] = -INFINITY;
+      }
+      float mx[4] = {sv[0], sv[1], sv[2], sv[3]};
+#pragma unroll
+      for (int i = 4; i < ATT_BN; i += 4) {
+        mx[0] = fmaxf(mx[0], sv[i]); mx[1] = fmaxf(mx[1], sv[i + 1]); mx[2] = fmaxf(mx[2], sv[i + 2]); mx[3] = fmaxf(mx[3], sv[i + 3]);
+      }
+      const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (j == 0) {
+        m_run = mt;                               // O is not initialised yet: P.V_0 overwrites it
+      } else {
+        const bool grow = (mt - m_run) * sl2 > 8.f;         // false for mt = -inf or NaN-free equal maxima
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = fmaxf(m_run, mt);
+          const float alpha = (m_new == -INFINITY) ? 1.f : fast_exp2((m_run - m_new) * sl2);
+          l_run *= alpha;
+          m_run = m_new;
+#pragma unroll
+          for (int c0 = 0; c0 < Cf::DN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(trow + (uint32_t)(Cf::O_COL + c0), v);
             tmem_ld_wait();
-          }
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float e0 = 0.f, e1 = 0.f;
-            if (c0 + i < kvalid) e0 = fast_exp2(__uint_as_float(v[i]) * sl2 - mneg);
-            if (c0 + i + 1 < kvalid) e1 = fast_exp2(__uint_as_float(v[i + 1]) * sl2 - mneg);
-            lsum += e0 + e1;
-            pk[i / 2] = pack2<T>(e0, e1);
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x16(trow + (uint32_t)(Cf::O_COL + c0), v);
           }
+          tmem_st_wait();
+        }
+      }
+      const float mneg = (m_run == -INFINITY) ? 0.f : m_run * sl2;
+      // p = exp2(s*sl2 - m*sl2), row sum, 16-bit P into swizzled smem (K-major, two 64-key halves)
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float e0 = fast_exp2(fmaf(sv[c0 + i], sl2, -mneg));
+          const float e1 = fast_exp2(fmaf(sv[c0 + i + 1], sl2, -mneg));
+          ls[(i / 2) & 3] += e0 + e1;
+          pk[i / 2] = pack2<T>(e0, e1);
         }
         // 32 keys = 4 x 16-byte chunks of row r in half (c0/64): chunk index cc = (c0%64)/8 + q
         unsigned char* base = sP + (c0 / 64) * (ATT_BM * 128) + (r / 8) * 1024 + (r % 8) * 128;
@@ -252,40 +244,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           *reinterpret_cast<uint4*>(base + ((cc ^ (r % 8)) * 16)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         }
       }
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      m_used = m_new;
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tc_fence_before();
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       mbar_arrive(p_full);
-      // accumulate O
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
+    }
+    const float m_used = m_run;
+    // epilogue: O / l from TMEM
+    mbar_wait(o_full, (NT - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    {
+      T* op = reinterpret_cast<T*>(p.out) + ((size_t)b * p.Lq + m0 + r) * p.out_ld + (size_t)h * p.d;
 #pragma unroll
       for (int c0 = 0; c0 < Cf::DN; c0 += 16) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(trow + (uint32_t)(Cf::O_COL + c0), v);
         tmem_ld_wait();
+        if (row_ok) {
+          if constexpr (D % 8 == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[c0 + i] = o[c0 + i] * alpha + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-    }
-    const float inv_l = 1.f / l_run;
-    if (row_ok) {
-      T* op = reinterpret_cast<T*>(p.out) + ((size_t)b * p.Lq + m0 + r) * p.out_ld + (size_t)h * p.d;
-      if constexpr (D % 8 == 0) {
+            for (int i = 0; i < 16; i += 8) {
+              if (c0 + i < D) {
+                uint4 u;
+                u.x = pack2<T>(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+                u.y = pack2<T>(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l);
+                u.z = pack2<T>(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l);
+                u.w = pack2<T>(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l);
+                *reinterpret_cast<uint4*>(op + c0 + i) = u;
+              }
+            }
+          } else {
 #pragma unroll
-        for (int i = 0; i < D; i += 8) {
-          uint4 u;
-          u.x = pack2<T>(o[i] * inv_l, o[i + 1] * inv_l); u.y = pack2<T>(o[i + 2] * inv_l, o[i + 3] * inv_l);
-          u.z = pack2<T>(o[i + 4] * inv_l, o[i + 5] * inv_l); u.w = pack2<T>(o[i + 6] * inv_l, o[i + 7] * inv_l);
-          *reinterpret_cast<uint4*>(op + i) = u;
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < D) op[c0 + i] = from_f32<T>(__uint_as_float(v[i]) * inv_l);
+          }
         }
-      } else {
-        for (int i = 0; i < D; ++i) op[i] = from_f32<T>(o[i] * inv_l);
       }
-      if (p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.Lq + m0 + r] = m_used * p.scale + logf(l_run);
+      if (row_ok && p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.Lq + m0 + r] = m_used * p.scale + logf(l_run);
     }
     if (p.probs != nullptr) {
       // single-tile case: S is still in TMEM; write softmax(S) as fp32 (n*H, Lq, Lk).  tcgen05.ld is .sync.aligned: the whole

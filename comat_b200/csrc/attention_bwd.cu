@@ -80,7 +80,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
                 const __grid_constant__ CUtensorMap tmT1,   // streamed transposed: MODE0 K^T | MODE1 dO^T  (box {64, DN})
                 const __grid_constant__ CUtensorMap tmT2,   //                      MODE1 Q^T
                 const AttnBwdKP p) {
-  pdl_grid_dependency_sync();
+  pdl_trigger();
   using Cf = ABCfg<D, MODE>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -115,6 +115,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                    // everything above touched no global memory
 
   if (warp == 0) {
     // ===================== TMA producer =====================

@@ -43,6 +43,10 @@ __device__ __forceinline__ void pdl_grid_dependency_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// split form for kernels with a global-memory-free prologue (barrier init, TMEM allocation): trigger first, set up, wait.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 inline bool comat_pdl_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("COMAT_PDL"); on = (e && e[0] == '0') ? 0 : 1; }

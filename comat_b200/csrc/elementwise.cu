@@ -30,7 +30,9 @@ __device__ __forceinline__ float gelu_grad(float x) {
 //   bwd    pass: a = dy*gamma*act'(.), b = a * xhat
 // Pass 2 (apply) consumes the chunk-reduced sums.  Two passes => x is read twice (algorithmic minimum for a
 // normalisation whose statistics span the whole image) and written once.
-constexpr int GN_THREADS = 256;
+// Both kernels use the same thread layout: a block covers rows_par rows x (C/8) 16-byte column vectors, each thread
+// keeps its 8 channels' constants in registers and walks rows with four independent 16-byte loads in flight.
+constexpr int GN_UNROLL = 4;
 
 template <typename T, int MODE>   // MODE 0: stats of x ; MODE 1: backward sums
 __global__ void __launch_bounds__(512) gn_partial_kernel(const T* __restrict__ x, const T* __restrict__ dy,
@@ -55,24 +57,37 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(const T* __restrict__ x
       for (int i = 0; i < 8; ++i) {
         const int c = v * 8 + i, gidx = c / cpg;
         g8[i] = gamma[c]; b8[i] = beta[c];
-        mu[i] = mean_rstd[((size_t)n * G + gidx) * 2]; rs[i] = mean_rstd[((size_t)n * G + gidx) * 2 + 1];
+        rs[i] = mean_rstd[((size_t)n * G + gidx) * 2 + 1]; mu[i] = -mean_rstd[((size_t)n * G + gidx) * 2] * rs[i];   // xh = x*rs + mu
       }
     }
-    for (int p = p_begin + pr; p < p_end; p += rows_par) {
-      const size_t off = ((size_t)n * HW + p) * C + v * 8;
-      Vec8<T> xv; xv.load(x + off);
-      if (MODE == 0) {
+    const T* xb = x + (size_t)n * HW * C + v * 8;
+    const T* db = (MODE == 1) ? dy + (size_t)n * HW * C + v * 8 : nullptr;
+    for (int p = p_begin + pr; p < p_end; p += GN_UNROLL * rows_par) {
+      Vec8<T> xv[GN_UNROLL], dv[GN_UNROLL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float f = xv.get(i); sa[i] += f; sb[i] += f * f; }
-      } else {
-        Vec8<T> dv; dv.load(dy + off);
+      for (int k = 0; k < GN_UNROLL; ++k) {
+        const int pk = p + k * rows_par;
+        if (pk < p_end) {
+          xv[k].load(xb + (size_t)pk * C);
+          if (MODE == 1) dv[k].load(db + (size_t)pk * C);
+        }
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (xv.get(i) - mu[i]) * rs[i];
-          float d = dv.get(i);
-          if (silu) d *= silu_grad(xh * g8[i] + b8[i]);
-          const float a = d * g8[i];
-          sa[i] += a; sb[i] += a * xh;
+      for (int k = 0; k < GN_UNROLL; ++k) {
+        if (p + k * rows_par < p_end) {
+          if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float f = xv[k].get(i); sa[i] += f; sb[i] = fmaf(f, f, sb[i]); }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xh = fmaf(xv[k].get(i), rs[i], mu[i]);
+              float d = dv[k].get(i);
+              if (silu) d *= silu_grad(fmaf(xh, g8[i], b8[i]));
+              const float a = d * g8[i];
+              sa[i] += a; sb[i] = fmaf(a, xh, sb[i]);
+            }
+          }
         }
       }
     }
@@ -92,63 +107,89 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(const T* __restrict__ x
   }
 }
 
-// reduce chunk partials -> (mean, rstd) [MODE 0] or (sum_a, sum_b) [MODE 1]
-__global__ void gn_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nG, int G, int chunks, float inv_cnt,
-                                 float eps, int mode) {
-  pdl_grid_dependency_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nG) return;
-  const int n = i / G, g = i % G;
-  float a = 0.f, b = 0.f;
-  for (int c = 0; c < chunks; ++c) {
-    const float* p = part + (((size_t)n * chunks + c) * G + g) * 2;
-    a += p[0]; b += p[1];
-  }
-  if (mode == 0) {
-    const float mean = a * inv_cnt;
-    const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
-    out[i * 2] = mean; out[i * 2 + 1] = rsqrtf(var + eps);
-  } else {
-    out[i * 2] = a * inv_cnt; out[i * 2 + 1] = b * inv_cnt;
-  }
-}
-
+// Pass 2.  Every block first reduces the chunk partials of its image (fixed order, so the result does not depend on the
+// grid) into per-group (mean, rstd) [MODE 0; block 0 of each image also saves them for the backward] or the backward's
+// (mean(a), mean(a*xhat)) [MODE 1]; then y = x*A + B with A = rstd*gamma, B = beta - mean*A  (or dx) streams through.
 template <typename T, int MODE>   // MODE 0: y = [silu](xhat*gamma+beta) ; MODE 1: dx
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
+__global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ mean_rstd, const float* __restrict__ sums,
-                                                       long long total_vec, int HW, int C, int G, int silu) {
+                                                       const float* __restrict__ part, float* __restrict__ mean_rstd,
+                                                       int HW, int C, int G, int chunks, int achunks, float inv_cnt, float eps, int silu) {
   pdl_grid_dependency_sync();
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total_vec) return;
+  extern __shared__ float sm[];   // [2*G]
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+      const float* pp = part + (((size_t)n * chunks + c) * G + g) * 2;
+      a += pp[0]; b += pp[1];
+    }
+    if (MODE == 0) {
+      const float mean = a * inv_cnt;
+      const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      sm[g] = mean; sm[G + g] = rstd;
+      if (chunk == 0) { mean_rstd[((size_t)n * G + g) * 2] = mean; mean_rstd[((size_t)n * G + g) * 2 + 1] = rstd; }
+    } else {
+      sm[g] = a * inv_cnt; sm[G + g] = b * inv_cnt;
+    }
+  }
+  __syncthreads();
   const int vcols = C / 8;
-  const int v = (int)(idx % vcols);
-  const long long row = idx / vcols;
-  const int n = (int)(row / HW);
+  const int rows_par = blockDim.x / vcols;
+  const int v = threadIdx.x % vcols, pr = threadIdx.x / vcols;
+  if (pr >= rows_par) return;
   const int cpg = C / G;
-  const size_t off = (size_t)row * C + v * 8;
-  Vec8<T> xv; xv.load(x + off);
-  Vec8<T> dv;
-  if (MODE == 1) dv.load(dy + off);
-  Vec8<T> o;
+  const int p_begin = (int)((long long)HW * chunk / achunks), p_end = (int)((long long)HW * (chunk + 1) / achunks);
+  float A[8], B[8], g8[8], b8[8], m1[8], m2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = v * 8 + i, g = c / cpg;
-    const float mu = mean_rstd[((size_t)n * G + g) * 2], rs = mean_rstd[((size_t)n * G + g) * 2 + 1];
-    const float xh = (xv.get(i) - mu) * rs;
     if (MODE == 0) {
-      float y = xh * gamma[c] + beta[c];
-      if (silu) y = silu_f(y);
-      o.set(i, y);
+      A[i] = sm[G + g] * gamma[c];
+      B[i] = fmaf(-sm[g], A[i], beta[c]);
     } else {
-      float d = dv.get(i);
-      if (silu) d *= silu_grad(xh * gamma[c] + beta[c]);
-      const float a = d * gamma[c];
-      const float m1 = sums[((size_t)n * G + g) * 2], m2 = sums[((size_t)n * G + g) * 2 + 1];
-      o.set(i, rs * (a - m1 - xh * m2));
+      const float rs = mean_rstd[((size_t)n * G + g) * 2 + 1];
+      A[i] = rs; B[i] = -mean_rstd[((size_t)n * G + g) * 2] * rs;      // xh = x*A + B
+      g8[i] = gamma[c]; b8[i] = beta[c]; m1[i] = sm[g]; m2[i] = sm[G + g];
     }
   }
-  o.store(out + off);
+  const T* xb = x + (size_t)n * HW * C + v * 8;
+  const T* db = (MODE == 1) ? dy + (size_t)n * HW * C + v * 8 : nullptr;
+  T* ob = out + (size_t)n * HW * C + v * 8;
+  for (int p = p_begin + pr; p < p_end; p += GN_UNROLL * rows_par) {
+    Vec8<T> xv[GN_UNROLL], dv[GN_UNROLL];
+#pragma unroll
+    for (int k = 0; k < GN_UNROLL; ++k) {
+      const int pk = p + k * rows_par;
+      if (pk < p_end) {
+        xv[k].load(xb + (size_t)pk * C);
+        if (MODE == 1) dv[k].load(db + (size_t)pk * C);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < GN_UNROLL; ++k) {
+      const int pk = p + k * rows_par;
+      if (pk < p_end) {
+        Vec8<T> o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (MODE == 0) {
+            float y = fmaf(xv[k].get(i), A[i], B[i]);
+            if (silu) y = silu_f(y);
+            o.set(i, y);
+          } else {
+            const float xh = fmaf(xv[k].get(i), A[i], B[i]);
+            float d = dv[k].get(i);
+            if (silu) d *= silu_grad(fmaf(xh, g8[i], b8[i]));
+            const float a = d * g8[i];
+            o.set(i, A[i] * (a - m1[i] - xh * m2[i]));
+          }
+        }
+        o.store(ob + (size_t)pk * C);
+      }
+    }
+  }
 }
 
 // ============================================================================================== LayerNorm (one warp per row)
@@ -417,6 +458,13 @@ static inline int gn_chunks(int n, int HW) {
   if (c > HW / 16) c = HW / 16;
   return c < 1 ? 1 : c;
 }
+// row blocks of the apply pass: ~8 blocks per SM so enough 16-byte loads are in flight to cover HBM latency
+static inline int gn_apply_chunks(int n, int HW, int rows_par) {
+  int c = (8 * num_sms() + n - 1) / n;
+  const int cap = HW / (rows_par * GN_UNROLL) > 0 ? HW / (rows_par * GN_UNROLL) : 1;
+  if (c > cap) c = cap;
+  return c < 1 ? 1 : c;
+}
 
 extern "C" size_t comat_groupnorm_workspace_floats(int n, int HW, int G) { return (size_t)n * gn_chunks(n, HW) * G * 2 + (size_t)n * G * 2; }
 
@@ -425,11 +473,11 @@ extern "C" int comat_groupnorm_fwd(const void* x, void* y, const float* gamma, c
   if (!x || !y || !gamma || !beta || !mean_rstd || !ws || C % 8 || C % G || C / 8 > 512) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = gn_chunks(n, HW);
-  const long long nvec = (long long)n * HW * (C / 8);
+  const int thr = gn_threads(C), achunks = gn_apply_chunks(n, HW, thr / (C / 8));
+  const float inv_cnt = 1.f / ((float)HW * (C / G));
   DISPATCH_T(dtype, {
-    launch_k(gn_partial_kernel<T, 0>, dim3(chunks, n), gn_threads(C), 2 * C * sizeof(float), st, (const T*)x, nullptr, gamma, beta, nullptr, ws, HW, C, G, chunks, 0);
-    launch_k(gn_reduce_kernel, (n * G + 127) / 128, 128, 0, st, ws, mean_rstd, n * G, G, chunks, 1.f / ((float)HW * (C / G)), eps, 0);
-    launch_k(gn_apply_kernel<T, 0>, (unsigned)((nvec + 255) / 256), 256, 0, st, (const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, nullptr, nvec, HW, C, G, silu);
+    launch_k(gn_partial_kernel<T, 0>, dim3(chunks, n), thr, 2 * C * sizeof(float), st, (const T*)x, nullptr, gamma, beta, nullptr, ws, HW, C, G, chunks, 0);
+    launch_k(gn_apply_kernel<T, 0>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, nullptr, (T*)y, gamma, beta, ws, mean_rstd, HW, C, G, chunks, achunks, inv_cnt, eps, silu);
   });
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
@@ -440,12 +488,11 @@ extern "C" int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, cons
   if (!x || !dy || !dx || !gamma || !beta || !mean_rstd || !ws || C % 8 || C % G || C / 8 > 512) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = gn_chunks(n, HW);
-  float* sums = ws + (size_t)n * chunks * G * 2;
-  const long long nvec = (long long)n * HW * (C / 8);
+  const int thr = gn_threads(C), achunks = gn_apply_chunks(n, HW, thr / (C / 8));
+  const float inv_cnt = 1.f / ((float)HW * (C / G));
   DISPATCH_T(dtype, {
-    launch_k(gn_partial_kernel<T, 1>, dim3(chunks, n), gn_threads(C), 2 * C * sizeof(float), st, (const T*)x, (const T*)dy, gamma, beta, mean_rstd, ws, HW, C, G, chunks, silu);
-    launch_k(gn_reduce_kernel, (n * G + 127) / 128, 128, 0, st, ws, sums, n * G, G, chunks, 1.f / ((float)HW * (C / G)), 0.f, 1);
-    launch_k(gn_apply_kernel<T, 1>, (unsigned)((nvec + 255) / 256), 256, 0, st, (const T*)x, (const T*)dy, (T*)dx, gamma, beta, mean_rstd, sums, nvec, HW, C, G, silu);
+    launch_k(gn_partial_kernel<T, 1>, dim3(chunks, n), thr, 2 * C * sizeof(float), st, (const T*)x, (const T*)dy, gamma, beta, mean_rstd, ws, HW, C, G, chunks, silu);
+    launch_k(gn_apply_kernel<T, 1>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, (const T*)dy, (T*)dx, gamma, beta, ws, const_cast<float*>(mean_rstd), HW, C, G, chunks, achunks, inv_cnt, 0.f, silu);
   });
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
-  pdl_grid_dependency_sync();
+  pdl_trigger();
   using S = GemmSmem<BN, STAGES>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -247,6 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tmem_alloc(tmem_ptr, tmem_cols<BN>());
     tmem_relinquish();
   }
+  pdl_wait();                                    // everything above touched no global memory
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < BN; i += GEMM_THREADS - 64)
       s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                        const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
-  pdl_grid_dependency_sync();
+  pdl_trigger();
   using S = PersistSmem<BN, STAGES>;
   constexpr int ACC = tmem_cols<BN>();           // TMEM columns per accumulator buffer
   extern __shared__ unsigned char smem_dyn[];
@@ -432,6 +433,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                    // everything above touched no global memory
 
   if (warp == 0) {
     // ===================== TMA producer: streams k-blocks of tile after tile =====================

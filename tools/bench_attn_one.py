@@ -18,3 +18,8 @@ for _ in range(5):
 e1.record(); torch.cuda.synchronize()
 fl = 4.0 * n * H * L * L * d
 print("attn fwd ms", e0.elapsed_time(e1) / 5, "TFLOP/s", fl / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e12)
+e0.record()
+for _ in range(5):
+    A.attention_bwd_native(q, k, v, o, lse, None, H, do, None)
+e1.record(); torch.cuda.synchronize()
+print("attn bwd ms", e0.elapsed_time(e1) / 5, "TFLOP/s", 2.5 * fl / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e12)
