@@ -6,8 +6,9 @@
 //   * the log-sum-exp per row saved for the backward pass.
 // Replaces F.scaled_dot_product_attention / baddbmm+softmax+bmm of diffusers' Attention and HF BLIP's eager attention.
 //
-// Layout: q (n, Lq, H*d), k (n, Lk, H*d) 16-bit token-major (the projection GEMMs' natural output); V is consumed as
-// V^T (n*H, d, Lk_pad) K-major (tiny pre-pass `kv_transpose`), so every MMA operand is a K-major 128B-swizzled tile.
+// Layout: q, k, v (n, L, H*d) 16-bit token-major (the projection GEMMs' natural output), read as they lie: a [128 keys][d]
+// tile of V lands in smem as 128-byte-swizzled rows, which is the canonical MN-major B operand of the P.V product
+// (reduction over the 128 key rows) - no V^T copy exists.
 // Head dims that are not multiples of 64 (40, 80, 160) are handled by a 3-D tensor map {d, H, rows}: the TMA box is 64
 // wide and elements past d are out-of-bounds -> zero-filled, so no padded copies of Q/K exist.
 //
@@ -43,12 +44,12 @@ struct AttnCfg {
   static constexpr int KSTEPS_QK = (D + 15) / 16;           // 16-wide k-steps actually issued
   static constexpr int Q_BYTES = NKC * ATT_BM * 128;
   static constexpr int K_BYTES = NKC * ATT_BN * 128;
-  static constexpr int VT_BYTES = 2 * DN * 128;             // two 64-key halves, DN rows of 128 B
-  static constexpr int KV_STAGE = K_BYTES + ((VT_BYTES + 1023) / 1024) * 1024;
+  static constexpr int V_BYTES = K_BYTES;                   // same [128 keys][NKC x 64] tile shape as K
+  static constexpr int KV_STAGE = K_BYTES + V_BYTES;
   static constexpr int P_BYTES = 2 * ATT_BM * 128;          // two 64-key halves
   static constexpr int STAGES = (D > 128) ? 1 : 2;
   static constexpr int BAR_OFF = Q_BYTES + STAGES * KV_STAGE + P_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 128;               // dynamic smem is declared 1024-B aligned (checked in-kernel)
   static constexpr int TMEM_COLS = (128 + DN) <= 256 ? 256 : 512;
   static constexpr int O_COL = 128;                         // S at columns [0,128), O tile at [128, 128+DN)
 };
@@ -69,11 +70,12 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
 template <int D, typename T>
 __global__ void __launch_bounds__(ATT_THREADS, (D <= 64) ? 2 : 1)     // d <= 64: two CTAs per SM (smem 112 KB, TMEM 256 columns each)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmVt, const AttnKP p) {
+                const __grid_constant__ CUtensorMap tmV, const AttnKP p) {
   pdl_trigger();
   using Cf = AttnCfg<D>;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzled tiles need 1024-B alignment; d <= 64 leaves no slack (2 CTAs / SM)
   unsigned char* sQ = smem;
   unsigned char* sKV = smem + Cf::Q_BYTES;
   unsigned char* sP = sKV + Cf::STAGES * Cf::KV_STAGE;
@@ -92,7 +94,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int NT = p.n_kv_tiles;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < Cf::STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
@@ -114,10 +116,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&kv_empty[stage], phase ^ 1);
         unsigned char* sK = sKV + stage * Cf::KV_STAGE;
         unsigned char* sV = sK + Cf::K_BYTES;
-        mbar_expect_tx(&kv_full[stage], Cf::K_BYTES + Cf::VT_BYTES);
-        for (int c = 0; c < Cf::NKC; ++c) tma_load_3d(sK + c * ATT_BN * 128, &tmK, &kv_full[stage], c * 64, h, b * p.Lk + j * ATT_BN);
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_2d(sV + hf * Cf::DN * 128, &tmVt, &kv_full[stage], j * ATT_BN + hf * 64, (b * p.H + h) * p.d);
+        mbar_expect_tx(&kv_full[stage], Cf::K_BYTES + Cf::V_BYTES);
+        for (int c = 0; c < Cf::NKC; ++c) {
+          tma_load_3d(sK + c * ATT_BN * 128, &tmK, &kv_full[stage], c * 64, h, b * p.Lk + j * ATT_BN);
+          tma_load_3d(sV + c * ATT_BN * 128, &tmV, &kv_full[stage], c * 64, h, b * p.Lk + j * ATT_BN);
+        }
         if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -146,8 +149,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int ks = 0; ks < ATT_BN / 16; ++ks) {
           const uint32_t offp = (uint32_t)(ks / 4) * (ATT_BM * 128) + (uint32_t)(ks % 4) * 32;
-          const uint32_t offv = (uint32_t)(ks / 4) * (Cf::DN * 128) + (uint32_t)(ks % 4) * 32;
-          umma_f16(tmem_base + Cf::O_COL, make_kmajor_sw128_desc(aP + offp), make_kmajor_sw128_desc(aV + offv), p.idesc_pv,
+          // V tile read MN-major: 16 key rows = 2048 B per k-step, d-panels ATT_BN*128 B apart
+          umma_f16(tmem_base + Cf::O_COL, make_kmajor_sw128_desc(aP + offp),
+                   make_mnmajor_sw128_desc(aV + (uint32_t)ks * 2048, ATT_BN * 128), p.idesc_pv,
                    (j > 0 || ks > 0) ? 1u : 0u);      // O accumulates in TMEM across key tiles
         }
         umma_commit(o_full);
@@ -306,24 +310,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cf::TMEM_COLS); }
 }
 
-// V (n, Lk, H*d) -> V^T (n*H, d, Lpad) with zero padding of keys >= Lk  (K-major B operand of P.V)
-template <typename T>
-__global__ void kv_transpose_kernel(const T* __restrict__ v, T* __restrict__ vt, int Lk, int H, int d, int Lpad) {
-  pdl_grid_dependency_sync();
-  __shared__ T tile[32][33];
-  const int bh = blockIdx.z, b = bh / H, h = bh % H;
-  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int key = k0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (key < Lk && c < d) ? v[((size_t)b * Lk + key) * (H * d) + h * d + c] : from_f32<T>(0.f);
-  }
-  __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int c = c0 + j, key = k0 + threadIdx.x;
-    if (c < d && key < Lpad) vt[((size_t)bh * d + c) * Lpad + key] = tile[threadIdx.x][j];
-  }
-}
-
 template <int D, typename T>
 static int launch_attn(const CUtensorMap* maps, const AttnKP& kp, dim3 grid, cudaStream_t st) {
   using Cf = AttnCfg<D>;
@@ -341,8 +327,8 @@ static int launch_attn(const CUtensorMap* maps, const AttnKP& kp, dim3 grid, cud
 using namespace comat;
 
 extern "C" size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d) {
-  const int Lpad = (Lk + 127) / 128 * 128;
-  return (size_t)n * H * d * Lpad * 2 + 256;
+  (void)n; (void)Lk; (void)H; (void)d;
+  return 256;      // no scratch is needed any more (V is read in place); kept for ABI stability
 }
 
 extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
@@ -354,12 +340,6 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
   if (probs && Lk > ATT_BN) return COMAT_ERR_UNSUPPORTED;
   if (((H * d) % 8) != 0 || (d % 8) != 0) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  const int Lpad = (Lk + 127) / 128 * 128;
-  void* vt = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-  {
-    dim3 g((Lpad + 31) / 32, (d + 31) / 32, n * H), blk(32, 8);
-    launch_k(kv_transpose_kernel<__half>, g, blk, 0, st, (const __half*)v, (__half*)vt, Lk, H, d, Lpad);
-  }
   AttnKP kp;
   memset(&kp, 0, sizeof(kp));
   kp.Lq = Lq; kp.Lk = Lk; kp.H = H; kp.d = d; kp.n_kv_tiles = (Lk + ATT_BN - 1) / ATT_BN;
@@ -369,7 +349,7 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
   const int fmt = kp.is_bf16 ? 1 : 0;
   const int DN = (d + 15) / 16 * 16;
   kp.idesc_qk = make_idesc_f16(ATT_BM, ATT_BN, fmt);
-  kp.idesc_pv = make_idesc_f16(ATT_BM, DN, fmt);
+  kp.idesc_pv = make_idesc_f16(ATT_BM, DN, fmt, 0, 1);        // B (= V) MN-major
   CUtensorMap maps[3];
   {
     const uint64_t dq[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * Lq};
@@ -379,10 +359,7 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
     const uint64_t dk[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * Lk};
     const uint32_t bk[3] = {64, 1, (uint32_t)ATT_BN};
     if (!make_tmap_16bit(&maps[1], k, 3, dk, sq, bk)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
-    const uint64_t dv[2] = {(uint64_t)Lpad, (uint64_t)n * H * d};
-    const uint64_t sv[1] = {(uint64_t)Lpad * 2};
-    const uint32_t bv[2] = {64, (uint32_t)DN};
-    if (!make_tmap_16bit(&maps[2], vt, 2, dv, sv, bv)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    if (!make_tmap_16bit(&maps[2], v, 3, dk, sq, bk)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   }
   dim3 grid((Lq + ATT_BM - 1) / ATT_BM, H, n);
 #define ATT_CASE(DD)                                                                      \

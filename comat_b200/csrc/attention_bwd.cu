@@ -10,8 +10,11 @@
 //   MODE 0 (dQ)    : CTA = 128 queries, loops over key tiles   : S = Q K^T, dP = dO V^T  -> dS (smem) -> dQ += dS K
 //   MODE 1 (dK,dV) : CTA = 128 keys,    loops over query tiles : S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (smem)
 //                                                                 -> dV += P^T dO,  dK += dS^T Q
-// Every MMA operand is a K-major, 128B-swizzled tile: the "transposed" B operands (K^T, Q^T, dO^T per head) come from a
-// small pre-pass, S / dP and the dQ / dK / dV accumulators live in TMEM (<= 448 of 512 columns), the elementwise softmax
+// No transposed copies exist anywhere: a streamed [64 rows][d] tile lands in smem as 128-byte-swizzled rows, which is at once
+// the canonical K-major operand for the S / dP products (reduction over d) and the canonical MN-major operand for the
+// accumulating products (reduction over the 64 rows) - the second use only flips the major bit of the instruction descriptor.
+// S / dP (64 columns each) and the dQ / dK / dV accumulators live in TMEM; for d <= 64 that is <= 256 columns and <= 113 KB of
+// smem, so two CTAs share an SM and one CTA's softmax-backward arithmetic overlaps the other's MMAs.  The elementwise softmax
 // backward is done by 128 row-owning threads.
 #include "tc_common.cuh"
 
@@ -41,22 +44,22 @@ struct ABCfg {
   static constexpr int NKC = (D + 63) / 64;
   static constexpr int DN = (D + 15) / 16 * 16;
   static constexpr int KSTEPS = (D + 15) / 16;
-  static constexpr int BY = (D <= 64) ? 128 : 64;                  // inner tile width
-  static constexpr int NHALF = BY / 64;
-  static constexpr int NT = (MODE == 0) ? 1 : 2;                   // transposed streamed tiles
-  static constexpr int NP = (MODE == 0) ? 1 : 2;                   // smem A tiles produced by the row threads
+  static constexpr int BY = 64;                                    // inner tile width (keys in MODE 0, queries in MODE 1)
+  static constexpr int NP = (MODE == 0) ? 1 : 2;                   // accumulators = smem A tiles produced by the row threads
   static constexpr int RES_BYTES = 2 * NKC * AB_ROWS * 128;
-  static constexpr int NAT_BYTES = NKC * BY * 128;                 // one natural streamed tile
-  static constexpr int TR_BYTES = NHALF * DN * 128;                // one transposed streamed tile
+  static constexpr int NAT_BYTES = NKC * BY * 128;                 // one streamed tile: NKC panels of [BY rows][128 B]
   static constexpr int VEC_BYTES = (MODE == 1) ? 2 * BY * 4 : 0;   // lse / D slices of the inner tile
-  static constexpr int STAGE_BYTES = ((2 * NAT_BYTES + NT * TR_BYTES + VEC_BYTES + 1023) / 1024) * 1024;
-  static constexpr int PD_BYTES = NP * NHALF * AB_ROWS * 128;
+  static constexpr int STAGE_BYTES = ((2 * NAT_BYTES + VEC_BYTES + 1023) / 1024) * 1024;
+  static constexpr int PD_BYTES = NP * AB_ROWS * 128;
   static constexpr int FIXED = RES_BYTES + PD_BYTES + 256 + 1024;
-  static constexpr int STAGES = (FIXED + 2 * STAGE_BYTES <= 225 * 1024) ? 2 : 1;
+  static constexpr int COL_S = 0, COL_DP = BY, COL_ACC0 = 2 * BY, COL_ACC1 = 2 * BY + DN;
+  static constexpr int TMEM_COLS = (2 * BY + NP * DN <= 256) ? 256 : 512;
+  // two CTAs per SM need 2 x (TOTAL + 1 KB reserved) <= 228 KB and 2 x 256 TMEM columns
+  static constexpr int OCC = (TMEM_COLS == 256 && FIXED + STAGE_BYTES <= 113 * 1024) ? 2 : 1;
+  static constexpr int BUDGET = (OCC == 2) ? 113 * 1024 : 225 * 1024;
+  static constexpr int STAGES = (FIXED + 2 * STAGE_BYTES <= BUDGET) ? 2 : 1;
   static constexpr int BAR_OFF = RES_BYTES + STAGES * STAGE_BYTES + PD_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-  static constexpr int COL_S = 0, COL_DP = BY, COL_ACC0 = 2 * BY, COL_ACC1 = 2 * BY + DN;
-  static constexpr int TMEM_COLS = 512;
 };
 
 template <typename T>
@@ -72,13 +75,11 @@ __device__ __forceinline__ unsigned char* sw128_chunk(unsigned char* half_base, 
 }
 
 template <int D, int MODE, typename T>
-__global__ void __launch_bounds__(AB_THREADS)
+__global__ void __launch_bounds__(AB_THREADS, ABCfg<D, MODE>::OCC)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 1: MODE0 Q   | MODE1 K      (box 128 rows)
                 const __grid_constant__ CUtensorMap tmA2,   // resident natural 2: MODE0 dO  | MODE1 V
                 const __grid_constant__ CUtensorMap tmB1,   // streamed natural 1: MODE0 K   | MODE1 Q      (box BY rows)
                 const __grid_constant__ CUtensorMap tmB2,   // streamed natural 2: MODE0 V   | MODE1 dO
-                const __grid_constant__ CUtensorMap tmT1,   // streamed transposed: MODE0 K^T | MODE1 dO^T  (box {64, DN})
-                const __grid_constant__ CUtensorMap tmT2,   //                      MODE1 Q^T
                 const AttnBwdKP p) {
   pdl_trigger();
   using Cf = ABCfg<D, MODE>;
@@ -129,19 +130,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       for (int it = 0; it < NI; ++it) {
         mbar_wait(&st_empty[stage], phase ^ 1);
         unsigned char* st = sStage + stage * Cf::STAGE_BYTES;
-        mbar_expect_tx(&st_full[stage], 2 * Cf::NAT_BYTES + Cf::NT * Cf::TR_BYTES + Cf::VEC_BYTES);
+        mbar_expect_tx(&st_full[stage], 2 * Cf::NAT_BYTES + Cf::VEC_BYTES);
         const int y0 = it * Cf::BY;
         for (int c = 0; c < Cf::NKC; ++c) {
           tma_load_3d(st + c * Cf::BY * 128, &tmB1, &st_full[stage], c * 64, h, b * Ly + y0);
           tma_load_3d(st + Cf::NAT_BYTES + c * Cf::BY * 128, &tmB2, &st_full[stage], c * 64, h, b * Ly + y0);
         }
-        unsigned char* tr = st + 2 * Cf::NAT_BYTES;
-        for (int hf = 0; hf < Cf::NHALF; ++hf) {
-          tma_load_2d(tr + hf * Cf::DN * 128, &tmT1, &st_full[stage], y0 + hf * 64, bh * p.d);
-          if (MODE == 1) tma_load_2d(tr + Cf::TR_BYTES + hf * Cf::DN * 128, &tmT2, &st_full[stage], y0 + hf * 64, bh * p.d);
-        }
         if (MODE == 1) {
-          unsigned char* vec = tr + Cf::NT * Cf::TR_BYTES;
+          unsigned char* vec = st + 2 * Cf::NAT_BYTES;
           bulk_g2s(vec, p.lse_pad + (size_t)bh * p.Lq_pad + y0, Cf::BY * 4, &st_full[stage]);
           bulk_g2s(vec + Cf::BY * 4, p.D_pad + (size_t)bh * p.Lq_pad + y0, Cf::BY * 4, &st_full[stage]);
         }
@@ -174,21 +170,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
         umma_commit(s_full);
         mbar_wait(p_full, it & 1);                          // row threads wrote P / dS of this tile
         tc_fence_after();
-        const uint32_t aT1 = aB1 + 2 * Cf::NAT_BYTES, aT2 = aT1 + Cf::TR_BYTES;
+        // accumulating products: B = a streamed natural tile read MN-major (reduction over its BY rows, 16 rows = 2048 B
+        // per k-step, d-panels BY*128 B apart)
+        const uint32_t aAcc0 = (MODE == 0) ? aB1 : aB2;      // MODE 0: dQ += dS K      MODE 1: dV += P^T dO
 #pragma unroll
         for (int ks = 0; ks < Cf::BY / 16; ++ks) {
-          const uint32_t offp = (uint32_t)(ks / 4) * (AB_ROWS * 128) + (uint32_t)(ks % 4) * 32;
-          const uint32_t offt = (uint32_t)(ks / 4) * (Cf::DN * 128) + (uint32_t)(ks % 4) * 32;
-          // MODE 0: dQ += dS K      MODE 1: dV += P^T dO
-          umma_f16(tmem_base + Cf::COL_ACC0, make_kmajor_sw128_desc(aPD + offp), make_kmajor_sw128_desc(aT1 + offt), p.idesc_acc,
-                   (it > 0 || ks > 0) ? 1u : 0u);
+          umma_f16(tmem_base + Cf::COL_ACC0, make_kmajor_sw128_desc(aPD + (uint32_t)ks * 32),
+                   make_mnmajor_sw128_desc(aAcc0 + (uint32_t)ks * 2048, Cf::BY * 128), p.idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
         }
         if (MODE == 1) {
 #pragma unroll
           for (int ks = 0; ks < Cf::BY / 16; ++ks) {
-            const uint32_t offp = (uint32_t)(Cf::NHALF * AB_ROWS * 128) + (uint32_t)(ks / 4) * (AB_ROWS * 128) + (uint32_t)(ks % 4) * 32;
-            const uint32_t offt = (uint32_t)(ks / 4) * (Cf::DN * 128) + (uint32_t)(ks % 4) * 32;
-            umma_f16(tmem_base + Cf::COL_ACC1, make_kmajor_sw128_desc(aPD + offp), make_kmajor_sw128_desc(aT2 + offt), p.idesc_acc,
+            umma_f16(tmem_base + Cf::COL_ACC1, make_kmajor_sw128_desc(aPD + (uint32_t)(AB_ROWS * 128) + (uint32_t)ks * 32),
+                     make_mnmajor_sw128_desc(aB1 + (uint32_t)ks * 2048, Cf::BY * 128), p.idesc_acc,
                      (it > 0 || ks > 0) ? 1u : 0u);          // dK += dS^T Q
           }
         }
@@ -217,7 +211,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       if (MODE == 1) mbar_wait(&st_full[stage], phase);      // acquire the TMA-written lse / D slices for generic loads
       tc_fence_after();
       const int y0 = it * Cf::BY;
-      const float* vec = reinterpret_cast<const float*>(sStage + stage * Cf::STAGE_BYTES + 2 * Cf::NAT_BYTES + Cf::NT * Cf::TR_BYTES);
+      const float* vec = reinterpret_cast<const float*>(sStage + stage * Cf::STAGE_BYTES + 2 * Cf::NAT_BYTES);
       // warp-uniform: no external dP, no padding / causal edge inside this (warp, tile) -> predicate-free fast path
       bool fast_w;
       if (MODE == 0) fast_w = (p.dp_ext == nullptr) && (y0 + Cf::BY <= klen) && (!p.causal || (y0 + Cf::BY - 1 <= x0 + q4 * 32));
@@ -281,8 +275,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
             pk_ds[i / 2] = ab_pack2<T>(dsv[0], dsv[1]);
           }
         }
-        unsigned char* half0 = sPD + (c0 / 64) * (AB_ROWS * 128);                            // MODE 0: dS   | MODE 1: P^T
-        unsigned char* half1 = sPD + Cf::NHALF * AB_ROWS * 128 + (c0 / 64) * (AB_ROWS * 128);  //              | MODE 1: dS^T
+        unsigned char* half0 = sPD;                      // MODE 0: dS   | MODE 1: P^T     (one 64-wide K-major tile each)
+        unsigned char* half1 = sPD + AB_ROWS * 128;      //              | MODE 1: dS^T
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int cc = (c0 % 64) / 8 + q;
@@ -332,24 +326,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cf::TMEM_COLS); }
-}
-
-// (n, L, H*d) -> per-head transpose (n*H, d, Lpad), zero padded  (same as the forward's V^T pre-pass)
-template <typename T>
-__global__ void ab_transpose_kernel(const T* __restrict__ v, T* __restrict__ vt, int L, int H, int d, int Lpad) {
-  pdl_grid_dependency_sync();
-  __shared__ T tile[32][33];
-  const int bh = blockIdx.z, b = bh / H, h = bh % H;
-  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int key = k0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (key < L && c < d) ? v[((size_t)b * L + key) * (H * d) + h * d + c] : from_f32<T>(0.f);
-  }
-  __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int c = c0 + j, key = k0 + threadIdx.x;
-    if (c < d && key < Lpad) vt[((size_t)bh * d + c) * Lpad + key] = tile[threadIdx.x][j];
-  }
 }
 
 // D_i = sum_c dO o O (+ sum_k P dP_ext), lse (x log2 e) padded with 1e30 / D padded with 0 to Lq_pad.
@@ -403,17 +379,16 @@ static int launch_ab(const CUtensorMap* m, const AttnBwdKP& kp, dim3 grid, cudaS
     COMAT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D, MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::TOTAL));
     configured = true;
   }
-  launch_k(attn_bwd_kernel<D, MODE, T>, grid, AB_THREADS, Cf::TOTAL, st, m[0], m[1], m[2], m[3], m[4], m[5], kp);
+  launch_k(attn_bwd_kernel<D, MODE, T>, grid, AB_THREADS, Cf::TOTAL, st, m[0], m[1], m[2], m[3], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 
 template <int D, typename T>
-static int run_bwd(const void* q, const void* k, const void* v, const void* dO, void* qT, void* kT, void* dOT, AttnBwdKP kp, int n,
+static int run_bwd(const void* q, const void* k, const void* v, const void* dO, AttnBwdKP kp, int n,
                    void* dq, void* dk, void* dv, int fmt, cudaStream_t st) {
-  constexpr int NKC = (D + 63) / 64; (void)NKC;
   constexpr int DN = (D + 15) / 16 * 16;
-  constexpr int BY = (D <= 64) ? 128 : 64;
+  constexpr int BY = ABCfg<D, 0>::BY;
   const int H = kp.H, d = kp.d, Lq = kp.Lq, Lk = kp.Lk;
   auto nat = [&](CUtensorMap* m, const void* base, int L, int rows) {
     const uint64_t dims[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * L};
@@ -421,28 +396,19 @@ static int run_bwd(const void* q, const void* k, const void* v, const void* dO, 
     const uint32_t box[3] = {64, 1, (uint32_t)rows};
     return make_tmap_16bit(m, base, 3, dims, str, box);
   };
-  auto trn = [&](CUtensorMap* m, const void* base, int Lpad) {
-    const uint64_t dims[2] = {(uint64_t)Lpad, (uint64_t)n * H * d};
-    const uint64_t str[1] = {(uint64_t)Lpad * 2};
-    const uint32_t box[2] = {64, (uint32_t)DN};
-    return make_tmap_16bit(m, base, 2, dims, str, box);
-  };
   kp.idesc_s = make_idesc_f16(AB_ROWS, BY, fmt);
-  kp.idesc_acc = make_idesc_f16(AB_ROWS, DN, fmt);
-  CUtensorMap m[6];
+  kp.idesc_acc = make_idesc_f16(AB_ROWS, DN, fmt, 0, 1);       // B operand MN-major
+  CUtensorMap m[4];
   memset(m, 0, sizeof(m));
   // ---- MODE 0: dQ
-  bool ok = nat(&m[0], q, Lq, AB_ROWS) && nat(&m[1], dO, Lq, AB_ROWS) && nat(&m[2], k, Lk, BY) && nat(&m[3], v, Lk, BY) &&
-            trn(&m[4], kT, kp.Lk_pad);
-  m[5] = m[4];
+  bool ok = nat(&m[0], q, Lq, AB_ROWS) && nat(&m[1], dO, Lq, AB_ROWS) && nat(&m[2], k, Lk, BY) && nat(&m[3], v, Lk, BY);
   if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   kp.n_inner = (Lk + BY - 1) / BY;
   kp.out0 = dq; kp.out1 = nullptr;
   int rc = launch_ab<D, 0, T>(m, kp, dim3((Lq + AB_ROWS - 1) / AB_ROWS, H, n), st);
   if (rc) return rc;
   // ---- MODE 1: dK, dV
-  ok = nat(&m[0], k, Lk, AB_ROWS) && nat(&m[1], v, Lk, AB_ROWS) && nat(&m[2], q, Lq, BY) && nat(&m[3], dO, Lq, BY) &&
-       trn(&m[4], dOT, kp.Lq_pad) && trn(&m[5], qT, kp.Lq_pad);
+  ok = nat(&m[0], k, Lk, AB_ROWS) && nat(&m[1], v, Lk, AB_ROWS) && nat(&m[2], q, Lq, BY) && nat(&m[3], dO, Lq, BY);
   if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   kp.n_inner = (Lq + BY - 1) / BY;
   kp.out0 = dk; kp.out1 = dv;
@@ -454,7 +420,8 @@ using namespace comat;
 
 extern "C" size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int H, int d) {
   const size_t Lqp = (size_t)(Lq + 127) / 128 * 128, Lkp = (size_t)(Lk + 127) / 128 * 128;
-  return (size_t)n * H * d * (2 * Lqp + Lkp) * 2 + (size_t)n * H * Lqp * 8 + 1024;
+  (void)Lkp; (void)d;
+  return (size_t)n * H * Lqp * 8 + 1024;       // padded lse (x log2 e) and D vectors
 }
 
 extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
@@ -467,15 +434,9 @@ extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, 
   cudaStream_t st = (cudaStream_t)stream;
   const int Lqp = (Lq + 127) / 128 * 128, Lkp = (Lk + 127) / 128 * 128;
   unsigned char* ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-  const size_t szq = (size_t)n * H * d * Lqp * 2, szk = (size_t)n * H * d * Lkp * 2;
-  void* qT = ws; void* dOT = ws + szq; void* kT = ws + 2 * szq;
-  float* lse_pad = reinterpret_cast<float*>(ws + 2 * szq + szk);
+  float* lse_pad = reinterpret_cast<float*>(ws);
   float* D_pad = lse_pad + (size_t)n * H * Lqp;
   {
-    dim3 blk(32, 8);
-    launch_k(ab_transpose_kernel<__half>, dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st, (const __half*)q, (__half*)qT, Lq, H, d, Lqp);
-    launch_k(ab_transpose_kernel<__half>, dim3((Lqp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st, (const __half*)dO, (__half*)dOT, Lq, H, d, Lqp);
-    launch_k(ab_transpose_kernel<__half>, dim3((Lkp + 31) / 32, (d + 31) / 32, n * H), blk, 0, st, (const __half*)k, (__half*)kT, Lk, H, d, Lkp);
     const long long rows = (long long)n * Lqp;
     if (H > 32) return COMAT_ERR_UNSUPPORTED;
     if (dtype == COMAT_F16)
@@ -492,8 +453,8 @@ extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, 
   const int fmt = dtype == COMAT_BF16 ? 1 : 0;
 #define AB_CASE(DD)                                                                                                          \
   case DD:                                                                                                                   \
-    return fmt ? run_bwd<DD, __nv_bfloat16>(q, k, v, dO, qT, kT, dOT, kp, n, dq, dk, dv, fmt, st)                            \
-               : run_bwd<DD, __half>(q, k, v, dO, qT, kT, dOT, kp, n, dq, dk, dv, fmt, st);
+    return fmt ? run_bwd<DD, __nv_bfloat16>(q, k, v, dO, kp, n, dq, dk, dv, fmt, st)                                         \
+               : run_bwd<DD, __half>(q, k, v, dO, kp, n, dq, dk, dv, fmt, st);
   switch (d) { AB_CASE(16) AB_CASE(32) AB_CASE(40) AB_CASE(64) AB_CASE(80) AB_CASE(128) AB_CASE(160) }
 #undef AB_CASE
   return COMAT_ERR_UNSUPPORTED;

@@ -43,6 +43,7 @@ struct GemmKP {
   long long out32_ld;
   uint32_t idesc;
   int is_bf16;
+  int a_mn, b_mn;              // operand stored MN-major ([K, M] / [K, N] row-major): TMA panels + MN-major descriptors
   int tiles_m;                 // number of 128-row (or 128-pixel) output tiles
   int split_k, kb_per_split;   // split-K: blockIdx.z handles k-blocks [z*kb_per_split, ...) and writes raw fp32 partials
   float* splitk_ws;            // [split_k][M][N] fp32
@@ -273,8 +274,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         unsigned char* sb = sa + S::A_BYTES;
         mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
         if (p.conv) tma_load_4d(sa, mA, &full_bar[stage], cb * BK, w0 + p.dw[tap], h0 + p.dh[tap], img0);
+        else if (p.a_mn) { tma_load_2d(sa, mA, &full_bar[stage], m0, cb * BK); tma_load_2d(sa + 8192, mA, &full_bar[stage], m0 + 64, cb * BK); }
         else        tma_load_2d(sa, mA, &full_bar[stage], cb * BK, m0);
-        tma_load_2d(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, n0);
+        if (p.b_mn) {
+#pragma unroll
+          for (int pn = 0; pn < BN / 64; ++pn) tma_load_2d(sb + pn * 8192, mB, &full_bar[stage], n0 + pn * 64, cb * BK);
+        } else tma_load_2d(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -288,12 +293,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
         const uint32_t sb = sa + S::A_BYTES;
-        const uint64_t da = make_kmajor_sw128_desc(sa);
-        const uint64_t db = make_kmajor_sw128_desc(sb);
+        const uint64_t da = p.a_mn ? make_mnmajor_sw128_desc(sa, 8192) : make_kmajor_sw128_desc(sa);
+        const uint64_t db = p.b_mn ? make_mnmajor_sw128_desc(sb, 8192) : make_kmajor_sw128_desc(sb);
+        const uint64_t ka = p.a_mn ? 128 : 2, kbs = p.b_mn ? 128 : 2;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the (addr>>4) field
-          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          // advance 16 elements along K: K-major = 32 B inside the 128-B swizzle row (+2 in the addr>>4 field),
+          // MN-major = 16 rows of 128 B (+128)
+          umma_f16(tmem_base, da + ka * k, db + kbs * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);          // frees this smem stage when the MMAs above have read it
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -456,8 +463,12 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           unsigned char* sb = sa + S::A_BYTES;
           mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           if (p.conv) tma_load_4d(sa, mA, &full_bar[stage], cb * BK, c.w0 + p.dw[tap], c.h0 + p.dh[tap], c.img0);
+          else if (p.a_mn) { tma_load_2d(sa, mA, &full_bar[stage], c.m0, cb * BK); tma_load_2d(sa + 8192, mA, &full_bar[stage], c.m0 + 64, cb * BK); }
           else        tma_load_2d(sa, mA, &full_bar[stage], cb * BK, c.m0);
-          tma_load_2d(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, n0);
+          if (p.b_mn) {
+#pragma unroll
+            for (int pn = 0; pn < BN / 64; ++pn) tma_load_2d(sb + pn * 8192, mB, &full_bar[stage], n0 + pn * 64, cb * BK);
+          } else tma_load_2d(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (++rem == kb_per_tap) { rem = 0; ++tap; }
         }
@@ -481,11 +492,12 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint32_t sb = sa + S::A_BYTES;
-          const uint64_t da = make_kmajor_sw128_desc(sa);
-          const uint64_t db = make_kmajor_sw128_desc(sb);
+          const uint64_t da = p.a_mn ? make_mnmajor_sw128_desc(sa, 8192) : make_kmajor_sw128_desc(sa);
+          const uint64_t db = p.b_mn ? make_mnmajor_sw128_desc(sb, 8192) : make_kmajor_sw128_desc(sb);
+          const uint64_t ka = p.a_mn ? 128 : 2, kbs = p.b_mn ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16(d_tmem, da + ka * k, db + kbs * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -637,7 +649,13 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   // 256-wide tiles need 25 % less smem operand traffic per FLOP than 160-wide ones; take them when N divides and
   // there are enough of them to fill the machine (profiles/r01_gemm_persist_vs_tile.md)
   if (g->force_bn == 0 && (g->N % 256) == 0 && (long long)((g->M + BM - 1) / BM) * (g->N / 256) >= num_sms()) BN = 256;
-  kp.idesc = make_idesc_f16(BM, BN, kp.is_bf16 ? 1 : 0);
+  const int a_mn = g->a_mn_major ? 1 : 0, b_mn = g->b_mn_major ? 1 : 0;
+  if (a_mn || b_mn) {
+    if (g->conv || g->n_seg != 1) return COMAT_ERR_UNSUPPORTED;
+    if (b_mn && (BN % 64) != 0) BN = g->N > 64 ? 128 : 64;        // B panels are 64 columns wide
+  }
+  kp.a_mn = a_mn; kp.b_mn = b_mn;
+  kp.idesc = make_idesc_f16(BM, BN, kp.is_bf16 ? 1 : 0, a_mn, b_mn);
   CUtensorMap maps[5];
   memset(maps, 0, sizeof(maps));
   dim3 grid;
@@ -670,7 +688,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   }
   for (int s = 0; s < g->n_seg; ++s) {
     const int K = g->a_k[s];
-    if (K <= 0 || (K % 8) != 0 || !g->a[s] || !g->b[s]) return COMAT_ERR_INVALID;
+    if (K <= 0 || ((!a_mn || !b_mn) && (K % 8) != 0) || !g->a[s] || !g->b[s]) return COMAT_ERR_INVALID;   // K-major rows need 16-B pitch
     if ((reinterpret_cast<uintptr_t>(g->a[s]) & 15) || (reinterpret_cast<uintptr_t>(g->b[s]) & 15)) return COMAT_ERR_INVALID;
     if (kp.conv && (K % BK) != 0) return COMAT_ERR_UNSUPPORTED;   // channel slabs of 64
     kp.seg_kblocks[s] = (K + BK - 1) / BK;
@@ -680,6 +698,12 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
       const uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)K * 2 * g->W, (uint64_t)K * 2 * g->W * g->H};
       const uint32_t box[4] = {(uint32_t)BK, (uint32_t)kp.TW, (uint32_t)kp.TH, (uint32_t)kp.TN};
       if (!make_tmap_16bit(&maps[s], g->a[s], 4, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    } else if (a_mn) {                                   // A stored [K, M] row-major: panels of 64 M-columns x 64 k-rows
+      if ((g->a_ld[s] % 8) != 0) return COMAT_ERR_INVALID;
+      const uint64_t dims[2] = {(uint64_t)g->M, (uint64_t)K};
+      const uint64_t str[1] = {(uint64_t)g->a_ld[s] * 2};
+      const uint32_t box[2] = {64u, (uint32_t)BK};
+      if (!make_tmap_16bit(&maps[s], g->a[s], 2, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
     } else {
       if ((g->a_ld[s] % 8) != 0) return COMAT_ERR_INVALID;
       const uint64_t dims[2] = {(uint64_t)K, (uint64_t)g->M};
@@ -687,7 +711,13 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
       const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
       if (!make_tmap_16bit(&maps[s], g->a[s], 2, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
     }
-    {
+    if (b_mn) {                                          // B stored [K, N] row-major
+      if ((g->b_ld[s] % 8) != 0) return COMAT_ERR_INVALID;
+      const uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)K};
+      const uint64_t str[1] = {(uint64_t)g->b_ld[s] * 2};
+      const uint32_t box[2] = {64u, (uint32_t)BK};
+      if (!make_tmap_16bit(&maps[2 + s], g->b[s], 2, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    } else {
       if ((g->b_ld[s] % 8) != 0) return COMAT_ERR_INVALID;
       const uint64_t kext = kp.conv ? (uint64_t)g->n_taps * g->c_total : (uint64_t)g->b_koff[s] + K;
       const uint64_t dims[2] = {kext, (uint64_t)g->N};

@@ -122,9 +122,25 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major tile, 128-byte swizzle: the tile is stored as panels of [k rows][64 x 16-bit = 128 B] (what a TMA box {64, rows}
+// with SWIZZLE_128B writes); 8 k-rows form one 1024-B swizzle atom (SBO), consecutive 64-element MN chunks are
+// `panel_bytes` apart (LBO).  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.  A 16-deep k-step advances
+// the start address by 16 rows = 2048 B.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t panel_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((panel_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // instruction descriptor, kind::f16: D=f32, A/B = f16 (fmt 0) or bf16 (fmt 1), both K-major, M x N tile.
-__host__ __device__ inline uint32_t make_idesc_f16(int M, int N, int fmt) {
+__host__ __device__ inline uint32_t make_idesc_f16(int M, int N, int fmt, int a_mn_major = 0, int b_mn_major = 0) {
   uint32_t d = 0;
+  d |= (uint32_t)(a_mn_major ? 1 : 0) << 15;   // a_major: 0 = K-major, 1 = MN-major
+  d |= (uint32_t)(b_mn_major ? 1 : 0) << 16;   // b_major
   d |= 1u << 4;                       // c_format = F32
   d |= (uint32_t)fmt << 7;            // a_format
   d |= (uint32_t)fmt << 10;           // b_format

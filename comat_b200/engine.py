@@ -191,10 +191,8 @@ def linear(tape, x: Var, lw: LinW, lora: Optional[LoRAW] = None, residual: Optio
             if lora is not None:
                 u = ops.gemm([dy2], [lora.up16_t])                                   # dy . up      (M, r)
                 if lora.wgrad:
-                    dyT, tT = ops.transpose16(dy2, 8), ops.transpose16(t, 8)
-                    gu = ops.gemm([dyT], [tT], out_fp32=True)                        # d up   = dy^T t  (N, r)
-                    uT, xT = ops.transpose16(u, 8), ops.transpose16(x2, 8)
-                    gd = ops.gemm([uT], [xT], out_fp32=True)                         # d down = u^T x   (r, K)
+                    gu = ops.gemm_tn(dy2, t)                                         # d up   = dy^T t  (N, r)
+                    gd = ops.gemm_tn(u, x2)                                          # d down = u^T x   (r, K)
                     lora.g_up = gu if lora.g_up is None else lora.g_up + gu
                     lora.g_down = gd if lora.g_down is None else lora.g_down + gd
                 if x.needs_grad:

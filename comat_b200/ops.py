@@ -24,7 +24,8 @@ class GemmParams(C.Structure):
                 ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rows_per_group", C.c_int32),
                 ("act", C.c_int32), ("residual", C.c_void_p), ("res_ld", C.c_int64), ("out16", C.c_void_p),
                 ("out_ld", C.c_int64), ("out32", C.c_void_p), ("out32_ld", C.c_int64), ("force_bn", C.c_int32),
-                ("split_k", C.c_int32), ("accumulate", C.c_int32), ("splitk_ws", C.c_void_p), ("rowvec_ld", C.c_int64)]
+                ("split_k", C.c_int32), ("accumulate", C.c_int32), ("splitk_ws", C.c_void_p), ("rowvec_ld", C.c_int64),
+                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32)]
 
 
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
@@ -113,7 +114,7 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         kb = sum((a.shape[-1] + 63) // 64 for a in a_segs) * (len(conv_taps) if conv else 1)
         tiles = ((M + 127) // 128) * ((N + 127) // 128)
         if tiles <= 74 and kb >= 32:
-            split_k = max(1, min(kb // 8, 296 // tiles))
+            split_k = max(1, min(kb // 8, 148 // tiles))
     if split_k > 1:
         ws = torch.empty(split_k * M * N, dtype=torch.float32, device=a0.device)
         p.split_k, p.splitk_ws, p.accumulate = split_k, ws.data_ptr(), int(accumulate)
@@ -136,6 +137,59 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         PROFILE["flops"] += fl
     if conv:
         return out.reshape(n_img, H, W, N) if out.dim() == 2 else out
+    return out
+
+
+def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, split_k: int = 0) -> torch.Tensor:
+    """out[m, n] = sum_k a_km[k, m] * b_kn[k, n]   (= a_km^T @ b_kn), both operands read as they lie in memory.
+
+    The weight-gradient shape: K is the token dimension (tens of thousands), M and N are feature dimensions.  Both operands
+    go through TMA as MN-major panels and the tcgen05 descriptors carry the MN-major flag, so no transposed copies are made.
+    K-split partial sums are reduced in a fixed order (deterministic)."""
+    _lib.require_cuda(a_km)
+    dt = a_km.dtype
+    if dt not in (torch.float16, torch.bfloat16) or b_kn.dtype != dt:
+        raise _lib.ComatError("gemm_tn: operands must share a 16-bit dtype")
+    if a_km.dim() != 2 or b_kn.dim() != 2 or a_km.shape[0] != b_kn.shape[0]:
+        raise _lib.ComatError("gemm_tn: expected (K, M) and (K, N)")
+    if a_km.stride(1) != 1:
+        a_km = a_km.contiguous()
+    if b_kn.stride(1) != 1:
+        b_kn = b_kn.contiguous()
+    K, M = a_km.shape
+    N = b_kn.shape[1]
+    p = GemmParams()
+    p.M, p.N, p.dtype, p.n_seg = M, N, DT[dt], 1
+    p.a[0], p.a_ld[0], p.a_k[0] = a_km.data_ptr(), a_km.stride(0), K
+    p.b[0], p.b_ld[0] = b_kn.data_ptr(), b_kn.stride(0)
+    p.a_mn_major, p.b_mn_major = 1, 1
+    p.alpha = 1.0
+    p.rows_per_group = 1
+    out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else dt, device=a_km.device)
+    if out_fp32:
+        p.out32, p.out32_ld = out.data_ptr(), N
+    else:
+        p.out16, p.out_ld = out.data_ptr(), N
+    kb = (K + 63) // 64
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if split_k == 0 and tiles <= 74 and kb >= 32:
+        split_k = max(1, min(kb // 8, 148 // tiles))
+    ws = None
+    if split_k > 1:
+        ws = torch.empty(split_k * M * N, dtype=torch.float32, device=a_km.device)
+        p.split_k, p.splitk_ws = split_k, ws.data_ptr()
+    timed = PROFILE is not None and "keys_only" not in PROFILE
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(_lib.lib().comat_gemm(C.byref(p), _lib.stream_ptr()), "gemm_tn")
+    _lib.count_launch()
+    if PROFILE is not None:
+        if timed:
+            e1.record()
+        fl = 2.0 * M * N * K
+        PROFILE["events"].append((e0 if timed else None, e1 if timed else None, (M, N, (K,), -1, int(p.split_k), bool(out_fp32)), fl))
+        PROFILE["flops"] += fl
     return out
 
 

@@ -132,6 +132,11 @@ typedef struct {
   float* splitk_ws;
   int64_t rowvec_ld;        /* row pitch of rowvec in floats (0 = N): lets all ResBlock time-embedding projections of a UNet call
                                come from ONE GEMM whose output is sliced per block */
+  int32_t a_mn_major;       /* 1: a[0] is stored [K, M] row-major (M contiguous) instead of [M, K]; a_ld = its row pitch, a_k = K.
+                               out = A^T-stored . B: the LoRA weight-gradient GEMMs (d up = dy^T t, d down = u^T x of
+                               training_utils/pipeline.py:94-115's backward) read dy / t / x as they lie, no transposed copies.
+                               Plain mode, one K segment only. */
+  int32_t b_mn_major;       /* 1: b[0] is stored [K, N] row-major (N contiguous) */
 } comat_gemm_params;
 
 int comat_gemm(const comat_gemm_params* p, void* stream);

@@ -149,9 +149,14 @@ def nhwc_to_nchw_f32(x, cout, scale=1.0):
     return (x[..., :cout].float() * scale).permute(0, 3, 1, 2).contiguous()
 
 
+def gemm_tn(a_km, b_kn, *, out_fp32=True, split_k=0):
+    y = a_km.double().t() @ b_kn.double()
+    return y.float() if out_fp32 else y.to(a_km.dtype)
+
+
 def install(monkeypatch):
     from comat_b200 import ops
-    for name in ("gemm", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
+    for name in ("gemm", "gemm_tn", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
                  "elementwise", "spatial", "transpose16", "concat_channels", "latent_to_nhwc", "nhwc_to_nchw_f32"):
         monkeypatch.setattr(ops, name, globals()[name])
 

@@ -48,6 +48,25 @@ def test_gemm_kernel_selection_paths(M, N, K, why):
     assert torch.equal(out.float(), ref), (why, (out.float() - ref).abs().nonzero()[:8])
 
 
+@pytest.mark.parametrize("K,M,N,split", [(64, 128, 128, 1), (256, 128, 64, 1), (4096, 320, 128, 0), (1000, 128, 320, 0),
+                                         (8 * 4096, 1280, 128, 0), (616, 136, 776, 1), (130, 8, 24, 1)])
+def test_gemm_tn_mn_major_operands_exact(K, M, N, split):
+    """out = A^T B with both operands read MN-major (TMA panels + MN-major tcgen05 descriptors): the LoRA weight-gradient
+    shapes.  Small-integer data, fp32 output: exact, so a wrong panel stride / k-step / major bit is a wrong integer."""
+    from comat_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(K + M + N)
+    a = torch.randint(-2, 3, (K, M), device="cuda", generator=g).half()
+    b = torch.randint(-2, 3, (K, N), device="cuda", generator=g).half()
+    # sparsify so sums stay exactly representable with long K
+    a = a * (torch.rand(K, M, device="cuda", generator=g) < 0.25)
+    out = ops.gemm_tn(a, b, split_k=split)
+    ref = a.float().t() @ b.float()
+    assert ref.abs().max() < 2 ** 24
+    assert torch.equal(out, ref), (out - ref).abs().nonzero()[:8]
+    out_b = ops.gemm_tn(a.bfloat16(), b.bfloat16(), out_fp32=False, split_k=split)
+    assert torch.allclose(out_b.float(), ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+
+
 def test_gemm_identity_pattern_exact():
     """small integers are exact in fp16/fp32: any descriptor / swizzle / row-mapping slip shows up as a wrong integer."""
     from comat_b200 import ops
