@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--no_gan", action="store_true")
     p.add_argument("--no_attrcon", action="store_true")
     p.add_argument("--no_graphs", action="store_true", help="disable CUDA-graph replay of the no-grad UNet forwards")
+    p.add_argument("--kineto_steps", type=int, default=1, help="consecutive steps inside the --kineto_step window")
     p.add_argument("--sync_debug", action="store_true", help="run ONE step with torch.cuda.set_sync_debug_mode('warn') and list the host-sync call sites")
     p.add_argument("--gemm_shapes", default="", help="write the per-shape GEMM table of the instrumented step to this path")
     p.add_argument("--kineto_step", default="", help="profile ONE step with torch.profiler (CUPTI) and write a per-kernel table to this path")
@@ -227,7 +228,8 @@ def main():
         d_unet, _ = synthetic.build_sd15(dev, dt, rank=rank_lora, seed=43, tiny=a.tiny)
         D = D_sd(EngineUNet(d_unet, dt))
     pipe.unet.use_graphs = not a.no_graphs
-    trainer = CoMatTrainer(args, pipe, cap, D, process_group=None)
+    trainer = CoMatTrainer(args, pipe, cap, D, process_group=None,
+                           manual_gc_interval=0 if os.environ.get("COMAT_MANUAL_GC") == "0" else 25)
     ctx_dim = 64 if a.tiny else 768
     host_batches = [synthetic.synthetic_batch(a.batch, 1000 * rank + i, ctx_dim, args.resolution, attrcon, gan, pinned=True)
                     for i in range(4)]
@@ -287,7 +289,8 @@ def main():
         if a.gemm_shapes:
             ops.PROFILE = gp = {"flops": 0.0, "events": [], "keys_only": True}
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            trainer.train_step(dev_batches[0])
+            for i in range(a.kineto_steps):
+                trainer.train_step(dev_batches[i % len(dev_batches)])
             torch.cuda.synchronize()
         ops.PROFILE = None
         if a.gemm_shapes:
@@ -319,18 +322,21 @@ def main():
             # gaps mean the GPU waited for the host
             try:
                 from torch.autograd import DeviceType
-                dev_ev = sorted(((e.time_range.start, e.time_range.end) for e in prof.events()
+                dev_ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
                                  if e.device_type == DeviceType.CUDA and e.time_range.end > e.time_range.start), key=lambda t: t[0])
                 edges = [2, 5, 20, 100, 1000, 1e9]
                 cnt, tot_gap = [0] * len(edges), [0.0] * len(edges)
-                end = dev_ev[0][1]
-                for st, en in dev_ev[1:]:
+                end, prev_name, big = dev_ev[0][1], dev_ev[0][2], []
+                for st, en, nm in dev_ev[1:]:
                     gap = st - end
                     if gap > 0:
                         k = next(i for i, e_ in enumerate(edges) if gap < e_)
                         cnt[k] += 1
                         tot_gap[k] += gap
-                    end = max(end, en)
+                        if gap > 200:
+                            big.append((gap, (end - dev_ev[0][0]) / 1e3, prev_name[:60], nm[:60]))
+                    if en >= end:
+                        end, prev_name = en, nm
                 span = (dev_ev[-1][1] - dev_ev[0][0]) / 1e3
                 fh.write(f"\ndevice timeline: {len(dev_ev)} kernels over {span:.1f} ms; idle gaps between consecutive kernels:\n")
                 fh.write("| gap (us) | count | total ms |\n|---|---:|---:|\n")
@@ -338,6 +344,9 @@ def main():
                 for e_, c_, t_ in zip(edges, cnt, tot_gap):
                     fh.write(f"| {lo}-{e_ if e_ < 1e9 else 'inf'} | {c_} | {t_ / 1e3:.2f} |\n")
                     lo = e_
+                fh.write("\nlargest idle gaps (us, at ms from the first kernel, kernel before -> kernel after):\n")
+                for g_, at_, pn_, nn_ in sorted(big, reverse=True)[:16]:
+                    fh.write(f"- {g_:.0f} us at {at_:.1f} ms: `{pn_}` -> `{nn_}`\n")
             except Exception as ex:  # profiler internals differ between torch versions
                 fh.write(f"\n(gap analysis unavailable: {ex!r})\n")
         return 0
@@ -349,12 +358,17 @@ def main():
         torch.cuda.profiler.stop()
         return 0
     clocks = ClockSampler(local) if rank == 0 else None
+    ms0 = torch.cuda.memory_stats()
     if clocks:
         clocks.start()
     l0 = _lib.LAUNCH_COUNT
     lib0 = attention.LIBRARY_CALLS + caption.LIBRARY_CALLS + image_ops.LIBRARY_CALLS
     t_dev, _, logs = timed(a.steps, host_inputs=False)
     host_issue_ms = 1e3 * timed.host_issue_s
+    ms1 = torch.cuda.memory_stats()
+    mem_note = {"peak_allocated_gb": ms1.get("allocated_bytes.all.peak", 0) / 2**30, "peak_reserved_gb": ms1.get("reserved_bytes.all.peak", 0) / 2**30,
+                "cudaMalloc_calls_in_timed_steps": ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0),
+                "alloc_retries_in_timed_steps": ms1.get("num_alloc_retries", 0) - ms0.get("num_alloc_retries", 0)}
     launches = _lib.LAUNCH_COUNT - l0
     lib_calls = attention.LIBRARY_CALLS + caption.LIBRARY_CALLS + image_ops.LIBRARY_CALLS - lib0
     t_e2e, d2h, _ = timed(a.steps, host_inputs=True)
@@ -377,7 +391,7 @@ def main():
     if rank == 0:
         value = a.steps / t_dev
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": 1e3 * t_dev / a.steps, "host_issue_ms_per_step": host_issue_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": 1e3 * t_dev / a.steps, "host_issue_ms_per_step": host_issue_ms, "memory": mem_note, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.dtype, "data": "synthetic",
                 "config": {"workload": ("TINY-DEBUG " if a.tiny else "") + "SD1.5 512^2 full CoMat (BLIP concept-match + attention-map "
                            "token/pixel loss on 2 attrcon steps + GAN G/D), S=%d DDPM steps, K=%d, batch %d/GPU, LoRA r=%d, cfg 7.5 "

@@ -33,3 +33,12 @@ def golden():
     def load(name):
         return torch.load(os.path.join(GOLDEN, f"{name}.pt"), weights_only=False)
     return load
+
+
+@pytest.fixture(autouse=True)
+def _restore_python_gc():
+    """CoMatTrainer takes over the cyclic GC while it steps (trainer.py); give every test the interpreter defaults back."""
+    import gc
+    yield
+    gc.unfreeze()
+    gc.enable()
