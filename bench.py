@@ -296,7 +296,7 @@ def main():
         if a.gemm_shapes:
             # kernel durations (CUPTI) of the GEMM launches in issue order <-> the shapes ops.gemm recorded in the same order
             # (only valid with --no_graphs: graph replays do not pass through ops.gemm)
-            kev = sorted((e for e in prof.events() if "gemm_tc_kernel" in e.name), key=lambda e: e.time_range.start)
+            kev = sorted((e for e in prof.events() if "gemm_tc_" in e.name), key=lambda e: e.time_range.start)
             by = {}
             if len(kev) == len(gp["events"]):
                 for e, (_, _, key, fl) in zip(kev, gp["events"]):

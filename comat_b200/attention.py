@@ -21,6 +21,7 @@ LIBRARY_CALLS = 0
 NATIVE_HEAD_DIMS = (16, 32, 40, 64, 80, 128, 160)
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 _lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
+_lib.register_signature("comat_attention_fwd_strided", [_vp] * 7 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _vp])
 _lib.register_signature("comat_attention_bwd", [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
 NATIVE_BWD = True
 _DT = {torch.float16: 1, torch.bfloat16: 2}
@@ -31,9 +32,19 @@ def native_supported(q, k, heads, export_probs):
     return (q.is_cuda and q.dtype in _DT and d in NATIVE_HEAD_DIMS and (not export_probs or k.shape[1] <= 128))
 
 
+def _rows(x):
+    """(n, L, C) operand as the kernel reads it: rows of C contiguous elements at a uniform pitch.  Column slices of a wider
+    matrix (fused q|k|v / k|v projection outputs) are passed in place; anything else is made contiguous."""
+    n, L, Cc = x.shape
+    if (x.stride(2) == 1 and x.stride(1) % 8 == 0 and x.stride(1) >= Cc and (n == 1 or x.stride(0) == L * x.stride(1))
+            and x.data_ptr() % 16 == 0):
+        return x, x.stride(1)
+    return x.contiguous(), Cc
+
+
 def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False, kv_lens=None, causal=False):
     """tcgen05 fused attention forward (csrc/attention.cu).  returns (o, probs | None, lse | None)"""
-    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    (q, q_ld), (k, k_ld), (v, v_ld) = _rows(q), _rows(k), _rows(v)
     n, Lq, Cq = q.shape
     Lk = k.shape[1]
     d = Cq // heads
@@ -41,15 +52,15 @@ def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False, kv_
     L.comat_attention_workspace_bytes.restype = C.c_size_t
     L.comat_attention_workspace_bytes.argtypes = [_i, _i, _i, _i]
     ws = torch.empty(int(L.comat_attention_workspace_bytes(n, Lk, heads, d)), dtype=torch.uint8, device=q.device)
-    o = torch.empty_like(q)
+    o = torch.empty(n, Lq, Cq, dtype=q.dtype, device=q.device)
     probs = torch.empty(n * heads, Lq, Lk, dtype=torch.float32, device=q.device) if export_probs else None
     lse = torch.empty(n * heads, Lq, dtype=torch.float32, device=q.device) if need_lse else None
-    _lib.check(L.comat_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
-                                     None if probs is None else probs.data_ptr(), None if lse is None else lse.data_ptr(),
-                                     ws.data_ptr(), n, Lq, Lk, heads, d, float(d) ** -0.5, _DT[q.dtype],
-                                     None if kv_lens is None else kv_lens.data_ptr(), int(causal), _lib.stream_ptr()),
+    _lib.check(L.comat_attention_fwd_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                             None if probs is None else probs.data_ptr(), None if lse is None else lse.data_ptr(),
+                                             ws.data_ptr(), n, Lq, Lk, heads, d, q_ld, k_ld, v_ld, float(d) ** -0.5, _DT[q.dtype],
+                                             None if kv_lens is None else kv_lens.data_ptr(), int(causal), _lib.stream_ptr()),
                "attention_fwd")
-    _lib.count_launch(2)
+    _lib.count_launch(1)
     return o, probs, lse
 
 
@@ -137,7 +148,7 @@ def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None
                                      dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), n, Lq, Lk, heads, d,
                                      float(d) ** -0.5, _DT[q.dtype], None if kv_lens is None else kv_lens.data_ptr(), int(causal),
                                      _lib.stream_ptr()), "attention_bwd")
-    _lib.count_launch(6)
+    _lib.count_launch(3)          # row-statistics prep + dQ kernel + dK/dV kernel
     return dq, dk, dv
 
 

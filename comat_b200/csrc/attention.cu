@@ -331,10 +331,12 @@ extern "C" size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d) {
   return 256;      // no scratch is needed any more (V is read in place); kept for ABI stability
 }
 
-extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
-                                   int n, int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal,
-                                   void* stream) {
+extern "C" int comat_attention_fwd_strided(const void* q, const void* k, const void* v, void* out, float* probs, float* lse,
+                                           void* workspace, int n, int Lq, int Lk, int H, int d, long long q_ld, long long k_ld,
+                                           long long v_ld, float scale, int dtype, const int* kv_lens, int causal, void* stream) {
   if (!q || !k || !v || !out || !workspace || n <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return COMAT_ERR_INVALID;
+  if (q_ld < (long long)H * d || k_ld < (long long)H * d || v_ld < (long long)H * d || (q_ld % 8) || (k_ld % 8) || (v_ld % 8)) return COMAT_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15)) return COMAT_ERR_INVALID;
   if (d != 40 && d != 64 && d != 80 && d != 128 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
   if (dtype != COMAT_F16 && dtype != COMAT_BF16) return COMAT_ERR_UNSUPPORTED;
   if (probs && Lk > ATT_BN) return COMAT_ERR_UNSUPPORTED;
@@ -353,13 +355,15 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
   CUtensorMap maps[3];
   {
     const uint64_t dq[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * Lq};
-    const uint64_t sq[2] = {(uint64_t)d * 2, (uint64_t)H * d * 2};
+    const uint64_t sq[2] = {(uint64_t)d * 2, (uint64_t)q_ld * 2};
     const uint32_t bq[3] = {64, 1, (uint32_t)ATT_BM};
     if (!make_tmap_16bit(&maps[0], q, 3, dq, sq, bq)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
     const uint64_t dk[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * Lk};
+    const uint64_t sk[2] = {(uint64_t)d * 2, (uint64_t)k_ld * 2};
+    const uint64_t sv[2] = {(uint64_t)d * 2, (uint64_t)v_ld * 2};
     const uint32_t bk[3] = {64, 1, (uint32_t)ATT_BN};
-    if (!make_tmap_16bit(&maps[1], k, 3, dk, sq, bk)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
-    if (!make_tmap_16bit(&maps[2], v, 3, dk, sq, bk)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    if (!make_tmap_16bit(&maps[1], k, 3, dk, sk, bk)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+    if (!make_tmap_16bit(&maps[2], v, 3, dk, sv, bk)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   }
   dim3 grid((Lq + ATT_BM - 1) / ATT_BM, H, n);
 #define ATT_CASE(DD)                                                                      \
@@ -370,4 +374,11 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
   }
 #undef ATT_CASE
   return COMAT_ERR_UNSUPPORTED;
+}
+
+extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
+                                   int n, int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal,
+                                   void* stream) {
+  const long long ld = (long long)H * d;
+  return comat_attention_fwd_strided(q, k, v, out, probs, lse, workspace, n, Lq, Lk, H, d, ld, ld, ld, scale, dtype, kv_lens, causal, stream);
 }

@@ -284,6 +284,15 @@ def attention(tape, q: Var, k: Var, v: Var, heads: int, export_probs: bool = Fal
 # ------------------------------------------------------------------------------------------------------------
 # network executors built from diffusers-shaped modules (state-dict compatible with oracle/sd_modules.py or diffusers)
 # ------------------------------------------------------------------------------------------------------------
+class _MergedLin:
+    """LinW-shaped view of a projection with its LoRA folded in: w = W + up.down (N, K), wt = w^T (K, N) for dgrad."""
+    __slots__ = ("w", "wt", "bias", "n", "k")
+
+    def __init__(self, w, bias):
+        self.w, self.wt, self.bias = w, None, bias
+        self.n, self.k = w.shape
+
+
 class _Attn:
     def __init__(self, m, dtype):
         self.heads = m.heads
@@ -291,6 +300,48 @@ class _Attn:
         self.loras = [LoRAW(l.lora_layer, dtype) if getattr(l, "lora_layer", None) is not None else None
                       for l in (m.to_q, m.to_k, m.to_v, m.to_out[0])]
         self.gn = NormW(m.group_norm, m.group_norm.num_groups) if m.group_norm is not None else None
+        self.mq = self.mk = self.mv = self.mo = None      # merged projections, built by build_merged()
+
+    # ---- LoRA folded into the projection weights (passes that need no LoRA weight gradient)
+    # y = W x + up(down(x)) (training_utils/pipeline.py:94-115) == (W + up.down) x: the no-grad rollout forwards and the
+    # frozen-LoRA discriminator pass (gan_sdxl.py:52-89) run ONE plain GEMM per projection; q|k|v (self-attention) and k|v
+    # (text context) live in one row-concatenated buffer so they are one GEMM each.
+    def build_merged(self):
+        dev, dt = self.q.w.device, self.q.w.dtype
+        C = self.q.n
+        if self.k.n != C or self.v.n != C:
+            raise ValueError("attention projections must share the inner width")
+        if self.k.k == self.q.k:                          # self-attention geometry: one (3C, K) buffer
+            self.w_qkv = torch.empty(3 * C, self.q.k, dtype=dt, device=dev)
+            wq, self.w_kv = self.w_qkv[:C], self.w_qkv[C:]
+        else:
+            self.w_qkv = None
+            wq = torch.empty(C, self.q.k, dtype=dt, device=dev)
+            self.w_kv = torch.empty(2 * C, self.k.k, dtype=dt, device=dev)
+        wo = torch.empty(self.o.n, self.o.k, dtype=dt, device=dev)
+        self.mq, self.mk, self.mv, self.mo = (_MergedLin(w, l.bias) for w, l in
+                                              ((wq, self.q), (self.w_kv[:C], self.k), (self.w_kv[C:], self.v), (wo, self.o)))
+        bs = [self.q.bias, self.k.bias, self.v.bias]
+        cat = lambda xs, ls: None if all(b is None for b in xs) else torch.cat(
+            [b if b is not None else torch.zeros(l.n, dtype=torch.float32, device=dev) for b, l in zip(xs, ls)])
+        self.b_qkv = cat(bs, (self.q, self.k, self.v))
+        self.b_kv = cat(bs[1:], (self.k, self.v))
+
+    def refresh_merged(self, transposed: bool):
+        if self.mq is None:
+            self.build_merged()
+        for ml, lw, lora in zip((self.mq, self.mk, self.mv, self.mo), (self.q, self.k, self.v, self.o), self.loras):
+            if lora is None:
+                ml.w.copy_(lw.w)
+            else:
+                ops.gemm([lora.up16], [lora.down16_t], residual=lw.w, out=ml.w)          # W + up.down, rounded once
+            if transposed:
+                if ml.wt is None:
+                    ml.wt = torch.empty(lw.k, lw.n, dtype=lw.w.dtype, device=lw.w.device)
+                if lora is None:
+                    ml.wt.copy_(lw.wt)
+                else:
+                    ops.gemm([lora.down16_t], [lora.up16], residual=lw.wt, out=ml.wt)    # (W + up.down)^T
 
 
 class _TBlock:
@@ -336,19 +387,47 @@ def _resnet(tape, r: _Res, x: Var, temb_act16, skip: Optional[Var] = None) -> Va
     return conv(tape, [h], r.c2, residual=sc)
 
 
-def _attn_layer(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, capture=None, place=None):
-    q = linear(tape, x, a.q, a.loras[0])
-    src = x if ctx is None else ctx
-    k = linear(tape, src, a.k, a.loras[1])
-    v = linear(tape, src, a.v, a.loras[2])
+def _attn_layer(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, capture=None, place=None, mode="train",
+                cross_kv=None):
+    """mode 'train': LoRA branch explicit (weight gradients wanted).  'frozen': taped, LoRA folded into the weights (data
+    gradients only).  'merged': no tape - folded weights, fused q|k|v / k|v GEMMs, ``cross_kv`` = the text context's
+    pre-projected (n, T, 2C) k|v (identical for every UNet call of a rollout, so it is computed once per optimiser step)."""
     export = capture is not None and ctx is not None and capture.wants(place)
+    if mode == "merged" and tape is None:
+        C = a.q.n
+        x2 = x.v.reshape(-1, a.q.k)
+        lead = x.v.shape[:-1]
+        if ctx is None and a.w_qkv is not None:
+            qkv = ops.gemm([x2], [a.w_qkv], bias=a.b_qkv).reshape(*lead, 3 * C)
+            q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        else:
+            q = ops.gemm([x2], [a.mq.w], bias=a.mq.bias).reshape(*lead, C)
+            if cross_kv is not None and ctx is not None:
+                kv = cross_kv
+            else:
+                src = x.v if ctx is None else ctx.v
+                kv = ops.gemm([src.reshape(-1, a.k.k)], [a.w_kv], bias=a.b_kv).reshape(*src.shape[:-1], 2 * C)
+            k, v = kv[..., :C], kv[..., C:]
+        o, probs, _ = attn_ops.attention_fwd(q, k, v, a.heads, export, need_bwd=False)
+        if capture is not None:
+            capture.push(Var(probs) if export else None, ctx is not None, place)
+        y = ops.gemm([o.reshape(-1, C)], [a.mo.w], bias=a.mo.bias, residual=residual.v.reshape(-1, a.mo.n))
+        return Var(y.reshape(*lead, a.mo.n))
+    if mode == "train":
+        lq, lk, lv, lo, loras = a.q, a.k, a.v, a.o, a.loras
+    else:
+        lq, lk, lv, lo, loras = a.mq, a.mk, a.mv, a.mo, (None, None, None, None)
+    q = linear(tape, x, lq, loras[0])
+    src = x if ctx is None else ctx
+    k = linear(tape, src, lk, loras[1])
+    v = linear(tape, src, lv, loras[2])
     o, p = attention(tape, q, k, v, a.heads, export_probs=export)
     if capture is not None:
         capture.push(p, ctx is not None, place)
-    return linear(tape, o, a.o, a.loras[3], residual=residual)
+    return linear(tape, o, lo, loras[3], residual=residual)
 
 
-def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=None) -> Var:
+def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=None, mode="train", cross_kv=None) -> Var:
     n, H, W, C = x.v.shape
     h = groupnorm(tape, x, t.gn, False)
     if t.linear_proj:
@@ -356,8 +435,9 @@ def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=No
     else:
         h = _reshape(tape, conv(tape, [h], t.pin), (n, H * W, t.pin.cout))
     for b in t.blocks:
-        h = _attn_layer(tape, b.a1, layernorm(tape, h, b.n1), None, h, capture, place)
-        h = _attn_layer(tape, b.a2, layernorm(tape, h, b.n2), ctx, h, capture, place)
+        h = _attn_layer(tape, b.a1, layernorm(tape, h, b.n1), None, h, capture, place, mode)
+        h = _attn_layer(tape, b.a2, layernorm(tape, h, b.n2), ctx, h, capture, place, mode,
+                        None if cross_kv is None else cross_kv.get(id(b.a2)))
         ff = geglu(tape, linear(tape, layernorm(tape, h, b.n3), b.ff1))
         h = linear(tape, ff, b.ff2, residual=h)
     if t.linear_proj:
@@ -447,17 +527,47 @@ class UNetEngine:
         self._temb_w = torch.cat([r.temb.w for r in self._res_all], 0).contiguous()
         self._temb_b = torch.cat([r.temb.bias for r in self._res_all], 0).contiguous()
         self.loras: List[LoRAW] = []
+        self._attns: List[_Attn] = []
+        self._cross_attns: List[_Attn] = []
         for blocks in [self.down, [(self.mid[0], self.mid[1], None)], self.up]:
             for _, attns, _ in blocks:
                 for t in attns or []:
                     for b in t.blocks:
+                        self._cross_attns.append(b.a2)
                         for a in (b.a1, b.a2):
+                            self._attns.append(a)
                             self.loras.extend(l for l in a.loras if l is not None)
+        self.lora_version, self._merged_version, self._merged_t = 0, -1, False
 
     # ---- LoRA plumbing
     def refresh_lora(self):
         for l in self.loras:
             l.refresh()
+        self.lora_version += 1                 # folded weights / cached context projections are stale now
+
+    def ensure_merged(self, transposed: bool = False):
+        """(re)build the LoRA-folded projection weights if the LoRA parameters changed since the last build.  Runs eagerly
+        (never inside a CUDA-graph capture: callers invoke it before capturing / replaying)."""
+        if self._merged_version != self.lora_version:
+            for a in self._attns:
+                a.refresh_merged(transposed or self._merged_t)
+            self._merged_version, self._merged_t = self.lora_version, transposed or self._merged_t
+        elif transposed and not self._merged_t:
+            for a in self._attns:
+                a.refresh_merged(True)
+            self._merged_t = True
+
+    def cross_kv(self, ctx16: torch.Tensor, out=None):
+        """k|v projections of the text context for every cross-attention layer: {id(layer): (n, T, 2C)}.  The context and
+        the (folded) weights are the same for all UNet calls between two optimiser steps, so callers cache the result."""
+        self.ensure_merged()
+        n, T, D = ctx16.shape
+        c2 = ctx16.reshape(n * T, D)
+        res = {}
+        for a in self._cross_attns:
+            o = None if out is None else out[id(a)].reshape(n * T, 2 * a.q.n)
+            res[id(a)] = ops.gemm([c2], [a.w_kv], bias=a.b_kv, out=o).reshape(n, T, 2 * a.q.n)
+        return res
 
     def set_lora_wgrad(self, flag: bool):
         for l in self.loras:
@@ -486,10 +596,17 @@ class UNetEngine:
         return ops.elementwise("silu", e.to(self.dtype))
 
     def forward(self, tape: Optional[Tape], x: Var, t: torch.Tensor, ctx: torch.Tensor, capture: Optional[AttnCapture] = None,
-                added_cond=None) -> Var:
+                added_cond=None, lora_mode: Optional[str] = None, cross_kv=None) -> Var:
         """x: Var of NHWC 16-bit latents zero-padded to 64 channels (n, h, w, 64); ctx: (n, 77, D) 16-bit.
+        ``lora_mode``: 'train' (explicit LoRA branch, weight gradients), 'frozen' (taped, LoRA folded into the weights) or
+        'merged' (no tape, folded + fused projections; default without a tape).  ``cross_kv``: cached ``self.cross_kv(ctx)``.
         returns Var (n, h, w, 4)."""
         n = x.v.shape[0]
+        mode = lora_mode or ("train" if tape is not None else "merged")
+        if mode == "merged" and tape is not None:
+            mode = "frozen"
+        if mode != "train":
+            self.ensure_merged(transposed=tape is not None)
         temb16 = self.temb(t, n, added_cond)
         allp = ops.gemm([temb16], [self._temb_w], bias=self._temb_b, out_fp32=True)       # (n, sum Cout) fp32
         temb, off = {}, 0
@@ -503,19 +620,19 @@ class UNetEngine:
             for i, r in enumerate(resnets):
                 h = _resnet(tape, r, h, temb)
                 if attns is not None:
-                    h = _transformer(tape, attns[i], h, cvar, capture, "down")
+                    h = _transformer(tape, attns[i], h, cvar, capture, "down", mode, cross_kv)
                 skips.append(h)
             if ds is not None:
                 h = conv(tape, [h], ds)
                 skips.append(h)
         h = _resnet(tape, self.mid[0][0], h, temb)
-        h = _transformer(tape, self.mid[1][0], h, cvar, capture, "mid")
+        h = _transformer(tape, self.mid[1][0], h, cvar, capture, "mid", mode, cross_kv)
         h = _resnet(tape, self.mid[0][1], h, temb)
         for resnets, attns, us in self.up:
             for i, r in enumerate(resnets):
                 h = _resnet(tape, r, h, temb, skip=skips.pop())
                 if attns is not None:
-                    h = _transformer(tape, attns[i], h, cvar, capture, "up")
+                    h = _transformer(tape, attns[i], h, cvar, capture, "up", mode, cross_kv)
             if us is not None:
                 h = conv(tape, [upsample2x(tape, h)], us)
         h = groupnorm(tape, h, self.norm_out, True)

@@ -23,7 +23,10 @@ class _UNetFn(torch.autograd.Function):
         eng = mod.engine
         tape = E.Tape()
         xv = E.Var(ops.latent_to_nhwc(x, eng.dtype, 64), needs_grad=ctx.needs_input_grad[1])
-        out = eng.forward(tape, xv, t, ehs.to(eng.dtype), capture=capture, added_cond=added)
+        ctx.wgrad = bool(mod.train_lora and any(p.requires_grad for p in lora_params))
+        # no LoRA weight gradient wanted (the discriminator's generator-side pass, gan_sdxl.py:52-89): LoRA folded into the weights
+        out = eng.forward(tape, xv, t, ehs.to(eng.dtype), capture=capture, added_cond=added,
+                          lora_mode="train" if ctx.wgrad else "frozen")
         eps = ops.nhwc_to_nchw_f32(out.v, mod.out_channels)
         pvars = []
         if capture is not None:
@@ -31,7 +34,6 @@ class _UNetFn(torch.autograd.Function):
                 pvars.extend(capture.store[place])
         ctx.tape, ctx.xv, ctx.out, ctx.pvars, ctx.mod = tape, xv, out, pvars, mod
         ctx.x_dtype = x.dtype
-        ctx.wgrad = bool(mod.train_lora and any(p.requires_grad for p in lora_params))
         return (eps.to(x.dtype), *[p.v for p in pvars])
 
     @staticmethod
@@ -62,13 +64,18 @@ class _GraphedForward:
     def __init__(self, mod: "EngineUNet", sample, t, ehs):
         from . import _lib
         eng = mod.engine
+        self.mod = mod
         self.x = torch.empty_like(sample)
         self.t = torch.zeros((), dtype=torch.int64, device=sample.device)
-        self.ehs = torch.empty_like(ehs)
-        self.x.copy_(sample); self.t.copy_(t.reshape(())); self.ehs.copy_(ehs)
+        self.x.copy_(sample); self.t.copy_(t.reshape(()))
+        # the text context and its per-layer k|v projections are graph INPUTS (static buffers refreshed only when the
+        # caller's context tensor or the LoRA weights change): the 32 context GEMMs are not part of the replayed work
+        self.ehs16 = ehs.to(eng.dtype).contiguous()
+        self.kv = eng.cross_kv(self.ehs16)
+        self._key = (ehs, ehs._version, eng.lora_version)
 
         def run():
-            out = eng.forward(None, E.Var(ops.latent_to_nhwc(self.x, eng.dtype, 64), False), self.t, self.ehs.to(eng.dtype))
+            out = eng.forward(None, E.Var(ops.latent_to_nhwc(self.x, eng.dtype, 64), False), self.t, self.ehs16, cross_kv=self.kv)
             return ops.nhwc_to_nchw_f32(out.v, mod.out_channels)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -83,7 +90,13 @@ class _GraphedForward:
 
     def __call__(self, sample, t, ehs):
         from . import _lib
-        self.x.copy_(sample); self.t.copy_(t.reshape(())); self.ehs.copy_(ehs)
+        eng = self.mod.engine
+        eng.ensure_merged()                                   # eager, before the replay reads the folded weights
+        self.x.copy_(sample); self.t.copy_(t.reshape(()))
+        if not (self._key[0] is ehs and self._key[1] == ehs._version and self._key[2] == eng.lora_version):
+            self.ehs16.copy_(ehs)
+            eng.cross_kv(self.ehs16, out=self.kv)
+            self._key = (ehs, ehs._version, eng.lora_version)
         self.graph.replay()
         _lib.count_launch(self.launches)
         return self.out.clone()
@@ -107,6 +120,7 @@ class EngineUNet(torch.nn.Module):
         self.grad_scale = 4096.0 if dtype == torch.float16 else 1.0   # power of two: exact scale / unscale around the 16-bit backward
         self.use_graphs = False                # bench / trainer switch: CUDA-graph the no-grad forwards of the rollout
         self._graphs = {}
+        self._kv_key, self._kv_val = None, None   # cached 16-bit context + per-layer k|v projections (eager no-grad path)
 
     @property
     def dtype(self):
@@ -122,6 +136,20 @@ class EngineUNet(torch.nn.Module):
     def refresh_lora(self):
         """call after every optimiser step: re-materialise the 16-bit LoRA operands from the fp32 masters."""
         self.engine.refresh_lora()
+
+    def _context_kv(self, ehs):
+        """16-bit text context and its k|v projections for every cross-attention layer, cached while the caller keeps passing
+        the SAME tensor object (unmodified: ``_version``) and the LoRA weights are unchanged - true for every step of a
+        rollout (TrainableSDPipeline.py:132-150 passes one ``prompt_embeds`` to all S UNet calls).  The key holds a
+        reference to the tensor, so its storage cannot be recycled under the cache."""
+        eng = self.engine
+        k = self._kv_key
+        if k is not None and k[0] is ehs and k[1] == ehs._version and k[2] == eng.lora_version:
+            return self._kv_val
+        ctx16 = ehs.detach().to(eng.dtype).contiguous()
+        self._kv_val = (ctx16, eng.cross_kv(ctx16))
+        self._kv_key = (ehs, ehs._version, eng.lora_version)
+        return self._kv_val
 
     def enable_gradient_checkpointing(self):
         pass                                  # never recomputes: activations of K steps fit in 180 GB (DESIGN.md)
@@ -140,13 +168,15 @@ class EngineUNet(torch.nn.Module):
         elif self.use_graphs and capture is None and added_cond_kwargs is None and sample.is_cuda:
             key = (tuple(sample.shape), tuple(encoder_hidden_states.shape), sample.dtype, encoder_hidden_states.dtype)
             if key not in self._graphs:
-                self._graphs[key] = _GraphedForward(self, sample.detach(), t, encoder_hidden_states.detach())
-            eps = self._graphs[key](sample.detach(), t, encoder_hidden_states.detach()).to(sample.dtype)
+                self.engine.ensure_merged()
+                self._graphs[key] = _GraphedForward(self, sample.detach(), t, encoder_hidden_states)
+            eps = self._graphs[key](sample.detach(), t, encoder_hidden_states).to(sample.dtype)
             probs = ()
         else:
             eng = self.engine
+            ctx16, kv = self._context_kv(encoder_hidden_states)
             out = eng.forward(None, E.Var(ops.latent_to_nhwc(sample, eng.dtype, 64), False), t,
-                              encoder_hidden_states.to(eng.dtype), capture=capture, added_cond=added_cond_kwargs)
+                              ctx16, capture=capture, added_cond=added_cond_kwargs, cross_kv=kv)
             eps = ops.nhwc_to_nchw_f32(out.v, self.out_channels).to(sample.dtype)
             probs = ()
         if capture is not None:

@@ -125,7 +125,7 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.check(_lib.lib().comat_gemm(C.byref(p), _lib.stream_ptr()), "gemm")
-    _lib.count_launch()
+    _lib.count_launch(2 if split_k > 1 else 1)          # split-K adds the fixed-order reduction kernel
     if PROFILE is not None:
         if "keys_only" in PROFILE:
             e0 = e1 = None
@@ -183,7 +183,7 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.check(_lib.lib().comat_gemm(C.byref(p), _lib.stream_ptr()), "gemm_tn")
-    _lib.count_launch()
+    _lib.count_launch(2 if split_k > 1 else 1)
     if PROFILE is not None:
         if timed:
             e1.record()
@@ -232,7 +232,7 @@ def groupnorm_fwd(x, gamma, beta, G, eps, silu):
     y = torch.empty_like(x)
     mr = torch.empty(n * G * 2, dtype=torch.float32, device=x.device)
     _call("comat_groupnorm_fwd", x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mr.data_ptr(),
-          _gn_ws(n, HW, G, x.device).data_ptr(), n, HW, C_, G, eps, int(silu), DT[x.dtype], _lib.stream_ptr(), launches=3)
+          _gn_ws(n, HW, G, x.device).data_ptr(), n, HW, C_, G, eps, int(silu), DT[x.dtype], _lib.stream_ptr(), launches=2)
     return y, mr
 
 
@@ -242,7 +242,7 @@ def groupnorm_bwd(x, dy, gamma, beta, mr, G, silu):
     HW = x.numel() // (n * C_)
     dx = torch.empty_like(x)
     _call("comat_groupnorm_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mr.data_ptr(),
-          _gn_ws(n, HW, G, x.device).data_ptr(), n, HW, C_, G, int(silu), DT[x.dtype], _lib.stream_ptr(), launches=3)
+          _gn_ws(n, HW, G, x.device).data_ptr(), n, HW, C_, G, int(silu), DT[x.dtype], _lib.stream_ptr(), launches=2)
     return dx
 
 

@@ -203,6 +203,12 @@ size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d);
 /* kv_lens: optional int32[n] valid-key counts (padding mask); causal != 0: key index <= query index. */
 int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, float* probs, float* lse, void* workspace,
                         int n, int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal, void* stream);
+/* Same, with explicit row pitches (elements) for q, k and v: the operands may be column slices of a wider matrix, e.g.
+ * the (tokens, 3*H*d) output of one fused q|k|v projection GEMM (to_q/to_k/to_v of tc_attn_utils.py:113-121 share their
+ * input for self-attention) or the cached k|v projection of the text context.  Pitches must be multiples of 8. */
+int comat_attention_fwd_strided(const void* q, const void* k, const void* v, void* out, float* probs, float* lse,
+                                void* workspace, int n, int Lq, int Lk, int H, int d, long long q_ld, long long k_ld,
+                                long long v_ld, float scale, int dtype, const int* kv_lens, int causal, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused classifier-free guidance + DDPM ancestral step on the fp32 latent chain.

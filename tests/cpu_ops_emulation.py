@@ -42,6 +42,9 @@ def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_grou
     if residual is not None:
         y = y + residual.reshape(M, N).double()
     y = y.to(torch.float32 if out_fp32 else a0.dtype)
+    if out is not None:
+        out.reshape(M, N).copy_(y)          # in-place destination (row-slice views of fused weight buffers, static graph inputs)
+        y = out
     if conv_taps is not None:
         return y.reshape(n, H, W, N)
     return y

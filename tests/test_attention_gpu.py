@@ -36,6 +36,28 @@ def test_attention_forward(n, Lq, Lk, H, d, dtype, tol):
     assert rel(lse, lse_ref) < 1e-3
 
 
+@pytest.mark.parametrize("n,L,T,H,d", [(2, 1024, 77, 8, 40), (2, 256, 77, 8, 80), (1, 300, 77, 10, 64), (2, 64, 77, 8, 160)])
+def test_attention_forward_reads_fused_projection_slices_in_place(n, L, T, H, d):
+    """q|k|v column slices of one (tokens, 3C) projection output (self-attention) and k|v slices of the cached (n*T, 2C)
+    context projection (cross-attention) go to the kernel with their row pitch - results equal the contiguous call."""
+    from comat_b200 import attention as A
+    torch.manual_seed(L + d)
+    C = H * d
+    qkv = torch.randn(n, L, 3 * C, device="cuda").half()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    assert A._rows(k)[1] == 3 * C and A._rows(k)[0].data_ptr() == k.data_ptr()
+    o, _, lse = A.attention_fwd_native(q, k, v, H, need_lse=True)
+    o2, _, lse2 = A.attention_fwd_native(q.contiguous(), k.contiguous(), v.contiguous(), H, need_lse=True)
+    assert torch.equal(o, o2) and torch.equal(lse, lse2)
+    o_ref, _, _ = ref_attn(q, k, v, H)
+    assert rel(o.float(), o_ref) < 3e-3
+    kv = torch.randn(n, T, 2 * C, device="cuda").half()
+    qc = torch.randn(n, L, C, device="cuda").half()
+    o, p, _ = A.attention_fwd_native(qc, kv[..., :C], kv[..., C:], H, export_probs=True)
+    o2, p2, _ = A.attention_fwd_native(qc, kv[..., :C].contiguous(), kv[..., C:].contiguous(), H, export_probs=True)
+    assert torch.equal(o, o2) and torch.equal(p, p2)
+
+
 @pytest.mark.parametrize("n,HW,H,d", [(2, 4096, 8, 40), (2, 1024, 8, 80), (3, 256, 8, 160), (2, 64, 8, 160), (2, 256, 10, 64)])
 def test_cross_attention_with_probability_export(n, HW, H, d):
     """UNet cross-attention: 77 text tokens, P exported fp32 (n*H, HW, 77) — rows sum to 1, match the reference softmax."""

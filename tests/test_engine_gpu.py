@@ -98,3 +98,81 @@ def test_vae_decoder_engine_fwd_bwd_vs_oracle():
     tape.backward()
     dz = ops.nhwc_to_nchw_f32(zv.g, 4, 1.0 / vae.config.scaling_factor)
     assert rel(dz, gref) < 3e-2
+
+
+@pytest.mark.parametrize("sdxl", [False, True])
+def test_unet_engine_folded_lora_modes_vs_oracle(sdxl):
+    """'merged' (no tape: LoRA folded into the weights, fused q|k|v / k|v GEMMs, cached context projections) and 'frozen'
+    (taped, data gradient only) against the fp32 oracle's explicit-LoRA module; a LoRA update invalidates the folded weights."""
+    from comat_b200 import engine as E, ops
+    unet, _ = _tiny(sdxl)
+    dtype, tol = torch.float16, 8e-3
+    eng = E.UNetEngine(unet, dtype)
+    g = torch.Generator().manual_seed(2)
+    n, hw = 2, 32
+    x = torch.randn(n, 4, hw, hw, generator=g).cuda()
+    ctx = torch.randn(n, 77, 64, generator=g).cuda()
+    added = dict(text_embeds=torch.randn(n, 16, generator=g).cuda(),
+                 time_ids=torch.tensor([[512., 512, 0, 0, 512, 512]] * n).cuda()) if sdxl else None
+    kw = dict(added_cond_kwargs=added) if sdxl else {}
+    t = torch.tensor(501, device="cuda")
+    dy = torch.randn(n, 4, hw, hw, generator=g).cuda()
+    xr = x.clone().requires_grad_(True)
+    ref = unet(xr, t, ctx, return_dict=False, **kw)[0]
+    gx_ref = torch.autograd.grad(ref, xr, dy)[0]
+    ctx16 = ctx.to(dtype)
+    out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, dtype, 64), False), t, ctx16, added_cond=added)
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), ref) < tol
+    out_kv = eng.forward(None, E.Var(ops.latent_to_nhwc(x, dtype, 64), False), t, ctx16, added_cond=added, cross_kv=eng.cross_kv(ctx16))
+    assert rel(out_kv.v, out.v) < 2e-3          # not bitwise: GroupNorm partial sums use shared-memory float atomics
+    tape = E.Tape()
+    xv = E.Var(ops.latent_to_nhwc(x, dtype, 64))
+    outf = eng.forward(tape, xv, t, ctx16, added_cond=added, lora_mode="frozen")
+    assert rel(ops.nhwc_to_nchw_f32(outf.v, 4), ref) < tol
+    outf.g = dy.permute(0, 2, 3, 1).contiguous().to(dtype)
+    eng.zero_lora_grads()
+    tape.backward()
+    assert rel(ops.nhwc_to_nchw_f32(xv.g, 4), gx_ref) < 3 * tol
+    assert all(gr is None for gr in eng.lora_grads())
+    with torch.no_grad():
+        for p in eng.lora_params():
+            p.mul_(1.5)
+    eng.refresh_lora()
+    ref2 = unet(x, t, ctx, return_dict=False, **kw)[0]
+    assert rel(ref2, ref) > 2 * tol
+    out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, dtype, 64), False), t, ctx16, added_cond=added)
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), ref2) < tol
+
+
+def test_engine_unet_module_graph_and_eager_share_context_cache():
+    """EngineUNet no-grad call: CUDA-graph replay and eager execution agree; the cached context projections follow the
+    caller's tensor (identity + in-place version) and the LoRA version."""
+    from comat_b200.modules import EngineUNet
+    unet, _ = _tiny()
+    mod = EngineUNet(unet, torch.float16)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 32, 32, generator=g).cuda()
+    ctx = torch.randn(2, 77, 64, generator=g).cuda()
+    ctx_b = torch.randn(2, 77, 64, generator=g).cuda()
+    t = torch.tensor(301, device="cuda")
+    with torch.no_grad():
+        e0 = mod(x, t, encoder_hidden_states=ctx)[0].clone()
+        e0b = mod(x, t, encoder_hidden_states=ctx_b)[0].clone()
+        mod.use_graphs = True
+        assert rel(e0b, e0) > 5e-2
+        for c, want in ((ctx, e0), (ctx, e0), (ctx_b, e0b), (ctx, e0)):
+            assert rel(mod(x, t, encoder_hidden_states=c)[0], want) < 2e-3
+        ctx.mul_(0.5)                                       # in-place edit of the caller's tensor: version changes
+        e1 = mod(x, t, encoder_hidden_states=ctx)[0].clone()
+        mod.use_graphs = False
+        assert rel(mod(x, t, encoder_hidden_states=ctx)[0], e1) < 2e-3
+        assert rel(e1, e0) > 2e-2
+        for p in mod.lora_parameters():
+            p.mul_(1.5)
+        mod.refresh_lora()
+        e2 = mod(x, t, encoder_hidden_states=ctx)[0].clone()
+        mod.use_graphs = True
+        assert rel(mod(x, t, encoder_hidden_states=ctx)[0], e2) < 2e-3
+        assert rel(e2, e1) > 2e-2
+    ref = unet(x, t, ctx, return_dict=False)[0]
+    assert rel(e2, ref) < 8e-3

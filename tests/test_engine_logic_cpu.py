@@ -72,3 +72,55 @@ def test_vae_executor_matches_oracle(monkeypatch):
     out.g = dy.permute(0, 2, 3, 1).contiguous()
     tape.backward()
     assert rel(ops.nhwc_to_nchw_f32(zv.g, 4, 1.0 / vae.config.scaling_factor), gref) < 1e-4
+
+
+@pytest.mark.parametrize("sdxl", [False, True])
+def test_unet_merged_lora_modes_match_oracle(monkeypatch, sdxl):
+    """LoRA folded into the projection weights: 'merged' (no tape: fused q|k|v and k|v GEMMs, cached context projections)
+    and 'frozen' (taped, data gradients only - the discriminator's generator-side pass, gan_sdxl.py:52-89) must equal
+    the oracle's explicit-LoRA forward / input gradient; a LoRA update must invalidate the folded weights."""
+    EMU.install(monkeypatch)
+    from comat_b200 import engine as E, ops
+    unet = _tiny(sdxl)
+    dtype = torch.float32
+    eng = E.UNetEngine(unet, dtype)
+    g = torch.Generator().manual_seed(1)
+    n, hw = 2, 16
+    x = torch.randn(n, 4, hw, hw, generator=g)
+    ctx = torch.randn(n, 77, 64, generator=g)
+    added = dict(text_embeds=torch.randn(n, 16, generator=g), time_ids=torch.tensor([[512., 512, 0, 0, 512, 512]] * n)) if sdxl else None
+    kw = dict(added_cond_kwargs=added) if sdxl else {}
+    t = torch.tensor(500)
+    dy = torch.randn(n, 4, hw, hw, generator=g)
+    xr = x.clone().requires_grad_(True)
+    out_ref = unet(xr, t, ctx, return_dict=False, **kw)[0]
+    gx_ref = torch.autograd.grad(out_ref, xr, dy)[0]
+    # merged, context projections computed inside the call
+    cap = E.AttnCapture(["up_8", "up_16"])
+    out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, dtype, 64), False), t, ctx, capture=cap, added_cond=added)
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), out_ref) < 1e-4
+    assert cap.count == len(unet.attn_processors)
+    # merged, with the cached per-layer k|v of the context
+    kv = eng.cross_kv(ctx)
+    assert len(kv) == len(unet.attn_processors) // 2
+    out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, dtype, 64), False), t, ctx, added_cond=added, cross_kv=kv)
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), out_ref) < 1e-4
+    # frozen: taped, folded weights, input gradient only
+    tape = E.Tape()
+    xv = E.Var(ops.latent_to_nhwc(x, dtype, 64))
+    out = eng.forward(tape, xv, t, ctx, added_cond=added, lora_mode="frozen")
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), out_ref) < 1e-4
+    out.g = dy.permute(0, 2, 3, 1).contiguous()
+    eng.zero_lora_grads()
+    tape.backward()
+    assert rel(ops.nhwc_to_nchw_f32(xv.g, 4), gx_ref) < 1e-4
+    assert all(gr is None for gr in eng.lora_grads())
+    # a LoRA update (optimiser step + refresh_lora) must be seen by the folded weights and the cached projections
+    with torch.no_grad():
+        for p in eng.lora_params():
+            p.mul_(1.5)
+    eng.refresh_lora()
+    out_ref2 = unet(x, t, ctx, return_dict=False, **kw)[0]
+    assert rel(out_ref2, out_ref) > 1e-3
+    out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, dtype, 64), False), t, ctx, added_cond=added, cross_kv=eng.cross_kv(ctx))
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), out_ref2) < 1e-4
