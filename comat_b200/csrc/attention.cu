@@ -1,25 +1,32 @@
 // Fused multi-head attention forward on tcgen05:  O = softmax(scale * Q K^T) V  per (sample, head), flash-style
-// (online softmax over 128-key tiles; S and the per-tile P.V product live in TMEM), with
-//   * optional export of the normalised fp32 probabilities when all keys fit one tile (UNet cross-attention, 77 text
+// (online softmax over 64-key tiles; S and the running P.V product live in TMEM), with
+//   * optional export of the normalised fp32 probabilities when all keys fit two tiles (UNet cross-attention, 77 text
 //     tokens): this is the tensor the reference's hooked Attention.forward hands to AttentionStore
 //     (attn_utils/tc_attn_utils.py:126-145, :60-68) — written once, never re-read by this kernel;
 //   * the log-sum-exp per row saved for the backward pass.
 // Replaces F.scaled_dot_product_attention / baddbmm+softmax+bmm of diffusers' Attention and HF BLIP's eager attention.
 //
-// Layout: q, k, v (n, L, H*d) 16-bit token-major (the projection GEMMs' natural output), read as they lie: a [128 keys][d]
-// tile of V lands in smem as 128-byte-swizzled rows, which is the canonical MN-major B operand of the P.V product
-// (reduction over the 128 key rows) - no V^T copy exists.
-// Head dims that are not multiples of 64 (40, 80, 160) are handled by a 3-D tensor map {d, H, rows}: the TMA box is 64
-// wide and elements past d are out-of-bounds -> zero-filled, so no padded copies of Q/K exist.
+// Layout: q, k, v (n, L, H*d) 16-bit token-major (the projection GEMMs' natural output, or column slices of a fused
+// q|k|v projection: row pitches are parameters), read as they lie: a [64 keys][d] tile of V lands in smem as
+// 128-byte-swizzled rows, which is the canonical MN-major B operand of the P.V product (reduction over the key rows) -
+// no V^T copy exists.  Head dims that are not multiples of 64 (40, 80, 160) are handled by a 3-D tensor map {d, H, rows}:
+// the TMA box is 64 wide and elements past d are out-of-bounds -> zero-filled, so no padded copies of Q/K exist.
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 softmax / epilogue
 // (one thread per query row: row max / sum need no shuffles).
+//
+// Pipeline (r01 v6).  The UNet's 64x64-latent self-attention has d = 40: 160 tensor FLOPs per exponential, so the kernel is
+// bound by the SFU (16 ex2/clk/SM), not the tensor pipe.  The first version kept ONE score tile in TMEM, so every key tile
+// was a serial chain  Q.K^T -> softmax -> P.V -> next Q.K^T  and the softmax warps idled for the MMA round trip each tile
+// (ncu: XU pipe 55 % busy, profiles/r01_attn_fwd40_ncu_v5.md).  Now S and P are double-buffered: Q.K^T of tile j+1 is
+// issued BEFORE P.V of tile j, so scores are always waiting when the softmax warps finish a tile.  64-key tiles keep that
+// within 256 TMEM columns (S0 | S1 | O) and 96 KB of smem for d <= 64, i.e. two CTAs (8 softmax warps) per SM.
 #include "tc_common.cuh"
 
 namespace comat {
 
 constexpr int ATT_BM = 128;   // queries per CTA
-constexpr int ATT_BN = 128;   // keys per tile
+constexpr int ATT_BN = 64;    // keys per tile
 constexpr int ATT_THREADS = 192;
 
 struct AttnKP {
@@ -28,7 +35,7 @@ struct AttnKP {
   float scale_log2;    // scale * log2(e)
   float scale;
   void* out;           // (n, Lq, H*d) 16-bit
-  float* probs;        // (n*H, Lq, Lk) fp32 or null (requires n_kv_tiles == 1)
+  float* probs;        // (n*H, Lq, Lk) fp32 or null (requires n_kv_tiles <= 2)
   float* lse;          // (n*H, Lq) fp32 or null
   long long out_ld;    // H*d
   uint32_t idesc_qk, idesc_pv;
@@ -44,14 +51,15 @@ struct AttnCfg {
   static constexpr int KSTEPS_QK = (D + 15) / 16;           // 16-wide k-steps actually issued
   static constexpr int Q_BYTES = NKC * ATT_BM * 128;
   static constexpr int K_BYTES = NKC * ATT_BN * 128;
-  static constexpr int V_BYTES = K_BYTES;                   // same [128 keys][NKC x 64] tile shape as K
+  static constexpr int V_BYTES = K_BYTES;                   // same [64 keys][NKC x 64] tile shape as K
   static constexpr int KV_STAGE = K_BYTES + V_BYTES;
-  static constexpr int P_BYTES = 2 * ATT_BM * 128;          // two 64-key halves
-  static constexpr int STAGES = (D > 128) ? 1 : 2;
-  static constexpr int BAR_OFF = Q_BYTES + STAGES * KV_STAGE + P_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 128;               // dynamic smem is declared 1024-B aligned (checked in-kernel)
+  static constexpr int P_BYTES = ATT_BM * 128;              // one buffer: [128 rows][64 keys] 16-bit = one swizzle row per query
+  static constexpr int STAGES = 3;                          // tile j+1 loads while tile j is in use and tile j-1 drains
+  static_assert(Q_BYTES + 3 * KV_STAGE + 2 * ATT_BM * 128 + 256 <= 232448, "attention smem budget");
+  static constexpr int BAR_OFF = Q_BYTES + STAGES * KV_STAGE + 2 * P_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256;               // dynamic smem is declared 1024-B aligned (checked in-kernel)
   static constexpr int TMEM_COLS = (128 + DN) <= 256 ? 256 : 512;
-  static constexpr int O_COL = 128;                         // S at columns [0,128), O tile at [128, 128+DN)
+  static constexpr int O_COL = 128;                         // S buffers at columns [0,64) and [64,128), O tile at [128, 128+DN)
 };
 
 template <typename T>
@@ -68,7 +76,7 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
 }
 
 template <int D, typename T>
-__global__ void __launch_bounds__(ATT_THREADS, (D <= 64) ? 2 : 1)     // d <= 64: two CTAs per SM (smem 112 KB, TMEM 256 columns each)
+__global__ void __launch_bounds__(ATT_THREADS, (D <= 64) ? 2 : 1)     // d <= 64: two CTAs per SM (smem 96 KB, TMEM 256 columns each)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnKP p) {
   pdl_trigger();
@@ -78,15 +86,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzled tiles need 1024-B alignment; d <= 64 leaves no slack (2 CTAs / SM)
   unsigned char* sQ = smem;
   unsigned char* sKV = smem + Cf::Q_BYTES;
-  unsigned char* sP = sKV + Cf::STAGES * Cf::KV_STAGE;
+  unsigned char* sP = sKV + Cf::STAGES * Cf::KV_STAGE;            // two P buffers
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cf::BAR_OFF);
   uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // STAGES
-  uint64_t* kv_empty = bars + 3;      // STAGES
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;       // [3]
+  uint64_t* kv_empty = bars + 4;      // [3]
+  uint64_t* s_full = bars + 7;        // [2] scores of tile j in S buffer j & 1
+  uint64_t* p_full = bars + 9;        // [2] probabilities of tile j in P buffer j & 1 (128 arrivals)
+  uint64_t* pv_done = bars + 11;      // [2] P.V of tile j complete: P buffer j & 1 reusable, O consistent
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * ATT_BM;
@@ -97,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < Cf::STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, Cf::TMEM_COLS); tmem_relinquish(); }
@@ -128,40 +136,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      auto issue_qk = [&](int stage) {
+      // S_j = Q K_j^T into S buffer j & 1
+      auto issue_qk = [&](int stage, int sbuf) {
         const uint32_t aK = smem_u32(sKV + stage * Cf::KV_STAGE);
 #pragma unroll
         for (int ks = 0; ks < Cf::KSTEPS_QK; ++ks) {
-          const uint32_t off = (uint32_t)(ks / 4) * (ATT_BM * 128) + (uint32_t)(ks % 4) * 32;
-          umma_f16(tmem_base, make_kmajor_sw128_desc(aQ + off), make_kmajor_sw128_desc(aK + off), p.idesc_qk, ks > 0 ? 1u : 0u);
+          const uint32_t offq = (uint32_t)(ks / 4) * (ATT_BM * 128) + (uint32_t)(ks % 4) * 32;
+          const uint32_t offk = (uint32_t)(ks / 4) * (ATT_BN * 128) + (uint32_t)(ks % 4) * 32;
+          umma_f16(tmem_base + (uint32_t)(sbuf * ATT_BN), make_kmajor_sw128_desc(aQ + offq), make_kmajor_sw128_desc(aK + offk),
+                   p.idesc_qk, ks > 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[sbuf]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      issue_qk(0);
-      int stage = 0, phase = 0;
+      issue_qk(0, 0);
+      int stage = 0, phase = 0;                  // ring position of tile j
       for (int j = 0; j < NT; ++j) {
-        mbar_wait(p_full, j & 1);                 // P_j is in smem (and S_j has been fully read)
+        int nstage = stage + 1, nphase = phase;
+        if (nstage == Cf::STAGES) { nstage = 0; nphase ^= 1; }
+        if (j + 1 < NT) {
+          // scores of the NEXT tile first: S buffer (j+1)&1 was last read by the softmax of tile j-1, whose p_full this
+          // thread has already observed; the softmax warps find them ready when they finish tile j
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          issue_qk(nstage, (j + 1) & 1);
+        }
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);          // P_j is in smem
         tc_fence_after();
         const uint32_t aV = smem_u32(sKV + stage * Cf::KV_STAGE + Cf::K_BYTES);
+        const uint32_t aPj = aP + (uint32_t)(j & 1) * Cf::P_BYTES;
 #pragma unroll
         for (int ks = 0; ks < ATT_BN / 16; ++ks) {
-          const uint32_t offp = (uint32_t)(ks / 4) * (ATT_BM * 128) + (uint32_t)(ks % 4) * 32;
           // V tile read MN-major: 16 key rows = 2048 B per k-step, d-panels ATT_BN*128 B apart
-          umma_f16(tmem_base + Cf::O_COL, make_kmajor_sw128_desc(aP + offp),
+          umma_f16(tmem_base + Cf::O_COL, make_kmajor_sw128_desc(aPj + (uint32_t)ks * 32),
                    make_mnmajor_sw128_desc(aV + (uint32_t)ks * 2048, ATT_BN * 128), p.idesc_pv,
                    (j > 0 || ks > 0) ? 1u : 0u);      // O accumulates in TMEM across key tiles
         }
-        umma_commit(o_full);
+        umma_commit(&pv_done[j & 1]);
         umma_commit(&kv_empty[stage]);
-        if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
-        if (j + 1 < NT) {
-          mbar_wait(&kv_full[stage], phase);
-          tc_fence_after();
-          issue_qk(stage);
-        }
+        stage = nstage; phase = nphase;
       }
     }
     __syncwarp();
@@ -169,7 +184,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ---------------- softmax + epilogue: thread = query row ----------------
     // O accumulates in TMEM across key tiles (the P.V MMAs run with accumulate on); the running row maximum is only
     // refreshed when some row of the warp grew by more than 2^8 (in the exp2 domain), so the TMEM read-scale-write of O
-    // is rare after the first tiles and exp2 arguments stay <= 8.  The 128 scores of a row are read from TMEM once and
+    // is rare after the first tiles and exp2 arguments stay <= 8.  The 64 scores of a row are read from TMEM once and
     // kept in registers for the max and the exponentials.
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
@@ -180,17 +195,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sl2 = p.scale_log2;
 
     for (int j = 0; j < NT; ++j) {
-      mbar_wait(s_full, j & 1);                   // S_j complete; the tensor pipe is in order, so P.V_{j-1} is complete too
+      const int sb = j & 1;
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
       const int ktile = min(ATT_BN, klen - j * ATT_BN);                       // warp-uniform
       const int kvalid = p.causal ? min(ktile, m0 + r - j * ATT_BN + 1) : ktile;   // per-row limit
-      // warp-uniform: every row of this warp sees all 128 keys of the tile -> no masking
+      // warp-uniform: every row of this warp sees all keys of the tile -> no masking
       const bool full_w = (ktile == ATT_BN) && (!p.causal || (m0 + q4 * 32 - j * ATT_BN + 1 >= ATT_BN));
       float sv[ATT_BN];
 #pragma unroll
       for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+        tmem_ld_32x32b_x32(trow + (uint32_t)(sb * ATT_BN + c0), v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) sv[c0 + i] = __uint_as_float(v[i]);
       }
@@ -215,6 +231,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float alpha = (m_new == -INFINITY) ? 1.f : fast_exp2((m_run - m_new) * sl2);
           l_run *= alpha;
           m_run = m_new;
+          // P.V of tile j-1 may still be accumulating into O (its Q.K^T successor was issued ahead of it): wait for it.
+          // P.V of tile j cannot start before this thread's p_full arrival below.
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
 #pragma unroll
           for (int c0 = 0; c0 < Cf::DN; c0 += 16) {
             uint32_t v[16];
@@ -228,8 +248,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       const float mneg = (m_run == -INFINITY) ? 0.f : m_run * sl2;
-      // p = exp2(s*sl2 - m*sl2), row sum, 16-bit P into swizzled smem (K-major, two 64-key halves)
+      // P buffer sb was last read by P.V of tile j-2
+      if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
+      // p = exp2(s*sl2 - m*sl2), row sum, 16-bit P into swizzled smem (K-major: one 128-byte row of 64 keys per query)
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      unsigned char* prow = sP + sb * Cf::P_BYTES + (r / 8) * 1024 + (r % 8) * 128;
 #pragma unroll
       for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
         uint32_t pk[16];
@@ -240,22 +263,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ls[(i / 2) & 3] += e0 + e1;
           pk[i / 2] = pack2<T>(e0, e1);
         }
-        // 32 keys = 4 x 16-byte chunks of row r in half (c0/64): chunk index cc = (c0%64)/8 + q
-        unsigned char* base = sP + (c0 / 64) * (ATT_BM * 128) + (r / 8) * 1024 + (r % 8) * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int cc = (c0 % 64) / 8 + q;
-          *reinterpret_cast<uint4*>(base + ((cc ^ (r % 8)) * 16)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          const int cc = c0 / 8 + q;                      // 16-byte chunk (8 keys) inside the row
+          *reinterpret_cast<uint4*>(prow + ((cc ^ (r % 8)) * 16)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         }
       }
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tc_fence_before();
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[sb]);
     }
     const float m_used = m_run;
     // epilogue: O / l from TMEM
-    mbar_wait(o_full, (NT - 1) & 1);
+    mbar_wait(&pv_done[(NT - 1) & 1], ((NT - 1) >> 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l_run;
     {
@@ -288,8 +309,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (row_ok && p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.Lq + m0 + r] = m_used * p.scale + logf(l_run);
     }
     if (p.probs != nullptr) {
-      // single-tile case: S is still in TMEM; write softmax(S) as fp32 (n*H, Lq, Lk).  tcgen05.ld is .sync.aligned: the whole
-      // warp executes the loads, only the stores are predicated on the row being valid.
+      // at most two key tiles: both score buffers are still in TMEM (columns = key index); write softmax(S) as fp32
+      // (n*H, Lq, Lk).  tcgen05.ld is .sync.aligned: the whole warp executes the loads, only the stores are predicated.
       float* pp = p.probs + (((size_t)b * p.H + h) * p.Lq + m0 + r) * p.Lk;
       const float mneg = m_used * p.scale_log2;
 #pragma unroll 1
@@ -339,7 +360,7 @@ extern "C" int comat_attention_fwd_strided(const void* q, const void* k, const v
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15)) return COMAT_ERR_INVALID;
   if (d != 40 && d != 64 && d != 80 && d != 128 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
   if (dtype != COMAT_F16 && dtype != COMAT_BF16) return COMAT_ERR_UNSUPPORTED;
-  if (probs && Lk > ATT_BN) return COMAT_ERR_UNSUPPORTED;
+  if (probs && Lk > 2 * ATT_BN) return COMAT_ERR_UNSUPPORTED;     // both score buffers must still hold the whole row
   if (((H * d) % 8) != 0 || (d % 8) != 0) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   AttnKP kp;

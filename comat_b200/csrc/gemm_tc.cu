@@ -24,6 +24,8 @@ namespace comat {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 x 16-bit = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
+constexpr int PERSIST_EPI_WARPS = 8;                       // persistent kernel: 2 epilogue warps per TMEM lane quarter
+constexpr int PERSIST_THREADS = 64 + 32 * PERSIST_EPI_WARPS;
 
 struct GemmKP {
   int M, N;
@@ -399,7 +401,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int t, int til
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                        const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
@@ -429,7 +431,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     if (p.tma_store) tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);      // one arrival per epilogue warp
+    mbar_init(&tempty[0], PERSIST_EPI_WARPS); mbar_init(&tempty[1], PERSIST_EPI_WARPS);      // one arrival per epilogue warp
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -506,10 +508,14 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (8 warps: a TMEM lane quarter is shared by two warps that take alternate 32-column
+    // chunks).  With four warps the ~1000 dependent instructions per 128 x 160 tile ran on ONE warp per scheduler and the
+    // epilogue, not the MMA, set the pace of K <= 640 GEMMs (ncu: issue slots 11 % busy, tensor pipe 21 %,
+    // profiles/r01_gemm_k320_ncu_v5.md); two warps per scheduler hide each other's TMEM-load and conversion latency.
+    const int q = warp & 3;                      // hardware rule: a warp reads TMEM lanes 32 * (warp % 4) ...
+    const int half = (warp - 2) >> 2;            // 0: chunks 0, 2, 4 ... ; 1: chunks 1, 3, 5 ...
     const int r = q * 32 + lane;
-    const int et = threadIdx.x - 64;             // 0..127
+    const int et = threadIdx.x - 64;             // 0 .. 255
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const TileCoord c = decode_tile(p, t, tiles_n);
@@ -528,14 +534,14 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       }
       const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * p.rowvec_ld : nullptr;
       float* bias_buf = s_bias + (it & 1) * BN;
-      for (int i = et; i < BN; i += 128) bias_buf[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+      for (int i = et; i < BN; i += 32 * PERSIST_EPI_WARPS) bias_buf[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
       if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();   // previous tile's stores have read the staging tile
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -546,7 +552,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator buffer free for tile it + 2
       if (p.tma_store) {
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
         if (warp == 2 && lane == 0) {
 #pragma unroll 1
           for (int pn = 0; pn < (BN + 31) / 32; ++pn) {
@@ -616,7 +622,7 @@ static int launch_gemm_persist(const CUtensorMap* maps, const GemmKP& kp, int to
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  launch_k(gemm_tc_persist_kernel<BN, STAGES>, grid, GEMM_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  launch_k(gemm_tc_persist_kernel<BN, STAGES>, grid, PERSIST_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
