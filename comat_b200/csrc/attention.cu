@@ -121,7 +121,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int c = 0; c < Cf::NKC; ++c) tma_load_3d(sQ + c * ATT_BM * 128, &tmQ, q_full, c * 64, h, b * p.Lq + m0);
       int stage = 0, phase = 0;
       for (int j = 0; j < NT; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_wait_backoff(&kv_empty[stage], phase ^ 1);
         unsigned char* sK = sKV + stage * Cf::KV_STAGE;
         unsigned char* sV = sK + Cf::K_BYTES;
         mbar_expect_tx(&kv_full[stage], Cf::K_BYTES + Cf::V_BYTES);
@@ -159,11 +159,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (j + 1 < NT) {
           // scores of the NEXT tile first: S buffer (j+1)&1 was last read by the softmax of tile j-1, whose p_full this
           // thread has already observed; the softmax warps find them ready when they finish tile j
-          mbar_wait(&kv_full[nstage], nphase);
+          mbar_wait_backoff(&kv_full[nstage], nphase);
           tc_fence_after();
           issue_qk(nstage, (j + 1) & 1);
         }
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);          // P_j is in smem
+        mbar_wait_backoff(&p_full[j & 1], (j >> 1) & 1);  // P_j is in smem
         tc_fence_after();
         const uint32_t aV = smem_u32(sKV + stage * Cf::KV_STAGE + Cf::K_BYTES);
         const uint32_t aPj = aP + (uint32_t)(j & 1) * Cf::P_BYTES;
@@ -251,15 +251,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // P buffer sb was last read by P.V of tile j-2
       if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
       // p = exp2(s*sl2 - m*sl2), row sum, 16-bit P into swizzled smem (K-major: one 128-byte row of 64 keys per query)
+      // The exponentials are issued LA elements ahead of their consumers (row sum, 16-bit pack): with the consumer right
+      // behind its ex2 the warp stalled ~20 cycles per pair on the SFU result while the SFU queue (8 issue cycles per
+      // warp instruction) ran dry - XU pipe 55 % busy with two softmax warps per scheduler (profiles/r01_attn_fwd40_ncu_v5.md).
+      constexpr int LA = 8;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
       unsigned char* prow = sP + sb * Cf::P_BYTES + (r / 8) * 1024 + (r % 8) * 128;
+#pragma unroll
+      for (int i = 0; i < LA; ++i) sv[i] = fast_exp2(fmaf(sv[i], sl2, -mneg));
 #pragma unroll
       for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float e0 = fast_exp2(fmaf(sv[c0 + i], sl2, -mneg));
-          const float e1 = fast_exp2(fmaf(sv[c0 + i + 1], sl2, -mneg));
+          if (c0 + i + LA < ATT_BN) {
+            sv[c0 + i + LA] = fast_exp2(fmaf(sv[c0 + i + LA], sl2, -mneg));
+            sv[c0 + i + LA + 1] = fast_exp2(fmaf(sv[c0 + i + LA + 1], sl2, -mneg));
+          }
+          const float e0 = sv[c0 + i], e1 = sv[c0 + i + 1];
           ls[(i / 2) & 3] += e0 + e1;
           pk[i / 2] = pack2<T>(e0, e1);
         }

@@ -118,6 +118,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for single-thread role warps (TMA producer, MMA issuer) that share a scheduler with arithmetic warps: a spinning
+// try_wait loop is always eligible and steals issue slots from them (ncu: 'branch resolving' stalls on the softmax warps)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
 
 // ---------------------------------------------------------------- 1-D bulk async copies (TMA engine, UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

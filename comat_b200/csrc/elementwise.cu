@@ -192,82 +192,141 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x, 
   }
 }
 
-// ============================================================================================== LayerNorm (one warp per row)
-template <typename T, int MODE>   // 0 fwd (saves mean,rstd) ; 1 bwd
+// ============================================================================================== LayerNorm
+// A warp normalises R rows at a time: all R x NV 16-byte loads of its rows are issued before the first reduction, so an SM
+// keeps >= 40 KB in flight (the one-row-per-warp version had ~20 KB per SM outstanding and ran the UNet's 64x64-level
+// LayerNorms - 32768 rows x 320 channels - at ~45 % of the HBM rate, profiles/r01_step_kernels_v5.md).  Two-pass statistics
+// on the register copy (mean, then centred sum of squares).
+template <typename T, int MODE, int NV, int R>   // MODE 0 fwd (saves mean,rstd) ; 1 bwd.  NV = 16-byte vectors per lane, R = rows per warp
 __global__ void __launch_bounds__(256) ln_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                  float* __restrict__ mean_rstd, long long rows, int C, float eps) {
   pdl_grid_dependency_sync();
-  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   const int vcols = C / 8;
-  const T* xr = x + (size_t)row * C;
-  constexpr int MAXV = 8;   // up to C = 2048
-  Vec8<T> xv[MAXV];
-  float s = 0.f;
+  const float inv_c = 1.f / (float)C;
+  Vec8<T> xv[R][NV];
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int v = lane + k * 32;
-    if (v < vcols) {
-      xv[k].load(xr + v * 8);
+  for (int r = 0; r < R; ++r) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += xv[k].get(i);
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + k * 32;
+      if (v < vcols && row0 + r < rows) xv[r][k].load(x + (size_t)(row0 + r) * C + v * 8);
     }
   }
-  float mean, rstd;
   if (MODE == 0) {
-    mean = warp_sum(s) / (float)C;
-    float q = 0.f;
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int v = lane + k * 32;
-      if (v < vcols) {
+    for (int r = 0; r < R; ++r) {
+      float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = xv[k].get(i) - mean; q += d * d; }
+      for (int k = 0; k < NV; ++k) {
+        if (lane + k * 32 < vcols && row0 + r < rows) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s += xv[r][k].get(i);
+        }
       }
+      mean[r] = s;
     }
-    rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-    if (lane == 0) { mean_rstd[row * 2] = mean; mean_rstd[row * 2 + 1] = rstd; }
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
+    for (int r = 0; r < R; ++r) mean[r] = warp_sum(mean[r]) * inv_c;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        if (lane + k * 32 < vcols && row0 + r < rows) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float d = xv[r][k].get(i) - mean[r]; q = fmaf(d, d, q); }
+        }
+      }
+      rstd[r] = q;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(warp_sum(rstd[r]) * inv_c + eps);
+    if (lane < R && row0 + lane < rows) {
+      float m = mean[0], rs = rstd[0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) if (lane == r) { m = mean[r]; rs = rstd[r]; }
+      mean_rstd[(row0 + lane) * 2] = m; mean_rstd[(row0 + lane) * 2 + 1] = rs;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < vcols) {
-        Vec8<T> o;
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+        const float g8[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.set(i, (xv[k].get(i) - mean) * rstd * gamma[v * 8 + i] + beta[v * 8 + i]);
-        o.store(out + (size_t)row * C + v * 8);
+        for (int r = 0; r < R; ++r) {
+          if (row0 + r < rows) {
+            Vec8<T> o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.set(i, (xv[r][k].get(i) - mean[r]) * rstd[r] * g8[i] + b8[i]);
+            o.store(out + (size_t)(row0 + r) * C + v * 8);
+          }
+        }
       }
     }
   } else {
-    mean = mean_rstd[row * 2]; rstd = mean_rstd[row * 2 + 1];
-    Vec8<T> dv[MAXV];
-    float m1 = 0.f, m2 = 0.f;
+    Vec8<T> dv[R][NV];
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int v = lane + k * 32;
+        if (v < vcols && row0 + r < rows) dv[r][k].load(dy + (size_t)(row0 + r) * C + v * 8);
+      }
+    }
+    float mean[R], rstd[R], m1[R], m2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long rr = row0 + r < rows ? row0 + r : rows - 1;
+      mean[r] = mean_rstd[rr * 2]; rstd[r] = mean_rstd[rr * 2 + 1];
+      m1[r] = 0.f; m2[r] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < vcols) {
-        dv[k].load(dy + (size_t)row * C + v * 8);
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+        const float g8[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a = dv[k].get(i) * gamma[v * 8 + i];
-          m1 += a; m2 += a * (xv[k].get(i) - mean) * rstd;
+        for (int r = 0; r < R; ++r) {
+          if (row0 + r < rows) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a = dv[r][k].get(i) * g8[i];
+              m1[r] += a; m2[r] = fmaf(a, (xv[r][k].get(i) - mean[r]) * rstd[r], m2[r]);
+            }
+          }
         }
       }
     }
-    m1 = warp_sum(m1) / (float)C; m2 = warp_sum(m2) / (float)C;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
+    for (int r = 0; r < R; ++r) { m1[r] = warp_sum(m1[r]) * inv_c; m2[r] = warp_sum(m2[r]) * inv_c; }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < vcols) {
-        Vec8<T> o;
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+        const float g8[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a = dv[k].get(i) * gamma[v * 8 + i];
-          const float xh = (xv[k].get(i) - mean) * rstd;
-          o.set(i, rstd * (a - m1 - xh * m2));
+        for (int r = 0; r < R; ++r) {
+          if (row0 + r < rows) {
+            Vec8<T> o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a = dv[r][k].get(i) * g8[i];
+              const float xh = (xv[r][k].get(i) - mean[r]) * rstd[r];
+              o.set(i, rstd[r] * (a - m1[r] - xh * m2[r]));
+            }
+            o.store(out + (size_t)(row0 + r) * C + v * 8);
+          }
         }
-        o.store(out + (size_t)row * C + v * 8);
       }
     }
   }
@@ -498,17 +557,28 @@ extern "C" int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, cons
   return COMAT_OK;
 }
 
+// vectors per lane / rows per warp by channel count: C <= 512 -> 2 x 4 rows, <= 768 -> 3 x 2, <= 1280 -> 5 x 2, <= 2048 -> 8 x 1
+#define LN_CASE(MODE, NV, R, ...)                                                                                            \
+  DISPATCH_T(dtype, (launch_k(ln_kernel<T, MODE, NV, R>, (unsigned)((rows + 8 * R - 1) / (8 * R)), 256, 0, (cudaStream_t)stream, __VA_ARGS__)))
+#define LN_LAUNCH(MODE, ...)                                    \
+  do {                                                          \
+    if (C <= 512) { LN_CASE(MODE, 2, 4, __VA_ARGS__); }         \
+    else if (C <= 768) { LN_CASE(MODE, 3, 2, __VA_ARGS__); }    \
+    else if (C <= 1280) { LN_CASE(MODE, 5, 2, __VA_ARGS__); }   \
+    else { LN_CASE(MODE, 8, 1, __VA_ARGS__); }                  \
+  } while (0)
+
 extern "C" int comat_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, long long rows,
                                    int C, float eps, int dtype, void* stream) {
   if (!x || !y || !gamma || !beta || !mean_rstd || C % 8 || C > 2048) return COMAT_ERR_INVALID;
-  DISPATCH_T(dtype, (launch_k(ln_kernel<T, 0>, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, (const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, rows, C, eps)));
+  LN_LAUNCH(0, (const T*)x, nullptr, (T*)y, gamma, beta, mean_rstd, rows, C, eps);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 extern "C" int comat_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* mean_rstd, long long rows,
                                    int C, int dtype, void* stream) {
   if (!x || !dy || !dx || !gamma || !mean_rstd || C % 8 || C > 2048) return COMAT_ERR_INVALID;
-  DISPATCH_T(dtype, (launch_k(ln_kernel<T, 1>, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, (T*)dx, gamma, nullptr, const_cast<float*>(mean_rstd), rows, C, 0.f)));
+  LN_LAUNCH(1, (const T*)x, (const T*)dy, (T*)dx, gamma, nullptr, const_cast<float*>(mean_rstd), rows, C, 0.f);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }

@@ -777,7 +777,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   }
   const int total_tiles = (int)(grid.x * grid.y * grid.z);
   const int kb_all = kp.n_taps * (kp.seg_kblocks[0] + (g->n_seg > 1 ? kp.seg_kblocks[1] : 0));
-  const bool use_persist = kernel_mode == 1 || (kernel_mode == 2 && (kb_all <= 24 || total_tiles <= num_sms()));
+  const bool use_persist = g->force_kernel == 2 || (g->force_kernel != 1 && (kernel_mode == 1 || (kernel_mode == 2 && (kb_all <= 24 || total_tiles <= num_sms()))));
   if (use_persist) {
     switch (BN) {
       case 32:  rc = launch_gemm_persist<32, 8>(maps, kp, total_tiles, st); break;

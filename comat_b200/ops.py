@@ -25,12 +25,28 @@ class GemmParams(C.Structure):
                 ("act", C.c_int32), ("residual", C.c_void_p), ("res_ld", C.c_int64), ("out16", C.c_void_p),
                 ("out_ld", C.c_int64), ("out32", C.c_void_p), ("out32_ld", C.c_int64), ("force_bn", C.c_int32),
                 ("split_k", C.c_int32), ("accumulate", C.c_int32), ("splitk_ws", C.c_void_p), ("rowvec_ld", C.c_int64),
-                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32)]
+                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("force_kernel", C.c_int32)]
 
 
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
 
 ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2}
+KERNEL = {None: 0, "auto": 0, "tile": 1, "persist": 2}
+
+
+def _load_tuning():
+    """measured (tile width, kernel, split-K) choices per GEMM shape of the SD1.5 / SDXL step, written by tools/tune_gemm.py
+    on a B200 (comat_b200/gemm_tuning.json).  Shapes that are not in the table use the C side's heuristics."""
+    import json, os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_tuning.json")
+    if os.environ.get("COMAT_GEMM_TUNING", "1") == "0" or not os.path.exists(path):
+        return {}
+    with open(path) as fh:
+        raw = json.load(fh)
+    return {tuple(tuple(x) if isinstance(x, list) else x for x in e["key"]): (e["bn"], e["kernel"], e["split_k"]) for e in raw["entries"]}
+
+
+TUNING = _load_tuning()
 PROFILE = None      # bench.py sets {"flops": 0.0, "events": []} for one instrumented step (per-launch CUDA events)
 TAPS_3x3 = [(dh, dw) for dh in (-1, 0, 1) for dw in (-1, 0, 1)]
 
@@ -43,7 +59,7 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
          bias: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_group: int = 1,
          act=None, residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
          out_fp32: bool = False, conv_taps=None, c_total: int = 0, force_bn: int = 0, split_k: int = 0,
-         accumulate: bool = False) -> torch.Tensor:
+         accumulate: bool = False, kernel=None) -> torch.Tensor:
     """out[m,n] = act(alpha * sum_s A_s[m,:] . B_s[n,:] + bias[n] + rowvec[m // rows_per_group, n]) + residual[m,n]
 
     plain mode : A_s is (M, K_s) (last dim contiguous); B_s is (N, >=K_s) K-major.
@@ -109,7 +125,12 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         p.out32, p.out32_ld = o2.data_ptr(), o2.stride(0)
     else:
         p.out16, p.out_ld = o2.data_ptr(), o2.stride(0)
+    if force_bn == 0 and split_k == 0 and kernel is None and TUNING and not accumulate:
+        t = TUNING.get((M, N, tuple(a.shape[-1] for a in a_segs), len(conv_taps) if conv else 0))
+        if t is not None:
+            force_bn, kernel, split_k = t
     p.force_bn = force_bn
+    p.force_kernel = KERNEL[kernel]
     if split_k == 0:                      # auto: fill the machine when the output has few tiles and K is long
         kb = sum((a.shape[-1] + 63) // 64 for a in a_segs) * (len(conv_taps) if conv else 1)
         tiles = ((M + 127) // 128) * ((N + 127) // 128)

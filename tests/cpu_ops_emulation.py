@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 
 def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_group=1, act=None, residual=None, alpha=1.0,
-         out=None, out_fp32=False, conv_taps=None, c_total=0, force_bn=0, split_k=0, accumulate=False):
+         out=None, out_fp32=False, conv_taps=None, c_total=0, force_bn=0, split_k=0, accumulate=False, kernel=None):
     a0 = a_segs[0]
     N = b_segs[0].shape[0]
     if conv_taps is not None:
