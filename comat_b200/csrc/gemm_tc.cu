@@ -385,19 +385,31 @@ struct PersistSmem {
 struct TileCoord {
   int tile_n, z, m0, img0, h0, w0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int t, int tiles_n) {
+__device__ __forceinline__ TileCoord make_coord(const GemmKP& p, int tile_m, int tile_n, int z) {
   TileCoord c;
-  const int per_z = p.tiles_m * tiles_n;
-  c.z = t / per_z;
-  const int r = t - c.z * per_z;
-  const int tile_m = r / tiles_n;
-  c.tile_n = r - tile_m * tiles_n;
+  c.z = z; c.tile_n = tile_n;
   c.m0 = tile_m * BM; c.img0 = 0; c.h0 = 0; c.w0 = 0;
   if (p.conv) {
     const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
     c.w0 = tw * p.TW; c.h0 = th * p.TH; c.img0 = tn * p.TN;
   }
   return c;
+}
+__device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int t, int tiles_n) {
+  const int per_z = p.tiles_m * tiles_n;
+  const int z = t / per_z;
+  const int r = t - z * per_z;
+  const int tile_m = r / tiles_n;
+  return make_coord(p, tile_m, r - tile_m * tiles_n, z);
+}
+// CTA-pair kernel: pair-tile t covers m-tiles 2*pm and 2*pm+1 (this CTA takes 2*pm + rank; an odd tail tile is out of bounds:
+// TMA zero-fills its loads and clips its stores), n fastest
+__device__ __forceinline__ TileCoord decode_pair_tile(const GemmKP& p, int t, int tiles_n, int pairs_m, int rank) {
+  const int per_z = pairs_m * tiles_n;
+  const int z = t / per_z;
+  const int r = t - z * per_z;
+  const int pm = r / tiles_n;
+  return make_coord(p, 2 * pm + rank, r - pm * tiles_n, z);
 }
 
 template <int BN, int STAGES>
@@ -573,6 +585,207 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on the two SMs of a TPC computes a 256 x BN tile with ONE
+// tcgen05.mma per k-step.  Why: in the one-CTA kernels every operand byte crosses an SM's shared memory twice (written by
+// TMA, read by the tensor core) - 128 x 256 tiles move 2 x 48 KB per 512 MMA cycles = 187 B/clk against ~128 B/clk of
+// shared-memory bandwidth, which is exactly the 67-69 % tensor-pipe ceiling ncu shows for them (57-60 % at BN = 160:
+// profiles/r01_gemm_ncu_v8.md).  In a pair each SM stores its own 128 rows of A and only HALF of B; the B halves are read by
+// both tensor cores, so the same tile costs 2 x 32 KB per SM.
+// Roles as in the persistent kernel (warp 0 TMA producer, warp 1 TMEM alloc (+ MMA issue on the leader), 8 epilogue
+// warps); both producers complete their bytes on the LEADER's full barrier, the leader's tcgen05.commit multicasts the
+// "stage free" / "accumulator ready" arrivals to both CTAs, and the peer's epilogue warps release the accumulator with
+// a remote arrive on the leader's barrier.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct PairSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;                 // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TILES = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFF = TILES;
+  static constexpr int STAGING_BYTES = ((BN + 31) / 32) * 8192;
+  static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;       // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int BIAS_OFF = (TMEMPTR_OFF + 8 + 15) & ~15;
+  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;
+  static_assert(STAGE_BYTES % 1024 == 0, "stage tiles must stay 1024-byte aligned");
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
+  pdl_trigger();
+  using S = PairSmem<BN, STAGES>;
+  constexpr int ACC = tmem_cols<BN>();
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn;               // both CTAs of a pair must use identical offsets: no per-CTA realignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull = empty_bar + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::TMEMPTR_OFF);
+  float* s_bias = reinterpret_cast<float*>(smem + S::BIAS_OFF);
+  unsigned char* staging = smem + S::STAGING_OFF;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int pairs_m = (p.tiles_m + 1) / 2;
+  const int total_pairs = pairs_m * tiles_n * p.split_k;
+  const int kb_per_tap = p.seg_kblocks[0] + (p.n_seg > 1 ? p.seg_kblocks[1] : 0);
+  const int num_kb_total = p.n_taps * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.n_seg > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
+    if (p.tma_store) tma_prefetch_desc(&tmO);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 2 * PERSIST_EPI_WARPS); mbar_init(&tempty[1], 2 * PERSIST_EPI_WARPS);   // epilogue warps of BOTH CTAs
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_ptr, 2 * ACC);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // the peer's barriers exist before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): own A rows + own half of B, bytes counted on the leader's barrier
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int t = cluster_id; t < total_pairs; t += n_clusters) {
+        const TileCoord c = decode_pair_tile(p, t, tiles_n, pairs_m, (int)rank);
+        const int nb0 = c.tile_n * BN + (int)rank * (BN / 2);
+        const int kb_begin = c.z * p.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+        int tap = kb_begin / kb_per_tap;
+        int rem = kb_begin - tap * kb_per_tap;
+        for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
+          const int sg = (rem >= p.seg_kblocks[0]) ? 1 : 0;
+          const int cb = rem - (sg ? p.seg_kblocks[0] : 0);
+          const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
+          const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * S::STAGE_BYTES;
+          unsigned char* sb = sa + S::A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          if (p.conv) tma_load_4d_2sm(sa, mA, &full_bar[stage], cb * BK, c.w0 + p.dw[tap], c.h0 + p.dh[tap], c.img0);
+          else        tma_load_2d_2sm(sa, mA, &full_bar[stage], cb * BK, c.m0);
+          tma_load_2d_2sm(sb, mB, &full_bar[stage], tap * p.c_total + p.seg_bkoff[sg] + cb * BK, nb0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++rem == kb_per_tap) { rem = 0; ++tap; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one thread of the LEADER drives both tensor cores
+    if (lane == 0 && rank == 0) {
+      int stage = 0, phase = 0, it = 0;
+      for (int t = cluster_id; t < total_pairs; t += n_clusters, ++it) {
+        const int z = t / (pairs_m * tiles_n);
+        const int kb_begin = z * p.kb_per_split;
+        const int num_kb = min(num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
+        const int acc = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t da = make_kmajor_sw128_desc(sa);
+          const uint64_t db = make_kmajor_sw128_desc(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 3);          // both producers may refill this stage
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull[acc], 3);                  // both epilogues may drain this accumulator
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (8 warps per CTA; this CTA's 128 accumulator rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int t = cluster_id; t < total_pairs; t += n_clusters, ++it) {
+      const TileCoord c = decode_pair_tile(p, t, tiles_n, pairs_m, (int)rank);
+      const int n0 = c.tile_n * BN;
+      const int acc = it & 1, aph = (it >> 1) & 1;
+      long long m;
+      bool row_ok;
+      if (p.conv) {
+        const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
+        const int n_i = c.img0 + tn, hh = c.h0 + th, ww = c.w0 + tw;
+        row_ok = (n_i < p.n_img) && (hh < p.H) && (ww < p.W);
+        m = ((long long)n_i * p.H + hh) * p.W + ww;
+      } else {
+        m = (long long)c.m0 + r;
+        row_ok = m < p.M;
+      }
+      const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * p.rowvec_ld : nullptr;
+      float* bias_buf = s_bias + (it & 1) * BN;
+      for (int i = et; i < BN; i += 32 * PERSIST_EPI_WARPS) bias_buf[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+      if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+        tmem_ld_wait();
+        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {                           // accumulator buffer free for pair-tile it + 2: tell the leader's MMA thread
+        if (rank == 0) mbar_arrive(&tempty[acc]);
+        else           mbar_arrive_cluster(&tempty[acc], 0);
+      }
+      if (p.tma_store) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
+        if (warp == 2 && lane == 0) {
+#pragma unroll 1
+          for (int pn = 0; pn < (BN + 31) / 32; ++pn) {
+            if (n0 + pn * 32 >= p.N) break;
+            if (p.conv) tma_store_4d(&tmO, staging + pn * 8192, n0 + pn * 32, c.w0, c.h0, c.img0);
+            else        tma_store_2d(&tmO, staging + pn * 8192, n0 + pn * 32, c.m0);
+          }
+          bulk_commit();
+        }
+      }
+    }
+    if (p.tma_store && warp == 2 && lane == 0) bulk_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // the peer's shared memory / barriers stay alive until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * ACC);
+  }
+}
+
 // split-K second pass: out = act(alpha * sum_s ws[s] + bias + rowvec) + residual  (+ accumulate into out32)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int accumulate) {
   pdl_grid_dependency_sync();
@@ -627,6 +840,32 @@ static int launch_gemm_persist(const CUtensorMap* maps, const GemmKP& kp, int to
   return COMAT_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_gemm_pair(const CUtensorMap* maps, const GemmKP& kp, int total_pairs, cudaStream_t st) {
+  using S = PairSmem<BN, STAGES>;
+  static_assert(S::TOTAL <= 232448, "pair GEMM smem budget");
+  static bool configured = false;
+  if (!configured) {
+    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const int max_clusters = num_sms() / 2;
+  const int clusters = total_pairs < max_clusters ? total_pairs : max_clusters;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(PERSIST_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = comat_pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, STAGES>, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
 }  // namespace comat
 
 using namespace comat;
@@ -661,7 +900,37 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     if (b_mn && (BN % 64) != 0) BN = g->N > 64 ? 128 : 64;        // B panels are 64 columns wide
   }
   kp.a_mn = a_mn; kp.b_mn = b_mn;
-  kp.idesc = make_idesc_f16(BM, BN, kp.is_bf16 ? 1 : 0, a_mn, b_mn);
+  // CTA-pair kernel (cta_group::2; force_kernel == 3 or chosen here): K-major operands, tile widths whose halves are whole
+  // 8-row swizzle groups.  Automatic choice: K >= 640 (shorter K is epilogue-bound, where the pair buys nothing) and a
+  // tile width whose pair-tiles fill the 74 SM pairs: score = N-tile efficiency x wave efficiency x width factor
+  // (wider tiles move fewer operand bytes per FLOP).  COMAT_GEMM_PAIR=0 disables the automatic choice.
+  bool use_pair = g->force_kernel == 3 && !a_mn && !b_mn;
+  if (use_pair && BN != 128 && BN != 160 && BN != 256) BN = (g->N % 256 == 0 || g->N > 512) ? 256 : (g->N % 160 == 0 ? 160 : 128);
+  if (g->force_kernel == 0 && !a_mn && !b_mn) {
+    static int pair_mode = -1;
+    if (pair_mode < 0) { const char* e = getenv("COMAT_GEMM_PAIR"); pair_mode = (e && e[0] == '0') ? 0 : 1; }
+    int kb_est = 0;
+    for (int s2 = 0; s2 < g->n_seg; ++s2) kb_est += (g->a_k[s2] + BK - 1) / BK;
+    kb_est *= g->conv ? g->n_taps : 1;
+    const int tiles_m_est = (g->M + BM - 1) / BM;
+    if (pair_mode == 1 && kb_est >= 10 && tiles_m_est >= 2 && g->N >= 128) {
+      const int split = g->split_k > 1 ? g->split_k : 1;
+      const int clusters = num_sms() / 2;
+      const int cand[3] = {256, 160, 128};
+      const float wfac[3] = {1.0f, 0.93f, 0.88f};
+      float best = 0.f; int best_bn = 0;
+      for (int c = 0; c < 3; ++c) {
+        if (g->force_bn != 0 && g->force_bn != cand[c]) continue;
+        const int tn = (g->N + cand[c] - 1) / cand[c];
+        const int pairs = ((tiles_m_est + 1) / 2) * tn * split;
+        const float wave = (float)pairs / (float)(((pairs + clusters - 1) / clusters) * clusters);
+        const float score = wave * ((float)g->N / (float)(tn * cand[c])) * wfac[c];
+        if (score > best) { best = score; best_bn = cand[c]; }
+      }
+      if (best >= 0.6f) { use_pair = true; BN = best_bn; }
+    }
+  }
+  kp.idesc = make_idesc_f16(use_pair ? 2 * BM : BM, BN, kp.is_bf16 ? 1 : 0, a_mn, b_mn);
   CUtensorMap maps[5];
   memset(maps, 0, sizeof(maps));
   dim3 grid;
@@ -728,7 +997,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
       const uint64_t kext = kp.conv ? (uint64_t)g->n_taps * g->c_total : (uint64_t)g->b_koff[s] + K;
       const uint64_t dims[2] = {kext, (uint64_t)g->N};
       const uint64_t str[1] = {(uint64_t)g->b_ld[s] * 2};
-      const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+      const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_pair ? BN / 2 : BN)};      // pair: each CTA loads half of the B tile
       if (!make_tmap_16bit(&maps[2 + s], g->b[s], 2, dims, str, box)) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
     }
   }
@@ -778,7 +1047,14 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   const int total_tiles = (int)(grid.x * grid.y * grid.z);
   const int kb_all = kp.n_taps * (kp.seg_kblocks[0] + (g->n_seg > 1 ? kp.seg_kblocks[1] : 0));
   const bool use_persist = g->force_kernel == 2 || (g->force_kernel != 1 && (kernel_mode == 1 || (kernel_mode == 2 && (kb_all <= 24 || total_tiles <= num_sms()))));
-  if (use_persist) {
+  if (use_pair) {
+    const int pairs = (int)(((grid.x + 1) / 2) * grid.y * grid.z);
+    switch (BN) {
+      case 128: rc = launch_gemm_pair<128, 6>(maps, kp, pairs, st); break;
+      case 160: rc = launch_gemm_pair<160, 6>(maps, kp, pairs, st); break;
+      case 256: rc = launch_gemm_pair<256, 4>(maps, kp, pairs, st); break;
+    }
+  } else if (use_persist) {
     switch (BN) {
       case 32:  rc = launch_gemm_persist<32, 8>(maps, kp, total_tiles, st); break;
       case 64:  rc = launch_gemm_persist<64, 8>(maps, kp, total_tiles, st); break;

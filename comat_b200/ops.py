@@ -31,7 +31,7 @@ class GemmParams(C.Structure):
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
 
 ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2}
-KERNEL = {None: 0, "auto": 0, "tile": 1, "persist": 2}
+KERNEL = {None: 0, "auto": 0, "tile": 1, "persist": 2, "pair": 3}
 
 
 def _load_tuning():

@@ -137,7 +137,8 @@ typedef struct {
                                training_utils/pipeline.py:94-115's backward) read dy / t / x as they lie, no transposed copies.
                                Plain mode, one K segment only. */
   int32_t b_mn_major;       /* 1: b[0] is stored [K, N] row-major (N contiguous) */
-  int32_t force_kernel;     /* 0 = auto; 1 = one-tile-per-CTA kernel; 2 = persistent kernel (tuning table / tests) */
+  int32_t force_kernel;     /* 0 = auto; 1 = one-tile-per-CTA kernel; 2 = persistent kernel; 3 = CTA-pair (cta_group::2) kernel
+                               (tuning table / tests) */
 } comat_gemm_params;
 
 int comat_gemm(const comat_gemm_params* p, void* stream);

@@ -160,3 +160,51 @@ def test_split_k_matches_single_pass_and_reference():
     for sk in (1, 5, 0):
         out = ops.gemm([x], [wk], bias=bias, rowvec=temb, rows_per_group=64, residual=res, conv_taps=ops.TAPS_3x3, split_k=sk)
         assert _rel(out.float(), ref)[0] < 2e-3, sk
+
+
+@pytest.mark.parametrize("M,N,K,bn,split", [
+    (256, 256, 64, 256, 1), (512, 512, 256, 256, 1), (384, 256, 128, 256, 1), (40 * 128, 1024, 320, 256, 1),
+    (301 * 128 + 17, 320, 192, 160, 1), (2048, 1280, 1280, 160, 1), (1024, 640, 2560, 128, 1), (130, 96, 64, 128, 1),
+    (512, 1280, 2304, 256, 3), (8192, 2560, 320, 256, 1),
+])
+def test_pair_kernel_exact(M, N, K, bn, split):
+    """CTA-pair kernel (cta_group::2: 256 x BN tiles over two SMs): small-integer data, exact results.  Covers an odd number of
+    m-tiles (the peer CTA's tile is out of bounds), N not a multiple of the tile, several pair-tiles per cluster (both TMEM
+    accumulator buffers wrap), split-K, bias."""
+    from comat_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randint(-2, 3, (M, K), device="cuda", generator=g).half()
+    b = torch.randint(-2, 3, (N, K), device="cuda", generator=g).half()
+    a = a * (torch.rand(M, K, device="cuda", generator=g) < 0.5)
+    bias = torch.randint(-4, 5, (N,), device="cuda", generator=g).float()
+    out = ops.gemm([a], [b], bias=bias, force_bn=bn, kernel="pair", split_k=split)
+    ref = a.float() @ b.float().t() + bias
+    assert ref.abs().max() < 2048
+    assert torch.equal(out.float(), ref), (out.float() - ref).abs().nonzero()[:8]
+
+
+@pytest.mark.parametrize("n,H,W,C,Cout,bn", [(2, 64, 64, 320, 320, 160), (3, 32, 32, 640, 320, 160), (2, 16, 16, 1280, 640, 128),
+                                             (3, 8, 8, 1280, 1280, 256), (1, 128, 128, 128, 128, 128), (2, 24, 40, 64, 64, 128)])
+def test_pair_kernel_conv_and_fused_epilogue(n, H, W, C, Cout, bn):
+    from comat_b200 import ops
+    torch.manual_seed(H + C)
+    dtype = torch.float16
+    x = torch.randn(n, H, W, C, device="cuda").to(dtype)
+    w = (torch.randn(Cout, C, 3, 3, device="cuda") / (9 * C) ** 0.5).to(dtype)
+    bias = torch.randn(Cout, device="cuda")
+    res = torch.randn(n, H, W, Cout, device="cuda").to(dtype)
+    temb = torch.randn(n, Cout, device="cuda")
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()
+    out = ops.gemm([x], [wk], bias=bias, conv_taps=ops.TAPS_3x3, rowvec=temb, rows_per_group=H * W, residual=res, force_bn=bn, kernel="pair")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1) + temb[:, None, None, :] + res.float()
+    l2, mx = _rel(out.float(), ref)
+    assert l2 < 2e-3, (l2, mx)
+    # two K segments (LoRA branch / fused concat) through the pair kernel
+    M, N, K, r = n * H * W, Cout, C, 128
+    xa = x.reshape(M, K)
+    w2 = (torch.randn(N, K, device="cuda") / K ** 0.5).to(dtype)
+    t = torch.randn(M, r, device="cuda").to(dtype)
+    up = (torch.randn(N, r, device="cuda") * 0.05).to(dtype)
+    out2 = ops.gemm([xa, t], [w2, up], act="silu", force_bn=bn, kernel="pair")
+    ref2 = F.silu(xa.float() @ w2.float().t() + t.float() @ up.float().t())
+    assert _rel(out2.float(), ref2)[0] < 3e-3

@@ -84,7 +84,9 @@ def main():
             if bn > 64 and bn >= 2 * N:
                 continue
             tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
-            for kern in ("tile", "persist"):
+            for kern in ("tile", "persist", "pair"):
+                if kern == "pair" and bn == 64:
+                    continue
                 for sk in (1, 2, 3, 4, 6, 8):
                     if sk > 1 and (tiles * sk > 2 * 148 or kb // sk < 4):
                         continue
