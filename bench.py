@@ -177,13 +177,36 @@ def run_reference(a):
                              "sample": f"{len(times)} sample steps of {total / len(times):.1f} s each ({flops / 1e12:.2f} TFLOP per sample step, "
                                        f"{flops / 1e12 / (total / len(times)):.2f} TFLOP/s on {threads} threads)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
 # --------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """the driver parses ONE JSON line from stdout: route everything libraries print to fd 1 during the run (NCCL's version
+    banner, warnings) to stderr and keep the original stdout for that line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     a = parse()
+    _claim_stdout()
     if a.impl == "reference":
         return run_reference(a)
     import torch
@@ -398,7 +421,9 @@ def main():
             "share_of_step": gemm_s / step_s, "algorithmic_tflop_per_step": prof["flops"] / 1e12}
 
     if rank == 0:
-        value = a.steps / t_dev
+        # whole-job aggregate (weak scaling): every rank runs K optimiser steps on its own batch of `--batch` prompts, so the job
+        # processes world x K per-GPU-batch steps in t_dev; the data-parallel optimiser advances value / world global steps/s
+        value = world * a.steps / t_dev
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * t_dev / a.steps, "host_issue_ms_per_step": host_issue_ms, "memory": mem_note, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.dtype, "data": "synthetic",
@@ -407,13 +432,14 @@ def main():
                            "(BASELINE configs[1])" % (a.total_step, a.K, a.batch, rank_lora),
                            "global_batch": a.batch * world, "parallelism": f"dp{world}", "cuda_graphs": not a.no_graphs,
                            "l2_policy": "inputs rotate over 4 batches; per-step working set (weights 7 GB + activations > 50 GB) exceeds the 126 MB L2",
-                           "samples_per_sec": value * a.batch * world,
+                           "samples_per_sec": value * a.batch, "global_optimizer_steps_per_sec": value / world,
+                           "value_definition": "per-GPU-batch train-steps per second summed over ranks (= n_gpus x global optimiser steps/s)",
                            "library_calls_per_step": lib_calls / a.steps,
                            "library_note": ("0 = every conv / linear / attention (fwd+bwd) / norm / loss / resize / optimiser launch of the step "
                                             "is a comat_b200 kernel; torch supplies memory, the fp32 latent-chain glue, "
                                             "embedding gathers and layout permutes") if lib_calls == 0 else
                                            "calls that fell back to aten/HF kernels (shapes the native kernels do not cover)"},
-                "e2e": {"value": a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": world * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof,
                 "losses": {k: float(v) for k, v in logs.items() if hasattr(v, "numel") and v.numel() == 1}}
         if not a.no_cpu_baseline:
@@ -425,7 +451,7 @@ def main():
                                                   f"({flops / 1e12 / times[0]:.2f} TFLOP/s), scaled by FLOPs to config-2 steps (203 TFLOP)"}
             except Exception as e:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -95,6 +95,7 @@ class LoRAW:
         self.g_down = None
         self.g_up = None
         self.wgrad = True
+        self.direct, self.inv_scale = False, 1.0     # set per backward pass by modules._UNetFn
         self.refresh()
 
     def refresh(self):
@@ -191,10 +192,14 @@ def linear(tape, x: Var, lw: LinW, lora: Optional[LoRAW] = None, residual: Optio
             if lora is not None:
                 u = ops.gemm([dy2], [lora.up16_t])                                   # dy . up      (M, r)
                 if lora.wgrad:
-                    gu = ops.gemm_tn(dy2, t)                                         # d up   = dy^T t  (N, r)
-                    gd = ops.gemm_tn(u, x2)                                          # d down = u^T x   (r, K)
-                    lora.g_up = gu if lora.g_up is None else lora.g_up + gu
-                    lora.g_down = gd if lora.g_down is None else lora.g_down + gd
+                    if lora.direct:
+                        # straight into the optimiser's flat gradient buffer (param.grad views), loss scale undone by alpha:
+                        # no per-parameter AccumulateGrad add, no unscale pass (training_script.py:659 accumulates the same sums)
+                        ops.gemm_tn(dy2, t, accumulate_into=lora.up.grad, alpha=lora.inv_scale)      # d up   += dy^T t  (N, r)
+                        ops.gemm_tn(u, x2, accumulate_into=lora.down.grad, alpha=lora.inv_scale)    # d down += u^T x   (r, K)
+                    else:
+                        lora.g_up = ops.gemm_tn(dy2, t, accumulate_into=lora.g_up)
+                        lora.g_down = ops.gemm_tn(u, x2, accumulate_into=lora.g_down)
                 if x.needs_grad:
                     g = ops.gemm([dy2, u], [lw.wt, lora.down16_t], residual=x.g.reshape(-1, lw.k) if x.g is not None else None)
                     x.g = g.reshape(xv.shape)

@@ -46,12 +46,18 @@ class _UNetFn(torch.autograd.Function):
                 p.g = (g.float() * S).contiguous()
         eng.zero_lora_grads()
         eng.set_lora_wgrad(ctx.wgrad)
+        # direct mode (the trainer owns zero_grad + the flat gradient buffer): weight gradients accumulate in place into
+        # param.grad, so autograd gets None for them
+        direct = bool(ctx.wgrad and ctx.mod.direct_lora_grads and all(
+            p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in eng.lora_params()))
+        for l in eng.loras:
+            l.direct, l.inv_scale = direct, 1.0 / S
         ctx.tape.backward()
         gx = None
         if ctx.needs_input_grad[1] and ctx.xv.g is not None:
             gx = ops.nhwc_to_nchw_f32(ctx.xv.g, ctx.mod.in_channels, 1.0 / S).to(ctx.x_dtype)
-        lg = eng.lora_grads() if ctx.wgrad else [None] * len(eng.lora_grads())
-        if ctx.wgrad and S != 1.0:
+        lg = eng.lora_grads() if (ctx.wgrad and not direct) else [None] * len(eng.lora_grads())
+        if ctx.wgrad and not direct and S != 1.0:
             torch._foreach_mul_([g for g in lg if g is not None], 1.0 / S)
         ctx.tape = ctx.xv = ctx.out = ctx.pvars = None
         return (None, gx, None, None, None, None, None, *lg)
@@ -120,6 +126,7 @@ class EngineUNet(torch.nn.Module):
         self.grad_scale = 4096.0 if dtype == torch.float16 else 1.0   # power of two: exact scale / unscale around the 16-bit backward
         self.use_graphs = False                # bench / trainer switch: CUDA-graph the no-grad forwards of the rollout
         self._graphs = {}
+        self.direct_lora_grads = False         # trainer switch: LoRA weight gradients accumulate straight into param.grad
         self._kv_key, self._kv_val = None, None   # cached 16-bit context + per-layer k|v projections (eager no-grad path)
 
     @property

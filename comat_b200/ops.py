@@ -161,12 +161,15 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
     return out
 
 
-def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, split_k: int = 0) -> torch.Tensor:
+def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, split_k: int = 0,
+            accumulate_into: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
     """out[m, n] = sum_k a_km[k, m] * b_kn[k, n]   (= a_km^T @ b_kn), both operands read as they lie in memory.
 
     The weight-gradient shape: K is the token dimension (tens of thousands), M and N are feature dimensions.  Both operands
     go through TMA as MN-major panels and the tcgen05 descriptors carry the MN-major flag, so no transposed copies are made.
-    K-split partial sums are reduced in a fixed order (deterministic)."""
+    K-split partial sums are reduced in a fixed order (deterministic).  ``accumulate_into`` (fp32 (M, N), contiguous): the
+    result is ADDED to it by the split-K reduction pass (gradient accumulation over the K back-propagated sampler steps)
+    instead of going through a separate elementwise add."""
     _lib.require_cuda(a_km)
     dt = a_km.dtype
     if dt not in (torch.float16, torch.bfloat16) or b_kn.dtype != dt:
@@ -184,17 +187,23 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
     p.a[0], p.a_ld[0], p.a_k[0] = a_km.data_ptr(), a_km.stride(0), K
     p.b[0], p.b_ld[0] = b_kn.data_ptr(), b_kn.stride(0)
     p.a_mn_major, p.b_mn_major = 1, 1
-    p.alpha = 1.0
+    p.alpha = alpha
     p.rows_per_group = 1
-    out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else dt, device=a_km.device)
-    if out_fp32:
-        p.out32, p.out32_ld = out.data_ptr(), N
-    else:
-        p.out16, p.out_ld = out.data_ptr(), N
     kb = (K + 63) // 64
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if split_k == 0 and tiles <= 74 and kb >= 32:
         split_k = max(1, min(kb // 8, 148 // tiles))
+    acc = accumulate_into is not None and out_fp32 and kb >= 2 and accumulate_into.is_contiguous() and accumulate_into.dtype == torch.float32
+    if acc:
+        split_k = max(split_k, 2)              # the accumulate epilogue lives in the split-K reduction pass
+        out = accumulate_into
+        p.accumulate = 1
+    else:
+        out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else dt, device=a_km.device)
+    if out_fp32:
+        p.out32, p.out32_ld = out.data_ptr(), N
+    else:
+        p.out16, p.out_ld = out.data_ptr(), N
     ws = None
     if split_k > 1:
         ws = torch.empty(split_k * M * N, dtype=torch.float32, device=a_km.device)
@@ -211,6 +220,8 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
         fl = 2.0 * M * N * K
         PROFILE["events"].append((e0 if timed else None, e1 if timed else None, (M, N, (K,), -1, int(p.split_k), bool(out_fp32)), fl))
         PROFILE["flops"] += fl
+    if accumulate_into is not None and not acc:
+        return accumulate_into + out
     return out
 
 

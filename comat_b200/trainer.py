@@ -41,6 +41,11 @@ class CoMatTrainer:
                                          max_grad_norm=args.max_grad_norm_D, process_group=process_group)
             D.unet.refresh_lora()
         pipeline.unet.refresh_lora()
+        # both optimisers own flat gradient buffers that are zeroed before each backward: let the UNet executors accumulate
+        # the LoRA weight gradients of the K back-propagated sampler steps into them directly
+        for u in [pipeline.unet] + ([D.unet] if D is not None else []):
+            if hasattr(u, "direct_lora_grads"):
+                u.direct_lora_grads = True
         self.attrcon = "attrcon" in args.pretrain_model_name
         self.train_layer_ls = getattr(args, "train_layer_ls", None) or (
             ["mid_8", "up_16", "up_32", "up_64"] if "sdxl" not in args.pretrain_model_name else ["mid_16", "up_16", "up_32"])

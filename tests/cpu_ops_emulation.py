@@ -152,9 +152,13 @@ def nhwc_to_nchw_f32(x, cout, scale=1.0):
     return (x[..., :cout].float() * scale).permute(0, 3, 1, 2).contiguous()
 
 
-def gemm_tn(a_km, b_kn, *, out_fp32=True, split_k=0):
-    y = a_km.double().t() @ b_kn.double()
-    return y.float() if out_fp32 else y.to(a_km.dtype)
+def gemm_tn(a_km, b_kn, *, out_fp32=True, split_k=0, accumulate_into=None, alpha=1.0):
+    y = alpha * (a_km.double().t() @ b_kn.double())
+    y = y.float() if out_fp32 else y.to(a_km.dtype)
+    if accumulate_into is not None:
+        accumulate_into += y
+        return accumulate_into
+    return y
 
 
 def install(monkeypatch):
