@@ -21,7 +21,8 @@
 namespace comat {
 
 constexpr int AB_ROWS = 128;
-constexpr int AB_THREADS = 192;
+constexpr int AB_ROW_WARPS = 8;                 // two row warps per TMEM lane quarter, each owning 32 of a tile's 64 columns
+constexpr int AB_THREADS = 64 + 32 * AB_ROW_WARPS;
 
 struct AttnBwdKP {
   int Lq, Lk, H, d;
@@ -108,7 +109,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
   if (warp == 0 && lane == 0) {
     mbar_init(res_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(acc_full, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 32 * AB_ROW_WARPS); mbar_init(acc_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, Cf::TMEM_COLS); tmem_relinquish(); }
@@ -194,7 +195,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
     __syncwarp();
   } else {
     // ===================== row threads: softmax backward + epilogue =====================
+    // Eight warps: warps w and w + 4 share a TMEM lane quarter (rows) and split every 64-column inner tile in two
+    // 32-column halves.  With four row warps one warp per scheduler carried the whole row phase and its TMEM-load / SFU
+    // latencies sat on the critical path of the S -> P/dS -> accumulate chain (ncu: issue slots 29-33 % busy, XU 25-35 %,
+    // profiles/r01_attn_bwd40_ncu_v4.md); four warps per scheduler (two CTAs per SM) hide them.
     const int q4 = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q4 * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const int xrow = x0 + r;
@@ -205,6 +211,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       D_r = p.D_pad[(size_t)bh * p.Lq_pad + xrow];
     }
     const int klen = (p.kv_lens != nullptr) ? min(p.Lk, p.kv_lens[b]) : p.Lk;
+    const int cb = half * 32;                    // this warp's first column inside a tile
     int stage = 0, phase = 0;
     for (int it = 0; it < NI; ++it) {
       mbar_wait(s_full, it & 1);
@@ -217,55 +224,61 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       if (MODE == 0) fast_w = (p.dp_ext == nullptr) && (y0 + Cf::BY <= klen) && (!p.causal || (y0 + Cf::BY - 1 <= x0 + q4 * 32));
       else           fast_w = (p.dp_ext == nullptr) && (x0 + q4 * 32 + 31 < klen) && (!p.causal || (x0 + q4 * 32 + 31 <= y0));
       const float sl2 = p.scale_log2;
-#pragma unroll 1
-      for (int c0 = 0; c0 < Cf::BY; c0 += 32) {
-        uint32_t vs[32], vd[32];
-        tmem_ld_32x32b_x32(trow + (uint32_t)(Cf::COL_S + c0), vs);
-        tmem_ld_32x32b_x32(trow + (uint32_t)(Cf::COL_DP + c0), vd);
-        tmem_ld_wait();
-        uint32_t pk_p[16], pk_ds[16];
+      uint32_t vs[2][16], vd[2][16];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        tmem_ld_32x32b_x16(trow + (uint32_t)(Cf::COL_S + cb + 16 * g), vs[g]);
+        tmem_ld_32x32b_x16(trow + (uint32_t)(Cf::COL_DP + cb + 16 * g), vd[g]);
+      }
+      tmem_ld_wait();
+      unsigned char* half0 = sPD;                      // MODE 0: dS   | MODE 1: P^T     (one 64-wide K-major tile each)
+      unsigned char* half1 = sPD + AB_ROWS * 128;      //              | MODE 1: dS^T
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int c0 = cb + 16 * g;
+        uint32_t pk_p[8], pk_ds[8];
         if (fast_w) {
           if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = fast_exp2(fmaf(__uint_as_float(vs[i]), sl2, -lse_r));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(vs[i + 1]), sl2, -lse_r));
-              pk_ds[i / 2] = ab_pack2<T>(p0 * (__uint_as_float(vd[i]) - D_r), p1 * (__uint_as_float(vd[i + 1]) - D_r));
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(vs[g][i]), sl2, -lse_r));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(vs[g][i + 1]), sl2, -lse_r));
+              pk_ds[i / 2] = ab_pack2<T>(p0 * (__uint_as_float(vd[g][i]) - D_r), p1 * (__uint_as_float(vd[g][i + 1]) - D_r));
             }
           } else {
             const float4* l4 = reinterpret_cast<const float4*>(vec + c0);
             const float4* d4 = reinterpret_cast<const float4*>(vec + Cf::BY + c0);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < 16; i += 4) {
               const float4 L = l4[i / 4], Dv = d4[i / 4];
-              const float p0 = fast_exp2(fmaf(__uint_as_float(vs[i]), sl2, -L.x));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(vs[i + 1]), sl2, -L.y));
-              const float p2 = fast_exp2(fmaf(__uint_as_float(vs[i + 2]), sl2, -L.z));
-              const float p3 = fast_exp2(fmaf(__uint_as_float(vs[i + 3]), sl2, -L.w));
+              const float p0 = fast_exp2(fmaf(__uint_as_float(vs[g][i]), sl2, -L.x));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(vs[g][i + 1]), sl2, -L.y));
+              const float p2 = fast_exp2(fmaf(__uint_as_float(vs[g][i + 2]), sl2, -L.z));
+              const float p3 = fast_exp2(fmaf(__uint_as_float(vs[g][i + 3]), sl2, -L.w));
               pk_p[i / 2] = ab_pack2<T>(p0, p1);
               pk_p[i / 2 + 1] = ab_pack2<T>(p2, p3);
-              pk_ds[i / 2] = ab_pack2<T>(p0 * (__uint_as_float(vd[i]) - Dv.x), p1 * (__uint_as_float(vd[i + 1]) - Dv.y));
-              pk_ds[i / 2 + 1] = ab_pack2<T>(p2 * (__uint_as_float(vd[i + 2]) - Dv.z), p3 * (__uint_as_float(vd[i + 3]) - Dv.w));
+              pk_ds[i / 2] = ab_pack2<T>(p0 * (__uint_as_float(vd[g][i]) - Dv.x), p1 * (__uint_as_float(vd[g][i + 1]) - Dv.y));
+              pk_ds[i / 2 + 1] = ab_pack2<T>(p2 * (__uint_as_float(vd[g][i + 2]) - Dv.z), p3 * (__uint_as_float(vd[g][i + 3]) - Dv.w));
             }
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
+          for (int i = 0; i < 16; i += 2) {
             float pv[2], dsv[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int c = c0 + i + e;                      // inner index within the tile
               const int y = y0 + c;
-              float pr, dp = __uint_as_float(vd[i + e]);
+              float pr, dp = __uint_as_float(vd[g][i + e]);
               if (MODE == 0) {
                 const bool kv_ok = (y < klen) && (!p.causal || y <= xrow);
-                pr = kv_ok ? fast_exp2(__uint_as_float(vs[i + e]) * sl2 - lse_r) : 0.f;
+                pr = kv_ok ? fast_exp2(__uint_as_float(vs[g][i + e]) * sl2 - lse_r) : 0.f;
                 if (p.dp_ext != nullptr && y < p.Lk && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + xrow) * p.Lk + y];
                 dsv[e] = pr * (dp - D_r);
               } else {
                 const float lse_c = vec[c], D_c = vec[Cf::BY + c];
                 const bool kv_ok = (xrow < klen) && (!p.causal || xrow <= y);
-                pr = kv_ok ? fast_exp2(__uint_as_float(vs[i + e]) * sl2 - lse_c) : 0.f;   // lse pad = 1e30 -> 0 beyond Lq
+                pr = kv_ok ? fast_exp2(__uint_as_float(vs[g][i + e]) * sl2 - lse_c) : 0.f;   // lse pad = 1e30 -> 0 beyond Lq
                 if (p.dp_ext != nullptr && y < p.Lq && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + y) * p.Lk + xrow];
                 dsv[e] = pr * (dp - D_c);
               }
@@ -275,11 +288,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
             pk_ds[i / 2] = ab_pack2<T>(dsv[0], dsv[1]);
           }
         }
-        unsigned char* half0 = sPD;                      // MODE 0: dS   | MODE 1: P^T     (one 64-wide K-major tile each)
-        unsigned char* half1 = sPD + AB_ROWS * 128;      //              | MODE 1: dS^T
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cc = (c0 % 64) / 8 + q;
+        for (int q = 0; q < 2; ++q) {
+          const int cc = c0 / 8 + q;                     // 16-byte chunk (8 columns) inside the 64-wide row
           if (MODE == 0) {
             *reinterpret_cast<uint4*>(sw128_chunk(half0, r, cc)) = make_uint4(pk_ds[q * 4], pk_ds[q * 4 + 1], pk_ds[q * 4 + 2], pk_ds[q * 4 + 3]);
           } else {
@@ -293,17 +304,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       mbar_arrive(p_full);
       if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
     }
-    // ---- epilogue: accumulators -> 16-bit global
+    // ---- epilogue: accumulators -> 16-bit global.  MODE 0: the two warps of a lane quarter take alternate 16-column groups
+    // of dQ (x scale).  MODE 1: half 0 writes acc0 = dV (x 1) -> out1, half 1 writes acc1 = dK (x scale) -> out0.
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int n_out = (MODE == 0) ? 1 : 2;
-    for (int o = 0; o < n_out; ++o) {
-      // MODE 0: acc0 = dQ (x scale).  MODE 1: acc0 = dV (x 1) -> out1, acc1 = dK (x scale) -> out0
+    {
+      const int o = (MODE == 0) ? 0 : half;
       const float mul = (MODE == 0 || o == 1) ? p.scale : 1.f;
       void* outp = (MODE == 0) ? p.out0 : (o == 0 ? p.out1 : p.out0);
       T* op = reinterpret_cast<T*>(outp) + ((size_t)b * Lx + xrow) * p.out_ld + (size_t)h * p.d;
 #pragma unroll 1
-      for (int c0 = 0; c0 < Cf::DN; c0 += 16) {
+      for (int c0 = (MODE == 0) ? half * 16 : 0; c0 < Cf::DN; c0 += (MODE == 0) ? 32 : 16) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(trow + (uint32_t)((o == 0 ? Cf::COL_ACC0 : Cf::COL_ACC1) + c0), v);
         tmem_ld_wait();
