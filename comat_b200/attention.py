@@ -23,6 +23,7 @@ _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 _lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
 _lib.register_signature("comat_attention_fwd_strided", [_vp] * 7 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _vp])
 _lib.register_signature("comat_attention_bwd", [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
+_lib.register_signature("comat_attention_bwd_strided", [_vp] * 12 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _vp])
 NATIVE_BWD = True
 _DT = {torch.float16: 1, torch.bfloat16: 2}
 
@@ -111,7 +112,7 @@ def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
         if not need_bwd:
             return o, probs, None
         if NATIVE_BWD:
-            return o, probs, ("native", q.contiguous(), k.contiguous(), v.contiguous(), o, lse, probs, heads)
+            return o, probs, ("native", q, k, v, o, lse, probs, heads)      # strided views are read in place by the backward too
         return o, probs, (q, k, v, heads, export_probs)
     LIBRARY_CALLS += 1
     n, Lq, Cc = q.shape
@@ -132,6 +133,7 @@ def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
 
 def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None, causal=False):
     """tcgen05 fused attention backward (csrc/attention_bwd.cu): (dq, dk, dv)."""
+    (q, q_ld), (k, k_ld), (v, v_ld) = _rows(q), _rows(k), _rows(v)
     n, Lq, Cq = q.shape
     Lk = k.shape[1]
     d = Cq // heads
@@ -140,14 +142,17 @@ def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None
     L.comat_attention_bwd_workspace_bytes.argtypes = [_i, _i, _i, _i, _i]
     ws = torch.empty(int(L.comat_attention_bwd_workspace_bytes(n, Lq, Lk, heads, d)), dtype=torch.uint8, device=q.device)
     do = torch.zeros_like(o) if do is None else do.contiguous()
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dq = torch.empty(n, Lq, Cq, dtype=q.dtype, device=q.device)
+    dk = torch.empty(n, Lk, Cq, dtype=q.dtype, device=q.device)
+    dv = torch.empty(n, Lk, Cq, dtype=q.dtype, device=q.device)
     if dprobs is not None:
         dprobs = dprobs.contiguous().float()
-    _lib.check(L.comat_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
-                                     None if dprobs is None else probs.data_ptr(), None if dprobs is None else dprobs.data_ptr(),
-                                     dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), n, Lq, Lk, heads, d,
-                                     float(d) ** -0.5, _DT[q.dtype], None if kv_lens is None else kv_lens.data_ptr(), int(causal),
-                                     _lib.stream_ptr()), "attention_bwd")
+    _lib.check(L.comat_attention_bwd_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                             None if dprobs is None else probs.data_ptr(), None if dprobs is None else dprobs.data_ptr(),
+                                             dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), n, Lq, Lk, heads, d,
+                                             q_ld, k_ld, v_ld, float(d) ** -0.5, _DT[q.dtype],
+                                             None if kv_lens is None else kv_lens.data_ptr(), int(causal), _lib.stream_ptr()),
+               "attention_bwd")
     _lib.count_launch(3)          # row-statistics prep + dQ kernel + dK/dV kernel
     return dq, dk, dv
 

@@ -397,13 +397,14 @@ static int launch_ab(const CUtensorMap* m, const AttnBwdKP& kp, dim3 grid, cudaS
 
 template <int D, typename T>
 static int run_bwd(const void* q, const void* k, const void* v, const void* dO, AttnBwdKP kp, int n,
-                   void* dq, void* dk, void* dv, int fmt, cudaStream_t st) {
+                   void* dq, void* dk, void* dv, int fmt, cudaStream_t st, long long q_ld, long long k_ld, long long v_ld) {
   constexpr int DN = (D + 15) / 16 * 16;
   constexpr int BY = ABCfg<D, 0>::BY;
   const int H = kp.H, d = kp.d, Lq = kp.Lq, Lk = kp.Lk;
-  auto nat = [&](CUtensorMap* m, const void* base, int L, int rows) {
+  const long long hd = (long long)H * d;
+  auto nat_ld = [&](CUtensorMap* m, const void* base, int L, int rows, long long ld) {
     const uint64_t dims[3] = {(uint64_t)d, (uint64_t)H, (uint64_t)n * L};
-    const uint64_t str[2] = {(uint64_t)d * 2, (uint64_t)H * d * 2};
+    const uint64_t str[2] = {(uint64_t)d * 2, (uint64_t)ld * 2};
     const uint32_t box[3] = {64, 1, (uint32_t)rows};
     return make_tmap_16bit(m, base, 3, dims, str, box);
   };
@@ -412,14 +413,14 @@ static int run_bwd(const void* q, const void* k, const void* v, const void* dO, 
   CUtensorMap m[4];
   memset(m, 0, sizeof(m));
   // ---- MODE 0: dQ
-  bool ok = nat(&m[0], q, Lq, AB_ROWS) && nat(&m[1], dO, Lq, AB_ROWS) && nat(&m[2], k, Lk, BY) && nat(&m[3], v, Lk, BY);
+  bool ok = nat_ld(&m[0], q, Lq, AB_ROWS, q_ld) && nat_ld(&m[1], dO, Lq, AB_ROWS, hd) && nat_ld(&m[2], k, Lk, BY, k_ld) && nat_ld(&m[3], v, Lk, BY, v_ld);
   if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   kp.n_inner = (Lk + BY - 1) / BY;
   kp.out0 = dq; kp.out1 = nullptr;
   int rc = launch_ab<D, 0, T>(m, kp, dim3((Lq + AB_ROWS - 1) / AB_ROWS, H, n), st);
   if (rc) return rc;
   // ---- MODE 1: dK, dV
-  ok = nat(&m[0], k, Lk, AB_ROWS) && nat(&m[1], v, Lk, AB_ROWS) && nat(&m[2], q, Lq, BY) && nat(&m[3], dO, Lq, BY);
+  ok = nat_ld(&m[0], k, Lk, AB_ROWS, k_ld) && nat_ld(&m[1], v, Lk, AB_ROWS, v_ld) && nat_ld(&m[2], q, Lq, BY, q_ld) && nat_ld(&m[3], dO, Lq, BY, hd);
   if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   kp.n_inner = (Lq + BY - 1) / BY;
   kp.out0 = dk; kp.out1 = dv;
@@ -435,10 +436,13 @@ extern "C" size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int
   return (size_t)n * H * Lqp * 8 + 1024;       // padded lse (x log2 e) and D vectors
 }
 
-extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
-                                   const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
-                                   int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal, void* stream) {
+extern "C" int comat_attention_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
+                                           const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
+                                           int Lq, int Lk, int H, int d, long long q_ld, long long k_ld, long long v_ld, float scale,
+                                           int dtype, const int* kv_lens, int causal, void* stream) {
   if (!q || !k || !v || !o || !dO || !lse || !dq || !dk || !dv || !workspace) return COMAT_ERR_INVALID;
+  if (q_ld < (long long)H * d || k_ld < (long long)H * d || v_ld < (long long)H * d || (q_ld % 8) || (k_ld % 8) || (v_ld % 8)) return COMAT_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15)) return COMAT_ERR_INVALID;
   if (d != 40 && d != 64 && d != 80 && d != 128 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
   if (dtype != COMAT_F16 && dtype != COMAT_BF16) return COMAT_ERR_UNSUPPORTED;
   if (dp_ext && !probs) return COMAT_ERR_INVALID;
@@ -464,9 +468,17 @@ extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, 
   const int fmt = dtype == COMAT_BF16 ? 1 : 0;
 #define AB_CASE(DD)                                                                                                          \
   case DD:                                                                                                                   \
-    return fmt ? run_bwd<DD, __nv_bfloat16>(q, k, v, dO, kp, n, dq, dk, dv, fmt, st)                                         \
-               : run_bwd<DD, __half>(q, k, v, dO, kp, n, dq, dk, dv, fmt, st);
+    return fmt ? run_bwd<DD, __nv_bfloat16>(q, k, v, dO, kp, n, dq, dk, dv, fmt, st, q_ld, k_ld, v_ld)                       \
+               : run_bwd<DD, __half>(q, k, v, dO, kp, n, dq, dk, dv, fmt, st, q_ld, k_ld, v_ld);
   switch (d) { AB_CASE(16) AB_CASE(32) AB_CASE(40) AB_CASE(64) AB_CASE(80) AB_CASE(128) AB_CASE(160) }
 #undef AB_CASE
   return COMAT_ERR_UNSUPPORTED;
+}
+
+extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
+                                   const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
+                                   int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal, void* stream) {
+  const long long ld = (long long)H * d;
+  return comat_attention_bwd_strided(q, k, v, o, dO, lse, probs, dp_ext, dq, dk, dv, workspace, n, Lq, Lk, H, d, ld, ld, ld, scale, dtype,
+                                     kv_lens, causal, stream);
 }

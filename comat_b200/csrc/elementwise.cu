@@ -733,3 +733,36 @@ extern "C" int comat_softmax_rows(const void* x, const void* dp, void* out, long
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
+
+// ============================================================================================== fp32 -> bf16 hi/lo split
+namespace comat {
+__global__ void __launch_bounds__(256) split_f32_bf16x2_kernel(const float4* __restrict__ src, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                                               long long nv, float alpha) {
+  pdl_grid_dependency_sync();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    const float f[4] = {v.x * alpha, v.y * alpha, v.z * alpha, v.w * alpha};
+    uint16_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat16 hb = __float2bfloat16_rn(f[k]);
+      const __nv_bfloat16 lb = __float2bfloat16_rn(f[k] - __bfloat162float(hb));
+      h[k] = *reinterpret_cast<const uint16_t*>(&hb);
+      l[k] = *reinterpret_cast<const uint16_t*>(&lb);
+    }
+    hi[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    lo[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+  }
+}
+}  // namespace comat
+
+extern "C" int comat_split_f32_bf16x2(const float* src, void* hi, void* lo, long long n, float alpha, void* stream) {
+  if (!src || !hi || !lo || n <= 0 || (n % 4) != 0) return COMAT_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(hi) & 7) || (reinterpret_cast<uintptr_t>(lo) & 7)) return COMAT_ERR_INVALID;
+  const long long nv = n / 4;
+  long long blocks = (nv + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_k(comat::split_f32_bf16x2_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, (const float4*)src, (uint2*)hi, (uint2*)lo, nv, alpha);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}

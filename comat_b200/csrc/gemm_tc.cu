@@ -50,6 +50,8 @@ struct GemmKP {
   int split_k, kb_per_split;   // split-K: blockIdx.z handles k-blocks [z*kb_per_split, ...) and writes raw fp32 partials
   float* splitk_ws;            // [split_k][M][N] fp32
   int tma_store;     // 1: epilogue stages 16-bit tiles in (free) pipeline smem and writes them with TMA bulk tensor stores
+  int atomic_acc;    // 1: out32 += alpha * (this CTA's partial sum) with vector fp32 atomics - gradient accumulation across
+                     //    K-splits AND across calls in one kernel (no partial workspace, no reduction pass)
 };
 
 __device__ __forceinline__ float act_apply(float x, int act) {
@@ -72,7 +74,21 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
 __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (&v)[32], int c0, int n0, long long m, bool row_ok,
                                            const float* rv, const float* s_bias, int r, unsigned char* stage, int zsplit) {
   const int ncol = min(32, p.N - (n0 + c0));
-  if (p.split_k > 1) {
+  if (p.atomic_acc) {
+    if (row_ok && ncol > 0) {
+      float* op = p.out32 + m * p.out32_ld + n0 + c0;
+      if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(op + j), make_float4(__uint_as_float(v[j]) * p.alpha, __uint_as_float(v[j + 1]) * p.alpha,
+                                                                     __uint_as_float(v[j + 2]) * p.alpha, __uint_as_float(v[j + 3]) * p.alpha));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) atomicAdd(op + j, __uint_as_float(v[j]) * p.alpha);
+      }
+    }
+  } else if (p.split_k > 1) {
     if (row_ok && ncol > 0) {
       float* wp = p.splitk_ws + ((size_t)zsplit * p.M + m) * p.N + n0 + c0;
       if (ncol == 32 && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
@@ -930,6 +946,9 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
       if (best >= 0.6f) { use_pair = true; BN = best_bn; }
     }
   }
+  // kind::f16 takes ONE 16-bit format for both operands: a descriptor with a_format != b_format raises an illegal-instruction
+  // fault on sm_100a (measured, profiles/r01_gpu_tests_run13.log), so mixed fp16 x bf16 operands are rejected here
+  if (g->b_dtype != 0 && g->b_dtype != g->dtype) return COMAT_ERR_UNSUPPORTED;
   kp.idesc = make_idesc_f16(use_pair ? 2 * BM : BM, BN, kp.is_bf16 ? 1 : 0, a_mn, b_mn);
   CUtensorMap maps[5];
   memset(maps, 0, sizeof(maps));
@@ -1007,12 +1026,17 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     int sk = g->split_k > 1 ? g->split_k : 1;
     if (sk > kb_total) sk = kb_total;
     if (sk > 1) {
-      if (!g->splitk_ws) return COMAT_ERR_WORKSPACE;
+      if (!g->splitk_ws && !g->accumulate) return COMAT_ERR_WORKSPACE;
       kp.kb_per_split = (kb_total + sk - 1) / sk;
       sk = (kb_total + kp.kb_per_split - 1) / kp.kb_per_split;
       kp.split_k = sk; kp.splitk_ws = g->splitk_ws;
       grid.z = sk;
     } else { kp.split_k = 1; kp.kb_per_split = kb_total; }
+    if (g->accumulate) {
+      // accumulate = fp32 atomics straight into out32 (alpha only: no bias / activation / residual / 16-bit output)
+      if (!g->out32 || g->out16 || g->bias || g->rowvec || g->act || g->residual) return COMAT_ERR_INVALID;
+      kp.atomic_acc = 1;
+    }
   }
   // TMA-store epilogue (default): needs a 16-bit output with 16-byte aligned base and row pitch
   static int epi_mode = -1;
@@ -1070,7 +1094,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     case 160: rc = launch_gemm<160, 3>(maps, kp, grid, st); break;
     case 256: rc = launch_gemm<256, 4>(maps, kp, grid, st); break;
   }
-  if (rc == COMAT_OK && kp.split_k > 1) {
+  if (rc == COMAT_OK && kp.split_k > 1 && !kp.atomic_acc) {
     const long long total = (long long)kp.M * kp.N;
     launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, kp, g->accumulate ? 1 : 0);
     COMAT_CHECK_LAUNCH();

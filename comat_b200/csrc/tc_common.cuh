@@ -137,13 +137,13 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
 }
 
 // instruction descriptor, kind::f16: D=f32, A/B = f16 (fmt 0) or bf16 (fmt 1), both K-major, M x N tile.
-__host__ __device__ inline uint32_t make_idesc_f16(int M, int N, int fmt, int a_mn_major = 0, int b_mn_major = 0) {
+__host__ __device__ inline uint32_t make_idesc_f16(int M, int N, int fmt, int a_mn_major = 0, int b_mn_major = 0, int b_fmt = -1) {
   uint32_t d = 0;
   d |= (uint32_t)(a_mn_major ? 1 : 0) << 15;   // a_major: 0 = K-major, 1 = MN-major
   d |= (uint32_t)(b_mn_major ? 1 : 0) << 16;   // b_major
   d |= 1u << 4;                       // c_format = F32
   d |= (uint32_t)fmt << 7;            // a_format
-  d |= (uint32_t)fmt << 10;           // b_format
+  d |= (uint32_t)(b_fmt < 0 ? fmt : b_fmt) << 10;           // b_format (independent of a_format)
   d |= (uint32_t)(N >> 3) << 17;      // n_dim
   d |= (uint32_t)(M >> 4) << 24;      // m_dim
   return d;

@@ -85,7 +85,9 @@ class LinW:
 
 
 class LoRAW:
-    """fp32 master parameters (trainable) + per-step 16-bit operand copies.  y = W x + up(down(x))."""
+    """fp32 master parameters (trainable) + per-step operand images.  y = W x + up(down(x)).
+    The images are views into arenas owned by the UNet executor (``UNetEngine._build_lora_arenas``), refreshed for ALL
+    adapters by a handful of flat conversions (one adapter at a time it was ~1500 tiny launches per optimiser step)."""
 
     def __init__(self, lora, dtype):
         self.down = lora.down.weight        # (r, K) fp32 nn.Parameter
@@ -96,17 +98,50 @@ class LoRAW:
         self.g_up = None
         self.wgrad = True
         self.direct, self.inv_scale = False, 1.0     # set per backward pass by modules._UNetFn
-        self.refresh()
+        # views assigned by the executor: 16-bit operands (and transposes), bf16 hi / lo images for the gradient projection
+        self.down16 = self.up16 = self.down16_t = self.up16_t = None
+        self.down_bh = self.up_bh = self.down_bl = self.up_bl = None
+
+
+class _LoRAArenas:
+    """All LoRA factors of one executor as flat buffers: fp32 staging, engine-dtype image, bf16 hi / lo images (fp32 range,
+    ~16 mantissa bits together: operands of the product-gradient projection, where the tensor core needs one format for
+    both operands), per-adapter transposed images.  Stable addresses (captured CUDA graphs keep reading them)."""
+
+    def __init__(self, loras: List["LoRAW"], dtype):
+        self.loras = loras
+        dev = loras[0].down.device
+        self.params = [p for l in loras for p in (l.down, l.up)]
+        n = sum(p.numel() for p in self.params)
+        self.f32 = torch.empty(n, dtype=torch.float32, device=dev)
+        self.tmp = torch.empty(n, dtype=torch.float32, device=dev)
+        self.h16 = torch.empty(n, dtype=dtype, device=dev)
+        self.bh = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        self.bl = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        self.f32_views, self.t_dst, self.t_src = [], [], []
+        off = 0
+        for l in loras:
+            for name, p in (("down", l.down), ("up", l.up)):
+                k = p.numel()
+                sl = slice(off, off + k)
+                self.f32_views.append(self.f32[sl].view_as(p))
+                v16 = self.h16[sl].view_as(p)
+                setattr(l, name + "16", v16)
+                setattr(l, name + "_bh", self.bh[sl].view_as(p))
+                setattr(l, name + "_bl", self.bl[sl].view_as(p))
+                t = torch.empty(p.shape[1], p.shape[0], dtype=dtype, device=dev)
+                setattr(l, name + "16_t", t)
+                self.t_dst.append(t)
+                self.t_src.append(v16.t())
+                off += k
 
     def refresh(self):
-        """re-materialise the 16-bit operands IN PLACE (stable addresses: captured CUDA graphs keep reading them)."""
-        d, u = self.down.detach(), self.up.detach()
-        if getattr(self, "down16", None) is None:
-            self.down16, self.up16 = d.to(self.dtype).contiguous(), u.to(self.dtype).contiguous()
-            self.down16_t, self.up16_t = d.t().to(self.dtype).contiguous(), u.t().to(self.dtype).contiguous()
-        else:
-            self.down16.copy_(d); self.up16.copy_(u)
-            self.down16_t.copy_(d.t()); self.up16_t.copy_(u.t())
+        torch._foreach_copy_(self.f32_views, [p.detach() for p in self.params])
+        self.h16.copy_(self.f32)
+        self.bh.copy_(self.f32)
+        torch.sub(self.f32, self.bh, out=self.tmp)          # fp32 - bf16 promotes to fp32
+        self.bl.copy_(self.tmp)
+        torch._foreach_copy_(self.t_dst, self.t_src)
 
 
 class NormW:
@@ -306,6 +341,7 @@ class _Attn:
                       for l in (m.to_q, m.to_k, m.to_v, m.to_out[0])]
         self.gn = NormW(m.group_norm, m.group_norm.num_groups) if m.group_norm is not None else None
         self.mq = self.mk = self.mv = self.mo = None      # merged projections, built by build_merged()
+        self.G = [None, None, None, None]                 # fp32 product-gradient accumulators dy^T x of q, k, v, o (UNetEngine arena)
 
     # ---- LoRA folded into the projection weights (passes that need no LoRA weight gradient)
     # y = W x + up(down(x)) (training_utils/pipeline.py:94-115) == (W + up.down) x: the no-grad rollout forwards and the
@@ -397,6 +433,8 @@ def _attn_layer(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, captu
     """mode 'train': LoRA branch explicit (weight gradients wanted).  'frozen': taped, LoRA folded into the weights (data
     gradients only).  'merged': no tape - folded weights, fused q|k|v / k|v GEMMs, ``cross_kv`` = the text context's
     pre-projected (n, T, 2C) k|v (identical for every UNet call of a rollout, so it is computed once per optimiser step)."""
+    if mode == "product" and tape is not None:
+        return _attn_layer_product(tape, a, x, ctx, residual, capture, place, cross_kv)
     export = capture is not None and ctx is not None and capture.wants(place)
     if mode == "merged" and tape is None:
         C = a.q.n
@@ -430,6 +468,72 @@ def _attn_layer(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, captu
     if capture is not None:
         capture.push(p, ctx is not None, place)
     return linear(tape, o, lo, loras[3], residual=residual)
+
+
+def _attn_layer_product(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, capture=None, place=None, cross_kv=None):
+    """Taped attention layer with LoRA weight gradients, 'product' form.  Forward runs on the folded weights exactly like the
+    no-grad path (one q|k|v GEMM, one k|v GEMM, strided attention operands).  Backward: data gradients through the folded
+    weights, and for every LoRA'd projection ONE accumulation  G += dy^T x  (fp32, full weight shape) instead of the
+    explicit branch's  t = x down^T,  u = dy up,  d up = dy^T t,  d down = u^T x : since
+    d up = (dy^T x) down^T  and  d down = up^T (dy^T x)  are linear in G and the factors are constant between optimiser steps,
+    G is accumulated over all back-propagated sampler steps and projected once per optimiser step
+    (UNetEngine.finalize_lora_grads).  Same gradients as training_utils/pipeline.py:94-115's autograd."""
+    C = a.q.n
+    xv = x.v
+    lead = xv.shape[:-1]
+    x2 = xv.reshape(-1, a.q.k)
+    export = capture is not None and ctx is not None and capture.wants(place)
+    if ctx is None and a.w_qkv is not None:
+        qkv = ops.gemm([x2], [a.w_qkv], bias=a.b_qkv).reshape(*lead, 3 * C)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        src2 = x2
+    else:
+        q = ops.gemm([x2], [a.mq.w], bias=a.mq.bias).reshape(*lead, C)
+        src = xv if ctx is None else ctx.v
+        src2 = src.reshape(-1, a.k.k)
+        if cross_kv is not None and ctx is not None:
+            kv = cross_kv
+        else:
+            kv = ops.gemm([src2], [a.w_kv], bias=a.b_kv).reshape(*src.shape[:-1], 2 * C)
+        k, v = kv[..., :C], kv[..., C:]
+    o, probs, saved = attn_ops.attention_fwd(q, k, v, a.heads, export, need_bwd=True)
+    pvar = Var(probs) if export else None
+    if capture is not None:
+        capture.push(pvar, ctx is not None, place)
+    o2 = o.reshape(-1, C)
+    y = ops.gemm([o2], [a.mo.w], bias=a.mo.bias, residual=residual.v.reshape(-1, a.mo.n))
+    out = Var(y.reshape(*lead, a.mo.n))
+
+    def wants(i):
+        return a.loras[i] is not None and a.loras[i].wgrad
+
+    def bwd():
+        dy = out.g
+        if dy is None and (pvar is None or pvar.g is None):
+            return
+        do = None
+        if dy is not None:
+            dy2 = dy.reshape(-1, a.mo.n)
+            _acc(residual, dy)
+            if wants(3):
+                ops.gemm_tn(dy2, o2, accumulate_into=a.G[3])
+            do = ops.gemm([dy2], [a.mo.wt]).reshape(o.shape)
+        dq, dk, dv = attn_ops.attention_bwd(saved, do, pvar.g if pvar is not None else None)
+        dq2, dk2, dv2 = dq.reshape(-1, C), dk.reshape(-1, C), dv.reshape(-1, C)
+        if wants(0):
+            ops.gemm_tn(dq2, x2, accumulate_into=a.G[0])
+        if wants(1):
+            ops.gemm_tn(dk2, src2, accumulate_into=a.G[1])
+        if wants(2):
+            ops.gemm_tn(dv2, src2, accumulate_into=a.G[2])
+        if x.needs_grad:
+            g = ops.gemm([dq2], [a.mq.wt], residual=x.g.reshape(-1, a.q.k) if x.g is not None else None)
+            if ctx is None:
+                g = ops.gemm([dk2], [a.mk.wt], residual=g)
+                g = ops.gemm([dv2], [a.mv.wt], residual=g)
+            x.g = g.reshape(xv.shape)
+    tape.record(bwd)
+    return out
 
 
 def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=None, mode="train", cross_kv=None) -> Var:
@@ -543,11 +647,21 @@ class UNetEngine:
                             self._attns.append(a)
                             self.loras.extend(l for l in a.loras if l is not None)
         self.lora_version, self._merged_version, self._merged_t = 0, -1, False
+        self._arenas = None
+        self.refresh_lora()
+        # 'product' (default): LoRA weight gradients through the accumulated full-size product G = dy^T x, projected onto the
+        # factors once per optimiser step; 'explicit': the literal LoRA branch (t = x down^T ...) in forward and backward
+        self.lora_train_impl = "product"
+        self._G = self._G_hi = self._G_lo = None
+        self._gproj = []
+        self.G_dirty = False
 
     # ---- LoRA plumbing
     def refresh_lora(self):
-        for l in self.loras:
-            l.refresh()
+        if self.loras:
+            if self._arenas is None:
+                self._arenas = _LoRAArenas(self.loras, self.dtype)
+            self._arenas.refresh()
         self.lora_version += 1                 # folded weights / cached context projections are stale now
 
     def ensure_merged(self, transposed: bool = False):
@@ -561,6 +675,55 @@ class UNetEngine:
             for a in self._attns:
                 a.refresh_merged(True)
             self._merged_t = True
+
+    def _ensure_G(self):
+        """fp32 arena of the product-gradient accumulators (same shapes as the LoRA'd projection weights) + its bf16 hi/lo images."""
+        if self._G is not None:
+            return
+        shapes = []
+        for a in self._attns:
+            for i, lw in enumerate((a.q, a.k, a.v, a.o)):
+                if a.loras[i] is not None:
+                    shapes.append((a, i, lw.n, lw.k))
+        total = sum(n * k for _, _, n, k in shapes)
+        dev = self.te1.w.device
+        self._G = torch.zeros(max(total, 4), dtype=torch.float32, device=dev)
+        self._G_hi = torch.empty(max(total, 4), dtype=torch.bfloat16, device=dev)
+        self._G_lo = torch.empty(max(total, 4), dtype=torch.bfloat16, device=dev)
+        off = 0
+        for a, i, n, k in shapes:
+            a.G[i] = self._G[off:off + n * k].view(n, k)
+            self._gproj.append((off, n, k, a.loras[i]))
+            off += n * k
+
+    def finalize_lora_grads(self, inv_scale: float = 1.0, into_param_grads: bool = True):
+        """project the accumulated products onto the LoRA factors:  d up = G down^T (N, r),  d down = up^T G (r, K), G fed to
+        the tensor cores as bf16 hi + lo (two K segments / two accumulating passes: ~16 mantissa bits at fp32 range).
+        ``into_param_grads``: accumulate into ``param.grad`` (the optimiser's flat buffer) and return None; otherwise return
+        the gradients in ``lora_params()`` order.  Clears the accumulators."""
+        if self._G is None or not self.G_dirty:
+            return None if into_param_grads else [None] * (2 * len(self.loras))
+        ops.split_f32_bf16x2(self._G, self._G_hi, self._G_lo, inv_scale)
+        res = {}
+        for off, n, k, lora in self._gproj:
+            hi, lo = self._G_hi[off:off + n * k].view(n, k), self._G_lo[off:off + n * k].view(n, k)
+            # (gh + gl)(dh + dl)^T without the gl.dl term (2^-16 relative), likewise for up^T G
+            if into_param_grads:
+                g_up, g_down = lora.up.grad, lora.down.grad
+            else:
+                g_up = torch.zeros(n, lora.rank, dtype=torch.float32, device=hi.device)
+                g_down = torch.zeros(lora.rank, k, dtype=torch.float32, device=hi.device)
+                res[id(lora)] = (g_down, g_up)
+            ops.gemm([hi, lo], [lora.down_bh, lora.down_bh], out=g_up, accumulate=True)
+            ops.gemm([hi], [lora.down_bl], out=g_up, accumulate=True)
+            ops.gemm_tn(lora.up_bh, hi, accumulate_into=g_down)
+            ops.gemm_tn(lora.up_bh, lo, accumulate_into=g_down)
+            ops.gemm_tn(lora.up_bl, hi, accumulate_into=g_down)
+        self._G.zero_()
+        self.G_dirty = False
+        if into_param_grads:
+            return None
+        return [g for l in self.loras for g in res.get(id(l), (None, None))]
 
     def cross_kv(self, ctx16: torch.Tensor, out=None):
         """k|v projections of the text context for every cross-attention layer: {id(layer): (n, T, 2C)}.  The context and
@@ -610,6 +773,10 @@ class UNetEngine:
         mode = lora_mode or ("train" if tape is not None else "merged")
         if mode == "merged" and tape is not None:
             mode = "frozen"
+        if mode == "train" and self.lora_train_impl == "product":
+            mode = "product"
+            self._ensure_G()
+            tape.record(lambda: setattr(self, "G_dirty", True))       # runs last in the backward: accumulators hold this pass
         if mode != "train":
             self.ensure_merged(transposed=tape is not None)
         temb16 = self.temb(t, n, added_cond)

@@ -19,14 +19,16 @@ from . import ops
 
 class _UNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mod: "EngineUNet", x, t, ehs, added, capture, n_lora, *lora_params):
+    def forward(ctx, mod: "EngineUNet", x, t, ehs, added, capture, ctx_kv, *lora_params):
         eng = mod.engine
         tape = E.Tape()
         xv = E.Var(ops.latent_to_nhwc(x, eng.dtype, 64), needs_grad=ctx.needs_input_grad[1])
         ctx.wgrad = bool(mod.train_lora and any(p.requires_grad for p in lora_params))
+        ctx.product = ctx.wgrad and eng.lora_train_impl == "product"
+        ctx16, kv = ctx_kv if ctx_kv is not None else (ehs.to(eng.dtype), None)
         # no LoRA weight gradient wanted (the discriminator's generator-side pass, gan_sdxl.py:52-89): LoRA folded into the weights
-        out = eng.forward(tape, xv, t, ehs.to(eng.dtype), capture=capture, added_cond=added,
-                          lora_mode="train" if ctx.wgrad else "frozen")
+        out = eng.forward(tape, xv, t, ctx16, capture=capture, added_cond=added,
+                          lora_mode="train" if ctx.wgrad else "frozen", cross_kv=kv if (ctx.product or not ctx.wgrad) else None)
         eps = ops.nhwc_to_nchw_f32(out.v, mod.out_channels)
         pvars = []
         if capture is not None:
@@ -56,9 +58,15 @@ class _UNetFn(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[1] and ctx.xv.g is not None:
             gx = ops.nhwc_to_nchw_f32(ctx.xv.g, ctx.mod.in_channels, 1.0 / S).to(ctx.x_dtype)
-        lg = eng.lora_grads() if (ctx.wgrad and not direct) else [None] * len(eng.lora_grads())
-        if ctx.wgrad and not direct and S != 1.0:
-            torch._foreach_mul_([g for g in lg if g is not None], 1.0 / S)
+        if ctx.product:
+            # the products dy^T x of this pass sit in the engine's accumulators: the trainer projects them once per optimiser
+            # step (EngineUNet.finalize_lora_grads); without a trainer they are projected here and handed to autograd
+            eng.G_dirty = True
+            lg = [None] * len(eng.lora_grads()) if direct else eng.finalize_lora_grads(1.0 / S, into_param_grads=False)
+        else:
+            lg = eng.lora_grads() if (ctx.wgrad and not direct) else [None] * len(eng.lora_grads())
+            if ctx.wgrad and not direct and S != 1.0:
+                torch._foreach_mul_([g for g in lg if g is not None], 1.0 / S)
         ctx.tape = ctx.xv = ctx.out = ctx.pvars = None
         return (None, gx, None, None, None, None, None, *lg)
 
@@ -144,7 +152,13 @@ class EngineUNet(torch.nn.Module):
         """call after every optimiser step: re-materialise the 16-bit LoRA operands from the fp32 masters."""
         self.engine.refresh_lora()
 
-    def _context_kv(self, ehs):
+    def finalize_lora_grads(self):
+        """project the product gradients accumulated by the backward passes since the last call onto the LoRA factors and
+        add them to ``param.grad`` (call once after ``loss.backward()``, before the optimiser's all-reduce / step)."""
+        if self.engine.G_dirty:
+            self.engine.finalize_lora_grads(1.0 / self.grad_scale, into_param_grads=True)
+
+    def _context_kv(self, ehs, store=True):
         """16-bit text context and its k|v projections for every cross-attention layer, cached while the caller keeps passing
         the SAME tensor object (unmodified: ``_version``) and the LoRA weights are unchanged - true for every step of a
         rollout (TrainableSDPipeline.py:132-150 passes one ``prompt_embeds`` to all S UNet calls).  The key holds a
@@ -154,9 +168,11 @@ class EngineUNet(torch.nn.Module):
         if k is not None and k[0] is ehs and k[1] == ehs._version and k[2] == eng.lora_version:
             return self._kv_val
         ctx16 = ehs.detach().to(eng.dtype).contiguous()
-        self._kv_val = (ctx16, eng.cross_kv(ctx16))
-        self._kv_key = (ehs, ehs._version, eng.lora_version)
-        return self._kv_val
+        val = (ctx16, eng.cross_kv(ctx16))
+        if store:                                  # one-off contexts (the attrcon half-batches) do not evict the rollout's entry
+            self._kv_val = val
+            self._kv_key = (ehs, ehs._version, eng.lora_version)
+        return val
 
     def enable_gradient_checkpointing(self):
         pass                                  # never recomputes: activations of K steps fit in 180 GB
@@ -170,7 +186,8 @@ class EngineUNet(torch.nn.Module):
         if capture is not None:
             capture.reset()
         if want_grad:
-            outs = _UNetFn.apply(self, sample, t, encoder_hidden_states, added_cond_kwargs, capture, len(params), *params)
+            ckv = self._context_kv(encoder_hidden_states, store=capture is None)
+            outs = _UNetFn.apply(self, sample, t, encoder_hidden_states, added_cond_kwargs, capture, ckv, *params)
             eps, probs = outs[0], outs[1:]
         elif self.use_graphs and capture is None and added_cond_kwargs is None and sample.is_cuda:
             key = (tuple(sample.shape), tuple(encoder_hidden_states.shape), sample.dtype, encoder_hidden_states.dtype)

@@ -25,7 +25,7 @@ class GemmParams(C.Structure):
                 ("act", C.c_int32), ("residual", C.c_void_p), ("res_ld", C.c_int64), ("out16", C.c_void_p),
                 ("out_ld", C.c_int64), ("out32", C.c_void_p), ("out32_ld", C.c_int64), ("force_bn", C.c_int32),
                 ("split_k", C.c_int32), ("accumulate", C.c_int32), ("splitk_ws", C.c_void_p), ("rowvec_ld", C.c_int64),
-                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("force_kernel", C.c_int32)]
+                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("b_dtype", C.c_int32), ("force_kernel", C.c_int32)]
 
 
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
@@ -84,11 +84,12 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         M = a0.numel() // a0.shape[-1]
     N = b_segs[0].shape[0]
     p.M, p.N, p.dtype, p.n_seg = M, N, DT[dt], len(a_segs)
+    p.b_dtype = DT[b_segs[0].dtype] if b_segs[0].dtype != dt else 0       # fp16 x bf16 operands: formats are per operand
     keep = []
     koff_auto = 0
     for s, (a, b) in enumerate(zip(a_segs, b_segs)):
-        if a.dtype != dt or b.dtype != dt:
-            raise _lib.ComatError("gemm: all operands must share the 16-bit dtype")
+        if a.dtype != dt or b.dtype not in DT or b.dtype == torch.float32 or b.dtype != b_segs[0].dtype:
+            raise _lib.ComatError("gemm: A segments share one 16-bit dtype, B segments share one (possibly the other) 16-bit dtype")
         if conv:
             a = a.contiguous()
             p.a_ld[s] = a.shape[-1]
@@ -136,17 +137,21 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         tiles = ((M + 127) // 128) * ((N + 127) // 128)
         if tiles <= 74 and kb >= 32:
             split_k = max(1, min(kb // 8, 148 // tiles))
-    if split_k > 1:
+    kb_total = sum((a.shape[-1] + 63) // 64 for a in a_segs) * (len(conv_taps) if conv else 1)
+    split_k = max(1, min(split_k, kb_total))
+    if accumulate:                          # out (fp32) += result: atomics from every K-split CTA, no workspace / second pass
+        if o2.dtype != torch.float32:
+            raise _lib.ComatError("gemm: accumulate needs an fp32 out")
+        p.split_k, p.accumulate = split_k, 1
+    elif split_k > 1:
         ws = torch.empty(split_k * M * N, dtype=torch.float32, device=a0.device)
-        p.split_k, p.splitk_ws, p.accumulate = split_k, ws.data_ptr(), int(accumulate)
+        p.split_k, p.splitk_ws = split_k, ws.data_ptr()
         keep.append(ws)
-    elif accumulate:
-        raise _lib.ComatError("gemm: accumulate=True needs split_k > 1")
     if PROFILE is not None and "keys_only" not in PROFILE:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.check(_lib.lib().comat_gemm(C.byref(p), _lib.stream_ptr()), "gemm")
-    _lib.count_launch(2 if split_k > 1 else 1)          # split-K adds the fixed-order reduction kernel
+    _lib.count_launch(2 if (split_k > 1 and not accumulate) else 1)          # split-K adds the fixed-order reduction kernel
     if PROFILE is not None:
         if "keys_only" in PROFILE:
             e0 = e1 = None
@@ -167,13 +172,13 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
 
     The weight-gradient shape: K is the token dimension (tens of thousands), M and N are feature dimensions.  Both operands
     go through TMA as MN-major panels and the tcgen05 descriptors carry the MN-major flag, so no transposed copies are made.
-    K-split partial sums are reduced in a fixed order (deterministic).  ``accumulate_into`` (fp32 (M, N), contiguous): the
-    result is ADDED to it by the split-K reduction pass (gradient accumulation over the K back-propagated sampler steps)
-    instead of going through a separate elementwise add."""
+    K-split partial sums are reduced in a fixed order (deterministic).  ``accumulate_into`` (fp32 (M, N), contiguous): every
+    K-split CTA ADDS its partial sum to it with vector fp32 atomics (gradient accumulation over K-splits and over the K
+    back-propagated sampler steps in one kernel: no partial workspace, no reduction pass, no elementwise add)."""
     _lib.require_cuda(a_km)
     dt = a_km.dtype
-    if dt not in (torch.float16, torch.bfloat16) or b_kn.dtype != dt:
-        raise _lib.ComatError("gemm_tn: operands must share a 16-bit dtype")
+    if dt not in (torch.float16, torch.bfloat16) or b_kn.dtype not in (torch.float16, torch.bfloat16):
+        raise _lib.ComatError("gemm_tn: operands must be 16-bit")
     if a_km.dim() != 2 or b_kn.dim() != 2 or a_km.shape[0] != b_kn.shape[0]:
         raise _lib.ComatError("gemm_tn: expected (K, M) and (K, N)")
     if a_km.stride(1) != 1:
@@ -187,16 +192,16 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
     p.a[0], p.a_ld[0], p.a_k[0] = a_km.data_ptr(), a_km.stride(0), K
     p.b[0], p.b_ld[0] = b_kn.data_ptr(), b_kn.stride(0)
     p.a_mn_major, p.b_mn_major = 1, 1
+    p.b_dtype = DT[b_kn.dtype] if b_kn.dtype != dt else 0
     p.alpha = alpha
     p.rows_per_group = 1
     kb = (K + 63) // 64
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if split_k == 0 and tiles <= 74 and kb >= 32:
         split_k = max(1, min(kb // 8, 148 // tiles))
-    acc = accumulate_into is not None and out_fp32 and kb >= 2 and accumulate_into.is_contiguous() and accumulate_into.dtype == torch.float32
+    acc = accumulate_into is not None and out_fp32 and accumulate_into.is_contiguous() and accumulate_into.dtype == torch.float32
     if acc:
-        split_k = max(split_k, 2)              # the accumulate epilogue lives in the split-K reduction pass
-        out = accumulate_into
+        out = accumulate_into                  # fp32 atomics from every K-split CTA (no workspace, no reduction pass)
         p.accumulate = 1
     else:
         out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else dt, device=a_km.device)
@@ -205,7 +210,10 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
     else:
         p.out16, p.out_ld = out.data_ptr(), N
     ws = None
-    if split_k > 1:
+    split_k = max(1, min(split_k, kb))
+    if acc:
+        p.split_k = split_k
+    elif split_k > 1:
         ws = torch.empty(split_k * M * N, dtype=torch.float32, device=a_km.device)
         p.split_k, p.splitk_ws = split_k, ws.data_ptr()
     timed = PROFILE is not None and "keys_only" not in PROFILE
@@ -213,7 +221,7 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.check(_lib.lib().comat_gemm(C.byref(p), _lib.stream_ptr()), "gemm_tn")
-    _lib.count_launch(2 if split_k > 1 else 1)
+    _lib.count_launch(2 if (split_k > 1 and not acc) else 1)
     if PROFILE is not None:
         if timed:
             e1.record()
@@ -221,7 +229,8 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
         PROFILE["events"].append((e0 if timed else None, e1 if timed else None, (M, N, (K,), -1, int(p.split_k), bool(out_fp32)), fl))
         PROFILE["flops"] += fl
     if accumulate_into is not None and not acc:
-        return accumulate_into + out
+        accumulate_into += out                 # K too short for the split-K epilogue: plain in-place add
+        return accumulate_into
     return out
 
 
@@ -397,3 +406,15 @@ def softmax_rows(x, dp=None):
     _call("comat_softmax_rows", x.data_ptr(), _p(dp.contiguous() if dp is not None else None), out.data_ptr(), x.shape[0], x.shape[1],
           0 if dp is None else 1, DT[x.dtype], _lib.stream_ptr())
     return out
+
+
+_lib.register_signature("comat_split_f32_bf16x2", [_vp, _vp, _vp, _ll, _f, _vp])
+
+
+def split_f32_bf16x2(src: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, alpha: float = 1.0):
+    """alpha * src (fp32, flat) ~= hi + lo (two bf16 tensors of the same numel): ~16 mantissa bits at fp32 range."""
+    _lib.require_cuda(src, hi, lo)
+    if src.dtype != torch.float32 or hi.dtype != torch.bfloat16 or lo.dtype != torch.bfloat16 or not (
+            src.is_contiguous() and hi.is_contiguous() and lo.is_contiguous()) or hi.numel() != src.numel() or lo.numel() != src.numel():
+        raise _lib.ComatError("split_f32_bf16x2: contiguous fp32 source and two bf16 destinations of the same size")
+    _call("comat_split_f32_bf16x2", src.data_ptr(), hi.data_ptr(), lo.data_ptr(), src.numel(), float(alpha), _lib.stream_ptr())

@@ -128,6 +128,8 @@ class CoMatTrainer:
         loss = logs["loss"]
         self.optimizer.zero_grad()                                                   # :658
         loss.backward()                                                              # :659
+        if hasattr(self.pipeline.unet, "finalize_lora_grads"):
+            self.pipeline.unet.finalize_lora_grads()                                 # accumulated dy^T x -> d up, d down (once per step)
         handle = self.optimizer.all_reduce()                                         # the only data-path collective
         self.optimizer.step(handle)                                                  # :661-663 (clip folded in)
         self.pipeline.unet.refresh_lora()
@@ -139,6 +141,8 @@ class CoMatTrainer:
                                                   num_inference_steps=a.total_step, batch={"latents": batch["real_latents"]})
             self.D_optimizer.zero_grad()
             d_loss.backward()
+            if hasattr(self.D.unet, "finalize_lora_grads"):
+                self.D.unet.finalize_lora_grads()
             h = self.D_optimizer.all_reduce()
             self.D_optimizer.step(h)
             self.D.unet.refresh_lora()

@@ -128,7 +128,8 @@ typedef struct {
   int32_t force_bn;         /* 0 = auto; else 32/64/128/160/256 (tuning / tests) */
   int32_t split_k;          /* >1: split the K loop over grid.z; needs splitk_ws = split_k*M*N floats; a second pass
                                reduces the partials in a fixed order and applies the epilogue */
-  int32_t accumulate;       /* split-K only: out32 += result (gradient accumulation over the K training steps) */
+  int32_t accumulate;       /* out32 += alpha * A.B with vector fp32 atomics from every (K-split) CTA: gradient accumulation over
+                               K-splits and over calls in one kernel; fp32 output only, no bias / act / residual; splitk_ws unused */
   float* splitk_ws;
   int64_t rowvec_ld;        /* row pitch of rowvec in floats (0 = N): lets all ResBlock time-embedding projections of a UNet call
                                come from ONE GEMM whose output is sliced per block */
@@ -137,6 +138,8 @@ typedef struct {
                                training_utils/pipeline.py:94-115's backward) read dy / t / x as they lie, no transposed copies.
                                Plain mode, one K segment only. */
   int32_t b_mn_major;       /* 1: b[0] is stored [K, N] row-major (N contiguous) */
+  int32_t b_dtype;          /* 0 or equal to dtype.  (A descriptor whose B format differs from A's faults on sm_100a, so mixed
+                               fp16 x bf16 operands return COMAT_ERR_UNSUPPORTED.) */
   int32_t force_kernel;     /* 0 = auto; 1 = one-tile-per-CTA kernel; 2 = persistent kernel; 3 = CTA-pair (cta_group::2) kernel
                                (tuning table / tests) */
 } comat_gemm_params;
@@ -231,6 +234,17 @@ size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int H, int d);
 int comat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
                         const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
                         int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal, void* stream);
+/* Same with explicit row pitches (elements) for q, k and v (column slices of a fused q|k|v / k|v projection output);
+ * o, dO and the three outputs are contiguous (n, L, H*d). */
+int comat_attention_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
+                                const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
+                                int Lq, int Lk, int H, int d, long long q_ld, long long k_ld, long long v_ld, float scale,
+                                int dtype, const int* kv_lens, int causal, void* stream);
+
+/* fp32 -> two bf16 tensors with  alpha * src ~= hi + lo  (hi = bf16(alpha*src), lo = bf16(alpha*src - hi)): ~16 mantissa bits at
+ * fp32 range.  Used to feed the fp32-accumulated full-size LoRA gradient products  G = dy^T x  to the 16-bit tensor-core GEMMs
+ * that project them onto the LoRA factors (d up = G down^T, d down = up^T G; training_utils/pipeline.py:94-115 backward). */
+int comat_split_f32_bf16x2(const float* src, void* hi, void* lo, long long n, float alpha, void* stream);
 
 /* Separable table-driven 2-D resampling with a fused per-channel affine (fp32 NCHW):
  *   out[b,c,oy,ox] = scale[c] * sum_{ky<yc[oy]} sum_{kx<xc[ox]} wy[oy*KY+ky] * wx[ox*KX+kx] * in[b,c,ys[oy]+ky,xs[ox]+kx] + shift[c]

@@ -41,9 +41,12 @@ def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_grou
         y = F.gelu(y)
     if residual is not None:
         y = y + residual.reshape(M, N).double()
-    y = y.to(torch.float32 if out_fp32 else a0.dtype)
+    y = y.to(torch.float32 if (out_fp32 or (out is not None and out.dtype == torch.float32)) else a0.dtype)
     if out is not None:
-        out.reshape(M, N).copy_(y)          # in-place destination (row-slice views of fused weight buffers, static graph inputs)
+        if accumulate:
+            out.reshape(M, N).add_(y.to(out.dtype))
+        else:
+            out.reshape(M, N).copy_(y)      # in-place destination (row-slice views of fused weight buffers, static graph inputs)
         y = out
     if conv_taps is not None:
         return y.reshape(n, H, W, N)
@@ -161,9 +164,16 @@ def gemm_tn(a_km, b_kn, *, out_fp32=True, split_k=0, accumulate_into=None, alpha
     return y
 
 
+def split_f32_bf16x2(src, hi, lo, alpha=1.0):
+    v = src.float() * alpha
+    h = v.to(hi.dtype)
+    hi.copy_(h)
+    lo.copy_((v - h.float()).to(lo.dtype))
+
+
 def install(monkeypatch):
     from comat_b200 import ops
-    for name in ("gemm", "gemm_tn", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
+    for name in ("gemm", "gemm_tn", "split_f32_bf16x2", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
                  "elementwise", "spatial", "transpose16", "concat_channels", "latent_to_nhwc", "nhwc_to_nchw_f32"):
         monkeypatch.setattr(ops, name, globals()[name])
 

@@ -138,3 +138,26 @@ def test_unfused_attention_vae_mid_block_geometry():
     assert rel(o.float(), o_ref) < 4e-3
     for name, a, b in (("dq", dq, gq), ("dk", dk, gk), ("dv", dv, gv)):
         assert rel(a.float(), b) < 1e-2, (name, rel(a.float(), b))
+
+
+@pytest.mark.parametrize("n,L,T,H,d", [(2, 1024, 77, 8, 40), (1, 300, 77, 10, 64), (2, 256, 77, 8, 80)])
+def test_attention_backward_reads_fused_projection_slices_in_place(n, L, T, H, d):
+    from comat_b200 import attention as A
+    torch.manual_seed(L + d + 1)
+    C = H * d
+    qkv = torch.randn(n, L, 3 * C, device="cuda").half()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    do = torch.randn(n, L, C, device="cuda").half()
+    o, _, lse = A.attention_fwd_native(q, k, v, H, need_lse=True)
+    got = A.attention_bwd_native(q, k, v, o, lse, None, H, do, None)
+    want = A.attention_bwd_native(q.contiguous(), k.contiguous(), v.contiguous(), o, lse, None, H, do, None)
+    for a, b in zip(got, want):
+        assert a.is_contiguous() and torch.equal(a, b)
+    kv = torch.randn(n, T, 2 * C, device="cuda").half()
+    qc = torch.randn(n, L, C, device="cuda").half()
+    dp = torch.randn(n * H, L, T, device="cuda") * 0.5
+    o, p, lse = A.attention_fwd_native(qc, kv[..., :C], kv[..., C:], H, export_probs=True, need_lse=True)
+    got = A.attention_bwd_native(qc, kv[..., :C], kv[..., C:], o, lse, p, H, do, dp)
+    want = A.attention_bwd_native(qc, kv[..., :C].contiguous(), kv[..., C:].contiguous(), o, lse, p, H, do, dp)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

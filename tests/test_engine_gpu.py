@@ -20,11 +20,13 @@ def _tiny(sdxl=False):
     return unet.cuda(), params
 
 
+@pytest.mark.parametrize("impl", ["product", "explicit"])
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 8e-3), (torch.bfloat16, 5e-2)])
-def test_unet_engine_fwd_bwd_vs_oracle(dtype, tol):
+def test_unet_engine_fwd_bwd_vs_oracle(dtype, tol, impl):
     from comat_b200 import engine as E, ops
     unet, _ = _tiny()
     eng = E.UNetEngine(unet, dtype)
+    eng.lora_train_impl = impl
     g = torch.Generator().manual_seed(0)
     n, hw = 2, 32
     x = torch.randn(n, 4, hw, hw, generator=g).cuda()
@@ -46,10 +48,25 @@ def test_unet_engine_fwd_bwd_vs_oracle(dtype, tol):
     tape.backward()
     dx = ops.nhwc_to_nchw_f32(xv.g, 4)
     assert rel(dx, grads_ref[0]) < 3 * tol
-    eg = eng.lora_grads()
+    eg = eng.finalize_lora_grads(1.0, into_param_grads=False) if impl == "product" else eng.lora_grads()
     assert len(eg) == len(params)
     worst = max(rel(a, b) for a, b in zip(eg, grads_ref[1:]))
     assert worst < 6 * tol, worst
+    if impl == "product":
+        # accumulation over passes + projection straight into param.grad (what the trainer does)
+        for p_ in params:
+            p_.grad = torch.zeros_like(p_)
+        for _ in range(2):
+            tape = E.Tape()
+            xv = E.Var(ops.latent_to_nhwc(x, dtype, 64))
+            out = eng.forward(tape, xv, t, ctx.to(dtype))
+            out.g = dy.permute(0, 2, 3, 1).contiguous().to(dtype)
+            tape.backward()
+        assert eng.G_dirty
+        eng.finalize_lora_grads(0.5, into_param_grads=True)
+        assert not eng.G_dirty and float(eng._G.abs().max()) == 0.0
+        worst = max(rel(p_.grad, b) for p_, b in zip(params, grads_ref[1:]))
+        assert worst < 6 * tol, worst
 
 
 def test_unet_engine_sdxl_geometry_and_capture():

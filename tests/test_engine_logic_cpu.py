@@ -20,13 +20,17 @@ def _tiny(sdxl=False):
     return unet
 
 
+@pytest.mark.parametrize("impl", ["product", "explicit"])
 @pytest.mark.parametrize("sdxl", [False, True])
-def test_unet_executor_matches_oracle(monkeypatch, sdxl):
+def test_unet_executor_matches_oracle(monkeypatch, sdxl, impl):
+    """taped forward + backward with LoRA weight gradients, both gradient forms: 'product' (G = dy^T x accumulated, projected
+    onto the factors at the end) and 'explicit' (the literal LoRA branch)."""
     EMU.install(monkeypatch)
     from comat_b200 import engine as E, ops
     unet = _tiny(sdxl)
     dtype = torch.float32
     eng = E.UNetEngine(unet, dtype)
+    eng.lora_train_impl = impl
     g = torch.Generator().manual_seed(0)
     n, hw = 2, 16
     x = torch.randn(n, 4, hw, hw, generator=g)
@@ -48,9 +52,20 @@ def test_unet_executor_matches_oracle(monkeypatch, sdxl):
     out.g = dy.permute(0, 2, 3, 1).contiguous()
     tape.backward()
     assert rel(ops.nhwc_to_nchw_f32(xv.g, 4), grads_ref[0]) < 1e-4
-    eg = eng.lora_grads()
+    eg = eng.finalize_lora_grads(1.0, into_param_grads=False) if impl == "product" else eng.lora_grads()
     assert len(eg) == len(params)
+    # 'product' feeds G to the projection GEMMs as bf16 hi + lo (16 mantissa bits)
     assert max(rel(a, b) for a, b in zip(eg, grads_ref[1:])) < 1e-3
+    if impl == "product":                                        # a second pass accumulates: twice the gradient
+        tape = E.Tape()
+        xv = E.Var(ops.latent_to_nhwc(x, dtype, 64))
+        for _ in range(2):
+            out = eng.forward(tape, xv, t, ctx, added_cond=added)
+            out.g = dy.permute(0, 2, 3, 1).contiguous()
+            tape.backward()
+        eg2 = eng.finalize_lora_grads(1.0, into_param_grads=False)
+        assert max(rel(a, 2 * b) for a, b in zip(eg2, grads_ref[1:])) < 1e-3
+        assert float(eng._G.abs().max()) == 0.0 and not eng.G_dirty
 
 
 def test_vae_executor_matches_oracle(monkeypatch):

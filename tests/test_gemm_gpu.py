@@ -208,3 +208,34 @@ def test_pair_kernel_conv_and_fused_epilogue(n, H, W, C, Cout, bn):
     out2 = ops.gemm([xa, t], [w2, up], act="silu", force_bn=bn, kernel="pair")
     ref2 = F.silu(xa.float() @ w2.float().t() + t.float() @ up.float().t())
     assert _rel(out2.float(), ref2)[0] < 3e-3
+
+
+def test_hi_lo_split_projection():
+    """fp32 G fed to the tensor cores as bf16 hi + lo, factors as bf16 hi + lo (one operand format per MMA): how the accumulated
+    LoRA product gradient is projected onto the factors; ~16 mantissa bits at fp32 range."""
+    from comat_b200 import ops, _lib
+    g = torch.Generator(device="cuda").manual_seed(11)
+    N, K, r = 320, 640, 128
+    G = torch.randn(N, K, device="cuda", generator=g) * 3.7e3                  # loss-scaled magnitudes, beyond fp16 comfort
+    hi, lo = torch.empty(N * K, device="cuda", dtype=torch.bfloat16), torch.empty(N * K, device="cuda", dtype=torch.bfloat16)
+    ops.split_f32_bf16x2(G.reshape(-1), hi, lo, 0.25)
+    rec = hi.float() + lo.float()
+    assert float(((rec - 0.25 * G.reshape(-1)).abs() / (0.25 * G.reshape(-1)).abs().clamp_min(1e-3)).max()) < 2 ** -15
+    hi, lo = hi.view(N, K), lo.view(N, K)
+    down = torch.randn(r, K, device="cuda", generator=g) / r ** 0.5
+    up = torch.randn(N, r, device="cuda", generator=g) * 0.05
+    dh, uh = down.bfloat16(), up.bfloat16()
+    dl, ul = (down - dh.float()).bfloat16(), (up - uh.float()).bfloat16()
+    g_up = torch.ones(N, r, device="cuda")
+    ops.gemm([hi, lo], [dh, dh], out=g_up, split_k=2, accumulate=True)
+    ops.gemm([hi], [dl], out=g_up, split_k=2, accumulate=True)
+    ref_up = 0.25 * G.double() @ down.double().t()
+    assert _rel(g_up - 1, ref_up)[0] < 5e-5
+    g_down = torch.zeros(r, K, device="cuda")
+    ops.gemm_tn(uh, hi, accumulate_into=g_down)
+    ops.gemm_tn(uh, lo, accumulate_into=g_down)
+    ops.gemm_tn(ul, hi, accumulate_into=g_down)
+    ref_down = up.double().t() @ (0.25 * G.double())
+    assert _rel(g_down, ref_down)[0] < 5e-5
+    with pytest.raises(_lib.ComatError):                                      # one operand format per MMA
+        ops.gemm([hi], [dh.half()], out_fp32=True)

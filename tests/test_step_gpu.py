@@ -73,6 +73,7 @@ def test_train_step_losses_and_grads_vs_oracle(dtype):
     g_ref = torch.autograd.grad(ref["loss"], [p for p in o_unet.parameters() if p.requires_grad], allow_unused=True)
     tr.optimizer.zero_grad()
     logs["loss"].backward()
+    tr.pipeline.unet.finalize_lora_grads()          # trainer protocol: accumulated dy^T x products -> d up / d down, once per step
     got = tr.optimizer.grad.double()
     want = torch.cat([(gr if gr is not None else torch.zeros_like(p)).reshape(-1) for p, gr in zip(tr.G_parameters, g_ref)]).double()
     cos = float((got * want).sum() / (got.norm() * want.norm()))

@@ -102,6 +102,7 @@ def test_train_step_matches_oracle_step(monkeypatch):
     g_ref = torch.autograd.grad(ref["loss"], [p for p in o_unet.parameters() if p.requires_grad], allow_unused=True)
     tr.optimizer.zero_grad()
     logs["loss"].backward()
+    tr.pipeline.unet.finalize_lora_grads()      # trainer protocol: accumulated dy^T x products -> d up / d down, once per step
     off = 0
     for p, gr in zip(tr.G_parameters, g_ref):
         got = tr.optimizer.grad[off:off + p.numel()].view_as(p)
