@@ -279,6 +279,7 @@ def main():
             if host_inputs:
                 loss_host = logs["step_loss"].float().cpu()       # D2H read of the step's result
                 d2h = loss_host.numel() * 4
+        trainer.sync()                                            # side-stream optimiser tails of the last step join the timed stream
         e1.record()
         timed.host_issue_s = (time.perf_counter() - th0) / n_steps    # time the host needed to enqueue a step (no sync inside)
         barrier()
@@ -379,9 +380,11 @@ def main():
                 fh.write(f"\n(gap analysis unavailable: {ex!r})\n")
         return 0
     if a.profile_step:
+        trainer.sync()
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         trainer.train_step(dev_batches[0])
+        trainer.sync()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return 0

@@ -50,6 +50,54 @@ class CoMatTrainer:
         self.train_layer_ls = getattr(args, "train_layer_ls", None) or (
             ["mid_8", "up_16", "up_32", "up_64"] if "sdxl" not in args.pretrain_model_name else ["mid_16", "up_16", "up_32"])
         self.global_step = 0
+        # The tail of each update (projection of the accumulated LoRA product gradients: ~640 tiny GEMMs per UNet; gradient
+        # all-reduce; clip + AdamW; refresh of the 16-bit operand images) touches only persistent buffers and is independent
+        # of what the main stream does next: the generator's update runs beside the discriminator step, the discriminator's
+        # beside the next step's rollout.  It is issued on a side stream and joined (event wait) right before the updated
+        # network is used again.  No tensor is allocated on the side stream (caching-allocator safety).
+        self.overlap_updates = bool(self.G_parameters and self.G_parameters[0].is_cuda)
+        self._side_stream = None
+        self._ev_G = self._ev_D = None
+
+    # ---- side-stream plumbing
+    def _run_update(self, fn, which):
+        if not self.overlap_updates:
+            fn()
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._side_stream.wait_stream(main)                  # after the backward pass that produced the gradients
+        with torch.cuda.stream(self._side_stream):
+            fn()
+            ev = torch.cuda.Event()
+            ev.record(self._side_stream)
+        setattr(self, which, ev)
+
+    def _join(self, which):
+        ev = getattr(self, which)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            setattr(self, which, None)
+
+    def sync(self):
+        """make the current stream wait for both outstanding updates (end of training / end of a timed region)."""
+        self._join("_ev_G")
+        self._join("_ev_D")
+
+    def _g_update(self):
+        if hasattr(self.pipeline.unet, "finalize_lora_grads"):
+            self.pipeline.unet.finalize_lora_grads()                                 # accumulated dy^T x -> d up, d down (once per step)
+        handle = self.optimizer.all_reduce()                                         # SURVEY 8e: the only data-path collective
+        self.optimizer.step(handle)                                                  # :661-663 (clip folded in)
+        self.pipeline.unet.refresh_lora()
+
+    def _d_update(self):
+        if hasattr(self.D.unet, "finalize_lora_grads"):
+            self.D.unet.finalize_lora_grads()
+        h = self.D_optimizer.all_reduce()
+        self.D_optimizer.step(h)
+        self.D.unet.refresh_lora()
 
     # -- training_script.py:563-566, :589-590
     def select_steps(self):
@@ -89,6 +137,7 @@ class CoMatTrainer:
         logs = {k: v.detach() for k, v in rewards.items()}
         loss = -rewards["total"].mean()                                              # :618
         if a.gan_loss:
+            self._join("_ev_D")                                                      # the discriminator's previous update is in
             g = self.D.D_sd_pipeline_forward(training_latents, side="G", negative_prompt_embeds=batch["gan_null_embeds"],
                                              num_inference_steps=a.total_step)
             loss = loss + a.gan_loss_weight * g                                      # :620-625
@@ -124,15 +173,12 @@ class CoMatTrainer:
     def train_step(self, batch: Dict) -> Dict[str, torch.Tensor]:
         a = self.args
         self._gc_before_step()
+        self._join("_ev_G")                                                          # the generator's previous update is in
         logs = self.g_losses(batch)
         loss = logs["loss"]
         self.optimizer.zero_grad()                                                   # :658
         loss.backward()                                                              # :659
-        if hasattr(self.pipeline.unet, "finalize_lora_grads"):
-            self.pipeline.unet.finalize_lora_grads()                                 # accumulated dy^T x -> d up, d down (once per step)
-        handle = self.optimizer.all_reduce()                                         # the only data-path collective
-        self.optimizer.step(handle)                                                  # :661-663 (clip folded in)
-        self.pipeline.unet.refresh_lora()
+        self._run_update(self._g_update, "_ev_G")                                    # :661-664, beside the discriminator step
         out = {k: v for k, v in logs.items() if not k.startswith("_")}
         out["step_loss"] = loss.detach()
         out.update(logs.get("_norm_holder", {}))
@@ -141,11 +187,7 @@ class CoMatTrainer:
                                                   num_inference_steps=a.total_step, batch={"latents": batch["real_latents"]})
             self.D_optimizer.zero_grad()
             d_loss.backward()
-            if hasattr(self.D.unet, "finalize_lora_grads"):
-                self.D.unet.finalize_lora_grads()
-            h = self.D_optimizer.all_reduce()
-            self.D_optimizer.step(h)
-            self.D.unet.refresh_lora()
+            self._run_update(self._d_update, "_ev_D")                                # :689-694, beside the next step's rollout
             out["D_loss"] = d_loss.detach()
         self.global_step += 1
         self._gc_after_step()

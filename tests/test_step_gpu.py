@@ -81,3 +81,53 @@ def test_train_step_losses_and_grads_vs_oracle(dtype):
     assert cos > 0.98 and abs(float(got.norm() / want.norm()) - 1) < 0.1
     out = tr.train_step(batch)
     assert torch.isfinite(out["step_loss"]) and torch.isfinite(out["D_loss"])
+
+
+def _make_trainer(dtype, overlap):
+    from comat_b200 import synthetic
+    from comat_b200.caption import Blip, CaptionModelWrapper
+    from comat_b200.gan import D_sd
+    from comat_b200.modules import EngineUNet, EngineVAE
+    from comat_b200.pipelines import AttentionStore, AttrConcenTrainableSDPipeline, register_attention_control
+    from comat_b200.trainer import CoMatTrainer
+    dev = torch.device("cuda")
+    B, S, K, res = 2, 4, 2, 256
+    unet_p, vae_p = synthetic.build_sd15(dev, dtype, rank=8, seed=7, tiny=True, lora_up_std=0.05)
+    d_p, _ = synthetic.build_sd15(dev, dtype, rank=8, seed=8, tiny=True)
+    torch.manual_seed(21)
+    blip_model = R.make_blip(large=False).to(dev)
+    head = torch.nn.Sequential(torch.nn.Linear(4, 1)).to(dev)
+    args = synthetic.default_args(pretrain_model_name="sd_1_5_attrcon", train_batch_size=B, K=K, total_step=S, gan_loss=True,
+                                  gan_model_arch="gansd_1_5", attrcon_train_steps=2, resolution=res, max_grad_norm=0.1, seed=3,
+                                  learning_rate=1e-3, learning_rate_D=1e-3)
+    args.train_layer_ls = ["up_8", "up_16", "up_32"]
+    pipe = AttrConcenTrainableSDPipeline(EngineVAE(vae_p, dtype), EngineUNet(unet_p, dtype))
+    register_attention_control(pipe, AttentionStore(args.train_layer_ls))
+    D = D_sd(EngineUNet(d_p, dtype), mlp=head)
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(blip_model)), D, rng=random.Random(5))
+    tr.overlap_updates = overlap
+    batches = [synthetic.batch_to_device(synthetic.synthetic_batch(B, 40 + i, 64, res, True, True), dev)[0] for i in range(3)]
+    return tr, batches
+
+
+def test_side_stream_updates_match_serial_updates():
+    """the optimiser tails (gradient projection, clip + AdamW, operand refresh) issued on the side stream next to the
+    discriminator step / the next rollout give the same parameters and losses as the serial schedule over several steps."""
+    results = []
+    for overlap in (False, True):
+        tr, batches = _make_trainer(torch.float16, overlap)
+        losses = []
+        for i in range(4):
+            out = tr.train_step(batches[i % len(batches)])
+            losses.append((float(out["step_loss"]), float(out["D_loss"])))
+        tr.sync()
+        torch.cuda.synchronize()
+        results.append((losses, tr.optimizer.flat.clone(), tr.D_optimizer.flat.clone()))
+    (l0, g0, d0), (l1, g1, d1) = results
+    # same arithmetic on both schedules; fp32 atomics / GroupNorm shared-memory atomics reorder sums, hence tolerances
+    for (a, b), (c, d) in zip(l0, l1):
+        assert abs(a - c) <= 2e-3 * max(1.0, abs(a)) and abs(b - d) <= 2e-3 * max(1.0, abs(b)), (l0, l1)
+    assert float((g0 - g1).abs().max()) <= 5e-2 * float(g0.abs().max())
+    assert float((d0 - d1).abs().max()) <= 5e-2 * float(d0.abs().max())
+    moved = float((g0 - _make_trainer(torch.float16, False)[0].optimizer.flat).abs().max())
+    assert moved > 1e-3                                   # the four steps did change the parameters
