@@ -75,10 +75,12 @@ class _GraphedForward:
     """One captured no-grad UNet forward (fixed shapes): ~700 launches replayed by a single cudaGraphLaunch.
     CUDA graphs instead of a tracing compiler — the executor's Python runs once, at capture."""
 
-    def __init__(self, mod: "EngineUNet", sample, t, ehs):
+    def __init__(self, mod: "EngineUNet", sample, t, ehs, added=None):
         from . import _lib
         eng = mod.engine
         self.mod = mod
+        # SDXL's pooled-text / time-id conditioning (TrainableSDPipeline.py:772-784): static copies, refreshed per call (tiny)
+        self.added = None if added is None else {k: v.detach().clone() for k, v in added.items()}
         self.x = torch.empty_like(sample)
         self.t = torch.zeros((), dtype=torch.int64, device=sample.device)
         self.x.copy_(sample); self.t.copy_(t.reshape(()))
@@ -89,7 +91,8 @@ class _GraphedForward:
         self._key = (ehs, ehs._version, eng.lora_version)
 
         def run():
-            out = eng.forward(None, E.Var(ops.latent_to_nhwc(self.x, eng.dtype, 64), False), self.t, self.ehs16, cross_kv=self.kv)
+            out = eng.forward(None, E.Var(ops.latent_to_nhwc(self.x, eng.dtype, 64), False), self.t, self.ehs16, cross_kv=self.kv,
+                              added_cond=self.added)
             return ops.nhwc_to_nchw_f32(out.v, mod.out_channels)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -102,11 +105,14 @@ class _GraphedForward:
             self.out = run()
         self.launches = _lib.LAUNCH_COUNT - l0
 
-    def __call__(self, sample, t, ehs):
+    def __call__(self, sample, t, ehs, added=None):
         from . import _lib
         eng = self.mod.engine
         eng.ensure_merged()                                   # eager, before the replay reads the folded weights
         self.x.copy_(sample); self.t.copy_(t.reshape(()))
+        if self.added is not None:
+            for k, v in self.added.items():
+                v.copy_(added[k])
         if not (self._key[0] is ehs and self._key[1] == ehs._version and self._key[2] == eng.lora_version):
             self.ehs16.copy_(ehs)
             eng.cross_kv(self.ehs16, out=self.kv)
@@ -189,12 +195,13 @@ class EngineUNet(torch.nn.Module):
             ckv = self._context_kv(encoder_hidden_states, store=capture is None)
             outs = _UNetFn.apply(self, sample, t, encoder_hidden_states, added_cond_kwargs, capture, ckv, *params)
             eps, probs = outs[0], outs[1:]
-        elif self.use_graphs and capture is None and added_cond_kwargs is None and sample.is_cuda:
-            key = (tuple(sample.shape), tuple(encoder_hidden_states.shape), sample.dtype, encoder_hidden_states.dtype)
+        elif self.use_graphs and capture is None and sample.is_cuda:
+            key = (tuple(sample.shape), tuple(encoder_hidden_states.shape), sample.dtype, encoder_hidden_states.dtype,
+                   None if added_cond_kwargs is None else tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(added_cond_kwargs.items())))
             if key not in self._graphs:
                 self.engine.ensure_merged()
-                self._graphs[key] = _GraphedForward(self, sample.detach(), t, encoder_hidden_states)
-            eps = self._graphs[key](sample.detach(), t, encoder_hidden_states).to(sample.dtype)
+                self._graphs[key] = _GraphedForward(self, sample.detach(), t, encoder_hidden_states, added_cond_kwargs)
+            eps = self._graphs[key](sample.detach(), t, encoder_hidden_states, added_cond_kwargs).to(sample.dtype)
             probs = ()
         else:
             eng = self.engine

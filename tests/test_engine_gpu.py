@@ -193,3 +193,27 @@ def test_engine_unet_module_graph_and_eager_share_context_cache():
         assert rel(e2, e1) > 2e-2
     ref = unet(x, t, ctx, return_dict=False)[0]
     assert rel(e2, ref) < 8e-3
+
+
+def test_engine_unet_module_graph_sdxl_conditioning():
+    """SDXL geometry: the CUDA-graphed no-grad forward takes the pooled-text / time-id conditioning as static inputs and
+    follows their values call by call."""
+    from comat_b200.modules import EngineUNet
+    unet, _ = _tiny(sdxl=True)
+    mod = EngineUNet(unet, torch.float16)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 4, 32, 32, generator=g).cuda()
+    ctx = torch.randn(2, 77, 64, generator=g).cuda()
+    t = torch.tensor(301, device="cuda")
+    mk = lambda: dict(text_embeds=torch.randn(2, 16, generator=g).cuda(), time_ids=torch.tensor([[512., 512, 0, 0, 512, 512]] * 2).cuda())
+    a1, a2 = mk(), mk()
+    with torch.no_grad():
+        e1 = mod(x, t, encoder_hidden_states=ctx, added_cond_kwargs=a1)[0].clone()
+        e2 = mod(x, t, encoder_hidden_states=ctx, added_cond_kwargs=a2)[0].clone()
+        assert rel(e2, e1) > 1e-2
+        mod.use_graphs = True
+        for a, want in ((a1, e1), (a2, e2), (a2, e2), (a1, e1)):
+            assert rel(mod(x, t, encoder_hidden_states=ctx, added_cond_kwargs=a)[0], want) < 2e-3
+        assert len(mod._graphs) == 1
+    ref = unet(x, t, ctx, added_cond_kwargs=a1, return_dict=False)[0]
+    assert rel(e1, ref) < 8e-3

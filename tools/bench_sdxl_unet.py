@@ -48,7 +48,19 @@ with torch.no_grad():
         mod(x, t, encoder_hidden_states=ctx, added_cond_kwargs=added)
     e1.record(); torch.cuda.synchronize()
 msf = e0.elapsed_time(e1) / 3
+mod.use_graphs = True                       # the same no-grad forward replayed from a CUDA graph (what the rollout's no-grad steps use)
+with torch.no_grad():
+    for _ in range(2):
+        eg = mod(x, t, encoder_hidden_states=ctx, added_cond_kwargs=added)[0]
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        mod(x, t, encoder_hidden_states=ctx, added_cond_kwargs=added)
+    e1.record(); torch.cuda.synchronize()
+msg = e0.elapsed_time(e1) / 3
+assert torch.isfinite(eg).all()
 F = {64: 1.589, 128: 6.76}.get(lat)
-print(f"SDXL UNet latent {lat}x{lat} n={n}: fwd {msf:.1f} ms" + (f" ({n * F / msf * 1e3:.0f} TFLOP/s)" if F else "") +
+print(f"SDXL UNet latent {lat}x{lat} n={n}: fwd eager {msf:.1f} ms" + (f" ({n * F / msf * 1e3:.0f} TFLOP/s)" if F else "") +
+      f", fwd graph {msg:.1f} ms" + (f" ({n * F / msg * 1e3:.0f} TFLOP/s)" if F else "") +
       f", fwd+bwd(+LoRA grads) {ms:.1f} ms" + (f" ({3 * n * F / ms * 1e3:.0f} TFLOP/s at 3x fwd FLOPs)" if F else "") +
       f", |eps| {float(eps.abs().mean()):.3f}, LoRA grad norm {gn:.3e}, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GB")
