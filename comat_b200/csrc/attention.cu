@@ -257,19 +257,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr int LA = 8;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
       unsigned char* prow = sP + sb * Cf::P_BYTES + (r / 8) * 1024 + (r % 8) * 128;
-      // every POLY-th exponential runs on the FMA pipe instead of the SFU (indices are compile-time after unrolling)
-      constexpr int POLY = (D <= 64) ? 4 : 0;     // only where the kernel is SFU-bound (d <= 64: < 256 tensor FLOPs per ex2)
-#define ATT_EXP2(idx, x) ((POLY != 0 && ((idx) % (POLY ? POLY : 1)) == (POLY ? POLY : 1) - 1) ? exp2_poly(x) : fast_exp2(x))
 #pragma unroll
-      for (int i = 0; i < LA; ++i) sv[i] = ATT_EXP2(i, fmaf(sv[i], sl2, -mneg));
+      for (int i = 0; i < LA; ++i) sv[i] = fast_exp2(fmaf(sv[i], sl2, -mneg));
 #pragma unroll
       for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           if (c0 + i + LA < ATT_BN) {
-            sv[c0 + i + LA] = ATT_EXP2(c0 + i + LA, fmaf(sv[c0 + i + LA], sl2, -mneg));
-            sv[c0 + i + LA + 1] = ATT_EXP2(c0 + i + LA + 1, fmaf(sv[c0 + i + LA + 1], sl2, -mneg));
+            sv[c0 + i + LA] = fast_exp2(fmaf(sv[c0 + i + LA], sl2, -mneg));
+            sv[c0 + i + LA + 1] = fast_exp2(fmaf(sv[c0 + i + LA + 1], sl2, -mneg));
           }
           const float e0 = sv[c0 + i], e1 = sv[c0 + i + 1];
           ls[(i / 2) & 3] += e0 + e1;
@@ -282,7 +279,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-#undef ATT_EXP2
       tc_fence_before();
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       mbar_arrive(&p_full[sb]);

@@ -86,22 +86,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// 2^x on the FMA / ALU pipes (no SFU): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, degree-4 polynomial for
-// 2^f on [-0.5, 0.5] (relative error < 5e-5), n added into the exponent field.  x <= 126; x <= -125 returns ~2^-125 (== 0 for
-// every 16-bit consumer).  Used for a FRACTION of the softmax exponentials of the d = 40 attention forward, which is bound by
-// the 16 ex2/clk/SM SFU rate: tools/bench_sfu.cu measures 15.9 ex2/clk/SM on the SFU and 11.8 /clk/SM for this sequence.
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;
-  const float n = t - 12582912.f;
-  const float f = x - n;
-  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
-  p = fmaf(p, f, 0.2402265070f);
-  p = fmaf(p, f, 0.6931471806f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
