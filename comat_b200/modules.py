@@ -154,9 +154,13 @@ class EngineUNet(torch.nn.Module):
     def lora_parameters(self):
         return self.engine.lora_params()
 
-    def refresh_lora(self):
-        """call after every optimiser step: re-materialise the 16-bit LoRA operands from the fp32 masters."""
+    def refresh_lora(self, rebuild_folded: bool = False):
+        """call after every optimiser step: re-materialise the 16-bit LoRA operands from the fp32 masters.
+        ``rebuild_folded``: also rebuild the LoRA-folded projection weights now (the trainer does, on its side stream) instead of
+        lazily at the next forward."""
         self.engine.refresh_lora()
+        if rebuild_folded and self.engine._merged_version >= 0:
+            self.engine.ensure_merged(transposed=self.engine._merged_t)
 
     def finalize_lora_grads(self):
         """project the product gradients accumulated by the backward passes since the last call onto the LoRA factors and

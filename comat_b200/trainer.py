@@ -90,14 +90,21 @@ class CoMatTrainer:
             self.pipeline.unet.finalize_lora_grads()                                 # accumulated dy^T x -> d up, d down (once per step)
         handle = self.optimizer.all_reduce()                                         # the only data-path collective
         self.optimizer.step(handle)                                                  # :661-663 (clip folded in)
-        self.pipeline.unet.refresh_lora()
+        self._refresh(self.pipeline.unet)
+
+    @staticmethod
+    def _refresh(unet):
+        try:
+            unet.refresh_lora(rebuild_folded=True)      # EngineUNet: folded weights rebuilt here, off the critical path
+        except TypeError:
+            unet.refresh_lora()
 
     def _d_update(self):
         if hasattr(self.D.unet, "finalize_lora_grads"):
             self.D.unet.finalize_lora_grads()
         h = self.D_optimizer.all_reduce()
         self.D_optimizer.step(h)
-        self.D.unet.refresh_lora()
+        self._refresh(self.D.unet)
 
     # -- training_script.py:563-566, :589-590
     def select_steps(self):
