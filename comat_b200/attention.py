@@ -16,8 +16,9 @@ import ctypes as C
 
 from . import _lib
 
-IMPL = "native"          # forward: tcgen05 kernel when the shape is covered; backward: library path for now (round 1)
+IMPL = "native"          # forward and backward: tcgen05 kernels for every head dim in NATIVE_HEAD_DIMS (all shapes of the step)
 LIBRARY_CALLS = 0
+ALLOW_LIBRARY_PATH = False   # the aten comparator below is opt-in (tests switch it on); the product raises instead of falling back
 NATIVE_HEAD_DIMS = (16, 32, 40, 64, 80, 128, 160)
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 _lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
@@ -114,6 +115,9 @@ def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
         if NATIVE_BWD:
             return o, probs, ("native", q, k, v, o, lse, probs, heads)      # strided views are read in place by the backward too
         return o, probs, (q, k, v, heads, export_probs)
+    if not ALLOW_LIBRARY_PATH:
+        raise _lib.ComatError(f"attention: no native kernel for this call (device {q.device.type}, dtype {q.dtype}, head dim "
+                              f"{q.shape[-1] // heads}, keys {k.shape[1]}, export={export_probs}); comat_b200 has no fallback path")
     LIBRARY_CALLS += 1
     n, Lq, Cc = q.shape
     d = Cc // heads

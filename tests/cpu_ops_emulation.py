@@ -172,7 +172,8 @@ def split_f32_bf16x2(src, hi, lo, alpha=1.0):
 
 
 def install(monkeypatch):
-    from comat_b200 import ops
+    from comat_b200 import attention, ops
+    monkeypatch.setattr(attention, "ALLOW_LIBRARY_PATH", True)     # CPU logic tests run attention through the aten comparator
     for name in ("gemm", "gemm_tn", "split_f32_bf16x2", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
                  "elementwise", "spatial", "transpose16", "concat_channels", "latent_to_nhwc", "nhwc_to_nchw_f32"):
         monkeypatch.setattr(ops, name, globals()[name])
