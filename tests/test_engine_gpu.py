@@ -217,3 +217,46 @@ def test_engine_unet_module_graph_sdxl_conditioning():
         assert len(mod._graphs) == 1
     ref = unet(x, t, ctx, added_cond_kwargs=a1, return_dict=False)[0]
     assert rel(e1, ref) < 8e-3
+
+
+def test_full_size_sd15_unet_vs_oracle():
+    """BASELINE geometry: the 859.5 M-parameter SD1.5 UNet (LoRA r = 128) at a 64x64 latent, CFG batch of 2 - engine (fp16,
+    tcgen05 kernels, LoRA folded for the no-grad call / product-form gradients for the taped call) against the fp32 oracle
+    module with torch autograd on the same weights: noise prediction, input gradient and every LoRA gradient."""
+    from comat_b200 import engine as E, ops
+    torch.manual_seed(42)
+    with torch.device("cuda"):
+        unet = sdm.UNet2DConditionModel(**sdm.SD15_UNET_CONFIG)
+    unet.requires_grad_(False)
+    params = sdm.install_lora(unet, 128, up_std=0.02, seed=1)
+    unet = unet.cuda()
+    params = [p for p in unet.parameters() if p.requires_grad]
+    assert sum(p.numel() for p in unet.parameters() if not p.requires_grad) == 859_520_964
+    g = torch.Generator().manual_seed(5)
+    n, hw = 2, 64
+    x = torch.randn(n, 4, hw, hw, generator=g).cuda()
+    ctx = torch.randn(n, 77, 768, generator=g).cuda()
+    dy = torch.randn(n, 4, hw, hw, generator=g).cuda()
+    t = torch.tensor(601, device="cuda")
+    xr = x.clone().requires_grad_(True)
+    ref = unet(xr, t, ctx, return_dict=False)[0]
+    grads_ref = torch.autograd.grad(ref, [xr] + params, dy)
+    dtype = torch.float16
+    eng = E.UNetEngine(unet, dtype)
+    ctx16 = ctx.to(dtype)
+    out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, dtype, 64), False), t, ctx16, cross_kv=eng.cross_kv(ctx16))
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), ref) < 1e-2
+    tape = E.Tape()
+    xv = E.Var(ops.latent_to_nhwc(x, dtype, 64))
+    out = eng.forward(tape, xv, t, ctx16)
+    assert rel(ops.nhwc_to_nchw_f32(out.v, 4), ref) < 1e-2
+    S = 256.0                                                  # loss scale, as modules._UNetFn applies around the fp16 backward
+    out.g = (dy * S).permute(0, 2, 3, 1).contiguous().to(dtype)
+    tape.backward()
+    assert rel(ops.nhwc_to_nchw_f32(xv.g, 4, 1.0 / S), grads_ref[0]) < 3e-2
+    eg = eng.finalize_lora_grads(1.0 / S, into_param_grads=False)
+    errs = [rel(a, b) for a, b in zip(eg, grads_ref[1:])]
+    assert len(errs) == 256 and max(errs) < 6e-2, (max(errs), sum(errs) / len(errs))
+    got = torch.cat([a.reshape(-1) for a in eg]).double()
+    want = torch.cat([b.reshape(-1) for b in grads_ref[1:]]).double()
+    assert float((got * want).sum() / (got.norm() * want.norm())) > 0.9995
