@@ -14,9 +14,10 @@ from .scheduler import DDPMScheduler
 
 
 class D_sd(torch.nn.Module):
-    def __init__(self, unet: EngineUNet, mlp: torch.nn.Module = None, scheduler: DDPMScheduler = None):
+    def __init__(self, unet: EngineUNet, mlp: torch.nn.Module = None, scheduler: DDPMScheduler = None, pipeline=None):
         super().__init__()
         self.unet = unet
+        self.D_sd_pipeline = pipeline          # optional TrainableSD(XL)Pipeline carrying the D side's text encoder(s) (gan_sdxl.py:13)
         self.mlp = mlp if mlp is not None else torch.nn.Sequential(torch.nn.Linear(4, 1))    # gan_sdxl.py:31-34 (fp32)
         self.mlp.to(device=unet.device, dtype=torch.float32)
         self.ori_scheduler = scheduler or DDPMScheduler()
@@ -55,6 +56,22 @@ class D_sd(torch.nn.Module):
         if side == "D":
             target[: target.shape[0] // 2] = 0
         return F.binary_cross_entropy_with_logits(pred, target)
+
+    @torch.no_grad()
+    def encode_prompt(self, prompt, device, batch_size, do_classifier_free_guidance=False):
+        """gan_sdxl.py:134-155: the D pipeline's embedding of ``prompt`` (the trainer passes '' once, training_script.py:516)
+        -> (null_embed, pooled_null_embed | None); the text encoder is released afterwards ("only called once")."""
+        pipe = self.D_sd_pipeline
+        if pipe is None:
+            raise NotImplementedError("D_sd was built without a D_sd_pipeline (text encoder): pass gan_null_embeds in the batch")
+        if pipe.is_sdxl:
+            null, _, pooled, _ = pipe.encode_prompt(prompt, device=device, num_images_per_prompt=batch_size,
+                                                    do_classifier_free_guidance=do_classifier_free_guidance)
+        else:
+            null = pipe.encode_prompt(prompt, device, batch_size, do_classifier_free_guidance=do_classifier_free_guidance)[0]
+            pooled = None
+        pipe.text_encoder = None               # the reference parks it on the CPU and deletes it (:151-152, training_script.py:529-530)
+        return null, pooled
 
 
 def load_discriminator(args, unet: EngineUNet):

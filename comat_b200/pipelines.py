@@ -9,6 +9,7 @@ spaCy parsing and GSAM masks are out of scope: prompts enter as ``p
 """
 from __future__ import annotations
 
+from types import SimpleNamespace
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -24,10 +25,12 @@ class TrainableSDPipeline:
     is_sdxl = False
 
     def __init__(self, vae: EngineVAE, unet: EngineUNet, scheduler: Optional[DDPMScheduler] = None, text_encoder=None,
-                 tokenizer=None, **_ignored):
+                 tokenizer=None, text_encoder_2=None, tokenizer_2=None, force_zeros_for_empty_prompt: bool = True, **_ignored):
         self.vae, self.unet = vae, unet
         self.scheduler = scheduler or DDPMScheduler()
         self.text_encoder, self.tokenizer = text_encoder, tokenizer
+        self.text_encoder_2, self.tokenizer_2 = text_encoder_2, tokenizer_2              # SDXL only
+        self.config = SimpleNamespace(force_zeros_for_empty_prompt=force_zeros_for_empty_prompt)
         self.controller: Optional[E.AttnCapture] = None
         self.attn_dict: Dict[str, Dict[str, List[torch.Tensor]]] = {}
 
@@ -38,25 +41,70 @@ class TrainableSDPipeline:
     def to(self, *a, **k):
         return self
 
-    # -- prompt encoding is "next" scope: only the pre-computed-embedding path is implemented
+    # -- prompt encoding (TrainableSDPipeline.py:227-424): CLIP-L on the B200 executor (text_encoder.EngineCLIPText)
+    @staticmethod
+    def _tokenize(tokenizer, text, max_length, device):
+        t = tokenizer(text, padding="max_length", max_length=max_length, truncation=True, return_tensors="pt")
+        return t.input_ids.to(device), getattr(t, "attention_mask", None)
+
+    @staticmethod
+    def _mask_for(text_encoder, mask, device):
+        cfg = getattr(text_encoder, "config", None)                      # :312-322: only when the config asks for it
+        if mask is not None and getattr(cfg, "use_attention_mask", False):
+            return mask.to(device)
+        return None
+
+    def _need_encoder(self, what):
+        if self.text_encoder is None or self.tokenizer is None:
+            raise NotImplementedError(f"{what}: this pipeline was built without text_encoder / tokenizer - pass the "
+                                      "pre-computed embeddings instead (TrainableSDPipeline.py:227-424)")
+
     def encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt=None,
                       prompt_embeds=None, negative_prompt_embeds=None, lora_scale=None, clip_skip=None):
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, (list, tuple)):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        text_mask = None
         if prompt_embeds is None:
-            if self.text_encoder is None or self.tokenizer is None:
-                raise NotImplementedError("text encoders are outside the hot-path scope: pass prompt_embeds "
-                                          "(TrainableSDPipeline.py:227-424 is 'next' in SURVEY 8f)")
-            ids = self.tokenizer(prompt, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
-                                 return_tensors="pt").input_ids.to(device)
-            prompt_embeds = self.text_encoder(ids)[0]
+            self._need_encoder("encode_prompt(prompt=...)")
+            ids, text_mask = self._tokenize(self.tokenizer, prompt, self.tokenizer.model_max_length, device)
+            mask = self._mask_for(self.text_encoder, text_mask, device)
+            if clip_skip is None:
+                prompt_embeds = self.text_encoder(ids, attention_mask=mask)[0]
+            else:                                                                        # :329-340
+                out = self.text_encoder(ids, attention_mask=mask, output_hidden_states=True)
+                prompt_embeds = self.text_encoder.text_model.final_layer_norm(out[-1][-(clip_skip + 1)])
         prompt_embeds = prompt_embeds.to(device=device, dtype=torch.float32)
         b, L, D = prompt_embeds.shape
         prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, D)
+        if do_classifier_free_guidance and negative_prompt_embeds is None:               # :357-407
+            if negative_prompt is None:
+                uncond = [""] * batch_size
+            elif prompt is not None and type(prompt) is not type(negative_prompt):
+                raise TypeError(f"`negative_prompt` should be the same type to `prompt`, but got {type(negative_prompt)} != {type(prompt)}.")
+            elif isinstance(negative_prompt, str):
+                uncond = [negative_prompt]
+            elif batch_size != len(negative_prompt):
+                raise ValueError(f"`negative_prompt` has batch size {len(negative_prompt)}, but `prompt` has batch size {batch_size}.")
+            else:
+                uncond = list(negative_prompt)
+            self._need_encoder("encode_prompt without negative_prompt_embeds")
+            ids, m = self._tokenize(self.tokenizer, uncond, L, device)
+            # the reference reuses the *prompt's* mask here (:390-399, `text_inputs.attention_mask`); kept when there is one
+            mask = self._mask_for(self.text_encoder, text_mask if text_mask is not None else m, device)
+            negative_prompt_embeds = self.text_encoder(ids, attention_mask=mask)[0]
         if do_classifier_free_guidance:
-            if negative_prompt_embeds is None:
-                raise NotImplementedError("pass negative_prompt_embeds (the trainer always does, training_script.py:513-525)")
             negative_prompt_embeds = negative_prompt_embeds.to(device=device, dtype=torch.float32)
-            negative_prompt_embeds = negative_prompt_embeds.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, D)
+            Ln = negative_prompt_embeds.shape[1]
+            negative_prompt_embeds = negative_prompt_embeds.repeat(1, num_images_per_prompt, 1).view(batch_size * num_images_per_prompt, Ln, -1)
         return prompt_embeds, negative_prompt_embeds
+
+    def _encode_for_forward(self, prompt, device, n_per, cfg, negative_prompt, prompt_embeds, negative_prompt_embeds, kw):
+        return self.encode_prompt(prompt, device, n_per, cfg, negative_prompt, prompt_embeds=prompt_embeds,
+                                  negative_prompt_embeds=negative_prompt_embeds)
 
     def prepare_latents(self, batch_size, num_channels, height, width, dtype, device, generator, latents=None):
         shape = (batch_size, num_channels, height // 8, width // 8)
@@ -101,9 +149,8 @@ class TrainableSDPipeline:
         prev = torch.is_grad_enabled()
         try:
             torch.set_grad_enabled(False)
-            prompt_embeds, negative_prompt_embeds = self.encode_prompt(
-                prompt, device, num_images_per_prompt, cfg, negative_prompt, prompt_embeds=prompt_embeds,
-                negative_prompt_embeds=negative_prompt_embeds)
+            prompt_embeds, negative_prompt_embeds = self._encode_for_forward(
+                prompt, device, num_images_per_prompt, cfg, negative_prompt, prompt_embeds, negative_prompt_embeds, sdxl_kwargs)
             embeds = torch.cat([negative_prompt_embeds, prompt_embeds]) if cfg else prompt_embeds
             added = self._added_cond(batch_size * num_images_per_prompt, height, width, cfg, added_cond_kwargs, sdxl_kwargs)
             self.scheduler.set_timesteps(num_inference_steps, device=device)
@@ -169,6 +216,69 @@ class TrainableSDXLPipeline(TrainableSDPipeline):
 
     is_sdxl = True
 
+    def _encode_pair(self, texts, texts_2, max_length, device, clip_skip):
+        """both encoders over one prompt list each: penultimate hidden states concatenated on the feature axis, pooled vector =
+        encoder 2's projected EOS token (diffusers StableDiffusionXLPipeline.encode_prompt, un-vendored)."""
+        if self.text_encoder_2 is None or self.tokenizer_2 is None:
+            raise NotImplementedError("SDXL encode_prompt: this pipeline was built without text_encoder_2 / tokenizer_2 - "
+                                      "pass prompt_embeds and pooled_prompt_embeds instead")
+        pairs = [(texts_2, self.tokenizer_2, self.text_encoder_2)]
+        if self.tokenizer is not None and self.text_encoder is not None:
+            pairs.insert(0, (texts, self.tokenizer, self.text_encoder))
+        embeds, pooled = [], None
+        for txt, tok, enc in pairs:
+            ids, _ = self._tokenize(tok, txt, max_length or tok.model_max_length, device)
+            out = enc(ids, output_hidden_states=True)
+            pooled = out[0]                                  # only the last (projection) encoder's survives
+            embeds.append(out.hidden_states[-2] if clip_skip is None else out.hidden_states[-(clip_skip + 2)])
+        return torch.cat(embeds, -1), pooled
+
+    def encode_prompt(self, prompt, prompt_2=None, device=None, num_images_per_prompt: int = 1,
+                      do_classifier_free_guidance: bool = True, negative_prompt=None, negative_prompt_2=None,
+                      prompt_embeds=None, negative_prompt_embeds=None, pooled_prompt_embeds=None,
+                      negative_pooled_prompt_embeds=None, lora_scale=None, clip_skip=None):
+        """-> (prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds), the 4-tuple
+        training_script.py:521 unpacks."""
+        device = device or self._execution_device
+        prompt = [prompt] if isinstance(prompt, str) else prompt
+        batch_size = len(prompt) if prompt is not None else prompt_embeds.shape[0]
+        if prompt_embeds is None:
+            prompt_2 = prompt_2 or prompt
+            prompt_2 = [prompt_2] if isinstance(prompt_2, str) else prompt_2
+            prompt_embeds, pooled_prompt_embeds = self._encode_pair(list(prompt), list(prompt_2), None, device, clip_skip)
+        zero_out = negative_prompt is None and self.config.force_zeros_for_empty_prompt
+        if do_classifier_free_guidance and negative_prompt_embeds is None and zero_out:
+            negative_prompt_embeds = torch.zeros_like(prompt_embeds)
+            negative_pooled_prompt_embeds = None if pooled_prompt_embeds is None else torch.zeros_like(pooled_prompt_embeds)
+        elif do_classifier_free_guidance and negative_prompt_embeds is None:
+            negative_prompt = negative_prompt or ""
+            negative_prompt_2 = negative_prompt_2 or negative_prompt
+            neg = batch_size * [negative_prompt] if isinstance(negative_prompt, str) else list(negative_prompt)
+            neg_2 = batch_size * [negative_prompt_2] if isinstance(negative_prompt_2, str) else list(negative_prompt_2)
+            if prompt is not None and batch_size != len(neg):
+                raise ValueError(f"`negative_prompt` has batch size {len(neg)}, but `prompt` has batch size {batch_size}.")
+            negative_prompt_embeds, negative_pooled_prompt_embeds = self._encode_pair(neg, neg_2, prompt_embeds.shape[1], device, None)
+        prompt_embeds = prompt_embeds.to(device=device, dtype=torch.float32)
+        b, L, D = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, D)
+        if do_classifier_free_guidance:
+            negative_prompt_embeds = negative_prompt_embeds.to(device=device, dtype=torch.float32)
+            negative_prompt_embeds = negative_prompt_embeds.repeat(1, num_images_per_prompt, 1).view(batch_size * num_images_per_prompt, L, -1)
+        if pooled_prompt_embeds is not None:
+            pooled_prompt_embeds = pooled_prompt_embeds.to(device=device, dtype=torch.float32).repeat(1, num_images_per_prompt).view(
+                b * num_images_per_prompt, -1)
+        if do_classifier_free_guidance and negative_pooled_prompt_embeds is not None:
+            negative_pooled_prompt_embeds = negative_pooled_prompt_embeds.to(device=device, dtype=torch.float32).repeat(
+                1, num_images_per_prompt).view(b * num_images_per_prompt, -1)
+        return prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds
+
+    def _encode_for_forward(self, prompt, device, n_per, cfg, negative_prompt, prompt_embeds, negative_prompt_embeds, kw):
+        pe, npe, pp, npp = self.encode_prompt(
+            prompt, kw.get("prompt_2"), device, n_per, cfg, negative_prompt, kw.get("negative_prompt_2"), prompt_embeds,
+            negative_prompt_embeds, kw.get("pooled_prompt_embeds"), kw.get("negative_pooled_prompt_embeds"))
+        kw["pooled_prompt_embeds"], kw["negative_pooled_prompt_embeds"] = pp, npp
+        return pe, npe
+
     def _get_add_time_ids(self, original_size, crops_coords_top_left, target_size, dtype=torch.float32):
         add_time_ids = list(original_size + crops_coords_top_left + target_size)        # :428-449
         want = self.unet.ref.add_embedding.linear_1.in_features
@@ -182,7 +292,7 @@ class TrainableSDXLPipeline(TrainableSDPipeline):
             return added_cond_kwargs
         pooled, neg_pooled = kw.get("pooled_prompt_embeds"), kw.get("negative_pooled_prompt_embeds")
         if pooled is None:
-            raise NotImplementedError("pass pooled_prompt_embeds (text encoders are outside the hot-path scope)")
+            raise NotImplementedError("pass pooled_prompt_embeds with prompt_embeds, or build the pipeline with text_encoder_2 / tokenizer_2")
         self._pooled_dim = pooled.shape[-1]
         osz = kw.get("original_size") or (height, width)
         tsz = kw.get("target_size") or (height, width)

@@ -70,6 +70,63 @@ def build_blip(device, dtype=torch.float16, seed=0, large=True, label_smoothing=
     return m.to(device=device, dtype=dtype)
 
 
+def build_clip_text(device, dtype=torch.float16, seed=7, which="clip_l", tiny=False):
+    """Random-init HF CLIP text tower at the geometry the SD checkpoints ship: ``clip_l`` = CLIPTextModel 12 x 768,
+    12 heads, quick-GELU (SD1.5 ``text_encoder`` / SDXL ``text_encoder``); ``bigg`` = CLIPTextModelWithProjection 32 x 1280,
+    20 heads, GELU, projection 1280 (SDXL ``text_encoder_2``).  ``eos_token_id = 2`` is the legacy value those configs carry."""
+    from transformers import CLIPTextConfig, CLIPTextModel, CLIPTextModelWithProjection
+    if which == "clip_l":
+        kw = dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12, hidden_act="quick_gelu",
+                  projection_dim=768)
+        cls = CLIPTextModel
+    elif which == "bigg":
+        kw = dict(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=20, hidden_act="gelu",
+                  projection_dim=1280)
+        cls = CLIPTextModelWithProjection
+    else:
+        raise NotImplementedError(which)
+    if tiny:
+        kw.update(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, projection_dim=64)
+    cfg = CLIPTextConfig(vocab_size=49408, max_position_embeddings=77, eos_token_id=2, bos_token_id=0, pad_token_id=1, **kw)
+    torch.manual_seed(seed)
+    m = cls(cfg)
+    m.eval().requires_grad_(False)
+    return m.to(device=device, dtype=dtype)
+
+
+class SyntheticClipTokenizer:
+    """Stand-in for ``CLIPTokenizer`` (its vocabulary / merges files are not on disk and there is no Hub access): the same call
+    protocol and framing - BOS 49406, one id per whitespace word (a stable hash into the BPE id range), EOS 49407, padding with
+    ``pad_token_id`` (49407 for SD1.5 / SDXL tokenizer 1, 0 for SDXL tokenizer 2) - so ``encode_prompt`` runs on prompt strings.
+    Not a BPE: real deployments pass the real tokenizer, which has this interface."""
+
+    bos_token_id, eos_token_id = 49406, 49407
+
+    def __init__(self, model_max_length: int = 77, pad_token_id: int = 49407):
+        self.model_max_length, self.pad_token_id = model_max_length, pad_token_id
+
+    @staticmethod
+    def _word_id(w: str) -> int:
+        h = 2166136261
+        for ch in w.encode("utf-8"):
+            h = ((h ^ ch) * 16777619) & 0xFFFFFFFF            # FNV-1a: stable across processes (hash() is salted)
+        return 1000 + h % 48000
+
+    def __call__(self, text, padding="max_length", max_length=None, truncation=True, return_tensors="pt", **_):
+        texts = [text] if isinstance(text, str) else list(text)
+        rows = [[self.bos_token_id] + [self._word_id(w) for w in t.lower().split()] + [self.eos_token_id] for t in texts]
+        limit = max_length or self.model_max_length
+        if truncation:
+            rows = [r if len(r) <= limit else r[:limit - 1] + [self.eos_token_id] for r in rows]
+        T = limit if padding == "max_length" else max(len(r) for r in rows)
+        ids = torch.full((len(rows), T), self.pad_token_id, dtype=torch.long)
+        am = torch.zeros(len(rows), T, dtype=torch.long)
+        for i, r in enumerate(rows):
+            ids[i, :len(r)] = torch.tensor(r)
+            am[i, :len(r)] = 1
+        return SimpleNamespace(input_ids=ids, attention_mask=am)
+
+
 def random_mask(g, size=512, empty=False):
     m = torch.zeros(1, 1, size, size, dtype=torch.bool)
     if empty:

@@ -1,0 +1,152 @@
+"""CLIP text encoders of the step: what ``encode_prompt`` (TrainableSDPipeline.py:227-424; the SDXL twin is the
+un-vendored diffusers ``StableDiffusionXLPipeline.encode_prompt``) calls once per optimiser step under ``no_grad``.
+
+CLIP-L (12 x 768, 12 heads, quick-GELU) for SD1.5 / SDXL encoder 1 and OpenCLIP-bigG (32 x 1280, 20 heads, GELU, text
+projection) for SDXL encoder 2 run on the same tcgen05 GEMM / attention kernels and HBM-bound LayerNorm kernels as the UNet:
+pre-LN blocks, q|k|v as ONE GEMM whose column slices the causal attention kernel reads in place, head dim 64.
+
+quick-GELU ``x * sigmoid(1.702 x)`` needs no kernel of its own: it equals ``silu(1.702 x) / 1.702``, so fc1 runs with
+``alpha = 1.702`` (bias pre-scaled) and the SiLU epilogue, and fc2 with ``alpha = 1 / 1.702``.
+
+The parameter owner is an HF ``CLIPTextModel`` / ``CLIPTextModelWithProjection`` (real checkpoint or random init); weights are
+packed once.  Frozen path only: ``--tune_text_encoder`` / ``--train_text_encoder_lora`` (training_script.py:227-255) would need
+the UNet executor to emit d(encoder_hidden_states) and are rejected by the trainer.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import attention as attn_ops
+from . import engine as E
+from . import ops
+
+_QG = 1.702
+
+
+class _FusedQKV:
+    def __init__(self, attn, dtype):
+        w = torch.cat([attn.q_proj.weight.detach(), attn.k_proj.weight.detach(), attn.v_proj.weight.detach()], 0)
+        b = torch.cat([attn.q_proj.bias.detach(), attn.k_proj.bias.detach(), attn.v_proj.bias.detach()], 0)
+        self.w = w.to(dtype).contiguous()            # [3C, C] K-major
+        self.bias = b.float().contiguous()
+
+
+class ClipTextEngine:
+    """forward-only executor (no tape: the encoders are frozen on the CoMat path, training_script.py:210-226)."""
+
+    def __init__(self, model, dtype=torch.float16):
+        cfg = model.config
+        tm = model.text_model
+        self.dtype = dtype
+        self.heads = cfg.num_attention_heads
+        self.dim = cfg.hidden_size
+        self.eos_token_id = cfg.eos_token_id
+        act = cfg.hidden_act
+        if act not in ("quick_gelu", "gelu"):
+            raise NotImplementedError(f"CLIP text hidden_act {act!r} (SD1.5 / SDXL use quick_gelu and gelu)")
+        self.quick = act == "quick_gelu"
+        self.tok = tm.embeddings.token_embedding.weight.detach()
+        self.pos = tm.embeddings.position_embedding.weight.detach()
+        self.layers = []
+        for lyr in tm.encoder.layers:
+            fc1, fc2 = E.LinW(lyr.mlp.fc1, dtype), E.LinW(lyr.mlp.fc2, dtype)
+            if self.quick:
+                fc1.bias = (fc1.bias * _QG).contiguous()
+            self.layers.append(dict(n1=E.NormW(lyr.layer_norm1), qkv=_FusedQKV(lyr.self_attn, dtype),
+                                    out=E.LinW(lyr.self_attn.out_proj, dtype), n2=E.NormW(lyr.layer_norm2), fc1=fc1, fc2=fc2))
+        self.final_ln = E.NormW(tm.final_layer_norm)
+        proj = getattr(model, "text_projection", None)
+        self.proj = None if proj is None else proj.weight.detach().to(dtype).contiguous()      # [proj_dim, C], no bias
+
+    def final_layer_norm(self, h: torch.Tensor) -> torch.Tensor:
+        x = h.to(self.dtype).contiguous()
+        return ops.layernorm_fwd(x, self.final_ln.gamma, self.final_ln.beta, self.final_ln.eps)[0]
+
+    def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, all_hidden: bool = False):
+        """input_ids (B, T) int64 -> (last_hidden_state (B,T,C) 16-bit, pooled (B,C), text_embeds | None, hidden_states | None)."""
+        B, T = input_ids.shape
+        C_ = self.dim
+        h = (self.tok[input_ids] + self.pos[:T][None]).to(self.dtype).contiguous()
+        # right-padded prompts (the CLIP tokenizer pads after EOS): a per-sample key length on top of the causal mask
+        lens = (torch.full((B,), T, dtype=torch.int32, device=h.device) if attention_mask is None
+                else attention_mask.sum(1).to(torch.int32).contiguous())
+        hidden = [h] if all_hidden else None
+        for L in self.layers:
+            y = ops.layernorm_fwd(h, L["n1"].gamma, L["n1"].beta, L["n1"].eps)[0]
+            qkv = ops.gemm([y.reshape(B * T, C_)], [L["qkv"].w], bias=L["qkv"].bias).reshape(B, T, 3 * C_)
+            a, _, _ = attn_ops.attention_fwd_native(qkv[..., :C_], qkv[..., C_:2 * C_], qkv[..., 2 * C_:], self.heads,
+                                                    kv_lens=lens, causal=True)
+            h = ops.gemm([a.reshape(B * T, C_)], [L["out"].w], bias=L["out"].bias, residual=h.reshape(B * T, C_)).reshape(B, T, C_)
+            y = ops.layernorm_fwd(h, L["n2"].gamma, L["n2"].beta, L["n2"].eps)[0].reshape(B * T, C_)
+            if self.quick:
+                f = ops.gemm([y], [L["fc1"].w], bias=L["fc1"].bias, alpha=_QG, act="silu")
+                h = ops.gemm([f], [L["fc2"].w], bias=L["fc2"].bias, alpha=1.0 / _QG, residual=h.reshape(B * T, C_)).reshape(B, T, C_)
+            else:
+                f = ops.gemm([y], [L["fc1"].w], bias=L["fc1"].bias, act="gelu")
+                h = ops.gemm([f], [L["fc2"].w], bias=L["fc2"].bias, residual=h.reshape(B * T, C_)).reshape(B, T, C_)
+            if all_hidden:
+                hidden.append(h)
+        last = ops.layernorm_fwd(h, self.final_ln.gamma, self.final_ln.beta, self.final_ln.eps)[0]
+        ids = input_ids.to(torch.int32)
+        # pooled token: transformers CLIPTextTransformer.forward — the legacy configs (eos_token_id == 2, what the SD / SDXL
+        # checkpoints ship) take the arg-max id (EOS = 49407 is the largest), newer ones the first EOS position
+        eos = ids.argmax(-1) if self.eos_token_id == 2 else (ids == self.eos_token_id).int().argmax(-1)
+        pooled = last[torch.arange(B, device=last.device), eos].contiguous()
+        embeds = None
+        if self.proj is not None:
+            embeds = ops.gemm([pooled], [self.proj])
+        return last, pooled, embeds, hidden
+
+
+class _TextOutput:
+    """ordered-field result with the tuple indexing the reference relies on (``out[0]``; ``out[-1][-(clip_skip + 1)]`` when
+    hidden states were requested, TrainableSDPipeline.py:325-335) and HF attribute names."""
+
+    def __init__(self, **fields):
+        self._keys = [k for k, v in fields.items() if v is not None]
+        for k, v in fields.items():
+            setattr(self, k, v)
+
+    def __getitem__(self, i):
+        if isinstance(i, str):
+            return getattr(self, i)
+        return getattr(self, self._keys[i])
+
+    def keys(self):
+        return list(self._keys)
+
+    def __len__(self):
+        return len(self._keys)
+
+
+class EngineCLIPText(torch.nn.Module):
+    """HF call surface ``text_encoder(input_ids, attention_mask=None, output_hidden_states=False)`` backed by ``ClipTextEngine``.
+    Outputs are fp32 (the pipelines' interface dtype, like ``EngineUNet.dtype``); the arithmetic is 16-bit on the tensor cores."""
+
+    def __init__(self, model, dtype=torch.float16):
+        super().__init__()
+        self.ref = model
+        self.config = model.config
+        self.engine = ClipTextEngine(model, dtype)
+        self.with_projection = self.engine.proj is not None
+        self.text_model = SimpleNamespace(final_layer_norm=lambda h: self.engine.final_layer_norm(h).float())
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    @property
+    def device(self):
+        return self.engine.tok.device
+
+    @torch.no_grad()
+    def forward(self, input_ids, attention_mask=None, output_hidden_states: bool = False, **_):
+        last, pooled, embeds, hidden = self.engine.forward(input_ids.to(self.device), None if attention_mask is None else
+                                                           attention_mask.to(self.device), all_hidden=bool(output_hidden_states))
+        hs = None if hidden is None else tuple(x.float() for x in hidden)
+        if self.with_projection:           # CLIPTextModelOutput: text_embeds first (SDXL reads out[0] as the pooled vector)
+            return _TextOutput(text_embeds=embeds.float(), last_hidden_state=last.float(), hidden_states=hs)
+        return _TextOutput(last_hidden_state=last.float(), pooler_output=pooled.float(), hidden_states=hs)

@@ -28,6 +28,10 @@ class CoMatTrainer:
         explicitly), so device memory does not depend on the collector.  0 leaves the interpreter's GC settings alone."""
         self.manual_gc_interval = int(manual_gc_interval)
         self.args, self.pipeline, self.caption_model, self.D = args, pipeline, caption_model, D
+        if getattr(args, "tune_text_encoder", False) or getattr(args, "train_text_encoder_lora", False):
+            # training_script.py:227-255,569-573: needs d(encoder_hidden_states) out of the UNet executor - not built (SURVEY 8f-1)
+            raise NotImplementedError("--tune_text_encoder / --train_text_encoder_lora: the text encoders are frozen on this path")
+        self.null_embed = self.pooled_null_embed = self.gan_null_embed = None
         self.rng = rng or random.Random(args.seed)
         self.G_parameters = list(pipeline.unet.lora_parameters())                 # training_utils/pipeline.py:123-143
         self.optimizer = FlatAdamW(self.G_parameters, lr=args.learning_rate, betas=(args.adam_beta1, args.adam_beta2),
@@ -106,6 +110,29 @@ class CoMatTrainer:
         self.D_optimizer.step(h)
         self._refresh(self.D.unet)
 
+    # -- training_script.py:513-525: the '' embeddings, encoded ONCE before the loop (pipelines built with text encoders)
+    @torch.no_grad()
+    def prepare_null_embeds(self):
+        a, pipe = self.args, self.pipeline
+        dev = pipe._execution_device
+        if not a.do_classifier_free_guidance:
+            return
+        if a.gan_loss and self.D is not None and getattr(self.D, "D_sd_pipeline", None) is not None:
+            self.gan_null_embed, _ = self.D.encode_prompt("", dev, a.train_batch_size, do_classifier_free_guidance=False)
+        if pipe.is_sdxl:
+            self.null_embed, _, self.pooled_null_embed, _ = pipe.encode_prompt(
+                "", device=dev, num_images_per_prompt=a.train_batch_size, do_classifier_free_guidance=False)
+        else:
+            self.null_embed = pipe.encode_prompt("", dev, a.train_batch_size, do_classifier_free_guidance=False)[0]
+
+    def _null(self, batch, key, attr):
+        v = batch.get(key)
+        if v is None:
+            if getattr(self, attr) is None:
+                self.prepare_null_embeds()
+            v = getattr(self, attr)
+        return v
+
     # -- training_script.py:563-566, :589-590
     def select_steps(self):
         a = self.args
@@ -122,17 +149,18 @@ class CoMatTrainer:
         steps, attr = batch.get("training_steps"), batch.get("attrcon_steps")
         if steps is None:
             steps, attr = self.select_steps()
-        kwargs = dict(prompt=batch.get("text"), prompt_embeds=batch["prompt_embeds"], height=a.resolution, width=a.resolution,
+        kwargs = dict(prompt=batch.get("text"), prompt_embeds=batch.get("prompt_embeds"), height=a.resolution, width=a.resolution,
                       training_timesteps=steps, detach_gradient=True, train_text_encoder=False,
                       num_inference_steps=a.total_step, guidance_scale=a.cfg_scale, guidance_rescale=a.cfg_rescale,
-                      negative_prompt_embeds=batch["null_embeds"] if a.do_classifier_free_guidance else None,
+                      negative_prompt_embeds=self._null(batch, "null_embeds", "null_embed") if a.do_classifier_free_guidance else None,
                       early_exit=False, return_latents=bool(a.gan_loss), latents=batch.get("init_latents"),
                       noises=batch.get("noises"))
         if self.attrcon:
             kwargs["attrcon_train_steps"] = attr
         if pipe.is_sdxl:
-            kwargs.update(pooled_prompt_embeds=batch["pooled_prompt_embeds"],
-                          negative_pooled_prompt_embeds=batch.get("pooled_null_embeds"))
+            kwargs.update(pooled_prompt_embeds=batch.get("pooled_prompt_embeds"),
+                          negative_pooled_prompt_embeds=self._null(batch, "pooled_null_embeds", "pooled_null_embed")
+                          if a.do_classifier_free_guidance else None)
             out = pipe.forward(**kwargs)
         else:
             out = pipe.forward(bp_on_trained=True, double_laststep=False, fast_training=False, **kwargs)
@@ -145,7 +173,7 @@ class CoMatTrainer:
         loss = -rewards["total"].mean()                                              # :618
         if a.gan_loss:
             self._join("_ev_D")                                                      # the discriminator's previous update is in
-            g = self.D.D_sd_pipeline_forward(training_latents, side="G", negative_prompt_embeds=batch["gan_null_embeds"],
+            g = self.D.D_sd_pipeline_forward(training_latents, side="G", negative_prompt_embeds=self._null(batch, "gan_null_embeds", "gan_null_embed"),
                                              num_inference_steps=a.total_step)
             loss = loss + a.gan_loss_weight * g                                      # :620-625
             logs["G_loss"] = g.detach()
@@ -190,7 +218,7 @@ class CoMatTrainer:
         out["step_loss"] = loss.detach()
         out.update(logs.get("_norm_holder", {}))
         if a.gan_loss:                                                               # :679-694
-            d_loss = self.D.D_sd_pipeline_forward(logs["_latents"].detach(), side="D", negative_prompt_embeds=batch["gan_null_embeds"],
+            d_loss = self.D.D_sd_pipeline_forward(logs["_latents"].detach(), side="D", negative_prompt_embeds=self._null(batch, "gan_null_embeds", "gan_null_embed"),
                                                   num_inference_steps=a.total_step, batch={"latents": batch["real_latents"]})
             self.D_optimizer.zero_grad()
             d_loss.backward()

@@ -385,3 +385,100 @@ def g_step_loss(unet, vae, scheduler, blip_model, batch, cfgd, controller=None, 
     out["loss"] = loss
     out["attn_dict"] = attn_dict
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# prompt encoding  
+# --------------------------------------------------------------------------------------------
+def make_clip_text(which="clip_l", tiny=True, seed=7, dtype=torch.float32, device="cpu", layers=None):
+    """random-init HF CLIP text tower (transformers is the un-vendored third-party layer here, used directly like BLIP):
+    ``clip_l`` -> CLIPTextModel (quick_gelu), ``bigg`` -> CLIPTextModelWithProjection (gelu)."""
+    from transformers import CLIPTextConfig, CLIPTextModel, CLIPTextModelWithProjection
+    if which == "clip_l":
+        kw = dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12, hidden_act="quick_gelu",
+                  projection_dim=768)
+        cls = CLIPTextModel
+    else:
+        kw = dict(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=20, hidden_act="gelu",
+                  projection_dim=1280)
+        cls = CLIPTextModelWithProjection
+    if tiny:
+        kw.update(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, projection_dim=64)
+    if layers is not None:
+        kw["num_hidden_layers"] = layers
+    cfg = CLIPTextConfig(vocab_size=49408, max_position_embeddings=77, eos_token_id=2, bos_token_id=0, pad_token_id=1, **kw)
+    torch.manual_seed(seed)
+    with torch.device(device):
+        m = cls(cfg)
+    return m.eval().requires_grad_(False).to(dtype)
+
+
+@torch.no_grad()
+def encode_prompt_sd(text_encoder, tokenizer, prompt, num_images_per_prompt: int, do_cfg: bool, negative_prompt=None,
+                     negative_prompt_embeds=None, clip_skip: Optional[int] = None):
+    """TrainableSDPipeline.py:227-424 for a frozen, non-DDP encoder whose config has no ``use_attention_mask``
+    (the SD1.5 CLIP-L): tokenise to model_max_length (:291-297), ``text_encoder(ids)[0]`` (:324-327) or the
+    clip_skip branch with the final LayerNorm re-applied (:328-340), repeat per image (:353-356), '' as the
+    default negative prompt tokenised to the prompt's length (:359-404), repeated the same way (:406-413)."""
+    prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+    ids = tokenizer(prompts, padding="max_length", max_length=tokenizer.model_max_length, truncation=True,
+                    return_tensors="pt").input_ids
+    if clip_skip is None:
+        pe = text_encoder(ids, attention_mask=None)[0]
+    else:
+        out = text_encoder(ids, attention_mask=None, output_hidden_states=True)
+        pe = text_encoder.text_model.final_layer_norm(out[-1][-(clip_skip + 1)])
+    b, L, _ = pe.shape
+    pe = pe.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, -1)
+    npe = negative_prompt_embeds
+    if do_cfg and npe is None:
+        if negative_prompt is None:
+            uncond = [""] * b
+        elif isinstance(negative_prompt, str):
+            uncond = [negative_prompt]
+        else:
+            uncond = list(negative_prompt)
+        nids = tokenizer(uncond, padding="max_length", max_length=L, truncation=True, return_tensors="pt").input_ids
+        npe = text_encoder(nids, attention_mask=None)[0]
+    if do_cfg:
+        npe = npe.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, npe.shape[1], -1)
+    return pe, npe, ids
+
+
+@torch.no_grad()
+def encode_prompt_sdxl(text_encoder, text_encoder_2, tokenizer, tokenizer_2, prompt, num_images_per_prompt: int, do_cfg: bool,
+                       negative_prompt=None, force_zeros_for_empty_prompt: bool = True, clip_skip: Optional[int] = None):
+    """diffusers (0.22-0.25) ``StableDiffusionXLPipeline.encode_prompt`` - inherited un-overridden by the reference's
+    TrainableSDXLPipeline (TrainableSDPipeline.py:427; called at training_script.py:521,573) and NOT on disk: restated from
+    the published behaviour, **parity unpinned**.  Per encoder: ``out = enc(ids, output_hidden_states=True)``,
+    ``pooled = out[0]`` (the projection encoder's ``text_embeds`` wins), ``hidden_states[-2]`` (or ``-(clip_skip + 2)``),
+    concatenated on the feature axis; negatives are zeros when ``negative_prompt is None and force_zeros_for_empty_prompt``,
+    else the encoding of '' / the negative prompt."""
+    prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+    b = len(prompts)
+
+    def enc_pair(texts, max_len, skip):
+        outs, pooled = [], None
+        for tok, enc in ((tokenizer, text_encoder), (tokenizer_2, text_encoder_2)):
+            ids = tok(texts, padding="max_length", max_length=max_len or tok.model_max_length, truncation=True,
+                      return_tensors="pt").input_ids
+            out = enc(ids, output_hidden_states=True)
+            pooled = out[0]
+            outs.append(out.hidden_states[-2] if skip is None else out.hidden_states[-(skip + 2)])
+        return torch.cat(outs, -1), pooled
+
+    pe, pp = enc_pair(prompts, None, clip_skip)
+    npe = npp = None
+    if do_cfg and negative_prompt is None and force_zeros_for_empty_prompt:
+        npe, npp = torch.zeros_like(pe), torch.zeros_like(pp)
+    elif do_cfg:
+        neg = negative_prompt or ""
+        neg = b * [neg] if isinstance(neg, str) else list(neg)
+        npe, npp = enc_pair(neg, pe.shape[1], None)
+    L = pe.shape[1]
+    pe = pe.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, -1)
+    pp = pp.repeat(1, num_images_per_prompt).view(b * num_images_per_prompt, -1)
+    if do_cfg:
+        npe = npe.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, -1)
+        npp = npp.repeat(1, num_images_per_prompt).view(b * num_images_per_prompt, -1)
+    return pe, npe, pp, npp

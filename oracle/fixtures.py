@@ -213,3 +213,48 @@ def gan_world(seed, B, S, hw):
     head = torch.nn.Sequential(torch.nn.Linear(4, 1))
     return dict(d_unet=d_unet, head=head, fake=torch.randn(B, 4, hw, hw, generator=g),
                 real=torch.randn(B, 4, hw, hw, generator=g), null=torch.randn(B, 77, 64, generator=g))
+
+
+# ---- prompt encoding: no CLIP vocabulary on disk -> a framing-exact stand-in tokenizer
+class ClipTokenizerStub:
+    """CLIPTokenizer call protocol and framing (BOS 49406 + one id per whitespace word + EOS 49407, padded with ``pad_token_id``);
+    word ids are an FNV-1a hash into [1000, 49000).  ORACLE-side twin of comat_b200.synthetic.SyntheticClipTokenizer (written
+    independently; tests/test_text_encoder_cpu.py checks both against the ids stored in tests/golden/encode_prompt.pt)."""
+
+    def __init__(self, model_max_length=77, pad_token_id=49407):
+        self.model_max_length, self.pad_token_id = model_max_length, pad_token_id
+
+    def __call__(self, text, padding="max_length", max_length=None, truncation=True, return_tensors="pt", **_):
+        from types import SimpleNamespace
+        texts = [text] if isinstance(text, str) else list(text)
+        rows = []
+        for t in texts:
+            r = [49406]
+            for w in t.lower().split():
+                h = 0x811C9DC5
+                for byte in w.encode("utf-8"):
+                    h = ((h ^ byte) * 0x01000193) % (1 << 32)
+                r.append(1000 + h % 48000)
+            r.append(49407)
+            cap = max_length or self.model_max_length
+            if truncation and len(r) > cap:
+                r = r[:cap - 1] + [49407]
+            rows.append(r)
+        width = (max_length or self.model_max_length) if padding == "max_length" else max(map(len, rows))
+        ids = torch.full((len(rows), width), self.pad_token_id, dtype=torch.long)
+        mask = torch.zeros(len(rows), width, dtype=torch.long)
+        for i, r in enumerate(rows):
+            ids[i, :len(r)] = torch.tensor(r)
+            mask[i, :len(r)] = 1
+        return SimpleNamespace(input_ids=ids, attention_mask=mask)
+
+    def batch_decode(self, ids):
+        return [" ".join(str(int(x)) for x in row) for row in ids]
+
+
+ENCODE_PROMPT_CASES = [
+    dict(prompts=["a red apple on a wooden table", "two dogs"], n_per=1, cfg=True, negative=None, clip_skip=None, seed=7),
+    dict(prompts=["the quick brown fox jumps over the lazy dog"], n_per=2, cfg=True, negative="blurry low quality", clip_skip=None, seed=8),
+    dict(prompts=["a blue car and a green bench", "a cat", "snow"], n_per=1, cfg=False, negative=None, clip_skip=1, seed=9),
+    dict(prompts=[" ".join(["word%d" % i for i in range(90)])], n_per=1, cfg=True, negative=None, clip_skip=None, seed=10),   # truncated at 77
+]

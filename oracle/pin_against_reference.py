@@ -230,11 +230,47 @@ def pin_gan():
     return out
 
 
+def pin_encode_prompt():
+    """Reference TrainableSDPipeline.encode_prompt (TrainableSDPipeline.py:227-424), verbatim, over an HF CLIPTextModel (tiny
+    geometry, seeded) and the framing-exact tokenizer stub; vs oracle encode_prompt_sd.  The SDXL twin lives in diffusers
+    (un-vendored) and stays unpinned."""
+    ref_shim.install()
+    pl = ref_shim.import_reference("TrainableSDPipeline")
+    out = {}
+    for case in FX.ENCODE_PROMPT_CASES:
+        enc = R.make_clip_text("clip_l", tiny=True, seed=case["seed"])
+        tok = FX.ClipTokenizerStub()
+        pipe = pl.TrainableSDPipeline.__new__(pl.TrainableSDPipeline)
+        ref_shim._PipelineBase.__init__(pipe, vae=None, text_encoder=enc, tokenizer=tok, unet=None, scheduler=None)
+        with torch.no_grad():
+            pe_ref, npe_ref = pipe.encode_prompt(case["prompts"], torch.device("cpu"), case["n_per"], case["cfg"],
+                                                 negative_prompt=None if case["negative"] is None else [case["negative"]] * len(case["prompts"]),
+                                                 clip_skip=case["clip_skip"])
+        neg = case["negative"]
+        pe, npe, ids = R.encode_prompt_sd(enc, tok, case["prompts"], case["n_per"], case["cfg"],
+                                          negative_prompt=None if neg is None else [neg] * len(case["prompts"]),
+                                          clip_skip=case["clip_skip"])
+        _close(pe, pe_ref, 1e-6, f"encode_prompt embeds {case['seed']}")
+        if case["cfg"]:
+            _close(npe, npe_ref, 1e-6, f"encode_prompt negative embeds {case['seed']}")
+        else:
+            assert npe_ref is None and npe is None
+        out["seed%d" % case["seed"]] = {"case": case, "input_ids": ids.clone(), "prompt_embeds": pe_ref.clone(),
+                                        "negative_prompt_embeds": None if npe_ref is None else npe_ref.clone()}
+    return out
+
+
+PINS = [("layer_loss", pin_layer_loss), ("mask_loss", pin_mask_loss), ("blip_score", pin_blip_score),
+        ("gan", pin_gan), ("pipeline", pin_attention_store_and_pipeline), ("encode_prompt", pin_encode_prompt)]
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
-    for name, fn in [("layer_loss", pin_layer_loss), ("mask_loss", pin_mask_loss), ("blip_score", pin_blip_score),
-                     ("gan", pin_gan), ("pipeline", pin_attention_store_and_pipeline)]:
+    only = set(sys.argv[1:])            # e.g. `python -m oracle.pin_against_reference encode_prompt` re-pins one golden file
+    for name, fn in PINS:
+        if only and name not in only:
+            continue
         res = fn()
         path = os.path.join(GOLDEN_DIR, f"{name}.pt")
         torch.save(res, path)

@@ -1,0 +1,180 @@
+"""CPU: prompt encoding - oracle vs the golden outputs of the reference's own ``encode_prompt``
+(tests/golden/encode_prompt.pt, written by oracle/pin_against_reference.py), and the product's text-encoder executor +
+``encode_prompt`` host logic vs the oracle with the CUDA ops emulated in torch (test infrastructure)."""
+import pytest
+import torch
+
+from oracle import comat_ref as R
+from oracle import fixtures as FX
+from tests import cpu_ops_emulation as EMU
+
+
+def _neg(case):
+    return None if case["negative"] is None else [case["negative"]] * len(case["prompts"])
+
+
+def test_oracle_encode_prompt_matches_reference_golden(golden):
+    gold = golden("encode_prompt")
+    assert len(gold) == len(FX.ENCODE_PROMPT_CASES)
+    for case in FX.ENCODE_PROMPT_CASES:
+        g = gold["seed%d" % case["seed"]]
+        enc = R.make_clip_text("clip_l", tiny=True, seed=case["seed"])
+        pe, npe, ids = R.encode_prompt_sd(enc, FX.ClipTokenizerStub(), case["prompts"], case["n_per"], case["cfg"],
+                                          negative_prompt=_neg(case), clip_skip=case["clip_skip"])
+        assert torch.equal(ids, g["input_ids"])
+        assert pe.shape == (len(case["prompts"]) * case["n_per"], 77, 128)
+        torch.testing.assert_close(pe, g["prompt_embeds"], rtol=1e-5, atol=1e-6)
+        if case["cfg"]:
+            torch.testing.assert_close(npe, g["negative_prompt_embeds"], rtol=1e-5, atol=1e-6)
+        else:
+            assert npe is None and g["negative_prompt_embeds"] is None
+
+
+def test_product_tokenizer_stub_matches_golden_ids(golden):
+    from comat_b200.synthetic import SyntheticClipTokenizer
+    gold = golden("encode_prompt")
+    tok = SyntheticClipTokenizer()
+    for case in FX.ENCODE_PROMPT_CASES:
+        ids = tok(case["prompts"], padding="max_length", max_length=77, truncation=True, return_tensors="pt").input_ids
+        assert torch.equal(ids, gold["seed%d" % case["seed"]]["input_ids"])
+    t2 = SyntheticClipTokenizer(pad_token_id=0)(["a b"], padding="longest")
+    assert t2.input_ids.shape == (1, 4) and t2.attention_mask.sum() == 4
+
+
+@pytest.mark.parametrize("which", ["clip_l", "bigg"])
+def test_text_executor_matches_hf(monkeypatch, which):
+    EMU.install_blip(monkeypatch)
+    from comat_b200.text_encoder import EngineCLIPText
+    model = R.make_clip_text(which, tiny=True, seed=3)
+    tok = FX.ClipTokenizerStub()
+    t = tok(["a photo of a cat", "two red cubes on a blue sphere next to a green cone", ""])
+    with torch.no_grad():
+        ref = model(t.input_ids, output_hidden_states=True)
+    out = EngineCLIPText(model, torch.float32)(t.input_ids, output_hidden_states=True)
+    torch.testing.assert_close(out.last_hidden_state, ref.last_hidden_state, rtol=1e-4, atol=1e-5)
+    assert len(out.hidden_states) == len(ref.hidden_states) == 3
+    for a, b in zip(out.hidden_states, ref.hidden_states):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    if which == "bigg":
+        assert out.keys() == ["text_embeds", "last_hidden_state", "hidden_states"]
+        torch.testing.assert_close(out[0], ref.text_embeds, rtol=1e-4, atol=1e-5)
+    else:
+        assert out.keys() == ["last_hidden_state", "pooler_output", "hidden_states"]
+        torch.testing.assert_close(out.pooler_output, ref.pooler_output, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(out[-1][-2], ref.hidden_states[-2], rtol=1e-4, atol=1e-5)
+    # key-padding mask on top of the causal mask (configs with use_attention_mask, TrainableSDPipeline.py:312-322)
+    with torch.no_grad():
+        ref_m = model(t.input_ids, attention_mask=t.attention_mask)
+    out_m = EngineCLIPText(model, torch.float32)(t.input_ids, attention_mask=t.attention_mask)
+    for i in range(3):
+        L = int(t.attention_mask[i].sum())
+        torch.testing.assert_close(out_m[0 if which == "clip_l" else 1][i, :L], ref_m.last_hidden_state[i, :L], rtol=1e-4, atol=1e-5)
+
+
+def _sd_pipe(enc, tok):
+    from comat_b200.pipelines import TrainableSDPipeline
+    pipe = TrainableSDPipeline.__new__(TrainableSDPipeline)
+    TrainableSDPipeline.__init__(pipe, vae=None, unet=None, text_encoder=enc, tokenizer=tok)
+    return pipe
+
+
+def test_sd_encode_prompt_matches_reference_golden(monkeypatch, golden):
+    EMU.install_blip(monkeypatch)
+    from comat_b200.synthetic import SyntheticClipTokenizer
+    from comat_b200.text_encoder import EngineCLIPText
+    gold = golden("encode_prompt")
+    for case in FX.ENCODE_PROMPT_CASES:
+        g = gold["seed%d" % case["seed"]]
+        pipe = _sd_pipe(EngineCLIPText(R.make_clip_text("clip_l", tiny=True, seed=case["seed"]), torch.float32), SyntheticClipTokenizer())
+        pe, npe = pipe.encode_prompt(case["prompts"], torch.device("cpu"), case["n_per"], case["cfg"], negative_prompt=_neg(case),
+                                     clip_skip=case["clip_skip"])
+        torch.testing.assert_close(pe, g["prompt_embeds"], rtol=1e-4, atol=1e-5)
+        if case["cfg"]:
+            torch.testing.assert_close(npe, g["negative_prompt_embeds"], rtol=1e-4, atol=1e-5)
+        else:
+            assert npe is None
+
+
+def test_sd_encode_prompt_errors_and_passthrough(monkeypatch):
+    EMU.install_blip(monkeypatch)
+    from comat_b200.synthetic import SyntheticClipTokenizer
+    from comat_b200.text_encoder import EngineCLIPText
+    pipe = _sd_pipe(EngineCLIPText(R.make_clip_text("clip_l", tiny=True, seed=1), torch.float32), SyntheticClipTokenizer())
+    with pytest.raises(TypeError):                                   # TrainableSDPipeline.py:363-367
+        pipe.encode_prompt(["a", "b"], torch.device("cpu"), 1, True, negative_prompt="x")
+    with pytest.raises(ValueError):                                  # :370-375
+        pipe.encode_prompt(["a", "b"], torch.device("cpu"), 1, True, negative_prompt=["x"])
+    # the trainer's null-embedding call (training_script.py:519): '' repeated train_batch_size times, no guidance
+    null = pipe.encode_prompt("", torch.device("cpu"), 3, False)[0]
+    assert null.shape == (3, 77, 128) and torch.equal(null[0], null[2])
+    # pre-computed embeddings skip the encoder entirely
+    bare = _sd_pipe(None, None)
+    pe, npe = bare.encode_prompt(None, torch.device("cpu"), 2, True, prompt_embeds=torch.ones(1, 77, 8), negative_prompt_embeds=torch.zeros(1, 77, 8))
+    assert pe.shape == npe.shape == (2, 77, 8)
+    with pytest.raises(NotImplementedError):
+        bare.encode_prompt("a", torch.device("cpu"), 1, False)
+
+
+@pytest.mark.parametrize("force_zeros,negative", [(True, None), (False, None), (True, "ugly")])
+def test_sdxl_encode_prompt_matches_oracle(monkeypatch, force_zeros, negative):
+    EMU.install_blip(monkeypatch)
+    from comat_b200.pipelines import TrainableSDXLPipeline
+    from comat_b200.synthetic import SyntheticClipTokenizer
+    from comat_b200.text_encoder import EngineCLIPText
+    e1, e2 = R.make_clip_text("clip_l", tiny=True, seed=11), R.make_clip_text("bigg", tiny=True, seed=12)
+    prompts = ["a brown horse and a white fence", "three yellow birds"]
+    ref = R.encode_prompt_sdxl(e1, e2, FX.ClipTokenizerStub(), FX.ClipTokenizerStub(pad_token_id=0), prompts, 2, True,
+                               negative_prompt=negative, force_zeros_for_empty_prompt=force_zeros)
+    pipe = TrainableSDXLPipeline.__new__(TrainableSDXLPipeline)
+    TrainableSDXLPipeline.__init__(pipe, vae=None, unet=None, text_encoder=EngineCLIPText(e1, torch.float32),
+                                   tokenizer=SyntheticClipTokenizer(), text_encoder_2=EngineCLIPText(e2, torch.float32),
+                                   tokenizer_2=SyntheticClipTokenizer(pad_token_id=0), force_zeros_for_empty_prompt=force_zeros)
+    got = pipe.encode_prompt(prompts, device=torch.device("cpu"), num_images_per_prompt=2, do_classifier_free_guidance=True,
+                             negative_prompt=negative)
+    assert got[0].shape == (4, 77, 256) and got[2].shape == (4, 64)
+    for a, b in zip(got, ref):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    if force_zeros and negative is None:
+        assert float(got[1].abs().max()) == 0.0 and float(got[3].abs().max()) == 0.0
+    # the trainer's call (training_script.py:521): 4-tuple, negatives None without guidance
+    null, nneg, pnull, pneg = pipe.encode_prompt("", device=torch.device("cpu"), num_images_per_prompt=3, do_classifier_free_guidance=False)
+    assert null.shape == (3, 77, 256) and pnull.shape == (3, 64) and nneg is None and pneg is None
+
+
+def test_trainer_step_from_prompt_strings_equals_step_from_oracle_embeddings(monkeypatch):
+    """training_script.py:513-525 + :575-588: the trainer encodes '' once, the pipeline encodes batch['text'] inside forward."""
+    from tests.test_trainer_logic_cpu import _emulate_cuda_only
+    _emulate_cuda_only(monkeypatch)
+    EMU.install_blip(monkeypatch)
+    from comat_b200 import containers as Cn, synthetic
+    from comat_b200.caption import Blip, CaptionModelWrapper
+    from comat_b200.modules import EngineUNet, EngineVAE
+    from comat_b200.pipelines import TrainableSDPipeline
+    from comat_b200.text_encoder import EngineCLIPText
+    from comat_b200.trainer import CoMatTrainer
+    B, S, res = 2, 2, 64
+    torch.manual_seed(0)
+    unet = Cn.UNet2DConditionModel(block_out_channels=(64, 128, 256, 256), heads=4, cross_attention_dim=128)
+    vae = Cn.AutoencoderKL(block_out_channels=(64, 64, 128, 128))
+    unet.requires_grad_(False); vae.requires_grad_(False)
+    unet.install_lora(4, up_std=0.05)
+    clip = R.make_clip_text("clip_l", tiny=True, seed=21)
+    args = synthetic.default_args(pretrain_model_name="sd_1_5", train_batch_size=B, K=1, total_step=S, gan_loss=False, resolution=res, seed=3)
+    pipe = TrainableSDPipeline(EngineVAE(vae, torch.float32), EngineUNet(unet, torch.float32), text_encoder=EngineCLIPText(clip, torch.float32),
+                               tokenizer=synthetic.SyntheticClipTokenizer())
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(R.make_blip(large=False))), None)
+    prompts = ["a red apple on a table", "two dogs"]
+    g = torch.Generator().manual_seed(9)
+    ids, mask = FX.blip_token_batch(g, B, 8)
+    base = dict(blip={"input_ids": ids, "attention_mask": mask}, init_latents=torch.randn(B, 4, res // 8, res // 8, generator=g),
+                noises=[torch.randn(B, 4, res // 8, res // 8, generator=g) for _ in range(S)], training_steps=[1], attrcon_steps=None, crop=(0, 0))
+    l_text = tr.g_losses(dict(base, text=prompts))["loss"]
+    pe, _, _ = R.encode_prompt_sd(clip, FX.ClipTokenizerStub(), prompts, 1, False)
+    null, _, _ = R.encode_prompt_sd(clip, FX.ClipTokenizerStub(), "", B, False)
+    assert tr.null_embed.shape == (B, 77, 128)
+    torch.testing.assert_close(tr.null_embed, null, rtol=1e-4, atol=1e-5)
+    l_emb = tr.g_losses(dict(base, prompt_embeds=pe, null_embeds=null))["loss"]
+    assert abs(float(l_text.detach()) - float(l_emb.detach())) < 1e-4 * abs(float(l_emb.detach()))
+    args2 = synthetic.default_args(pretrain_model_name="sd_1_5", train_text_encoder_lora=True)
+    with pytest.raises(NotImplementedError):
+        CoMatTrainer(args2, pipe, None, None)
