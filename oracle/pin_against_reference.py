@@ -260,8 +260,40 @@ def pin_encode_prompt():
     return out
 
 
+def reference_function(rel_path: str, name: str, namespace: dict):
+    """compile ONE top-level function of a reference file that cannot be imported whole (training_script.py imports accelerate)
+    from its own source text - nothing is copied into the repo; the function body runs verbatim."""
+    import ast
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, rel_path)).read()
+    tree = ast.parse(src)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    code = compile(ast.Module(body=[fn], type_ignores=[]), os.path.join(ref_shim.REFERENCE_ROOT, rel_path), "exec")
+    exec(code, namespace)
+    return namespace[name]
+
+
+def pin_lora_state_dict():
+    """Reference ``unet_lora_state_dict`` (training_script.py:50-66), verbatim, on the restated diffusers-shaped UNets with LoRA
+    installed (meta device: names and shapes only) -> the tensor names / shapes of pytorch_lora_weights.safetensors before
+    diffusers' own ``unet.`` prefixing.  Written as JSON (tests/golden/lora_state_dict_keys.json)."""
+    import json
+    fn = reference_function("training_script.py", "unet_lora_state_dict", {"UNet2DConditionModel": sdm.UNet2DConditionModel, "torch": torch})
+    out = {}
+    for name, cfg, rank in (("sd15_r128", {}, 128), ("sdxl_r128", sdm.SDXL_UNET_CONFIG, 128), ("tiny_r4", sdm.tiny_unet_config(width=64, cross_attention_dim=64), 4)):
+        with torch.device("meta"):
+            unet = sdm.UNet2DConditionModel(**cfg)
+            sdm.install_lora(unet, rank)
+        sd = fn(unet)
+        out[name] = {"n": len(sd), "numel": int(sum(v.numel() for v in sd.values())), "keys": [[k, list(v.shape)] for k, v in sd.items()]}
+    with open(os.path.join(GOLDEN_DIR, "lora_state_dict_keys.json"), "w") as f:
+        json.dump(out, f)
+    print({k: (v["n"], v["numel"]) for k, v in out.items()})
+    return None
+
+
 PINS = [("layer_loss", pin_layer_loss), ("mask_loss", pin_mask_loss), ("blip_score", pin_blip_score),
-        ("gan", pin_gan), ("pipeline", pin_attention_store_and_pipeline), ("encode_prompt", pin_encode_prompt)]
+        ("gan", pin_gan), ("pipeline", pin_attention_store_and_pipeline), ("encode_prompt", pin_encode_prompt),
+        ("lora_state_dict", pin_lora_state_dict)]
 
 
 def main():
@@ -272,6 +304,8 @@ def main():
         if only and name not in only:
             continue
         res = fn()
+        if res is None:                   # the pin wrote its own (JSON) golden
+            continue
         path = os.path.join(GOLDEN_DIR, f"{name}.pt")
         torch.save(res, path)
         print(f"pinned {name}: {len(res)} cases -> {path} ({os.path.getsize(path)} bytes)")
