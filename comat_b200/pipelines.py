@@ -210,6 +210,32 @@ class TrainableSDPipeline:
     def _added_cond(self, n, height, width, cfg, added_cond_kwargs, sdxl_kwargs):
         return added_cond_kwargs
 
+    @torch.no_grad()
+    def __call__(self, prompt=None, height: int = 512, width: int = 512, num_inference_steps: int = 50, guidance_scale: float = 7.5,
+                 negative_prompt=None, num_images_per_prompt: int = 1, eta: float = 0.0, generator=None, latents=None,
+                 prompt_embeds=None, negative_prompt_embeds=None, output_type: str = "pil", return_dict: bool = True,
+                 guidance_rescale: float = 0.0, noises=None, **sdxl_kwargs):
+        """Plain sampling - the inherited diffusers ``__call__`` as the reference uses it: GAN ground-truth latents
+        (tools/gan_gt_generate.py:171-180, 50 steps, cfg 7.5, ``output_type='latent'``) and validation images
+        (training_script.py:456-489).  Same rollout as ``forward`` with no training timesteps; every UNet call is a no-grad
+        forward (CUDA-graphed when ``unet.use_graphs``).  ``.images``: latents, or the decoded image clamped to [0, 1] as a
+        tensor (``'pt'``), HWC numpy (``'np'``) or PIL images (``'pil'``)."""
+        if output_type not in ("latent", "pt", "np", "pil"):
+            raise ValueError(f"output_type {output_type!r}")
+        out = self.forward(prompt=prompt, height=height, width=width, training_timesteps=(), num_inference_steps=num_inference_steps,
+                           guidance_scale=guidance_scale, negative_prompt=negative_prompt, num_images_per_prompt=num_images_per_prompt,
+                           eta=eta, generator=generator, latents=latents, prompt_embeds=prompt_embeds,
+                           negative_prompt_embeds=negative_prompt_embeds, output_type="latent" if output_type == "latent" else "image",
+                           guidance_rescale=guidance_rescale, noises=noises, **sdxl_kwargs)
+        if output_type != "latent":
+            out = out.clamp(0, 1)
+            if output_type in ("np", "pil"):
+                out = out.permute(0, 2, 3, 1).float().cpu().numpy()
+            if output_type == "pil":
+                from PIL import Image
+                out = [Image.fromarray((im * 255).round().astype("uint8")) for im in out]
+        return SimpleNamespace(images=out) if return_dict else (out,)
+
 
 class TrainableSDXLPipeline(TrainableSDPipeline):
     """SDXL twin (TrainableSDPipeline.py:427-846): UNet input always detached, pooled-text + time-id conditioning."""
