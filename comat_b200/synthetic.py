@@ -89,9 +89,10 @@ def build_clip_text(device, dtype=torch.float16, seed=7, which="clip_l", tiny=Fa
         kw.update(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, projection_dim=64)
     cfg = CLIPTextConfig(vocab_size=49408, max_position_embeddings=77, eos_token_id=2, bos_token_id=0, pad_token_id=1, **kw)
     torch.manual_seed(seed)
-    m = cls(cfg)
+    with torch.device(device):
+        m = cls(cfg)
     m.eval().requires_grad_(False)
-    return m.to(device=device, dtype=dtype)
+    return m.to(dtype=dtype)
 
 
 class SyntheticClipTokenizer:

@@ -37,6 +37,8 @@ def test_clip_text_executor_vs_hf(which, layers, dtype, tol):
     n_layers = model.config.num_hidden_layers
     assert _lib.LAUNCH_COUNT - l0 >= 7 * n_layers        # 2 LN + 4 GEMM + 1 attention per block, all ours
     assert out.last_hidden_state.dtype == torch.float32 and len(out.hidden_states) == n_layers + 1
+    print(f"[measured] {which} L={n_layers} {dtype}: last {rel(out.last_hidden_state, ref.last_hidden_state):.2e} "
+          f"h[-2] {rel(out.hidden_states[-2], ref.hidden_states[-2]):.2e}")
     assert rel(out.last_hidden_state, ref.last_hidden_state) < tol
     assert rel(out.hidden_states[-2], ref.hidden_states[-2]) < tol
     if which == "bigg":
@@ -70,6 +72,7 @@ def test_encode_prompt_sd15_on_strings_vs_oracle():
             return t
     pe_ref, npe_ref, _ = R.encode_prompt_sd(model, _Tok(), PROMPTS[:2], 2, True)
     assert pe.shape == pe_ref.shape == (4, 77, 768) and pe.is_cuda
+    print(f"[measured] sd15 encode_prompt: {rel(pe, pe_ref):.2e} {rel(npe, npe_ref):.2e}")
     assert rel(pe, pe_ref) < 5e-3 and rel(npe, npe_ref) < 5e-3
     null = pipe.encode_prompt("", dev, 4, False)[0]                          # training_script.py:519
     assert null.shape == (4, 77, 768) and rel(null[:1], npe_ref[:1]) < 5e-3
@@ -94,5 +97,6 @@ def test_encode_prompt_sdxl_on_strings_vs_oracle():
     ref = R.encode_prompt_sdxl(e1, e2, _Tok(), _Tok(pad_token_id=0), PROMPTS[:3], 1, True, force_zeros_for_empty_prompt=False)
     got = pipe.encode_prompt(PROMPTS[:3], device=torch.device("cuda"), num_images_per_prompt=1, do_classifier_free_guidance=True)
     assert got[0].shape == (3, 77, 2048) and got[2].shape == (3, 1280)
+    print("[measured] sdxl encode_prompt:", ["%.2e" % rel(a, b) for a, b in zip(got, ref)])
     for a, b in zip(got, ref):
         assert rel(a, b) < 5e-3
