@@ -122,9 +122,42 @@ class _TextOutput:
         return len(self._keys)
 
 
+class _GraphedEncoder:
+    """One captured encoder forward for a fixed (batch, length, mask?, hidden?) signature: ~100 launches of a launch-bound pass
+    (M = B x 77 rows) replayed by one cudaGraphLaunch.  Token ids / mask are static inputs, outputs are static buffers."""
+
+    def __init__(self, eng: ClipTextEngine, ids, mask, all_hidden):
+        from . import _lib
+        self.ids = ids.clone()
+        self.mask = None if mask is None else mask.clone()
+        run = lambda: eng.forward(self.ids, self.mask, all_hidden=all_hidden)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()                                   # eager warm-up off the capturing stream (one-time entry-point setup)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCH_COUNT
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+        self.launches = _lib.LAUNCH_COUNT - l0
+
+    def __call__(self, ids, mask):
+        from . import _lib
+        self.ids.copy_(ids)
+        if self.mask is not None:
+            self.mask.copy_(mask)
+        self.graph.replay()
+        _lib.count_launch(self.launches)
+        return self.out                             # static buffers: the caller converts (copies) before the next replay
+
+
 class EngineCLIPText(torch.nn.Module):
     """HF call surface ``text_encoder(input_ids, attention_mask=None, output_hidden_states=False)`` backed by ``ClipTextEngine``.
-    Outputs are fp32 (the pipelines' interface dtype, like ``EngineUNet.dtype``); the arithmetic is 16-bit on the tensor cores."""
+    Outputs are fp32 (the pipelines' interface dtype, like ``EngineUNet.dtype``); the arithmetic is 16-bit on the tensor cores.
+    ``use_graphs`` (default on for CUDA inputs): one captured CUDA graph per call signature, at most ``MAX_GRAPHS`` kept."""
+
+    MAX_GRAPHS = 8
 
     def __init__(self, model, dtype=torch.float16):
         super().__init__()
@@ -133,6 +166,8 @@ class EngineCLIPText(torch.nn.Module):
         self.engine = ClipTextEngine(model, dtype)
         self.with_projection = self.engine.proj is not None
         self.text_model = SimpleNamespace(final_layer_norm=lambda h: self.engine.final_layer_norm(h).float())
+        self.use_graphs = True
+        self._graphs = {}
 
     @property
     def dtype(self):
@@ -144,9 +179,19 @@ class EngineCLIPText(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, input_ids, attention_mask=None, output_hidden_states: bool = False, **_):
-        last, pooled, embeds, hidden = self.engine.forward(input_ids.to(self.device), None if attention_mask is None else
-                                                           attention_mask.to(self.device), all_hidden=bool(output_hidden_states))
-        hs = None if hidden is None else tuple(x.float() for x in hidden)
+        ids = input_ids.to(self.device)
+        mask = None if attention_mask is None else attention_mask.to(self.device)
+        if self.use_graphs and ids.is_cuda:
+            key = (tuple(ids.shape), mask is not None, bool(output_hidden_states))
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= self.MAX_GRAPHS:
+                    self._graphs.pop(next(iter(self._graphs)))
+                g = self._graphs[key] = _GraphedEncoder(self.engine, ids, mask, bool(output_hidden_states))
+            last, pooled, embeds, hidden = g(ids, mask)
+        else:
+            last, pooled, embeds, hidden = self.engine.forward(ids, mask, all_hidden=bool(output_hidden_states))
+        hs = None if hidden is None else tuple(x.float() for x in hidden)       # .float() copies out of the graph's buffers
         if self.with_projection:           # CLIPTextModelOutput: text_embeds first (SDXL reads out[0] as the pooled vector)
             return _TextOutput(text_embeds=embeds.float(), last_hidden_state=last.float(), hidden_states=hs)
         return _TextOutput(last_hidden_state=last.float(), pooler_output=pooled.float(), hidden_states=hs)

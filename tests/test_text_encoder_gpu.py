@@ -100,3 +100,28 @@ def test_encode_prompt_sdxl_on_strings_vs_oracle():
     print("[measured] sdxl encode_prompt:", ["%.2e" % rel(a, b) for a, b in zip(got, ref)])
     for a, b in zip(got, ref):
         assert rel(a, b) < 5e-3
+
+
+def test_graphed_encoder_replays_follow_inputs_and_match_eager():
+    """the captured forward (static id / mask buffers) returns what the eager launches return, call after call, per signature."""
+    from comat_b200.text_encoder import EngineCLIPText
+    model = R.make_clip_text("bigg", tiny=False, seed=5, device="cuda", layers=3)
+    enc = EngineCLIPText(model, torch.float16)
+    tok = FX.ClipTokenizerStub()
+    a, b = tok(PROMPTS[:3]), tok(PROMPTS[2:5])
+    enc.use_graphs = False
+    want = [enc(t.input_ids.cuda(), output_hidden_states=True) for t in (a, b)]
+    want_m = enc(a.input_ids.cuda(), attention_mask=a.attention_mask.cuda())
+    enc.use_graphs = True
+    for t, w in ((a, want[0]), (b, want[1]), (b, want[1]), (a, want[0])):
+        got = enc(t.input_ids.cuda(), output_hidden_states=True)
+        assert torch.equal(got.text_embeds, w.text_embeds) and torch.equal(got.last_hidden_state, w.last_hidden_state)
+        assert all(torch.equal(x, y) for x, y in zip(got.hidden_states, w.hidden_states))
+    got_m = enc(a.input_ids.cuda(), attention_mask=a.attention_mask.cuda())
+    assert torch.equal(got_m.last_hidden_state, want_m.last_hidden_state)
+    assert len(enc._graphs) == 2                                      # (3,77) with hidden states; (3,77) with a mask
+    # results handed out earlier are copies, not views of the graph's static buffers
+    first = enc(a.input_ids.cuda(), output_hidden_states=True).last_hidden_state
+    keep = first.clone()
+    enc(b.input_ids.cuda(), output_hidden_states=True)
+    assert torch.equal(first, keep)
