@@ -125,3 +125,32 @@ def test_checkpoint_round_trip_on_device(tmp_path):
             assert torch.equal(la.down16, lb.down16) and torch.equal(la.up16, lb.up16)
         ya = a.pipeline.unet(x, t, encoder_hidden_states=ehs)[0]
         assert torch.isfinite(ya).all()
+
+
+def test_train_step_from_prompt_strings_on_device():
+    """training_script.py:513-525,575-588 on the device: '' encoded once by the trainer, batch['text'] encoded inside forward;
+    the loss equals the one obtained from the oracle's fp32 embeddings of the same strings (16-bit encoder error only)."""
+    from comat_b200 import synthetic
+    from comat_b200.blip_engine import BlipEngine
+    from comat_b200.caption import Blip, CaptionModelWrapper
+    from comat_b200.trainer import CoMatTrainer
+    pipe, _, clip = _world()
+    B, S, res = 2, 2, 256
+    args = synthetic.default_args(pretrain_model_name="sd_1_5", train_batch_size=B, K=1, total_step=S, gan_loss=False, resolution=res, seed=3)
+    blip = Blip(BlipEngine(R.make_blip(large=False).cuda(), torch.float16))
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], blip), None)
+    prompts = ["a red apple on a table", "two dogs"]
+    g = torch.Generator().manual_seed(9)
+    ids, mask = FX.blip_token_batch(g, B, 8)
+    base = dict(blip={"input_ids": ids.cuda(), "attention_mask": mask.cuda()}, init_latents=torch.randn(B, 4, res // 8, res // 8, generator=g).cuda(),
+                noises=[torch.randn(B, 4, res // 8, res // 8, generator=g).cuda() for _ in range(S)], training_steps=[1], attrcon_steps=None, crop=(0, 0))
+    l_text = tr.g_losses(dict(base, text=prompts))["loss"].detach()
+    pe, _, _ = R.encode_prompt_sd(clip, _Tok(), prompts, 1, False)
+    null, _, _ = R.encode_prompt_sd(clip, _Tok(), "", B, False)
+    assert tr.null_embed.shape == (B, 77, 128) and rel(tr.null_embed, null) < 5e-3
+    l_emb = tr.g_losses(dict(base, prompt_embeds=pe, null_embeds=null))["loss"].detach()
+    print(f"[measured] step loss from strings {float(l_text):.6f} vs from oracle embeddings {float(l_emb):.6f}")
+    assert abs(float(l_text) - float(l_emb)) < 5e-3 * abs(float(l_emb))
+    out = tr.train_step(dict(base, text=prompts))                    # full step (backward + fused AdamW) from strings
+    tr.sync()
+    assert torch.isfinite(out["step_loss"])
