@@ -24,14 +24,19 @@ LIBRARY_CALLS = 0
 
 
 class Blip(torch.nn.Module):
-    def __init__(self, model, device=None, prompt_length: int = 4, pad_token_id: int = 0):
+    def __init__(self, model, device=None, prompt_length: int = 4, pad_token_id: int = 0, tokenizer=None):
         """``model``: a BlipEngine or an HF BlipForConditionalGeneration (frozen, caption_blip.py:20-21).
-        ``prompt_length`` = len(tok("a photography of").input_ids) - 1 (caption_blip.py:38-39) = 4 for BERT wordpieces."""
+        ``prompt_length`` = len(tok("a photography of").input_ids) - 1 (caption_blip.py:38-39) = 4 for BERT wordpieces.
+        ``tokenizer`` (optional, the BLIP processor's BertTokenizer protocol): lets ``score`` take prompt strings (:47-48)."""
         super().__init__()
         self.model = model
         self.prompt = "a photography of"
         self.prompt_length = prompt_length
         self.pad_token_id = pad_token_id
+        self.tokenizer = tokenizer
+        if tokenizer is not None:
+            self.prompt_length = len(tokenizer(self.prompt).input_ids) - 1
+            self.pad_token_id = tokenizer.pad_token_id
         for p in getattr(model, "parameters", lambda: [])():
             p.requires_grad = False
 
@@ -42,7 +47,11 @@ class Blip(torch.nn.Module):
     def score(self, images, prompts=None, input_ids: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None, **_):
         global LIBRARY_CALLS
         if input_ids is None:
-            raise NotImplementedError("pass input_ids/attention_mask (BERT tokenisation of 'a photography of ' + prompt.lower())")
+            if self.tokenizer is None or prompts is None:
+                raise NotImplementedError("pass input_ids/attention_mask (BERT tokenisation of 'a photography of ' + prompt.lower()) "
+                                          "or build Blip with a tokenizer")
+            t = self.tokenizer([self.prompt + " " + p.lower() for p in prompts], return_tensors="pt", padding="longest")   # :47-48
+            input_ids, attention_mask = t.input_ids.to(images.device), t.attention_mask.to(images.device)
         pix = self.preprocess(images)
         labels = input_ids.masked_fill(input_ids == self.pad_token_id, IGNORE_INDEX)        # caption_blip.py:51-53
         labels[:, : self.prompt_length] = IGNORE_INDEX                                       # :54

@@ -128,6 +128,34 @@ class SyntheticClipTokenizer:
         return SimpleNamespace(input_ids=ids, attention_mask=am)
 
 
+class SyntheticBertTokenizer:
+    """Stand-in for the BLIP processor's ``BertTokenizer`` (vocabulary not on disk): [CLS] 101 + one id per whitespace word +
+    [SEP] 102, right-padded with 0 to the longest row; 'a photography of' maps to the real wordpiece ids 1037 5855 1997 so
+    ``prompt_length = len(tok('a photography of').input_ids) - 1 = 4`` as in caption_blip.py:38-39.  Other words hash (FNV-1a)
+    into [1000, 30000) like SURVEY 8d's synthetic ids."""
+
+    pad_token_id, cls_token_id, sep_token_id = 0, 101, 102
+    _FIXED = {"a": 1037, "photography": 5855, "of": 1997}
+
+    def _ids(self, text: str):
+        return [self.cls_token_id] + [self._FIXED.get(w) or 1000 + SyntheticClipTokenizer._word_id(w) % 29000 for w in text.lower().split()] + [self.sep_token_id]
+
+    def __call__(self, text, padding="longest", return_tensors=None, **_):
+        if isinstance(text, str):
+            ids = self._ids(text)
+            if return_tensors is None:
+                return SimpleNamespace(input_ids=ids, attention_mask=[1] * len(ids))
+            text = [text]
+        rows = [self._ids(t) for t in text]
+        T = max(len(r) for r in rows)
+        ids = torch.zeros(len(rows), T, dtype=torch.long)
+        am = torch.zeros(len(rows), T, dtype=torch.long)
+        for i, r in enumerate(rows):
+            ids[i, :len(r)] = torch.tensor(r)
+            am[i, :len(r)] = 1
+        return SimpleNamespace(input_ids=ids, attention_mask=am)
+
+
 def random_mask(g, size=512, empty=False):
     m = torch.zeros(1, 1, size, size, dtype=torch.bool)
     if empty:

@@ -1,0 +1,267 @@
+"""Training entry point - the loop of ``Trainer.train`` (training_script.py:496-735) around ``CoMatTrainer.train_step``:
+epochs over the prompt data, resume (``--resume_from_checkpoint``, :156-205), per-step logs, ``checkpoint-<n>`` every
+``--validation_steps`` (:711-717) and at the end (:722-733), ``--max_train_steps``.
+
+    torchrun --nproc-per-node 8 -m comat_b200.train --pretrain_model_name sd_1_5_attrcon --gan_loss ... [reference flags]
+
+takes the reference's 72 flags unchanged (``comat_b200.arguments``) plus ``--weights synthetic|synthetic_tiny`` - this image has
+no Hub access, diffusers or tokenizer vocabularies, so the entry point builds random-init networks at the real geometry and the
+stand-in tokenizers of ``comat_b200.synthetic``; a deployment passes real modules through ``Trainer(args, components=...)``
+(see INTEGRATION.md).  What the reference obtains from Grounded-SAM + spaCy per batch (noun / attribute token lists, masks:
+training_script.py:627-637) comes from ``components['attr_provider'](prompts, images) -> (words, masks)``; the synthetic entry
+uses the SURVEY 8d generator.  Logs go to ``<output_dir>/train_log.jsonl`` (one JSON object per optimiser step) instead of
+TensorBoard; scalars are read back once per ``--log_every`` steps, not 7 ``.item()`` syncs per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import random
+import sys
+import time
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import checkpoint as CK
+from . import synthetic
+from .arguments import parse_args
+from .data import ShardedBatches, get_dataset
+
+
+def lr_at(args, step: int) -> float:
+    """multiplier schedule of diffusers' ``get_scheduler(args.lr_scheduler, num_warmup_steps, num_training_steps)``
+    (training_script.py:289-294; un-vendored, the published definitions) evaluated at optimiser step ``step``."""
+    name, warm, total = args.lr_scheduler, args.lr_warmup_steps, max(1, args.max_train_steps)
+    if name == "constant":
+        return 1.0
+    if step < warm:
+        return step / max(1, warm)
+    if name == "constant_with_warmup":
+        return 1.0
+    prog = (step - warm) / max(1, total - warm)
+    if name == "linear":
+        return max(0.0, 1.0 - prog)
+    if name == "cosine":
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
+    raise NotImplementedError(f"lr_scheduler {name!r}")
+
+
+def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False) -> Dict:
+    """random-init networks at the real (or tiny) geometry + stand-in tokenizers (no Hub access in this image)."""
+    from .blip_engine import BlipEngine
+    from .caption import Blip, CaptionModelWrapper
+    from .gan import D_sd
+    from .modules import EngineUNet, EngineVAE
+    from . import pipelines as P
+    from .text_encoder import EngineCLIPText
+    name = args.pretrain_model_name
+    if "sdxl" in name:
+        raise NotImplementedError("the synthetic entry point builds SD1.5 pipelines; pass SDXL modules through components=")
+    seed = args.seed if args.seed is not None else 42
+    rank = 8 if tiny else args.lora_rank
+
+    def tiny_unet(sd):            # tiny geometry whose text-context width matches the tiny CLIP tower (128)
+        from . import containers as Cn
+        torch.manual_seed(sd)
+        with torch.device(device):
+            u = Cn.UNet2DConditionModel(block_out_channels=(64, 128, 256, 256), heads=4, cross_attention_dim=128)
+        u.requires_grad_(False)
+        u.install_lora(rank)
+        return u
+    unet, vae = synthetic.build_sd15(device, dtype, rank=rank, seed=seed, tiny=tiny)
+    if tiny:
+        unet = tiny_unet(seed)
+    clip = synthetic.build_clip_text(device, torch.float32, seed=seed + 1, which="clip_l", tiny=tiny)
+    cls = P.AttrConcenTrainableSDPipeline if "attrcon" in name else P.TrainableSDPipeline
+    pipe = cls(EngineVAE(vae, dtype), EngineUNet(unet, dtype), text_encoder=EngineCLIPText(clip, dtype),
+               tokenizer=synthetic.SyntheticClipTokenizer())
+    blip = Blip(BlipEngine(synthetic.build_blip(device, dtype, large=not tiny), dtype), tokenizer=synthetic.SyntheticBertTokenizer())
+    comp = {"pipeline": pipe, "caption_model": CaptionModelWrapper(list(args.caption_model), list(args.reward_weights), blip), "D": None}
+    if args.gan_loss:
+        d_unet = tiny_unet(seed + 2) if tiny else synthetic.build_sd15(device, dtype, rank=rank, seed=seed + 2)[0]
+        d_pipe = P.TrainableSDPipeline(None, None, text_encoder=pipe.text_encoder, tokenizer=pipe.tokenizer)
+        comp["D"] = D_sd(EngineUNet(d_unet, dtype), pipeline=d_pipe)
+    if "attrcon" in name:
+        g = torch.Generator().manual_seed(seed + 3)
+        rr = random.Random(seed + 3)
+
+        def attr_provider(prompts, images):
+            """SURVEY 8d stand-in for Grounded-SAM + spaCy: 1-3 words per prompt with 1-3 token positions each inside the
+            prompt's token span, rectangle masks, 10 % empty ('not detected', gsam_interface.py:132-133)."""
+            res = images.shape[-1]
+            words, masks = [], []
+            for _ in prompts:
+                nw = rr.randint(1, 3)
+                pos = rr.sample(range(1, 40), 9)
+                words.append([[pos.pop() for _ in range(rr.randint(1, 3))] for _ in range(nw)])
+                m = torch.cat([synthetic.random_mask(g, res, empty=(rr.random() < 0.1)) for _ in range(nw)]).to(images.device)
+                masks.append([m[i:i + 1] for i in range(nw)])
+            return words, masks
+        comp["attr_provider"] = attr_provider
+    return comp
+
+
+class Trainer:
+    """training_script.py:100-735 around the B200 step."""
+
+    def __init__(self, args, components: Optional[Dict] = None, device=None, rank: int = 0, world: int = 1, process_group=None,
+                 weights: str = "synthetic", log_every: int = 1, dtype=torch.float16, train_layer_ls=None):
+        from .pipelines import AttentionStore, register_attention_control
+        from .trainer import CoMatTrainer
+        if args.gradient_accumulation_steps != 1:
+            raise NotImplementedError("gradient_accumulation_steps > 1 (the CoMat scripts use 1: scripts/sd15.sh, scripts/sdxl.sh)")
+        if args.full_finetuning or args.tune_vae:
+            raise NotImplementedError("--full_finetuning / --tune_vae: this path trains the LoRA factors only")
+        self.args, self.rank, self.world, self.log_every = args, rank, world, max(1, log_every)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        if args.seed is not None:                                                    # :129-130 set_seed(args.seed + process_index)
+            random.seed(args.seed + rank)
+            torch.manual_seed(args.seed + rank)
+        comp = components or synthetic_components(args, self.device, dtype, tiny=(weights == "synthetic_tiny"))
+        self.pipeline, self.caption_model, self.D = comp["pipeline"], comp["caption_model"], comp.get("D")
+        self.attr_provider = comp.get("attr_provider")
+        if "attrcon" in args.pretrain_model_name:                                     # :307-320
+            layers = train_layer_ls or comp.get("train_layer_ls") or (["mid_16", "up_16", "up_32"] if "sdxl" in args.pretrain_model_name
+                                                    else ["mid_8", "up_16", "up_32", "up_64"])
+            args.train_layer_ls = layers
+            register_attention_control(self.pipeline, AttentionStore(layers))
+            if self.attr_provider is None:
+                raise NotImplementedError("attrcon models need components['attr_provider'] (Grounded-SAM + spaCy are external)")
+        self.pipeline.unet.use_graphs = True
+        self.core = CoMatTrainer(args, self.pipeline, self.caption_model, self.D, rng=random.Random((args.seed or 0) + rank),
+                                 process_group=process_group)
+        self.dataset = get_dataset(args)
+        self.loader = ShardedBatches(self.dataset, args.train_batch_size, rank, world, seed=args.seed or 0)
+        self.steps_per_epoch = max(1, len(self.loader))                               # :282
+        if args.max_train_steps is None:
+            args.max_train_steps = args.num_train_epochs * self.steps_per_epoch
+        args.num_train_epochs = math.ceil(args.max_train_steps / self.steps_per_epoch)   # :326
+        self.global_step = 0
+        if args.resume_from_checkpoint:                                               # :156-205
+            if args.resume_from_checkpoint == "latest":
+                step = CK.load_checkpoint(self.core, args.output_dir, "latest")
+            else:
+                step = CK.load_checkpoint(self.core, args.resume_from_checkpoint, "explicit")
+            if step is None:
+                self._print(f"Checkpoint '{args.resume_from_checkpoint}' does not exist. Starting a new training run.")
+            else:
+                self._print(f"Resuming from checkpoint-{step}")
+                self.global_step = step
+        self.first_epoch = self.global_step // self.steps_per_epoch                   # :287-288
+        self.resume_step = self.global_step % self.steps_per_epoch
+        self._pending = []
+        self._log_file = None
+        if rank == 0:
+            os.makedirs(args.output_dir, exist_ok=True)
+            self._log_file = open(os.path.join(args.output_dir, "train_log.jsonl"), "a")
+
+    def _print(self, *a):
+        if self.rank == 0:
+            print(*a, file=sys.stderr, flush=True)
+
+    def _barrier(self):
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier()
+
+    def save(self):
+        """:711-717 / :722-733: rank 0 writes ``checkpoint-<global_step>`` (all ranks hold identical parameters under DP)."""
+        path = None
+        if self.rank == 0:
+            path = CK.save_checkpoint(self.core, self.args.output_dir, self.global_step)
+        self._barrier()
+        return path
+
+    def _flush_logs(self):
+        """ONE device->host transfer for all scalars queued since the last flush."""
+        if not self._pending:
+            return
+        keys = sorted({k for _, d in self._pending for k in d})
+        mat = torch.stack([torch.stack([d[k].float().reshape(()) if k in d else torch.full((), float("nan"), device=self.device)
+                                        for k in keys]) for _, d in self._pending])
+        if self.world > 1 and dist.is_initialized():                                  # :673-683 accelerator.gather(...).mean()
+            dist.all_reduce(mat, op=dist.ReduceOp.SUM)
+            mat /= self.world
+        host = mat.cpu()
+        if self._log_file is not None:
+            for (step, _), row in zip(self._pending, host):
+                rec = {"step": step, "lr": self.args.learning_rate * lr_at(self.args, step - 1)}
+                rec.update({k: float(v) for k, v in zip(keys, row) if not math.isnan(float(v))})
+                self._log_file.write(json.dumps(rec) + "\n")
+            self._log_file.flush()
+        self._pending = []
+
+    def _make_batch(self, raw: Dict) -> Dict:
+        a = self.args
+        batch = dict(raw)
+        if a.batch_repeat > 1:                                                        # :552-553
+            batch["text"] = batch["text"] * a.batch_repeat
+        if "real_latents" in batch:
+            batch["real_latents"] = batch["real_latents"].to(self.device, non_blocking=True)
+        return batch
+
+    def train(self) -> int:
+        a = self.args
+        self._print(f"***** Running training *****  examples {len(self.dataset)}  epochs {a.num_train_epochs}  "
+                    f"batch/device {a.train_batch_size}  world {self.world}  optimisation steps {a.max_train_steps}")
+        t0 = time.time()
+        for epoch in range(self.first_epoch, a.num_train_epochs):
+            self.loader.set_epoch(epoch)
+            for step, raw in enumerate(self.loader):
+                if a.resume_from_checkpoint and epoch == self.first_epoch and step < self.resume_step:   # :546-549
+                    continue
+                if self.global_step >= a.max_train_steps:
+                    break
+                batch = self._make_batch(raw)
+                if self.attr_provider is not None:
+                    # the reference segments the generated image inside the step (:627-637); the provider sees the prompts and
+                    # the image size - masks for the synthetic provider do not depend on the pixels
+                    probe = torch.empty(0, 3, a.resolution, a.resolution, device=self.device)
+                    batch["words"], batch["masks"] = self.attr_provider(batch["text"], probe)
+                self.core.optimizer.lr = a.learning_rate * lr_at(a, self.global_step)  # :663 lr_scheduler.step()
+                logs = self.core.train_step(batch)
+                self.global_step += 1
+                self._pending.append((self.global_step, {k: v.detach() for k, v in logs.items() if torch.is_tensor(v) and v.numel() == 1}))
+                if self.global_step % self.log_every == 0:
+                    self._flush_logs()
+                if self.global_step % a.validation_steps == 0:                        # :711-717 (saving half of save_and_evaluate)
+                    self._flush_logs()
+                    self.save()
+            if self.global_step >= a.max_train_steps:
+                break
+        self.core.sync()
+        self._flush_logs()
+        self.save()                                                                   # :722-733
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        self._print(f"done: {self.global_step} steps in {time.time() - t0:.1f} s")
+        if self._log_file is not None:
+            self._log_file.close()
+        return self.global_step
+
+
+def main(argv=None) -> int:
+    pre = argparse.ArgumentParser(add_help=False)
+    pre.add_argument("--weights", choices=["synthetic", "synthetic_tiny"], default="synthetic")
+    pre.add_argument("--log_every", type=int, default=10)
+    extra, rest = pre.parse_known_args(argv)
+    args = parse_args(rest)
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("comat_b200.train needs a GPU: the package has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tr = Trainer(args, None, dev, rank, world, weights=extra.weights, log_every=extra.log_every)
+    tr.train()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -78,3 +78,49 @@ def test_two_rank_flat_allreduce_matches_single_process(tmp_path):
     finally:
         optim.FlatAdamW.step = old
     assert torch.allclose(got, opt.flat, atol=1e-6), (got - opt.flat).abs().max()
+
+
+# ---- the training entry point under DP (comat_b200/train.py): sharded prompts, one gradient all-reduce per optimiser, rank-0
+# ---- checkpoints, rank-averaged logs
+class _Patch:
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def _loop_worker(rank, world, port, prompts, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests import cpu_ops_emulation as EMU
+    from tests.test_trainer_logic_cpu import _emulate_cuda_only
+    _emulate_cuda_only(_Patch())
+    EMU.install_blip(_Patch())
+    from comat_b200 import optim, synthetic
+    from comat_b200.train import Trainer
+    optim.FlatAdamW.step = _torch_step
+    a = synthetic.default_args(pretrain_model_name="sd_1_5", train_batch_size=1, K=1, total_step=2, resolution=64,
+                               training_prompts=prompts, output_dir=out, max_train_steps=2, validation_steps=100,
+                               resume_from_checkpoint=None, seed=3, gradient_accumulation_steps=1)
+    tr = Trainer(a, None, torch.device("cpu"), rank, world, weights="synthetic_tiny", dtype=torch.float32)
+    seen = [t for b in tr.loader for t in b["text"]]
+    tr.train()
+    torch.save({"flat": tr.core.optimizer.flat.clone(), "seen": seen}, os.path.join(out, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_loop(tmp_path):
+    import json
+    prompts = tmp_path / "prompts.txt"
+    prompts.write_text("\n".join(["a red apple", "two dogs on a sofa", "a blue car", "snow on a hill", "a green bench"]) + "\n")
+    out = str(tmp_path / "run")
+    os.makedirs(out)
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_loop_worker, args=(2, port, str(prompts), out), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(out, f"rank{r}.pt")) for r in range(2))
+    assert torch.equal(r0["flat"], r1["flat"])                                   # replicas stay identical: same averaged gradient
+    assert len(r0["seen"]) == len(r1["seen"]) == 2 and not set(r0["seen"]) & set(r1["seen"])
+    assert sorted(d for d in os.listdir(out) if d.startswith("checkpoint")) == ["checkpoint-2"]      # written once, by rank 0
+    logs = [json.loads(l) for l in open(os.path.join(out, "train_log.jsonl"))]
+    assert [l["step"] for l in logs] == [1, 2] and all(abs(l["step_loss"]) > 0 for l in logs)

@@ -1,0 +1,80 @@
+"""CPU: the training entry point (comat_b200/train.py - the loop of training_script.py:496-735): epochs / max_train_steps,
+checkpoint cadence, resume arithmetic (:287-288, :546-549), per-step jsonl logs, the lr schedule, and the data-parallel prompt
+sharding of SURVEY 8e.  CUDA ops emulated in torch (test infrastructure)."""
+import json
+import os
+
+import pytest
+import torch
+
+
+def test_sharded_batches_partition_the_epoch():
+    from comat_b200.data import PromptDataset, ShardedBatches
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "prompts.txt")
+        open(p, "w").write("\n".join("prompt %d" % i for i in range(23)) + "\n")
+        ds = PromptDataset(p)
+        assert len(ds) == 23 and ds[3] == {"text": "prompt 3"}
+        loaders = [ShardedBatches(ds, 2, r, 4, seed=5) for r in range(4)]
+        assert {len(l) for l in loaders} == {2}                                    # 23 // (2*4): same count on every rank
+        seen = [t for l in loaders for b in l for t in b["text"]]
+        assert len(seen) == 16 and len(set(seen)) == 16                            # disjoint across ranks within an epoch
+        e0 = [b["text"] for b in loaders[1]]
+        loaders[1].set_epoch(1)
+        assert [b["text"] for b in loaders[1]] != e0                               # reshuffled per epoch
+        loaders[1].set_epoch(0)
+        assert [b["text"] for b in loaders[1]] == e0                               # and reproducible
+        js = os.path.join(td, "prompts.json")
+        json.dump(["a", "b", "c"], open(js, "w"))
+        assert PromptDataset(js, max_train_samples=2)[1] == {"text": "b"}
+
+
+def test_lr_schedules():
+    from comat_b200 import synthetic
+    from comat_b200.train import lr_at
+    a = synthetic.default_args(lr_scheduler="constant", lr_warmup_steps=0, max_train_steps=10)
+    assert [lr_at(a, s) for s in (0, 5, 9)] == [1.0, 1.0, 1.0]
+    a = synthetic.default_args(lr_scheduler="constant_with_warmup", lr_warmup_steps=4, max_train_steps=10)
+    assert [lr_at(a, s) for s in (0, 2, 4, 9)] == [0.0, 0.5, 1.0, 1.0]
+    a = synthetic.default_args(lr_scheduler="linear", lr_warmup_steps=2, max_train_steps=10)
+    assert lr_at(a, 1) == 0.5 and lr_at(a, 2) == 1.0 and abs(lr_at(a, 6) - 0.5) < 1e-12 and lr_at(a, 10) == 0.0
+    a = synthetic.default_args(lr_scheduler="cosine", lr_warmup_steps=0, max_train_steps=10)
+    assert lr_at(a, 0) == 1.0 and abs(lr_at(a, 5) - 0.5) < 1e-12
+
+
+def test_training_loop_checkpoints_logs_and_resume(tmp_path, monkeypatch):
+    from tests.test_trainer_logic_cpu import _emulate_cuda_only
+    from tests import cpu_ops_emulation as EMU
+    _emulate_cuda_only(monkeypatch)
+    EMU.install_blip(monkeypatch)
+    from comat_b200 import checkpoint as CK, synthetic
+    from comat_b200.train import Trainer
+    prompts = tmp_path / "prompts.txt"
+    prompts.write_text("\n".join(["a red apple", "two dogs on a sofa", "a blue car", "snow on a hill", "a green bench"]) + "\n")
+    out = str(tmp_path / "run")
+
+    def mk(max_steps, resume):
+        a = synthetic.default_args(pretrain_model_name="sd_1_5_attrcon", train_batch_size=2, K=1, total_step=2, resolution=64,
+                                   training_prompts=str(prompts), output_dir=out, max_train_steps=max_steps, validation_steps=2,
+                                   resume_from_checkpoint=resume, seed=3, attrcon_train_steps=1, lr_scheduler="constant_with_warmup", gradient_accumulation_steps=1,
+                                   lr_warmup_steps=2)
+        # 8x8 latent: the only captured cross-attention place of the tiny UNet within reses (64, 32, 16, 8) is up_8
+        return Trainer(a, None, torch.device("cpu"), weights="synthetic_tiny", dtype=torch.float32, train_layer_ls=["up_8"])
+    tr = mk(3, None)
+    assert tr.steps_per_epoch == 2 and tr.args.num_train_epochs == 2
+    assert tr.train() == 3
+    assert sorted(d for d in os.listdir(out) if d.startswith("checkpoint")) == ["checkpoint-2", "checkpoint-3"]
+    logs = [json.loads(l) for l in open(os.path.join(out, "train_log.jsonl"))]
+    assert [l["step"] for l in logs] == [1, 2, 3] and all("step_loss" in l and "Blip" in l and "token_loss" in l and "pixel_loss" in l for l in logs)
+    assert [l["lr"] for l in logs] == [0.0, tr.args.learning_rate * 0.5, tr.args.learning_rate]
+    flat3 = tr.core.optimizer.flat.clone()
+    # resume: picks checkpoint-3, skips the first batch of epoch 1, runs exactly one more step
+    tr2 = mk(4, "latest")
+    assert tr2.global_step == 3 and tr2.first_epoch == 1 and tr2.resume_step == 1
+    assert torch.equal(tr2.core.optimizer.flat, flat3) and tr2.core.optimizer.step_count == 3
+    assert tr2.train() == 4 and tr2.core.optimizer.step_count == 4
+    assert CK.latest_checkpoint(out).endswith("checkpoint-4")
+    assert [json.loads(l)["step"] for l in open(os.path.join(out, "train_log.jsonl"))] == [1, 2, 3, 4]
+    with pytest.raises(NotImplementedError):
+        Trainer(synthetic.default_args(gradient_accumulation_steps=2, training_prompts=str(prompts)), {}, torch.device("cpu"))
