@@ -175,6 +175,32 @@ class Trainer:
         self._barrier()
         return path
 
+    @torch.no_grad()
+    def validate(self):
+        """the evaluate half of ``save_and_evaluate`` (training_script.py:456-489): ``num_validation_images`` samples per
+        validation prompt, one prompt per call, ``num_inference_steps = total_step``, one seeded generator for the whole sweep;
+        PNGs under ``<output_dir>/validation/step-<n>/test_<prompt>_<k>.png`` stand in for TensorBoard's ``test_<i>`` image rows."""
+        a = self.args
+        if self.rank != 0 or not a.validation_prompts or a.num_validation_images <= 0:
+            return []
+        prompts = list(a.validation_prompts)
+        if a.validation_prompts_file is not None:
+            with open(a.validation_prompts_file, "r") as f:
+                prompts += f.readlines()
+        prompts = [p.strip() for p in prompts]
+        gen = torch.Generator(device=self.device).manual_seed(a.seed) if a.seed else None
+        self.core.sync()
+        out_dir = os.path.join(a.output_dir, "validation", f"step-{self.global_step}")
+        os.makedirs(out_dir, exist_ok=True)
+        paths = []
+        for i, p in enumerate(prompts):
+            for k in range(a.num_validation_images):
+                img = self.pipeline([p], height=a.resolution, width=a.resolution, num_inference_steps=a.total_step, generator=gen,
+                                    guidance_scale=a.cfg_scale, guidance_rescale=a.cfg_rescale, output_type="pil").images[0]
+                paths.append(os.path.join(out_dir, f"test_{i}_{k}.png"))
+                img.save(paths[-1])
+        return paths
+
     def _flush_logs(self):
         """ONE device->host transfer for all scalars queued since the last flush."""
         if not self._pending:
@@ -230,6 +256,7 @@ class Trainer:
                 if self.global_step % a.validation_steps == 0:                        # :711-717 (saving half of save_and_evaluate)
                     self._flush_logs()
                     self.save()
+                    self.validate()
             if self.global_step >= a.max_train_steps:
                 break
         self.core.sync()

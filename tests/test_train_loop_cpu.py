@@ -58,7 +58,7 @@ def test_training_loop_checkpoints_logs_and_resume(tmp_path, monkeypatch):
         a = synthetic.default_args(pretrain_model_name="sd_1_5_attrcon", train_batch_size=2, K=1, total_step=2, resolution=64,
                                    training_prompts=str(prompts), output_dir=out, max_train_steps=max_steps, validation_steps=2,
                                    resume_from_checkpoint=resume, seed=3, attrcon_train_steps=1, lr_scheduler="constant_with_warmup", gradient_accumulation_steps=1,
-                                   lr_warmup_steps=2)
+                                   lr_warmup_steps=2, validation_prompts=["a cat on a mat", "two birds"], num_validation_images=2)
         # 8x8 latent: the only captured cross-attention place of the tiny UNet within reses (64, 32, 16, 8) is up_8
         return Trainer(a, None, torch.device("cpu"), weights="synthetic_tiny", dtype=torch.float32, train_layer_ls=["up_8"])
     tr = mk(3, None)
@@ -68,6 +68,10 @@ def test_training_loop_checkpoints_logs_and_resume(tmp_path, monkeypatch):
     logs = [json.loads(l) for l in open(os.path.join(out, "train_log.jsonl"))]
     assert [l["step"] for l in logs] == [1, 2, 3] and all("step_loss" in l and "Blip" in l and "token_loss" in l and "pixel_loss" in l for l in logs)
     assert [l["lr"] for l in logs] == [0.0, tr.args.learning_rate * 0.5, tr.args.learning_rate]
+    val = sorted(os.listdir(os.path.join(out, "validation", "step-2")))          # :456-489 at the validation_steps cadence
+    assert val == ["test_0_0.png", "test_0_1.png", "test_1_0.png", "test_1_1.png"]
+    from PIL import Image
+    assert Image.open(os.path.join(out, "validation", "step-2", val[0])).size == (64, 64)
     flat3 = tr.core.optimizer.flat.clone()
     # resume: picks checkpoint-3, skips the first batch of epoch 1, runs exactly one more step
     tr2 = mk(4, "latest")
