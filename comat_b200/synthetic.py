@@ -70,7 +70,7 @@ def build_blip(device, dtype=torch.float16, seed=0, large=True, label_smoothing=
     return m.to(device=device, dtype=dtype)
 
 
-def build_clip_text(device, dtype=torch.float16, seed=7, which="clip_l", tiny=False):
+def build_clip_text(device, dtype=torch.float16, seed=7, which="clip_l", tiny=False, **overrides):
     """Random-init HF CLIP text tower at the geometry the SD checkpoints ship: ``clip_l`` = CLIPTextModel 12 x 768,
     12 heads, quick-GELU (SD1.5 ``text_encoder`` / SDXL ``text_encoder``); ``bigg`` = CLIPTextModelWithProjection 32 x 1280,
     20 heads, GELU, projection 1280 (SDXL ``text_encoder_2``).  ``eos_token_id = 2`` is the legacy value those configs carry."""
@@ -87,6 +87,7 @@ def build_clip_text(device, dtype=torch.float16, seed=7, which="clip_l", tiny=Fa
         raise NotImplementedError(which)
     if tiny:
         kw.update(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, projection_dim=64)
+    kw.update(overrides)
     cfg = CLIPTextConfig(vocab_size=49408, max_position_embeddings=77, eos_token_id=2, bos_token_id=0, pad_token_id=1, **kw)
     torch.manual_seed(seed)
     with torch.device(device):

@@ -52,6 +52,7 @@ def lr_at(args, step: int) -> float:
 
 def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False) -> Dict:
     """random-init networks at the real (or tiny) geometry + stand-in tokenizers (no Hub access in this image)."""
+    from . import containers as Cn
     from .blip_engine import BlipEngine
     from .caption import Blip, CaptionModelWrapper
     from .gan import D_sd
@@ -59,31 +60,45 @@ def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False) 
     from . import pipelines as P
     from .text_encoder import EngineCLIPText
     name = args.pretrain_model_name
-    if "sdxl" in name:
-        raise NotImplementedError("the synthetic entry point builds SD1.5 pipelines; pass SDXL modules through components=")
+    sdxl = "sdxl" in name
     seed = args.seed if args.seed is not None else 42
     rank = 8 if tiny else args.lora_rank
 
-    def tiny_unet(sd):            # tiny geometry whose text-context width matches the tiny CLIP tower (128)
-        from . import containers as Cn
+    def tiny_unet(sd):            # tiny SD1.5 geometry whose text-context width matches the tiny CLIP tower (128)
         torch.manual_seed(sd)
         with torch.device(device):
             u = Cn.UNet2DConditionModel(block_out_channels=(64, 128, 256, 256), heads=4, cross_attention_dim=128)
         u.requires_grad_(False)
         u.install_lora(rank)
         return u
-    unet, vae = synthetic.build_sd15(device, dtype, rank=rank, seed=seed, tiny=tiny)
-    if tiny:
-        unet = tiny_unet(seed)
-    clip = synthetic.build_clip_text(device, torch.float32, seed=seed + 1, which="clip_l", tiny=tiny)
-    cls = P.AttrConcenTrainableSDPipeline if "attrcon" in name else P.TrainableSDPipeline
-    pipe = cls(EngineVAE(vae, dtype), EngineUNet(unet, dtype), text_encoder=EngineCLIPText(clip, dtype),
-               tokenizer=synthetic.SyntheticClipTokenizer())
+    torch.manual_seed(seed + 6)
+    with torch.device(device):
+        vae = Cn.AutoencoderKL(**(dict(block_out_channels=(64, 64, 128, 128)) if tiny else {}),
+                               scaling_factor=0.13025 if sdxl else 0.18215)          # sdxl-vae / sd-vae scaling factors
+    vae.requires_grad_(False)
+    if sdxl:
+        # SDXL: UNet 2.57 B, text context = CLIP-L penultimate (768) | OpenCLIP-bigG penultimate (1280), pooled = bigG projection
+        unet = synthetic.build_sdxl_unet(device, rank=rank, seed=seed, tiny=tiny)
+        small = dict(hidden_size=32, intermediate_size=64, projection_dim=16) if tiny else {}     # 32 + 32 = tiny context 64
+        clip = synthetic.build_clip_text(device, torch.float32, seed=seed + 1, which="clip_l", tiny=tiny, **small)
+        clip2 = synthetic.build_clip_text(device, torch.float32, seed=seed + 4, which="bigg", tiny=tiny, **small)
+        cls = P.AttrConcenTrainableSDXLPipeline if "attrcon" in name else P.TrainableSDXLPipeline
+        pipe = cls(EngineVAE(vae, dtype), EngineUNet(unet, dtype), text_encoder=EngineCLIPText(clip, dtype),
+                   tokenizer=synthetic.SyntheticClipTokenizer(), text_encoder_2=EngineCLIPText(clip2, dtype),
+                   tokenizer_2=synthetic.SyntheticClipTokenizer(pad_token_id=0))
+    else:
+        unet = tiny_unet(seed) if tiny else synthetic.build_sd15(device, dtype, rank=rank, seed=seed)[0]
+        clip = synthetic.build_clip_text(device, torch.float32, seed=seed + 1, which="clip_l", tiny=tiny)
+        cls = P.AttrConcenTrainableSDPipeline if "attrcon" in name else P.TrainableSDPipeline
+        pipe = cls(EngineVAE(vae, dtype), EngineUNet(unet, dtype), text_encoder=EngineCLIPText(clip, dtype),
+                   tokenizer=synthetic.SyntheticClipTokenizer())
     blip = Blip(BlipEngine(synthetic.build_blip(device, dtype, large=not tiny), dtype), tokenizer=synthetic.SyntheticBertTokenizer())
     comp = {"pipeline": pipe, "caption_model": CaptionModelWrapper(list(args.caption_model), list(args.reward_weights), blip), "D": None}
     if args.gan_loss:
+        # the discriminator is an SD1.5 UNet with its own CLIP-L for the '' embedding, also under SDXL (scripts/sdxl.sh:15)
         d_unet = tiny_unet(seed + 2) if tiny else synthetic.build_sd15(device, dtype, rank=rank, seed=seed + 2)[0]
-        d_pipe = P.TrainableSDPipeline(None, None, text_encoder=pipe.text_encoder, tokenizer=pipe.tokenizer)
+        d_clip = EngineCLIPText(synthetic.build_clip_text(device, torch.float32, seed=seed + 5, which="clip_l", tiny=tiny), dtype) if sdxl else pipe.text_encoder
+        d_pipe = P.TrainableSDPipeline(None, None, text_encoder=d_clip, tokenizer=synthetic.SyntheticClipTokenizer())
         comp["D"] = D_sd(EngineUNet(d_unet, dtype), pipeline=d_pipe)
     if "attrcon" in name:
         g = torch.Generator().manual_seed(seed + 3)

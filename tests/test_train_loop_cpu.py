@@ -82,3 +82,34 @@ def test_training_loop_checkpoints_logs_and_resume(tmp_path, monkeypatch):
     assert [json.loads(l)["step"] for l in open(os.path.join(out, "train_log.jsonl"))] == [1, 2, 3, 4]
     with pytest.raises(NotImplementedError):
         Trainer(synthetic.default_args(gradient_accumulation_steps=2, training_prompts=str(prompts)), {}, torch.device("cpu"))
+
+
+def test_sdxl_entry_trains_from_prompt_strings(tmp_path, monkeypatch):
+    """configs[3] shape of the entry point at tiny geometry: SDXL UNet with pooled-text / time-id conditioning fed by BOTH text
+    encoders from prompt strings, SD1.5 discriminator with its own CLIP-L null embedding (scripts/sdxl.sh:15), attrcon losses."""
+    from tests.test_trainer_logic_cpu import _emulate_cuda_only
+    from tests import cpu_ops_emulation as EMU
+    _emulate_cuda_only(monkeypatch)
+    EMU.install_blip(monkeypatch)
+    from comat_b200 import gan_data as GD, synthetic
+    from comat_b200.train import Trainer
+    # GAN data on disk in the reference's format (gan_dataset.py): jsonl index + latents/*.pt
+    idx = tmp_path / "train_data" / "gan_train_data.jsonl"
+    os.makedirs(tmp_path / "train_data" / "latents")
+    g = torch.Generator().manual_seed(1)
+    with open(idx, "w") as f:
+        for i, p in enumerate(["a red apple", "two dogs on a sofa", "a blue car"]):
+            path = str(tmp_path / "train_data" / "latents" / f"{GD.short_uid()}.pt")
+            torch.save(torch.randn(4, 16, 16, generator=g), path)
+            f.write(json.dumps({"prompt": p, "file_path": path}) + "\n")
+    a = synthetic.default_args(pretrain_model_name="sdxl_attrcon", train_batch_size=1, K=1, total_step=2, resolution=128, gan_loss=True,   # 16x16 latent: up_8 captured
+                               gan_model_arch="gansd_1_5", training_prompts=str(idx), output_dir=str(tmp_path / "run"), max_train_steps=2,
+                               validation_steps=100, resume_from_checkpoint=None, seed=5, attrcon_train_steps=1, gradient_accumulation_steps=1)
+    tr = Trainer(a, None, torch.device("cpu"), weights="synthetic_tiny", dtype=torch.float32, train_layer_ls=["up_8"])
+    assert tr.pipeline.is_sdxl and tr.D is not None and len(tr.dataset) == 3
+    assert tr.train() == 2
+    assert tr.core.null_embed.shape == (1, 77, 64) and tr.core.pooled_null_embed.shape == (1, 16)        # 32 | 32 context, 16 pooled
+    assert tr.core.gan_null_embed.shape == (1, 77, 128) and tr.D.D_sd_pipeline.text_encoder is None       # D's own CLIP-L, released
+    logs = [json.loads(l) for l in open(os.path.join(a.output_dir, "train_log.jsonl"))]
+    assert len(logs) == 2 and all(k in logs[0] for k in ("Blip", "G_loss", "D_loss", "step_loss"))
+    assert sorted(os.listdir(os.path.join(a.output_dir, "checkpoint-2"))) == ["D_sd", "pytorch_lora_weights.safetensors", "trainer_state.pt"]
