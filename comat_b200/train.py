@@ -127,8 +127,7 @@ class Trainer:
                  weights: str = "synthetic", log_every: int = 1, dtype=torch.float16, train_layer_ls=None):
         from .pipelines import AttentionStore, register_attention_control
         from .trainer import CoMatTrainer
-        if args.gradient_accumulation_steps != 1:
-            raise NotImplementedError("gradient_accumulation_steps > 1 (the CoMat scripts use 1: scripts/sd15.sh, scripts/sdxl.sh)")
+        self.accum = max(1, int(args.gradient_accumulation_steps))
         if args.full_finetuning or args.tune_vae:
             raise NotImplementedError("--full_finetuning / --tune_vae: this path trains the LoRA factors only")
         self.args, self.rank, self.world, self.log_every = args, rank, world, max(1, log_every)
@@ -151,7 +150,7 @@ class Trainer:
                                  process_group=process_group)
         self.dataset = get_dataset(args)
         self.loader = ShardedBatches(self.dataset, args.train_batch_size, rank, world, seed=args.seed or 0)
-        self.steps_per_epoch = max(1, len(self.loader))                               # :282
+        self.steps_per_epoch = max(1, math.ceil(len(self.loader) / self.accum))       # :282 optimiser steps per epoch
         if args.max_train_steps is None:
             args.max_train_steps = args.num_train_epochs * self.steps_per_epoch
         args.num_train_epochs = math.ceil(args.max_train_steps / self.steps_per_epoch)   # :326
@@ -166,9 +165,10 @@ class Trainer:
             else:
                 self._print(f"Resuming from checkpoint-{step}")
                 self.global_step = step
-        self.first_epoch = self.global_step // self.steps_per_epoch                   # :287-288
-        self.resume_step = self.global_step % self.steps_per_epoch
+        self.first_epoch = self.global_step // self.steps_per_epoch                   # :287-288 (resume_step counts micro-batches)
+        self.resume_step = (self.global_step * self.accum) % (self.steps_per_epoch * self.accum)
         self._pending = []
+        self._micro = 0
         self._log_file = None
         if rank == 0:
             os.makedirs(args.output_dir, exist_ok=True)
@@ -263,12 +263,18 @@ class Trainer:
                     probe = torch.empty(0, 3, a.resolution, a.resolution, device=self.device)
                     batch["words"], batch["masks"] = self.attr_provider(batch["text"], probe)
                 self.core.optimizer.lr = a.learning_rate * lr_at(a, self.global_step)  # :663 lr_scheduler.step()
-                logs = self.core.train_step(batch)
+                # accelerator.accumulate (:556): gradients sync every accum-th batch and at the end of the dataloader
+                first = self._micro == 0
+                last = self._micro == self.accum - 1 or step == len(self.loader) - 1
+                logs = self.core.train_step(batch, accum_steps=self.accum, first=first, last=last)
+                self._micro = 0 if last else self._micro + 1
+                if not last:
+                    continue
                 self.global_step += 1
                 self._pending.append((self.global_step, {k: v.detach() for k, v in logs.items() if torch.is_tensor(v) and v.numel() == 1}))
                 if self.global_step % self.log_every == 0:
                     self._flush_logs()
-                if self.global_step % a.validation_steps == 0:                        # :711-717 (saving half of save_and_evaluate)
+                if self.global_step % a.validation_steps == 0:                        # :711-717
                     self._flush_logs()
                     self.save()
                     self.validate()

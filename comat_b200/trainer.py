@@ -205,25 +205,33 @@ class CoMatTrainer:
         if self.manual_gc_interval > 0 and self.global_step % self.manual_gc_interval == 0:
             gc.collect()
 
-    def train_step(self, batch: Dict) -> Dict[str, torch.Tensor]:
+    def train_step(self, batch: Dict, accum_steps: int = 1, first: bool = True, last: bool = True) -> Dict[str, torch.Tensor]:
+        """one micro-batch.  ``accum_steps`` > 1 = ``accelerator.accumulate`` (training_script.py:556, :679): the gradients of
+        consecutive calls add up from the one flagged ``first`` (buffers zeroed) to the one flagged ``last`` (optimisers step),
+        each loss scaled by 1/accum_steps as ``accelerator.backward`` does."""
         a = self.args
         self._gc_before_step()
         self._join("_ev_G")                                                          # the generator's previous update is in
         logs = self.g_losses(batch)
         loss = logs["loss"]
-        self.optimizer.zero_grad()                                                   # :658
-        loss.backward()                                                              # :659
-        self._run_update(self._g_update, "_ev_G")                                    # :661-664, beside the discriminator step
+        if first:
+            self.optimizer.zero_grad()                                               # :658
+        (loss if accum_steps == 1 else loss / accum_steps).backward()                # :659
+        if last:
+            self._run_update(self._g_update, "_ev_G")                                # :661-664, beside the discriminator step
         out = {k: v for k, v in logs.items() if not k.startswith("_")}
         out["step_loss"] = loss.detach()
         out.update(logs.get("_norm_holder", {}))
         if a.gan_loss:                                                               # :679-694
             d_loss = self.D.D_sd_pipeline_forward(logs["_latents"].detach(), side="D", negative_prompt_embeds=self._null(batch, "gan_null_embeds", "gan_null_embed"),
                                                   num_inference_steps=a.total_step, batch={"latents": batch["real_latents"]})
-            self.D_optimizer.zero_grad()
-            d_loss.backward()
-            self._run_update(self._d_update, "_ev_D")                                # :689-694, beside the next step's rollout
+            if first:
+                self.D_optimizer.zero_grad()
+            (d_loss if accum_steps == 1 else d_loss / accum_steps).backward()
+            if last:
+                self._run_update(self._d_update, "_ev_D")                            # :689-694, beside the next step's rollout
             out["D_loss"] = d_loss.detach()
-        self.global_step += 1
-        self._gc_after_step()
+        if last:
+            self.global_step += 1
+            self._gc_after_step()
         return out

@@ -81,7 +81,7 @@ def test_training_loop_checkpoints_logs_and_resume(tmp_path, monkeypatch):
     assert CK.latest_checkpoint(out).endswith("checkpoint-4")
     assert [json.loads(l)["step"] for l in open(os.path.join(out, "train_log.jsonl"))] == [1, 2, 3, 4]
     with pytest.raises(NotImplementedError):
-        Trainer(synthetic.default_args(gradient_accumulation_steps=2, training_prompts=str(prompts)), {}, torch.device("cpu"))
+        Trainer(synthetic.default_args(full_finetuning=True, training_prompts=str(prompts)), {}, torch.device("cpu"))
 
 
 def test_sdxl_entry_trains_from_prompt_strings(tmp_path, monkeypatch):
@@ -113,3 +113,50 @@ def test_sdxl_entry_trains_from_prompt_strings(tmp_path, monkeypatch):
     logs = [json.loads(l) for l in open(os.path.join(a.output_dir, "train_log.jsonl"))]
     assert len(logs) == 2 and all(k in logs[0] for k in ("Blip", "G_loss", "D_loss", "step_loss"))
     assert sorted(os.listdir(os.path.join(a.output_dir, "checkpoint-2"))) == ["D_sd", "pytorch_lora_weights.safetensors", "trainer_state.pt"]
+
+
+def test_gradient_accumulation_sums_scaled_micro_batch_gradients(tmp_path, monkeypatch):
+    """accelerator.accumulate semantics (training_script.py:556,658-664): two micro-batches with accumulation 2 leave
+    (g1 + g2) / 2 in the flat gradient buffer and take ONE optimiser step; the loop counts optimiser steps."""
+    from tests.test_trainer_logic_cpu import _emulate_cuda_only
+    from tests import cpu_ops_emulation as EMU
+    _emulate_cuda_only(monkeypatch)
+    EMU.install_blip(monkeypatch)
+    from comat_b200 import synthetic
+    from comat_b200.train import Trainer
+    prompts = tmp_path / "prompts.txt"
+    prompts.write_text("\n".join(["a red apple", "two dogs on a sofa", "a blue car", "snow on a hill", "a green bench"]) + "\n")
+
+    def mk(accum, out):
+        a = synthetic.default_args(pretrain_model_name="sd_1_5", train_batch_size=1, K=1, total_step=2, resolution=64,
+                                   training_prompts=str(prompts), output_dir=str(tmp_path / out), max_train_steps=2, validation_steps=100,
+                                   resume_from_checkpoint=None, seed=3, gradient_accumulation_steps=accum)
+        return Trainer(a, None, torch.device("cpu"), weights="synthetic_tiny", dtype=torch.float32)
+    tr = mk(2, "acc")
+    assert tr.steps_per_epoch == 3                     # ceil(5 / 2): the dataloader's tail batch syncs on its own
+    g = torch.Generator().manual_seed(1)
+    mkb = lambda t: dict(text=[t], init_latents=torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(len(t))),
+                         noises=[torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(7 + i)) for i in range(2)],
+                         training_steps=[1], attrcon_steps=None, crop=(0, 0))
+    b1, b2 = mkb("a red apple"), mkb("two dogs on a sofa")
+    core = tr.core
+    core.overlap_updates = False
+    singles = []
+    for b in (b1, b2):
+        core.optimizer.zero_grad()
+        core.g_losses(b)["loss"].backward()
+        core.pipeline.unet.finalize_lora_grads()
+        singles.append(core.optimizer.grad.clone())
+    steps = []
+    monkeypatch.setattr(type(core), "_g_update", lambda self: (self.pipeline.unet.finalize_lora_grads(), steps.append(self.optimizer.grad.clone())))
+    core.train_step(b1, accum_steps=2, first=True, last=False)
+    assert steps == [] and core.global_step == 0
+    core.train_step(b2, accum_steps=2, first=False, last=True)
+    assert len(steps) == 1 and core.global_step == 1
+    want = 0.5 * (singles[0] + singles[1])
+    assert float((steps[0] - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    monkeypatch.undo()
+    _emulate_cuda_only(monkeypatch)
+    EMU.install_blip(monkeypatch)
+    tr2 = mk(2, "acc2")
+    assert tr2.train() == 2 and tr2.core.optimizer.step_count == 2
