@@ -258,3 +258,90 @@ ENCODE_PROMPT_CASES = [
     dict(prompts=["a blue car and a green bench", "a cat", "snow"], n_per=1, cfg=False, negative=None, clip_skip=1, seed=9),
     dict(prompts=[" ".join(["word%d" % i for i in range(90)])], n_per=1, cfg=True, negative=None, clip_skip=None, seed=10),   # truncated at 77
 ]
+
+
+# ---- prompt parsing / CLIP alignment: spaCy and the CLIP vocabulary are not in this image -> hand-written parses
+class FakeToken:
+    """spaCy ``Token`` protocol subset the reference reads: ``.text .pos_ .dep_ .head .children`` (children in sentence order)."""
+
+    def __init__(self, i, text, pos, dep):
+        self.i, self.text, self.pos_, self.dep_ = i, text, pos, dep
+        self.head, self.children = self, []
+
+    def __repr__(self):
+        return f"{self.text}/{self.pos_}/{self.dep_}"
+
+
+def fake_doc(spec):
+    """spec: [(text, pos, dep, head_index), ...] (head_index == own index for the root) -> list of FakeToken."""
+    toks = [FakeToken(i, t, p, d) for i, (t, p, d, _) in enumerate(spec)]
+    for tok, (_, _, _, h) in zip(toks, spec):
+        tok.head = toks[h]
+        if h != tok.i:
+            toks[h].children.append(tok)
+    return toks
+
+
+class BpeStub:
+    """``tokenizer(prompt).input_ids`` + ``convert_ids_to_tokens`` with CLIP's conventions: BOS / EOS strings, ``</w>`` on the last
+    piece of a word, configurable multi-piece words."""
+
+    def __init__(self, splits=None):
+        self.splits = splits or {}
+        self.vocab = ["<|startoftext|>", "<|endoftext|>"]
+
+    def _id(self, piece):
+        if piece not in self.vocab:
+            self.vocab.append(piece)
+        return self.vocab.index(piece)
+
+    def __call__(self, prompt, **_):
+        from types import SimpleNamespace
+        ids = [0]
+        for w in prompt.lower().split():
+            pieces = self.splits.get(w, [w])
+            ids += [self._id(p + ("</w>" if j == len(pieces) - 1 else "")) for j, p in enumerate(pieces)]
+        return SimpleNamespace(input_ids=ids + [1])
+
+    def convert_ids_to_tokens(self, ids):
+        return [self.vocab[i] for i in ids]
+
+
+ATTR_ALIGN_CASES = {
+    "a red apple and a blue car": [
+        ("a", "DET", "det", 2), ("red", "ADJ", "amod", 2), ("apple", "NOUN", "ROOT", 2), ("and", "CCONJ", "cc", 2),
+        ("a", "DET", "det", 6), ("blue", "ADJ", "amod", 6), ("car", "NOUN", "conj", 2)],
+    "a dog that is red": [
+        ("a", "DET", "det", 1), ("dog", "NOUN", "ROOT", 1), ("that", "PRON", "nsubj", 3), ("is", "AUX", "relcl", 1),
+        ("red", "ADJ", "acomp", 3)],
+    "the strawberry cake is pink and fluffy": [
+        ("the", "DET", "det", 2), ("strawberry", "NOUN", "compound", 2), ("cake", "NOUN", "nsubj", 3), ("is", "AUX", "ROOT", 3),
+        ("pink", "ADJ", "acomp", 3), ("and", "CCONJ", "cc", 4), ("fluffy", "ADJ", "conj", 4)],
+    "a red red red bear": [
+        ("a", "DET", "det", 4), ("red", "ADJ", "amod", 4), ("red", "ADJ", "amod", 4), ("red", "ADJ", "amod", 4),
+        ("bear", "NOUN", "ROOT", 4)],
+    "two cats and two dogs": [
+        ("two", "NUM", "nummod", 1), ("cats", "NOUN", "ROOT", 1), ("and", "CCONJ", "cc", 1), ("two", "NUM", "nummod", 4),
+        ("dogs", "NOUN", "conj", 1)],
+    "a big old red wooden table": [
+        ("a", "DET", "det", 5), ("big", "ADJ", "amod", 5), ("old", "ADJ", "amod", 5), ("red", "ADJ", "amod", 5),
+        ("wooden", "ADJ", "amod", 5), ("table", "NOUN", "ROOT", 5)],
+    "a red bear and a red car near a skateboard": [
+        ("a", "DET", "det", 2), ("red", "ADJ", "amod", 2), ("bear", "NOUN", "ROOT", 2), ("and", "CCONJ", "cc", 2),
+        ("a", "DET", "det", 6), ("red", "ADJ", "amod", 6), ("car", "NOUN", "conj", 2), ("near", "ADP", "prep", 6),
+        ("a", "DET", "det", 9), ("skateboard", "NOUN", "pobj", 7)],
+    "a dark blue metal bench that looks very old": [
+        ("a", "DET", "det", 4), ("dark", "ADJ", "amod", 2), ("blue", "ADJ", "amod", 4), ("metal", "NOUN", "compound", 4),
+        ("bench", "NOUN", "ROOT", 4), ("that", "PRON", "nsubj", 6), ("looks", "VERB", "relcl", 4), ("very", "ADV", "advmod", 8),
+        ("old", "ADJ", "acomp", 6)],
+    "a strawberry cake on a skateboard": [
+        ("a", "DET", "det", 2), ("strawberry", "NOUN", "compound", 2), ("cake", "NOUN", "ROOT", 2), ("on", "ADP", "prep", 2),
+        ("a", "DET", "det", 5), ("skateboard", "NOUN", "pobj", 3)],
+    "the wooden skateboard is fluffy": [
+        ("the", "DET", "det", 2), ("wooden", "ADJ", "amod", 2), ("skateboard", "NOUN", "nsubj", 3), ("is", "AUX", "ROOT", 3),
+        ("fluffy", "ADJ", "acomp", 3)],
+    "a fluffy cat and a fluffy dog": [
+        ("a", "DET", "det", 2), ("fluffy", "ADJ", "amod", 2), ("cat", "NOUN", "ROOT", 2), ("and", "CCONJ", "cc", 2),
+        ("a", "DET", "det", 6), ("fluffy", "ADJ", "amod", 6), ("dog", "NOUN", "conj", 2)],
+}
+ATTR_ALIGN_SPLITS = {"strawberry": ["straw", "berry"], "skateboard": ["skate", "board"], "fluffy": ["flu", "ffy"]}

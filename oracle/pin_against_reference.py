@@ -291,9 +291,38 @@ def pin_lora_state_dict():
     return None
 
 
+def pin_attr_align():
+    """Reference ``attribute_concen_utils`` (imported as is) and ``AttrConcenTrainableSDPipeline._extract_attribution_indices`` /
+    ``_align_indices`` / ``unify_lists`` (verbatim through the shim) over hand-written dependency parses and a CLIP-convention
+    word-piece stub -> tests/golden/attr_align.json (token texts per extractor, aligned CLIP positions, index -> word piece)."""
+    import json
+    ref_shim.install()
+    acu = ref_shim.import_reference("attribute_concen_utils")
+    pl = ref_shim.import_reference("AttrConcenTrainableSDPipeline")
+    out = {}
+    for prompt, spec in FX.ATTR_ALIGN_CASES.items():
+        doc = FX.fake_doc(spec)
+        tok = FX.BpeStub(FX.ATTR_ALIGN_SPLITS)
+        pipe = pl.AttrConcenTrainableSDPipeline.__new__(pl.AttrConcenTrainableSDPipeline)
+        pipe.tokenizer, pipe.doc = tok, {prompt: doc}
+        names = lambda groups: None if groups is None else [[t.i for t in g] for g in groups]
+        out[prompt] = {
+            "plain": names(acu.extract_attribution_indices(doc)),
+            "with_verbs": names(acu.extract_attribution_indices_with_verbs(doc)),
+            "verb_root": names(acu.extract_attribution_indices_with_verb_root(doc)),
+            "aligned": pipe._extract_attribution_indices(prompt),
+            "idx_to_wp": {str(k): v for k, v in acu.get_attention_map_index_to_wordpiece(tok, prompt).items()},
+        }
+    with open(os.path.join(GOLDEN_DIR, "attr_align.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    for k, v in out.items():
+        print(k, "->", v["aligned"])
+    return None
+
+
 PINS = [("layer_loss", pin_layer_loss), ("mask_loss", pin_mask_loss), ("blip_score", pin_blip_score),
         ("gan", pin_gan), ("pipeline", pin_attention_store_and_pipeline), ("encode_prompt", pin_encode_prompt),
-        ("lora_state_dict", pin_lora_state_dict)]
+        ("lora_state_dict", pin_lora_state_dict), ("attr_align", pin_attr_align)]
 
 
 def main():
