@@ -8,8 +8,8 @@ takes the reference's 72 flags unchanged (``comat_b200.arguments``) plus ``--wei
 no Hub access, diffusers or tokenizer vocabularies, so the entry point builds random-init networks at the real geometry and the
 stand-in tokenizers of ``comat_b200.synthetic``; a deployment passes real modules through ``Trainer(args, components=...)``
 (see INTEGRATION.md).  What the reference obtains from Grounded-SAM + spaCy per batch (noun / attribute token lists, masks:
-training_script.py:627-637) comes from ``components['attr_provider'](prompts, images) -> (words, masks)``; the synthetic entry
-uses the SURVEY 8d generator.  Logs go to ``<output_dir>/train_log.jsonl`` (one JSON object per optimiser step) instead of
+training_script.py:627-637) comes from ``components['attr_provider'](prompts, images) -> (words, masks)``, called by the step on
+the image it has just generated; the synthetic entry uses the SURVEY 8d generator.  Logs go to ``<output_dir>/train_log.jsonl`` (one JSON object per optimiser step) instead of
 TensorBoard; scalars are read back once per ``--log_every`` steps, not 7 ``.item()`` syncs per step.
 """
 from __future__ import annotations
@@ -147,7 +147,7 @@ class Trainer:
                 raise NotImplementedError("attrcon models need components['attr_provider'] (Grounded-SAM + spaCy are external)")
         self.pipeline.unet.use_graphs = True
         self.core = CoMatTrainer(args, self.pipeline, self.caption_model, self.D, rng=random.Random((args.seed or 0) + rank),
-                                 process_group=process_group)
+                                 process_group=process_group, attr_provider=self.attr_provider)
         self.dataset = get_dataset(args)
         self.loader = ShardedBatches(self.dataset, args.train_batch_size, rank, world, seed=args.seed or 0)
         self.steps_per_epoch = max(1, math.ceil(len(self.loader) / self.accum))       # :282 optimiser steps per epoch
@@ -257,11 +257,6 @@ class Trainer:
                 if self.global_step >= a.max_train_steps:
                     break
                 batch = self._make_batch(raw)
-                if self.attr_provider is not None:
-                    # the reference segments the generated image inside the step (:627-637); the provider sees the prompts and
-                    # the image size - masks for the synthetic provider do not depend on the pixels
-                    probe = torch.empty(0, 3, a.resolution, a.resolution, device=self.device)
-                    batch["words"], batch["masks"] = self.attr_provider(batch["text"], probe)
                 self.core.optimizer.lr = a.learning_rate * lr_at(a, self.global_step)  # :663 lr_scheduler.step()
                 # accelerator.accumulate (:556): gradients sync every accum-th batch and at the end of the dataloader
                 first = self._micro == 0

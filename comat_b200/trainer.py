@@ -19,7 +19,7 @@ from .optim import FlatAdamW
 
 class CoMatTrainer:
     def __init__(self, args, pipeline, caption_model, D=None, rng: Optional[random.Random] = None, process_group=None,
-                 manual_gc_interval: int = 25):
+                 manual_gc_interval: int = 25, attr_provider=None):
         """``manual_gc_interval`` > 0: the trainer takes over Python's cyclic GC - automatic collection is switched off while it
         steps and a full collection runs every that many steps, right after a step has been enqueued (so it overlaps the GPU's
         backlog).  A step builds ~10^5 short-lived Python objects (tape nodes, ctypes structs); the automatic generation-2
@@ -28,6 +28,9 @@ class CoMatTrainer:
         explicitly), so device memory does not depend on the collector.  0 leaves the interpreter's GC settings alone."""
         self.manual_gc_interval = int(manual_gc_interval)
         self.args, self.pipeline, self.caption_model, self.D = args, pipeline, caption_model, D
+        # ``attr_provider(prompts, images in [0,1]) -> (words, masks)``: the Grounded-SAM + spaCy seam (training_script.py:627-637
+        # segments the image generated IN this step); used when the batch does not carry ``words`` / ``masks`` itself
+        self.attr_provider = attr_provider
         if getattr(args, "tune_text_encoder", False) or getattr(args, "train_text_encoder_lora", False):
             # training_script.py:227-255,569-573: needs d(encoder_hidden_states) out of the UNet executor - not built (SURVEY 8f-1)
             raise NotImplementedError("--tune_text_encoder / --train_text_encoder_lora: the text encoders are frozen on this path")
@@ -178,7 +181,13 @@ class CoMatTrainer:
             loss = loss + a.gan_loss_weight * g                                      # :620-625
             logs["G_loss"] = g.detach()
         if self.attrcon and pipe.attn_dict:
-            tok, pix = attn_loss.get_mask_loss(pipe.attn_dict, batch["words"], batch["masks"], self.train_layer_ls)
+            words, masks = batch.get("words"), batch.get("masks")
+            if words is None or masks is None:
+                if self.attr_provider is None:
+                    raise KeyError("attrcon step without batch['words'] / batch['masks'] and without an attr_provider")
+                with torch.no_grad():
+                    words, masks = self.attr_provider(batch["text"], image.detach().clamp(0, 1))          # :631-632
+            tok, pix = attn_loss.get_mask_loss(pipe.attn_dict, words, masks, self.train_layer_ls)
             loss = loss + a.mask_token_loss_weight * tok + a.mask_pixel_loss_weight * pix     # :639-640
             logs["token_loss"], logs["pixel_loss"] = tok.detach(), pix.detach()
             pipe.attn_dict = {}                                                      # :642
