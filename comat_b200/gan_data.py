@@ -143,3 +143,43 @@ def collate_gan_batch(examples: Iterable[Dict]) -> Dict:
     examples = list(examples)
     lat = torch.stack([e["latents"].float() for e in examples])
     return {"text": [e["text"] for e in examples], "latents": lat, "real_latents": lat}
+
+
+def main(argv=None) -> int:
+    """CLI of tools/gan_gt_generate.py (:45-55): same flags; ``--weights`` picks the random-init stand-ins (this image has no Hub
+    access - a deployment builds ``pipeline`` from real modules and calls ``generate_gan_ground_truth`` directly)."""
+    import argparse
+    p = argparse.ArgumentParser(description="GAN ground-truth latents (50-step cfg-7.5 sampling) -> latents/<uid>.pt + jsonl")
+    p.add_argument("--start", type=int, default=0)
+    p.add_argument("--end", type=int, default=10000)
+    p.add_argument("--unet-path", type=str)
+    p.add_argument("--use-cache", action="store_true")
+    p.add_argument("--prompt-path", type=str, default="merged_data/abc5k_hrs10k_t2icompall_20k.txt")
+    p.add_argument("--save-prompt-path", type=str, default="train_data/gan_train_data.jsonl")
+    p.add_argument("--model-path", type=str, default="runwayml/stable-diffusion-v1-5")
+    p.add_argument("--model-type", type=str, default="sd_1_5", choices=["sd_1_5", "sdxl", "sdxl_unet"])
+    p.add_argument("--batch-size", type=int, default=8)
+    p.add_argument("--weights", choices=["synthetic", "synthetic_tiny"], default="synthetic")
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--resolution", type=int, default=512)
+    a = p.parse_args(argv)
+    if not torch.cuda.is_available():
+        raise SystemExit("comat_b200.gan_data needs a GPU: the package has no CPU fallback")
+    import time
+    from . import synthetic
+    from .train import synthetic_components
+    name = {"sd_1_5": "sd_1_5", "sdxl": "sdxl", "sdxl_unet": "sdxl"}[a.model_type]
+    args = synthetic.default_args(pretrain_model_name=name, gan_loss=False, seed=42)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pipe = synthetic_components(args, dev, tiny=(a.weights == "synthetic_tiny"), with_caption=False)["pipeline"]
+    gen = torch.Generator(device=dev).manual_seed(int(time.time()))                  # :166 (time-seeded in the reference too)
+    n = generate_gan_ground_truth(pipe, read_prompts(a.prompt_path, a.start, a.end), a.save_prompt_path, batch_size=a.batch_size,
+                                  num_inference_steps=a.steps, guidance_scale=7.5, height=a.resolution, width=a.resolution,
+                                  generator=gen, use_cache=a.use_cache)
+    print(f"wrote {n} latents, index {a.save_prompt_path}")
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

@@ -50,7 +50,7 @@ def lr_at(args, step: int) -> float:
     raise NotImplementedError(f"lr_scheduler {name!r}")
 
 
-def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False) -> Dict:
+def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False, with_caption: bool = True) -> Dict:
     """random-init networks at the real (or tiny) geometry + stand-in tokenizers (no Hub access in this image)."""
     from . import containers as Cn
     from .blip_engine import BlipEngine
@@ -92,8 +92,10 @@ def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False) 
         cls = P.AttrConcenTrainableSDPipeline if "attrcon" in name else P.TrainableSDPipeline
         pipe = cls(EngineVAE(vae, dtype), EngineUNet(unet, dtype), text_encoder=EngineCLIPText(clip, dtype),
                    tokenizer=synthetic.SyntheticClipTokenizer())
-    blip = Blip(BlipEngine(synthetic.build_blip(device, dtype, large=not tiny), dtype), tokenizer=synthetic.SyntheticBertTokenizer())
-    comp = {"pipeline": pipe, "caption_model": CaptionModelWrapper(list(args.caption_model), list(args.reward_weights), blip), "D": None}
+    comp = {"pipeline": pipe, "caption_model": None, "D": None}
+    if with_caption:
+        blip = Blip(BlipEngine(synthetic.build_blip(device, dtype, large=not tiny), dtype), tokenizer=synthetic.SyntheticBertTokenizer())
+        comp["caption_model"] = CaptionModelWrapper(list(args.caption_model), list(args.reward_weights), blip)
     if args.gan_loss:
         # the discriminator is an SD1.5 UNet with its own CLIP-L for the '' embedding, also under SDXL (scripts/sdxl.sh:15)
         d_unet = tiny_unet(seed + 2) if tiny else synthetic.build_sd15(device, dtype, rank=rank, seed=seed + 2)[0]
