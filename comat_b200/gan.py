@@ -77,6 +77,12 @@ class D_sd(torch.nn.Module):
 def load_discriminator(args, unet: EngineUNet):
     """gan_sd_model.py:8-14 keeps the reference quirk: the arch string has 'gan' stripped and only 'sd_1_5' resolves
     (the default 'gan_sd_1_5' -> '_sd_1_5' resolves to nothing -> None)."""
+    if getattr(args, "gan_unet_lastlayer_cls", False):
+        # gan_sdxl.py:27-30 swaps the D UNet's conv_out for a 1-channel classifier conv; only the Linear(4,1) head (:31-34,
+        # what both shipped scripts train) is built here - refuse rather than silently train a different discriminator
+        raise NotImplementedError("--gan_unet_lastlayer_cls: the conv_out classification head is not implemented")
+    if getattr(args, "condition_discriminator", False):
+        raise NotImplementedError("--condition_discriminator crashes in the reference (gan_sdxl.py:60, self.pipeline undefined)")
     name = args.gan_model_arch.replace("gan", "")
     if name == "sd_1_5":
         return D_sd(unet)

@@ -55,7 +55,7 @@ def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False, 
     from . import containers as Cn
     from .blip_engine import BlipEngine
     from .caption import Blip, CaptionModelWrapper
-    from .gan import D_sd
+    from .gan import load_discriminator
     from .modules import EngineUNet, EngineVAE
     from . import pipelines as P
     from .text_encoder import EngineCLIPText
@@ -101,7 +101,12 @@ def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False, 
         d_unet = tiny_unet(seed + 2) if tiny else synthetic.build_sd15(device, dtype, rank=rank, seed=seed + 2)[0]
         d_clip = EngineCLIPText(synthetic.build_clip_text(device, torch.float32, seed=seed + 5, which="clip_l", tiny=tiny), dtype) if sdxl else pipe.text_encoder
         d_pipe = P.TrainableSDPipeline(None, None, text_encoder=d_clip, tokenizer=synthetic.SyntheticClipTokenizer())
-        comp["D"] = D_sd(EngineUNet(d_unet, dtype), pipeline=d_pipe)
+        D = load_discriminator(args, EngineUNet(d_unet, dtype))
+        if D is None:
+            raise NotImplementedError(f"--gan_model_arch {args.gan_model_arch!r} resolves to no discriminator (gan_sd_model.py:8-14 "
+                                      "strips 'gan' and knows 'sd_1_5' only; the shipped scripts pass gansd_1_5)")
+        D.D_sd_pipeline = d_pipe
+        comp["D"] = D
     if "attrcon" in name:
         g = torch.Generator().manual_seed(seed + 3)
         rr = random.Random(seed + 3)
