@@ -440,7 +440,8 @@ def main():
                            "library_calls_per_step": lib_calls / a.steps,
                            "library_note": ("0 = every conv / linear / attention (fwd+bwd) / norm / loss / resize / optimiser launch of the step "
                                             "is a comat_b200 kernel; torch supplies memory, the fp32 latent-chain glue, "
-                                            "embedding gathers and layout permutes") if lib_calls == 0 else
+                                            "embedding gathers, layout permutes and the discriminator's per-pixel Linear(4,1) + BCE head "
+                                            "(2 x B x 64 x 64 logits, fp32 as in gan_sdxl.py:32-34)") if lib_calls == 0 else
                                            "calls that fell back to aten/HF kernels (shapes the native kernels do not cover)"},
                 "e2e": {"value": world * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof,
