@@ -157,7 +157,10 @@ class Trainer:
                                  process_group=process_group, attr_provider=self.attr_provider)
         self.dataset = get_dataset(args)
         self.loader = ShardedBatches(self.dataset, args.train_batch_size, rank, world, seed=args.seed or 0)
-        self.steps_per_epoch = max(1, math.ceil(len(self.loader) / self.accum))       # :282 optimiser steps per epoch
+        if len(self.loader) == 0:
+            raise ValueError(f"{len(self.dataset)} training prompts do not fill one batch of {args.train_batch_size} on each of "
+                             f"{world} rank(s)")
+        self.steps_per_epoch = math.ceil(len(self.loader) / self.accum)               # :282 optimiser steps per epoch
         if args.max_train_steps is None:
             args.max_train_steps = args.num_train_epochs * self.steps_per_epoch
         args.num_train_epochs = math.ceil(args.max_train_steps / self.steps_per_epoch)   # :326

@@ -82,6 +82,10 @@ def test_training_loop_checkpoints_logs_and_resume(tmp_path, monkeypatch):
     assert [json.loads(l)["step"] for l in open(os.path.join(out, "train_log.jsonl"))] == [1, 2, 3, 4]
     with pytest.raises(NotImplementedError):
         Trainer(synthetic.default_args(full_finetuning=True, training_prompts=str(prompts)), {}, torch.device("cpu"))
+    too_big = synthetic.default_args(pretrain_model_name="sd_1_5", train_batch_size=8, training_prompts=str(prompts), output_dir=out,
+                                     resume_from_checkpoint=None, seed=3)
+    with pytest.raises(ValueError):                     # 5 prompts cannot fill a batch of 8: refuse instead of "training" 0 steps
+        Trainer(too_big, None, torch.device("cpu"), weights="synthetic_tiny", dtype=torch.float32)
 
 
 def test_sdxl_entry_trains_from_prompt_strings(tmp_path, monkeypatch):
