@@ -301,6 +301,9 @@ def main(argv=None) -> int:
     pre.add_argument("--weights", choices=["synthetic", "synthetic_tiny"], default="synthetic")
     pre.add_argument("--log_every", type=int, default=10)
     extra, rest = pre.parse_known_args(argv)
+    if any(h in rest for h in ("-h", "--help")):
+        print("entry-point options (on top of the reference flags below):\n  --weights {synthetic,synthetic_tiny}   random-init "
+              "networks at the real / a tiny geometry\n  --log_every N                          read the step scalars back every N steps\n")
     args = parse_args(rest)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if not torch.cuda.is_available():
