@@ -120,3 +120,40 @@ def test_reader_formats(tmp_path):
     txt = str(tmp_path / "p.txt")
     open(txt, "w").write("a\nb\nc\n")
     assert GD.read_prompts(txt, 1, 3) == ["b", "c"]
+
+
+import pytest
+
+
+@pytest.mark.needs_reference
+def test_reference_reader_reads_what_our_producer_writes(tmp_path, monkeypatch):
+    """drop-in check in the build container: the reference's OWN ``Gan_Dataset`` (training_utils/gan_dataset.py, imported as is;
+    its Ceph client and matplotlib are stubbed) reads the jsonl + latents our producer wrote, item for item like our reader."""
+    import sys
+    import types
+    from oracle import ref_shim
+    from comat_b200 import gan_data as GD
+    pipe, _, _ = _world(monkeypatch)
+    index = str(tmp_path / "train_data" / "gan_train_data.jsonl")
+    prompts = ["a red apple", "two dogs on a sofa", "a blue car"]
+    GD.generate_gan_ground_truth(pipe, prompts, index, batch_size=2, num_inference_steps=1, height=64, width=64,
+                                 generator=torch.Generator().manual_seed(2))
+
+    class Client:                                       # aoss_client.client.Client('~/aoss.conf').get(path) -> bytes
+        def __init__(self, *_):
+            pass
+
+        def get(self, path):
+            return open(path, "rb").read()
+    for name in ("aoss_client", "aoss_client.client", "matplotlib", "matplotlib.pyplot"):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    sys.modules["aoss_client.client"].Client = Client
+    ref_shim.install()
+    ref = ref_shim.import_reference("training_utils.gan_dataset")
+    args = SimpleNamespace(training_prompts=index)
+    theirs, ours = ref.Gan_Dataset(args), GD.Gan_Dataset(args)
+    assert len(theirs) == len(ours) == 3
+    for i in range(3):
+        a, b = theirs[i], ours[i]
+        assert a["text"] == b["text"] == prompts[i] and set(a) == set(b) == {"text", "latents"}
+        assert a["latents"].dtype == torch.float32 and a["latents"].shape == (4, 8, 8) and torch.equal(a["latents"], b["latents"])
