@@ -164,3 +164,23 @@ def test_gradient_accumulation_sums_scaled_micro_batch_gradients(tmp_path, monke
     EMU.install_blip(monkeypatch)
     tr2 = mk(2, "acc2")
     assert tr2.train() == 2 and tr2.core.optimizer.step_count == 2
+
+
+@pytest.mark.parametrize("script,name,batch,lr_d", [("sd15.sh", "sd_1_5_attrcon", 4, 2e-5), ("sdxl.sh", "sdxl_attrcon_unet", 6, 5e-5)])
+def test_canonical_scripts_parse_with_the_entry_point(script, name, batch, lr_d):
+    """scripts/*.sh carry the reference's canonical hyper-parameters (its scripts/sd15.sh, scripts/sdxl.sh): every flag parses."""
+    import argparse
+    import shlex
+    from tests.conftest import ROOT
+    from comat_b200.arguments import parse_args
+    text = open(os.path.join(ROOT, "scripts", script)).read().replace("\\\n", " ")
+    cmd = next(l for l in text.splitlines() if l.startswith("torchrun"))
+    argv = shlex.split(cmd.replace('"$@"', "").replace('"${WEIGHTS:-synthetic}"', "synthetic"))
+    argv = argv[argv.index("comat_b200.train") + 1:]
+    pre = argparse.ArgumentParser(add_help=False)
+    pre.add_argument("--weights")
+    _, rest = pre.parse_known_args(argv)
+    a = parse_args(rest)
+    assert a.pretrain_model_name == name and a.train_batch_size == batch and a.learning_rate_D == lr_d
+    assert a.K == 5 and a.total_step == 50 and a.lora_rank == 128 and a.gan_loss and a.gan_model_arch == "gansd_1_5"
+    assert a.gradient_accumulation_steps == 1 and a.attrcon_train_steps == 2 and a.mixed_precision == "fp16" and a.seed == 42
