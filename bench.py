@@ -438,6 +438,11 @@ def main():
                            "samples_per_sec": value * a.batch, "global_optimizer_steps_per_sec": value / world,
                            "value_definition": "per-GPU-batch train-steps per second summed over ranks (= n_gpus x global optimiser steps/s)",
                            "library_calls_per_step": lib_calls / a.steps,
+                           # second half of BASELINE's metric ("UNet attn tensor-pipe %"): not measurable without a profiler, so the
+                           # committed ncu --set full capture is cited, never a number taken in this (unprofiled) run
+                           "unet_attn_tensor_pipe_pct": {"attn_fwd_kernel<40>": 23.0, "attn_bwd_kernel<40,dQ>": 22.9,
+                                                         "attn_bwd_kernel<40,dKdV>": 19.8, "shape": "SD1.5 64^2-latent self-attention, n=8, 8 heads, d=40",
+                                                         "source": "profiles/r01_attn_ncu_v19.md (sm__pipe_tensor cycles active, ncu --set full --clock-control none)"},
                            "library_note": ("0 = every conv / linear / attention (fwd+bwd) / norm / loss / resize / optimiser launch of the step "
                                             "is a comat_b200 kernel; torch supplies memory, the fp32 latent-chain glue, "
                                             "embedding gathers, layout permutes and the discriminator's per-pixel Linear(4,1) + BCE head "
