@@ -143,6 +143,12 @@ PIPELINE_CASES = [
 ]
 
 
+SDXL_PIPELINE_CASES = [
+    dict(seed=41, B=2, S=4, K=2, hw=32, rank=4),
+    dict(seed=42, B=1, S=3, K=1, hw=32, rank=4, rescale=0.7),
+]
+
+
 def make_tiny_unet(seed, rank=4, sdxl=False, up_std=0.05, width=32, ctx=64):
     torch.manual_seed(seed)
     unet = sdm.UNet2DConditionModel(**sdm.tiny_unet_config(sdxl=sdxl, width=width, cross_attention_dim=ctx))

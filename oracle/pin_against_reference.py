@@ -320,9 +320,92 @@ def pin_attr_align():
     return None
 
 
+def pin_sdxl_pipeline():
+    """Reference AttrConcenTrainableSDXLPipeline.forward + _attrcon_forward (AttrConcenTrainableSDXLPipeline.py:234-496) with the
+    SDXL attention hook (attn_utils/tc_sdxl_attn_utils.py), verbatim, on the restated tiny SDXL-geometry UNet / VAE (VAE in
+    fp16 as the reference decodes ``latents.half()``, :438-444); vs oracle rollout(sdxl=True).  Pins rows a3 / a5: always-detached
+    UNet input, pooled-text + time-id conditioning split per CFG half, un-rescaled image with ``return_latents``."""
+    from types import SimpleNamespace
+    ref_shim.install()
+    tca = ref_shim.import_reference("attn_utils.tc_sdxl_attn_utils")
+    pl = ref_shim.import_reference("AttrConcenTrainableSDXLPipeline")
+    out = {}
+    for case in FX.SDXL_PIPELINE_CASES:
+        w = FX.pipeline_world(**case, sdxl=True)
+        S, T, A, B, hw = case["S"], w["training_steps"], w["attrcon_steps"], case["B"], case["hw"]
+        g = torch.Generator().manual_seed(case["seed"] + 9)
+        pooled, npooled = torch.randn(B, 16, generator=g), torch.randn(B, 16, generator=g)
+        vae = w["vae"].half()
+        layers = ["up_8", "up_16"]
+        # --- reference run
+        unet = w["make_unet"]()
+        ctrl = tca.AttentionStore(layers)
+        tca.register_attention_control(unet, ctrl)
+        n_layers = ctrl.num_att_layers
+        pipe = pl.AttrConcenTrainableSDXLPipeline.__new__(pl.AttrConcenTrainableSDXLPipeline)
+        sys.modules["diffusers"].StableDiffusionXLPipeline.__init__(
+            pipe, vae=vae, text_encoder=None, text_encoder_2=SimpleNamespace(config=SimpleNamespace(projection_dim=16)),
+            tokenizer=None, tokenizer_2=None, unet=unet, scheduler=sdm.DDPMScheduler())
+        pipe.parser = lambda p: p
+        pipe.attn_dict = {}
+        pipe.controller = ctrl
+        gen = torch.Generator().manual_seed(case["seed"] + 77)
+        prompts = ["p%d" % i for i in range(B)]
+        image, lat = pipe.forward(prompt=prompts, height=hw * 8, width=hw * 8, training_timesteps=T, detach_gradient=True,
+                                  train_text_encoder=False, num_inference_steps=S, guidance_scale=7.5,
+                                  guidance_rescale=case.get("rescale", 0.0), prompt_embeds=w["prompt_embeds"],
+                                  negative_prompt_embeds=w["null_embeds"], pooled_prompt_embeds=pooled,
+                                  negative_pooled_prompt_embeds=npooled, latents=w["latents"].clone(), generator=gen, early_exit=False,
+                                  return_latents=True, attrcon_train_steps=A)
+        torch.set_grad_enabled(True)
+        ref_attn = pipe.attn_dict
+        params_ref = [p for p in unet.parameters() if p.requires_grad]
+        loss_ref = (image.float() ** 2).mean() + sum((m.float() ** 2).sum() for d in ref_attn.values() for v in d.values() for m in v) * 1e-3
+        g_ref = torch.autograd.grad(loss_ref, params_ref, allow_unused=True)
+        # --- oracle run (noise pre-drawn from the same generator stream)
+        unet2 = w["make_unet"]()
+        ctrl2 = R.AttentionStore(layers)
+        assert R.register_attention_control(unet2, ctrl2) == n_layers
+        gen2 = torch.Generator().manual_seed(case["seed"] + 77)
+        noises = [torch.randn(w["latents"].shape, generator=gen2) for _ in range(S)]
+        ids = torch.tensor([[hw * 8., hw * 8, 0, 0, hw * 8, hw * 8]]).repeat(B, 1)
+        added = {"text_embeds": torch.cat([npooled, pooled]), "time_ids": torch.cat([ids, ids])}
+        image2, lat2, attn2 = R.rollout(unet2, vae, sdm.DDPMScheduler(), w["prompt_embeds"], w["null_embeds"], w["latents"].clone(),
+                                        noises, S, T, 7.5, case.get("rescale", 0.0), A, ctrl2, added_cond_kwargs=added, sdxl=True,
+                                        return_latents=True)
+        _close(lat2.half().float(), lat.float(), 1e-5, f"sdxl pipeline latents {case}")
+        _close(image2.float(), image.float(), 2e-3, f"sdxl pipeline image (fp16 VAE) {case}")
+        assert set(attn2.keys()) == set(ref_attn.keys()), (attn2.keys(), ref_attn.keys())
+        keyset = {}
+        for t in ref_attn:
+            assert set(attn2[t].keys()) == set(ref_attn[t].keys())
+            for k in ref_attn[t]:
+                assert len(attn2[t][k]) == len(ref_attn[t][k])
+                keyset[k] = len(ref_attn[t][k])
+                for a, b in zip(attn2[t][k], ref_attn[t][k]):
+                    _close(a, b, 1e-5, f"sdxl pipeline attn {t} {k}")
+        params2 = [p for p in unet2.parameters() if p.requires_grad]
+        loss2 = (image2.float() ** 2).mean() + sum((m.float() ** 2).sum() for d in attn2.values() for v in d.values() for m in v) * 1e-3
+        g2 = torch.autograd.grad(loss2, params2, allow_unused=True)
+        n_checked = 0
+        for a, b in zip(g2, g_ref):
+            if b is not None and float(b.abs().max()) > 0:
+                _close(a, b, 5e-3, f"sdxl pipeline lora grad {case}")
+                n_checked += 1
+        assert n_checked > 0
+        out[FX.case_key(case)] = {
+            "case": case, "num_att_layers": n_layers, "keyset": keyset, "timesteps": sorted(ref_attn.keys()),
+            "image_mean": float(image.double().mean()), "image_l2": float(image.double().norm()),
+            "latents": lat.detach().clone(), "pooled": pooled, "npooled": npooled, "loss": float(loss_ref),
+            "grad_l2": [float(g.double().norm()) if g is not None else 0.0 for g in g_ref],
+        }
+    return out
+
+
 PINS = [("layer_loss", pin_layer_loss), ("mask_loss", pin_mask_loss), ("blip_score", pin_blip_score),
         ("gan", pin_gan), ("pipeline", pin_attention_store_and_pipeline), ("encode_prompt", pin_encode_prompt),
-        ("lora_state_dict", pin_lora_state_dict), ("attr_align", pin_attr_align)]
+        ("lora_state_dict", pin_lora_state_dict), ("attr_align", pin_attr_align),
+        ("sdxl_pipeline", pin_sdxl_pipeline)]
 
 
 def main():

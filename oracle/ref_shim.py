@@ -91,6 +91,20 @@ def install():
             super().__init__(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet, scheduler=scheduler, **kw)
             self.text_encoder_2, self.tokenizer_2 = text_encoder_2, tokenizer_2
 
+        def encode_prompt(self, prompt=None, prompt_2=None, device=None, num_images_per_prompt=1, do_classifier_free_guidance=True,
+                          negative_prompt=None, negative_prompt_2=None, prompt_embeds=None, negative_prompt_embeds=None,
+                          pooled_prompt_embeds=None, negative_pooled_prompt_embeds=None, lora_scale=None, clip_skip=None):
+            """diffusers StableDiffusionXLPipeline.encode_prompt restricted to what the pins need: all four embeddings are
+            passed in and only repeated ``num_images_per_prompt`` times (the text-encoding half lives in
+            oracle/comat_ref.encode_prompt_sdxl)."""
+            if prompt_embeds is None or pooled_prompt_embeds is None:
+                raise NotImplementedError("shim: pass prompt_embeds and pooled_prompt_embeds")
+            n = num_images_per_prompt
+            rep = lambda t: None if t is None else t.repeat(1, n, *([1] * (t.dim() - 2))).view(t.shape[0] * n, *t.shape[1:])
+            if not do_classifier_free_guidance:
+                negative_prompt_embeds = negative_pooled_prompt_embeds = None
+            return rep(prompt_embeds), rep(negative_prompt_embeds), rep(pooled_prompt_embeds), rep(negative_pooled_prompt_embeds)
+
     class _Dummy:
         def __init__(self, *a, **k):
             pass

@@ -114,6 +114,29 @@ def test_pipeline_golden(case, golden):
     assert rel(image.double().mean(), g["image_mean"]) < 1e-4
 
 
+@pytest.mark.parametrize("case", FX.SDXL_PIPELINE_CASES, ids=FX.case_key)
+def test_sdxl_pipeline_golden(case, golden):
+    """rows a3 / a5: oracle rollout(sdxl=True) vs the outputs of the reference's own AttrConcenTrainableSDXLPipeline.forward
+    (tests/golden/sdxl_pipeline.pt; VAE in fp16 as the reference decodes latents.half())."""
+    g = golden("sdxl_pipeline")[FX.case_key(case)]
+    w = FX.pipeline_world(**case, sdxl=True)
+    B, hw = case["B"], case["hw"]
+    unet = w["make_unet"]()
+    ctrl = R.AttentionStore(["up_8", "up_16"])
+    assert R.register_attention_control(unet, ctrl) == g["num_att_layers"]
+    gen = torch.Generator().manual_seed(case["seed"] + 77)
+    noises = [torch.randn(w["latents"].shape, generator=gen) for _ in range(case["S"])]
+    ids = torch.tensor([[hw * 8., hw * 8, 0, 0, hw * 8, hw * 8]]).repeat(B, 1)
+    added = {"text_embeds": torch.cat([g["npooled"], g["pooled"]]), "time_ids": torch.cat([ids, ids])}
+    image, lat, attn = R.rollout(unet, w["vae"].half(), sdm.DDPMScheduler(), w["prompt_embeds"], w["null_embeds"], w["latents"].clone(),
+                                 noises, case["S"], w["training_steps"], 7.5, case.get("rescale", 0.0), w["attrcon_steps"], ctrl,
+                                 added_cond_kwargs=added, sdxl=True, return_latents=True)
+    assert sorted(attn.keys()) == g["timesteps"]
+    assert {k: len(v) for k, v in next(iter(attn.values())).items()} == g["keyset"]
+    assert rel(lat.half().float(), g["latents"].float()) < 2e-3                      # the reference hands back latents.half()
+    assert rel(image.double().mean(), g["image_mean"]) < 5e-3                         # un-rescaled image (:438-440), fp16 VAE
+
+
 @pytest.mark.needs_reference
 def test_reference_hook_captures_expected_keys_on_restated_unet():
     """The reference's own register_attention_control must hook the restated UNet (SURVEY 8c checks 2-4)."""

@@ -1,6 +1,6 @@
 """CPU: SDXL twin of the drop-in pipeline (TrainableSDPipeline.py:657-846 / AttrConcenTrainableSDXLPipeline.py:234-496):
 always-detached UNet input, pooled-text + time-id conditioning, un-rescaled image when return_latents — vs the oracle rollout
-(whose SD1.5 branch is pinned to the reference's own pipeline), with the C-ABI ops emulated."""
+(pinned to the reference's own SD1.5 and SDXL pipelines: tests/golden/pipeline.pt, sdxl_pipeline.pt), with the C-ABI ops emulated."""
 import random
 
 import torch
