@@ -402,10 +402,36 @@ def pin_sdxl_pipeline():
     return out
 
 
+def pin_lora_install():
+    """Reference ``set_pipeline_trainable_module`` + ``get_trainable_parameters`` (training_utils/pipeline.py:84-121, :123-187; row
+    a14), verbatim through the shim, on the restated UNets (meta device): which projections carry LoRA, rank, dtype, and the order
+    of the trainable-parameter list -> tests/golden/lora_trainable_params.json."""
+    import argparse
+    import json
+    from types import SimpleNamespace
+    ref_shim.install()
+    tp = ref_shim.import_reference("training_utils.pipeline")
+    out = {}
+    for name, cfg, rank in (("sd15_r128", {}, 128), ("sdxl_r128", sdm.SDXL_UNET_CONFIG, 128), ("tiny_r4", sdm.tiny_unet_config(width=64, cross_attention_dim=64), 4)):
+        args = argparse.Namespace(full_finetuning=False, lora_rank=rank, train_text_encoder_lora=False, tune_vae=False, tune_text_encoder=False)
+        with torch.device("meta"):
+            unet = sdm.UNet2DConditionModel(**cfg)
+            pipe = SimpleNamespace(unet=unet, vae=None, text_encoder=None)
+            tp.set_pipeline_trainable_module(args, pipe)
+            G, text = tp.get_trainable_parameters(args, pipe)
+        names = {id(p): n for n, p in unet.named_parameters()}
+        assert text == [] and all(p.dtype == torch.float32 for p in G)
+        out[name] = {"n": len(G), "numel": int(sum(p.numel() for p in G)), "params": [[names[id(p)], list(p.shape)] for p in G]}
+    with open(os.path.join(GOLDEN_DIR, "lora_trainable_params.json"), "w") as f:
+        json.dump(out, f)
+    print({k: (v["n"], v["numel"], v["params"][0]) for k, v in out.items()})
+    return None
+
+
 PINS = [("layer_loss", pin_layer_loss), ("mask_loss", pin_mask_loss), ("blip_score", pin_blip_score),
         ("gan", pin_gan), ("pipeline", pin_attention_store_and_pipeline), ("encode_prompt", pin_encode_prompt),
         ("lora_state_dict", pin_lora_state_dict), ("attr_align", pin_attr_align),
-        ("sdxl_pipeline", pin_sdxl_pipeline)]
+        ("sdxl_pipeline", pin_sdxl_pipeline), ("lora_install", pin_lora_install)]
 
 
 def main():

@@ -124,3 +124,32 @@ def test_trainer_checkpoint_layout_and_exact_resume(tmp_path, monkeypatch):
     assert CK.load_checkpoint(c, os.path.join(out, "checkpoint-9"), resume="explicit") == 9
     assert torch.equal(c.optimizer.flat, a.optimizer.flat) and torch.equal(c.D_optimizer.flat, d_before)
     assert CK.load_checkpoint(c, str(tmp_path / "empty"), "latest") is None
+
+
+@pytest.mark.parametrize("name", ["sd15_r128", "sdxl_r128", "tiny_r4"])
+def test_lora_install_matches_reference_functions(name):
+    """row a14: the reference's own ``set_pipeline_trainable_module`` + ``get_trainable_parameters`` (training_utils/pipeline.py:84-187,
+    run verbatim for tests/golden/lora_trainable_params.json) and the product's ``install_lora`` / executor agree on which projections
+    carry LoRA, the rank, fp32 masters, and the ORDER of the trainable-parameter list (= layout of the optimiser's flat buffer)."""
+    from comat_b200 import containers as Cn
+    gold = json.load(open(os.path.join(GOLDEN, "lora_trainable_params.json")))[name]
+    cfg = {"sd15_r128": {}, "sdxl_r128": Cn.SDXL_UNET,
+           "tiny_r4": dict(block_out_channels=(64, 128, 256, 256), heads=4, cross_attention_dim=64)}[name]
+    with torch.device("meta"):
+        unet = Cn.UNet2DConditionModel(**cfg)
+        params = unet.install_lora(128 if name != "tiny_r4" else 4)
+    names = {id(p): n for n, p in unet.named_parameters()}
+    assert [[names[id(p)], list(p.shape)] for p in params] == gold["params"]
+    assert len(params) == gold["n"] and sum(p.numel() for p in params) == gold["numel"] and all(p.dtype == torch.float32 for p in params)
+
+
+def test_executor_lora_parameter_order_matches_reference_order():
+    from comat_b200 import synthetic
+    from comat_b200.modules import EngineUNet
+    gold = json.load(open(os.path.join(GOLDEN, "lora_trainable_params.json")))["tiny_r4"]
+    unet, _ = synthetic.build_sd15("cpu", torch.float32, rank=4, seed=1, tiny=True)
+    eng = EngineUNet(unet, torch.float32)
+    names = {id(p): n for n, p in unet.named_parameters()}
+    got = [[names[id(p)], list(p.shape)] for p in eng.lora_parameters()]
+    assert sorted(map(str, got)) == sorted(map(str, gold["params"]))               # same set of tensors ...
+    assert got == gold["params"]                                                    # ... in the reference's order
