@@ -178,3 +178,52 @@ def test_trainer_step_from_prompt_strings_equals_step_from_oracle_embeddings(mon
     args2 = synthetic.default_args(pretrain_model_name="sd_1_5", train_text_encoder_lora=True)
     with pytest.raises(NotImplementedError):
         CoMatTrainer(args2, pipe, None, None)
+
+
+@pytest.mark.needs_reference
+def test_discriminator_encode_prompt_vs_reference(monkeypatch):
+    """gan_sdxl.py:134-155 run verbatim (reference D_sd.encode_prompt over the reference TrainableSDPipeline.encode_prompt, HF CLIP,
+    tokenizer stub) vs the product's D_sd.encode_prompt: the '' embedding the trainer asks for once (training_script.py:516), and
+    the release of the D pipeline's text encoder afterwards."""
+    from types import SimpleNamespace
+    from oracle import ref_shim
+    EMU.install_blip(monkeypatch)
+    ref_shim.install()
+    gan = ref_shim.import_reference("training_utils.gan_sdxl")
+    pl = ref_shim.import_reference("TrainableSDPipeline")
+    clip = R.make_clip_text("clip_l", tiny=True, seed=31)
+    moved = []
+
+    class Enc(torch.nn.Module):                                  # records .to('cpu') like the reference parks it (:151)
+        def __init__(self):
+            super().__init__()
+            self.m, self.config = clip, clip.config
+
+        @property
+        def dtype(self):
+            return torch.float32
+
+        def forward(self, *a, **k):
+            return self.m(*a, **k)
+
+        def to(self, *a, **k):
+            moved.append(a)
+            return self
+    rp = pl.TrainableSDPipeline.__new__(pl.TrainableSDPipeline)
+    ref_shim._PipelineBase.__init__(rp, vae=SimpleNamespace(to=lambda *a: moved.append(a)), text_encoder=Enc(), tokenizer=FX.ClipTokenizerStub(),
+                                    unet=None, scheduler=None)
+    self_ns = SimpleNamespace(D_sd_pipeline=rp)
+    null_ref, pooled_ref = gan.D_sd.encode_prompt(self_ns, "", torch.device("cpu"), 3, do_classifier_free_guidance=False)
+    assert pooled_ref is None and null_ref.shape == (3, 77, 128) and len(moved) == 2
+    # product
+    from comat_b200.gan import D_sd
+    from comat_b200.pipelines import TrainableSDPipeline
+    from comat_b200.synthetic import SyntheticClipTokenizer
+    from comat_b200.text_encoder import EngineCLIPText
+    dp = TrainableSDPipeline(None, None, text_encoder=EngineCLIPText(clip, torch.float32), tokenizer=SyntheticClipTokenizer())
+    D = D_sd.__new__(D_sd)
+    torch.nn.Module.__init__(D)
+    D.D_sd_pipeline = dp
+    null, pooled = D.encode_prompt("", torch.device("cpu"), 3, do_classifier_free_guidance=False)
+    assert pooled is None and dp.text_encoder is None
+    torch.testing.assert_close(null, null_ref, rtol=1e-4, atol=1e-5)
