@@ -261,12 +261,12 @@ def pin_encode_prompt():
 
 
 def reference_function(rel_path: str, name: str, namespace: dict):
-    """compile ONE top-level function of a reference file that cannot be imported whole (training_script.py imports accelerate)
+    """compile ONE top-level function (or class) of a reference file that cannot be imported whole (training_script.py imports accelerate)
     from its own source text - nothing is copied into the repo; the function body runs verbatim."""
     import ast
     src = open(os.path.join(ref_shim.REFERENCE_ROOT, rel_path)).read()
     tree = ast.parse(src)
-    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    fn = next(n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name == name)
     code = compile(ast.Module(body=[fn], type_ignores=[]), os.path.join(ref_shim.REFERENCE_ROOT, rel_path), "exec")
     exec(code, namespace)
     return namespace[name]

@@ -96,3 +96,26 @@ def test_select_training_steps():
     assert len(steps) == 5 and steps[1] - steps[0] == 4 and all(a in steps for a in attr)
     steps, _ = R.select_training_steps(50, 5, random.Random(1), 2)
     assert steps[-1] <= 49 and steps[1] - steps[0] == 10
+
+
+@pytest.mark.needs_reference
+def test_caption_model_wrapper_vs_reference_class():
+    """row a12: the reference's own ``CaptionModelWrapper`` (training_script.py:69-97; the file imports accelerate, so the class is
+    compiled from its source text, nothing copied) vs the product's, over one fake scorer: weights * reward and 'total'."""
+    import torch
+    from oracle.pin_against_reference import reference_function
+    from comat_b200.caption import CaptionModelWrapper
+
+    class Scorer:
+        def score(self, images, prompts, **kw):
+            return images.mean() * len(prompts)
+
+    def load_model(self, caption_model, device, args):            # concept_mat_utils/load_captionmodel.py:3-8 needs Hub weights
+        self.blip_model = Scorer()
+    Ref = reference_function("training_script.py", "CaptionModelWrapper", {"torch": torch, "load_model": load_model})
+    ref = Ref(["Blip"], [0.75], "cpu", None, torch.float32)
+    ours = CaptionModelWrapper(["Blip"], [0.75], Scorer())
+    x = torch.rand(2, 3, 8, 8)
+    a, b = ref(x, ["p", "q"], batch={}), ours(x, ["p", "q"], batch={})
+    assert set(a) == set(b) == {"Blip", "total"}
+    assert torch.equal(a["Blip"], b["Blip"]) and torch.equal(a["total"], b["total"])
