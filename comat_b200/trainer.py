@@ -217,7 +217,11 @@ class CoMatTrainer:
     def train_step(self, batch: Dict, accum_steps: int = 1, first: bool = True, last: bool = True) -> Dict[str, torch.Tensor]:
         """one micro-batch.  ``accum_steps`` > 1 = ``accelerator.accumulate`` (training_script.py:556, :679): the gradients of
         consecutive calls add up from the one flagged ``first`` (buffers zeroed) to the one flagged ``last`` (optimisers step),
-        each loss scaled by 1/accum_steps as ``accelerator.backward`` does."""
+        each loss scaled by 1/accum_steps as ``accelerator.backward`` does.  Identical to the reference at ``accum_steps = 1`` (both
+        shipped scripts).  For A > 1 this is the *intended* accumulation: the reference calls ``optimizer.zero_grad()`` before
+        ``backward`` on every micro-step (:658-659), and accelerate's wrapped ``zero_grad`` - un-vendored; a no-op only while
+        ``sync_gradients`` is False - therefore clears the accumulated gradients on the very micro-step that steps, so the
+        reference applies loss/A of the LAST micro-batch alone."""
         a = self.args
         self._gc_before_step()
         self._join("_ev_G")                                                          # the generator's previous update is in
