@@ -86,4 +86,8 @@ def load_discriminator(args, unet: EngineUNet):
     name = args.gan_model_arch.replace("gan", "")
     if name == "sd_1_5":
         return D_sd(unet)
+    if "sdxl" in name:
+        # gan_sd_model.py:13-14 would build D_sdxl, whose constructor cannot run (gan_sdxl.py:161 calls super().__init__() without
+        # the required arguments -> TypeError); both shipped scripts use the SD1.5 discriminator
+        raise NotImplementedError("an SDXL discriminator (D_sdxl) is broken in the reference and not implemented here; use gansd_1_5")
     return None

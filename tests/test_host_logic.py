@@ -119,3 +119,18 @@ def test_caption_model_wrapper_vs_reference_class():
     a, b = ref(x, ["p", "q"], batch={}), ours(x, ["p", "q"], batch={})
     assert set(a) == set(b) == {"Blip", "total"}
     assert torch.equal(a["Blip"], b["Blip"]) and torch.equal(a["total"], b["total"])
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("arch,kind", [("gansd_1_5", "D_sd"), ("gan_sd_1_5", None), ("sd_1_5", "D_sd"), ("ganother", None)])
+def test_load_discriminator_arch_strings_vs_reference(arch, kind, monkeypatch):
+    """gan_sd_model.py:8-14 run verbatim (D_sd patched to a marker): which ``--gan_model_arch`` strings resolve to a discriminator."""
+    import argparse
+    from oracle import ref_shim
+    from comat_b200 import gan as G
+    ref = ref_shim.import_reference("training_utils.gan_sd_model")
+    monkeypatch.setattr(ref, "D_sd", lambda *a: "D_sd")
+    got_ref = ref.load_discriminator(argparse.Namespace(gan_model_arch=arch), None, None)
+    monkeypatch.setattr(G, "D_sd", lambda unet: "D_sd")
+    got = G.load_discriminator(argparse.Namespace(gan_model_arch=arch, gan_unet_lastlayer_cls=False, condition_discriminator=False), None)
+    assert got_ref == got == kind
