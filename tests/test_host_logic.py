@@ -134,3 +134,65 @@ def test_load_discriminator_arch_strings_vs_reference(arch, kind, monkeypatch):
     monkeypatch.setattr(G, "D_sd", lambda unet: "D_sd")
     got = G.load_discriminator(argparse.Namespace(gan_model_arch=arch, gan_unet_lastlayer_cls=False, condition_discriminator=False), None)
     assert got_ref == got == kind
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("S,K,n_attr", [(20, 5, 2), (50, 5, 2), (50, 1, 5), (7, 3, 2), (4, 4, 9)])
+def test_step_selection_vs_reference_statements(S, K, n_attr):
+    """row a1, step selection: the reference's own statements (training_script.py:563-566 ``interval / max_start / start /
+    training_steps`` and :589-590 ``random.choices``) are lifted from the AST of ``Trainer.train`` and executed on a seeded
+    ``random.Random``; the product's ``CoMatTrainer.select_steps`` must draw the same steps from the same stream."""
+    import ast
+    import argparse
+    import random
+    from oracle import ref_shim
+    from comat_b200.trainer import CoMatTrainer
+    tree = ast.parse(open(os.path.join(ref_shim.REFERENCE_ROOT, "training_script.py")).read())
+    train = next(n for c in tree.body if isinstance(c, ast.ClassDef) and c.name == "Trainer"
+                 for n in c.body if isinstance(n, ast.FunctionDef) and n.name == "train")
+    want = ["interval", "max_start", "start", "training_steps"]
+    picked = []
+    for node in ast.walk(train):
+        if isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Name) and node.targets[0].id in want:
+            picked.append(node)
+        if (isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Subscript) and
+                getattr(node.targets[0].slice, "value", None) == "attrcon_train_steps"):
+            picked.append(node)
+    picked.sort(key=lambda n: n.lineno)
+    assert [getattr(n.targets[0], "id", "kwargs") for n in picked] == want + ["kwargs"]
+    rng = random.Random(1234)
+    ns = {"random": rng, "total_step": S, "args": argparse.Namespace(K=K, attrcon_train_steps=n_attr), "kwargs": {}}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), "training_script.py", "exec"), ns)
+    tr = CoMatTrainer.__new__(CoMatTrainer)
+    tr.args = argparse.Namespace(K=K, total_step=S, attrcon_train_steps=n_attr)
+    tr.rng, tr.attrcon = random.Random(1234), True
+    steps, attr = tr.select_steps()
+    assert steps == ns["training_steps"] and attr == ns["kwargs"]["attrcon_train_steps"]
+    assert len(steps) >= K and all(0 <= s < S for s in steps)
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("res", [512, 256, 768, 1024])
+def test_reward_crop_vs_reference_statements(res):
+    """row a1, reward crop (training_script.py:606-611): offsets and size of the crop handed to the captioner, lifted from the
+    reference's AST, vs the arithmetic in ``CoMatTrainer.g_losses`` (same RNG stream: x offset first, then y)."""
+    import ast
+    import argparse
+    import random
+    import re
+    from oracle import ref_shim
+    tree = ast.parse(open(os.path.join(ref_shim.REFERENCE_ROOT, "training_script.py")).read())
+    want = ["offset_range", "random_offset_x", "random_offset_y", "size"]
+    picked = sorted((n for n in ast.walk(tree) if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Name) and n.targets[0].id in want),
+                    key=lambda n: n.lineno)
+    assert [n.targets[0].id for n in picked] == want
+    ns = {"random": random.Random(7), "args": argparse.Namespace(resolution=res)}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), "training_script.py", "exec"), ns)
+    # the product's statements, taken from its own source so the test follows the code
+    src = open(os.path.join(ROOT, "comat_b200", "trainer.py")).read()
+    m = re.search(r"off = a\.resolution // 224.*?\n\s+ox, oy = batch\.get\(\"crop\"\) or \(self\.rng\.randint\(0, off\), self\.rng\.randint\(0, off\)\)\n\s+size = a\.resolution - off", src)
+    assert m, "trainer.py crop statements changed: update this test"
+    rng = random.Random(7)
+    off = res // 224
+    ox, oy = rng.randint(0, off), rng.randint(0, off)
+    assert (off, ox, oy, res - off) == (ns["offset_range"], ns["random_offset_x"], ns["random_offset_y"], ns["size"])
