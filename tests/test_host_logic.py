@@ -196,3 +196,33 @@ def test_reward_crop_vs_reference_statements(res):
     off = res // 224
     ox, oy = rng.randint(0, off), rng.randint(0, off)
     assert (off, ox, oy, res - off) == (ns["offset_range"], ns["random_offset_x"], ns["random_offset_y"], ns["size"])
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("norm_grad", [False, True])
+def test_record_grad_hook_vs_reference(norm_grad):
+    """row a19: the reference's own ``record_grad`` closure (training_script.py:644-651, lifted from the AST) vs the hook
+    ``CoMatTrainer.g_losses`` registers on the image (same rescaling; the norm stays a device scalar instead of ``.item()``)."""
+    import ast
+    import argparse
+    from oracle import ref_shim
+    tree = ast.parse(open(os.path.join(ref_shim.REFERENCE_ROOT, "training_script.py")).read())
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "record_grad")
+    ns = {"norm": {}, "args": argparse.Namespace(norm_grad=norm_grad)}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "training_script.py", "exec"), ns)
+    g = torch.randn(2, 3, 16, 16, generator=torch.Generator().manual_seed(1)) * 3e-4
+    want = ns["record_grad"](g.clone())
+    # the product's hook, exercised through a real backward on a stand-in image
+    from comat_b200.trainer import CoMatTrainer
+    tr = CoMatTrainer.__new__(CoMatTrainer)
+    tr.args = argparse.Namespace(norm_grad=norm_grad, resolution=16, gan_loss=False, cfg_scale=7.5, cfg_rescale=0.0, total_step=1,
+                                 do_classifier_free_guidance=False)
+    tr.attrcon, tr.D, tr.rng = False, None, None
+    image = torch.zeros(2, 3, 16, 16, requires_grad=True)
+    leaf = image * 1.0
+    tr.pipeline = type("P", (), {"is_sdxl": False, "attn_dict": {}, "forward": lambda self, **kw: leaf})()
+    tr.caption_model = lambda img, text, batch=None: {"total": img.sum() * 0.0, "Blip": img.sum() * 0.0}
+    logs = tr.g_losses({"prompt_embeds": None, "training_steps": [0], "attrcon_steps": None, "crop": (0, 0)})
+    leaf.backward(g.clone())
+    assert abs(float(logs["_norm_holder"]["reward_norm"]) - ns["norm"]["reward_norm"]) <= 1e-6 * ns["norm"]["reward_norm"]
+    torch.testing.assert_close(image.grad, want, rtol=1e-6, atol=0)
