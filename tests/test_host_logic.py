@@ -226,3 +226,39 @@ def test_record_grad_hook_vs_reference(norm_grad):
     leaf.backward(g.clone())
     assert abs(float(logs["_norm_holder"]["reward_norm"]) - ns["norm"]["reward_norm"]) <= 1e-6 * ns["norm"]["reward_norm"]
     torch.testing.assert_close(image.grad, want, rtol=1e-6, atol=0)
+
+
+@pytest.mark.needs_reference
+def test_optimizer_hyper_parameter_wiring_vs_reference():
+    """row a20: which ``args.*`` feed AdamW / clipping of the generator and the discriminator - read off the reference's own
+    ``optimizer_cls(...)`` and ``clip_grad_norm_(...)`` calls (AST of training_script.py:215-275, :661, :692) - vs the values
+    ``CoMatTrainer`` hands its two ``FlatAdamW`` instances when every flag carries a distinct value."""
+    import ast
+    import argparse
+    from oracle import ref_shim
+    tree = ast.parse(open(os.path.join(ref_shim.REFERENCE_ROOT, "training_script.py")).read())
+
+    def arg_name(node):
+        return node.attr if isinstance(node, ast.Attribute) and getattr(node.value, "id", "") == "args" else None
+    wiring = {}
+    for call in (n for n in ast.walk(tree) if isinstance(n, ast.Call) and getattr(n.func, "id", "") == "optimizer_cls"):
+        params = ast.unparse(call.args[0])
+        if params not in ("self.G_parameters", "self.D_parameters"):
+            continue                                               # the text-encoder-LoRA param-group variant (:239-252)
+        kw = {k.arg: k.value for k in call.keywords}
+        wiring[params] = {"lr": arg_name(kw["lr"]), "betas": tuple(arg_name(e) for e in kw["betas"].elts),
+                          "wd": arg_name(kw["weight_decay"]), "eps": arg_name(kw["eps"])}
+    for call in (n for n in ast.walk(tree) if isinstance(n, ast.Call) and getattr(n.func, "attr", "") == "clip_grad_norm_"):
+        wiring[ast.unparse(call.args[0])]["clip"] = arg_name(call.args[1])
+    assert set(wiring) == {"self.G_parameters", "self.D_parameters"}
+    vals = dict(learning_rate=1e-3, learning_rate_D=2e-3, adam_beta1=0.11, adam_beta2=0.22, adam_beta1_D=0.33, adam_beta2_D=0.44,
+                adam_weight_decay=0.55, adam_epsilon=6e-7, max_grad_norm=0.77, max_grad_norm_D=0.88)
+    from comat_b200.trainer import CoMatTrainer
+    mk = lambda: [torch.nn.Parameter(torch.zeros(3))]
+    pipe = type("P", (), {"unet": type("U", (), {"lora_parameters": lambda self: mk(), "refresh_lora": lambda self, **k: None})()})()
+    D = type("D", (), {"get_trainable_parameters": lambda self: mk(), "unet": pipe.unet})()
+    tr = CoMatTrainer(argparse.Namespace(seed=0, pretrain_model_name="sd_1_5", **vals), pipe, None, D)
+    for key, opt in (("self.G_parameters", tr.optimizer), ("self.D_parameters", tr.D_optimizer)):
+        w = wiring[key]
+        assert opt.lr == vals[w["lr"]] and tuple(opt.betas) == tuple(vals[b] for b in w["betas"])
+        assert opt.wd == vals[w["wd"]] and opt.eps == vals[w["eps"]] and opt.max_norm == vals[w["clip"]]
