@@ -34,6 +34,13 @@ class TrainableSDPipeline:
         self.controller: Optional[E.AttnCapture] = None
         self.attn_dict: Dict[str, Dict[str, List[torch.Tensor]]] = {}
 
+    @classmethod
+    def from_pretrained(cls, model_path, **kw):
+        """``PIPELINE.from_pretrained(model_path, revision=..., torch_type=...[, vae=..., unet=...])`` (training_utils/pipeline.py:19-39)
+        over a local diffusers-layout directory - see ``comat_b200.loading``."""
+        from .loading import from_pretrained
+        return from_pretrained(cls, model_path, **kw)
+
     @property
     def _execution_device(self):
         return self.unet.device

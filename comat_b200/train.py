@@ -127,11 +127,48 @@ def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False, 
     return comp
 
 
+def pretrained_components(args, device, dtype=torch.float16, blip_path: Optional[str] = None, d_model_path: Optional[str] = None,
+                          attr_provider=None) -> Dict:
+    """real checkpoints from LOCAL diffusers / transformers directories (``load_pipeline``, training_utils/pipeline.py:19-82;
+    ``load_model``, concept_mat_utils/load_captionmodel.py:3-8; ``D_sd.__init__``, gan_sdxl.py:7-35 - the reference pulls the same
+    three from the Hub): ``--pretrain_model`` must be a directory, ``blip_path`` one holding Salesforce/blip-image-captioning-large,
+    ``d_model_path`` one holding runwayml/stable-diffusion-v1-5 (defaults to ``--pretrain_model`` for SD1.5 runs)."""
+    from transformers import AutoTokenizer, BlipForConditionalGeneration
+    from . import pipelines as P
+    from .blip_engine import BlipEngine
+    from .caption import Blip, CaptionModelWrapper
+    from .gan import load_discriminator
+    from .loading import load_unet
+    name = args.pretrain_model_name
+    sdxl = "sdxl" in name
+    cls = {(False, False): P.TrainableSDPipeline, (False, True): P.AttrConcenTrainableSDPipeline,
+           (True, False): P.TrainableSDXLPipeline, (True, True): P.AttrConcenTrainableSDXLPipeline}[(sdxl, "attrcon" in name)]
+    unet = load_unet(args.sdxl_unet_path, device) if (name.endswith("_unet") and args.sdxl_unet_path) else None     # pipeline.py:30-36
+    pipe = cls.from_pretrained(args.pretrain_model, revision=args.revision, unet=unet, dtype=dtype, device=device, lora_rank=args.lora_rank)
+    if blip_path is None:
+        raise ValueError("--blip_path: a local directory with the BLIP captioner (the reference downloads "
+                         "Salesforce/blip-image-captioning-large, load_captionmodel.py:5)")
+    blip_hf = BlipForConditionalGeneration.from_pretrained(blip_path, local_files_only=True).to(device=device, dtype=dtype).eval()
+    blip = Blip(BlipEngine(blip_hf.requires_grad_(False), dtype), tokenizer=AutoTokenizer.from_pretrained(blip_path, local_files_only=True))
+    comp = {"pipeline": pipe, "caption_model": CaptionModelWrapper(list(args.caption_model), list(args.reward_weights), blip), "D": None,
+            "attr_provider": attr_provider}
+    if args.gan_loss:
+        d_pipe = P.TrainableSDPipeline.from_pretrained(d_model_path or args.pretrain_model, dtype=dtype, device=device, lora_rank=args.lora_rank)
+        D = load_discriminator(args, d_pipe.unet)
+        if D is None:
+            raise NotImplementedError(f"--gan_model_arch {args.gan_model_arch!r} resolves to no discriminator (gan_sd_model.py:8-14)")
+        d_pipe.unet = d_pipe.vae = None                 # D keeps its UNet; the D pipeline only lends its text encoder (gan_sdxl.py:134-155)
+        D.D_sd_pipeline = d_pipe
+        comp["D"] = D
+    return comp
+
+
 class Trainer:
     """training_script.py:100-735 around the B200 step."""
 
     def __init__(self, args, components: Optional[Dict] = None, device=None, rank: int = 0, world: int = 1, process_group=None,
-                 weights: str = "synthetic", log_every: int = 1, dtype=torch.float16, train_layer_ls=None):
+                 weights: str = "synthetic", log_every: int = 1, dtype=torch.float16, train_layer_ls=None, blip_path: Optional[str] = None,
+                 d_model_path: Optional[str] = None):
         from .pipelines import AttentionStore, register_attention_control
         from .trainer import CoMatTrainer
         self.accum = max(1, int(args.gradient_accumulation_steps))
@@ -142,6 +179,8 @@ class Trainer:
         if args.seed is not None:                                                    # :129-130 set_seed(args.seed + process_index)
             random.seed(args.seed + rank)
             torch.manual_seed(args.seed + rank)
+        if components is None and weights == "pretrained":
+            components = pretrained_components(args, self.device, dtype, blip_path, d_model_path)
         comp = components or synthetic_components(args, self.device, dtype, tiny=(weights == "synthetic_tiny"))
         self.pipeline, self.caption_model, self.D = comp["pipeline"], comp["caption_model"], comp.get("D")
         self.attr_provider = comp.get("attr_provider")
@@ -298,12 +337,16 @@ class Trainer:
 
 def main(argv=None) -> int:
     pre = argparse.ArgumentParser(add_help=False)
-    pre.add_argument("--weights", choices=["synthetic", "synthetic_tiny"], default="synthetic")
+    pre.add_argument("--weights", choices=["synthetic", "synthetic_tiny", "pretrained"], default="synthetic")
+    pre.add_argument("--blip_path", type=str, default=None)
+    pre.add_argument("--d_model_path", type=str, default=None)
     pre.add_argument("--log_every", type=int, default=10)
     extra, rest = pre.parse_known_args(argv)
     if any(h in rest for h in ("-h", "--help")):
-        print("entry-point options (on top of the reference flags below):\n  --weights {synthetic,synthetic_tiny}   random-init "
-              "networks at the real / a tiny geometry\n  --log_every N                          read the step scalars back every N steps\n")
+        print("entry-point options (on top of the reference flags below):\n"
+              "  --weights {synthetic,synthetic_tiny,pretrained}  random-init networks at the real / a tiny geometry, or local checkpoints:\n"
+              "                                         --pretrain_model DIR (diffusers layout), --blip_path DIR, --d_model_path DIR\n"
+              "  --log_every N                          read the step scalars back every N steps\n")
     args = parse_args(rest)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if not torch.cuda.is_available():
@@ -312,7 +355,8 @@ def main(argv=None) -> int:
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    tr = Trainer(args, None, dev, rank, world, weights=extra.weights, log_every=extra.log_every)
+    tr = Trainer(args, None, dev, rank, world, weights=extra.weights, log_every=extra.log_every, blip_path=extra.blip_path,
+                 d_model_path=extra.d_model_path)
     tr.train()
     if world > 1:
         dist.destroy_process_group()
