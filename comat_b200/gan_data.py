@@ -159,7 +159,8 @@ def main(argv=None) -> int:
     p.add_argument("--model-path", type=str, default="runwayml/stable-diffusion-v1-5")
     p.add_argument("--model-type", type=str, default="sd_1_5", choices=["sd_1_5", "sdxl", "sdxl_unet"])
     p.add_argument("--batch-size", type=int, default=8)
-    p.add_argument("--weights", choices=["synthetic", "synthetic_tiny"], default="synthetic")
+    p.add_argument("--weights", choices=["synthetic", "synthetic_tiny", "pretrained"], default="synthetic",
+                   help="pretrained: --model-path is a local diffusers-layout directory")
     p.add_argument("--steps", type=int, default=50)
     p.add_argument("--resolution", type=int, default=512)
     a = p.parse_args(argv)
@@ -171,7 +172,14 @@ def main(argv=None) -> int:
     name = {"sd_1_5": "sd_1_5", "sdxl": "sdxl", "sdxl_unet": "sdxl"}[a.model_type]
     args = synthetic.default_args(pretrain_model_name=name, gan_loss=False, seed=42)
     dev = torch.device("cuda", torch.cuda.current_device())
-    pipe = synthetic_components(args, dev, tiny=(a.weights == "synthetic_tiny"), with_caption=False)["pipeline"]
+    if a.weights == "pretrained":
+        from . import pipelines as P
+        from .loading import load_unet
+        cls = P.TrainableSDXLPipeline if name == "sdxl" else P.TrainableSDPipeline
+        unet = load_unet(a.unet_path, dev) if (a.model_type == "sdxl_unet" and a.unet_path) else None      # :75-79
+        pipe = cls.from_pretrained(a.model_path, unet=unet, device=dev)
+    else:
+        pipe = synthetic_components(args, dev, tiny=(a.weights == "synthetic_tiny"), with_caption=False)["pipeline"]
     gen = torch.Generator(device=dev).manual_seed(int(time.time()))                  # :166 (time-seeded in the reference too)
     n = generate_gan_ground_truth(pipe, read_prompts(a.prompt_path, a.start, a.end), a.save_prompt_path, batch_size=a.batch_size,
                                   num_inference_steps=a.steps, guidance_scale=7.5, height=a.resolution, width=a.resolution,
