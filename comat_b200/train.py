@@ -1,6 +1,7 @@
 """Training entry point - the loop of ``Trainer.train`` (training_script.py:496-735) around ``CoMatTrainer.train_step``:
 epochs over the prompt data, resume (``--resume_from_checkpoint``, :156-205), per-step logs, ``checkpoint-<n>`` every
-``--validation_steps`` (:711-717) and at the end (:722-733), ``--max_train_steps``.
+``--validation_steps`` (:711-717), ``--max_train_steps``; one more checkpoint is written when training ends (an addition: the
+reference only saves on the ``--validation_steps`` cadence, :720-722).
 
     torchrun --nproc-per-node 8 -m comat_b200.train --pretrain_model_name sd_1_5_attrcon --gan_loss ... [reference flags]
 
@@ -232,7 +233,7 @@ class Trainer:
             dist.barrier()
 
     def save(self):
-        """:711-717 / :722-733: rank 0 writes ``checkpoint-<global_step>`` (all ranks hold identical parameters under DP)."""
+        """:711-717: rank 0 writes ``checkpoint-<global_step>`` (all ranks hold identical parameters under DP)."""
         path = None
         if self.rank == 0:
             path = CK.save_checkpoint(self.core, self.args.output_dir, self.global_step)
@@ -326,7 +327,7 @@ class Trainer:
                 break
         self.core.sync()
         self._flush_logs()
-        self.save()                                                                   # :722-733
+        self.save()                                                                   # addition: the reference ends without saving (:720-722)
         if self.device.type == "cuda":
             torch.cuda.synchronize()
         self._print(f"done: {self.global_step} steps in {time.time() - t0:.1f} s")
