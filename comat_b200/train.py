@@ -10,8 +10,8 @@ no Hub access, diffusers or tokenizer vocabularies, so the entry point builds ra
 stand-in tokenizers of ``comat_b200.synthetic``; a deployment passes real modules through ``Trainer(args, components=...)``
 (see INTEGRATION.md).  What the reference obtains from Grounded-SAM + spaCy per batch (noun / attribute token lists, masks:
 training_script.py:627-637) comes from ``components['attr_provider'](prompts, images) -> (words, masks)``, called by the step on
-the image it has just generated; the synthetic entry uses the SURVEY 8d generator.  Logs go to ``<output_dir>/train_log.jsonl`` (one JSON object per optimiser step) instead of
-TensorBoard; scalars are read back once per ``--log_every`` steps, not 7 ``.item()`` syncs per step.
+the image it has just generated; the synthetic entry uses the SURVEY 8d generator.  Logs go to ``<output_dir>/train_log.jsonl`` (one JSON object per optimiser step) and, with
+``--report_to tensorboard`` (the default), to ``<output_dir>/<logging_dir>/<tracker_project_name>`` like accelerate's tracker; scalars are read back once per ``--log_every`` steps, not 7 ``.item()`` syncs per step.
 """
 from __future__ import annotations
 
@@ -220,9 +220,14 @@ class Trainer:
         self._pending = []
         self._micro = 0
         self._log_file = None
+        self._tb = None
         if rank == 0:
             os.makedirs(args.output_dir, exist_ok=True)
             self._log_file = open(os.path.join(args.output_dir, "train_log.jsonl"), "a")
+            if getattr(args, "report_to", None) == "tensorboard":
+                # :105-107, :359: accelerate's tensorboard tracker writes under <output_dir>/<logging_dir>/<tracker_project_name>
+                from torch.utils.tensorboard import SummaryWriter
+                self._tb = SummaryWriter(os.path.join(args.output_dir, args.logging_dir, args.tracker_project_name))
 
     def _print(self, *a):
         if self.rank == 0:
@@ -264,6 +269,11 @@ class Trainer:
                                     guidance_scale=a.cfg_scale, guidance_rescale=a.cfg_rescale, output_type="pil").images[0]
                 paths.append(os.path.join(out_dir, f"test_{i}_{k}.png"))
                 img.save(paths[-1])
+            if self._tb is not None:                                                  # :485-489 add_images('test_<i>', NHWC)
+                import numpy as np
+                from PIL import Image
+                row = np.stack([np.asarray(Image.open(q)) for q in paths[-a.num_validation_images:]])
+                self._tb.add_images(f"test_{i}", row, self.global_step, dataformats="NHWC")
         return paths
 
     def _flush_logs(self):
@@ -282,6 +292,11 @@ class Trainer:
                 rec = {"step": step, "lr": self.args.learning_rate * lr_at(self.args, step - 1)}
                 rec.update({k: float(v) for k, v in zip(keys, row) if not math.isnan(float(v))})
                 self._log_file.write(json.dumps(rec) + "\n")
+                if self._tb is not None:                                              # :702-703 accelerator.log(..., step=global_step)
+                    for k, v in rec.items():
+                        if k != "step":
+                            self._tb.add_scalar(k, v, step)
+                    self._tb.add_scalar("train_loss", rec.get("loss", rec.get("step_loss", 0.0)), step)
             self._log_file.flush()
         self._pending = []
 
@@ -333,6 +348,8 @@ class Trainer:
         self._print(f"done: {self.global_step} steps in {time.time() - t0:.1f} s")
         if self._log_file is not None:
             self._log_file.close()
+        if self._tb is not None:
+            self._tb.close()
         return self.global_step
 
 

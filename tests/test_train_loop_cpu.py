@@ -72,6 +72,13 @@ def test_training_loop_checkpoints_logs_and_resume(tmp_path, monkeypatch):
     assert val == ["test_0_0.png", "test_0_1.png", "test_1_0.png", "test_1_1.png"]
     from PIL import Image
     assert Image.open(os.path.join(out, "validation", "step-2", val[0])).size == (64, 64)
+    tb_dir = os.path.join(out, "logs", "comat")                                    # --report_to tensorboard (default): :105-107, :359
+    assert any(f.startswith("events.out.tfevents") for f in os.listdir(tb_dir))
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(tb_dir, size_guidance={"scalars": 0, "images": 0})
+    acc.Reload()
+    assert {"step_loss", "Blip", "lr", "train_loss"} <= set(acc.Tags()["scalars"]) and [e.step for e in acc.Scalars("step_loss")] == [1, 2, 3]
+    assert {"test_0", "test_1"} <= set(acc.Tags()["images"])
     flat3 = tr.core.optimizer.flat.clone()
     # resume: picks checkpoint-3, skips the first batch of epoch 1, runs exactly one more step
     tr2 = mk(4, "latest")
