@@ -177,9 +177,11 @@ class Trainer:
             raise NotImplementedError("--full_finetuning / --tune_vae: this path trains the LoRA factors only")
         self.args, self.rank, self.world, self.log_every = args, rank, world, max(1, log_every)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
-        if args.seed is not None:                                                    # :129-130 set_seed(args.seed + process_index)
-            random.seed(args.seed + rank)
-            torch.manual_seed(args.seed + rank)
+        if args.seed is not None:                                                    # :117-118 set_seed(args.seed): the SAME seed on every rank
+            random.seed(args.seed)                                                   # (step selection and sampler noise streams coincide across
+            torch.manual_seed(args.seed)                                             # ranks in the reference; only the prompts differ)
+            if self.device.type == "cuda":
+                torch.cuda.manual_seed_all(args.seed)
         if components is None and weights == "pretrained":
             components = pretrained_components(args, self.device, dtype, blip_path, d_model_path)
         comp = components or synthetic_components(args, self.device, dtype, tiny=(weights == "synthetic_tiny"))
@@ -193,7 +195,7 @@ class Trainer:
             if self.attr_provider is None:
                 raise NotImplementedError("attrcon models need components['attr_provider'] (Grounded-SAM + spaCy are external)")
         self.pipeline.unet.use_graphs = True
-        self.core = CoMatTrainer(args, self.pipeline, self.caption_model, self.D, rng=random.Random((args.seed or 0) + rank),
+        self.core = CoMatTrainer(args, self.pipeline, self.caption_model, self.D, rng=random.Random(args.seed or 0),
                                  process_group=process_group, attr_provider=self.attr_provider)
         self.dataset = get_dataset(args)
         self.loader = ShardedBatches(self.dataset, args.train_batch_size, rank, world, seed=args.seed or 0)
