@@ -51,6 +51,17 @@ def lr_at(args, step: int) -> float:
     raise NotImplementedError(f"lr_scheduler {name!r}")
 
 
+def compute_dtype(args) -> torch.dtype:
+    """``--mixed_precision`` -> the 16-bit type of the frozen weights / activations (training_script.py:122-127; node8.yaml runs fp16).
+    The flag defaults to None (accelerate then reads its own config, fp16 in node8.yaml:8); 'no' = an fp32 network has no tensor-core
+    path in this package and is refused, as are optimisers other than AdamW (:216-226)."""
+    if args.mixed_precision == "no":
+        raise NotImplementedError("--mixed_precision no: the executors run 16-bit operands on the tensor cores (fp16 or bf16)")
+    if getattr(args, "use_8bit_adam", False) or getattr(args, "optimizer_class", "AdamW") != "AdamW":
+        raise NotImplementedError("only AdamW (the fused clip + AdamW kernel) is implemented; --use_8bit_adam / other --optimizer_class refused")
+    return torch.bfloat16 if args.mixed_precision == "bf16" else torch.float16
+
+
 def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False, with_caption: bool = True) -> Dict:
     """random-init networks at the real (or tiny) geometry + stand-in tokenizers (no Hub access in this image)."""
     from . import containers as Cn
@@ -376,7 +387,7 @@ def main(argv=None) -> int:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tr = Trainer(args, None, dev, rank, world, weights=extra.weights, log_every=extra.log_every, blip_path=extra.blip_path,
-                 d_model_path=extra.d_model_path)
+                 d_model_path=extra.d_model_path, dtype=compute_dtype(args))
     tr.train()
     if world > 1:
         dist.destroy_process_group()

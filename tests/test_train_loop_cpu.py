@@ -191,3 +191,14 @@ def test_canonical_scripts_parse_with_the_entry_point(script, name, batch, lr_d)
     assert a.pretrain_model_name == name and a.train_batch_size == batch and a.learning_rate_D == lr_d
     assert a.K == 5 and a.total_step == 50 and a.lora_rank == 128 and a.gan_loss and a.gan_model_arch == "gansd_1_5"
     assert a.gradient_accumulation_steps == 1 and a.attrcon_train_steps == 2 and a.mixed_precision == "fp16" and a.seed == 42
+
+
+def test_compute_dtype_follows_mixed_precision_flag():
+    from comat_b200 import synthetic
+    from comat_b200.train import compute_dtype
+    assert compute_dtype(synthetic.default_args(mixed_precision="fp16")) == torch.float16
+    assert compute_dtype(synthetic.default_args(mixed_precision="bf16")) == torch.bfloat16
+    assert compute_dtype(synthetic.default_args()) == torch.float16                  # unset: node8.yaml's fp16
+    for bad in (dict(mixed_precision="no"), dict(use_8bit_adam=True), dict(optimizer_class="Lion")):
+        with pytest.raises(NotImplementedError):
+            compute_dtype(synthetic.default_args(**bad))
