@@ -532,6 +532,10 @@ def _attn_layer_product(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Va
                 g = ops.gemm([dk2], [a.mk.wt], residual=g)
                 g = ops.gemm([dv2], [a.mv.wt], residual=g)
             x.g = g.reshape(xv.shape)
+        if ctx is not None and ctx.needs_grad:            # d(text context) through the folded k / v projections (off by default)
+            g = ops.gemm([dk2], [a.mk.wt], residual=ctx.g.reshape(-1, a.k.k) if ctx.g is not None else None)
+            g = ops.gemm([dv2], [a.mv.wt], residual=g)
+            ctx.g = g.reshape(ctx.v.shape)
     tape.record(bwd)
     return out
 
@@ -785,7 +789,8 @@ class UNetEngine:
         for r in self._res_all:
             temb[id(r)] = allp[:, off:off + r.temb.n]
             off += r.temb.n
-        cvar = Var(ctx, needs_grad=False)
+        # the text context is a constant of the CoMat step (frozen text encoders); a caller that wants d(ctx) passes a Var
+        cvar = ctx if isinstance(ctx, Var) else Var(ctx, needs_grad=False)
         h = conv(tape, [x], self.conv_in)
         skips = [h]
         for resnets, attns, ds in self.down:

@@ -26,8 +26,10 @@ class _UNetFn(torch.autograd.Function):
         ctx.wgrad = bool(mod.train_lora and any(p.requires_grad for p in lora_params))
         ctx.product = ctx.wgrad and eng.lora_train_impl == "product"
         ctx16, kv = ctx_kv if ctx_kv is not None else (ehs.to(eng.dtype), None)
+        # d(encoder_hidden_states) only when the caller's embeddings require grad (never on the frozen-text-encoder CoMat path)
+        cvar = E.Var(ctx16, needs_grad=True) if ctx.needs_input_grad[3] else ctx16
         # no LoRA weight gradient wanted (the discriminator's generator-side pass, gan_sdxl.py:52-89): LoRA folded into the weights
-        out = eng.forward(tape, xv, t, ctx16, capture=capture, added_cond=added,
+        out = eng.forward(tape, xv, t, cvar, capture=capture, added_cond=added,
                           lora_mode="train" if ctx.wgrad else "frozen", cross_kv=kv if (ctx.product or not ctx.wgrad) else None)
         eps = ops.nhwc_to_nchw_f32(out.v, mod.out_channels)
         pvars = []
@@ -35,7 +37,8 @@ class _UNetFn(torch.autograd.Function):
             for place in ("down", "mid", "up"):
                 pvars.extend(capture.store[place])
         ctx.tape, ctx.xv, ctx.out, ctx.pvars, ctx.mod = tape, xv, out, pvars, mod
-        ctx.x_dtype = x.dtype
+        ctx.cvar = cvar if isinstance(cvar, E.Var) else None
+        ctx.x_dtype, ctx.ehs_meta = x.dtype, (ehs.dtype, ehs.shape)
         return (eps.to(x.dtype), *[p.v for p in pvars])
 
     @staticmethod
@@ -67,8 +70,11 @@ class _UNetFn(torch.autograd.Function):
             lg = eng.lora_grads() if (ctx.wgrad and not direct) else [None] * len(eng.lora_grads())
             if ctx.wgrad and not direct and S != 1.0:
                 torch._foreach_mul_([g for g in lg if g is not None], 1.0 / S)
-        ctx.tape = ctx.xv = ctx.out = ctx.pvars = None
-        return (None, gx, None, None, None, None, None, *lg)
+        g_ehs = None
+        if ctx.cvar is not None and ctx.cvar.g is not None:
+            g_ehs = (ctx.cvar.g.float() / S).reshape(ctx.ehs_meta[1]).to(ctx.ehs_meta[0])
+        ctx.tape = ctx.xv = ctx.out = ctx.pvars = ctx.cvar = None
+        return (None, gx, None, g_ehs, None, None, None, *lg)
 
 
 class _GraphedForward:
@@ -191,7 +197,8 @@ class EngineUNet(torch.nn.Module):
                 return_dict=False):
         t = timestep if torch.is_tensor(timestep) else torch.tensor(timestep, device=sample.device)
         params = self.engine.lora_params()
-        want_grad = torch.is_grad_enabled() and (sample.requires_grad or (self.train_lora and any(p.requires_grad for p in params)))
+        want_grad = torch.is_grad_enabled() and (sample.requires_grad or encoder_hidden_states.requires_grad or
+                                                 (self.train_lora and any(p.requires_grad for p in params)))
         capture = self.capture
         if capture is not None:
             capture.reset()

@@ -139,3 +139,52 @@ def test_unet_merged_lora_modes_match_oracle(monkeypatch, sdxl):
     assert rel(out_ref2, out_ref) > 1e-3
     out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, dtype, 64), False), t, ctx, added_cond=added, cross_kv=eng.cross_kv(ctx))
     assert rel(ops.nhwc_to_nchw_f32(out.v, 4), out_ref2) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["product", "explicit", "frozen"])
+def test_unet_executor_context_gradient_matches_oracle(monkeypatch, mode):
+    """d(encoder_hidden_states): off on the CoMat path (frozen text encoders) and formed only when the caller passes the context as
+    a grad-requiring Var - through the folded k / v projections in 'product' mode, through ``linear`` otherwise."""
+    EMU.install(monkeypatch)
+    from comat_b200 import engine as E, ops
+    unet = _tiny(False)
+    eng = E.UNetEngine(unet, torch.float32)
+    if mode != "frozen":
+        eng.lora_train_impl = mode
+    g = torch.Generator().manual_seed(1)
+    n, hw = 2, 16
+    x, ctx = torch.randn(n, 4, hw, hw, generator=g), torch.randn(n, 77, 64, generator=g)
+    t, dy = torch.tensor(400), torch.randn(n, 4, hw, hw, generator=g)
+    cr = ctx.clone().requires_grad_(True)
+    g_ref = torch.autograd.grad(unet(x, t, cr, return_dict=False)[0], cr, dy)[0]
+    tape = E.Tape()
+    cv = E.Var(ctx, needs_grad=True)
+    out = eng.forward(tape, E.Var(ops.latent_to_nhwc(x, torch.float32, 64), False), t, cv, lora_mode="frozen" if mode == "frozen" else "train")
+    out.g = dy.permute(0, 2, 3, 1).contiguous()
+    tape.backward()
+    assert cv.g is not None and cv.g.shape == ctx.shape and rel(cv.g, g_ref) < 1e-4
+    # default: a plain tensor context gets no gradient work at all
+    tape = E.Tape()
+    out = eng.forward(tape, E.Var(ops.latent_to_nhwc(x, torch.float32, 64), False), t, ctx, lora_mode="frozen" if mode == "frozen" else "train")
+    out.g = dy.permute(0, 2, 3, 1).contiguous()
+    tape.backward()
+
+
+def test_engine_unet_module_returns_context_gradient_to_autograd(monkeypatch):
+    EMU.install(monkeypatch)
+    from comat_b200.modules import EngineUNet
+    unet = _tiny(False)
+    mod = EngineUNet(unet, torch.float32)
+    g = torch.Generator().manual_seed(2)
+    x, ctx = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 77, 64, generator=g)
+    t, dy = torch.tensor(300), torch.randn(2, 4, 16, 16, generator=g)
+    cr = ctx.clone().requires_grad_(True)
+    g_ref = torch.autograd.grad(unet(x, t, cr, return_dict=False)[0], cr, dy)[0]
+    c2 = ctx.clone().requires_grad_(True)
+    eps = mod(x, t, encoder_hidden_states=c2)[0]
+    (eps * dy).sum().backward()
+    assert rel(c2.grad, g_ref) < 1e-3
+    c3 = ctx.clone()                                             # no grad requested: the call returns None for the context
+    xr = x.clone().requires_grad_(True)
+    (mod(xr, t, encoder_hidden_states=c3)[0] * dy).sum().backward()
+    assert c3.grad is None and xr.grad is not None
