@@ -9,8 +9,15 @@ quick-GELU ``x * sigmoid(1.702 x)`` needs no kernel of its own: it equals ``silu
 ``alpha = 1.702`` (bias pre-scaled) and the SiLU epilogue, and fc2 with ``alpha = 1 / 1.702``.
 
 The parameter owner is an HF ``CLIPTextModel`` / ``CLIPTextModelWithProjection`` (real checkpoint or random init); weights are
-packed once.  Frozen path only: ``--tune_text_encoder`` / ``--train_text_encoder_lora`` (training_script.py:227-255) would need
-the UNet executor to emit d(encoder_hidden_states) and are rejected by the trainer.
+packed once.
+
+``--train_text_encoder_lora`` (training_script.py:227-255; SD1.5 form): ``install_text_lora`` puts a ``LoRALinearLayer(rank)`` on
+q_proj / k_proj / v_proj / out_proj of every block (the projections diffusers' ``LoraLoaderMixin._modify_text_encoder`` patches -
+un-vendored), and a grad-enabled call runs ``forward_taped``: the same kernels behind an explicit tape (projections un-fused so
+each carries its LoRA branch, attention backward with the causal mask), LoRA weight gradients returned to autograd, the data
+gradient arriving from the UNet executor's d(encoder_hidden_states).  Host logic checked against HF autograd on emulated ops
+(tests/test_text_encoder_cpu.py); this training path has NOT been run on the B200 yet.  ``--tune_text_encoder`` (full weights)
+is not implemented.
 """
 from __future__ import annotations
 
@@ -32,6 +39,34 @@ class _FusedQKV:
         b = torch.cat([attn.q_proj.bias.detach(), attn.k_proj.bias.detach(), attn.v_proj.bias.detach()], 0)
         self.w = w.to(dtype).contiguous()            # [3C, C] K-major
         self.bias = b.float().contiguous()
+
+
+def install_text_lora(model, rank: int, up_std: float = 0.0):
+    """LoRA(rank) on the attention projections of every CLIP block; fp32 masters, down ~ N(0, 1/rank), up = 0 (``up_std`` > 0 only
+    for gradient checks).  Returns the trainable parameters in module order (what ``get_trainable_parameters`` collects as
+    ``text_lora_parameters``, training_utils/pipeline.py:172-181)."""
+    from .containers import LoRALinearLayer
+    params = []
+    for lyr in model.text_model.encoder.layers:
+        for lin in (lyr.self_attn.q_proj, lyr.self_attn.k_proj, lyr.self_attn.v_proj, lyr.self_attn.out_proj):
+            l = LoRALinearLayer(lin.in_features, lin.out_features, rank).to(lin.weight.device, torch.float32)
+            if up_std > 0:
+                torch.nn.init.normal_(l.up.weight, std=up_std)
+            lin.lora_layer = l
+            params.extend(l.parameters())
+    return params
+
+
+def _quick_gelu(tape, x: E.Var) -> E.Var:
+    """x * sigmoid(1.702 x) = silu(1.702 x) / 1.702 with the elementwise kernels; d/dx = silu'(1.702 x)."""
+    s_ = ops.elementwise("scale", x.v, alpha=_QG)
+    out = E.Var(ops.elementwise("scale", ops.elementwise("silu", s_), alpha=1.0 / _QG))
+    if tape is not None:
+        def bwd():
+            if out.g is not None:
+                E._acc(x, ops.elementwise("silu_bwd", s_, out.g))
+        tape.record(bwd)
+    return out
 
 
 class ClipTextEngine:
@@ -57,9 +92,53 @@ class ClipTextEngine:
                 fc1.bias = (fc1.bias * _QG).contiguous()
             self.layers.append(dict(n1=E.NormW(lyr.layer_norm1), qkv=_FusedQKV(lyr.self_attn, dtype),
                                     out=E.LinW(lyr.self_attn.out_proj, dtype), n2=E.NormW(lyr.layer_norm2), fc1=fc1, fc2=fc2))
+        # training path: un-fused projections with their LoRA branches (built only when install_text_lora ran before packing)
+        self.loras, self.tlayers, self._arenas = [], [], None
+        if getattr(tm.encoder.layers[0].self_attn.q_proj, "lora_layer", None) is not None:
+            for lyr in tm.encoder.layers:
+                att = lyr.self_attn
+                lins = (att.q_proj, att.k_proj, att.v_proj, att.out_proj)
+                lw = [E.LoRAW(l.lora_layer, dtype) for l in lins]
+                self.loras.extend(lw)
+                self.tlayers.append(dict(lin=[E.LinW(l, dtype) for l in lins], lora=lw, fc1=E.LinW(lyr.mlp.fc1, dtype)))
         self.final_ln = E.NormW(tm.final_layer_norm)
         proj = getattr(model, "text_projection", None)
         self.proj = None if proj is None else proj.weight.detach().to(dtype).contiguous()      # [proj_dim, C], no bias
+
+    def refresh_lora(self):
+        """16-bit operand images of the LoRA factors follow the fp32 masters (call after every optimiser step)."""
+        if self.loras:
+            if self._arenas is None:
+                self._arenas = E._LoRAArenas(self.loras, self.dtype)
+            self._arenas.refresh()
+
+    def lora_params(self):
+        return [p for l in self.loras for p in (l.down, l.up)]
+
+    def forward_taped(self, tape, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> E.Var:
+        """taped forward with the LoRA branches explicit -> Var last_hidden_state (B, T, C); backward leaves d down / d up of
+        every adapter in ``lora.g_down / g_up``."""
+        from .blip_engine import _gelu, _mha
+        if not self.loras:
+            raise RuntimeError("forward_taped needs install_text_lora(model, rank) before the executor is built")
+        if self._arenas is None:
+            self.refresh_lora()
+        B, T = input_ids.shape
+        emb = (self.tok[input_ids] + self.pos[:T][None]).to(self.dtype).contiguous()
+        h = E.Var(emb, needs_grad=False)                      # embeddings are frozen: the tape ends at the first block's adapters
+        lens = (torch.full((B,), T, dtype=torch.int32, device=emb.device) if attention_mask is None
+                else attention_mask.sum(1).to(torch.int32).contiguous())
+        for L, TL in zip(self.layers, self.tlayers):
+            (lq, lk, lv, lo), (aq, ak, av, ao) = TL["lin"], TL["lora"]
+            y = E.layernorm(tape, h, L["n1"])
+            a = _mha(tape, E.linear(tape, y, lq, aq), E.linear(tape, y, lk, ak), E.linear(tape, y, lv, av), self.heads,
+                     kv_lens=lens, causal=True)
+            h = E.linear(tape, a, lo, ao, residual=h)
+            y = E.layernorm(tape, h, L["n2"])
+            f = E.linear(tape, y, TL["fc1"])
+            f = _quick_gelu(tape, f) if self.quick else _gelu(tape, f)
+            h = E.linear(tape, f, L["fc2"], residual=h)
+        return E.layernorm(tape, h, self.final_ln)
 
     def final_layer_norm(self, h: torch.Tensor) -> torch.Tensor:
         x = h.to(self.dtype).contiguous()
@@ -152,6 +231,33 @@ class _GraphedEncoder:
         return self.out                             # static buffers: the caller converts (copies) before the next replay
 
 
+class _TextLoRAFn(torch.autograd.Function):
+    """one autograd node for a grad-enabled encoder call: explicit tape inside, LoRA weight gradients out."""
+
+    @staticmethod
+    def forward(ctx, mod: "EngineCLIPText", ids, mask, *lora_params):
+        eng = mod.engine
+        tape = E.Tape()
+        for l in eng.loras:
+            l.wgrad, l.direct, l.g_down, l.g_up = True, False, None, None
+        out = eng.forward_taped(tape, ids, mask)
+        ctx.tape, ctx.out, ctx.mod = tape, out, mod
+        return out.v.float()
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.mod.engine
+        S = ctx.mod.grad_scale                       # static loss scaling of the 16-bit backward, as for the UNet
+        ctx.out.g = (g.float() * S).to(eng.dtype).contiguous()
+        ctx.tape.backward()
+        grads = []
+        for l in eng.loras:
+            grads += [None if l.g_down is None else l.g_down / S, None if l.g_up is None else l.g_up / S]
+            l.g_down = l.g_up = None
+        ctx.tape = ctx.out = None
+        return (None, None, None, *grads)
+
+
 class EngineCLIPText(torch.nn.Module):
     """HF call surface ``text_encoder(input_ids, attention_mask=None, output_hidden_states=False)`` backed by ``ClipTextEngine``.
     Outputs are fp32 (the pipelines' interface dtype, like ``EngineUNet.dtype``); the arithmetic is 16-bit on the tensor cores.
@@ -168,6 +274,16 @@ class EngineCLIPText(torch.nn.Module):
         self.text_model = SimpleNamespace(final_layer_norm=lambda h: self.engine.final_layer_norm(h).float())
         self.use_graphs = True
         self._graphs = {}
+        self.grad_scale = 4096.0 if dtype == torch.float16 else 1.0
+
+    def lora_parameters(self):
+        return self.engine.lora_params()
+
+    def refresh_lora(self):
+        """after an optimiser step on the text LoRA: new operand images; captured graphs of the (LoRA-free) frozen forward stay
+        valid only for encoders without adapters, so they are dropped here."""
+        self.engine.refresh_lora()
+        self._graphs = {}
 
     @property
     def dtype(self):
@@ -177,10 +293,25 @@ class EngineCLIPText(torch.nn.Module):
     def device(self):
         return self.engine.tok.device
 
-    @torch.no_grad()
     def forward(self, input_ids, attention_mask=None, output_hidden_states: bool = False, **_):
         ids = input_ids.to(self.device)
         mask = None if attention_mask is None else attention_mask.to(self.device)
+        params = self.engine.lora_params()
+        if params:
+            if output_hidden_states or self.with_projection:
+                raise NotImplementedError("text-encoder LoRA is implemented for the SD1.5 call form (last_hidden_state) only")
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                last = _TextLoRAFn.apply(self, ids, mask, *params)
+            else:                                     # adapters present but no gradient wanted: same executor, no tape kept
+                with torch.no_grad():
+                    last = self.engine.forward_taped(None, ids, mask).v.float()
+            eos = ids.to(torch.int32).argmax(-1) if self.engine.eos_token_id == 2 else (ids == self.engine.eos_token_id).int().argmax(-1)
+            pooled = last.detach()[torch.arange(ids.shape[0], device=last.device), eos]
+            return _TextOutput(last_hidden_state=last, pooler_output=pooled, hidden_states=None)
+        with torch.no_grad():
+            return self._frozen_forward(ids, mask, output_hidden_states)
+
+    def _frozen_forward(self, ids, mask, output_hidden_states):
         if self.use_graphs and ids.is_cuda:
             key = (tuple(ids.shape), mask is not None, bool(output_hidden_states))
             g = self._graphs.get(key)

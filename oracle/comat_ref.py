@@ -482,3 +482,17 @@ def encode_prompt_sdxl(text_encoder, text_encoder_2, tokenizer, tokenizer_2, pro
         npe = npe.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, L, -1)
         npp = npp.repeat(1, num_images_per_prompt).view(b * num_images_per_prompt, -1)
     return pe, npe, pp, npp
+
+
+def add_text_lora_hooks(model):
+    """text-encoder LoRA as the reference gets it from diffusers' ``_modify_text_encoder`` (training_script.py:227-255; un-vendored):
+    ``y = W x + up(down(x))`` on q_proj / k_proj / v_proj / out_proj of every CLIP block.  Implemented as forward hooks on the HF
+    module for every Linear that carries a ``lora_layer`` attribute (comat_b200.text_encoder.install_text_lora puts them there);
+    returns the hook handles."""
+    handles = []
+    for lyr in model.text_model.encoder.layers:
+        for lin in (lyr.self_attn.q_proj, lyr.self_attn.k_proj, lyr.self_attn.v_proj, lyr.self_attn.out_proj):
+            if getattr(lin, "lora_layer", None) is not None:
+                handles.append(lin.register_forward_hook(
+                    lambda m, inp, out: out + m.lora_layer.up(m.lora_layer.down(inp[0].to(m.lora_layer.down.weight.dtype))).to(out.dtype)))
+    return handles

@@ -227,3 +227,50 @@ def test_discriminator_encode_prompt_vs_reference(monkeypatch):
     null, pooled = D.encode_prompt("", torch.device("cpu"), 3, do_classifier_free_guidance=False)
     assert pooled is None and dp.text_encoder is None
     torch.testing.assert_close(null, null_ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("act", ["quick_gelu", "gelu"])
+def test_text_lora_taped_executor_matches_hf_autograd(monkeypatch, act):
+    """--train_text_encoder_lora building block: taped forward + backward of the CLIP executor with LoRA on q/k/v/out vs torch
+    autograd through the HF module carrying the same adapters (forward hooks): output, every d down / d up, and the frozen
+    (no-grad) call with adapters present."""
+    EMU.install_blip(monkeypatch)
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from comat_b200.text_encoder import EngineCLIPText, install_text_lora
+    torch.manual_seed(0)
+    model = CLIPTextModel(CLIPTextConfig(vocab_size=49408, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                                         max_position_embeddings=77, hidden_act=act, eos_token_id=2, bos_token_id=0, pad_token_id=1)).eval()
+    model.requires_grad_(False)
+    params = install_text_lora(model, 4, up_std=0.05)
+    assert len(params) == 2 * 4 * 2 and all(p.requires_grad and p.dtype == torch.float32 for p in params)
+    hooks = R.add_text_lora_hooks(model)
+    t = FX.ClipTokenizerStub()(["a photo of a cat", "two red cubes on a blue sphere", ""])
+    g = torch.Generator().manual_seed(3)
+    dy = torch.randn(3, 77, 128, generator=g)
+    ref = model(t.input_ids).last_hidden_state
+    g_ref = torch.autograd.grad(ref, params, dy)
+    for h in hooks:
+        h.remove()
+    enc = EngineCLIPText(model, torch.float32)
+    assert [id(p) for p in enc.lora_parameters()] == [id(p) for p in params]
+    out = enc(t.input_ids)
+    last = out[0]
+    assert last.requires_grad
+    torch.testing.assert_close(last, ref, rtol=1e-4, atol=1e-5)
+    got = torch.autograd.grad(last, params, dy)
+    for a, b in zip(got, g_ref):
+        assert float((a - b).norm() / b.norm().clamp_min(1e-12)) < 1e-4
+    with torch.no_grad():                                        # adapters present, no gradient wanted
+        frozen = enc(t.input_ids)[0]
+    assert not frozen.requires_grad
+    torch.testing.assert_close(frozen, ref.detach(), rtol=1e-4, atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        enc(t.input_ids, output_hidden_states=True)
+    # optimiser step -> refresh: the executor follows the new masters
+    with torch.no_grad():
+        for p in params:
+            p.mul_(1.5)
+    enc.refresh_lora()
+    hooks = R.add_text_lora_hooks(model)
+    with torch.no_grad():
+        torch.testing.assert_close(enc(t.input_ids)[0], model(t.input_ids).last_hidden_state, rtol=1e-4, atol=1e-5)
