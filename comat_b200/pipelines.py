@@ -155,10 +155,11 @@ class TrainableSDPipeline:
         T = list(training_timesteps)
         prev = torch.is_grad_enabled()
         try:
-            torch.set_grad_enabled(False)
+            torch.set_grad_enabled(bool(train_text_encoder))                            # :72 / :728
             prompt_embeds, negative_prompt_embeds = self._encode_for_forward(
                 prompt, device, num_images_per_prompt, cfg, negative_prompt, prompt_embeds, negative_prompt_embeds, sdxl_kwargs)
             embeds = torch.cat([negative_prompt_embeds, prompt_embeds]) if cfg else prompt_embeds
+            torch.set_grad_enabled(False)
             added = self._added_cond(batch_size * num_images_per_prompt, height, width, cfg, added_cond_kwargs, sdxl_kwargs)
             self.scheduler.set_timesteps(num_inference_steps, device=device)
             timesteps = self.scheduler.timesteps

@@ -101,6 +101,9 @@ def synthetic_components(args, device, dtype=torch.float16, tiny: bool = False, 
     else:
         unet = tiny_unet(seed) if tiny else synthetic.build_sd15(device, dtype, rank=rank, seed=seed)[0]
         clip = synthetic.build_clip_text(device, torch.float32, seed=seed + 1, which="clip_l", tiny=tiny)
+        if getattr(args, "train_text_encoder_lora", False):                           # pipeline.py:117-119 _modify_text_encoder(rank)
+            from .text_encoder import install_text_lora
+            install_text_lora(clip, rank)
         cls = P.AttrConcenTrainableSDPipeline if "attrcon" in name else P.TrainableSDPipeline
         pipe = cls(EngineVAE(vae, dtype), EngineUNet(unet, dtype), text_encoder=EngineCLIPText(clip, dtype),
                    tokenizer=synthetic.SyntheticClipTokenizer())

@@ -31,12 +31,23 @@ class CoMatTrainer:
         # ``attr_provider(prompts, images in [0,1]) -> (words, masks)``: the Grounded-SAM + spaCy seam (training_script.py:627-637
         # segments the image generated IN this step); used when the batch does not carry ``words`` / ``masks`` itself
         self.attr_provider = attr_provider
-        if getattr(args, "tune_text_encoder", False) or getattr(args, "train_text_encoder_lora", False):
-            # training_script.py:227-255,569-573: needs d(encoder_hidden_states) out of the UNet executor - not built
-            raise NotImplementedError("--tune_text_encoder / --train_text_encoder_lora: the text encoders are frozen on this path")
+        if getattr(args, "tune_text_encoder", False):
+            raise NotImplementedError("--tune_text_encoder: full text-encoder weight gradients are not implemented (LoRA only)")
         self.null_embed = self.pooled_null_embed = self.gan_null_embed = None
+        # --train_text_encoder_lora (training_script.py:227-255): the text LoRA joins G_parameters - one AdamW, one joint gradient-norm
+        # clip (:661 clips self.G_parameters, which includes them).  Host logic checked on emulated ops; not yet run on the B200.
+        self.train_text = bool(getattr(args, "train_text_encoder_lora", False))
+        self.text_parameters = []
+        if self.train_text:
+            enc = getattr(pipeline, "text_encoder", None)
+            self.text_parameters = list(enc.lora_parameters()) if hasattr(enc, "lora_parameters") else []
+            if pipeline.is_sdxl or not self.text_parameters:
+                raise NotImplementedError("--train_text_encoder_lora needs an SD1.5 pipeline whose text encoder was built after "
+                                          "comat_b200.text_encoder.install_text_lora(model, rank)")
+            if args.textenc_lora_lr is not None and args.textenc_lora_lr != args.learning_rate:
+                raise NotImplementedError("--textenc_lora_lr different from --learning_rate needs a per-group rate in the fused AdamW kernel")
         self.rng = rng or random.Random(args.seed)
-        self.G_parameters = list(pipeline.unet.lora_parameters())                 # training_utils/pipeline.py:123-143
+        self.G_parameters = list(pipeline.unet.lora_parameters()) + self.text_parameters   # training_utils/pipeline.py:123-143, :172-181
         self.optimizer = FlatAdamW(self.G_parameters, lr=args.learning_rate, betas=(args.adam_beta1, args.adam_beta2),
                                    weight_decay=args.adam_weight_decay, eps=args.adam_epsilon,
                                    max_grad_norm=args.max_grad_norm, process_group=process_group)
@@ -98,6 +109,8 @@ class CoMatTrainer:
         handle = self.optimizer.all_reduce()                                         # the only data-path collective
         self.optimizer.step(handle)                                                  # :661-663 (clip folded in)
         self._refresh(self.pipeline.unet)
+        if self.train_text:
+            self.pipeline.text_encoder.refresh_lora()
 
     @staticmethod
     def _refresh(unet):
@@ -130,6 +143,10 @@ class CoMatTrainer:
 
     def _null(self, batch, key, attr):
         v = batch.get(key)
+        if v is None and self.train_text and key == "null_embeds":
+            # :569-573: with a trained text encoder the '' embedding is re-encoded every step, inside the autograd graph
+            return self.pipeline.encode_prompt("", self.pipeline._execution_device, self.args.train_batch_size,
+                                               do_classifier_free_guidance=False)[0]
         if v is None:
             if getattr(self, attr) is None:
                 self.prepare_null_embeds()
@@ -153,7 +170,7 @@ class CoMatTrainer:
         if steps is None:
             steps, attr = self.select_steps()
         kwargs = dict(prompt=batch.get("text"), prompt_embeds=batch.get("prompt_embeds"), height=a.resolution, width=a.resolution,
-                      training_timesteps=steps, detach_gradient=True, train_text_encoder=False,
+                      training_timesteps=steps, detach_gradient=True, train_text_encoder=self.train_text,
                       num_inference_steps=a.total_step, guidance_scale=a.cfg_scale, guidance_rescale=a.cfg_rescale,
                       negative_prompt_embeds=self._null(batch, "null_embeds", "null_embed") if a.do_classifier_free_guidance else None,
                       early_exit=False, return_latents=bool(a.gan_loss), latents=batch.get("init_latents"),

@@ -217,7 +217,7 @@ def test_record_grad_hook_vs_reference(norm_grad):
     tr = CoMatTrainer.__new__(CoMatTrainer)
     tr.args = argparse.Namespace(norm_grad=norm_grad, resolution=16, gan_loss=False, cfg_scale=7.5, cfg_rescale=0.0, total_step=1,
                                  do_classifier_free_guidance=False)
-    tr.attrcon, tr.D, tr.rng = False, None, None
+    tr.attrcon, tr.D, tr.rng, tr.train_text = False, None, None, False
     image = torch.zeros(2, 3, 16, 16, requires_grad=True)
     leaf = image * 1.0
     tr.pipeline = type("P", (), {"is_sdxl": False, "attn_dict": {}, "forward": lambda self, **kw: leaf})()

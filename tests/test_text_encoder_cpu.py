@@ -274,3 +274,69 @@ def test_text_lora_taped_executor_matches_hf_autograd(monkeypatch, act):
     hooks = R.add_text_lora_hooks(model)
     with torch.no_grad():
         torch.testing.assert_close(enc(t.input_ids)[0], model(t.input_ids).last_hidden_state, rtol=1e-4, atol=1e-5)
+
+
+def test_trainer_text_lora_gradients_equal_the_chain_rule(monkeypatch):
+    """--train_text_encoder_lora end to end on emulated ops: one ``loss.backward()`` through trainer -> pipeline -> UNet executor
+    (d encoder_hidden_states) -> taped text encoder must give the text-LoRA gradients that the chain rule gives when the same
+    step is cut at the embeddings (d loss / d embeddings from a run with leaf embeddings, pushed through the encoder alone)."""
+    from tests.test_trainer_logic_cpu import _emulate_cuda_only
+    _emulate_cuda_only(monkeypatch)
+    EMU.install_blip(monkeypatch)
+    from comat_b200 import containers as Cn, synthetic
+    from comat_b200.caption import Blip, CaptionModelWrapper
+    from comat_b200.modules import EngineUNet, EngineVAE
+    from comat_b200.pipelines import TrainableSDPipeline
+    from comat_b200.text_encoder import EngineCLIPText, install_text_lora
+    from comat_b200.trainer import CoMatTrainer
+    B, S, res = 2, 2, 64
+    torch.manual_seed(0)
+    unet = Cn.UNet2DConditionModel(block_out_channels=(64, 128, 256, 256), heads=4, cross_attention_dim=128)
+    vae = Cn.AutoencoderKL(block_out_channels=(64, 64, 128, 128))
+    unet.requires_grad_(False); vae.requires_grad_(False)
+    unet.install_lora(4, up_std=0.05)
+    clip = R.make_clip_text("clip_l", tiny=True, seed=21)
+    tparams = install_text_lora(clip, 4, up_std=0.05)
+    args = synthetic.default_args(pretrain_model_name="sd_1_5", train_batch_size=B, K=1, total_step=S, gan_loss=False, resolution=res, seed=3,
+                                  train_text_encoder_lora=True)
+    enc = EngineCLIPText(clip, torch.float32)
+    pipe = TrainableSDPipeline(EngineVAE(vae, torch.float32), EngineUNet(unet, torch.float32), text_encoder=enc,
+                               tokenizer=synthetic.SyntheticClipTokenizer())
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(R.make_blip(large=False))), None)
+    assert tr.train_text and len(tr.G_parameters) == 256 + len(tparams) and tr.optimizer.n == sum(p.numel() for p in tr.G_parameters)
+    prompts = ["a red apple on a table", "two dogs"]
+    g = torch.Generator().manual_seed(9)
+    ids, mask = FX.blip_token_batch(g, B, 8)
+    base = dict(blip={"input_ids": ids, "attention_mask": mask}, init_latents=torch.randn(B, 4, res // 8, res // 8, generator=g),
+                noises=[torch.randn(B, 4, res // 8, res // 8, generator=g) for _ in range(S)], training_steps=[1], attrcon_steps=None, crop=(0, 0))
+    # (1) one backward through everything
+    tr.optimizer.zero_grad()
+    loss = tr.g_losses(dict(base, text=prompts))["loss"]
+    loss.backward()
+    tr.pipeline.unet.finalize_lora_grads()
+    got = [p.grad.clone() for p in tparams]
+    assert max(float(x.abs().max()) for x in got) > 0
+    # (2) the same step cut at the embeddings
+    tok = synthetic.SyntheticClipTokenizer()
+    pe = enc(tok(prompts).input_ids)[0]
+    null = enc(tok([""] * B).input_ids)[0]
+    pe_leaf, null_leaf = pe.detach().requires_grad_(True), null.detach().requires_grad_(True)
+    tr.optimizer.zero_grad()
+    # embeddings come in as leaves (train_text stays on so the pipeline keeps autograd enabled around the embedding plumbing)
+    loss2 = tr.g_losses(dict(base, prompt_embeds=pe_leaf, null_embeds=null_leaf))["loss"]
+    assert abs(float(loss2.detach()) - float(loss.detach())) < 1e-5 * abs(float(loss.detach()))
+    d_pe, d_null = torch.autograd.grad(loss2, [pe_leaf, null_leaf])
+    want = torch.autograd.grad([pe, null], tparams, [d_pe, d_null])
+    for a, b in zip(got, want):
+        assert float((a - b).norm()) <= 2e-3 * float(b.norm()) + 1e-9
+    # (3) a full step moves the text adapters and refreshes the executor's operand images
+    before = [p.detach().clone() for p in tparams]
+    tr.train_step(dict(base, text=prompts))
+    assert any(not torch.equal(a, b) for a, b in zip(before, tparams))
+    l0 = enc.engine.loras[0]
+    assert torch.equal(l0.down16.float(), l0.down.detach().to(l0.down16.dtype).float())
+    # refusals
+    with pytest.raises(NotImplementedError):
+        CoMatTrainer(synthetic.default_args(pretrain_model_name="sd_1_5", tune_text_encoder=True), pipe, None, None)
+    with pytest.raises(NotImplementedError):
+        CoMatTrainer(synthetic.default_args(pretrain_model_name="sd_1_5", train_text_encoder_lora=True, textenc_lora_lr=1e-6), pipe, None, None)
