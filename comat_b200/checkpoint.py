@@ -45,13 +45,30 @@ def unet_lora_state_dict(unet) -> Dict[str, torch.Tensor]:
     return out
 
 
+def text_encoder_lora_state_dict(text_encoder) -> Dict[str, torch.Tensor]:
+    """diffusers' ``text_encoder_lora_state_dict`` (training_script.py:388-389; un-vendored, restated from the 0.22-0.25 sources):
+    ``text_model.encoder.layers.<i>.self_attn.<q|k|v|out>_proj.lora_linear_layer.<down|up>.weight`` -> parameter."""
+    model = getattr(text_encoder, "ref", text_encoder)
+    out = {}
+    for i, lyr in enumerate(model.text_model.encoder.layers):
+        for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            lora = getattr(getattr(lyr.self_attn, proj), "lora_layer", None)
+            if lora is not None:
+                for matrix, p in lora.state_dict().items():
+                    out[f"text_model.encoder.layers.{i}.self_attn.{proj}.lora_linear_layer.{matrix}"] = p
+    return out
+
+
 def save_lora_weights(save_directory: str, unet_lora_layers: Dict[str, torch.Tensor], diffusers_prefix: bool = True,
-                      weight_name: str = LORA_FILE) -> str:
-    """``LoraLoaderMixin.save_lora_weights(save_directory=..., unet_lora_layers=...)`` as called at training_script.py:397-401."""
+                      weight_name: str = LORA_FILE, text_encoder_lora_layers: Optional[Dict[str, torch.Tensor]] = None) -> str:
+    """``LoraLoaderMixin.save_lora_weights(save_directory=..., unet_lora_layers=..., text_encoder_lora_layers=...)`` as called at
+    training_script.py:397-401: one file, ``unet.`` / ``text_encoder.`` prefixed entries."""
     from safetensors.torch import save_file
     os.makedirs(save_directory, exist_ok=True)
     sd = {(f"unet.{k}" if diffusers_prefix else k): v.detach().to("cpu", torch.float32).contiguous()
           for k, v in unet_lora_layers.items()}
+    for k, v in (text_encoder_lora_layers or {}).items():
+        sd[f"text_encoder.{k}"] = v.detach().to("cpu", torch.float32).contiguous()
     path = os.path.join(save_directory, weight_name)
     save_file(sd, path, metadata={"format": "pt"})
     return path
@@ -65,11 +82,35 @@ def lora_state_dict(path: str) -> Dict[str, torch.Tensor]:
     out = {}
     for k, v in load_file(path).items():
         if k.startswith("text_encoder"):
-            raise NotImplementedError("text-encoder LoRA entries (--train_text_encoder_lora) are not supported on this path")
+            continue                                    # read by text_lora_state_dict
         while k.startswith("unet."):
             k = k[len("unet."):]
         out[k] = v
     return out
+
+
+def text_lora_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """the ``text_encoder.`` entries of a LoRA file, prefix stripped (``load_lora_into_text_encoder``'s input, :183-185)."""
+    from safetensors.torch import load_file
+    if os.path.isdir(path):
+        path = os.path.join(path, LORA_FILE)
+    return {k[len("text_encoder."):]: v for k, v in load_file(path).items() if k.startswith("text_encoder.")}
+
+
+def load_lora_into_text_encoder(state: Dict[str, torch.Tensor], text_encoder) -> int:
+    """copy stored text-encoder LoRA factors into the installed adapters (in place); every stored tensor must find its adapter."""
+    mine = text_encoder_lora_state_dict(text_encoder)
+    missing = set(state) - set(mine)
+    if missing or set(mine) - set(state):
+        raise KeyError(f"text-encoder LoRA mismatch: {sorted(missing)[:3]} not in the model / {sorted(set(mine) - set(state))[:3]} not in the file")
+    with torch.no_grad():
+        for k, t in state.items():
+            if tuple(mine[k].shape) != tuple(t.shape):
+                raise ValueError(f"{k}: checkpoint shape {tuple(t.shape)} vs model {tuple(mine[k].shape)}")
+            mine[k].copy_(t.to(mine[k].device, mine[k].dtype))
+    if hasattr(text_encoder, "refresh_lora"):
+        text_encoder.refresh_lora()
+    return len(state)
 
 
 def load_lora_into_unet(state: Dict[str, torch.Tensor], unet) -> int:
@@ -137,7 +178,8 @@ def save_checkpoint(trainer, output_dir: str, global_step: Optional[int] = None,
     path = checkpoint_dir(output_dir, step)
     if hasattr(trainer, "sync"):
         trainer.sync()                                 # outstanding side-stream optimiser tails land before the parameters are read
-    save_lora_weights(path, unet_lora_state_dict(trainer.pipeline.unet), diffusers_prefix)
+    text = text_encoder_lora_state_dict(trainer.pipeline.text_encoder) if getattr(trainer, "train_text", False) else None     # :386-389
+    save_lora_weights(path, unet_lora_state_dict(trainer.pipeline.unet), diffusers_prefix, text_encoder_lora_layers=text)
     if trainer.D is not None:
         d_dir = os.path.join(path, "D_sd")
         save_lora_weights(d_dir, unet_lora_state_dict(trainer.D.unet), diffusers_prefix)
@@ -166,6 +208,8 @@ def load_checkpoint(trainer, path_or_output_dir: str, resume: str = "latest") ->
     if hasattr(trainer, "sync"):
         trainer.sync()
     load_lora_into_unet(lora_state_dict(os.path.join(path, LORA_FILE)), trainer.pipeline.unet)
+    if getattr(trainer, "train_text", False):                                       # :182-185
+        load_lora_into_text_encoder(text_lora_state_dict(os.path.join(path, LORA_FILE)), trainer.pipeline.text_encoder)
     with_d = trainer.D is not None and resume == "latest"
     if with_d:
         load_lora_into_unet(lora_state_dict(os.path.join(path, "D_sd", LORA_FILE)), trainer.D.unet)

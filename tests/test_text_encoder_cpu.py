@@ -340,3 +340,33 @@ def test_trainer_text_lora_gradients_equal_the_chain_rule(monkeypatch):
         CoMatTrainer(synthetic.default_args(pretrain_model_name="sd_1_5", tune_text_encoder=True), pipe, None, None)
     with pytest.raises(NotImplementedError):
         CoMatTrainer(synthetic.default_args(pretrain_model_name="sd_1_5", train_text_encoder_lora=True, textenc_lora_lr=1e-6), pipe, None, None)
+
+
+def test_text_lora_checkpoint_entries_round_trip(tmp_path, monkeypatch):
+    """training_script.py:386-401,182-185: text-encoder LoRA entries share pytorch_lora_weights.safetensors with the UNet's, under the
+    ``text_encoder.`` prefix and diffusers' ``...self_attn.<proj>.lora_linear_layer.<down|up>.weight`` names (un-vendored, restated)."""
+    EMU.install_blip(monkeypatch)
+    from safetensors import safe_open
+    from comat_b200 import checkpoint as CK, synthetic
+    from comat_b200.text_encoder import EngineCLIPText, install_text_lora
+    a, b = R.make_clip_text("clip_l", tiny=True, seed=1), R.make_clip_text("clip_l", tiny=True, seed=1)
+    install_text_lora(a, 4, up_std=0.05)
+    torch.manual_seed(9)
+    install_text_lora(b, 4, up_std=0.01)
+    unet, _ = synthetic.build_sd15("cpu", torch.float32, rank=4, seed=1, tiny=True)
+    ea, eb = EngineCLIPText(a, torch.float32), EngineCLIPText(b, torch.float32)
+    sd = CK.text_encoder_lora_state_dict(ea)
+    assert len(sd) == 2 * 4 * 2 and "text_model.encoder.layers.1.self_attn.out_proj.lora_linear_layer.up.weight" in sd
+    path = CK.save_lora_weights(str(tmp_path), CK.unet_lora_state_dict(unet), text_encoder_lora_layers=sd)
+    with safe_open(path, "pt") as f:
+        names = list(f.keys())
+    assert sum(n.startswith("text_encoder.text_model.") for n in names) == 16 and sum(n.startswith("unet.unet.") for n in names) == 256
+    assert len(CK.lora_state_dict(str(tmp_path))) == 256                       # the UNet reader skips the text entries
+    assert CK.load_lora_into_text_encoder(CK.text_lora_state_dict(str(tmp_path)), eb) == 16
+    for x, y in zip(ea.lora_parameters(), eb.lora_parameters()):
+        assert torch.equal(x, y)
+    ids = FX.ClipTokenizerStub()(["a cat"]).input_ids
+    with torch.no_grad():
+        torch.testing.assert_close(ea(ids)[0], eb(ids)[0])                         # the executor of b follows the loaded adapters
+    with pytest.raises(KeyError):
+        CK.load_lora_into_text_encoder({"text_model.encoder.layers.9.self_attn.q_proj.lora_linear_layer.up.weight": torch.zeros(1)}, eb)
