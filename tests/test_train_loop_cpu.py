@@ -202,3 +202,34 @@ def test_compute_dtype_follows_mixed_precision_flag():
     for bad in (dict(mixed_precision="no"), dict(use_8bit_adam=True), dict(optimizer_class="Lion")):
         with pytest.raises(NotImplementedError):
             compute_dtype(synthetic.default_args(**bad))
+
+
+def test_entry_point_with_text_encoder_lora(tmp_path, monkeypatch):
+    """--train_text_encoder_lora through the entry point: adapters installed before packing, trained with the UNet LoRA, written
+    to / restored from the shared safetensors file."""
+    from tests.test_trainer_logic_cpu import _emulate_cuda_only
+    from tests import cpu_ops_emulation as EMU
+    _emulate_cuda_only(monkeypatch)
+    EMU.install_blip(monkeypatch)
+    from safetensors import safe_open
+    from comat_b200 import synthetic
+    from comat_b200.train import Trainer
+    prompts = tmp_path / "prompts.txt"
+    prompts.write_text("a red apple\ntwo dogs on a sofa\na blue car\n")
+    out = str(tmp_path / "run")
+
+    def mk(steps, resume):
+        a = synthetic.default_args(pretrain_model_name="sd_1_5", train_batch_size=1, K=1, total_step=2, resolution=64, training_prompts=str(prompts),
+                                   output_dir=out, max_train_steps=steps, validation_steps=100, resume_from_checkpoint=resume, seed=3,
+                                   gradient_accumulation_steps=1, train_text_encoder_lora=True)
+        return Trainer(a, None, torch.device("cpu"), weights="synthetic_tiny", dtype=torch.float32)
+    tr = mk(2, None)
+    text = tr.core.text_parameters
+    assert len(text) == 2 * 4 * 2 and tr.core.optimizer.n == sum(p.numel() for p in tr.core.G_parameters)
+    up0 = [p.detach().clone() for p in text[1::2]]               # the zero-initialised `up` factors
+    assert tr.train() == 2
+    assert any(float((a - b).abs().max()) > 0 for a, b in zip(up0, text[1::2]))
+    with safe_open(os.path.join(out, "checkpoint-2", "pytorch_lora_weights.safetensors"), "pt") as f:
+        assert sum(k.startswith("text_encoder.") for k in f.keys()) == 16
+    tr2 = mk(3, "latest")
+    assert tr2.global_step == 2 and all(torch.equal(a, b) for a, b in zip(text, tr2.core.text_parameters))
