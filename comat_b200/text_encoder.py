@@ -70,7 +70,8 @@ def _quick_gelu(tape, x: E.Var) -> E.Var:
 
 
 class ClipTextEngine:
-    """forward-only executor (no tape: the encoders are frozen on the CoMat path, training_script.py:210-226)."""
+    """``forward``: the frozen encoder of the CoMat path (training_script.py:210-226) - fused q|k|v, no tape, CUDA-graph friendly.
+    ``forward_taped``: the same network with un-fused projections and explicit LoRA branches for ``--train_text_encoder_lora``."""
 
     def __init__(self, model, dtype=torch.float16):
         cfg = model.config
