@@ -2,30 +2,25 @@
 export (the hooked forward of attn_utils/tc_attn_utils.py:104-161 hands P to the AttentionStore) and a backward that
 accepts an extra dP from the attention-map loss.
 
-IMPL:
-  "native" — hand-written tcgen05 kernels (csrc/attention.cu) through the C ABI.
-  "torch"  — library path (aten SDPA / bmm+softmax), kept ONLY as the bring-up comparator for shapes the native
-             kernel does not cover yet; every use is counted in LIBRARY_CALLS and reported by bench.py.
+Every call runs the hand-written tcgen05 kernels (csrc/attention.cu, csrc/attention_bwd.cu) through the C ABI; a shape
+they do not cover raises.  There is no library (aten) path in the product: the torch comparator the CPU logic tests run
+the executors on lives in tests/cpu_ops_emulation.py.
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 import ctypes as C
 
 from . import _lib
 
-IMPL = "native"          # forward and backward: tcgen05 kernels for every head dim in NATIVE_HEAD_DIMS (all shapes of the step)
-LIBRARY_CALLS = 0
-ALLOW_LIBRARY_PATH = False   # the aten comparator below is opt-in (tests switch it on); the product raises instead of falling back
+LIBRARY_CALLS = 0        # always 0: kept so bench.py's per-module sum stays meaningful if a library call is ever introduced
 NATIVE_HEAD_DIMS = (16, 32, 40, 64, 80, 128, 160)
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 _lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
 _lib.register_signature("comat_attention_fwd_strided", [_vp] * 7 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _vp])
 _lib.register_signature("comat_attention_bwd", [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
 _lib.register_signature("comat_attention_bwd_strided", [_vp] * 12 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _vp])
-NATIVE_BWD = True
 _DT = {torch.float16: 1, torch.bfloat16: 2}
 
 
@@ -102,37 +97,18 @@ def attention_unfused_bwd(q, k, v, ps, do):
 
 def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
     """q: (n, Lq, C), k/v: (n, Lk, C) 16-bit.  returns (o (n, Lq, C), probs fp32 (n*heads, Lq, Lk) | None, saved)"""
-    global LIBRARY_CALLS
-    if (IMPL == "native" and heads == 1 and not export_probs and q.is_cuda and q.dtype in _DT and q.shape[-1] > 160
+    if (heads == 1 and not export_probs and q.is_cuda and q.dtype in _DT and q.shape[-1] > 160
             and q.shape[-1] % 64 == 0 and k.shape[1] % 8 == 0 and k.shape[1] <= 8192):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         o, ps = attention_unfused_fwd(q, k, v)
         return o, None, (("unfused", q, k, v, ps) if need_bwd else None)
-    if IMPL == "native" and native_supported(q, k, heads, export_probs):
-        o, probs, lse = attention_fwd_native(q, k, v, heads, export_probs, need_lse=need_bwd and NATIVE_BWD)
-        if not need_bwd:
-            return o, probs, None
-        if NATIVE_BWD:
-            return o, probs, ("native", q, k, v, o, lse, probs, heads)      # strided views are read in place by the backward too
-        return o, probs, (q, k, v, heads, export_probs)
-    if not ALLOW_LIBRARY_PATH:
+    if not native_supported(q, k, heads, export_probs):
         raise _lib.ComatError(f"attention: no native kernel for this call (device {q.device.type}, dtype {q.dtype}, head dim "
                               f"{q.shape[-1] // heads}, keys {k.shape[1]}, export={export_probs}); comat_b200 has no fallback path")
-    LIBRARY_CALLS += 1
-    n, Lq, Cc = q.shape
-    d = Cc // heads
-    qh, kh, vh = _split(q, heads), _split(k, heads), _split(v, heads)
-    probs = None
-    if export_probs:
-        s = torch.matmul(qh.float(), kh.float().transpose(-1, -2)) * d ** -0.5
-        p = s.softmax(-1)
-        probs = p.reshape(n * heads, Lq, -1)
-        o = torch.matmul(p.to(q.dtype), vh)
-    else:
-        o = F.scaled_dot_product_attention(qh, kh, vh)
-    o = o.permute(0, 2, 1, 3).reshape(n, Lq, Cc).contiguous()
-    saved = (q, k, v, heads, export_probs) if need_bwd else None
-    return o, probs, saved
+    o, probs, lse = attention_fwd_native(q, k, v, heads, export_probs, need_lse=need_bwd)
+    if not need_bwd:
+        return o, probs, None
+    return o, probs, ("native", q, k, v, o, lse, probs, heads)          # strided views are read in place by the backward too
 
 
 def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None, causal=False):
@@ -162,31 +138,8 @@ def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None
 
 
 def attention_bwd(saved, do, dprobs):
-    global LIBRARY_CALLS
     if saved[0] == "unfused":
         _, q, k, v, ps = saved
         return attention_unfused_bwd(q, k, v, ps, do)
-    if saved[0] == "native":
-        _, q, k, v, o, lse, probs, heads = saved
-        return attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs)
-    LIBRARY_CALLS += 1
-    q, k, v, heads, export = saved
-    n, Lq, Cc = q.shape
-    d = Cc // heads
-    with torch.enable_grad():
-        q_, k_, v_ = (t.detach().requires_grad_(True) for t in (q, k, v))
-        qh, kh, vh = _split(q_, heads), _split(k_, heads), _split(v_, heads)
-        if export:
-            s = torch.matmul(qh.float(), kh.float().transpose(-1, -2)) * d ** -0.5
-            p = s.softmax(-1)
-            o = torch.matmul(p.to(q.dtype), vh).permute(0, 2, 1, 3).reshape(n, Lq, Cc)
-            outs, grads = [], []
-            if do is not None:
-                outs.append(o); grads.append(do)
-            if dprobs is not None:
-                outs.append(p.reshape(n * heads, Lq, -1)); grads.append(dprobs)
-            dq, dk, dv = torch.autograd.grad(outs, (q_, k_, v_), grads)
-        else:
-            o = F.scaled_dot_product_attention(qh, kh, vh).permute(0, 2, 1, 3).reshape(n, Lq, Cc)
-            dq, dk, dv = torch.autograd.grad(o, (q_, k_, v_), do)
-    return dq.contiguous(), dk.contiguous(), dv.contiguous()
+    _, q, k, v, o, lse, probs, heads = saved
+    return attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs)

@@ -144,6 +144,8 @@ class BlipEngine:
         self.dec_wt = wt
         self.dec_b = (head.decoder.bias if head.decoder.bias is not None else head.bias).detach().float().contiguous()
         self.eps_ls = float(getattr(model.text_decoder, "label_smoothing", getattr(cfg_t, "label_smoothing", 0.0)))
+        # loss scale of the fp16 backward (activation gradients of the frozen tower underflow otherwise); halved by the trainer after an overflow
+        self.grad_scale = 16384.0 if dtype == torch.float16 else 1.0
 
     # ------------------------------------------------------------------------------------------------
     def vision(self, tape, pix: E.Var) -> E.Var:
@@ -228,12 +230,12 @@ class _BlipLossFn(torch.autograd.Function):
         tape = E.Tape() if need else None
         pv = E.Var(pix.to(eng.dtype).contiguous())
         loss = eng.caption_loss_tape(tape, pv, ids, mask, labels)
-        ctx.tape, ctx.pv, ctx.loss, ctx.dt, ctx.eng_dtype = tape, pv, loss, pix.dtype, eng.dtype
+        ctx.tape, ctx.pv, ctx.loss, ctx.dt, ctx.eng = tape, pv, loss, pix.dtype, eng
         return loss.v.reshape(()).clone()
 
     @staticmethod
     def backward(ctx, g):
-        S = 16384.0 if ctx.eng_dtype == torch.float16 else 1.0   # static loss scaling: fp16 activation gradients of the frozen tower underflow otherwise
+        S = ctx.eng.grad_scale
         ctx.loss.g = (g.reshape(1).float() * S).contiguous()
         ctx.tape.backward()
         gp = (ctx.pv.g.float() / S).to(ctx.dt) if ctx.pv.g is not None else None

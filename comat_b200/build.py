@@ -39,7 +39,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     for f in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "comat_b200.h")]:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())      # path-independent: the GPU box runs from another directory
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -49,6 +49,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:          # torchrun: every rank may get here at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+            return LIB                                                   # another rank built it while we waited
+        return _build_locked(dig, verbose)
+
+
+def _build_locked(dig: str, verbose: bool) -> str:
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)

@@ -4,10 +4,9 @@ Mirrors ``Blip`` (concept_mat_utils/caption_blip.py:14-59) and ``CaptionModelWra
 Tokenisation is outside the hot path (no vocabulary on disk offline): token ids are passed in ``input_ids`` /
 ``attention_mask`` (the reference forwards ``**batch`` into ``score``).
 
-Backends for the captioner network itself:
-  * ``BlipEngine`` (comat_b200/blip_engine.py) — native executor on the tcgen05 GEMM / attention / LayerNorm kernels;
-  * an HF ``BlipForConditionalGeneration`` module — library path used for bring-up comparison only (counted in
-    ``LIBRARY_CALLS``).
+The captioner network itself is a ``BlipEngine`` (comat_b200/blip_engine.py: native executor on the tcgen05 GEMM / attention /
+LayerNorm kernels) or any object with its ``caption_loss(pixel_values, input_ids, attention_mask, labels)`` method; an HF module
+is refused (no library path in the product - tests/hf_blip.py wraps one as the comparator).
 """
 from __future__ import annotations
 
@@ -25,7 +24,7 @@ LIBRARY_CALLS = 0
 
 class Blip(torch.nn.Module):
     def __init__(self, model, device=None, prompt_length: int = 4, pad_token_id: int = 0, tokenizer=None):
-        """``model``: a BlipEngine or an HF BlipForConditionalGeneration (frozen, caption_blip.py:20-21).
+        """``model``: a BlipEngine (frozen weights, caption_blip.py:20-21).
         ``prompt_length`` = len(tok("a photography of").input_ids) - 1 (caption_blip.py:38-39) = 4 for BERT wordpieces.
         ``tokenizer`` (optional, the BLIP processor's BertTokenizer protocol): lets ``score`` take prompt strings (:47-48)."""
         super().__init__()
@@ -37,15 +36,15 @@ class Blip(torch.nn.Module):
         if tokenizer is not None:
             self.prompt_length = len(tokenizer(self.prompt).input_ids) - 1
             self.pad_token_id = tokenizer.pad_token_id
-        for p in getattr(model, "parameters", lambda: [])():
-            p.requires_grad = False
+        if not hasattr(model, "caption_loss"):
+            raise TypeError("Blip needs a comat_b200.blip_engine.BlipEngine (or an object with its caption_loss method); an HF "
+                            "BlipForConditionalGeneration is not executed by the product - wrap it: BlipEngine(model, dtype)")
 
     def preprocess(self, images: torch.Tensor) -> torch.Tensor:
         """Resize((384,384), BICUBIC, antialias) + Normalize(CLIP mean/std), differentiable (caption_blip.py:33-36,45)."""
         return image_ops.resize_bicubic_aa_normalize(images, 384, CLIP_MEAN, CLIP_STD)
 
     def score(self, images, prompts=None, input_ids: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None, **_):
-        global LIBRARY_CALLS
         if input_ids is None:
             if self.tokenizer is None or prompts is None:
                 raise NotImplementedError("pass input_ids/attention_mask (BERT tokenisation of 'a photography of ' + prompt.lower()) "
@@ -55,13 +54,7 @@ class Blip(torch.nn.Module):
         pix = self.preprocess(images)
         labels = input_ids.masked_fill(input_ids == self.pad_token_id, IGNORE_INDEX)        # caption_blip.py:51-53
         labels[:, : self.prompt_length] = IGNORE_INDEX                                       # :54
-        if hasattr(self.model, "caption_loss"):
-            loss = self.model.caption_loss(pix, input_ids, attention_mask, labels)
-        else:
-            LIBRARY_CALLS += 1
-            dt = next(self.model.parameters()).dtype
-            with torch.autocast("cuda", dtype=dt, enabled=dt != torch.float32):
-                loss = self.model(pixel_values=pix.to(dt), input_ids=input_ids, attention_mask=attention_mask, labels=labels).loss
+        loss = self.model.caption_loss(pix, input_ids, attention_mask, labels)
         return -loss.float()                                                                 # :57-58 (one scalar for the batch)
 
 

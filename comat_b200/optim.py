@@ -16,7 +16,7 @@ from . import _lib
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 _lib.register_signature("comat_grad_sumsq", [_vp, _ll, _vp, _vp, _vp])
-_lib.register_signature("comat_adamw_clip", [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp])
+_lib.register_signature("comat_adamw_clip", [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp])
 
 
 class FlatAdamW:
@@ -38,9 +38,44 @@ class FlatAdamW:
             p.grad = self.grad[off:off + k].view_as(p.data)
             off += k
         self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
-        self.step_count = 0
+        self._step_host = 0
         self.pg = process_group
-        self._scratch = torch.empty(1024 + 1, dtype=torch.float32, device=dev) if dev.type == "cuda" else None
+        cuda = dev.type == "cuda"
+        self._scratch = torch.zeros(1024 + 1 + 4, dtype=torch.float32, device=dev) if cuda else None
+        # device-side step bookkeeping {steps taken, steps skipped on a non-finite gradient, last step skipped}: the overflow guard
+        # (GradScaler semantics) never needs the host; ``poll_overflow`` reads it back one step late without a sync
+        self.counters = torch.zeros(3, dtype=torch.int32, device=dev) if cuda else None
+        self._counters_host = torch.zeros(3, dtype=torch.int32).pin_memory() if cuda else None
+        self._counters_ev = None
+        self._skipped_seen = 0
+
+    @property
+    def step_count(self) -> int:
+        """optimiser steps actually taken (skipped overflow steps do not count, as with GradScaler).  On CUDA this reads the
+        device counter (a sync: checkpointing / tests only)."""
+        return int(self.counters[0].item()) if self.counters is not None else self._step_host
+
+    @step_count.setter
+    def step_count(self, v: int):
+        if self.counters is not None:
+            self.counters[0] = int(v)
+        self._step_host = int(v)
+
+    def poll_overflow(self):
+        """non-blocking: returns (new overflow-skipped steps since the last poll, steps taken) once the previous snapshot has
+        landed, else None; then queues the next snapshot of the device counters on the current stream."""
+        if self.counters is None:
+            return None
+        res = None
+        if self._counters_ev is None or self._counters_ev.query():
+            if self._counters_ev is not None:
+                skipped = int(self._counters_host[1])
+                res = (skipped - self._skipped_seen, int(self._counters_host[0]))
+                self._skipped_seen = skipped
+            self._counters_host.copy_(self.counters, non_blocking=True)
+            self._counters_ev = torch.cuda.Event()
+            self._counters_ev.record()
+        return res
 
     def zero_grad(self):
         self.grad.zero_()
@@ -66,20 +101,19 @@ class FlatAdamW:
     def step(self, handle=None):
         if handle is not None:
             handle.wait()
-        self.step_count += 1
         scale = 1.0 / self.world()
         if not self.flat.is_cuda:
             raise _lib.ComatError("FlatAdamW.step runs the fused CUDA kernel only (no CPU fallback)")
+        self._step_host += 1
         L = _lib.lib()
         st = _lib.stream_ptr()
-        sumsq = self._scratch[1024:]
-        if self.max_norm > 0:
-            _lib.check(L.comat_grad_sumsq(self.grad.data_ptr(), self.n, self._scratch.data_ptr(), sumsq.data_ptr(), st), "grad_sumsq")
-            _lib.count_launch(2)
+        sumsq, state = self._scratch[1024:1025], self._scratch[1025:]
+        # always reduced: the clip coefficient and the overflow guard (non-finite gradient -> the whole update is skipped) read it
+        _lib.check(L.comat_grad_sumsq(self.grad.data_ptr(), self.n, self._scratch.data_ptr(), sumsq.data_ptr(), st), "grad_sumsq")
         _lib.check(L.comat_adamw_clip(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.n,
-                                      self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count,
-                                      float(self.max_norm), scale, sumsq.data_ptr(), st), "adamw_clip")
-        _lib.count_launch()
+                                      self.lr, self.betas[0], self.betas[1], self.eps, self.wd, float(self.max_norm), scale,
+                                      sumsq.data_ptr(), state.data_ptr(), self.counters.data_ptr(), st), "adamw_clip")
+        _lib.count_launch(4)
 
     def grad_norm(self) -> torch.Tensor:
-        return self._scratch[1024:].sqrt() / self.world()
+        return self._scratch[1024:1025].sqrt() / self.world()

@@ -76,6 +76,47 @@ class CoMatTrainer:
         self.overlap_updates = bool(self.G_parameters and self.G_parameters[0].is_cuda)
         self._side_stream = None
         self._ev_G = self._ev_D = None
+        # fp16 loss scale of the explicit backward passes, managed as GradScaler does under ``--mixed_precision fp16``
+        # (training_script.py:111 -> accelerate): the fused AdamW skips an update whose gradient holds an inf / NaN (device-side,
+        # csrc/optim.cu); the skip counter is read back one step late without a sync, the scale is halved after an overflow and
+        # doubled again after ``scale_growth_interval`` clean steps
+        self.scale_growth_interval, self._clean_steps = 2000, 0
+        self.scale_min, self.scale_max = 1.0, 65536.0
+        self._scaled = None
+
+    # ---- dynamic loss scale
+    def _scaled_modules(self):
+        """executors that back-propagate in fp16 under a loss scale (bf16 executors carry grad_scale == 1 and are left alone)."""
+        if self._scaled is None:
+            blip = getattr(getattr(self.caption_model, "blip_model", None), "model", None)
+            mods = [self.pipeline.unet, getattr(self.pipeline, "vae", None), getattr(self.pipeline, "text_encoder", None), blip,
+                    self.D.unet if self.D is not None else None]
+            self._scaled = [m for m in mods if isinstance(getattr(m, "grad_scale", None), float) and m.grad_scale != 1.0]
+        return self._scaled
+
+    def loss_scale(self):
+        mods = self._scaled_modules()
+        return mods[0].grad_scale if mods else 1.0
+
+    def _update_loss_scale(self):
+        overflow, polled = False, False
+        for opt in (self.optimizer, self.D_optimizer):
+            r = opt.poll_overflow() if opt is not None and hasattr(opt, "poll_overflow") else None
+            if r is not None:
+                polled = True
+                overflow |= r[0] > 0
+        if not polled:
+            return
+        factor = 1.0
+        if overflow:
+            factor, self._clean_steps = 0.5, 0
+        else:
+            self._clean_steps += 1
+            if self._clean_steps >= self.scale_growth_interval:
+                factor, self._clean_steps = 2.0, 0
+        if factor != 1.0:
+            for m in self._scaled_modules():
+                m.grad_scale = float(min(self.scale_max, max(self.scale_min, m.grad_scale * factor)))
 
     # ---- side-stream plumbing
     def _run_update(self, fn, which):
@@ -242,6 +283,8 @@ class CoMatTrainer:
         a = self.args
         self._gc_before_step()
         self._join("_ev_G")                                                          # the generator's previous update is in
+        if first:
+            self._update_loss_scale()
         logs = self.g_losses(batch)
         loss = logs["loss"]
         if first:

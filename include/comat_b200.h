@@ -187,12 +187,16 @@ int comat_nhwc_to_nchw_f32(const void* in, float* out, int n, int Cout, int HW, 
  * Replaces accelerator.clip_grad_norm_ + torch.optim.AdamW.step (training_script.py:661-664, :692-694).
  *   comat_grad_sumsq : out[0] = sum g^2 (device scalar, no host sync); partial = >= 1024 floats of scratch.
  *   comat_adamw_clip : g' = g * grad_scale * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)); then torch-AdamW math
- *                      (decoupled weight decay, bias correction by `step` >= 1).  max_norm <= 0 disables clipping.
+ *                      (decoupled weight decay, bias correction by the DEVICE step counter).  max_norm <= 0 disables clipping.
+ *                      Overflow guard (accelerate's GradScaler behaviour, training_script.py:659-663 under mixed_precision=fp16):
+ *                      a non-finite sumsq skips the update - p, m, v and counters[0] stay untouched, counters[1] += 1,
+ *                      counters[2] = 1.  p, g, m, v 16-byte aligned; state = 4 floats of scratch, counters = 3 ints
+ *                      {steps taken, steps skipped, last step skipped}, both device memory owned by the caller.
  * ------------------------------------------------------------------------------------------------------------ */
 int comat_grad_sumsq(const float* g, long long n, float* partial, float* out, void* stream);
 int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, int step, float max_norm, float grad_scale, const float* sumsq,
-                     void* stream);
+                     float eps, float weight_decay, float max_norm, float grad_scale, const float* sumsq,
+                     float* state, int* counters, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused multi-head attention forward (tcgen05, flash-style):  out = softmax(scale * q k^T) v  per (sample, head).

@@ -173,7 +173,9 @@ def split_f32_bf16x2(src, hi, lo, alpha=1.0):
 
 def install(monkeypatch):
     from comat_b200 import attention, ops
-    monkeypatch.setattr(attention, "ALLOW_LIBRARY_PATH", True)     # CPU logic tests run attention through the aten comparator
+    # CPU logic tests run the executors' attention through the torch comparator below (the product has no such path)
+    monkeypatch.setattr(attention, "attention_fwd", attention_fwd)
+    monkeypatch.setattr(attention, "attention_bwd", attention_bwd)
     for name in ("gemm", "gemm_tn", "split_f32_bf16x2", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
                  "elementwise", "spatial", "transpose16", "concat_channels", "latent_to_nhwc", "nhwc_to_nchw_f32"):
         monkeypatch.setattr(ops, name, globals()[name])
@@ -196,6 +198,19 @@ def _ref_attn(q, k, v, heads, kv_lens=None, causal=False, dprobs=None):
     p = s.softmax(-1)
     o = (p @ sp(v)).permute(0, 2, 1, 3).reshape(n, Lq, C)
     return o, p.reshape(n * heads, Lq, Lk), torch.logsumexp(s, -1).reshape(n * heads, Lq)
+
+
+def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
+    """comat_b200.attention.attention_fwd protocol: (o, probs fp32 | None, saved)"""
+    o, p, _ = _ref_attn(q, k, v, heads)
+    return o.to(q.dtype), (p.float() if export_probs else None), ((q, k, v, heads) if need_bwd else None)
+
+
+def attention_bwd(saved, do, dprobs):
+    q, k, v, heads = saved
+    if do is None:
+        do = torch.zeros_like(q)
+    return attention_bwd_native(q, k, v, None, None, None, heads, do, dprobs)
 
 
 def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False, kv_lens=None, causal=False):

@@ -20,6 +20,7 @@ def rel(a, b):
 @pytest.mark.parametrize("dtype", [torch.float16])
 def test_train_step_losses_and_grads_vs_oracle(dtype):
     from comat_b200 import synthetic
+    from comat_b200.blip_engine import BlipEngine
     from comat_b200.caption import Blip, CaptionModelWrapper
     from comat_b200.gan import D_sd
     from comat_b200.modules import EngineUNet, EngineVAE
@@ -47,7 +48,7 @@ def test_train_step_losses_and_grads_vs_oracle(dtype):
     pipe = AttrConcenTrainableSDPipeline(EngineVAE(vae_p, dtype), EngineUNet(unet_p, dtype))
     register_attention_control(pipe, AttentionStore(args.train_layer_ls))
     D = D_sd(EngineUNet(d_p, dtype), mlp=head)
-    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(blip_model)), D)
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(BlipEngine(blip_model, dtype))), D)
     batch, _ = synthetic.batch_to_device(synthetic.synthetic_batch(B, 5, 64, res, True, True), dev)
     g = torch.Generator().manual_seed(9)
     lat = res // 8
@@ -85,6 +86,7 @@ def test_train_step_losses_and_grads_vs_oracle(dtype):
 
 def _make_trainer(dtype, overlap):
     from comat_b200 import synthetic
+    from comat_b200.blip_engine import BlipEngine
     from comat_b200.caption import Blip, CaptionModelWrapper
     from comat_b200.gan import D_sd
     from comat_b200.modules import EngineUNet, EngineVAE
@@ -104,7 +106,7 @@ def _make_trainer(dtype, overlap):
     pipe = AttrConcenTrainableSDPipeline(EngineVAE(vae_p, dtype), EngineUNet(unet_p, dtype))
     register_attention_control(pipe, AttentionStore(args.train_layer_ls))
     D = D_sd(EngineUNet(d_p, dtype), mlp=head)
-    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(blip_model)), D, rng=random.Random(5))
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(BlipEngine(blip_model, dtype))), D, rng=random.Random(5))
     tr.overlap_updates = overlap
     batches = [synthetic.batch_to_device(synthetic.synthetic_batch(B, 40 + i, 64, res, True, True), dev)[0] for i in range(3)]
     return tr, batches

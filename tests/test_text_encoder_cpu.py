@@ -7,6 +7,7 @@ import torch
 from oracle import comat_ref as R
 from oracle import fixtures as FX
 from tests import cpu_ops_emulation as EMU
+from tests.hf_blip import HFBlipComparator
 
 
 def _neg(case):
@@ -162,7 +163,7 @@ def test_trainer_step_from_prompt_strings_equals_step_from_oracle_embeddings(mon
     args = synthetic.default_args(pretrain_model_name="sd_1_5", train_batch_size=B, K=1, total_step=S, gan_loss=False, resolution=res, seed=3)
     pipe = TrainableSDPipeline(EngineVAE(vae, torch.float32), EngineUNet(unet, torch.float32), text_encoder=EngineCLIPText(clip, torch.float32),
                                tokenizer=synthetic.SyntheticClipTokenizer())
-    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(R.make_blip(large=False))), None)
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(HFBlipComparator(R.make_blip(large=False)))), None)
     prompts = ["a red apple on a table", "two dogs"]
     g = torch.Generator().manual_seed(9)
     ids, mask = FX.blip_token_batch(g, B, 8)
@@ -302,7 +303,7 @@ def test_trainer_text_lora_gradients_equal_the_chain_rule(monkeypatch):
     enc = EngineCLIPText(clip, torch.float32)
     pipe = TrainableSDPipeline(EngineVAE(vae, torch.float32), EngineUNet(unet, torch.float32), text_encoder=enc,
                                tokenizer=synthetic.SyntheticClipTokenizer())
-    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(R.make_blip(large=False))), None)
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(HFBlipComparator(R.make_blip(large=False)))), None)
     assert tr.train_text and len(tr.G_parameters) == 256 + len(tparams) and tr.optimizer.n == sum(p.numel() for p in tr.G_parameters)
     prompts = ["a red apple on a table", "two dogs"]
     g = torch.Generator().manual_seed(9)

@@ -8,6 +8,7 @@ import torch
 from oracle import comat_ref as R
 from oracle import sd_modules as sdm
 from tests import cpu_ops_emulation as EMU
+from tests.hf_blip import HFBlipComparator
 
 
 def rel(a, b):
@@ -76,7 +77,7 @@ def test_train_step_matches_oracle_step(monkeypatch):
     pipe = AttrConcenTrainableSDPipeline(EngineVAE(vae_p, torch.float32), EngineUNet(unet_p, torch.float32))
     register_attention_control(pipe, AttentionStore(args.train_layer_ls))
     D = D_sd(EngineUNet(d_p, torch.float32), mlp=head)
-    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(blip_model)), D)
+    tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], Blip(HFBlipComparator(blip_model))), D)
     hb = synthetic.synthetic_batch(B, 5, 64, res, True, True)
     batch, _ = synthetic.batch_to_device(hb, "cpu")
     g = torch.Generator().manual_seed(9)
