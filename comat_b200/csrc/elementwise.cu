@@ -525,12 +525,27 @@ static inline int gn_apply_chunks(int n, int HW, int rows_par) {
   return c < 1 ? 1 : c;
 }
 
+namespace comat {
+int gn_fused_launch(int mode, const void* x, const void* dy, void* out, const float* gamma, const float* beta, float* mean_rstd,
+                    int n, int HW, int C, int G, float eps, int silu, int dtype, cudaStream_t st);     // groupnorm_fused.cu
+}
+// COMAT_GN=twopass selects the two-launch kernels below (A/B measurements); default: the single-launch cluster kernel
+static inline bool gn_use_fused() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("COMAT_GN"); on = (e && !strcmp(e, "twopass")) ? 0 : 1; }
+  return on == 1;
+}
+
 extern "C" size_t comat_groupnorm_workspace_floats(int n, int HW, int G) { return (size_t)n * gn_chunks(n, HW) * G * 2 + (size_t)n * G * 2; }
 
 extern "C" int comat_groupnorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, float* ws,
                                    int n, int HW, int C, int G, float eps, int silu, int dtype, void* stream) {
   if (!x || !y || !gamma || !beta || !mean_rstd || !ws || C % 8 || C % G || C / 8 > 512) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (gn_use_fused()) {
+    const int rc = gn_fused_launch(0, x, nullptr, y, gamma, beta, mean_rstd, n, HW, C, G, eps, silu, dtype, st);
+    if (rc != COMAT_ERR_UNSUPPORTED) return rc;
+  }
   const int chunks = gn_chunks(n, HW);
   const int thr = gn_threads(C), achunks = gn_apply_chunks(n, HW, thr / (C / 8));
   const float inv_cnt = 1.f / ((float)HW * (C / G));
@@ -546,6 +561,10 @@ extern "C" int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, cons
                                    const float* mean_rstd, float* ws, int n, int HW, int C, int G, int silu, int dtype, void* stream) {
   if (!x || !dy || !dx || !gamma || !beta || !mean_rstd || !ws || C % 8 || C % G || C / 8 > 512) return COMAT_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (gn_use_fused()) {
+    const int rc = gn_fused_launch(1, x, dy, dx, gamma, beta, const_cast<float*>(mean_rstd), n, HW, C, G, 0.f, silu, dtype, st);
+    if (rc != COMAT_ERR_UNSUPPORTED) return rc;
+  }
   const int chunks = gn_chunks(n, HW);
   const int thr = gn_threads(C), achunks = gn_apply_chunks(n, HW, thr / (C / 8));
   const float inv_cnt = 1.f / ((float)HW * (C / G));

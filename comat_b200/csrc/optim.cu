@@ -42,12 +42,12 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, flo
 //   state[0] = skip (0 / 1)   state[1] = clip coefficient * grad_scale   state[2] = 1 - beta1^step   state[3] = sqrt(1 - beta2^step)
 //   counters[0] = optimiser steps taken   counters[1] = steps skipped   counters[2] = 1 if the LAST step was skipped
 __global__ void adamw_prepare_kernel(const float* __restrict__ sumsq, float* __restrict__ state, int* __restrict__ counters,
-                                     float b1, float b2, float max_norm, float grad_scale) {
+                                     double b1, double b2, double lr, float max_norm, float grad_scale) {
   pdl_grid_dependency_sync();
   if (threadIdx.x != 0) return;
   const float ss = sumsq[0];
   if (!isfinite(ss)) {
-    state[0] = 1.f; state[1] = 0.f; state[2] = 1.f; state[3] = 1.f;
+    state[0] = 1.f; state[1] = 0.f; state[2] = 0.f; state[3] = 1.f;
     counters[1] += 1; counters[2] = 1;
     return;
   }
@@ -55,38 +55,36 @@ __global__ void adamw_prepare_kernel(const float* __restrict__ sumsq, float* __r
   counters[0] = step; counters[2] = 0;
   float coef = grad_scale;
   if (max_norm > 0.f) coef *= fminf(1.f, max_norm / (sqrtf(ss) * grad_scale + 1e-6f));      // torch.nn.utils.clip_grad_norm_
+  // torch.optim.AdamW evaluates the bias corrections in Python doubles and hands the kernels their fp32 roundings
+  const double bc1 = 1.0 - pow(b1, (double)step);
+  const double bc2 = 1.0 - pow(b2, (double)step);
   state[0] = 0.f; state[1] = coef;
-  state[2] = 1.f - powf(b1, (float)step);
-  state[3] = sqrtf(1.f - powf(b2, (float)step));
+  state[2] = (float)(lr / bc1);                      // step_size
+  state[3] = (float)sqrt(bc2);                       // bias_correction2_sqrt
 }
 
+// torch's single-tensor AdamW arithmetic, operation by operation (fp32):  p *= 1 - lr*wd ;  m = lerp(m, g, 1 - b1) ;
+// v = v*b2 + (1 - b2)*g*g ;  p -= step_size * m / (sqrt(v) / bc2_sqrt + eps)
 __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                         float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                                         float wd, const float* __restrict__ state) {
+                                                         float* __restrict__ v, long long n, float decay, float b2, float omb1,
+                                                         float omb2, float eps, const float* __restrict__ state) {
   pdl_grid_dependency_sync();
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n || state[0] != 0.f) return;
-  const float coef = state[1], bc1 = state[2], bc2_sqrt = state[3];
-  const float decay = 1.f - lr * wd, step_size = lr / bc1;                    // decoupled weight decay
+  const float coef = state[1], step_size = state[2], bc2_sqrt = state[3];
+  auto upd = [&](float& pp, float& mm, float& vv, float gg) {
+    gg *= coef;
+    mm = omb1 < 0.5f ? fmaf(omb1, gg - mm, mm) : gg - (gg - mm) * (1.f - omb1);      // at::lerp
+    vv = fmaf(omb2 * gg, gg, vv * b2);
+    pp = pp * decay - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+  };
   if (i4 + 4 <= n) {
     const float4 g4 = *reinterpret_cast<const float4*>(g + i4);
     float4 p4 = *reinterpret_cast<float4*>(p + i4), m4 = *reinterpret_cast<float4*>(m + i4), v4 = *reinterpret_cast<float4*>(v + i4);
-    const float gs[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
-    float* pp = &p4.x; float* mm = &m4.x; float* vv = &v4.x;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mm[k] = b1 * mm[k] + (1.f - b1) * gs[k];
-      vv[k] = b2 * vv[k] + (1.f - b2) * gs[k] * gs[k];
-      pp[k] = pp[k] * decay - step_size * (mm[k] / (sqrtf(vv[k]) / bc2_sqrt + eps));
-    }
+    upd(p4.x, m4.x, v4.x, g4.x); upd(p4.y, m4.y, v4.y, g4.y); upd(p4.z, m4.z, v4.z, g4.z); upd(p4.w, m4.w, v4.w, g4.w);
     *reinterpret_cast<float4*>(p + i4) = p4; *reinterpret_cast<float4*>(m + i4) = m4; *reinterpret_cast<float4*>(v + i4) = v4;
   } else {
-    for (long long i = i4; i < n; ++i) {
-      const float gi = g[i] * coef;
-      const float mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
-      m[i] = mi; v[i] = vi;
-      p[i] = p[i] * decay - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-    }
+    for (long long i = i4; i < n; ++i) upd(p[i], m[i], v[i], g[i]);
   }
 }
 
@@ -103,14 +101,15 @@ extern "C" int comat_grad_sumsq(const float* g, long long n, float* partial /* >
   return COMAT_OK;
 }
 
-extern "C" int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                                float eps, float weight_decay, float max_norm, float grad_scale, const float* sumsq,
+extern "C" int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                                double eps, double weight_decay, float max_norm, float grad_scale, const float* sumsq,
                                 float* state /* 4 floats */, int* counters /* 3 ints: steps, skipped, last skipped */, void* stream) {
   if (!p || !g || !m || !v || n <= 0 || !sumsq || !state || !counters) return COMAT_ERR_INVALID;
   if ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) != 0) return COMAT_ERR_INVALID;
-  launch_k(adamw_prepare_kernel, 1, 32, 0, (cudaStream_t)stream, sumsq, state, counters, beta1, beta2, max_norm, grad_scale);
-  launch_k(adamw_clip_kernel, (unsigned)((n + 1023) / 1024), 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
-           (const float*)state);
+  launch_k(adamw_prepare_kernel, 1, 32, 0, (cudaStream_t)stream, sumsq, state, counters, beta1, beta2, lr, max_norm, grad_scale);
+  // hyper-parameters arrive as doubles (Python floats) and are rounded to fp32 exactly where torch rounds them
+  launch_k(adamw_clip_kernel, (unsigned)((n + 1023) / 1024), 256, 0, (cudaStream_t)stream, p, g, m, v, n, (float)(1.0 - lr * weight_decay),
+           (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (const float*)state);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }

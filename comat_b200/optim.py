@@ -14,9 +14,9 @@ import torch.distributed as dist
 
 from . import _lib
 
-_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_vp, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 _lib.register_signature("comat_grad_sumsq", [_vp, _ll, _vp, _vp, _vp])
-_lib.register_signature("comat_adamw_clip", [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp])
+_lib.register_signature("comat_adamw_clip", [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _f, _f, _vp, _vp, _vp, _vp])
 
 
 class FlatAdamW:

@@ -191,11 +191,13 @@ int comat_nhwc_to_nchw_f32(const void* in, float* out, int n, int Cout, int HW, 
  *                      Overflow guard (accelerate's GradScaler behaviour, training_script.py:659-663 under mixed_precision=fp16):
  *                      a non-finite sumsq skips the update - p, m, v and counters[0] stay untouched, counters[1] += 1,
  *                      counters[2] = 1.  p, g, m, v 16-byte aligned; state = 4 floats of scratch, counters = 3 ints
- *                      {steps taken, steps skipped, last step skipped}, both device memory owned by the caller.
+ *                      {steps taken, steps skipped, last step skipped}, both device memory owned by the caller.  Hyper-parameters
+ *                      are doubles: they are rounded to fp32 where torch.optim.AdamW rounds its Python floats (1 - beta2, lr / bias
+ *                      correction ...), so the update matches torch's to fp32 rounding.
  * ------------------------------------------------------------------------------------------------------------ */
 int comat_grad_sumsq(const float* g, long long n, float* partial, float* out, void* stream);
-int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, float max_norm, float grad_scale, const float* sumsq,
+int comat_adamw_clip(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                     double eps, double weight_decay, float max_norm, float grad_scale, const float* sumsq,
                      float* state, int* counters, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

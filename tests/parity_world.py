@@ -82,7 +82,12 @@ def sd15_world(dev, dtype, *, tiny, B, S, K, res, rank, n_attrcon=2, layers=None
     D = D_sd(EngineUNet(d_p, dtype), mlp=head)
     blip = Blip(BlipEngine(blip_model, dtype) if blip_wrap is None else blip_wrap(blip_model))
     tr = CoMatTrainer(args, pipe, CaptionModelWrapper(["Blip"], [1.0], blip), D)
-    batch, _ = synthetic.batch_to_device(synthetic.synthetic_batch(B, 5, ctx_dim, res, True, True), dev)
+    hb = synthetic.synthetic_batch(B, 5, ctx_dim, res, True, True)
+    for m in hb["masks_host"]:                 # no "object not detected" (all-false) masks here: they make the token loss a constant
+        for i in range(m.shape[0]):
+            if not bool(m[i].any()):
+                m[i, :, res // 5: res // 2 + 16 * i, res // 4: 3 * res // 4] = True
+    batch, _ = synthetic.batch_to_device(hb, dev)
     g = torch.Generator().manual_seed(9)
     lat = res // 8
     batch["init_latents"] = torch.randn(B, 4, lat, lat, generator=g).to(dev)

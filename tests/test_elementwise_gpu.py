@@ -13,7 +13,11 @@ def rel(a, b):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.2e-2)])
 @pytest.mark.parametrize("n,HW,C,silu,eps", [(2, 4096, 320, True, 1e-5), (3, 1024, 640, False, 1e-6), (2, 256, 1920, True, 1e-5),
-                                             (2, 64, 2560, True, 1e-5), (1, 16384, 128, True, 1e-6), (2, 64, 32, True, 1e-5)])
+                                             (2, 64, 2560, True, 1e-5), (1, 16384, 128, True, 1e-6), (2, 64, 32, True, 1e-5),
+                                             # single-launch cluster kernel: slabs larger than shared memory (rows re-read), 8-CTA
+                                             # clusters, one-vector channel sets (VAE), a row count that does not divide
+                                             (8, 4096, 960, True, 1e-5), (1, 65536, 256, True, 1e-6), (2, 262144, 128, False, 1e-6),
+                                             (2, 100, 64, True, 1e-5), (8, 1024, 1280, False, 1e-6)])
 def test_groupnorm(n, HW, C, silu, eps, dtype, tol):
     from comat_b200 import ops
     torch.manual_seed(C)
@@ -29,6 +33,10 @@ def test_groupnorm(n, HW, C, silu, eps, dtype, tol):
     yr.backward(dy.float())
     assert rel(y.float(), yr) < tol
     assert rel(dx.float(), xr.grad) < 2 * tol
+    xs = x.float().reshape(n, HW, 32, C // 32)
+    mean, var = xs.mean((1, 3)), xs.var((1, 3), unbiased=False)
+    mr = mr.reshape(n, 32, 2)
+    assert rel(mr[..., 0], mean) < 1e-4 + 1e-3 * float(var.sqrt().mean() / mean.abs().mean().clamp_min(1e-6)) and rel(mr[..., 1], (var + eps).rsqrt()) < 1e-3
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.2e-2)])

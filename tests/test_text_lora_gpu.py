@@ -1,7 +1,6 @@
-"""Device parity tests for code that was finished after the round-1 GPU budget ran out (NOT collected: the file name does not
-match ``test_*.py``).  Round 2: run ``pytest tests/pending_r02_gpu.py -m gpu`` on a B200 first, fix what it finds, then rename
-the file to ``test_text_lora_gpu.py``.  Covers: d(encoder_hidden_states) out of the UNet executor, the taped text encoder with
-LoRA, and a trainer step with ``--train_text_encoder_lora``.  Tolerances follow the measured 16-bit errors of the sibling tests
+"""GPU parity of the text-LoRA / context-gradient path (training_script.py:227-255, :569-573): d(encoder_hidden_states)
+out of the UNet executor, the taped CLIP text encoder with LoRA, and a trainer step with ``--train_text_encoder_lora``.
+First run on a B200 in round 2 (profiles/r02_gpu_tests_run1.log).  Tolerances follow the measured 16-bit errors of the sibling tests
 (UNet input gradient 3e-2, text encoder 5e-3)."""
 import pytest
 import torch
@@ -50,7 +49,9 @@ def test_text_lora_taped_executor_on_device(dtype, tol):
     params = install_text_lora(model, 16, up_std=0.05)
     hooks = R.add_text_lora_hooks(model)
     ids = FX.ClipTokenizerStub()(["a photo of a cat", "two red cubes on a blue sphere", ""]).input_ids.cuda()
-    dy = torch.randn(3, 77, 768, generator=torch.Generator().manual_seed(3)).cuda()
+    # a loss-sized upstream gradient: N(0, 1) x 4096 (the fp16 loss scale) overflows fp16 after a few layers, which is the guard's
+    # business (test_parity_fullsize_gpu.py::test_flat_adamw_skips_a_non_finite_gradient), not this comparison's
+    dy = (torch.randn(3, 77, 768, generator=torch.Generator().manual_seed(3)) * 1e-3).cuda()
     ref = model(ids).last_hidden_state
     g_ref = torch.autograd.grad(ref, params, dy)
     for h in hooks:
