@@ -125,6 +125,31 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
           if (j < ncol) f[j] += rvc[j];
       }
     }
+    if (p.act == 3) {
+      // GEGLU (diffusers GEGLU.forward: hidden * gelu(gate)) on a projection whose weight rows were interleaved at pack time
+      // (column 2j = hidden_j, 2j+1 = gate_j): 32 accumulator columns -> 16 outputs of the half-width tensor.  The (M, 2*inner)
+      // pre-activation never reaches HBM and the separate GEGLU pass disappears (no-grad passes; taped passes keep hg).
+      if (row_ok && ncol > 0) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g0 = f[4 * j + 1], g1 = f[4 * j + 3];
+          const float o0 = f[4 * j] * (0.5f * g0 * (1.f + erff(g0 * 0.70710678118654752f)));
+          const float o1 = f[4 * j + 2] * (0.5f * g1 * (1.f + erff(g1 * 0.70710678118654752f)));
+          pk[j] = pack16(o0, o1, p.is_bf16);
+        }
+        uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + ((n0 + c0) >> 1);
+        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+          *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (2 * j < ncol) op[j] = (uint16_t)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xFFFFu));
+        }
+      }
+      return;
+    }
     if (p.act == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
@@ -1038,11 +1063,15 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
       kp.atomic_acc = 1;
     }
   }
+  if (g->act == 3) {
+    // fused GEGLU epilogue: half-width 16-bit output, written with direct 32-byte stores
+    if (!g->out16 || g->out32 || g->residual || g->rowvec || kp.split_k > 1 || g->accumulate || (g->N & 1) || a_mn || b_mn) return COMAT_ERR_INVALID;
+  }
   // TMA-store epilogue (default): needs a 16-bit output with 16-byte aligned base and row pitch
   static int epi_mode = -1;
   if (epi_mode < 0) { const char* e = getenv("COMAT_GEMM_EPILOGUE"); epi_mode = (e && !strcmp(e, "direct")) ? 0 : 1; }
   kp.tma_store = 0;
-  if (epi_mode == 1 && kp.split_k == 1 && g->out16 && !g->out32 && (g->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(g->out16) & 15) == 0 &&
+  if (epi_mode == 1 && g->act != 3 && kp.split_k == 1 && g->out16 && !g->out32 && (g->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(g->out16) & 15) == 0 &&
       (!kp.conv || g->out_ld == g->N)) {
     bool ok;
     if (kp.conv) {

@@ -58,22 +58,28 @@ __device__ __forceinline__ float gnf_silu_grad(float x) {
 }
 
 template <typename T, int MODE>   // MODE 0: y = [silu](xhat * gamma + beta), saves (mean, rstd) ; MODE 1: dx
-__global__ void __launch_bounds__(512) gn_fused_kernel(const GnFP p) {
+__global__ void __launch_bounds__(256) gn_fused_kernel(const GnFP p) {
   pdl_grid_dependency_sync();
   extern __shared__ __align__(16) unsigned char gsm[];
   const int CL = gridDim.x, rank = blockIdx.x, set = blockIdx.y, n = blockIdx.z;
   const int VW = p.VW, SW = p.SW, gps = p.gps, cpg = p.cpg, C = p.C, HW = p.HW;
-  const int RP = blockDim.x / VW;
-  const int v = threadIdx.x % VW, pr = threadIdx.x / VW;
-  const bool active = pr < RP;
+  // warp-aligned mapping: a warp covers RPW = 32 / VW consecutive rows per step, lane = (row_sub, vector); the lanes that share a
+  // vector column are VW apart, so per-channel sums reduce with a few shuffles and ONE plain store per (warp, channel) - no
+  // shared-memory atomics (the first version added 16 partials per thread onto 2 * SW addresses: ~100-way CAS contention made
+  // the kernel 2x slower than the two-pass pair, profiles/r02_groupnorm_bench.md)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
+  const int RPW = 32 / VW;
+  const int v = lane % VW, rs = lane / VW;
+  const bool active = rs < RPW;
+  const int pr = warp * RPW + rs, RP = NW * RPW;       // first row of this thread, row step
   const int p0 = (int)((long long)HW * rank / CL), p1 = (int)((long long)HW * (rank + 1) / CL);
   const int R = p1 - p0;
   const int keep = R < p.keep_rows ? R : p.keep_rows;
 
-  float* s_ch = reinterpret_cast<float*>(gsm);                 // [2 * SW] per-channel sums of this CTA
-  float* s_part = s_ch + 2 * SW;                               // [2 * gps] per-group partials (read by the peers)
+  float* s_ch = reinterpret_cast<float*>(gsm);                 // [NW][2 * SW] per-warp per-channel sums
+  float* s_part = s_ch + (size_t)NW * 2 * SW;                  // [2 * gps] per-group partials (read by the peers)
   float* s_stat = s_part + 2 * gps;                            // [2 * gps] cluster-wide statistics
-  const int stat_bytes = ((2 * SW + 4 * gps) * 4 + 15) & ~15;
+  const int stat_bytes = ((NW * 2 * SW + 4 * gps) * 4 + 15) & ~15;
   uint4* s_x = reinterpret_cast<uint4*>(gsm + stat_bytes);     // [keep_rows][VW]
   uint4* s_d = s_x + (size_t)p.keep_rows * VW;                 // [keep_rows][VW]  (MODE 1)
 
@@ -89,7 +95,6 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnFP p) {
       if (MODE == 1) cp_async16(&s_d[(size_t)r * VW + v], dg + (size_t)r * C);
     }
   }
-  for (int i = threadIdx.x; i < 2 * SW; i += blockDim.x) s_ch[i] = 0.f;
 
   float g8[8], b8[8], rs8[8], mu8[8];
   if (MODE == 1 && active) {
@@ -138,14 +143,34 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnFP p) {
       if (MODE == 1) dv.u = s_d[(size_t)r * VW + v];
       accum(xv, dv);
     }
+  }
+  // lanes v, v + VW, v + 2 VW ... hold the same channels: fold them onto lane v (inactive lanes carry zeros)
+  const bool pow2 = (32 % VW) == 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { atomicAdd(&s_ch[v * 8 + i], sa[i]); atomicAdd(&s_ch[SW + v * 8 + i], sb[i]); }
+  for (int i = 0; i < 8; ++i) {
+    float a = sa[i], b = sb[i];
+    if (pow2) {
+      for (int off = 16; off >= VW; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+    } else {
+      for (int off = VW; off < 32; off += VW) {
+        const float a2 = __shfl_down_sync(0xffffffffu, sa[i], off), b2 = __shfl_down_sync(0xffffffffu, sb[i], off);
+        if (lane + off < RPW * VW) { a += a2; b += b2; }
+      }
+    }
+    if (lane < VW) { s_ch[(size_t)warp * 2 * SW + v * 8 + i] = a; s_ch[(size_t)warp * 2 * SW + SW + v * 8 + i] = b; }
   }
   __syncthreads();
-  if (threadIdx.x < gps) {
+  for (int t = threadIdx.x; t < 2 * SW; t += blockDim.x) {        // over the warps, fixed order; a thread touches its own column only
+    float acc = 0.f;
+    for (int w = 0; w < NW; ++w) acc += s_ch[(size_t)w * 2 * SW + t];
+    s_ch[t] = acc;
+  }
+  __syncthreads();
+  for (int g = warp; g < gps; g += NW) {                          // channels of a group: one warp, shuffle tree (deterministic)
     float a = 0.f, b = 0.f;
-    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { a += s_ch[c]; b += s_ch[SW + c]; }
-    s_part[2 * threadIdx.x] = a; s_part[2 * threadIdx.x + 1] = b;
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) { a += s_ch[c]; b += s_ch[SW + c]; }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { s_part[2 * g] = a; s_part[2 * g + 1] = b; }
   }
   cl_sync();                                             // every CTA's partials are published
   if (threadIdx.x < gps) {
@@ -229,15 +254,17 @@ static int gn_fused_launch_t(const GnFP& p0, int n, cudaStream_t st) {
          (((long long)(p.HW + CL - 1) / CL) * row_bytes > 48 * 1024 || (long long)n * nsets * CL < 2LL * num_sms()))
     CL *= 2;
   const int R = (p.HW + CL - 1) / CL;
-  const int stat_bytes = ((2 * p.SW + 4 * p.gps) * 4 + 15) & ~15;
+  const int RPW = 32 / p.VW;
+  int NW = (R + RPW - 1) / RPW;                          // one row per thread is enough for the smallest slabs
+  if (NW > 8) NW = 8;                                    // 256 threads: up to 4 CTAs per SM, their load / reduce / store phases overlap
+  if (NW < 2) NW = 2;
+  const int thr = NW * 32;
+  const int stat_bytes = ((NW * 2 * p.SW + 4 * p.gps) * 4 + 15) & ~15;
   const long long slab = (long long)R * row_bytes;
   const long long cap = slab + stat_bytes <= 200 * 1024 ? slab : 96 * 1024;      // fits: keep everything (1 CTA / SM if large)
   p.keep_rows = (int)(cap / row_bytes);
   if (p.keep_rows > R) p.keep_rows = R;
   const size_t smem = (size_t)stat_bytes + (size_t)p.keep_rows * row_bytes;
-  long long work = (long long)R * p.VW;
-  int thr = work >= 512 ? 512 : (int)((work + 31) / 32 * 32);
-  if (thr < 64) thr = 64;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(CL, nsets, n); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = smem; cfg.stream = st;

@@ -390,6 +390,12 @@ class _TBlock:
         self.n1, self.n2, self.n3 = NormW(m.norm1), NormW(m.norm2), NormW(m.norm3)
         self.a1, self.a2 = _Attn(m.attn1, dtype), _Attn(m.attn2, dtype)
         self.ff1, self.ff2 = LinW(m.ff.net[0].proj, dtype), LinW(m.ff.net[2], dtype)
+        # no-grad passes: GEGLU fused into the projection's epilogue - weight rows interleaved (2j = hidden_j, 2j+1 = gate_j) so an
+        # accumulator column pair is one output of ``hidden * gelu(gate)`` (diffusers GEGLU.forward: proj(x).chunk(2, -1))
+        w, b = m.ff.net[0].proj.weight.detach(), m.ff.net[0].proj.bias.detach()
+        inner = w.shape[0] // 2
+        self.ff1_il_w = UW.to16(torch.stack([w[:inner], w[inner:]], 1).reshape(2 * inner, -1), dtype)
+        self.ff1_il_b = torch.stack([b[:inner], b[inner:]], 1).reshape(-1).float().contiguous()
 
 
 class _Transformer:
@@ -551,7 +557,11 @@ def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=No
         h = _attn_layer(tape, b.a1, layernorm(tape, h, b.n1), None, h, capture, place, mode)
         h = _attn_layer(tape, b.a2, layernorm(tape, h, b.n2), ctx, h, capture, place, mode,
                         None if cross_kv is None else cross_kv.get(id(b.a2)))
-        ff = geglu(tape, linear(tape, layernorm(tape, h, b.n3), b.ff1))
+        if tape is None:
+            y3 = layernorm(None, h, b.n3).v
+            ff = Var(ops.gemm([y3.reshape(-1, y3.shape[-1])], [b.ff1_il_w], bias=b.ff1_il_b, act="geglu").reshape(*y3.shape[:-1], -1), False)
+        else:
+            ff = geglu(tape, linear(tape, layernorm(tape, h, b.n3), b.ff1))
         h = linear(tape, ff, b.ff2, residual=h)
     if t.linear_proj:
         return _reshape(tape, linear(tape, h, t.pout, residual=_reshape(tape, x, (n, H * W, C))), (n, H, W, C))

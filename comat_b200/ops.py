@@ -30,7 +30,7 @@ class GemmParams(C.Structure):
 
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
 
-ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2}
+ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2, "geglu": 3}
 KERNEL = {None: 0, "auto": 0, "tile": 1, "persist": 2, "pair": 3}
 
 
@@ -117,9 +117,10 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         if residual.dtype != dt:
             raise _lib.ComatError("gemm: residual dtype mismatch")
         p.residual, p.res_ld = residual.data_ptr(), residual.stride(0)
+    n_out = N // 2 if act == "geglu" else N      # fused GEGLU: interleaved (hidden_j, gate_j) weight rows -> hidden_j * gelu(gate_j)
     if out is None:
-        out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else dt, device=a0.device)
-    o2 = out.reshape(M, N) if out.dim() != 2 else out
+        out = torch.empty(M, n_out, dtype=torch.float32 if out_fp32 else dt, device=a0.device)
+    o2 = out.reshape(M, n_out) if out.dim() != 2 else out
     if o2.stride(-1) != 1:
         raise _lib.ComatError("gemm: out must have unit inner stride")
     if o2.dtype == torch.float32:
@@ -132,6 +133,8 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
             force_bn, kernel, split_k = t
     p.force_bn = force_bn
     p.force_kernel = KERNEL[kernel]
+    if act == "geglu":
+        split_k = 1
     if split_k == 0:                      # auto: fill the machine when the output has few tiles and K is long
         kb = sum((a.shape[-1] + 63) // 64 for a in a_segs) * (len(conv_taps) if conv else 1)
         tiles = ((M + 127) // 128) * ((N + 127) // 128)
@@ -162,7 +165,7 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
                                            bool(out_fp32)), fl))
         PROFILE["flops"] += fl
     if conv:
-        return out.reshape(n_img, H, W, N) if out.dim() == 2 else out
+        return out.reshape(n_img, H, W, n_out) if out.dim() == 2 else out
     return out
 
 

@@ -39,6 +39,9 @@ def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_grou
         y = F.silu(y)
     elif act == "gelu":
         y = F.gelu(y)
+    elif act == "geglu":                       # interleaved columns (hidden_j, gate_j) -> hidden_j * gelu(gate_j)
+        y = y[:, 0::2] * F.gelu(y[:, 1::2])
+        N = N // 2
     if residual is not None:
         y = y + residual.reshape(M, N).double()
     y = y.to(torch.float32 if (out_fp32 or (out is not None and out.dtype == torch.float32)) else a0.dtype)

@@ -239,3 +239,25 @@ def test_hi_lo_split_projection():
     assert _rel(g_down, ref_down)[0] < 5e-5
     with pytest.raises(_lib.ComatError):                                      # one operand format per MMA
         ops.gemm([hi], [dh.half()], out_fp32=True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,inner,K,kernel", [(8192, 1280, 320, None), (2048, 5120, 1280, None), (300, 320, 320, None), (1024, 2560, 640, "tile"),
+                                              (4096, 1280, 320, "persist"), (4096, 1280, 640, "pair"), (130, 48, 64, None)])
+def test_gemm_fused_geglu_epilogue(M, inner, K, kernel, dtype):
+    """act='geglu': the projection's weight rows are interleaved (2j = hidden_j, 2j+1 = gate_j) and the epilogue writes
+    hidden * gelu(gate) as a half-width tensor (diffusers GEGLU.forward) - vs the unfused fp32 computation."""
+    from comat_b200 import ops
+    torch.manual_seed(M + inner + K)
+    a = torch.randn(M, K, device="cuda").to(dtype)
+    w = (torch.randn(2 * inner, K, device="cuda") / K ** 0.5).to(dtype)
+    b = torch.randn(2 * inner, device="cuda") * 0.1
+    w_il = torch.stack([w[:inner], w[inner:]], 1).reshape(2 * inner, K).contiguous()
+    b_il = torch.stack([b[:inner], b[inner:]], 1).reshape(-1).contiguous()
+    out = ops.gemm([a], [w_il], bias=b_il, act="geglu", kernel=kernel)
+    assert out.shape == (M, inner)
+    hg = a.float() @ w.float().t() + b
+    ref = hg[:, :inner] * F.gelu(hg[:, inner:])
+    l2, mx = _rel(out.float(), ref)
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2
+    assert l2 < tol and mx < 4 * tol, (l2, mx)

@@ -87,7 +87,7 @@ def test_flat_adamw_vs_torch_adamw_and_clip(max_norm):
     record(f"adamw_clip max_norm={max_norm}", n=n, update_rel=upd, m_rel=PW.rel_l2(opt.m, m_ref), v_rel=PW.rel_l2(opt.v, v_ref),
            max_abs=float((opt.flat - flat_ref).abs().max()))
     assert n > 25_000_000 and opt.step_count == 3
-    assert upd < 2e-6 and PW.rel_l2(opt.m, m_ref) < 1e-6 and PW.rel_l2(opt.v, v_ref) < 1e-6
+    assert upd < 5e-6 and PW.rel_l2(opt.m, m_ref) < 1e-6 and PW.rel_l2(opt.v, v_ref) < 1e-6
     assert float((opt.flat - flat_ref).abs().max()) < 5e-7
     assert ours[0].data_ptr() == opt.flat.data_ptr() and ours[0].grad.data_ptr() == opt.grad.data_ptr()     # parameters live in the flat buffers
 
