@@ -41,7 +41,11 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="comat_b200", choices=["comat_b200", "reference", "gpu_reference"])
     p.add_argument("--no_gpu_reference", action="store_true", help="skip the eager-oracle-on-this-GPU denominator (gpu_reference key)")
-    p.add_argument("--batch", type=int, default=4)
+    p.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                   help="BASELINE.json configs[N-1]: 2 = SD1.5 full CoMat B=4 (the headline, default); 3 = the same at B=8/GPU; 4 = SDXL 512^2 "
+                        "attrcon + GAN (SD1.5 discriminator) B=1/GPU; 5 = SDXL UNet-only forward+backward microbench (--latent, B=2/GPU)")
+    p.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = the config's: 4 / 8 / 1 / 2)")
+    p.add_argument("--latent", type=int, default=128, help="config 5: latent side (64 = 512^2, 96 = 768^2, 128 = 1024^2)")
     p.add_argument("--total_step", type=int, default=20)
     p.add_argument("--K", type=int, default=5)
     p.add_argument("--rank_lora", type=int, default=128)
@@ -105,8 +109,9 @@ def load_peaks():
 def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
     """Times the oracle (plain PyTorch, fp32, eager) on the host cores on a BOUNDED sample of the workload: SD1.5 at full geometry
     (859.5 M-param UNet, VAE decoder, BLIP-large), B=1, S=2 DDPM steps, K=1 back-propagated step, cfg 7.5, concept-matching loss,
-    on a 32x32 latent (256^2 image) so one step is tens of seconds.  The sample's algorithmic FLOPs are counted with
-    torch.utils.flop_counter and the result is scaled to config-2 train-steps by FLOPs (203 TFLOP per config-2 step)."""
+    64x64 latent (512^2 image) = BASELINE.json configs[0] exactly, the reference's own CPU-runnable case (~10 TFLOP, several seconds
+    per step).  The sample's algorithmic FLOPs are counted with torch.utils.flop_counter and the result is scaled to config-2
+    train-steps by FLOPs (203 TFLOP per config-2 step)."""
     import torch
     from torch.utils.flop_counter import FlopCounterMode
     from oracle import comat_ref as R
@@ -122,7 +127,7 @@ def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
         ctx, res = 64, 128
     else:
         unet, vae, blip = sdm.UNet2DConditionModel(**sdm.SD15_UNET_CONFIG), sdm.AutoencoderKL(), R.make_blip(large=True)
-        ctx, res = 768, 256
+        ctx, res = 768, 512
     unet.requires_grad_(False)
     vae.requires_grad_(False)
     params = sdm.install_lora(unet, 128 if not tiny else 8)
@@ -135,9 +140,10 @@ def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
     cfg = dict(S=2, resolution=res)
     opt = torch.optim.AdamW(params, lr=5e-5)
     times, flops = [], None
-    for i in range(-1, warmup + steps):           # i == -1: untimed FLOP-counting pass (also warms oneDNN primitives)
+    first = 0 if warmup >= 1 else -1              # the FLOP-counting pass is the first warm-up step (an extra untimed one if W = 0)
+    for i in range(first, warmup + steps):
         t0 = time.perf_counter()
-        counter = FlopCounterMode(display=False) if i < 0 else None
+        counter = FlopCounterMode(display=False) if i == first else None
         if counter is not None:
             counter.__enter__()
         out = R.g_step_loss(unet, vae, sdm.DDPMScheduler(), blip, batch, cfg)
@@ -153,8 +159,8 @@ def cpu_oracle_sample(threads=None, steps=1, warmup=0, tiny=False):
     return times, threads, flops
 
 
-SAMPLE_DESC = ("SD1.5 full geometry (UNet 859.5 M, VAE decoder, BLIP-large), B=1, S=2, K=1, cfg 7.5, concept-match loss, 32x32 latent "
-               "(256^2 image), fp32 eager oracle")
+SAMPLE_DESC = ("BASELINE configs[0]: SD1.5 full geometry (UNet 859.5 M, VAE decoder, BLIP-large), B=1, S=2, K=1, cfg 7.5, concept-match loss, "
+               "64x64 latent (512^2 image), fp32 eager oracle")
 
 
 def run_reference(a):
@@ -164,12 +170,12 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    times, threads, flops = cpu_oracle_sample(steps=a.steps, warmup=min(a.warmup, 1), tiny=a.tiny)
+    times, threads, flops = cpu_oracle_sample(steps=a.steps, warmup=a.warmup, tiny=a.tiny)
     total = sum(times)
     sample_sps = len(times) / total
     value = sample_sps * (flops / (TFLOP_PER_STEP_CFG2 * 1e12))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": min(a.warmup, 1), "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "SD1.5 512^2 full CoMat, S=20, K=5, B=4 (BASELINE configs[1]); CPU value = bounded sample scaled by "
                                    "algorithmic FLOPs (%.2f TFLOP counted / 203 TFLOP per config-2 step)" % (flops / 1e12),
@@ -379,8 +385,97 @@ def _emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+CONFIGS = {2: dict(batch=4, metric=METRIC, tflop=TFLOP_PER_STEP_CFG2, name="SD1.5 512^2 full CoMat", tag="BASELINE configs[1]"),
+           3: dict(batch=8, metric=METRIC, tflop=TFLOP_PER_STEP_CFG2 * 2, name="SD1.5 512^2 full CoMat", tag="BASELINE configs[2] (masks precomputed; GAN on)"),
+           4: dict(batch=1, metric="sdxl_512_comat_train_steps_per_sec", tflop=90.0, name="SDXL 512^2 full CoMat, SD1.5 discriminator",
+                   tag="BASELINE configs[3]"),
+           5: dict(batch=2, metric="sdxl_unet_fwd_bwd_iters_per_sec", tflop=None, name="SDXL UNet forward + backward", tag="BASELINE configs[4]")}
+
+
+def run_config5(a):
+    """BASELINE configs[4]: SDXL UNet-only denoise forward + backward (data gradient + all 1 120 LoRA weight gradients) on the explicit
+    executors, per-GPU batch --batch at a --latent^2 latent.  One "step" = one fwd+bwd; value = iterations/s summed over ranks."""
+    import torch
+    import torch.distributed as dist
+    from comat_b200 import _lib, ops, synthetic
+    from comat_b200.modules import EngineUNet
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dt = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    lat, n = (32 if a.tiny else a.latent), a.batch
+    unet_p = synthetic.build_sdxl_unet(dev, rank=8 if a.tiny else a.rank_lora, seed=42, tiny=a.tiny)
+    mod = EngineUNet(unet_p, dt)
+    for p_ in mod.lora_parameters():
+        p_.grad = torch.zeros_like(p_)
+    mod.direct_lora_grads = True
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    x = torch.randn(n, 4, lat, lat, device=dev, generator=g)
+    ctx = torch.randn(n, 77, 64 if a.tiny else 2048, device=dev, generator=g)
+    added = dict(text_embeds=torch.randn(n, 16 if a.tiny else 1280, device=dev, generator=g),
+                 time_ids=torch.tensor([[8.0 * lat, 8.0 * lat, 0, 0, 8.0 * lat, 8.0 * lat]] * n, device=dev))
+    t = torch.tensor(500, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def it():
+        xr = x.clone().requires_grad_(True)
+        eps = mod(xr, t, encoder_hidden_states=ctx, added_cond_kwargs=added)[0]
+        eps.float().pow(2).mean().backward()
+        mod.finalize_lora_grads()
+        return eps
+    for _ in range(max(a.warmup, 2)):
+        it()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    l0 = _lib.LAUNCH_COUNT
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(a.steps):
+        eps = it()
+    e1.record()
+    torch.cuda.synchronize()
+    tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev = float(tt)
+    launches = _lib.LAUNCH_COUNT - l0
+    F_fwd = {32: None, 64: 1.589, 96: 1.589 * 2.25 * 1.05, 128: 6.76}.get(lat)          # TFLOP per sample forward (SURVEY 8d; 96: interpolated)
+    sustained, burst, hbm, peak_src = load_peaks()
+    if rank == 0:
+        value = world * a.steps / t_dev
+        tf = None if F_fwd is None else 3.0 * n * F_fwd * a.steps / t_dev              # fwd + dgrad + LoRA wgrad ~ 3 x forward FLOPs... dgrad only: 2x
+        line = {"metric": CONFIGS[5]["metric"], "value": value, "unit": "iters/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 2),
+                "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype,
+                "data": "synthetic",
+                "config": {"workload": ("TINY-DEBUG " if a.tiny else "") + "SDXL UNet (2.567 B) forward + backward incl. LoRA r=%d weight gradients, latent %dx%d, "
+                           "batch %d/GPU (BASELINE configs[4])" % (a.rank_lora, lat, lat, n), "parallelism": f"dp{world}", "global_batch": n * world,
+                           "l2_policy": "activations of one pass (> 10 GB) exceed the 126 MB L2"},
+                "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "microbench: inputs are device tensors by definition of this config"},
+                "gpu_launches": launches, "clocks": clocks.stop() if clocks else None,
+                "roofline": {"bound": "tensor", "kernel": "whole UNet fwd+bwd (tcgen05 GEMM / conv / attention)", "achieved": tf, "peak": sustained,
+                             "unit": "TFLOP/s", "frac": None if tf is None else tf / sustained, "traffic": None, "peak_source": peak_src + ", sustained",
+                             "flops_definition": "2 x forward FLOPs (forward + data gradient; LoRA weight gradients and recompute not counted)"},
+                "eps_abs_mean": float(eps.abs().mean())}
+        if tf is not None:
+            line["roofline"]["achieved"] = 2.0 * n * F_fwd * a.steps / t_dev
+            line["roofline"]["frac"] = line["roofline"]["achieved"] / sustained
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     a = parse()
+    if a.batch == 0:
+        a.batch = CONFIGS[a.config]["batch"]
     _claim_stdout()
     if os.environ.get("COMAT_HOST_ONLY_TIMING"):
         raise SystemExit("bench.py: COMAT_HOST_ONLY_TIMING is set - refusing to emit a bench line (tools/host_issue_time.py is the host-only probe)")
@@ -388,6 +483,8 @@ def main():
         return run_reference(a)
     if a.impl == "gpu_reference":
         return run_gpu_reference(a)
+    if a.config == 5:
+        return run_config5(a)
     import torch
     import torch.distributed as dist
     from comat_b200 import _lib, attention, caption, image_ops, ops, synthetic
@@ -410,16 +507,29 @@ def main():
     dt = torch.float16 if a.dtype == "fp16" else torch.bfloat16
     gan, attrcon = not a.no_gan, not a.no_attrcon
 
-    args = synthetic.default_args(pretrain_model_name="sd_1_5_attrcon" if attrcon else "sd_1_5", train_batch_size=a.batch,
+    sdxl = a.config == 4
+    base = ("sdxl" if sdxl else "sd_1_5") + ("_attrcon" if attrcon else "")
+    args = synthetic.default_args(pretrain_model_name=base, train_batch_size=a.batch,
                                   gradient_accumulation_steps=1, learning_rate=5e-5, learning_rate_D=2e-5, max_grad_norm=0.1,
                                   max_grad_norm_D=1.0, adam_beta1_D=0.0, lora_rank=a.rank_lora, K=a.K, total_step=a.total_step,
                                   gan_loss=gan, gan_model_arch="gansd_1_5", gan_loss_weight=1.0, attrcon_train_steps=2, seed=42,
                                   resolution=256 if a.tiny else 512)
     rank_lora = 8 if a.tiny else a.rank_lora
-    unet_p, vae_p = synthetic.build_sd15(dev, dt, rank=rank_lora, seed=42, tiny=a.tiny)
-    pipe = AttrConcenTrainableSDPipeline(EngineVAE(vae_p, dt), EngineUNet(unet_p, dt))
-    if attrcon:
+    if sdxl:
+        from comat_b200 import containers as Cn
+        from comat_b200.pipelines import AttrConcenTrainableSDXLPipeline
+        unet_p = synthetic.build_sdxl_unet(dev, rank=rank_lora, seed=42, tiny=a.tiny)
+        torch.manual_seed(48)
+        with torch.device(dev):
+            vae_p = Cn.AutoencoderKL(**(dict(block_out_channels=(64, 64, 128, 128)) if a.tiny else {}), scaling_factor=0.13025)
+        vae_p.requires_grad_(False)
+        pipe = AttrConcenTrainableSDXLPipeline(EngineVAE(vae_p, dt), EngineUNet(unet_p, dt))
+        layers = ["up_8", "up_16"] if a.tiny else ["mid_16", "up_16", "up_32"]              # training_script.py:312
+    else:
+        unet_p, vae_p = synthetic.build_sd15(dev, dt, rank=rank_lora, seed=42, tiny=a.tiny)
+        pipe = AttrConcenTrainableSDPipeline(EngineVAE(vae_p, dt), EngineUNet(unet_p, dt))
         layers = ["up_8", "up_16", "up_32"] if a.tiny else ["mid_8", "up_16", "up_32", "up_64"]
+    if attrcon:
         args.train_layer_ls = layers
         register_attention_control(pipe, AttentionStore(layers))
     from comat_b200.blip_engine import BlipEngine
@@ -427,13 +537,16 @@ def main():
     cap = CaptionModelWrapper(["Blip"], [1.0], blip)
     D = None
     if gan:
-        d_unet, _ = synthetic.build_sd15(dev, dt, rank=rank_lora, seed=43, tiny=a.tiny)
+        d_unet, _ = synthetic.build_sd15(dev, dt, rank=rank_lora, seed=43, tiny=a.tiny)     # SD1.5 discriminator, also under SDXL (scripts/sdxl.sh:15)
         D = D_sd(EngineUNet(d_unet, dt))
     pipe.unet.use_graphs = not a.no_graphs
     trainer = CoMatTrainer(args, pipe, cap, D, process_group=None,
                            manual_gc_interval=0 if os.environ.get("COMAT_MANUAL_GC") == "0" else 25)
-    ctx_dim = 64 if a.tiny else 768
-    host_batches = [synthetic.synthetic_batch(a.batch, 1000 * rank + i, ctx_dim, args.resolution, attrcon, gan, pinned=True)
+    ctx_dim = 64 if a.tiny else (2048 if sdxl else 768)
+    sd15_ctx = 64 if a.tiny else 768
+    pooled = 0 if not sdxl else (64 - 6 * 8 if a.tiny else 1280)
+    host_batches = [synthetic.synthetic_batch(a.batch, 1000 * rank + i, ctx_dim, args.resolution, attrcon, gan, pinned=True,
+                                              pooled_dim=pooled, gan_ctx_dim=sd15_ctx)
                     for i in range(4)]
     dev_batches = [synthetic.batch_to_device(b, dev)[0] for b in host_batches]
     h2d_bytes = synthetic.batch_to_device(host_batches[0], dev)[1]
@@ -606,12 +719,14 @@ def main():
         # whole-job aggregate (weak scaling): every rank runs K optimiser steps on its own batch of `--batch` prompts, so the job
         # processes world x K per-GPU-batch steps in t_dev; the data-parallel optimiser advances value / world global steps/s
         value = world * a.steps / t_dev
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        cfgd = CONFIGS[a.config]
+        line = {"metric": cfgd["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * t_dev / a.steps, "host_issue_ms_per_step": host_issue_ms, "memory": mem_note, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.dtype, "data": "synthetic",
-                "config": {"workload": ("TINY-DEBUG " if a.tiny else "") + "SD1.5 512^2 full CoMat (BLIP concept-match + attention-map "
+                "config": {"workload": ("TINY-DEBUG " if a.tiny else "") + cfgd["name"] + " (BLIP concept-match + attention-map "
                            "token/pixel loss on 2 attrcon steps + GAN G/D), S=%d DDPM steps, K=%d, batch %d/GPU, LoRA r=%d, cfg 7.5 "
-                           "(BASELINE configs[1])" % (a.total_step, a.K, a.batch, rank_lora),
+                           "(%s)" % (a.total_step, a.K, a.batch, rank_lora, cfgd["tag"]),
+                           "bench_config": a.config, "algorithmic_tflop_per_step_nominal": cfgd["tflop"],
                            "global_batch": a.batch * world, "parallelism": f"dp{world}", "cuda_graphs": not a.no_graphs,
                            "l2_policy": "inputs rotate over 4 batches; per-step working set (weights 7 GB + activations > 50 GB) exceeds the 126 MB L2",
                            "samples_per_sec": value * a.batch, "global_optimizer_steps_per_sec": value / world,
@@ -629,8 +744,8 @@ def main():
                                            "calls that fell back to aten/HF kernels (shapes the native kernels do not cover)"},
                 "e2e": {"value": world * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof,
-                "losses": {k: float(v) for k, v in logs.items() if hasattr(v, "numel") and v.numel() == 1}}
-        if not a.no_gpu_reference:
+                "losses": {k: float(v.detach()) for k, v in logs.items() if hasattr(v, "numel") and v.numel() == 1}}
+        if not a.no_gpu_reference and a.config == 2:
             # the denominator of BASELINE's ">= 10x the reference's own 1xB200 path" target, measured on this same box right after the
             # product's timed region (the product's weights / graphs stay resident: ~60 GB of the 180 GB)
             try:
@@ -640,9 +755,9 @@ def main():
                 line["gpu_reference"] = gr
             except Exception as e:  # a baseline must never take the bench line down
                 line["gpu_reference"] = {"value": None, "unit": UNIT, "error": repr(e)[:300]}
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and a.config == 2:
             try:
-                times, threads, flops = cpu_oracle_sample(steps=4, warmup=0, tiny=a.tiny)
+                times, threads, flops = cpu_oracle_sample(steps=2, warmup=0, tiny=a.tiny)
                 v = (len(times) / sum(times)) * (flops / (TFLOP_PER_STEP_CFG2 * 1e12))
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                         "sample": f"{len(times)} steps of [{SAMPLE_DESC}] = {sum(times):.1f} s, {flops / 1e12:.2f} TFLOP counted per step "

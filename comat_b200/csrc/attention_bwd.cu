@@ -38,6 +38,10 @@ struct AttnBwdKP {
   uint32_t idesc_s, idesc_acc;
   const int* kv_lens;
   int causal;
+  int nsplit;             // MODE 1 only: the query range is split over nsplit CTAs per key tile (cross-attention: 77 keys = ONE key tile,
+                          // so n*H CTAs would walk all query tiles serially); partial dK / dV are added into fp32 scratch with atomics
+  float* acc32_0;         // fp32 (n, Lk, H*d) scratch for dK (x scale) when nsplit > 1
+  float* acc32_1;         // ... for dV
 };
 
 template <int D, int MODE>
@@ -99,10 +103,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * AB_ROWS;          // first query (MODE 0) / key (MODE 1) of this CTA
+  const int nsplit = (MODE == 1 && p.nsplit > 1) ? p.nsplit : 1;
+  const int x0 = (blockIdx.x / nsplit) * AB_ROWS;          // first query (MODE 0) / key (MODE 1) of this CTA
   const int h = blockIdx.y, b = blockIdx.z;
   const int bh = b * p.H + h;
-  const int NI = p.n_inner;
+  const int split = blockIdx.x % nsplit;
+  const int it0 = (int)((long long)p.n_inner * split / nsplit);                  // this CTA's inner tiles [it0, it0 + NI)
+  const int NI = (int)((long long)p.n_inner * (split + 1) / nsplit) - it0;
   const int Lx = (MODE == 0) ? p.Lq : p.Lk;     // rows of the outer dimension
   const int Ly = (MODE == 0) ? p.Lk : p.Lq;     // inner dimension
 
@@ -132,7 +139,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
         mbar_wait(&st_empty[stage], phase ^ 1);
         unsigned char* st = sStage + stage * Cf::STAGE_BYTES;
         mbar_expect_tx(&st_full[stage], 2 * Cf::NAT_BYTES + Cf::VEC_BYTES);
-        const int y0 = it * Cf::BY;
+        const int y0 = (it0 + it) * Cf::BY;
         for (int c = 0; c < Cf::NKC; ++c) {
           tma_load_3d(st + c * Cf::BY * 128, &tmB1, &st_full[stage], c * 64, h, b * Ly + y0);
           tma_load_3d(st + Cf::NAT_BYTES + c * Cf::BY * 128, &tmB2, &st_full[stage], c * 64, h, b * Ly + y0);
@@ -217,7 +224,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       mbar_wait(s_full, it & 1);
       if (MODE == 1) mbar_wait(&st_full[stage], phase);      // acquire the TMA-written lse / D slices for generic loads
       tc_fence_after();
-      const int y0 = it * Cf::BY;
+      const int y0 = (it0 + it) * Cf::BY;
       const float* vec = reinterpret_cast<const float*>(sStage + stage * Cf::STAGE_BYTES + 2 * Cf::NAT_BYTES);
       // warp-uniform: no external dP, no padding / causal edge inside this (warp, tile) -> predicate-free fast path
       bool fast_w;
@@ -313,21 +320,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       const float mul = (MODE == 0 || o == 1) ? p.scale : 1.f;
       void* outp = (MODE == 0) ? p.out0 : (o == 0 ? p.out1 : p.out0);
       T* op = reinterpret_cast<T*>(outp) + ((size_t)b * Lx + xrow) * p.out_ld + (size_t)h * p.d;
+      float* ap = nullptr;                                   // split-query mode: fp32 partial sums, converted by ab_cvt_kernel
+      if (MODE == 1 && nsplit > 1) ap = (o == 0 ? p.acc32_1 : p.acc32_0) + ((size_t)b * Lx + xrow) * p.out_ld + (size_t)h * p.d;
 #pragma unroll 1
       for (int c0 = (MODE == 0) ? half * 16 : 0; c0 < Cf::DN; c0 += (MODE == 0) ? 32 : 16) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(trow + (uint32_t)((o == 0 ? Cf::COL_ACC0 : Cf::COL_ACC1) + c0), v);
         tmem_ld_wait();
         if (row_ok) {
+          if (ap != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 8) {
-            if (c0 + i + 8 <= D) {
-              uint4 u;
-              u.x = ab_pack2<T>(__uint_as_float(v[i]) * mul, __uint_as_float(v[i + 1]) * mul);
-              u.y = ab_pack2<T>(__uint_as_float(v[i + 2]) * mul, __uint_as_float(v[i + 3]) * mul);
-              u.z = ab_pack2<T>(__uint_as_float(v[i + 4]) * mul, __uint_as_float(v[i + 5]) * mul);
-              u.w = ab_pack2<T>(__uint_as_float(v[i + 6]) * mul, __uint_as_float(v[i + 7]) * mul);
-              *reinterpret_cast<uint4*>(op + c0 + i) = u;
+            for (int i = 0; i < 16; i += 4)
+              if (c0 + i + 4 <= D)
+                atomicAdd(reinterpret_cast<float4*>(ap + c0 + i), make_float4(__uint_as_float(v[i]) * mul, __uint_as_float(v[i + 1]) * mul,
+                                                                               __uint_as_float(v[i + 2]) * mul, __uint_as_float(v[i + 3]) * mul));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              if (c0 + i + 8 <= D) {
+                uint4 u;
+                u.x = ab_pack2<T>(__uint_as_float(v[i]) * mul, __uint_as_float(v[i + 1]) * mul);
+                u.y = ab_pack2<T>(__uint_as_float(v[i + 2]) * mul, __uint_as_float(v[i + 3]) * mul);
+                u.z = ab_pack2<T>(__uint_as_float(v[i + 4]) * mul, __uint_as_float(v[i + 5]) * mul);
+                u.w = ab_pack2<T>(__uint_as_float(v[i + 6]) * mul, __uint_as_float(v[i + 7]) * mul);
+                *reinterpret_cast<uint4*>(op + c0 + i) = u;
+              }
             }
           }
         }
@@ -382,6 +399,17 @@ __global__ void __launch_bounds__(256) ab_prep_kernel(const T* __restrict__ o, c
   }
 }
 
+// split-query mode: fp32 partial sums of dK / dV -> 16-bit outputs
+template <typename T>
+__global__ void __launch_bounds__(256) ab_cvt_kernel(const float* __restrict__ a, const float* __restrict__ b2, T* __restrict__ oa,
+                                                     T* __restrict__ ob, long long n) {
+  pdl_grid_dependency_sync();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  oa[i] = from_f32<T>(a[i]);
+  ob[i] = from_f32<T>(b2[i]);
+}
+
 template <int D, int MODE, typename T>
 static int launch_ab(const CUtensorMap* m, const AttnBwdKP& kp, dim3 grid, cudaStream_t st) {
   using Cf = ABCfg<D, MODE>;
@@ -424,7 +452,23 @@ static int run_bwd(const void* q, const void* k, const void* v, const void* dO, 
   if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   kp.n_inner = (Lq + BY - 1) / BY;
   kp.out0 = dk; kp.out1 = dv;
-  return launch_ab<D, 1, T>(m, kp, dim3((Lk + AB_ROWS - 1) / AB_ROWS, H, n), st);
+  const int xtiles = (Lk + AB_ROWS - 1) / AB_ROWS;
+  // few key tiles (cross-attention over 77 text tokens: one) and many query tiles: split the query range so the launch fills the GPU
+  int nsplit = 1;
+  if (kp.acc32_0 != nullptr && (long long)xtiles * H * n < num_sms() && kp.n_inner >= 8) {
+    nsplit = (int)((2LL * num_sms() + (long long)xtiles * H * n - 1) / ((long long)xtiles * H * n));
+    if (nsplit > kp.n_inner / 4) nsplit = kp.n_inner / 4;
+    if (nsplit < 1) nsplit = 1;
+  }
+  kp.nsplit = nsplit;
+  if (nsplit == 1) return launch_ab<D, 1, T>(m, kp, dim3(xtiles, H, n), st);
+  const long long cnt = (long long)n * Lk * hd;
+  if (cudaMemsetAsync(kp.acc32_0, 0, (size_t)cnt * 2 * sizeof(float), st) != cudaSuccess) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
+  rc = launch_ab<D, 1, T>(m, kp, dim3(xtiles * nsplit, H, n), st);
+  if (rc) return rc;
+  launch_k(ab_cvt_kernel<T>, (unsigned)((cnt + 255) / 256), 256, 0, st, (const float*)kp.acc32_0, (const float*)kp.acc32_1, (T*)dk, (T*)dv, cnt);
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
 }
 
 }  // namespace comat
@@ -433,7 +477,9 @@ using namespace comat;
 extern "C" size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int H, int d) {
   const size_t Lqp = (size_t)(Lq + 127) / 128 * 128, Lkp = (size_t)(Lk + 127) / 128 * 128;
   (void)Lkp; (void)d;
-  return (size_t)n * H * Lqp * 8 + 1024;       // padded lse (x log2 e) and D vectors
+  // padded lse (x log2 e) and D vectors + fp32 dK / dV partial sums of the split-query mode (short key sequences only)
+  const size_t split = (Lk <= 1024) ? (size_t)n * Lk * H * d * 8 + 256 : 0;
+  return (size_t)n * H * Lqp * 8 + 1024 + split;
 }
 
 extern "C" int comat_attention_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
@@ -465,6 +511,11 @@ extern "C" int comat_attention_bwd_strided(const void* q, const void* k, const v
   kp.scale = scale; kp.scale_log2 = scale * 1.4426950408889634f;
   kp.kv_lens = kv_lens; kp.causal = causal;
   kp.lse_pad = lse_pad; kp.D_pad = D_pad; kp.dp_ext = dp_ext; kp.out_ld = (long long)H * d;
+  if (Lk <= 1024) {                               // split-query scratch lives behind the two padded vectors (workspace_bytes sizes it)
+    float* sc = D_pad + (size_t)n * H * Lqp;
+    sc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sc) + 255) & ~uintptr_t(255));
+    kp.acc32_0 = sc; kp.acc32_1 = sc + (size_t)n * Lk * H * d;
+  }
   const int fmt = dtype == COMAT_BF16 ? 1 : 0;
 #define AB_CASE(DD)                                                                                                          \
   case DD:                                                                                                                   \

@@ -32,9 +32,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // normalisation whose statistics span the whole image) and written once.
 // Both kernels use the same thread layout: a block covers rows_par rows x (C/8) 16-byte column vectors, each thread
 // keeps its 8 channels' constants in registers and walks rows with four independent 16-byte loads in flight.
-constexpr int GN_UNROLL = 4;
 
-template <typename T, int MODE>   // MODE 0: stats of x ; MODE 1: backward sums
+template <typename T, int MODE, int GN_UNROLL>   // MODE 0: stats of x ; MODE 1: backward sums.  GN_UNROLL = 16-byte loads in flight per thread
 __global__ void __launch_bounds__(512) gn_partial_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 const float* __restrict__ mean_rstd, float* __restrict__ part,
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(const T* __restrict__ x
 // Pass 2.  Every block first reduces the chunk partials of its image (fixed order, so the result does not depend on the
 // grid) into per-group (mean, rstd) [MODE 0; block 0 of each image also saves them for the backward] or the backward's
 // (mean(a), mean(a*xhat)) [MODE 1]; then y = x*A + B with A = rstd*gamma, B = beta - mean*A  (or dx) streams through.
-template <typename T, int MODE>   // MODE 0: y = [silu](xhat*gamma+beta) ; MODE 1: dx
+template <typename T, int MODE, int GN_UNROLL>   // MODE 0: y = [silu](xhat*gamma+beta) ; MODE 1: dx
 __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ part, float* __restrict__ mean_rstd,
@@ -512,15 +511,23 @@ using namespace comat;
   else return COMAT_ERR_UNSUPPORTED;
 
 static inline int gn_threads(int C) { int v = C / 8; return v <= 256 ? 256 : ((v + 31) / 32) * 32; }
+static inline int gn_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && atoi(e) > 0) ? atoi(e) : dflt;
+}
+// tuning knobs (measured defaults, profiles/r02_groupnorm_bench.md): loads in flight per thread and CTAs per SM of the two passes
+static inline int gn_unroll() { static int u = gn_env("COMAT_GN_UNROLL", 4); return u; }
 static inline int gn_chunks(int n, int HW) {
-  int c = (2 * num_sms() + n - 1) / n;
+  static const int per_sm = gn_env("COMAT_GN_PARTIAL_CTAS", 2);
+  int c = (per_sm * num_sms() + n - 1) / n;
   if (c > HW / 16) c = HW / 16;
   return c < 1 ? 1 : c;
 }
 // row blocks of the apply pass: ~8 blocks per SM so enough 16-byte loads are in flight to cover HBM latency
 static inline int gn_apply_chunks(int n, int HW, int rows_par) {
-  int c = (8 * num_sms() + n - 1) / n;
-  const int cap = HW / (rows_par * GN_UNROLL) > 0 ? HW / (rows_par * GN_UNROLL) : 1;
+  static const int per_sm = gn_env("COMAT_GN_APPLY_CTAS", 8);
+  int c = (per_sm * num_sms() + n - 1) / n;
+  const int cap = HW / (rows_par * gn_unroll()) > 0 ? HW / (rows_par * gn_unroll()) : 1;
   if (c > cap) c = cap;
   return c < 1 ? 1 : c;
 }
@@ -529,10 +536,12 @@ namespace comat {
 int gn_fused_launch(int mode, const void* x, const void* dy, void* out, const float* gamma, const float* beta, float* mean_rstd,
                     int n, int HW, int C, int G, float eps, int silu, int dtype, cudaStream_t st);     // groupnorm_fused.cu
 }
-// COMAT_GN=twopass selects the two-launch kernels below (A/B measurements); default: the single-launch cluster kernel
+// COMAT_GN=fused selects the single-launch cluster kernel (groupnorm_fused.cu).  Default: the two-launch kernels below - measured
+// on B200 (profiles/r02_groupnorm_bench.md) the cluster kernel wins 10-30 % on slabs that fit in shared memory and loses up to 2x on
+// the VAE-sized ones, and the whole train step is the same to 0.1 % (505.5 vs 505.0 ms), so the simpler pair stays the product path.
 static inline bool gn_use_fused() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("COMAT_GN"); on = (e && !strcmp(e, "twopass")) ? 0 : 1; }
+  if (on < 0) { const char* e = getenv("COMAT_GN"); on = (e && !strcmp(e, "fused")) ? 1 : 0; }
   return on == 1;
 }
 
@@ -550,8 +559,13 @@ extern "C" int comat_groupnorm_fwd(const void* x, void* y, const float* gamma, c
   const int thr = gn_threads(C), achunks = gn_apply_chunks(n, HW, thr / (C / 8));
   const float inv_cnt = 1.f / ((float)HW * (C / G));
   DISPATCH_T(dtype, {
-    launch_k(gn_partial_kernel<T, 0>, dim3(chunks, n), thr, 2 * C * sizeof(float), st, (const T*)x, nullptr, gamma, beta, nullptr, ws, HW, C, G, chunks, 0);
-    launch_k(gn_apply_kernel<T, 0>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, nullptr, (T*)y, gamma, beta, ws, mean_rstd, HW, C, G, chunks, achunks, inv_cnt, eps, silu);
+    if (gn_unroll() >= 8) {
+      launch_k(gn_partial_kernel<T, 0, 8>, dim3(chunks, n), thr, 2 * C * sizeof(float), st, (const T*)x, nullptr, gamma, beta, nullptr, ws, HW, C, G, chunks, 0);
+      launch_k(gn_apply_kernel<T, 0, 8>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, nullptr, (T*)y, gamma, beta, ws, mean_rstd, HW, C, G, chunks, achunks, inv_cnt, eps, silu);
+    } else {
+      launch_k(gn_partial_kernel<T, 0, 4>, dim3(chunks, n), thr, 2 * C * sizeof(float), st, (const T*)x, nullptr, gamma, beta, nullptr, ws, HW, C, G, chunks, 0);
+      launch_k(gn_apply_kernel<T, 0, 4>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, nullptr, (T*)y, gamma, beta, ws, mean_rstd, HW, C, G, chunks, achunks, inv_cnt, eps, silu);
+    }
   });
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
@@ -569,8 +583,8 @@ extern "C" int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, cons
   const int thr = gn_threads(C), achunks = gn_apply_chunks(n, HW, thr / (C / 8));
   const float inv_cnt = 1.f / ((float)HW * (C / G));
   DISPATCH_T(dtype, {
-    launch_k(gn_partial_kernel<T, 1>, dim3(chunks, n), thr, 2 * C * sizeof(float), st, (const T*)x, (const T*)dy, gamma, beta, mean_rstd, ws, HW, C, G, chunks, silu);
-    launch_k(gn_apply_kernel<T, 1>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, (const T*)dy, (T*)dx, gamma, beta, ws, const_cast<float*>(mean_rstd), HW, C, G, chunks, achunks, inv_cnt, 0.f, silu);
+    launch_k(gn_partial_kernel<T, 1, 4>, dim3(chunks, n), thr, 2 * C * sizeof(float), st, (const T*)x, (const T*)dy, gamma, beta, mean_rstd, ws, HW, C, G, chunks, silu);
+    launch_k(gn_apply_kernel<T, 1, 4>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, (const T*)dy, (T*)dx, gamma, beta, ws, const_cast<float*>(mean_rstd), HW, C, G, chunks, achunks, inv_cnt, 0.f, silu);
   });
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;

@@ -171,9 +171,11 @@ def random_mask(g, size=512, empty=False):
 
 
 def synthetic_batch(B: int, seed: int, ctx_dim: int = 768, res: int = 512, attrcon: bool = True, gan: bool = True,
-                    pinned: bool = False) -> Dict:
+                    pinned: bool = False, pooled_dim: int = 0, gan_ctx_dim: int = 0) -> Dict:
     """Host-side batch (what a dataloader would hand over): prompt / null embeddings, BLIP token ids, attribute token
-    lists + per-word masks, 'real' latents for the discriminator."""
+    lists + per-word masks, 'real' latents for the discriminator.  ``pooled_dim`` > 0 adds SDXL's pooled text
+    embeddings (B, pooled_dim); ``gan_ctx_dim``: context width of the discriminator's own null embedding when it differs from the
+    generator's (SDXL generator + SD1.5 discriminator, scripts/sdxl.sh:15)."""
     g = torch.Generator().manual_seed(seed)
     rr = random.Random(seed)
     lat = res // 8
@@ -204,8 +206,12 @@ def synthetic_batch(B: int, seed: int, ctx_dim: int = 768, res: int = 512, attrc
             words.append(ws)
             masks.append(torch.cat([random_mask(g, res, empty=(rr.random() < 0.1)) for _ in range(nw)]))   # (nw,1,res,res)
         b["words"], b["masks_host"] = words, masks
+    if pooled_dim:
+        b["pooled_prompt_embeds"] = torch.randn(B, pooled_dim, generator=g)
+        b["pooled_null_embeds"] = torch.randn(1, pooled_dim, generator=g).expand(B, -1).contiguous()
     if gan:
-        b["gan_null_embeds"] = b["null_embeds"].clone()
+        b["gan_null_embeds"] = (b["null_embeds"].clone() if not gan_ctx_dim or gan_ctx_dim == ctx_dim else
+                                torch.randn(1, 77, gan_ctx_dim, generator=g).expand(B, -1, -1).contiguous())
         b["real_latents"] = torch.randn(B, 4, lat, lat, generator=g)
     if pinned:
         for k, v in list(b.items()):

@@ -157,3 +157,15 @@ def test_label_smoothed_ce_fwd_bwd():
     d = BE.ce_bwd(logits, labels, stats, out2, torch.ones(1, device="cuda"), V, Vpad, eps, torch.float16)
     assert float(d[:, V:].abs().max()) == 0
     assert rel(d[:, :V].float(), lr.grad) < 2e-3
+
+
+def test_groupnorm_fused_cluster_kernel_in_subprocess():
+    """COMAT_GN=fused (read once per process) routes GroupNorm to the single-launch cluster kernel (csrc/groupnorm_fused.cu): the
+    same parity cases, in a child interpreter."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, COMAT_GN="fused")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_elementwise_gpu.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "test_groupnorm and not subprocess"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout and "failed" not in r.stdout

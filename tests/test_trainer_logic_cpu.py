@@ -115,3 +115,30 @@ def test_train_step_matches_oracle_step(monkeypatch):
     out = tr.train_step(batch)
     assert "D_loss" in out and torch.isfinite(out["step_loss"])
     assert float((tr.optimizer.flat - before).abs().max()) > 0
+
+
+def test_dynamic_loss_scale_follows_the_overflow_counter():
+    """GradScaler's schedule driven by the optimiser's device-side skip counter (one step late, no host sync): halve after an
+    overflow-skipped step, double after ``scale_growth_interval`` clean steps, bf16 executors (scale 1) are never touched."""
+    from types import SimpleNamespace
+    from comat_b200.trainer import CoMatTrainer
+    tr = object.__new__(CoMatTrainer)
+    fp16_a, fp16_b, bf16 = SimpleNamespace(grad_scale=4096.0), SimpleNamespace(grad_scale=16384.0), SimpleNamespace(grad_scale=1.0)
+    tr._scaled = [m for m in (fp16_a, fp16_b, bf16) if m.grad_scale != 1.0]
+    tr.scale_growth_interval, tr._clean_steps, tr.scale_min, tr.scale_max = 3, 0, 1.0, 65536.0
+    feed = []
+    tr.optimizer = SimpleNamespace(poll_overflow=lambda: feed.pop(0) if feed else None)
+    tr.D_optimizer = None
+    tr._update_loss_scale()                                     # nothing landed yet
+    assert fp16_a.grad_scale == 4096.0
+    feed[:] = [(1, 5)]
+    tr._update_loss_scale()                                     # one skipped step seen -> halve
+    assert (fp16_a.grad_scale, fp16_b.grad_scale, bf16.grad_scale) == (2048.0, 8192.0, 1.0)
+    feed[:] = [(0, 6), (0, 7), (0, 8)]
+    for _ in range(3):
+        tr._update_loss_scale()
+    assert (fp16_a.grad_scale, fp16_b.grad_scale) == (4096.0, 16384.0) and tr._clean_steps == 0
+    fp16_a.grad_scale = 1.0
+    feed[:] = [(2, 8)]
+    tr._update_loss_scale()
+    assert fp16_a.grad_scale == 1.0                             # floor
