@@ -55,6 +55,9 @@ def parse():
     p.add_argument("--no_gan", action="store_true")
     p.add_argument("--no_attrcon", action="store_true")
     p.add_argument("--no_graphs", action="store_true", help="disable CUDA-graph replay of the no-grad UNet forwards")
+    p.add_argument("--graph_taped", default="auto", choices=["auto", "on", "off"],
+                   help="CUDA-graph the back-propagated UNet calls too (forward + backward graph pairs); auto = on where a call is "
+                        "host-bound (SDXL at batch 1, config 4), off for the SD1.5 batch-4 headline (measured: no gain, +40 GB)")
     p.add_argument("--kineto_steps", type=int, default=1, help="consecutive steps inside the --kineto_step window")
     p.add_argument("--sync_debug", action="store_true", help="run ONE step with torch.cuda.set_sync_debug_mode('warn') and list the host-sync call sites")
     p.add_argument("--gemm_shapes", default="", help="write the per-shape GEMM table of the instrumented step to this path")
@@ -540,6 +543,10 @@ def main():
         d_unet, _ = synthetic.build_sd15(dev, dt, rank=rank_lora, seed=43, tiny=a.tiny)     # SD1.5 discriminator, also under SDXL (scripts/sdxl.sh:15)
         D = D_sd(EngineUNet(d_unet, dt))
     pipe.unet.use_graphs = not a.no_graphs
+    taped = (not a.no_graphs) and (a.graph_taped == "on" or (a.graph_taped == "auto" and a.config == 4))
+    pipe.unet.graph_taped = taped
+    if D is not None:
+        D.unet.graph_taped = taped
     trainer = CoMatTrainer(args, pipe, cap, D, process_group=None,
                            manual_gc_interval=0 if os.environ.get("COMAT_MANUAL_GC") == "0" else 25)
     ctx_dim = 64 if a.tiny else (2048 if sdxl else 768)
@@ -699,13 +706,15 @@ def main():
 
     # ---- roofline of the dominant kernel family: one instrumented step (per-launch CUDA events)
     # (eager launches for this one step: kernels replayed from a CUDA graph do not pass through ops.gemm's event pair)
-    graphs_were = pipe.unet.use_graphs
-    pipe.unet.use_graphs = False
+    graphs_were, taped_were = pipe.unet.use_graphs, pipe.unet.graph_taped
+    pipe.unet.use_graphs = pipe.unet.graph_taped = False
+    if D is not None:
+        D.unet.graph_taped = False
     ops.PROFILE = prof = {"flops": 0.0, "events": []}
     trainer.train_step(dev_batches[0])
     torch.cuda.synchronize()
     ops.PROFILE = None
-    pipe.unet.use_graphs = graphs_were
+    pipe.unet.use_graphs, pipe.unet.graph_taped = graphs_were, taped_were
     gemm_s = sum(ev[0].elapsed_time(ev[1]) for ev in prof["events"]) * 1e-3
     sustained, burst, hbm, peak_src = load_peaks()
     step_s = t_dev / a.steps
@@ -728,6 +737,7 @@ def main():
                            "(%s)" % (a.total_step, a.K, a.batch, rank_lora, cfgd["tag"]),
                            "bench_config": a.config, "algorithmic_tflop_per_step_nominal": cfgd["tflop"],
                            "global_batch": a.batch * world, "parallelism": f"dp{world}", "cuda_graphs": not a.no_graphs,
+                           "cuda_graphs_taped_calls": bool(taped),
                            "l2_policy": "inputs rotate over 4 batches; per-step working set (weights 7 GB + activations > 50 GB) exceeds the 126 MB L2",
                            "samples_per_sec": value * a.batch, "global_optimizer_steps_per_sec": value / world,
                            "value_definition": "per-GPU-batch train-steps per second summed over ranks (= n_gpus x global optimiser steps/s)",

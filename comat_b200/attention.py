@@ -18,9 +18,9 @@ LIBRARY_CALLS = 0        # always 0: kept so bench.py's per-module sum stays mea
 NATIVE_HEAD_DIMS = (16, 32, 40, 64, 80, 128, 160)
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 _lib.register_signature("comat_attention_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
-_lib.register_signature("comat_attention_fwd_strided", [_vp] * 7 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _vp])
+_lib.register_signature("comat_attention_fwd_strided", [_vp] * 7 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _i, _vp])
 _lib.register_signature("comat_attention_bwd", [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _i, _vp, _i, _vp])
-_lib.register_signature("comat_attention_bwd_strided", [_vp] * 12 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _vp])
+_lib.register_signature("comat_attention_bwd_strided", [_vp] * 12 + [_i] * 5 + [C.c_longlong] * 3 + [_f, _i, _vp, _i, _i, _vp])
 _DT = {torch.float16: 1, torch.bfloat16: 2}
 
 
@@ -39,8 +39,9 @@ def _rows(x):
     return x.contiguous(), Cc
 
 
-def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False, kv_lens=None, causal=False):
-    """tcgen05 fused attention forward (csrc/attention.cu).  returns (o, probs | None, lse | None)"""
+def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False, kv_lens=None, causal=False, export_from=0):
+    """tcgen05 fused attention forward (csrc/attention.cu).  returns (o, probs | None, lse | None).  ``export_from`` = first sample
+    whose probabilities are exported (probs covers samples export_from .. n-1)."""
     (q, q_ld), (k, k_ld), (v, v_ld) = _rows(q), _rows(k), _rows(v)
     n, Lq, Cq = q.shape
     Lk = k.shape[1]
@@ -50,12 +51,13 @@ def attention_fwd_native(q, k, v, heads, export_probs=False, need_lse=False, kv_
     L.comat_attention_workspace_bytes.argtypes = [_i, _i, _i, _i]
     ws = torch.empty(int(L.comat_attention_workspace_bytes(n, Lk, heads, d)), dtype=torch.uint8, device=q.device)
     o = torch.empty(n, Lq, Cq, dtype=q.dtype, device=q.device)
-    probs = torch.empty(n * heads, Lq, Lk, dtype=torch.float32, device=q.device) if export_probs else None
+    probs = torch.empty((n - export_from) * heads, Lq, Lk, dtype=torch.float32, device=q.device) if export_probs else None
     lse = torch.empty(n * heads, Lq, dtype=torch.float32, device=q.device) if need_lse else None
     _lib.check(L.comat_attention_fwd_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
                                              None if probs is None else probs.data_ptr(), None if lse is None else lse.data_ptr(),
                                              ws.data_ptr(), n, Lq, Lk, heads, d, q_ld, k_ld, v_ld, float(d) ** -0.5, _DT[q.dtype],
-                                             None if kv_lens is None else kv_lens.data_ptr(), int(causal), _lib.stream_ptr()),
+                                             None if kv_lens is None else kv_lens.data_ptr(), int(causal), int(export_from) if export_probs else 0,
+                                             _lib.stream_ptr()),
                "attention_fwd")
     _lib.count_launch(1)
     return o, probs, lse
@@ -95,8 +97,8 @@ def attention_unfused_bwd(q, k, v, ps, do):
     return torch.stack(dq), torch.stack(dk), torch.stack(dv)
 
 
-def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
-    """q: (n, Lq, C), k/v: (n, Lk, C) 16-bit.  returns (o (n, Lq, C), probs fp32 (n*heads, Lq, Lk) | None, saved)"""
+def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False, export_from=0):
+    """q: (n, Lq, C), k/v: (n, Lk, C) 16-bit.  returns (o (n, Lq, C), probs fp32 ((n - export_from)*heads, Lq, Lk) | None, saved)"""
     if (heads == 1 and not export_probs and q.is_cuda and q.dtype in _DT and q.shape[-1] > 160
             and q.shape[-1] % 64 == 0 and k.shape[1] % 8 == 0 and k.shape[1] <= 8192):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
@@ -105,14 +107,14 @@ def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
     if not native_supported(q, k, heads, export_probs):
         raise _lib.ComatError(f"attention: no native kernel for this call (device {q.device.type}, dtype {q.dtype}, head dim "
                               f"{q.shape[-1] // heads}, keys {k.shape[1]}, export={export_probs}); comat_b200 has no fallback path")
-    o, probs, lse = attention_fwd_native(q, k, v, heads, export_probs, need_lse=need_bwd)
+    o, probs, lse = attention_fwd_native(q, k, v, heads, export_probs, need_lse=need_bwd, export_from=export_from)
     if not need_bwd:
         return o, probs, None
-    return o, probs, ("native", q, k, v, o, lse, probs, heads)          # strided views are read in place by the backward too
+    return o, probs, ("native", q, k, v, o, lse, probs, heads, export_from)   # strided views are read in place by the backward too
 
 
-def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None, causal=False):
-    """tcgen05 fused attention backward (csrc/attention_bwd.cu): (dq, dk, dv)."""
+def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None, causal=False, dp_from=0):
+    """tcgen05 fused attention backward (csrc/attention_bwd.cu): (dq, dk, dv).  ``dp_from``: first sample ``probs`` / ``dprobs`` cover."""
     (q, q_ld), (k, k_ld), (v, v_ld) = _rows(q), _rows(k), _rows(v)
     n, Lq, Cq = q.shape
     Lk = k.shape[1]
@@ -131,7 +133,8 @@ def attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, kv_lens=None
                                              None if dprobs is None else probs.data_ptr(), None if dprobs is None else dprobs.data_ptr(),
                                              dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), n, Lq, Lk, heads, d,
                                              q_ld, k_ld, v_ld, float(d) ** -0.5, _DT[q.dtype],
-                                             None if kv_lens is None else kv_lens.data_ptr(), int(causal), _lib.stream_ptr()),
+                                             None if kv_lens is None else kv_lens.data_ptr(), int(causal), int(dp_from) if dprobs is not None else 0,
+                                             _lib.stream_ptr()),
                "attention_bwd")
     _lib.count_launch(3)          # row-statistics prep + dQ kernel + dK/dV kernel
     return dq, dk, dv
@@ -141,5 +144,5 @@ def attention_bwd(saved, do, dprobs):
     if saved[0] == "unfused":
         _, q, k, v, ps = saved
         return attention_unfused_bwd(q, k, v, ps, do)
-    _, q, k, v, o, lse, probs, heads = saved
-    return attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs)
+    _, q, k, v, o, lse, probs, heads, export_from = saved
+    return attention_bwd_native(q, k, v, o, lse, probs, heads, do, dprobs, dp_from=export_from)

@@ -35,7 +35,9 @@ struct AttnKP {
   float scale_log2;    // scale * log2(e)
   float scale;
   void* out;           // (n, Lq, H*d) 16-bit
-  float* probs;        // (n*H, Lq, Lk) fp32 or null (requires n_kv_tiles <= 2)
+  float* probs;        // ((n - probs_b0)*H, Lq, Lk) fp32 or null (requires n_kv_tiles <= 2)
+  int probs_b0;        // first sample whose probabilities are exported (attrcon: the conditional half of a CFG batch)
+  int probs_staged;    // export through shared memory + one bulk copy per CTA (needs 16-byte aligned tiles)
   float* lse;          // (n*H, Lq) fp32 or null
   long long out_ld;    // H*d
   uint32_t idesc_qk, idesc_pv;
@@ -317,10 +319,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       if (row_ok && p.lse != nullptr) p.lse[((size_t)b * p.H + h) * p.Lq + m0 + r] = m_used * p.scale + logf(l_run);
     }
-    if (p.probs != nullptr) {
+    if (p.probs != nullptr && b >= p.probs_b0) {
       // at most two key tiles: both score buffers are still in TMEM (columns = key index); write softmax(S) as fp32
-      // (n*H, Lq, Lk).  tcgen05.ld is .sync.aligned: the whole warp executes the loads, only the stores are predicated.
-      float* pp = p.probs + (((size_t)b * p.H + h) * p.Lq + m0 + r) * p.Lk;
+      // ((n - b0)*H, Lq, Lk).  tcgen05.ld is .sync.aligned: the whole warp executes the loads, only the stores are predicated.
+      // A CTA's 128 rows x Lk probabilities are ONE contiguous block of the export tensor: the rows are staged in the (now idle)
+      // K/V + P shared-memory buffers - row pitch Lk = 77 words is odd, so the per-row writes are bank-conflict free - and leave
+      // with one bulk copy.  (r01 wrote them straight from registers: 32 lanes x 32 different rows per store instruction, 4-byte
+      // pieces of 32 sectors, 520 GB/s; profiles/r02_xattn_ncu.md.)
+      float* tile_g = p.probs + (((size_t)(b - p.probs_b0) * p.H + h) * p.Lq + m0) * p.Lk;
+      float* pp = tile_g + (size_t)r * p.Lk;
+      const int rows_valid = min(ATT_BM, p.Lq - m0);
+      constexpr int CAP = Cf::STAGES * Cf::KV_STAGE + 2 * Cf::P_BYTES;
+      const bool staged = p.probs_staged && ((rows_valid * p.Lk) & 3) == 0 && ATT_BM * p.Lk * 4 <= CAP;     // CTA-uniform
+      float* st = reinterpret_cast<float*>(sKV) + (size_t)r * p.Lk;
       const float mneg = m_used * p.scale_log2;
 #pragma unroll 1
       for (int c0 = 0; c0 < p.Lk; c0 += 32) {
@@ -328,12 +339,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
         tmem_ld_wait();
         if (row_ok) {
+          float* dst = staged ? st : pp;
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Lk) pp[c0 + i] = fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - mneg) * inv_l;
+            if (c0 + i < p.Lk) dst[c0 + i] = fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - mneg) * inv_l;
         }
       }
       tc_fence_before();
+      if (staged) {
+        fence_proxy_async_smem();                              // generic-proxy smem writes -> visible to the bulk-copy engine
+        asm volatile("bar.sync 1, 128;" ::: "memory");         // the four softmax warps
+        if (warp == 2 && lane == 0) {
+          bulk_s2g(tile_g, sKV, (uint32_t)(rows_valid * p.Lk * 4));
+          bulk_commit();
+          bulk_wait_read<0>();                                 // shared memory stays valid until the copy has read it
+        }
+      }
     }
   }
   __syncthreads();
@@ -363,8 +384,10 @@ extern "C" size_t comat_attention_workspace_bytes(int n, int Lk, int H, int d) {
 
 extern "C" int comat_attention_fwd_strided(const void* q, const void* k, const void* v, void* out, float* probs, float* lse,
                                            void* workspace, int n, int Lq, int Lk, int H, int d, long long q_ld, long long k_ld,
-                                           long long v_ld, float scale, int dtype, const int* kv_lens, int causal, void* stream) {
+                                           long long v_ld, float scale, int dtype, const int* kv_lens, int causal,
+                                           int probs_first_sample, void* stream) {
   if (!q || !k || !v || !out || !workspace || n <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return COMAT_ERR_INVALID;
+  if (probs_first_sample < 0 || probs_first_sample >= n) return COMAT_ERR_INVALID;
   if (q_ld < (long long)H * d || k_ld < (long long)H * d || v_ld < (long long)H * d || (q_ld % 8) || (k_ld % 8) || (v_ld % 8)) return COMAT_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15)) return COMAT_ERR_INVALID;
   if (d != 40 && d != 64 && d != 80 && d != 128 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
@@ -377,7 +400,8 @@ extern "C" int comat_attention_fwd_strided(const void* q, const void* k, const v
   kp.Lq = Lq; kp.Lk = Lk; kp.H = H; kp.d = d; kp.n_kv_tiles = (Lk + ATT_BN - 1) / ATT_BN;
   kp.scale = scale; kp.scale_log2 = scale * 1.4426950408889634f;
   kp.kv_lens = kv_lens; kp.causal = causal;
-  kp.out = out; kp.probs = probs; kp.lse = lse; kp.out_ld = (long long)H * d; kp.is_bf16 = dtype == COMAT_BF16;
+  kp.probs_staged = (probs != nullptr && (((long long)Lq * Lk) & 3) == 0 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0) ? 1 : 0;
+  kp.out = out; kp.probs = probs; kp.probs_b0 = probs_first_sample; kp.lse = lse; kp.out_ld = (long long)H * d; kp.is_bf16 = dtype == COMAT_BF16;
   const int fmt = kp.is_bf16 ? 1 : 0;
   const int DN = (d + 15) / 16 * 16;
   kp.idesc_qk = make_idesc_f16(ATT_BM, ATT_BN, fmt);
@@ -410,5 +434,5 @@ extern "C" int comat_attention_fwd(const void* q, const void* k, const void* v, 
                                    int n, int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal,
                                    void* stream) {
   const long long ld = (long long)H * d;
-  return comat_attention_fwd_strided(q, k, v, out, probs, lse, workspace, n, Lq, Lk, H, d, ld, ld, ld, scale, dtype, kv_lens, causal, stream);
+  return comat_attention_fwd_strided(q, k, v, out, probs, lse, workspace, n, Lq, Lk, H, d, ld, ld, ld, scale, dtype, kv_lens, causal, 0, stream);
 }

@@ -31,7 +31,8 @@ struct AttnBwdKP {
   float scale, scale_log2;
   const float* lse_pad;   // (n*H, Lq_pad), lse * log2(e), padded with +1e30
   const float* D_pad;     // (n*H, Lq_pad), padded with 0
-  const float* dp_ext;    // (n*H, Lq, Lk) fp32 or null
+  const float* dp_ext;    // ((n - dp_b0)*H, Lq, Lk) fp32 or null
+  int dp_b0;              // first sample that has an external dP (the conditional half of a CFG batch); earlier samples: none
   void* out0;             // MODE 0: dQ (n, Lq, H*d) ; MODE 1: dK (n, Lk, H*d)
   void* out1;             // MODE 1: dV
   long long out_ld;
@@ -107,6 +108,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
   const int x0 = (blockIdx.x / nsplit) * AB_ROWS;          // first query (MODE 0) / key (MODE 1) of this CTA
   const int h = blockIdx.y, b = blockIdx.z;
   const int bh = b * p.H + h;
+  const float* dp_ext = (p.dp_ext != nullptr && b >= p.dp_b0) ? p.dp_ext : nullptr;     // CTA-uniform
+  const int bhx = (b - p.dp_b0) * p.H + h;                                               // row block of this (sample, head) in dp_ext
   const int split = blockIdx.x % nsplit;
   const int it0 = (int)((long long)p.n_inner * split / nsplit);                  // this CTA's inner tiles [it0, it0 + NI)
   const int NI = (int)((long long)p.n_inner * (split + 1) / nsplit) - it0;
@@ -228,8 +231,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
       const float* vec = reinterpret_cast<const float*>(sStage + stage * Cf::STAGE_BYTES + 2 * Cf::NAT_BYTES);
       // warp-uniform: no external dP, no padding / causal edge inside this (warp, tile) -> predicate-free fast path
       bool fast_w;
-      if (MODE == 0) fast_w = (p.dp_ext == nullptr) && (y0 + Cf::BY <= klen) && (!p.causal || (y0 + Cf::BY - 1 <= x0 + q4 * 32));
-      else           fast_w = (p.dp_ext == nullptr) && (x0 + q4 * 32 + 31 < klen) && (!p.causal || (x0 + q4 * 32 + 31 <= y0));
+      if (MODE == 0) fast_w = (dp_ext == nullptr) && (y0 + Cf::BY <= klen) && (!p.causal || (y0 + Cf::BY - 1 <= x0 + q4 * 32));
+      else           fast_w = (dp_ext == nullptr) && (x0 + q4 * 32 + 31 < klen) && (!p.causal || (x0 + q4 * 32 + 31 <= y0));
       const float sl2 = p.scale_log2;
       uint32_t vs[2][16], vd[2][16];
 #pragma unroll
@@ -280,13 +283,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
               if (MODE == 0) {
                 const bool kv_ok = (y < klen) && (!p.causal || y <= xrow);
                 pr = kv_ok ? fast_exp2(__uint_as_float(vs[g][i + e]) * sl2 - lse_r) : 0.f;
-                if (p.dp_ext != nullptr && y < p.Lk && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + xrow) * p.Lk + y];
+                if (dp_ext != nullptr && y < p.Lk && row_ok) dp += dp_ext[((size_t)bhx * p.Lq + xrow) * p.Lk + y];
                 dsv[e] = pr * (dp - D_r);
               } else {
                 const float lse_c = vec[c], D_c = vec[Cf::BY + c];
                 const bool kv_ok = (xrow < klen) && (!p.causal || xrow <= y);
                 pr = kv_ok ? fast_exp2(__uint_as_float(vs[g][i + e]) * sl2 - lse_c) : 0.f;   // lse pad = 1e30 -> 0 beyond Lq
-                if (p.dp_ext != nullptr && y < p.Lq && row_ok) dp += p.dp_ext[((size_t)bh * p.Lq + y) * p.Lk + xrow];
+                if (dp_ext != nullptr && y < p.Lq && row_ok) dp += dp_ext[((size_t)bhx * p.Lq + y) * p.Lk + xrow];
                 dsv[e] = pr * (dp - D_c);
               }
               pv[e] = pr;
@@ -362,7 +365,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) ab_prep_kernel(const T* __restrict__ o, const T* __restrict__ dO, const float* __restrict__ lse,
                                                       const float* __restrict__ probs, const float* __restrict__ dp_ext,
                                                       float* __restrict__ lse_pad, float* __restrict__ D_pad, int n, int Lq, int Lk, int H,
-                                                      int d, int Lq_pad) {
+                                                      int d, int Lq_pad, int dp_b0) {
   pdl_grid_dependency_sync();
   __shared__ float s_acc[8][32];                       // per warp: up to 32 heads
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -389,9 +392,10 @@ __global__ void __launch_bounds__(256) ab_prep_kernel(const T* __restrict__ o, c
   for (int h = lane; h < H; h += 32) {
     const size_t bh = (size_t)b * H + h;
     float s = s_acc[warp][h];
-    if (dp_ext != nullptr) {
-      const float* pr = probs + (bh * Lq + q) * Lk;
-      const float* de = dp_ext + (bh * Lq + q) * Lk;
+    if (dp_ext != nullptr && b >= dp_b0) {
+      const size_t bhx = (size_t)(b - dp_b0) * H + h;
+      const float* pr = probs + (bhx * Lq + q) * Lk;
+      const float* de = dp_ext + (bhx * Lq + q) * Lk;
       for (int k = 0; k < Lk; ++k) s += pr[k] * de[k];
     }
     lse_pad[bh * Lq_pad + q] = lse[bh * Lq + q] * 1.4426950408889634f;    // log2 units: p = exp2(s*scale*log2e - lse2)
@@ -485,8 +489,9 @@ extern "C" size_t comat_attention_bwd_workspace_bytes(int n, int Lq, int Lk, int
 extern "C" int comat_attention_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
                                            const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
                                            int Lq, int Lk, int H, int d, long long q_ld, long long k_ld, long long v_ld, float scale,
-                                           int dtype, const int* kv_lens, int causal, void* stream) {
+                                           int dtype, const int* kv_lens, int causal, int dp_first_sample, void* stream) {
   if (!q || !k || !v || !o || !dO || !lse || !dq || !dk || !dv || !workspace) return COMAT_ERR_INVALID;
+  if (dp_first_sample < 0 || dp_first_sample >= n) return COMAT_ERR_INVALID;
   if (q_ld < (long long)H * d || k_ld < (long long)H * d || v_ld < (long long)H * d || (q_ld % 8) || (k_ld % 8) || (v_ld % 8)) return COMAT_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15)) return COMAT_ERR_INVALID;
   if (d != 40 && d != 64 && d != 80 && d != 128 && d != 160 && d != 32 && d != 16) return COMAT_ERR_UNSUPPORTED;
@@ -501,16 +506,16 @@ extern "C" int comat_attention_bwd_strided(const void* q, const void* k, const v
     const long long rows = (long long)n * Lqp;
     if (H > 32) return COMAT_ERR_UNSUPPORTED;
     if (dtype == COMAT_F16)
-      launch_k(ab_prep_kernel<__half>, (unsigned)((rows + 7) / 8), 256, 0, st, (const __half*)o, (const __half*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
+      launch_k(ab_prep_kernel<__half>, (unsigned)((rows + 7) / 8), 256, 0, st, (const __half*)o, (const __half*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp, dp_first_sample);
     else
-      launch_k(ab_prep_kernel<__nv_bfloat16>, (unsigned)((rows + 7) / 8), 256, 0, st, (const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp);
+      launch_k(ab_prep_kernel<__nv_bfloat16>, (unsigned)((rows + 7) / 8), 256, 0, st, (const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, lse, probs, dp_ext, lse_pad, D_pad, n, Lq, Lk, H, d, Lqp, dp_first_sample);
   }
   AttnBwdKP kp;
   memset(&kp, 0, sizeof(kp));
   kp.Lq = Lq; kp.Lk = Lk; kp.H = H; kp.d = d; kp.Lq_pad = Lqp; kp.Lk_pad = Lkp;
   kp.scale = scale; kp.scale_log2 = scale * 1.4426950408889634f;
   kp.kv_lens = kv_lens; kp.causal = causal;
-  kp.lse_pad = lse_pad; kp.D_pad = D_pad; kp.dp_ext = dp_ext; kp.out_ld = (long long)H * d;
+  kp.lse_pad = lse_pad; kp.D_pad = D_pad; kp.dp_ext = dp_ext; kp.dp_b0 = dp_first_sample; kp.out_ld = (long long)H * d;
   if (Lk <= 1024) {                               // split-query scratch lives behind the two padded vectors (workspace_bytes sizes it)
     float* sc = D_pad + (size_t)n * H * Lqp;
     sc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sc) + 255) & ~uintptr_t(255));
@@ -531,5 +536,5 @@ extern "C" int comat_attention_bwd(const void* q, const void* k, const void* v, 
                                    int Lq, int Lk, int H, int d, float scale, int dtype, const int* kv_lens, int causal, void* stream) {
   const long long ld = (long long)H * d;
   return comat_attention_bwd_strided(q, k, v, o, dO, lse, probs, dp_ext, dq, dk, dv, workspace, n, Lq, Lk, H, d, ld, ld, ld, scale, dtype,
-                                     kv_lens, causal, stream);
+                                     kv_lens, causal, 0, stream);
 }

@@ -303,10 +303,10 @@ def concat(tape, a: Var, b: Var) -> Var:
     return out
 
 
-def attention(tape, q: Var, k: Var, v: Var, heads: int, export_probs: bool = False):
+def attention(tape, q: Var, k: Var, v: Var, heads: int, export_probs: bool = False, export_from: int = 0):
     """softmax(scale q k^T) v per head; optionally exports the fp32 probabilities (n*heads, Lq, Lk) as a Var whose
     gradient (from the attention-map loss) is added into the softmax backward (SURVEY 'hard parts')."""
-    o, probs, saved = attn_ops.attention_fwd(q.v, k.v, v.v, heads, export_probs, need_bwd=tape is not None)
+    o, probs, saved = attn_ops.attention_fwd(q.v, k.v, v.v, heads, export_probs, need_bwd=tape is not None, export_from=export_from)
     out = Var(o)
     pvar = Var(probs) if export_probs else None
     if tape is not None:
@@ -457,7 +457,7 @@ def _attn_layer(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, captu
                 src = x.v if ctx is None else ctx.v
                 kv = ops.gemm([src.reshape(-1, a.k.k)], [a.w_kv], bias=a.b_kv).reshape(*src.shape[:-1], 2 * C)
             k, v = kv[..., :C], kv[..., C:]
-        o, probs, _ = attn_ops.attention_fwd(q, k, v, a.heads, export, need_bwd=False)
+        o, probs, _ = attn_ops.attention_fwd(q, k, v, a.heads, export, need_bwd=False, export_from=capture.sample_from if export else 0)
         if capture is not None:
             capture.push(Var(probs) if export else None, ctx is not None, place)
         y = ops.gemm([o.reshape(-1, C)], [a.mo.w], bias=a.mo.bias, residual=residual.v.reshape(-1, a.mo.n))
@@ -470,7 +470,7 @@ def _attn_layer(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, captu
     src = x if ctx is None else ctx
     k = linear(tape, src, lk, loras[1])
     v = linear(tape, src, lv, loras[2])
-    o, p = attention(tape, q, k, v, a.heads, export_probs=export)
+    o, p = attention(tape, q, k, v, a.heads, export_probs=export, export_from=capture.sample_from if export else 0)
     if capture is not None:
         capture.push(p, ctx is not None, place)
     return linear(tape, o, lo, loras[3], residual=residual)
@@ -502,7 +502,7 @@ def _attn_layer_product(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Va
         else:
             kv = ops.gemm([src2], [a.w_kv], bias=a.b_kv).reshape(*src.shape[:-1], 2 * C)
         k, v = kv[..., :C], kv[..., C:]
-    o, probs, saved = attn_ops.attention_fwd(q, k, v, a.heads, export, need_bwd=True)
+    o, probs, saved = attn_ops.attention_fwd(q, k, v, a.heads, export, need_bwd=True, export_from=capture.sample_from if export else 0)
     pvar = Var(probs) if export else None
     if capture is not None:
         capture.push(pvar, ctx is not None, place)
@@ -584,6 +584,9 @@ class AttnCapture:
 
     def __init__(self, train_layer_ls):
         self.places = sorted({s.split("_")[0] for s in train_layer_ls})
+        # first sample of the batch whose maps are captured: the attrcon step stores the CONDITIONAL half of the CFG batch
+        # (AttrConcenTrainableSDPipeline.py:239-279), so one full-batch UNet call with sample_from = n/2 replaces the two half calls
+        self.sample_from = 0
         self.reset()
 
     def reset(self):

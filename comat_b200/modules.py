@@ -128,6 +128,115 @@ class _GraphedForward:
         return self.out.clone()
 
 
+class _GraphedTaped:
+    """One captured TAPED UNet call (fixed shapes): a forward graph and a backward graph that share a private memory pool, so the
+    activations the forward leaves behind are exactly what the backward replay reads.  The executor's Python (tape, closures,
+    ~2 000 ctypes launches for forward + backward) runs once, at capture; a training step then costs two cudaGraphLaunch calls per
+    back-propagated UNet call.  Matters where a call's GPU time is below the host's issue time - SDXL at batch 1 / GPU
+    (BASELINE configs[3]) and the discriminator's SD1.5 UNet at n = 1 / 2 - see DESIGN.md section 6.
+
+    Static inputs: sample, timestep, text context (+ its per-layer k|v projections), SDXL's added conditioning, and - for the
+    backward - the loss-scaled 16-bit gradient of the noise prediction and the fp32 gradients of the exported probabilities.
+    LoRA weight gradients accumulate into the engine's product-gradient arena (persistent buffer, fp32 atomics), exactly as in
+    the eager 'product' path; the trainer projects them once per optimiser step.  An instance is busy from its forward replay
+    until its backward replay: K back-propagated sampler steps hold K instances."""
+
+    def __init__(self, mod: "EngineUNet", sample, t, ehs, added, capture, needs_xgrad: bool, wgrad: bool):
+        from . import _lib
+        eng = mod.engine
+        self.mod, self.busy, self.wgrad, self.needs_xgrad = mod, False, wgrad, needs_xgrad
+        self.x = sample.detach().clone()
+        self.t = torch.zeros((), dtype=torch.int64, device=sample.device)
+        self.t.copy_(t.reshape(()))
+        self.added = None if added is None else {k: v.detach().clone() for k, v in added.items()}
+        self.ehs16 = ehs.detach().to(eng.dtype).contiguous()
+        eng.ensure_merged(transposed=True)
+        if wgrad:
+            eng._ensure_G()                                 # persistent arena: must not be born inside the graph's pool
+        self.kv = eng.cross_kv(self.ehs16)
+        self._key = (ehs, ehs._version, eng.lora_version)
+        tape = E.Tape()
+        if capture is not None:
+            capture.reset()
+        l0 = _lib.LAUNCH_COUNT
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd):
+            xv = E.Var(ops.latent_to_nhwc(self.x, eng.dtype, 64), needs_grad=needs_xgrad)
+            out = eng.forward(tape, xv, self.t, self.ehs16, capture=capture, added_cond=self.added,
+                              lora_mode="train" if wgrad else "frozen", cross_kv=self.kv)
+            self.eps = ops.nhwc_to_nchw_f32(out.v, mod.out_channels)
+        self.fwd_launches = _lib.LAUNCH_COUNT - l0
+        self.places, flat = [], []
+        if capture is not None:
+            for place in ("down", "mid", "up"):
+                self.places.append((place, len(capture.store[place])))
+                flat.extend(capture.store[place])
+            self.count = capture.count
+        self.probs = [p.v for p in flat]
+        self.g_out = torch.zeros_like(out.v)                # (n, h, w, 4) 16-bit, loss-scaled by the caller
+        self.g_probs = [torch.zeros_like(p) for p in self.probs]
+        l0 = _lib.LAUNCH_COUNT
+        self.g_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
+            out.g = self.g_out
+            for p, g in zip(flat, self.g_probs):
+                p.g = g
+            eng.zero_lora_grads()
+            eng.set_lora_wgrad(wgrad)
+            for l in eng.loras:
+                l.direct, l.inv_scale = False, 1.0
+            tape.backward()
+            self.gx = ops.nhwc_to_nchw_f32(xv.g, mod.in_channels, 1.0) if (needs_xgrad and xv.g is not None) else None
+        self.bwd_launches = _lib.LAUNCH_COUNT - l0
+
+    def load_inputs(self, sample, t, ehs, added):
+        eng = self.mod.engine
+        eng.ensure_merged(transposed=True)                  # eager, before a replay reads the folded weights
+        self.x.copy_(sample.detach())
+        self.t.copy_(t.reshape(()))
+        if self.added is not None:
+            for k, v in self.added.items():
+                v.copy_(added[k])
+        if not (self._key[0] is ehs and self._key[1] == ehs._version and self._key[2] == eng.lora_version):
+            self.ehs16.copy_(ehs.detach())
+            eng.cross_kv(self.ehs16, out=self.kv)
+            self._key = (ehs, ehs._version, eng.lora_version)
+
+
+class _GraphedUNetFn(torch.autograd.Function):
+    """autograd node around one _GraphedTaped instance (same contract as _UNetFn with the trainer's settings: LoRA weight gradients
+    stay in the engine's product arena, so autograd gets None for them)"""
+
+    @staticmethod
+    def forward(ctx, inst: _GraphedTaped, x, *lora_params):
+        from . import _lib
+        inst.g_fwd.replay()
+        _lib.count_launch(inst.fwd_launches)
+        ctx.inst, ctx.x_dtype = inst, x.dtype
+        return (inst.eps.clone().to(x.dtype), *[p.detach() for p in inst.probs])
+
+    @staticmethod
+    def backward(ctx, g_eps, *g_probs):
+        from . import _lib
+        inst = ctx.inst
+        S = inst.mod.grad_scale
+        inst.g_out.copy_((g_eps.float() * S).permute(0, 2, 3, 1))
+        for buf, g in zip(inst.g_probs, g_probs):
+            if g is None:
+                buf.zero_()
+            else:
+                torch.mul(g, S, out=buf)
+        inst.g_bwd.replay()
+        _lib.count_launch(inst.bwd_launches)
+        if inst.wgrad:
+            inst.mod.engine.G_dirty = True                  # the products of this pass sit in the arena (finalize_lora_grads)
+        gx = None
+        if ctx.needs_input_grad[1] and inst.gx is not None:
+            gx = (inst.gx / S).to(ctx.x_dtype)
+        inst.busy = False
+        return (None, gx, *[None] * (len(ctx.needs_input_grad) - 2))
+
+
 class EngineUNet(torch.nn.Module):
     """Wraps a diffusers-shaped UNet2DConditionModel (parameters + LoRA layers live there, state-dict compatible) and
     executes it with the B200 kernels."""
@@ -147,6 +256,12 @@ class EngineUNet(torch.nn.Module):
         self.use_graphs = False                # bench / trainer switch: CUDA-graph the no-grad forwards of the rollout
         self._graphs = {}
         self.direct_lora_grads = False         # trainer switch: LoRA weight gradients accumulate straight into param.grad
+        # trainer / bench switch: CUDA-graph the TAPED calls too (forward + backward graph pairs, _GraphedTaped).  Needs the
+        # trainer's protocol (direct_lora_grads + finalize_lora_grads once per step) and holds each instance's activations for
+        # the life of the module, so it is opt-in
+        self.graph_taped = False
+        self.max_taped_instances = 8
+        self._taped = {}
         self._kv_key, self._kv_val = None, None   # cached 16-bit context + per-layer k|v projections (eager no-grad path)
 
     @property
@@ -193,6 +308,43 @@ class EngineUNet(torch.nn.Module):
     def enable_gradient_checkpointing(self):
         pass                                  # never recomputes: activations of K steps fit in 180 GB
 
+    def new_step(self):
+        """trainer hook (start of an optimiser step): graph instances whose backward never ran (a forward without a backward)
+        become available again"""
+        for slot in self._taped.values():
+            for inst in slot["inst"]:
+                inst.busy = False
+
+    def _taped_instance(self, sample, t, ehs, added, capture, needs_xgrad, wgrad):
+        """a free captured (forward, backward) graph pair for this call signature, or None -> run the call eagerly.  The first call
+        of a signature always runs eagerly (one-time kernel attribute set-up, allocator warm-up)."""
+        eng = self.engine
+        if not (self.graph_taped and sample.is_cuda and not ehs.requires_grad):
+            return None
+        if wgrad and not (eng.lora_train_impl == "product" and self.direct_lora_grads):
+            return None
+        key = (tuple(sample.shape), tuple(ehs.shape), sample.dtype, ehs.dtype, needs_xgrad, wgrad,
+               None if capture is None else (tuple(capture.places), capture.sample_from),
+               None if added is None else tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(added.items())))
+        slot = self._taped.setdefault(key, {"warm": False, "inst": [], "off": False})
+        if not slot["warm"]:
+            slot["warm"] = True
+            return None
+        inst = next((i for i in slot["inst"] if not i.busy), None)
+        if inst is None:
+            if slot["off"] or len(slot["inst"]) >= self.max_taped_instances:
+                return None
+            try:
+                inst = _GraphedTaped(self, sample, t, ehs, added, capture, needs_xgrad, wgrad)
+            except torch.cuda.OutOfMemoryError:
+                slot["off"] = True            # no room for another resident activation set: this signature stays eager
+                torch.cuda.empty_cache()
+                return None
+            slot["inst"].append(inst)
+        inst.load_inputs(sample, t, ehs, added)
+        inst.busy = True
+        return inst
+
     def forward(self, sample, timestep, encoder_hidden_states, cross_attention_kwargs=None, added_cond_kwargs=None,
                 return_dict=False):
         t = timestep if torch.is_tensor(timestep) else torch.tensor(timestep, device=sample.device)
@@ -202,7 +354,21 @@ class EngineUNet(torch.nn.Module):
         capture = self.capture
         if capture is not None:
             capture.reset()
-        if want_grad:
+        inst = None
+        if want_grad and self.graph_taped:
+            wgrad = bool(self.train_lora and any(p.requires_grad for p in params))
+            inst = self._taped_instance(sample, t, encoder_hidden_states, added_cond_kwargs, capture, bool(sample.requires_grad), wgrad)
+        if inst is not None:
+            outs = _GraphedUNetFn.apply(inst, sample, *params)
+            eps, probs = outs[0], outs[1:]
+            if capture is not None:           # the AttentionStore protocol on the replayed call: same counts, Vars over the outputs
+                capture.reset()
+                capture.count = inst.count
+                i = 0
+                for place, cnt in inst.places:
+                    capture.store[place] = [E.Var(probs[i + j]) for j in range(cnt)]
+                    i += cnt
+        elif want_grad:
             ckv = self._context_kv(encoder_hidden_states, store=capture is None)
             outs = _UNetFn.apply(self, sample, t, encoder_hidden_states, added_cond_kwargs, capture, ckv, *params)
             eps, probs = outs[0], outs[1:]

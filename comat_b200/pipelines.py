@@ -123,15 +123,32 @@ class TrainableSDPipeline:
     def _unet(self, x, t, embeds, added):
         return self.unet(x, t, encoder_hidden_states=embeds, added_cond_kwargs=added, return_dict=False)[0]
 
+    # True (default): the attrcon step runs ONE UNet call over the whole classifier-free-guidance batch and the attention kernel
+    # exports the probabilities of the conditional half only.  Per-sample arithmetic (GroupNorm, attention) is unchanged, so
+    # the result equals the reference's two half-batch calls + torch.cat (AttrConcenTrainableSDPipeline.py:239-279), without
+    # their second pass over the weights and at twice the GEMM M.  False: the reference's literal two-call structure.
+    merge_attrcon_call = True
+
     def _attrcon_forward(self, latents, t, prompt_embeds, added=None, t_host=None):
-        """AttrConcenTrainableSDPipeline.py:239-279: conditional half with attention capture, then the unconditional half."""
+        """AttrConcenTrainableSDPipeline.py:239-279: conditional half with attention capture, unconditional half without."""
         h = latents.shape[0] // 2
+        key = str(int(t) if t_host is None else t_host)
+        if self.merge_attrcon_call and hasattr(self.controller, "sample_from"):
+            self.unet.capture = self.controller
+            self.controller.sample_from = h
+            try:
+                eps = self._unet(latents, t, prompt_embeds, added)
+                self.attn_dict[key] = self.controller.attn_dict()[0]
+            finally:
+                self.unet.capture = None
+                self.controller.sample_from = 0
+            return eps
         split = (lambda d, s: None if d is None else {k: v[s] for k, v in d.items()})
         self.unet.capture = self.controller
         try:
             n_c = self._unet(latents[h:], t, prompt_embeds[h:], split(added, slice(h, None)))
             maps, _ = self.controller.attn_dict()
-            self.attn_dict[str(int(t) if t_host is None else t_host)] = maps
+            self.attn_dict[key] = maps
         finally:
             self.unet.capture = None
         n_u = self._unet(latents[:h], t, prompt_embeds[:h], split(added, slice(0, h)))

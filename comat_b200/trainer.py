@@ -285,6 +285,9 @@ class CoMatTrainer:
         self._join("_ev_G")                                                          # the generator's previous update is in
         if first:
             self._update_loss_scale()
+            for u in (self.pipeline.unet, getattr(self.D, "unet", None)):
+                if hasattr(u, "new_step"):
+                    u.new_step()                                                     # captured taped-call graphs are all free again
         logs = self.g_losses(batch)
         loss = logs["loss"]
         if first:

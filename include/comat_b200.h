@@ -219,7 +219,11 @@ int comat_attention_fwd(const void* q, const void* k, const void* v, void* out, 
  * input for self-attention) or the cached k|v projection of the text context.  Pitches must be multiples of 8. */
 int comat_attention_fwd_strided(const void* q, const void* k, const void* v, void* out, float* probs, float* lse,
                                 void* workspace, int n, int Lq, int Lk, int H, int d, long long q_ld, long long k_ld,
-                                long long v_ld, float scale, int dtype, const int* kv_lens, int causal, void* stream);
+                                long long v_ld, float scale, int dtype, const int* kv_lens, int causal,
+                                int probs_first_sample, void* stream);
+/* probs_first_sample = b0: only samples b >= b0 export their probabilities and `probs` is ((n - b0)*H, Lq, Lk).  The attrcon step
+ * (AttrConcenTrainableSDPipeline.py:239-279) captures the maps of the CONDITIONAL half of the classifier-free-guidance batch; with
+ * b0 = n/2 both halves run as one UNet call instead of the reference's two half-batch calls. */
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused classifier-free guidance + DDPM ancestral step on the fp32 latent chain.
@@ -232,7 +236,9 @@ int comat_cfg_ddpm_step_fwd(const float* eps, const float* x, const float* noise
 int comat_cfg_ddpm_step_bwd(const float* grad_out, float* d_eps, float* dx, long long n, float guidance, float c_eps,
                             float c_x, int cfg, void* stream);
 
-/* Fused attention backward (tcgen05, recomputation; two launches: dQ, then dK+dV; no atomics).
+/* Fused attention backward (tcgen05, recomputation; two launches: dQ, then dK+dV; bit-reproducible except for short key sequences
+ * - Lk <= 1024 with >= 8 query tiles, i.e. the UNet's cross-attention - where the dK/dV launch splits the query range over several
+ * CTAs per key tile and adds the partial sums with fp32 atomics).
  * Inputs as the forward plus o, dO (n, Lq, H*d) 16-bit and the forward's lse.  `probs` + `dp_ext` (both fp32 (n*H, Lq, Lk),
  * Lk <= 128) inject the gradient of the exported probabilities (attention-map loss) into the softmax backward; pass nulls
  * otherwise.  Outputs dq / dk / dv in the layouts of q / k / v. */
@@ -245,7 +251,8 @@ int comat_attention_bwd(const void* q, const void* k, const void* v, const void*
 int comat_attention_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse,
                                 const float* probs, const float* dp_ext, void* dq, void* dk, void* dv, void* workspace, int n,
                                 int Lq, int Lk, int H, int d, long long q_ld, long long k_ld, long long v_ld, float scale,
-                                int dtype, const int* kv_lens, int causal, void* stream);
+                                int dtype, const int* kv_lens, int causal, int dp_first_sample, void* stream);
+/* dp_first_sample = b0: `probs` / `dp_ext` are ((n - b0)*H, Lq, Lk) and belong to samples b >= b0 (see probs_first_sample). */
 
 /* fp32 -> two bf16 tensors with  alpha * src ~= hi + lo  (hi = bf16(alpha*src), lo = bf16(alpha*src - hi)): ~16 mantissa bits at
  * fp32 range.  Used to feed the fp32-accumulated full-size LoRA gradient products  G = dy^T x  to the 16-bit tensor-core GEMMs

@@ -203,16 +203,18 @@ def _ref_attn(q, k, v, heads, kv_lens=None, causal=False, dprobs=None):
     return o, p.reshape(n * heads, Lq, Lk), torch.logsumexp(s, -1).reshape(n * heads, Lq)
 
 
-def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False):
-    """comat_b200.attention.attention_fwd protocol: (o, probs fp32 | None, saved)"""
+def attention_fwd(q, k, v, heads, export_probs=False, need_bwd=False, export_from=0):
+    """comat_b200.attention.attention_fwd protocol: (o, probs fp32 of samples export_from.. | None, saved)"""
     o, p, _ = _ref_attn(q, k, v, heads)
-    return o.to(q.dtype), (p.float() if export_probs else None), ((q, k, v, heads) if need_bwd else None)
+    return o.to(q.dtype), (p[export_from * heads:].float() if export_probs else None), ((q, k, v, heads, export_from) if need_bwd else None)
 
 
 def attention_bwd(saved, do, dprobs):
-    q, k, v, heads = saved
+    q, k, v, heads, export_from = saved
     if do is None:
         do = torch.zeros_like(q)
+    if dprobs is not None and export_from:
+        dprobs = torch.cat([dprobs.new_zeros(export_from * heads, *dprobs.shape[1:]), dprobs])
     return attention_bwd_native(q, k, v, None, None, None, heads, do, dprobs)
 
 

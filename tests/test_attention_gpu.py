@@ -161,3 +161,29 @@ def test_attention_backward_reads_fused_projection_slices_in_place(n, L, T, H, d
     want = A.attention_bwd_native(qc, kv[..., :C].contiguous(), kv[..., C:].contiguous(), o, lse, p, H, do, dp)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_attention_exports_and_differentiates_the_conditional_half_only():
+    """export_from / dp_from = n/2 (the merged attrcon call): probabilities of samples >= n/2 only, identical to the rows a full export
+    gives, and a backward whose external dP covers the same samples equals the full-batch backward with zeros for the others."""
+    from comat_b200 import attention as A
+    torch.manual_seed(5)
+    n, L, T, H, d = 4, 1024, 77, 8, 40
+    C = H * d
+    q = torch.randn(n, L, C, device="cuda").half()
+    k, v = torch.randn(n, T, C, device="cuda").half(), torch.randn(n, T, C, device="cuda").half()
+    do = torch.randn(n, L, C, device="cuda").half()
+    o_f, p_f, lse_f = A.attention_fwd_native(q, k, v, H, export_probs=True, need_lse=True)
+    o_h, p_h, lse_h = A.attention_fwd_native(q, k, v, H, export_probs=True, need_lse=True, export_from=n // 2)
+    assert p_h.shape == ((n - n // 2) * H, L, T)
+    assert torch.equal(o_f, o_h) and torch.equal(lse_f, lse_h) and torch.equal(p_h, p_f[(n // 2) * H:])
+    dp_h = torch.randn_like(p_h) * 0.5
+    dp_f = torch.cat([torch.zeros_like(dp_h), dp_h])
+    got = A.attention_bwd_native(q, k, v, o_h, lse_h, p_h, H, do, dp_h, dp_from=n // 2)
+    want = A.attention_bwd_native(q, k, v, o_f, lse_f, p_f, H, do, dp_f)
+    assert torch.equal(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        assert float((a.float() - b.float()).norm() / b.float().norm()) < 1e-3
+    saved = A.attention_fwd(q, k, v, H, export_probs=True, need_bwd=True, export_from=n // 2)[2]
+    again = A.attention_bwd(saved, do, dp_h)
+    assert torch.equal(again[0], want[0])

@@ -260,3 +260,53 @@ def test_full_size_sd15_unet_vs_oracle():
     got = torch.cat([a.reshape(-1) for a in eg]).double()
     want = torch.cat([b.reshape(-1) for b in grads_ref[1:]]).double()
     assert float((got * want).sum() / (got.norm() * want.norm())) > 0.998
+
+
+@pytest.mark.parametrize("with_capture", [False, True])
+def test_engine_unet_graphed_taped_calls_match_eager(with_capture):
+    """graph_taped: the back-propagated UNet call replayed from a (forward graph, backward graph) pair - noise prediction, exported
+    cross-attention probabilities, input gradient and the LoRA gradients (product arena -> finalize_lora_grads) equal the eager
+    taped call's, call after call with new inputs; two calls in flight use two instances."""
+    from comat_b200 import engine as E
+    from comat_b200.modules import EngineUNet
+    unet, _ = _tiny()
+    g = torch.Generator().manual_seed(11)
+    ins = [(torch.randn(2, 4, 32, 32, generator=g).cuda(), torch.randn(2, 77, 64, generator=g).cuda(), torch.tensor(t, device="cuda"),
+            torch.randn(2, 4, 32, 32, generator=g).cuda()) for t in (801, 401, 1, 601)]
+
+    def run(graphed):
+        mod = EngineUNet(unet, torch.float16)
+        for p in mod.lora_parameters():
+            p.grad = torch.zeros_like(p)
+        mod.direct_lora_grads, mod.graph_taped = True, graphed
+        if with_capture:
+            mod.capture = E.AttnCapture(["up_8", "up_16"])
+        res = []
+        for k in range(0, len(ins), 2):                      # two taped calls, then both backward passes (K > 1 steps in flight)
+            mod.new_step()
+            outs, leaves = [], []
+            for x, ctx, t, w in ins[k:k + 2]:
+                xr = x.clone().requires_grad_(True)
+                eps = mod(xr, t, encoder_hidden_states=ctx)[0]
+                loss = (eps * w).sum()
+                if with_capture:
+                    maps, _ = mod.capture.attn_dict()
+                    loss = loss + sum((m * m).sum() for v in maps.values() for m in v) * 1e-2
+                    res.append(torch.cat([m.reshape(-1) for v in maps.values() for m in v]).detach().clone())
+                outs.append(loss)
+                leaves.append(xr)
+                res.append(eps.detach().clone())
+            for loss, xr in zip(reversed(outs), reversed(leaves)):
+                loss.backward()
+                res.append(xr.grad.clone())
+            mod.finalize_lora_grads()
+            res.append(torch.cat([p.grad.reshape(-1) for p in mod.lora_parameters()]).clone())
+            for p in mod.lora_parameters():
+                p.grad.zero_()
+        n_inst = sum(len(s["inst"]) for s in mod._taped.values())
+        return res, n_inst
+    ref, n0 = run(False)
+    got, n1 = run(True)
+    assert n0 == 0 and n1 == 2                               # first pair eager (warm-up), second pair: two captured instances
+    for a, b in zip(got, ref):
+        assert rel(a, b) < 3e-3, rel(a, b)
