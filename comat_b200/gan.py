@@ -7,8 +7,8 @@ Mirrors ``D_sd`` (training_utils/gan_sdxl.py:6-155) and ``load_discriminator`` (
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
+from . import ops
 from .modules import EngineUNet
 from .scheduler import DDPMScheduler
 
@@ -51,11 +51,12 @@ class D_sd(torch.nn.Module):
         else:
             raise ValueError(side)
         eps = self.unet(x, t, encoder_hidden_states=cond, return_dict=False)[0]
-        pred = self.mlp(eps.permute(0, 2, 3, 1).float())
-        target = torch.ones_like(pred)
-        if side == "D":
-            target[: target.shape[0] // 2] = 0
-        return F.binary_cross_entropy_with_logits(pred, target)
+        head = self.mlp[0] if isinstance(self.mlp, torch.nn.Sequential) and len(self.mlp) == 1 else self.mlp
+        if not (isinstance(head, torch.nn.Linear) and head.out_features == 1 and head.in_features == eps.shape[1] and head.bias is not None):
+            raise NotImplementedError("D_sd head: the per-pixel nn.Linear(4, 1) of gan_sdxl.py:31-34 is the one built here "
+                                      "(--gan_unet_lastlayer_cls swaps in a conv head, refused in load_discriminator)")
+        # permute -> Linear(4, 1) -> BCEWithLogits (:84-89 / :118-132) as one fused kernel; targets: generated half 0 on the D side
+        return ops.gan_head_bce(eps, head.weight, head.bias, x.shape[0] // 2 if side == "D" else 0)
 
     @torch.no_grad()
     def encode_prompt(self, prompt, device, batch_size, do_classifier_free_guidance=False):

@@ -421,3 +421,39 @@ def split_f32_bf16x2(src: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, alph
             src.is_contiguous() and hi.is_contiguous() and lo.is_contiguous()) or hi.numel() != src.numel() or lo.numel() != src.numel():
         raise _lib.ComatError("split_f32_bf16x2: contiguous fp32 source and two bf16 destinations of the same size")
     _call("comat_split_f32_bf16x2", src.data_ptr(), hi.data_ptr(), lo.data_ptr(), src.numel(), float(alpha), _lib.stream_ptr())
+
+
+_lib.register_signature("comat_gan_head_bce_fwd", [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
+_lib.register_signature("comat_gan_head_bce_bwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
+
+
+class _GanHeadBCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eps, w, b, n_zero):
+        _lib.require_cuda(eps, w, b)
+        eps = eps.float().contiguous()
+        w32, b32 = w.detach().float().contiguous().reshape(-1), b.detach().float().contiguous().reshape(-1)
+        n, C_, H, W = eps.shape
+        loss = torch.zeros(1, dtype=torch.float32, device=eps.device)
+        _call("comat_gan_head_bce_fwd", eps.data_ptr(), w32.data_ptr(), b32.data_ptr(), loss.data_ptr(), n, C_, H * W, int(n_zero), _lib.stream_ptr())
+        ctx.save_for_backward(eps, w32, b32)
+        ctx.n_zero, ctx.w_shape, ctx.b_shape = int(n_zero), w.shape, b.shape
+        return (loss / float(n * H * W)).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        eps, w32, b32 = ctx.saved_tensors
+        n, C_, H, W = eps.shape
+        d_eps = torch.empty_like(eps) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w32) if ctx.needs_input_grad[1] else None
+        db = torch.zeros_like(b32) if ctx.needs_input_grad[2] else None
+        gout = g.detach().float().reshape(1).contiguous()
+        _call("comat_gan_head_bce_bwd", eps.data_ptr(), w32.data_ptr(), b32.data_ptr(), gout.data_ptr(), _p(d_eps), _p(dw), _p(db),
+              n, C_, H * W, ctx.n_zero, _lib.stream_ptr())
+        return d_eps, None if dw is None else dw.reshape(ctx.w_shape), None if db is None else db.reshape(ctx.b_shape), None
+
+
+def gan_head_bce(eps, weight, bias, n_zero: int):
+    """mean BCEWithLogits(Linear(C, 1)(eps.permute(0, 2, 3, 1)), target) with target 0 for the first ``n_zero`` samples and 1 for the
+    rest (gan_sdxl.py:84-89, :118-132), one fused kernel forward and one backward.  eps (n, C, H, W) fp32; weight (1, C), bias (1)."""
+    return _GanHeadBCE.apply(eps, weight, bias, n_zero)

@@ -254,6 +254,19 @@ int comat_attention_bwd_strided(const void* q, const void* k, const void* v, con
                                 int dtype, const int* kv_lens, int causal, int dp_first_sample, void* stream);
 /* dp_first_sample = b0: `probs` / `dp_ext` are ((n - b0)*H, Lq, Lk) and belong to samples b >= b0 (see probs_first_sample). */
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Discriminator head of the fidelity GAN, fused (SURVEY 8b `gan_head_bce`): per-pixel Linear(C, 1) over the D UNet's noise
+ * prediction + BCEWithLogits, mean over n*HW logits.  Replaces permute -> nn.Linear(4, 1) -> nn.BCEWithLogitsLoss of
+ * training_utils/gan_sdxl.py:31-34, :84-89 (side 'G': n_zero = 0, all targets 1) and :118-132 (side 'D': n_zero = n/2, the
+ * generated half has target 0).  eps (n, C, H, W) fp32 NCHW, C <= 8; w (C), b (1) fp32.
+ *   fwd: loss_sum[0] += sum of the per-logit losses (caller zeroes it and divides by n*HW).
+ *   bwd: d_eps = dL/d eps (may be null), dw / db ACCUMULATED (fp32 atomics; may be null); gout = device scalar dL_total/dL.
+ * ------------------------------------------------------------------------------------------------------------ */
+int comat_gan_head_bce_fwd(const float* eps, const float* w, const float* b, float* loss_sum, int n, int C, int HW, int n_zero,
+                           void* stream);
+int comat_gan_head_bce_bwd(const float* eps, const float* w, const float* b, const float* gout, float* d_eps, float* dw, float* db,
+                           int n, int C, int HW, int n_zero, void* stream);
+
 /* fp32 -> two bf16 tensors with  alpha * src ~= hi + lo  (hi = bf16(alpha*src), lo = bf16(alpha*src - hi)): ~16 mantissa bits at
  * fp32 range.  Used to feed the fp32-accumulated full-size LoRA gradient products  G = dy^T x  to the 16-bit tensor-core GEMMs
  * that project them onto the LoRA factors (d up = G down^T, d down = up^T G; training_utils/pipeline.py:94-115 backward). */

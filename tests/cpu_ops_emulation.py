@@ -174,8 +174,16 @@ def split_f32_bf16x2(src, hi, lo, alpha=1.0):
     lo.copy_((v - h.float()).to(lo.dtype))
 
 
+def gan_head_bce(eps, weight, bias, n_zero):
+    pred = F.linear(eps.permute(0, 2, 3, 1).float(), weight.float(), bias.float())
+    target = torch.ones_like(pred)
+    target[:n_zero] = 0
+    return F.binary_cross_entropy_with_logits(pred, target)
+
+
 def install(monkeypatch):
     from comat_b200 import attention, ops
+    monkeypatch.setattr(ops, "gan_head_bce", gan_head_bce)
     # CPU logic tests run the executors' attention through the torch comparator below (the product has no such path)
     monkeypatch.setattr(attention, "attention_fwd", attention_fwd)
     monkeypatch.setattr(attention, "attention_bwd", attention_bwd)

@@ -169,3 +169,23 @@ def test_groupnorm_fused_cluster_kernel_in_subprocess():
                         "-k", "test_groupnorm and not subprocess"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "passed" in r.stdout and "failed" not in r.stdout
+
+
+@pytest.mark.parametrize("n,hw,n_zero", [(4, 64, 0), (8, 64, 4), (2, 32, 1), (3, 17, 0)])
+def test_gan_head_bce_fwd_bwd_vs_torch(n, hw, n_zero):
+    """comat_gan_head_bce: permute -> Linear(4, 1) -> BCEWithLogits of gan_sdxl.py:84-89 / :118-132, loss and all three gradients."""
+    from comat_b200 import ops
+    torch.manual_seed(n + hw)
+    eps = (torch.randn(n, 4, hw, hw, device="cuda") * 2).requires_grad_(True)
+    lin = torch.nn.Linear(4, 1).cuda()
+    loss = ops.gan_head_bce(eps, lin.weight, lin.bias, n_zero)
+    g = torch.autograd.grad(loss * 3.0, [eps, lin.weight, lin.bias])
+    eps2 = eps.detach().clone().requires_grad_(True)
+    pred = lin(eps2.permute(0, 2, 3, 1))
+    target = torch.ones_like(pred)
+    target[:n_zero] = 0
+    ref = F.binary_cross_entropy_with_logits(pred, target)
+    gr = torch.autograd.grad(ref * 3.0, [eps2, lin.weight, lin.bias])
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    for a, b in zip(g, gr):
+        assert a.shape == b.shape and rel(a, b) < 1e-4
