@@ -232,3 +232,32 @@ def get_grounding_loss_by_layer(_gt_seg_list, word_token_idx_ls, res, input_attn
                            [list(_gt_seg_list)], dev, T)
     out = fused_attnmap_loss(plan, list(input_attn_map_ls))
     return {"token_loss": out[0], "pixel_loss": out[1]}
+
+
+class SegModel:
+    """Call-compatible stand-in for ``GsamSegModel`` (attr_concen_utils/gsam_interface.py:22-53, :140-228) as training_script.py:631-637
+    uses it:  ``seg_model.get_mask_loss(images, prompt, all_subtree_indices, attn_map_idx_to_wp_all, attn_map)
+    -> (token_loss, pixel_loss, grounding_loss_dict)``.  The noun / attribute bookkeeping is the reference's (:163-196, :232-261);
+    the mask producer (Grounded-SAM, an external model) is injected as ``mask_fn(image (3,H,W), nouns) -> [ (1,1,H,W) bool per noun ]
+    | None``; every (sample, timestep, layer) term then goes through ONE fused kernel launch instead of the Python triple loop."""
+
+    def __init__(self, train_layer_ls: Sequence[str], mask_fn, tokens: int = 77):
+        self.train_layer_ls, self.mask_fn, self.tokens = list(train_layer_ls), mask_fn, tokens
+
+    update_nouns_attributes = staticmethod(update_nouns_attributes)
+
+    def get_mask(self, image, nouns):
+        return self.mask_fn(image, nouns)
+
+    def get_mask_loss(self, images, prompt, all_subtree_indices, attn_map_idx_to_wp_all, attn_map):
+        images = images.detach()
+        words, masks = [], []
+        for idx, subtree_indices in enumerate(all_subtree_indices):
+            nouns, attrs = words_from_subtrees(subtree_indices, attn_map_idx_to_wp_all[idx])
+            m = self.get_mask(images[idx], nouns) if nouns else None                # :188-202: no nouns / no mask -> sample skipped
+            words.append(attrs if m is not None else [])
+            masks.append(list(m) if m is not None else None)
+        token_loss, pixel_loss = get_mask_loss(attn_map, words, masks, self.train_layer_ls, self.tokens)
+        # the reference also returns per-(timestep, layer) sums that nothing reads (training_script.py:633 discards them); the fused
+        # kernel reduces all terms on the device, so the dictionary carries the two totals only
+        return token_loss, pixel_loss, {"token/total": token_loss.detach(), "pixel/total": pixel_loss.detach()}

@@ -1,8 +1,8 @@
 """Prompt data for the training loop: ``get_dataset_dataloader`` (training_utils/dataset.py:10-57) without the HF ``datasets`` /
 image-folder machinery the CoMat scripts never use (prompts only; ``Gan_Dataset`` when the GAN loss is on), and the
 data-parallel sharding of SURVEY 8e: every epoch ONE seeded permutation shared by all ranks, rank r takes positions
-``i = r (mod world)`` - no prompt is seen twice in an epoch (the reference shuffles independently per rank, dataset.py:39,47-52,
-so duplicates across ranks are possible there)."""
+``i = r (mod world)`` - no prompt is seen twice in an epoch.  (The reference builds a shuffling DataLoader, dataset.py:39,47-52, and
+passes it through ``accelerator.prepare`` (training_script.py:324-330), which shards it across ranks as well.)"""
 from __future__ import annotations
 
 import json

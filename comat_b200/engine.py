@@ -669,6 +669,13 @@ class UNetEngine:
         # 'product' (default): LoRA weight gradients through the accumulated full-size product G = dy^T x, projected onto the
         # factors once per optimiser step; 'explicit': the literal LoRA branch (t = x down^T ...) in forward and backward
         self.lora_train_impl = "product"
+        # Folding (W' = round16(W16 + up16.down16)) quantises the adapter's contribution to the ulp of W: harmless in fp16 (ulp 2^-11 |W|)
+        # once the adapter has grown for a few steps, but in bf16 (ulp 2^-8 |W| ~ 1.2e-4 at |W| ~ 0.03) a young adapter is rounded away
+        # entirely and the loss does not see it.  bf16 engines therefore run the literal LoRA branch y = W x + up(down(x)) in every
+        # pass (the reference's arithmetic, training_utils/pipeline.py:94-115) - slower, exact in the adapter.
+        self.fold_lora = dtype != torch.bfloat16
+        if not self.fold_lora:
+            self.lora_train_impl = "explicit"
         self._G = self._G_hi = self._G_lo = None
         self._gproj = []
         self.G_dirty = False
@@ -790,6 +797,8 @@ class UNetEngine:
         mode = lora_mode or ("train" if tape is not None else "merged")
         if mode == "merged" and tape is not None:
             mode = "frozen"
+        if not self.fold_lora and self.loras and self.lora_train_impl != "product":
+            mode, cross_kv = "train", None         # bf16: explicit LoRA branch in every pass (wgrad switched per pass by set_lora_wgrad)
         if mode == "train" and self.lora_train_impl == "product":
             mode = "product"
             self._ensure_G()

@@ -75,9 +75,24 @@ class D_sd(torch.nn.Module):
         return null, pooled
 
 
-def load_discriminator(args, unet: EngineUNet):
+def load_discriminator(args, unet_or_dtype, device=None):
     """gan_sd_model.py:8-14 keeps the reference quirk: the arch string has 'gan' stripped and only 'sd_1_5' resolves
-    (the default 'gan_sd_1_5' -> '_sd_1_5' resolves to nothing -> None)."""
+    (the default 'gan_sd_1_5' -> '_sd_1_5' resolves to nothing -> None).
+
+    Two call forms: ``load_discriminator(args, unet)`` with a ready ``EngineUNet`` (synthetic weights, tests), and the reference's
+    ``load_discriminator(args, weight_dtype, device)`` (training_script.py:290), which builds the D pipeline from the local
+    diffusers directory ``args.gan_pretrain_model`` / ``args.pretrain_model`` like ``D_sd.__init__`` (gan_sdxl.py:7-35: the reference
+    hard-codes the Hub id runwayml/stable-diffusion-v1-5; there is no Hub here)."""
+    if isinstance(unet_or_dtype, torch.dtype):
+        from .pipelines import TrainableSDPipeline
+        path = getattr(args, "gan_pretrain_model", None) or args.pretrain_model
+        d_pipe = TrainableSDPipeline.from_pretrained(path, dtype=unet_or_dtype, device=device or "cuda", lora_rank=args.lora_rank)
+        D = load_discriminator(args, d_pipe.unet)
+        if D is not None:
+            d_pipe.unet = d_pipe.vae = None            # D keeps the UNet; the D pipeline only lends its text encoder (:134-155)
+            D.D_sd_pipeline = d_pipe
+        return D
+    unet = unet_or_dtype
     if getattr(args, "gan_unet_lastlayer_cls", False):
         # gan_sdxl.py:27-30 swaps the D UNet's conv_out for a 1-channel classifier conv; only the Linear(4,1) head (:31-34,
         # what both shipped scripts train) is built here - refuse rather than silently train a different discriminator

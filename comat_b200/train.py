@@ -33,10 +33,14 @@ from .arguments import parse_args
 from .data import ShardedBatches, get_dataset
 
 
-def lr_at(args, step: int) -> float:
+def lr_at(args, step: int, world: int = 1) -> float:
     """multiplier schedule of diffusers' ``get_scheduler(args.lr_scheduler, num_warmup_steps, num_training_steps)``
-    (training_script.py:289-294; un-vendored, the published definitions) evaluated at optimiser step ``step``."""
+    (training_script.py:289-294; un-vendored, the published definitions) after ``step`` optimiser steps.  The reference passes the
+    scheduler through ``accelerator.prepare`` (:324-330): accelerate's AcceleratedScheduler then advances it ``num_processes`` times
+    per optimiser step (split_batches = False), so on N GPUs warm-up and decay run N x faster - mirrored by ``world``.  Both shipped
+    scripts use ``constant``, where this makes no difference."""
     name, warm, total = args.lr_scheduler, args.lr_warmup_steps, max(1, args.max_train_steps)
+    step = step * max(1, int(world))
     if name == "constant":
         return 1.0
     if step < warm:
@@ -305,7 +309,7 @@ class Trainer:
         host = mat.cpu()
         if self._log_file is not None:
             for (step, _), row in zip(self._pending, host):
-                rec = {"step": step, "lr": self.args.learning_rate * lr_at(self.args, step - 1)}
+                rec = {"step": step, "lr": self.args.learning_rate * lr_at(self.args, step - 1, self.world)}
                 rec.update({k: float(v) for k, v in zip(keys, row) if not math.isnan(float(v))})
                 self._log_file.write(json.dumps(rec) + "\n")
                 if self._tb is not None:                                              # :702-703 accelerator.log(..., step=global_step)
@@ -338,7 +342,7 @@ class Trainer:
                 if self.global_step >= a.max_train_steps:
                     break
                 batch = self._make_batch(raw)
-                self.core.optimizer.lr = a.learning_rate * lr_at(a, self.global_step)  # :663 lr_scheduler.step()
+                self.core.optimizer.lr = a.learning_rate * lr_at(a, self.global_step, self.world)  # :663 lr_scheduler.step()
                 # accelerator.accumulate (:556): gradients sync every accum-th batch and at the end of the dataloader
                 first = self._micro == 0
                 last = self._micro == self.accum - 1 or step == len(self.loader) - 1

@@ -312,3 +312,39 @@ def test_engine_unet_graphed_taped_calls_match_eager(with_capture):
     # run and a flipped fp16 rounding early in the network moves the outputs by ~1e-3 and the gradients by a few 1e-3
     for a, b in zip(got, ref):
         assert rel(a, b) < 1.5e-2, rel(a, b)
+
+
+def test_bf16_engine_sees_a_young_lora_adapter():
+    """with the adapter folded into bf16 weights a small LoRA delta (|up.down| below half an ulp of W) vanishes from the
+    forward pass.  bf16 engines run the explicit branch: the change of the noise prediction caused by a young adapter follows the fp32
+    oracle's, in the no-grad pass and in the taped pass."""
+    from comat_b200 import engine as E, ops
+    unet, _ = _tiny()
+    params = [p for p in unet.parameters() if p.requires_grad]
+    g = torch.Generator().manual_seed(8)
+    x, ctx = torch.randn(2, 4, 32, 32, generator=g).cuda(), torch.randn(2, 77, 64, generator=g).cuda()
+    t = torch.tensor(501, device="cuda")
+    ups = [p for p in params if p.shape[1] == 8]                       # (N, r) factors
+    saved = [p.detach().clone() for p in ups]
+
+    def outs():
+        eng = E.UNetEngine(unet, torch.bfloat16)
+        assert not eng.fold_lora and eng.lora_train_impl == "explicit"
+        e0 = ops.nhwc_to_nchw_f32(eng.forward(None, E.Var(ops.latent_to_nhwc(x, torch.bfloat16, 64), False), t, ctx.bfloat16()).v, 4)
+        e1 = ops.nhwc_to_nchw_f32(eng.forward(E.Tape(), E.Var(ops.latent_to_nhwc(x, torch.bfloat16, 64)), t, ctx.bfloat16()).v, 4)
+        return e0, e1, unet(x, t, ctx, return_dict=False)[0]
+    with torch.no_grad():
+        for p in ups:
+            p.zero_()
+        a0, a1, ar = outs()
+        for p, s in zip(ups, saved):
+            p.copy_(s * 2e-2)                                          # up ~ N(0, 1e-3): the adapter after a few optimiser steps
+        b0, b1, br = outs()
+        for p, s in zip(ups, saved):
+            p.copy_(s)
+    d_ref = br - ar
+    assert float(d_ref.norm() / ar.norm()) < 5e-2                       # a small perturbation of the output ...
+    for d in (b0 - a0, b1 - a1):                                        # ... that the bf16 engine reproduces in direction and size
+        cos = float((d.double() * d_ref.double()).sum() / (d.double().norm() * d_ref.double().norm()))
+        print(f"[measured] bf16 young-adapter sensitivity: cos {cos:.3f}, norm ratio {float(d.norm() / d_ref.norm()):.3f}")
+        assert cos > 0.5 and 0.3 < float(d.norm() / d_ref.norm()) < 3.0, (cos, float(d.norm() / d_ref.norm()))

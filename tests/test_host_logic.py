@@ -262,3 +262,53 @@ def test_optimizer_hyper_parameter_wiring_vs_reference():
         w = wiring[key]
         assert opt.lr == vals[w["lr"]] and tuple(opt.betas) == tuple(vals[b] for b in w["betas"])
         assert opt.wd == vals[w["wd"]] and opt.eps == vals[w["eps"]] and opt.max_norm == vals[w["clip"]]
+
+
+def test_seg_model_adapter_has_the_reference_call_signature(monkeypatch):
+    """SegModel.get_mask_loss(images, prompt, all_subtree_indices, attn_map_idx_to_wp_all, attn_map) -> 3 values, with the reference's
+    noun / attribute bookkeeping (gsam_interface.py:163-202) in front of the fused loss."""
+    import torch
+    from comat_b200 import attn_loss
+    seen = {}
+
+    def fake_loss(attn_map, words, masks, layers, tokens=77):
+        seen.update(words=words, masks=masks, layers=list(layers))
+        return torch.tensor(2.0), torch.tensor(3.0)
+    monkeypatch.setattr(attn_loss, "get_mask_loss", fake_loss)
+    calls = []
+
+    def mask_fn(image, nouns):
+        calls.append(list(nouns))
+        return None if nouns == ["dog"] else [torch.ones(1, 1, 8, 8, dtype=torch.bool) for _ in nouns]
+    seg = attn_loss.SegModel(["up_16"], mask_fn)
+    wp = {1: "a", 2: "red", 3: "app", 4: "le", 5: "dog", 6: "street"}
+    subtrees = [[[2, [3, 4]]], [[5]], [[6]], []]              # red apple | dog (no mask found) | street (stop-listed) | nothing
+    tok, pix, d = seg.get_mask_loss(torch.zeros(4, 3, 8, 8), ["p"] * 4, subtrees, [wp] * 4, {"1": {"up_16": []}})
+    assert (float(tok), float(pix)) == (2.0, 3.0) and set(d) == {"token/total", "pixel/total"}
+    assert calls == [["apple"], ["dog"]]
+    assert seen["words"] == [[[2, 3, 4]], [], [], []] and [m is None for m in seen["masks"]] == [False, True, True, True]
+
+
+def test_load_discriminator_accepts_the_reference_signature(monkeypatch):
+    import torch
+    from types import SimpleNamespace
+    from comat_b200 import gan, pipelines
+    made = {}
+
+    class FakeUNet:
+        device = "cpu"
+
+        def lora_parameters(self):
+            return []
+
+    def fake_from_pretrained(path, **kw):
+        made.update(path=path, **kw)
+        return SimpleNamespace(unet=FakeUNet(), vae=object(), text_encoder=object(), is_sdxl=False)
+    monkeypatch.setattr(pipelines.TrainableSDPipeline, "from_pretrained", staticmethod(fake_from_pretrained))
+    args = SimpleNamespace(gan_model_arch="gansd_1_5", pretrain_model="/models/sd15", lora_rank=128, gan_unet_lastlayer_cls=False,
+                           condition_discriminator=False)
+    D = gan.load_discriminator(args, torch.float16, "cpu")        # training_script.py:290 form
+    assert isinstance(D, gan.D_sd) and made["path"] == "/models/sd15" and made["dtype"] == torch.float16 and made["lora_rank"] == 128
+    assert D.D_sd_pipeline.unet is None and D.D_sd_pipeline.text_encoder is not None
+    args.gan_model_arch = "gan_sd_1_5"                            # the default string resolves to nothing in the reference too
+    assert gan.load_discriminator(args, torch.float16, "cpu") is None

@@ -41,6 +41,8 @@ def test_lr_schedules():
     assert lr_at(a, 1) == 0.5 and lr_at(a, 2) == 1.0 and abs(lr_at(a, 6) - 0.5) < 1e-12 and lr_at(a, 10) == 0.0
     a = synthetic.default_args(lr_scheduler="cosine", lr_warmup_steps=0, max_train_steps=10)
     assert lr_at(a, 0) == 1.0 and abs(lr_at(a, 5) - 0.5) < 1e-12
+    # accelerate's prepared scheduler advances num_processes times per optimiser step (training_script.py:324-330)
+    assert lr_at(a, 2, world=2) == lr_at(a, 4) and lr_at(a, 3, world=8) == lr_at(a, 24)
 
 
 def test_training_loop_checkpoints_logs_and_resume(tmp_path, monkeypatch):
