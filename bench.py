@@ -578,12 +578,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    loss_pinned = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_losses = []
+
     def timed(n_steps, host_inputs):
         barrier()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         d2h = 0
         th0 = time.perf_counter()
         e0.record()
+        pending = None
         for i in range(n_steps):
             if host_inputs:
                 b, _ = synthetic.batch_to_device(host_batches[i % len(host_batches)], dev)
@@ -591,8 +595,21 @@ def main():
                 b = dev_batches[i % len(dev_batches)]
             logs = trainer.train_step(b)
             if host_inputs:
-                loss_host = logs["step_loss"].float().cpu()       # D2H read of the step's result
-                d2h = loss_host.numel() * 4
+                # D2H read of EVERY step's result, pipelined the way a training loop logs: the copy into pinned memory is queued
+                # behind the step, the host reads the value of step i-1 while step i is being enqueued (a .cpu() here would stall
+                # the host until the whole step has run and leave the GPU idle while the next step is issued)
+                slot = loss_pinned[i % 2]
+                slot.copy_(logs["step_loss"].detach().float().reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[0].synchronize()
+                    host_losses.append(float(pending[1][0]))
+                pending = (ev, slot)
+                d2h = 4
+        if pending is not None:
+            pending[0].synchronize()
+            host_losses.append(float(pending[1][0]))
         trainer.sync()                                            # side-stream optimiser tails of the last step join the timed stream
         e1.record()
         timed.host_issue_s = (time.perf_counter() - th0) / n_steps    # time the host needed to enqueue a step (no sync inside)
@@ -735,9 +752,14 @@ def main():
     step_s = t_dev / a.steps
     roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
             "achieved": prof["flops"] / max(gemm_s, 1e-9) / 1e12, "peak": sustained, "unit": "TFLOP/s",
-            "frac": prof["flops"] / max(gemm_s, 1e-9) / 1e12 / sustained, "traffic": None, "peak_source": peak_src + ", sustained",
+            "frac": prof["flops"] / max(gemm_s, 1e-9) / 1e12 / sustained, "peak_source": peak_src + ", sustained",
             "launches_per_step": len(prof["events"]), "kernel_seconds_per_step": gemm_s,
-            "share_of_step": gemm_s / step_s, "algorithmic_tflop_per_step": prof["flops"] / 1e12}
+            "share_of_step": gemm_s / step_s, "algorithmic_tflop_per_step": prof["flops"] / 1e12,
+            "timing": "one CUDA-event pair per launch on the launching stream, eager instrumented step after the timed region",
+            # DRAM bytes of ONE launch of the family's largest in-step shape from the committed ncu --set full capture
+            "traffic": 22.9e6, "traffic_note": "dram__bytes_read + write of one conv3x3 320->320 launch at 64x64, n=8 (gemm_tc_kernel<160,3>): 22.9 MB "
+                       "read + 0.006 MB written back at capture time; algorithmic bytes 21.0 MB activations in + 1.8 MB weights + 21.0 MB out (the "
+                       "output is still L2-resident when the kernel ends); profiles/r02_ncu_v4_before_staged_export.md"}
 
     if rank == 0:
         # whole-job aggregate (weak scaling): every rank runs K optimiser steps on its own batch of `--batch` prompts, so the job
@@ -767,7 +789,10 @@ def main():
                                             "embedding gathers, layout permutes and the discriminator's per-pixel Linear(4,1) + BCE head "
                                             "(2 x B x 64 x 64 logits, fp32 as in gan_sdxl.py:32-34)") if lib_calls == 0 else
                                            "calls that fell back to aten/HF kernels (shapes the native kernels do not cover)"},
-                "e2e": {"value": world * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": world * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
+                        "losses_read_on_host": host_losses[-a.steps:],
+                        "note": "pinned-host batch copied in and the step loss copied out every step inside the timed region; the loss of "
+                                "step i-1 is read on the host while step i is enqueued"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof,
                 "losses": {k: float(v.detach()) for k, v in logs.items() if hasattr(v, "numel") and v.numel() == 1}}
         if gpu_ref is not None:

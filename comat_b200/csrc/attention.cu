@@ -64,6 +64,12 @@ struct AttnCfg {
   static constexpr int O_COL = 128;                         // S buffers at columns [0,64) and [64,128), O tile at [128, 128+DN)
 };
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 template <typename T>
 __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <>
@@ -218,12 +224,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int i = 0; i < ATT_BN; ++i)
           if (i >= kvalid) sv[i] = -INFINITY;
       }
+      // row maximum with the three-input max of sm_100 (FMNMX3): 32 instead of 63 instructions per row and tile
       float mx[4] = {sv[0], sv[1], sv[2], sv[3]};
 #pragma unroll
-      for (int i = 4; i < ATT_BN; i += 4) {
-        mx[0] = fmaxf(mx[0], sv[i]); mx[1] = fmaxf(mx[1], sv[i + 1]); mx[2] = fmaxf(mx[2], sv[i + 2]); mx[3] = fmaxf(mx[3], sv[i + 3]);
+      for (int i = 4; i + 8 <= ATT_BN; i += 8) {
+        mx[0] = fmax3(mx[0], sv[i], sv[i + 1]); mx[1] = fmax3(mx[1], sv[i + 2], sv[i + 3]);
+        mx[2] = fmax3(mx[2], sv[i + 4], sv[i + 5]); mx[3] = fmax3(mx[3], sv[i + 6], sv[i + 7]);
       }
-      const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      mx[0] = fmax3(mx[0], sv[ATT_BN - 4], sv[ATT_BN - 3]); mx[1] = fmax3(mx[1], sv[ATT_BN - 2], sv[ATT_BN - 1]);
+      const float mt = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]);
       if (j == 0) {
         m_run = mt;                               // O is not initialised yet: P.V_0 overwrites it
       } else {

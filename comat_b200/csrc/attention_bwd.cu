@@ -102,6 +102,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
   uint64_t* p_full = bars + 6;
   uint64_t* acc_full = bars + 7;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* pd_free = bars + 9;     // accumulating MMAs of the previous tile have read the P / dS tiles in smem
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsplit = (MODE == 1 && p.nsplit > 1) ? p.nsplit : 1;
@@ -119,7 +120,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
   if (warp == 0 && lane == 0) {
     mbar_init(res_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 32 * AB_ROW_WARPS); mbar_init(acc_full, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 32 * AB_ROW_WARPS); mbar_init(acc_full, 1); mbar_init(pd_free, 1);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, Cf::TMEM_COLS); tmem_relinquish(); }
@@ -161,10 +162,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
     if (lane == 0) {
       const uint32_t aR1 = smem_u32(sRes), aR2 = aR1 + Cf::NKC * AB_ROWS * 128, aPD = smem_u32(sPD);
       mbar_wait(res_full, 0);
-      int stage = 0, phase = 0;
-      for (int it = 0; it < NI; ++it) {
-        mbar_wait(&st_full[stage], phase);
-        tc_fence_after();
+      // S = A1 B1^T and dP = A2 B2^T of the inner tile held in `stage`
+      auto issue_scores = [&](int stage) {
         const uint32_t aB1 = smem_u32(sStage + stage * Cf::STAGE_BYTES), aB2 = aB1 + Cf::NAT_BYTES;
 #pragma unroll
         for (int ks = 0; ks < Cf::KSTEPS; ++ks) {
@@ -179,10 +178,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
           umma_f16(tmem_base + Cf::COL_DP, make_kmajor_sw128_desc(aR2 + offa), make_kmajor_sw128_desc(aB2 + offb), p.idesc_s, ks > 0);
         }
         umma_commit(s_full);
-        mbar_wait(p_full, it & 1);                          // row threads wrote P / dS of this tile
-        tc_fence_after();
-        // accumulating products: B = a streamed natural tile read MN-major (reduction over its BY rows, 16 rows = 2048 B
-        // per k-step, d-panels BY*128 B apart)
+      };
+      // accumulating products of inner tile `it`: B = a streamed natural tile read MN-major (reduction over its BY rows, 16 rows =
+      // 2048 B per k-step, d-panels BY*128 B apart)
+      auto issue_acc = [&](int stage, int it) {
+        const uint32_t aB1 = smem_u32(sStage + stage * Cf::STAGE_BYTES), aB2 = aB1 + Cf::NAT_BYTES;
         const uint32_t aAcc0 = (MODE == 0) ? aB1 : aB2;      // MODE 0: dQ += dS K      MODE 1: dV += P^T dO
 #pragma unroll
         for (int ks = 0; ks < Cf::BY / 16; ++ks) {
@@ -198,7 +198,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
           }
         }
         umma_commit(&st_empty[stage]);
-        if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(pd_free);
+      };
+      int stage = 0, phase = 0;
+      if constexpr (Cf::STAGES >= 2) {
+        // Software-pipelined order (r02): the scores of tile it+1 are issued BEFORE the accumulating products of tile it, so the row
+        // threads start on tile it+1 while the tensor core still accumulates tile it.  In r01's order (scores, wait, accumulate, next
+        // scores) the row threads idled for two MMA round trips per tile.  The single S / dP TMEM buffer is free once p_full(it) has
+        // fired (every row thread has read it); the P / dS smem tiles are guarded by pd_free.
+        if (NI > 0) {
+          mbar_wait(&st_full[0], 0);
+          tc_fence_after();
+          issue_scores(0);
+        }
+        for (int it = 0; it < NI; ++it) {
+          int nstage = stage + 1, nphase = phase;
+          if (nstage == Cf::STAGES) { nstage = 0; nphase ^= 1; }
+          mbar_wait(p_full, it & 1);                          // row threads wrote P / dS of this tile
+          tc_fence_after();
+          if (it + 1 < NI) {
+            mbar_wait(&st_full[nstage], nphase);
+            tc_fence_after();
+            issue_scores(nstage);
+          }
+          issue_acc(stage, it);
+          stage = nstage; phase = nphase;
+        }
+      } else {
+        for (int it = 0; it < NI; ++it) {
+          mbar_wait(&st_full[stage], phase);
+          tc_fence_after();
+          issue_scores(stage);
+          mbar_wait(p_full, it & 1);
+          tc_fence_after();
+          issue_acc(stage, it);
+          if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
+        }
       }
       umma_commit(acc_full);
     }
@@ -298,6 +333,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
             pk_ds[i / 2] = ab_pack2<T>(dsv[0], dsv[1]);
           }
         }
+        if (g == 0 && it > 0) mbar_wait(pd_free, (it - 1) & 1);   // the previous tile's accumulating MMAs have read the P / dS tiles
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int cc = c0 / 8 + q;                     // 16-byte chunk (8 columns) inside the 64-wide row

@@ -151,16 +151,20 @@ def test_attention_backward_reads_fused_projection_slices_in_place(n, L, T, H, d
     o, _, lse = A.attention_fwd_native(q, k, v, H, need_lse=True)
     got = A.attention_bwd_native(q, k, v, o, lse, None, H, do, None)
     want = A.attention_bwd_native(q.contiguous(), k.contiguous(), v.contiguous(), o, lse, None, H, do, None)
-    for a, b in zip(got, want):
-        assert a.is_contiguous() and torch.equal(a, b)
+    close = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm()) < 1e-3
+    assert got[0].is_contiguous() and torch.equal(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        # dK / dV: with few key tiles the query range is split over CTAs and summed with fp32 atomics (order varies run to run)
+        assert a.is_contiguous() and close(a, b)
     kv = torch.randn(n, T, 2 * C, device="cuda").half()
     qc = torch.randn(n, L, C, device="cuda").half()
     dp = torch.randn(n * H, L, T, device="cuda") * 0.5
     o, p, lse = A.attention_fwd_native(qc, kv[..., :C], kv[..., C:], H, export_probs=True, need_lse=True)
     got = A.attention_bwd_native(qc, kv[..., :C], kv[..., C:], o, lse, p, H, do, dp)
     want = A.attention_bwd_native(qc, kv[..., :C].contiguous(), kv[..., C:].contiguous(), o, lse, p, H, do, dp)
-    for a, b in zip(got, want):
-        assert torch.equal(a, b)
+    assert torch.equal(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        assert close(a, b)
 
 
 def test_attention_exports_and_differentiates_the_conditional_half_only():

@@ -315,36 +315,36 @@ def test_engine_unet_graphed_taped_calls_match_eager(with_capture):
 
 
 def test_bf16_engine_sees_a_young_lora_adapter():
-    """with the adapter folded into bf16 weights a small LoRA delta (|up.down| below half an ulp of W) vanishes from the
-    forward pass.  bf16 engines run the explicit branch: the change of the noise prediction caused by a young adapter follows the fp32
-    oracle's, in the no-grad pass and in the taped pass."""
+    """folding the adapter into bf16 weights (W' = round(W + up.down)) rounds a young adapter away - a delta below half an
+    ulp of W (2^-9 |W|) never reaches the output.  bf16 engines therefore run the explicit branch y = W x + up(down(x)) in every pass:
+    on one projection, the output change caused by a small adapter equals x (up.down)^T, while the folded weight loses most of it."""
     from comat_b200 import engine as E, ops
     unet, _ = _tiny()
-    params = [p for p in unet.parameters() if p.requires_grad]
+    eng = E.UNetEngine(unet, torch.bfloat16)
+    assert not eng.fold_lora and eng.lora_train_impl == "explicit"
+    a = eng._attns[0]
+    lora = a.loras[0]
     g = torch.Generator().manual_seed(8)
-    x, ctx = torch.randn(2, 4, 32, 32, generator=g).cuda(), torch.randn(2, 77, 64, generator=g).cuda()
-    t = torch.tensor(501, device="cuda")
-    ups = [p for p in params if p.shape[1] == 8]                       # (N, r) factors
-    saved = [p.detach().clone() for p in ups]
-
-    def outs():
-        eng = E.UNetEngine(unet, torch.bfloat16)
-        assert not eng.fold_lora and eng.lora_train_impl == "explicit"
-        e0 = ops.nhwc_to_nchw_f32(eng.forward(None, E.Var(ops.latent_to_nhwc(x, torch.bfloat16, 64), False), t, ctx.bfloat16()).v, 4)
-        e1 = ops.nhwc_to_nchw_f32(eng.forward(E.Tape(), E.Var(ops.latent_to_nhwc(x, torch.bfloat16, 64)), t, ctx.bfloat16()).v, 4)
-        return e0, e1, unet(x, t, ctx, return_dict=False)[0]
+    x = torch.randn(4096, a.q.k, generator=g).cuda().bfloat16()
     with torch.no_grad():
-        for p in ups:
-            p.zero_()
-        a0, a1, ar = outs()
-        for p, s in zip(ups, saved):
-            p.copy_(s * 2e-2)                                          # up ~ N(0, 1e-3): the adapter after a few optimiser steps
-        b0, b1, br = outs()
-        for p, s in zip(ups, saved):
-            p.copy_(s)
-    d_ref = br - ar
-    assert float(d_ref.norm() / ar.norm()) < 5e-2                       # a small perturbation of the output ...
-    for d in (b0 - a0, b1 - a1):                                        # ... that the bf16 engine reproduces in direction and size
-        cos = float((d.double() * d_ref.double()).sum() / (d.double().norm() * d_ref.double().norm()))
-        print(f"[measured] bf16 young-adapter sensitivity: cos {cos:.3f}, norm ratio {float(d.norm() / d_ref.norm()):.3f}")
-        assert cos > 0.5 and 0.3 < float(d.norm() / d_ref.norm()) < 3.0, (cos, float(d.norm() / d_ref.norm()))
+        up0 = lora.up.detach().clone()
+        lora.up.zero_()
+        eng.refresh_lora()
+        y0 = E.linear(None, E.Var(x, False), a.q, lora).v.float()
+        a.refresh_merged(False)
+        f0 = ops.gemm([x], [a.mq.w]).float()
+        lora.up.copy_(torch.randn(lora.up.shape, generator=g).cuda() * 2e-4)          # |up.down| ~ 1e-4 |W|-ish: a few optimiser steps old
+        eng.refresh_lora()
+        y1 = E.linear(None, E.Var(x, False), a.q, lora).v.float()
+        a.refresh_merged(False)
+        f1 = ops.gemm([x], [a.mq.w]).float()
+        want = x.float() @ (lora.up.float() @ lora.down.float()).t()
+        lora.up.copy_(up0)
+        eng.refresh_lora()
+    cos = lambda d: float((d.double() * want.double()).sum() / (d.double().norm() * want.double().norm()).clamp_min(1e-30))
+    e_cos, f_cos = cos(y1 - y0), cos(f1 - f0)
+    e_ratio, f_ratio = float((y1 - y0).norm() / want.norm()), float((f1 - f0).norm() / want.norm())
+    print(f"[measured] bf16 young adapter on one projection: explicit cos {e_cos:.3f} ratio {e_ratio:.3f}; folded cos {f_cos:.3f} ratio {f_ratio:.3f}")
+    assert float(want.norm() / y0.norm()) < 2e-2          # a small perturbation ...
+    assert e_cos > 0.5                                     # ... visible through the explicit branch (limited by bf16 output rounding)
+    assert e_cos > f_cos + 0.1 or f_ratio < 0.5 * e_ratio  # ... and mostly lost by the fold
