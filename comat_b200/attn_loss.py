@@ -142,7 +142,18 @@ class AttnMapLossPlan:
             offs.append(o)
             o += s
         self._off = offs
-        self.map_ptr = torch.tensor([m.data_ptr() for m in self.maps], dtype=torch.int64).to(device, non_blocking=True)
+        # the gradient of every map lives in ONE pre-allocated buffer whose pointer table is uploaded here together with the map
+        # pointers: the backward is then a single kernel launch - no allocation, no host-to-device copy (r01: 20 empty_like + a
+        # pageable pointer-table upload around a 74 us kernel cost 300 us, profiles/r01_attnmap_bench_v3.json)
+        sizes_el = [m.numel() for m in self.maps]
+        self.grad_flat = torch.empty(sum(sizes_el), dtype=torch.float32, device=device)
+        self.grad_views, goff = [], 0
+        for m, k in zip(self.maps, sizes_el):
+            self.grad_views.append(self.grad_flat[goff:goff + k].view(m.shape))
+            goff += k
+        ptrs = torch.tensor([m.data_ptr() for m in self.maps] + [g.data_ptr() for g in self.grad_views], dtype=torch.int64)
+        self._ptrs = ptrs.to(device, non_blocking=True)
+        self.map_ptr, self.grad_ptr = self._ptrs[:len(self.maps)], self._ptrs[len(self.maps):]
         p = _lib.AttnmapPlan()
         p.n_maps, p.n_groups, p.n_samples, p.n_words = len(self.maps), self.n_groups, B, self.n_words
         p.n_pairs, p.n_work, p.tokens = self.n_pairs, self.n_work, tokens
@@ -181,13 +192,11 @@ class _AttnMapLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g2):
         plan = ctx.plan
-        grads = [torch.empty_like(m) for m in plan.maps]
-        gp = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64).to(plan.device, non_blocking=True)
         g2 = g2.contiguous().float()
-        _lib.check(_lib.lib().comat_attnmap_loss_bwd(C.byref(plan.c), _lib.ptr(g2), _lib.ptr(ctx.state), _lib.ptr(gp),
+        _lib.check(_lib.lib().comat_attnmap_loss_bwd(C.byref(plan.c), _lib.ptr(g2), _lib.ptr(ctx.state), _lib.ptr(plan.grad_ptr),
                                                      _lib.stream_ptr()), "attnmap_loss_bwd")
         _lib.count_launch()
-        return (None, *[g.reshape(s) for g, s in zip(grads, ctx.shapes)])
+        return (None, *[g.reshape(s) for g, s in zip(plan.grad_views, ctx.shapes)])
 
 
 def fused_attnmap_loss(plan: AttnMapLossPlan, maps_for_grad: Sequence[torch.Tensor]):

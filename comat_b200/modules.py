@@ -38,6 +38,8 @@ class _UNetFn(torch.autograd.Function):
                 pvars.extend(capture.store[place])
         ctx.tape, ctx.xv, ctx.out, ctx.pvars, ctx.mod = tape, xv, out, pvars, mod
         ctx.cvar = cvar if isinstance(cvar, E.Var) else None
+        ctx.taped_key = (mod._taped_key(x, ehs, added, capture, bool(ctx.needs_input_grad[1]), ctx.wgrad)
+                         if mod.graph_taped and not ctx.needs_input_grad[3] else None)
         ctx.x_dtype, ctx.ehs_meta = x.dtype, (ehs.dtype, ehs.shape)
         return (eps.to(x.dtype), *[p.v for p in pvars])
 
@@ -74,6 +76,8 @@ class _UNetFn(torch.autograd.Function):
         if ctx.cvar is not None and ctx.cvar.g is not None:
             g_ehs = (ctx.cvar.g.float() / S).reshape(ctx.ehs_meta[1]).to(ctx.ehs_meta[0])
         ctx.tape = ctx.xv = ctx.out = ctx.pvars = ctx.cvar = None
+        if ctx.taped_key is not None:          # this signature has now run forward + backward eagerly: later calls may be captured
+            ctx.mod._taped.setdefault(ctx.taped_key, {"warm": False, "inst": [], "off": False})["warm"] = True
         return (None, gx, None, g_ehs, None, None, None, *lg)
 
 
@@ -315,20 +319,25 @@ class EngineUNet(torch.nn.Module):
             for inst in slot["inst"]:
                 inst.busy = False
 
+    @staticmethod
+    def _taped_key(sample, ehs, added, capture, needs_xgrad, wgrad):
+        return (tuple(sample.shape), tuple(ehs.shape), sample.dtype, ehs.dtype, needs_xgrad, wgrad,
+                None if capture is None else (tuple(capture.places), capture.sample_from),
+                None if added is None else tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(added.items())))
+
     def _taped_instance(self, sample, t, ehs, added, capture, needs_xgrad, wgrad):
-        """a free captured (forward, backward) graph pair for this call signature, or None -> run the call eagerly.  The first call
-        of a signature always runs eagerly (one-time kernel attribute set-up, allocator warm-up)."""
+        """a free captured (forward, backward) graph pair for this call signature, or None -> run the call eagerly.  A signature is
+        captured only after one EAGER forward + backward of it has completed (``_UNetFn.backward`` marks it): every kernel variant
+        the pass launches has then been loaded and configured - CUDA's lazy module loading inside a stream capture invalidates the
+        capture (cudaErrorStreamCaptureInvalidated, profiles/r02_gpu_tests_run7.log)."""
         eng = self.engine
         if not (self.graph_taped and sample.is_cuda and not ehs.requires_grad):
             return None
         if wgrad and not (eng.lora_train_impl == "product" and self.direct_lora_grads):
             return None
-        key = (tuple(sample.shape), tuple(ehs.shape), sample.dtype, ehs.dtype, needs_xgrad, wgrad,
-               None if capture is None else (tuple(capture.places), capture.sample_from),
-               None if added is None else tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(added.items())))
+        key = self._taped_key(sample, ehs, added, capture, needs_xgrad, wgrad)
         slot = self._taped.setdefault(key, {"warm": False, "inst": [], "off": False})
         if not slot["warm"]:
-            slot["warm"] = True
             return None
         inst = next((i for i in slot["inst"] if not i.busy), None)
         if inst is None:

@@ -307,7 +307,7 @@ def test_engine_unet_graphed_taped_calls_match_eager(with_capture):
         return res, n_inst
     ref, n0 = run(False)
     got, n1 = run(True)
-    assert n0 == 0 and n1 == 2                               # first pair eager (warm-up), second pair: two captured instances
+    assert n0 == 0 and n1 == 2                               # first pair eager (its backward marks the signature ready), second pair: two captured instances
     # same kernels, same order - but fp32 atomics (split-K gradient accumulation, GroupNorm partial sums) reorder sums from run to
     # run and a flipped fp16 rounding early in the network moves the outputs by ~1e-3 and the gradients by a few 1e-3
     for a, b in zip(got, ref):
