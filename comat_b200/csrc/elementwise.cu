@@ -571,6 +571,25 @@ extern "C" int comat_groupnorm_fwd(const void* x, void* y, const float* gamma, c
   return COMAT_OK;
 }
 
+// Statistics already accumulated by the producing GEMM's epilogue (comat_gemm_params.gn_sums: (sum, sum of squares) per
+// (image, group) = the chunk-partial layout with ONE chunk): only the apply pass runs - x is read once and y written once.
+extern "C" int comat_groupnorm_fwd_from_sums(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd,
+                                             const float* sums, int n, int HW, int C, int G, float eps, int silu, int dtype,
+                                             void* stream) {
+  if (!x || !y || !gamma || !beta || !mean_rstd || !sums || C % 8 || C % G || C / 8 > 512) return COMAT_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int thr = gn_threads(C), achunks = gn_apply_chunks(n, HW, thr / (C / 8));
+  const float inv_cnt = 1.f / ((float)HW * (C / G));
+  DISPATCH_T(dtype, {
+    if (gn_unroll() >= 8)
+      launch_k(gn_apply_kernel<T, 0, 8>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, nullptr, (T*)y, gamma, beta, sums, mean_rstd, HW, C, G, 1, achunks, inv_cnt, eps, silu);
+    else
+      launch_k(gn_apply_kernel<T, 0, 4>, dim3(achunks, n), thr, 2 * G * sizeof(float), st, (const T*)x, nullptr, (T*)y, gamma, beta, sums, mean_rstd, HW, C, G, 1, achunks, inv_cnt, eps, silu);
+  });
+  COMAT_CHECK_LAUNCH();
+  return COMAT_OK;
+}
+
 extern "C" int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* beta,
                                    const float* mean_rstd, float* ws, int n, int HW, int C, int G, int silu, int dtype, void* stream) {
   if (!x || !dy || !dx || !gamma || !beta || !mean_rstd || !ws || C % 8 || C % G || C / 8 > 512) return COMAT_ERR_INVALID;

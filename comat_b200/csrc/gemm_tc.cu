@@ -52,6 +52,10 @@ struct GemmKP {
   int tma_store;     // 1: epilogue stages 16-bit tiles in (free) pipeline smem and writes them with TMA bulk tensor stores
   int atomic_acc;    // 1: out32 += alpha * (this CTA's partial sum) with vector fp32 atomics - gradient accumulation across
                      //    K-splits AND across calls in one kernel (no partial workspace, no reduction pass)
+  // GroupNorm statistics of the OUTPUT tensor, accumulated by the epilogue (the consumer's GroupNorm then needs no statistics
+  // pass over HBM): gn_sums[(image * gn_G + group) * 2 + {0, 1}] += {sum, sum of squares} of this tile's fp32 results
+  float* gn_sums;
+  int gn_G, gn_cpg, gn_rows_per_img, gn_n_img;
 };
 
 __device__ __forceinline__ float act_apply(float x, int act) {
@@ -66,13 +70,62 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
+// GroupNorm statistics of one 32-row x 32-column piece of the output (one epilogue warp, one chunk).  f[] = this lane's row.
+// Transposing butterfly: 31 shuffles turn "lane = row, register = column" into "lane = column" with the 32 rows summed, then a
+// segmented suffix sum over the lanes of one channel group (groups are runs of gn_cpg consecutive columns) leaves the group
+// totals in each run's first lane, which adds them to the (image, group) accumulators with one fp32 atomic each.
+// Must be called by all 32 lanes (TMA-store epilogues only: every thread walks every chunk).
+__device__ __forceinline__ float gn_transpose_sum(float (&s)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float send = up ? s[k] : s[k + w];
+      const float keep = up ? s[k + w] : s[k];
+      s[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return s[0];
+}
+// image that the 32 rows of TMEM lane quarter q of a tile belong to (the host only enables the statistics when a quarter cannot
+// straddle two images: conv tiles with TW*TH >= 32 pixels per image, plain GEMMs with rows_per_image % 32 == 0)
+__device__ __forceinline__ int gn_warp_image(const GemmKP& p, int m0, int img0, int q) {
+  if (p.gn_sums == nullptr) return 0;
+  return p.conv ? img0 + (q * 32) / (p.TW * p.TH) : (m0 + q * 32) / p.gn_rows_per_img;
+}
+__device__ __forceinline__ void gn_stats_chunk(const GemmKP& p, const float (&f)[32], int col0, int ncol, bool row_ok, int img) {
+  const int lane = threadIdx.x & 31;
+  float s[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s[j] = (row_ok && j < ncol) ? f[j] : 0.f;
+  float S = gn_transpose_sum(s, lane);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s[j] = (row_ok && j < ncol) ? f[j] * f[j] : 0.f;
+  float Q = gn_transpose_sum(s, lane);
+  const int c = col0 + lane;                               // this lane's output channel
+  const int g = c / p.gn_cpg;
+  const int last = min(31, (g + 1) * p.gn_cpg - 1 - col0);  // last lane of this lane's group inside the chunk
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float ts = __shfl_down_sync(0xffffffffu, S, d), tq = __shfl_down_sync(0xffffffffu, Q, d);
+    if (lane + d <= last) { S += ts; Q += tq; }
+  }
+  const bool head = lane == 0 || (c % p.gn_cpg) == 0;
+  if (head && lane < ncol && img < p.gn_n_img) {
+    float* o = p.gn_sums + ((size_t)img * p.gn_G + g) * 2;
+    atomicAdd(o, S);
+    atomicAdd(o + 1, Q);
+  }
+}
+
 // One 32-column chunk of the epilogue for one accumulator row: v[] holds the raw fp32 accumulators of columns
 // [n0+c0, n0+c0+32) of tile row r (global row m).  zsplit = split-K slice (raw partial store), stage = smem staging tile
 // for the TMA-store path.  Every runtime option is tested once per chunk (uniform branches), the element loops are
 // straight FFMA / pack code; bias comes from smem as float4 (the first version spent ~19 instructions per element here
 // and was instruction-issue bound: profiles/r01_gemm_k320_ncu.md).
 __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (&v)[32], int c0, int n0, long long m, bool row_ok,
-                                           const float* rv, const float* s_bias, int r, unsigned char* stage, int zsplit) {
+                                           const float* rv, const float* s_bias, int r, unsigned char* stage, int zsplit, int gn_img = 0) {
   const int ncol = min(32, p.N - (n0 + c0));
   if (p.atomic_acc) {
     if (row_ok && ncol > 0) {
@@ -195,6 +248,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
         }
       }
     }
+    if (p.gn_sums != nullptr && ncol > 0) gn_stats_chunk(p, f, n0 + c0, ncol, row_ok, gn_img);   // warp-uniform (tma_store path)
     uint32_t pk[16];
     if (p.out16 != nullptr) {
       if (p.is_bf16) {
@@ -375,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
       tmem_ld_wait();
-      epilogue_chunk(p, v, c0, n0, m, row_ok, rv, s_bias, r, smem, blockIdx.z);
+      epilogue_chunk(p, v, c0, n0, m, row_ok, rv, s_bias, r, smem, blockIdx.z, gn_warp_image(p, m0, img0, q));
     }
     tc_fence_before();
     if (p.tma_store) {
@@ -598,7 +652,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         uint32_t v[32];
         tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
         tmem_ld_wait();
-        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z);
+        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, gn_warp_image(p, c.m0, c.img0, q));
       }
       tc_fence_before();
       __syncwarp();
@@ -794,7 +848,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         uint32_t v[32];
         tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
         tmem_ld_wait();
-        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z);
+        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, gn_warp_image(p, c.m0, c.img0, q));
       }
       tc_fence_before();
       __syncwarp();
@@ -832,7 +886,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int 
   pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)p.M * p.N;
-  if (idx >= total) return;
+  if (idx >= total) return;                      // whole warps leave together when the statistics are on (N % 32 == 0)
   const long long m = idx / p.N;
   const int n = (int)(idx % p.N);
   float acc = 0.f;
@@ -850,6 +904,25 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int 
     uint16_t* o = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n;
     if (p.is_bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(x); *o = *reinterpret_cast<const uint16_t*>(&t); }
     else           { const __half t = __float2half_rn(x);           *o = *reinterpret_cast<const uint16_t*>(&t); }
+  }
+  if (p.gn_sums != nullptr) {
+    // GroupNorm statistics of the output (host guarantees N % 32 == 0: a warp holds 32 consecutive channels of ONE row):
+    // segmented suffix sums over the lanes of a channel group, one pair of atomics per (row, group piece)
+    const int lane = threadIdx.x & 31;
+    const int col0 = n - lane;
+    const int g = n / p.gn_cpg;
+    const int last = min(31, (g + 1) * p.gn_cpg - 1 - col0);
+    float S = x, Q = x * x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float ts = __shfl_down_sync(0xffffffffu, S, d), tq = __shfl_down_sync(0xffffffffu, Q, d);
+      if (lane + d <= last) { S += ts; Q += tq; }
+    }
+    if (lane == 0 || (n % p.gn_cpg) == 0) {
+      float* o = p.gn_sums + ((size_t)(m / p.gn_rows_per_img) * p.gn_G + g) * 2;
+      atomicAdd(o, S);
+      atomicAdd(o + 1, Q);
+    }
   }
 }
 
@@ -1087,6 +1160,24 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     }
     kp.tma_store = ok ? 1 : 0;
   }
+  if (g->gn_sums != nullptr) {
+    // GroupNorm statistics of the output.  One-pass problems: in the TMA-store epilogue (every epilogue thread walks every
+    // chunk, so the warp shuffles are convergent), lane quarters must stay inside one image.  Split-K problems: in the
+    // reduction pass, where a warp holds 32 consecutive channels of one row.
+    const int G = g->gn_groups;
+    bool ok = G > 0 && (g->N % G) == 0 && !kp.atomic_acc && !a_mn && !b_mn && g->act != 3;
+    const int rpi = kp.conv ? g->H * g->W : g->gn_rows_per_image;
+    if (ok && kp.split_k > 1) ok = (g->N % 32) == 0 && rpi > 0 && (g->M % rpi) == 0;
+    else if (ok) {
+      ok = kp.tma_store != 0;
+      if (ok && kp.conv) ok = kp.TW * kp.TH >= 32;
+      else if (ok) ok = rpi >= 32 && (rpi % 32) == 0 && (g->M % rpi) == 0;
+    }
+    if (!ok) return COMAT_ERR_UNSUPPORTED;
+    kp.gn_sums = g->gn_sums; kp.gn_G = G; kp.gn_cpg = g->N / G;
+    kp.gn_rows_per_img = rpi;
+    kp.gn_n_img = g->M / rpi;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   int rc = COMAT_ERR_UNSUPPORTED;
   // kernel choice (COMAT_GEMM_KERNEL=tile|persist forces one for A/B measurements): the persistent kernel wins when the
@@ -1129,4 +1220,33 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     COMAT_CHECK_LAUNCH();
   }
   return rc;
+}
+
+// 1 when comat_gemm would accept p->gn_sums for this problem (same conditions, evaluated without launching anything):
+// callers use it to decide between the fused statistics and the two-pass GroupNorm.
+extern "C" int comat_gemm_gn_supported(const comat_gemm_params* g) {
+  if (!g || g->gn_groups <= 0 || (g->N % g->gn_groups) != 0 || g->a_mn_major || g->b_mn_major) return 0;
+  if (g->accumulate || g->act == 3 || g->n_seg < 1 || g->n_seg > 2) return 0;
+  const int rpi = g->conv ? g->H * g->W : g->gn_rows_per_image;
+  if (rpi <= 0 || (g->M % rpi) != 0) return 0;
+  int kb_total = 0;
+  for (int s = 0; s < g->n_seg; ++s) kb_total += (g->a_k[s] + BK - 1) / BK;
+  kb_total *= g->conv ? g->n_taps : 1;
+  int sk = g->split_k > 1 ? g->split_k : 1;
+  if (sk > kb_total) sk = kb_total;
+  if (sk > 1) { const int per = (kb_total + sk - 1) / sk; sk = (kb_total + per - 1) / per; }
+  if (sk > 1) return (g->N % 32) == 0 ? 1 : 0;              // statistics in the split-K reduction pass
+  if (!g->out16 || g->out32) return 0;
+  const char* e = getenv("COMAT_GEMM_EPILOGUE");
+  if (e && !strcmp(e, "direct")) return 0;
+  if ((g->out_ld % 8) != 0 || (reinterpret_cast<uintptr_t>(g->out16) & 15) != 0) return 0;
+  if (g->conv) {
+    if (g->out_ld != g->N || g->W <= 0 || g->H <= 0) return 0;
+    int TW = 1;
+    while (TW < g->W && TW < 128) TW <<= 1;
+    int TH = 128 / TW;
+    if (TH > g->H) { int th = 1; while (th < g->H) th <<= 1; TH = th < 128 / TW ? th : 128 / TW; }
+    return TW * TH >= 32 ? 1 : 0;
+  }
+  return (rpi >= 32 && (rpi % 32) == 0) ? 1 : 0;
 }

@@ -16,17 +16,24 @@ from typing import List, Optional, Sequence
 
 import torch
 
+import os
+
 from . import attention as attn_ops
 from . import ops
 from . import unet_weights as UW
 
+# GroupNorm statistics accumulated in the epilogue of the GEMM / conv that produces the normalised tensor (north star: ResBlock
+# conv + GN fused).  COMAT_GN_EPILOGUE=0 restores the two-pass GroupNorm everywhere (A/B measurements).
+FUSE_GN_STATS = os.environ.get("COMAT_GN_EPILOGUE", "1") != "0"
+
 
 class Var:
-    """value + accumulated gradient"""
-    __slots__ = ("v", "g", "needs_grad")
+    """value + accumulated gradient (+ the GroupNorm statistics of ``v`` when the GEMM that produced it accumulated them in its
+    epilogue: ``gn`` = (groups, sums tensor), consumed by ``groupnorm``)"""
+    __slots__ = ("v", "g", "needs_grad", "gn")
 
     def __init__(self, v, needs_grad=True):
-        self.v, self.g, self.needs_grad = v, None, needs_grad
+        self.v, self.g, self.needs_grad, self.gn = v, None, needs_grad, None
 
 
 class Tape:
@@ -156,23 +163,31 @@ class NormW:
 # ops (forward + recorded backward)
 # ------------------------------------------------------------------------------------------------------------
 def conv(tape: Optional[Tape], xs: Sequence[Var], cw: ConvW, rowvec: Optional[torch.Tensor] = None,
-         residual: Optional[Var] = None) -> Var:
+         residual: Optional[Var] = None, out_gn: Optional[int] = None) -> Var:
     """conv3x3 (stride 1 or 2) / conv1x1 over one or two channel segments (torch.cat fused away), fused
-    + bias + per-sample time-embedding row vector + residual.  NHWC in/out."""
+    + bias + per-sample time-embedding row vector + residual.  NHWC in/out.
+    ``out_gn``: group count of the GroupNorm that consumes the result - its statistics ride in this GEMM's epilogue."""
     n, H, W = xs[0].v.shape[:3]
     chans = [x.v.shape[-1] for x in xs]
     koffs = [0, chans[0]] if len(xs) == 2 else [0]
     res = residual.v if residual is not None else None
+    gn = None if (out_gn is None or not FUSE_GN_STATS) else (out_gn, H * W)
     if cw.k == 1:
         y = ops.gemm([x.v.reshape(n * H * W, c) for x, c in zip(xs, chans)], [cw.w_f] * len(xs), b_koff=koffs + [0],
-                     bias=cw.bias, rowvec=rowvec, rows_per_group=H * W, residual=res).reshape(n, H, W, cw.cout)
+                     bias=cw.bias, rowvec=rowvec, rows_per_group=H * W, residual=res, gn=gn)
+        y, sums = y if gn is not None else (y, None)
+        y = y.reshape(n, H, W, cw.cout)
     elif cw.stride == 1:
         y = ops.gemm([x.v for x in xs], [cw.w_f] * len(xs), b_koff=koffs + [0], bias=cw.bias, rowvec=rowvec,
-                     rows_per_group=H * W, residual=res, conv_taps=cw.taps_f, c_total=sum(chans) if len(xs) == 2 else cw.cin_pad)
+                     rows_per_group=H * W, residual=res, conv_taps=cw.taps_f, c_total=sum(chans) if len(xs) == 2 else cw.cin_pad, gn=gn)
+        y, sums = y if gn is not None else (y, None)
     else:
         xs2d = ops.spatial(xs[0].v, "s2d")
-        y = ops.gemm([xs2d], [cw.w_f], bias=cw.bias, conv_taps=cw.taps_f)
+        y = ops.gemm([xs2d], [cw.w_f], bias=cw.bias, conv_taps=cw.taps_f, gn=gn)
+        y, sums = y if gn is not None else (y, None)
     out = Var(y)
+    if sums is not None:
+        out.gn = (out_gn, sums)
     if tape is not None:
         def bwd():
             dy = out.g
@@ -204,18 +219,24 @@ def conv(tape: Optional[Tape], xs: Sequence[Var], cw: ConvW, rowvec: Optional[to
     return out
 
 
-def linear(tape, x: Var, lw: LinW, lora: Optional[LoRAW] = None, residual: Optional[Var] = None) -> Var:
-    """y = x W^T (+ (x down^T) up^T) + b (+ residual); token-major (.., K) -> (.., N)."""
+def linear(tape, x: Var, lw: LinW, lora: Optional[LoRAW] = None, residual: Optional[Var] = None,
+           out_gn: Optional[int] = None) -> Var:
+    """y = x W^T (+ (x down^T) up^T) + b (+ residual); token-major (.., K) -> (.., N).
+    ``out_gn`` (x is (n, L, K)): group count of the GroupNorm that consumes the result (statistics in the epilogue)."""
     xv = x.v
     x2 = xv.reshape(-1, lw.k)
     res = residual.v.reshape(-1, lw.n) if residual is not None else None
+    gn = None if (out_gn is None or not FUSE_GN_STATS or xv.dim() != 3) else (out_gn, xv.shape[1])
     if lora is not None:
         t = ops.gemm([x2], [lora.down16])
-        y = ops.gemm([x2, t], [lw.w, lora.up16], bias=lw.bias, residual=res)
+        y = ops.gemm([x2, t], [lw.w, lora.up16], bias=lw.bias, residual=res, gn=gn)
     else:
         t = None
-        y = ops.gemm([x2], [lw.w], bias=lw.bias, residual=res)
+        y = ops.gemm([x2], [lw.w], bias=lw.bias, residual=res, gn=gn)
+    y, sums = y if gn is not None else (y, None)
     out = Var(y.reshape(*xv.shape[:-1], lw.n))
+    if sums is not None:
+        out.gn = (out_gn, sums)
     if tape is not None:
         def bwd():
             dy = out.g
@@ -246,7 +267,11 @@ def linear(tape, x: Var, lw: LinW, lora: Optional[LoRAW] = None, residual: Optio
 
 
 def groupnorm(tape, x: Var, nw: NormW, silu: bool) -> Var:
-    y, mr = ops.groupnorm_fwd(x.v, nw.gamma, nw.beta, nw.groups, nw.eps, silu)
+    if x.gn is not None and x.gn[0] == nw.groups:
+        # statistics came with x from the epilogue of the GEMM that produced it: one pass (read x, write y)
+        y, mr = ops.groupnorm_fwd_from_sums(x.v, x.gn[1], nw.gamma, nw.beta, nw.groups, nw.eps, silu)
+    else:
+        y, mr = ops.groupnorm_fwd(x.v, nw.gamma, nw.beta, nw.groups, nw.eps, silu)
     out = Var(y)
     if tape is not None:
         def bwd():
@@ -417,9 +442,11 @@ class _Res:
         self.short = ConvW(m.conv_shortcut, dtype) if m.conv_shortcut is not None else None
 
 
-def _resnet(tape, r: _Res, x: Var, temb_act16, skip: Optional[Var] = None) -> Var:
+def _resnet(tape, r: _Res, x: Var, temb_act16, skip: Optional[Var] = None, out_gn: Optional[int] = None) -> Var:
     """ResnetBlock2D.  ``skip``: the UNet skip tensor — GroupNorm spans the concatenation so it is
-    materialised once; the 1x1 shortcut reads the two segments directly."""
+    materialised once; the 1x1 shortcut reads the two segments directly.
+    GroupNorm statistics: norm2's come out of conv1's epilogue, norm1's out of whatever GEMM produced ``x`` (``x.gn``; not
+    across a concatenation), and ``out_gn`` asks conv2 for the statistics of the GroupNorm that consumes this block's output."""
     xin = concat(tape, x, skip) if skip is not None else x
     h = groupnorm(tape, xin, r.n1, True)
     rowvec = None
@@ -428,10 +455,10 @@ def _resnet(tape, r: _Res, x: Var, temb_act16, skip: Optional[Var] = None) -> Va
             rowvec = temb_act16[id(r)]
         else:
             rowvec = ops.gemm([temb_act16], [r.temb.w], bias=r.temb.bias, out_fp32=True)  # (n, Cout) fp32, constant wrt params
-    h = conv(tape, [h], r.c1, rowvec=rowvec)
+    h = conv(tape, [h], r.c1, rowvec=rowvec, out_gn=r.n2.groups)
     h = groupnorm(tape, h, r.n2, True)
     sc = conv(tape, [xin], r.short) if r.short is not None else xin
-    return conv(tape, [h], r.c2, residual=sc)
+    return conv(tape, [h], r.c2, residual=sc, out_gn=out_gn)
 
 
 def _attn_layer(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Var, capture=None, place=None, mode="train",
@@ -546,7 +573,8 @@ def _attn_layer_product(tape, a: _Attn, x: Var, ctx: Optional[Var], residual: Va
     return out
 
 
-def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=None, mode="train", cross_kv=None) -> Var:
+def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=None, mode="train", cross_kv=None,
+                 out_gn: Optional[int] = None) -> Var:
     n, H, W, C = x.v.shape
     h = groupnorm(tape, x, t.gn, False)
     if t.linear_proj:
@@ -564,12 +592,13 @@ def _transformer(tape, t: _Transformer, x: Var, ctx: Var, capture=None, place=No
             ff = geglu(tape, linear(tape, layernorm(tape, h, b.n3), b.ff1))
         h = linear(tape, ff, b.ff2, residual=h)
     if t.linear_proj:
-        return _reshape(tape, linear(tape, h, t.pout, residual=_reshape(tape, x, (n, H * W, C))), (n, H, W, C))
-    return conv(tape, [_reshape(tape, h, (n, H, W, h.v.shape[-1]))], t.pout, residual=x)
+        return _reshape(tape, linear(tape, h, t.pout, residual=_reshape(tape, x, (n, H * W, C)), out_gn=out_gn), (n, H, W, C))
+    return conv(tape, [_reshape(tape, h, (n, H, W, h.v.shape[-1]))], t.pout, residual=x, out_gn=out_gn)
 
 
 def _reshape(tape, x: Var, shape) -> Var:
     out = Var(x.v.reshape(shape), x.needs_grad)
+    out.gn = x.gn                                   # per-(image, group) statistics do not depend on the view
     if tape is not None:
         def bwd():
             if out.g is not None:
@@ -813,25 +842,34 @@ class UNetEngine:
             off += r.temb.n
         # the text context is a constant of the CoMat step (frozen text encoders); a caller that wants d(ctx) passes a Var
         cvar = ctx if isinstance(ctx, Var) else Var(ctx, needs_grad=False)
-        h = conv(tape, [x], self.conv_in)
+        # GroupNorm statistics ride in the epilogue of the GEMM that produces the normalised tensor: every producer is told the
+        # group count of the GroupNorm that reads its output (None: the consumer normalises a concatenation or is not a GroupNorm)
+        ops.gn_arena_reset(x.v.device)
+        mid_gn = self.mid[0][0].n1.groups
+        h = conv(tape, [x], self.conv_in, out_gn=self.down[0][0][0].n1.groups)
         skips = [h]
-        for resnets, attns, ds in self.down:
+        for bi, (resnets, attns, ds) in enumerate(self.down):
             for i, r in enumerate(resnets):
-                h = _resnet(tape, r, h, temb)
+                nxt = resnets[i + 1].n1.groups if i + 1 < len(resnets) else (None if ds is not None else mid_gn)
+                h = _resnet(tape, r, h, temb, out_gn=attns[i].gn.groups if attns is not None else nxt)
                 if attns is not None:
-                    h = _transformer(tape, attns[i], h, cvar, capture, "down", mode, cross_kv)
+                    h = _transformer(tape, attns[i], h, cvar, capture, "down", mode, cross_kv, out_gn=nxt)
                 skips.append(h)
             if ds is not None:
-                h = conv(tape, [h], ds)
+                h = conv(tape, [h], ds, out_gn=self.down[bi + 1][0][0].n1.groups if bi + 1 < len(self.down) else mid_gn)
                 skips.append(h)
-        h = _resnet(tape, self.mid[0][0], h, temb)
-        h = _transformer(tape, self.mid[1][0], h, cvar, capture, "mid", mode, cross_kv)
-        h = _resnet(tape, self.mid[0][1], h, temb)
-        for resnets, attns, us in self.up:
+        h = _resnet(tape, self.mid[0][0], h, temb, out_gn=self.mid[1][0].gn.groups)
+        h = _transformer(tape, self.mid[1][0], h, cvar, capture, "mid", mode, cross_kv, out_gn=self.mid[0][1].n1.groups)
+        h = _resnet(tape, self.mid[0][1], h, temb)                    # consumed through a concatenation with the skip tensor
+        n_up = len(self.up)
+        for bi, (resnets, attns, us) in enumerate(self.up):
             for i, r in enumerate(resnets):
-                h = _resnet(tape, r, h, temb, skip=skips.pop())
+                # only the very last block output feeds a GroupNorm directly (conv_norm_out); the others are concatenated first
+                last = bi == n_up - 1 and i == len(resnets) - 1 and us is None
+                fin = self.norm_out.groups if last else None
+                h = _resnet(tape, r, h, temb, skip=skips.pop(), out_gn=(attns[i].gn.groups if attns is not None else fin))
                 if attns is not None:
-                    h = _transformer(tape, attns[i], h, cvar, capture, "up", mode, cross_kv)
+                    h = _transformer(tape, attns[i], h, cvar, capture, "up", mode, cross_kv, out_gn=fin)
             if us is not None:
                 h = conv(tape, [upsample2x(tape, h)], us)
         h = groupnorm(tape, h, self.norm_out, True)
@@ -860,19 +898,23 @@ class VAEDecoderEngine:
         """z: Var NHWC 16-bit (n,h,w,64) = latents / scaling_factor zero-padded; returns (n, 8h, 8w, 3)."""
         n, H, W, _ = z.v.shape
         # post_quant_conv is 1x1 4->4: run on the padded tensor, then re-pad its 4 outputs to 64 for conv_in
+        ops.gn_arena_reset(z.v.device)
         pq = conv(tape, [z], self.pq_as_padded())
-        h = conv(tape, [pq], self.conv_in)
-        h = _resnet(tape, self.mid_res[0], h, None)
+        h = conv(tape, [pq], self.conv_in, out_gn=self.mid_res[0].n1.groups)
         a = self.mid_attn
+        h = _resnet(tape, self.mid_res[0], h, None, out_gn=a.gn.groups)
         hn = _reshape(tape, groupnorm(tape, h, a.gn, False), (n, H * W, h.v.shape[-1]))
         hr = _reshape(tape, h, (n, H * W, h.v.shape[-1]))
         h = _reshape(tape, _attn_layer(tape, a, hn, None, hr), (n, H, W, h.v.shape[-1]))
-        h = _resnet(tape, self.mid_res[1], h, None)
+        # every later GroupNorm reads the output of the conv right before it (no concatenations in the decoder)
+        chain = [r for resnets, _ in self.ups for r in resnets]
+        nxt_of = {id(r): (chain[i + 1].n1.groups if i + 1 < len(chain) else self.norm_out.groups) for i, r in enumerate(chain)}
+        h = _resnet(tape, self.mid_res[1], h, None, out_gn=chain[0].n1.groups)
         for resnets, us in self.ups:
-            for r in resnets:
-                h = _resnet(tape, r, h, None)
+            for j, r in enumerate(resnets):
+                h = _resnet(tape, r, h, None, out_gn=None if (us is not None and j == len(resnets) - 1) else nxt_of[id(r)])
             if us is not None:
-                h = conv(tape, [upsample2x(tape, h)], us)
+                h = conv(tape, [upsample2x(tape, h)], us, out_gn=nxt_of[id(resnets[-1])])
         h = groupnorm(tape, h, self.norm_out, True)
         return conv(tape, [h], self.conv_out)
 

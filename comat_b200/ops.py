@@ -25,10 +25,12 @@ class GemmParams(C.Structure):
                 ("act", C.c_int32), ("residual", C.c_void_p), ("res_ld", C.c_int64), ("out16", C.c_void_p),
                 ("out_ld", C.c_int64), ("out32", C.c_void_p), ("out32_ld", C.c_int64), ("force_bn", C.c_int32),
                 ("split_k", C.c_int32), ("accumulate", C.c_int32), ("splitk_ws", C.c_void_p), ("rowvec_ld", C.c_int64),
-                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("b_dtype", C.c_int32), ("force_kernel", C.c_int32)]
+                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("b_dtype", C.c_int32), ("force_kernel", C.c_int32),
+                ("gn_sums", C.c_void_p), ("gn_groups", C.c_int32), ("gn_rows_per_image", C.c_int32)]
 
 
 _lib.register_signature("comat_gemm", [C.POINTER(GemmParams), C.c_void_p])
+_lib.register_signature("comat_gemm_gn_supported", [C.POINTER(GemmParams)])
 
 ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2, "geglu": 3}
 KERNEL = {None: 0, "auto": 0, "tile": 1, "persist": 2, "pair": 3}
@@ -55,12 +57,43 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# GroupNorm statistics accumulated by a producing GEMM's epilogue (comat_gemm_params.gn_sums) must start from zero: the
+# executors zero ONE arena per network call (gn_arena_reset) and every fused producer takes its (image, group, 2) slice from it,
+# instead of one memset launch per GroupNorm.  Slices are consumed by the GroupNorm that follows on the same stream, so the arena
+# is reused by the next call.
+_GN_ARENA_FLOATS = 1 << 18
+_gn_arena = {}
+
+
+def gn_arena_reset(device):
+    a = _gn_arena.get(device)
+    if a is None:
+        a = _gn_arena[device] = {"buf": torch.zeros(_GN_ARENA_FLOATS, dtype=torch.float32, device=device), "off": 0}
+    else:
+        a["buf"].zero_()
+        a["off"] = 0
+
+
+def _gn_take(floats: int, device) -> torch.Tensor:
+    a = _gn_arena.get(device)
+    if a is None or a["off"] + floats > _GN_ARENA_FLOATS:
+        return torch.zeros(floats, dtype=torch.float32, device=device)
+    o = a["off"]
+    a["off"] = o + (floats + 3) // 4 * 4
+    return a["buf"][o:o + floats]
+
+
 def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_koff: Sequence[int] = (0, 0),
          bias: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_group: int = 1,
          act=None, residual: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
          out_fp32: bool = False, conv_taps=None, c_total: int = 0, force_bn: int = 0, split_k: int = 0,
-         accumulate: bool = False, kernel=None) -> torch.Tensor:
+         accumulate: bool = False, kernel=None, gn: Optional[tuple] = None):
     """out[m,n] = act(alpha * sum_s A_s[m,:] . B_s[n,:] + bias[n] + rowvec[m // rows_per_group, n]) + residual[m,n]
+
+    ``gn = (groups, rows_per_image)``: also accumulate the GroupNorm statistics of ``out`` in the epilogue; returns
+    ``(out, sums)`` with sums (images * groups * 2) fp32 = (sum, sum of squares) per (image, group), or ``(out, None)`` when the
+    problem cannot take the fused statistics (split-K, fp32 output, images smaller than 32 rows): the caller then runs the
+    two-pass GroupNorm.
 
     plain mode : A_s is (M, K_s) (last dim contiguous); B_s is (N, >=K_s) K-major.
     conv mode  : ``conv_taps`` = [(dh, dw), ...]; A_s is NHWC (n, H, W, C_s) contiguous; B_s is (N, taps*c_total)
@@ -150,6 +183,13 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         ws = torch.empty(split_k * M * N, dtype=torch.float32, device=a0.device)
         p.split_k, p.splitk_ws = split_k, ws.data_ptr()
         keep.append(ws)
+    sums = None
+    if gn is not None:
+        p.gn_groups = gn[0]
+        p.gn_rows_per_image = (H * W) if conv else gn[1]
+        if _lib.lib().comat_gemm_gn_supported(C.byref(p)) == 1:
+            sums = _gn_take((M // p.gn_rows_per_image) * gn[0] * 2, a0.device)
+            p.gn_sums = sums.data_ptr()
     if PROFILE is not None and "keys_only" not in PROFILE:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -164,9 +204,9 @@ def gemm(a_segs: Sequence[torch.Tensor], b_segs: Sequence[torch.Tensor], *, b_ko
         PROFILE["events"].append((e0, e1, (M, N, tuple(a.shape[-1] for a in a_segs), len(conv_taps) if conv else 0, int(p.split_k),
                                            bool(out_fp32)), fl))
         PROFILE["flops"] += fl
-    if conv:
-        return out.reshape(n_img, H, W, n_out) if out.dim() == 2 else out
-    return out
+    if conv and out.dim() == 2:
+        out = out.reshape(n_img, H, W, n_out)
+    return (out, sums) if gn is not None else out
 
 
 def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, split_k: int = 0,
@@ -242,6 +282,7 @@ def gemm_tn(a_km: torch.Tensor, b_kn: torch.Tensor, *, out_fp32: bool = True, sp
 # ------------------------------------------------------------------------------------------------------------
 _vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 _lib.register_signature("comat_groupnorm_fwd", [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp])
+_lib.register_signature("comat_groupnorm_fwd_from_sums", [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp])
 _lib.register_signature("comat_groupnorm_bwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
 _lib.register_signature("comat_layernorm_fwd", [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp])
 _lib.register_signature("comat_layernorm_bwd", [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp])
@@ -277,6 +318,20 @@ def groupnorm_fwd(x, gamma, beta, G, eps, silu):
     mr = torch.empty(n * G * 2, dtype=torch.float32, device=x.device)
     _call("comat_groupnorm_fwd", x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mr.data_ptr(),
           _gn_ws(n, HW, G, x.device).data_ptr(), n, HW, C_, G, eps, int(silu), DT[x.dtype], _lib.stream_ptr(), launches=2)
+    return y, mr
+
+
+def groupnorm_fwd_from_sums(x, sums, gamma, beta, G, eps, silu):
+    """GroupNorm whose (sum, sum of squares) per (image, group) were accumulated by the GEMM that produced ``x``
+    (``gemm(..., gn=...)``): one pass over x.  Same return values as ``groupnorm_fwd``."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    n, C_ = x.shape[0], x.shape[-1]
+    HW = x.numel() // (n * C_)
+    y = torch.empty_like(x)
+    mr = torch.empty(n * G * 2, dtype=torch.float32, device=x.device)
+    _call("comat_groupnorm_fwd_from_sums", x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mr.data_ptr(),
+          sums.data_ptr(), n, HW, C_, G, eps, int(silu), DT[x.dtype], _lib.stream_ptr())
     return y, mr
 
 

@@ -142,9 +142,22 @@ typedef struct {
                                fp16 x bf16 operands return COMAT_ERR_UNSUPPORTED.) */
   int32_t force_kernel;     /* 0 = auto; 1 = one-tile-per-CTA kernel; 2 = persistent kernel; 3 = CTA-pair (cta_group::2) kernel
                                (tuning table / tests) */
+  float* gn_sums;           /* optional: GroupNorm statistics of the OUTPUT, accumulated by the epilogue with fp32 atomics into
+                               gn_sums[(image * gn_groups + group) * 2 + {0, 1}] += {sum, sum of squares} of the fp32 results
+                               (ZEROED by the caller).  The GroupNorm that consumes `out` (diffusers ResnetBlock2D.norm1 / norm2,
+                               Transformer2DModel.norm, conv_norm_out) then runs comat_groupnorm_fwd_from_sums: no statistics pass
+                               over HBM.  Conv mode: image = n; plain mode: image = row / gn_rows_per_image.
+                               COMAT_ERR_UNSUPPORTED when comat_gemm_gn_supported() is 0 for the problem. */
+  int32_t gn_groups;        /* number of channel groups (N % gn_groups == 0) */
+  int32_t gn_rows_per_image;/* plain mode only: rows per image, a multiple of 32 */
 } comat_gemm_params;
 
 int comat_gemm(const comat_gemm_params* p, void* stream);
+/* 1 if comat_gemm accepts p->gn_sums for this problem, else 0 (p->gn_sums itself is not read).  One-pass problems: 16-bit
+ * TMA-store epilogue, no accumulate / GEGLU, and a 32-row accumulator quarter never straddles two images (conv tiles with >= 32
+ * pixels per image, plain GEMMs with gn_rows_per_image % 32 == 0).  Split-K problems: N % 32 == 0 (the statistics are taken in
+ * the reduction pass). */
+int comat_gemm_gn_supported(const comat_gemm_params* p);
 
 /* ------------------------------------------------------------------------------------------------------------
  * HBM-bound normalisation / activation / rearrangement kernels (16-bit activations, fp32 statistics).
@@ -157,6 +170,10 @@ size_t comat_groupnorm_workspace_floats(int n, int HW, int G);
 /* y = [silu](GroupNorm(x)); saves (mean, rstd) per (n, group) in mean_rstd[n*G*2] */
 int comat_groupnorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, float* ws,
                         int n, int HW, int C, int G, float eps, int silu, int dtype, void* stream);
+/* same result from statistics a producing comat_gemm accumulated (comat_gemm_params.gn_sums): sums[n*G*2] = (sum, sum of
+ * squares) per (image, group); one pass over x (read once, written once) */
+int comat_groupnorm_fwd_from_sums(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd,
+                                  const float* sums, int n, int HW, int C, int G, float eps, int silu, int dtype, void* stream);
 int comat_groupnorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* beta,
                         const float* mean_rstd, float* ws, int n, int HW, int C, int G, int silu, int dtype, void* stream);
 int comat_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean_rstd, long long rows,

@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 
 def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_group=1, act=None, residual=None, alpha=1.0,
-         out=None, out_fp32=False, conv_taps=None, c_total=0, force_bn=0, split_k=0, accumulate=False, kernel=None):
+         out=None, out_fp32=False, conv_taps=None, c_total=0, force_bn=0, split_k=0, accumulate=False, kernel=None, gn=None):
     a0 = a_segs[0]
     N = b_segs[0].shape[0]
     if conv_taps is not None:
@@ -44,6 +44,12 @@ def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_grou
         N = N // 2
     if residual is not None:
         y = y + residual.reshape(M, N).double()
+    sums = None
+    if gn is not None:                         # epilogue statistics: (sum, sum of squares) per (image, group) of the fp32 results
+        G, rpi = gn[0], (H * W if conv_taps is not None else gn[1])
+        if M % rpi == 0 and ((split_k <= 1 and rpi % 32 == 0 and not out_fp32) or (split_k > 1 and N % 32 == 0)):
+            yg = y.reshape(M // rpi, rpi, G, N // G)
+            sums = torch.stack([yg.sum((1, 3)), (yg * yg).sum((1, 3))], -1).float().reshape(-1)
     y = y.to(torch.float32 if (out_fp32 or (out is not None and out.dtype == torch.float32)) else a0.dtype)
     if out is not None:
         if accumulate:
@@ -52,8 +58,26 @@ def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_grou
             out.reshape(M, N).copy_(y)      # in-place destination (row-slice views of fused weight buffers, static graph inputs)
         y = out
     if conv_taps is not None:
-        return y.reshape(n, H, W, N)
-    return y
+        y = y.reshape(n, H, W, N)
+    return (y, sums) if gn is not None else y
+
+
+def gn_arena_reset(device):
+    pass
+
+
+def groupnorm_fwd_from_sums(x, sums, gamma, beta, G, eps, silu):
+    n, C = x.shape[0], x.shape[-1]
+    cnt = x.numel() // (n * G)
+    s = sums.double().reshape(n, G, 2)
+    mean = s[..., 0] / cnt
+    var = (s[..., 1] / cnt - mean * mean).clamp_min(0)
+    rstd = (var + eps).rsqrt()
+    xf = x.double().reshape(n, -1, G, C // G)
+    y = ((xf - mean[:, None, :, None]) * rstd[:, None, :, None]).reshape(n, -1, C) * gamma.double() + beta.double()
+    if silu:
+        y = F.silu(y)
+    return y.reshape(x.shape).to(x.dtype), (mean[:, None, :, None], rstd[:, None, :, None], eps)
 
 
 def groupnorm_fwd(x, gamma, beta, G, eps, silu):
@@ -187,7 +211,7 @@ def install(monkeypatch):
     # CPU logic tests run the executors' attention through the torch comparator below (the product has no such path)
     monkeypatch.setattr(attention, "attention_fwd", attention_fwd)
     monkeypatch.setattr(attention, "attention_bwd", attention_bwd)
-    for name in ("gemm", "gemm_tn", "split_f32_bf16x2", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
+    for name in ("gemm", "gemm_tn", "split_f32_bf16x2", "groupnorm_fwd", "groupnorm_fwd_from_sums", "gn_arena_reset", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd",
                  "elementwise", "spatial", "transpose16", "concat_channels", "latent_to_nhwc", "nhwc_to_nchw_f32"):
         monkeypatch.setattr(ops, name, globals()[name])
 

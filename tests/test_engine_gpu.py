@@ -348,3 +348,35 @@ def test_bf16_engine_sees_a_young_lora_adapter():
     assert float(want.norm() / y0.norm()) < 2e-2          # a small perturbation ...
     assert e_cos > 0.5                                     # ... visible through the explicit branch (limited by bf16 output rounding)
     assert e_cos > f_cos + 0.1 or f_ratio < 0.5 * e_ratio  # ... and mostly lost by the fold
+
+
+def test_unet_groupnorm_statistics_come_from_the_producing_gemm(monkeypatch):
+    """NS-1 wiring: in a UNet call every GroupNorm whose input is the output of one GEMM / conv (norm2 of every ResBlock, norm1 of
+    the down / mid ResBlocks, every Transformer2DModel.norm, conv_norm_out) takes its statistics from that GEMM's epilogue; only
+    the up-path norm1's (which normalise a concatenation with the skip tensor) and shapes the epilogue refuses (split-K) run the
+    statistics pass.  The result equals the all-two-pass executor's to rounding."""
+    from comat_b200 import engine as E, ops
+    unet, _ = _tiny()
+    eng = E.UNetEngine(unet, torch.float16)
+    g = torch.Generator().manual_seed(0)
+    n, hw = 2, 32
+    x = torch.randn(n, 4, hw, hw, generator=g).cuda()
+    ctx = torch.randn(n, 77, 64, generator=g).cuda().half()
+    t = torch.tensor(500, device="cuda")
+    calls = {"fused": 0, "two_pass": 0}
+    f0, f1 = ops.groupnorm_fwd_from_sums, ops.groupnorm_fwd
+    monkeypatch.setattr(ops, "groupnorm_fwd_from_sums", lambda *a, **k: (calls.__setitem__("fused", calls["fused"] + 1), f0(*a, **k))[1])
+    monkeypatch.setattr(ops, "groupnorm_fwd", lambda *a, **k: (calls.__setitem__("two_pass", calls["two_pass"] + 1), f1(*a, **k))[1])
+    out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, torch.float16, 64), False), t, ctx)
+    n_res = len(eng._res_all)
+    n_up_res = sum(len(rs) for rs, _, _ in eng.up)
+    n_tr = sum(len(a) for _, a, _ in eng.down + eng.up if a is not None) + len(eng.mid[1])
+    total = 2 * n_res + n_tr + 1
+    assert calls["fused"] + calls["two_pass"] == total
+    assert calls["two_pass"] >= n_up_res                       # concatenated inputs
+    assert calls["fused"] >= total - n_up_res - 6, calls       # a few small-map convs run split-K (statistics refused)
+    monkeypatch.setattr(E, "FUSE_GN_STATS", False)
+    calls["fused"] = 0
+    ref = eng.forward(None, E.Var(ops.latent_to_nhwc(x, torch.float16, 64), False), t, ctx)
+    assert calls["fused"] == 0
+    assert rel(out.v.float(), ref.v.float()) < 2e-3

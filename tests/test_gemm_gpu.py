@@ -261,3 +261,91 @@ def test_gemm_fused_geglu_epilogue(M, inner, K, kernel, dtype):
     l2, mx = _rel(out.float(), ref)
     tol = 2e-3 if dtype == torch.float16 else 1.2e-2
     assert l2 < tol and mx < 4 * tol, (l2, mx)
+
+
+def _gn_ref_sums(out, n_img, G):
+    """(sum, sum of squares) per (image, group) of the stored 16-bit result, in fp64"""
+    C = out.shape[-1]
+    y = out.double().reshape(n_img, -1, G, C // G)
+    return torch.stack([y.sum((1, 3)), (y * y).sum((1, 3))], -1)
+
+
+@pytest.mark.parametrize("n,H,W,C,Cout,kernel,bn,why", [
+    (2, 32, 32, 320, 320, None, 0, "cpg 10: groups straddle the 32-column chunks"),
+    (2, 32, 32, 320, 320, "tile", 160, "one-tile kernel (4 epilogue warps)"),
+    (2, 32, 32, 320, 320, "persist", 128, "BN=128: groups straddle N tiles (128 % 10 != 0)"),
+    (4, 16, 16, 640, 640, "pair", 160, "CTA-pair kernel, cpg 20"),
+    (4, 16, 16, 640, 1280, "pair", 256, "CTA-pair kernel BN=256, cpg 40"),
+    (6, 8, 8, 1280, 1280, "tile", 0, "8x8 maps: two images per 128-pixel tile"),
+    (3, 24, 24, 128, 256, None, 0, "W=24 < TW=32: out-of-bounds tile rows must not count"),
+    (1, 64, 64, 320, 320, None, 0, "several tiles per image"),
+])
+def test_conv_epilogue_groupnorm_statistics(n, H, W, C, Cout, kernel, bn, why):
+    """NS-1: the GroupNorm statistics of a conv's output come out of its epilogue (comat_gemm_params.gn_sums) and the
+    one-pass GroupNorm built on them matches the two-pass kernel and torch's group_norm on the same tensor."""
+    from comat_b200 import ops
+    torch.manual_seed(n * H + C)
+    x = torch.randn(n, H, W, C, device="cuda").half()
+    w = (torch.randn(Cout, 9 * C, device="cuda") / (9 * C) ** 0.5).half()
+    bias = torch.randn(Cout, device="cuda") * 0.5 + 0.3            # non-zero mean: exercises E[x^2] - mean^2
+    rowvec = torch.randn(n, Cout, device="cuda")
+    res = torch.randn(n * H * W, Cout, device="cuda").half()
+    G = 32
+    ops.gn_arena_reset(x.device)
+    out, sums = ops.gemm([x], [w], conv_taps=ops.TAPS_3x3, bias=bias, rowvec=rowvec, rows_per_group=H * W, residual=res,
+                         kernel=kernel, force_bn=bn, gn=(G, H * W))
+    assert sums is not None, why
+    plain = ops.gemm([x], [w], conv_taps=ops.TAPS_3x3, bias=bias, rowvec=rowvec, rows_per_group=H * W, residual=res,
+                     kernel=kernel, force_bn=bn)
+    assert torch.equal(out, plain)                                 # the statistics do not touch the result
+    ref = _gn_ref_sums(out, n, G)
+    got = sums.double().reshape(n, G, 2)
+    cnt = H * W * (Cout // G)
+    # sums of the fp32 accumulators vs sums of their fp16 roundings: 2^-11 relative per element, averaging down with the count
+    assert ((got[..., 0] - ref[..., 0]).abs() / cnt).max() < 2e-4, why
+    assert ((got[..., 1] - ref[..., 1]).abs() / ref[..., 1]).max() < 1e-3, why
+    gamma, beta = torch.randn(Cout, device="cuda"), torch.randn(Cout, device="cuda")
+    y1, mr1 = ops.groupnorm_fwd_from_sums(out, sums, gamma, beta, G, 1e-5, True)
+    y2, mr2 = ops.groupnorm_fwd(out, gamma, beta, G, 1e-5, True)
+    yt = F.silu(F.group_norm(out.float().permute(0, 3, 1, 2), G, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+    assert _rel(y1.float(), yt)[0] < 2e-3 and _rel(y1.float(), y2.float())[0] < 1e-3, why
+    assert _rel(mr1, mr2)[0] < 1e-3, why
+
+
+@pytest.mark.parametrize("n,L,K,N,why", [(8, 4096, 320, 320, "proj_out at the 64x64 level (persistent kernel, K = 320)"),
+                                         (4, 1024, 640, 640, "32x32 level"), (4, 64, 1280, 1280, "8x8 level: 64 rows per image"),
+                                         (2, 256, 2048, 1280, "pair kernel (long K)")])
+def test_linear_epilogue_groupnorm_statistics(n, L, K, N, why):
+    from comat_b200 import ops
+    torch.manual_seed(L + K)
+    a = torch.randn(n * L, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).half()
+    res = (torch.randn(n * L, N, device="cuda") + 0.7).half()
+    ops.gn_arena_reset(a.device)
+    out, sums = ops.gemm([a], [w], residual=res, gn=(32, L))
+    assert sums is not None, why
+    ref = _gn_ref_sums(out.reshape(n, L, N), n, 32)
+    got = sums.double().reshape(n, 32, 2)
+    assert ((got[..., 0] - ref[..., 0]).abs() / (L * N // 32)).max() < 2e-4, why
+    assert ((got[..., 1] - ref[..., 1]).abs() / ref[..., 1]).max() < 1e-3, why
+
+
+def test_epilogue_groupnorm_statistics_split_k_and_refusals():
+    """split-K problems take the statistics in the reduction pass; one-pass fp32 outputs and images of fewer than 32 rows cannot
+    carry them: gemm() hands back sums=None and the caller keeps the two-pass GroupNorm"""
+    from comat_b200 import ops
+    torch.manual_seed(0)
+    a = torch.randn(256, 4096, device="cuda").half()
+    w = (torch.randn(320, 4096, device="cuda") / 64).half()
+    ops.gn_arena_reset(a.device)
+    out, sums = ops.gemm([a], [w], split_k=4, gn=(32, 64))
+    assert sums is not None and _rel(out.float(), a.float() @ w.float().t())[0] < 2e-3
+    ref = _gn_ref_sums(out.reshape(4, 64, 320), 4, 32)
+    got = sums.double().reshape(4, 32, 2)
+    assert ((got[..., 0] - ref[..., 0]).abs() / 640).max() < 2e-4
+    assert ((got[..., 1] - ref[..., 1]).abs() / ref[..., 1]).max() < 1e-3
+    a2, w2 = a[:, :320].contiguous(), w[:, :320].contiguous()
+    out, sums = ops.gemm([a2], [w2], out_fp32=True, gn=(32, 64))
+    assert sums is None
+    out, sums = ops.gemm([a2], [w2], gn=(32, 16))            # 16 rows per image: a 32-row accumulator quarter spans two images
+    assert sums is None
