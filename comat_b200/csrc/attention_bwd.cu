@@ -145,8 +145,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmA1,   // resident natural 
         mbar_expect_tx(&st_full[stage], 2 * Cf::NAT_BYTES + Cf::VEC_BYTES);
         const int y0 = (it0 + it) * Cf::BY;
         for (int c = 0; c < Cf::NKC; ++c) {
-          tma_load_3d(st + c * Cf::BY * 128, &tmB1, &st_full[stage], c * 64, h, b * Ly + y0);
-          tma_load_3d(st + Cf::NAT_BYTES + c * Cf::BY * 128, &tmB2, &st_full[stage], c * 64, h, b * Ly + y0);
+          // streamed tiles: 2-D maps, the 64-column window that starts at the head's first column (see nat_st below)
+          tma_load_2d(st + c * Cf::BY * 128, &tmB1, &st_full[stage], h * p.d + c * 64, b * Ly + y0);
+          tma_load_2d(st + Cf::NAT_BYTES + c * Cf::BY * 128, &tmB2, &st_full[stage], h * p.d + c * 64, b * Ly + y0);
         }
         if (MODE == 1) {
           unsigned char* vec = st + 2 * Cf::NAT_BYTES;
@@ -476,19 +477,29 @@ static int run_bwd(const void* q, const void* k, const void* v, const void* dO, 
     const uint32_t box[3] = {64, 1, (uint32_t)rows};
     return make_tmap_16bit(m, base, 3, dims, str, box);
   };
+  // Streamed operand tiles (K, V in the dQ pass; Q, dO in the dK / dV pass) use a 2-D map over (H*d, rows): for d = 40 the 64-wide
+  // window also carries 24 columns of the next head, which meet the zero-filled columns of the RESIDENT tiles (3-D map, out of
+  // bounds beyond d) in the S / dP products and land in accumulator columns >= d that the epilogue never stores.  With the 3-D
+  // map every 80-byte box row ended out of bounds and cost 4.3 L2 requests (profiles/r02_attn_fwd_analysis.md).
+  auto nat_st = [&](CUtensorMap* m, const void* base, int L, int rows, long long ld) {
+    const uint64_t dims[2] = {(uint64_t)H * d, (uint64_t)n * L};
+    const uint64_t str[1] = {(uint64_t)ld * 2};
+    const uint32_t box[2] = {64, (uint32_t)rows};
+    return make_tmap_16bit(m, base, 2, dims, str, box);
+  };
   kp.idesc_s = make_idesc_f16(AB_ROWS, BY, fmt);
   kp.idesc_acc = make_idesc_f16(AB_ROWS, DN, fmt, 0, 1);       // B operand MN-major
   CUtensorMap m[4];
   memset(m, 0, sizeof(m));
   // ---- MODE 0: dQ
-  bool ok = nat_ld(&m[0], q, Lq, AB_ROWS, q_ld) && nat_ld(&m[1], dO, Lq, AB_ROWS, hd) && nat_ld(&m[2], k, Lk, BY, k_ld) && nat_ld(&m[3], v, Lk, BY, v_ld);
+  bool ok = nat_ld(&m[0], q, Lq, AB_ROWS, q_ld) && nat_ld(&m[1], dO, Lq, AB_ROWS, hd) && nat_st(&m[2], k, Lk, BY, k_ld) && nat_st(&m[3], v, Lk, BY, v_ld);
   if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   kp.n_inner = (Lk + BY - 1) / BY;
   kp.out0 = dq; kp.out1 = nullptr;
   int rc = launch_ab<D, 0, T>(m, kp, dim3((Lq + AB_ROWS - 1) / AB_ROWS, H, n), st);
   if (rc) return rc;
   // ---- MODE 1: dK, dV
-  ok = nat_ld(&m[0], k, Lk, AB_ROWS, k_ld) && nat_ld(&m[1], v, Lk, AB_ROWS, v_ld) && nat_ld(&m[2], q, Lq, BY, q_ld) && nat_ld(&m[3], dO, Lq, BY, hd);
+  ok = nat_ld(&m[0], k, Lk, AB_ROWS, k_ld) && nat_ld(&m[1], v, Lk, AB_ROWS, v_ld) && nat_st(&m[2], q, Lq, BY, q_ld) && nat_st(&m[3], dO, Lq, BY, hd);
   if (!ok) { comat_set_cuda_error(-1); return COMAT_ERR_CUDA; }
   kp.n_inner = (Lq + BY - 1) / BY;
   kp.out0 = dk; kp.out1 = dv;

@@ -98,7 +98,8 @@ def test_attention_backward(n, Lq, Lk, H, d, ext, dtype, tol):
         assert rel(a.float(), b) < tol, (name, rel(a.float(), b))
 
 
-@pytest.mark.parametrize("n,L,H,d,causal", [(3, 24, 12, 64, True), (2, 150, 4, 64, True), (3, 40, 4, 64, False)])
+@pytest.mark.parametrize("n,L,H,d,causal", [(3, 24, 12, 64, True), (2, 150, 4, 64, True), (3, 40, 4, 64, False), (2, 300, 4, 64, False),
+                                            (2, 330, 8, 40, False)])
 def test_attention_padding_and_causal_masks_fwd_bwd(n, L, H, d, causal):
     """BLIP text decoder self-attention: causal mask x key-padding mask (HF modeling_blip_text.py:496-545)."""
     from comat_b200 import attention as A
