@@ -147,7 +147,6 @@ class AttnMapLossPlan:
         # pageable pointer-table upload around a 74 us kernel cost 300 us, profiles/r01_attnmap_bench_v3.json)
         sizes_el = [m.numel() for m in self.maps]
         self.grad_flat = torch.empty(sum(sizes_el), dtype=torch.float32, device=device)
-        self.grads_handed_out = False
         self.grad_views, goff = [], 0
         for m, k in zip(self.maps, sizes_el):
             self.grad_views.append(self.grad_flat[goff:goff + k].view(m.shape))
@@ -195,16 +194,17 @@ class _AttnMapLossFn(torch.autograd.Function):
         plan = ctx.plan
         g2 = g2.contiguous().float()
         views, grad_ptr = plan.grad_views, plan.grad_ptr
-        if plan.grads_handed_out:
-            # a second backward through the same forward (retain_graph): the first call's gradients may still be alive, so this
-            # one gets its own buffer + pointer table (slow path; the training step differentiates each forward once)
+        if getattr(ctx, "backward_ran", False):
+            # a second backward through the SAME forward (retain_graph): the first call's gradients may still be alive, so this
+            # one gets its own buffer + pointer table (slow path; the training step differentiates each forward once).  A plan
+            # reused by a later forward hands out the same buffer again: its gradients are valid until that plan's next backward.
             flat = torch.empty_like(plan.grad_flat)
             views, goff = [], 0
             for m in plan.maps:
                 views.append(flat[goff:goff + m.numel()].view(m.shape))
                 goff += m.numel()
             grad_ptr = torch.tensor([g.data_ptr() for g in views], dtype=torch.int64).to(plan.device)
-        plan.grads_handed_out = True
+        ctx.backward_ran = True
         _lib.check(_lib.lib().comat_attnmap_loss_bwd(C.byref(plan.c), _lib.ptr(g2), _lib.ptr(ctx.state), _lib.ptr(grad_ptr),
                                                      _lib.stream_ptr()), "attnmap_loss_bwd")
         _lib.count_launch()
