@@ -119,13 +119,27 @@ __device__ __forceinline__ void gn_stats_chunk(const GemmKP& p, const float (&f)
   }
 }
 
+// Residual prefetch: the 64 bytes of the residual row that a thread adds to one 32-column chunk, requested BEFORE the thread waits
+// for the accumulator / while it works on the previous chunk.  Without it every chunk exposed one global-memory round trip, and
+// the epilogue - not the MMA - paced the K <= 640 linears that carry a residual (out-projections, feed-forward outputs, every
+// gradient accumulation `dx += ...`: ~3 us per 128 x 160 tile against 0.8 us of MMA, profiles/r02_gemm_shapes_v7.md).
+__device__ __forceinline__ bool res_prefetch(const GemmKP& p, uint4 (&r)[4], long long m, bool row_ok, int n0, int c0) {
+  if (p.residual == nullptr || !row_ok || p.split_k > 1 || p.atomic_acc || p.act == 3 || n0 + c0 + 32 > p.N) return false;
+  const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
+  if ((reinterpret_cast<uintptr_t>(rp) & 15) != 0) return false;
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) r[j4] = *reinterpret_cast<const uint4*>(rp + j4 * 8);
+  return true;
+}
+
 // One 32-column chunk of the epilogue for one accumulator row: v[] holds the raw fp32 accumulators of columns
 // [n0+c0, n0+c0+32) of tile row r (global row m).  zsplit = split-K slice (raw partial store), stage = smem staging tile
 // for the TMA-store path.  Every runtime option is tested once per chunk (uniform branches), the element loops are
 // straight FFMA / pack code; bias comes from smem as float4 (the first version spent ~19 instructions per element here
 // and was instruction-issue bound: profiles/r01_gemm_k320_ncu.md).
 __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (&v)[32], int c0, int n0, long long m, bool row_ok,
-                                           const float* rv, const float* s_bias, int r, unsigned char* stage, int zsplit, int gn_img = 0) {
+                                           const float* rv, const float* s_bias, int r, unsigned char* stage, int zsplit, int gn_img = 0,
+                                           const uint4* rpre = nullptr) {
   const int ncol = min(32, p.N - (n0 + c0));
   if (p.atomic_acc) {
     if (row_ok && ncol > 0) {
@@ -212,10 +226,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
     }
     if (p.residual != nullptr && row_ok && ncol > 0) {
       const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
-      if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+      if (rpre != nullptr || (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0))) {
         uint4 u[4];
+        if (rpre != nullptr) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) u[j4] = *reinterpret_cast<const uint4*>(rp + j4 * 8);
+          for (int j4 = 0; j4 < 4; ++j4) u[j4] = rpre[j4];          // loaded while the accumulator was still being produced
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) u[j4] = *reinterpret_cast<const uint4*>(rp + j4 * 8);
+        }
         if (p.is_bf16) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -421,6 +440,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       row_ok = m < p.M;
     }
     const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * p.rowvec_ld : nullptr;
+    uint4 rcur[4], rnxt[4];
+    bool have_nxt = res_prefetch(p, rnxt, m, row_ok, n0, 0);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -428,8 +449,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+      const bool have = have_nxt;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
+      have_nxt = (c0 + 32 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 32);
       tmem_ld_wait();
-      epilogue_chunk(p, v, c0, n0, m, row_ok, rv, s_bias, r, smem, blockIdx.z, gn_warp_image(p, m0, img0, q));
+      epilogue_chunk(p, v, c0, n0, m, row_ok, rv, s_bias, r, smem, blockIdx.z, gn_warp_image(p, m0, img0, q), have ? rcur : nullptr);
     }
     tc_fence_before();
     if (p.tma_store) {
@@ -644,6 +669,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       for (int i = et; i < BN; i += 32 * PERSIST_EPI_WARPS) bias_buf[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
       if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();   // previous tile's stores have read the staging tile
       asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
+      uint4 rcur[4], rnxt[4];
+      bool have_nxt = res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
@@ -651,8 +678,12 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+        const bool have = have_nxt;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
+        have_nxt = (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
         tmem_ld_wait();
-        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, gn_warp_image(p, c.m0, c.img0, q));
+        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, gn_warp_image(p, c.m0, c.img0, q), have ? rcur : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -840,6 +871,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       for (int i = et; i < BN; i += 32 * PERSIST_EPI_WARPS) bias_buf[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
       if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();
       asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
+      uint4 rcur[4], rnxt[4];
+      bool have_nxt = res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
@@ -847,8 +880,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(trow + (uint32_t)c0, v);
+        const bool have = have_nxt;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
+        have_nxt = (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
         tmem_ld_wait();
-        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, gn_warp_image(p, c.m0, c.img0, q));
+        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, gn_warp_image(p, c.m0, c.img0, q), have ? rcur : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -878,6 +915,57 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 2 * ACC);
+  }
+}
+
+// split-K second pass, four columns per thread (N % 4 == 0, 16-byte aligned rows): the partials are read as float4 - the scalar
+// version below ran at ~24 us per call on the SDXL step's small-M GEMMs (54 ms of a 481 ms step, profiles/r02_cfg4_sdxl_step_kernels_*)
+__global__ void __launch_bounds__(256) splitk_reduce4_kernel(const GemmKP p, int accumulate) {
+  pdl_grid_dependency_sync();
+  const long long idx4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.M * p.N;
+  if (idx4 * 4 >= total) return;
+  const long long m = (idx4 * 4) / p.N;
+  const int n = (int)((idx4 * 4) - m * p.N);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* ws4 = reinterpret_cast<const float4*>(p.splitk_ws);
+  const long long stride4 = total / 4;
+#pragma unroll 4
+  for (int s = 0; s < p.split_k; ++s) {
+    const float4 v = ws4[(size_t)s * stride4 + idx4];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float x[4] = {acc.x * p.alpha, acc.y * p.alpha, acc.z * p.alpha, acc.w * p.alpha};
+  if (p.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
+    x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w;
+  }
+  if (p.rowvec) {
+    const float* rv = p.rowvec + (m / p.rows_per_group) * p.rowvec_ld + n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] += rv[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = act_apply(x[i], p.act);
+  if (p.residual) {
+    const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n);
+    const uint32_t w[2] = {r.x, r.y};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (p.is_bf16) { x[2 * e] += __uint_as_float(w[e] << 16); x[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u); }
+      else { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e])); x[2 * e] += t.x; x[2 * e + 1] += t.y; }
+    }
+  }
+  if (p.out32) {
+    float4* o = reinterpret_cast<float4*>(p.out32 + m * p.out32_ld + n);
+    float4 v = make_float4(x[0], x[1], x[2], x[3]);
+    if (accumulate) { const float4 c = *o; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+    *o = v;
+  }
+  if (p.out16) {
+    uint2 u;
+    u.x = pack16(x[0], x[1], p.is_bf16); u.y = pack16(x[2], x[3], p.is_bf16);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n) = u;
   }
 }
 
@@ -1216,7 +1304,12 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   }
   if (rc == COMAT_OK && kp.split_k > 1 && !kp.atomic_acc) {
     const long long total = (long long)kp.M * kp.N;
-    launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, kp, g->accumulate ? 1 : 0);
+    auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+    const bool vec4 = kp.gn_sums == nullptr && (kp.N % 4) == 0 && al(kp.splitk_ws, 16) && al(kp.bias, 16) && al(kp.out32, 16) && (kp.out32_ld % 4) == 0 &&
+                      al(kp.out16, 8) && (kp.out_ld % 4) == 0 && al(kp.residual, 8) && (kp.res_ld % 4) == 0 &&
+                      (kp.rowvec == nullptr || (kp.rowvec_ld % 4) == 0);
+    if (vec4) launch_k(splitk_reduce4_kernel, (unsigned)((total / 4 + 255) / 256), 256, 0, st, kp, g->accumulate ? 1 : 0);
+    else launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, kp, g->accumulate ? 1 : 0);
     COMAT_CHECK_LAUNCH();
   }
   return rc;
