@@ -974,7 +974,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int 
   pdl_grid_dependency_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)p.M * p.N;
-  if (idx >= total) return;                      // whole warps leave together when the statistics are on (N % 32 == 0)
+  if (idx >= total) return;
   const long long m = idx / p.N;
   const int n = (int)(idx % p.N);
   float acc = 0.f;
@@ -992,25 +992,6 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int 
     uint16_t* o = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n;
     if (p.is_bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(x); *o = *reinterpret_cast<const uint16_t*>(&t); }
     else           { const __half t = __float2half_rn(x);           *o = *reinterpret_cast<const uint16_t*>(&t); }
-  }
-  if (p.gn_sums != nullptr) {
-    // GroupNorm statistics of the output (host guarantees N % 32 == 0: a warp holds 32 consecutive channels of ONE row):
-    // segmented suffix sums over the lanes of a channel group, one pair of atomics per (row, group piece)
-    const int lane = threadIdx.x & 31;
-    const int col0 = n - lane;
-    const int g = n / p.gn_cpg;
-    const int last = min(31, (g + 1) * p.gn_cpg - 1 - col0);
-    float S = x, Q = x * x;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const float ts = __shfl_down_sync(0xffffffffu, S, d), tq = __shfl_down_sync(0xffffffffu, Q, d);
-      if (lane + d <= last) { S += ts; Q += tq; }
-    }
-    if (lane == 0 || (n % p.gn_cpg) == 0) {
-      float* o = p.gn_sums + ((size_t)(m / p.gn_rows_per_img) * p.gn_G + g) * 2;
-      atomicAdd(o, S);
-      atomicAdd(o + 1, Q);
-    }
   }
 }
 
@@ -1249,18 +1230,15 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     kp.tma_store = ok ? 1 : 0;
   }
   if (g->gn_sums != nullptr) {
-    // GroupNorm statistics of the output.  One-pass problems: in the TMA-store epilogue (every epilogue thread walks every
-    // chunk, so the warp shuffles are convergent), lane quarters must stay inside one image.  Split-K problems: in the
-    // reduction pass, where a warp holds 32 consecutive channels of one row.
+    // GroupNorm statistics of the output in the epilogue: needs the TMA-store epilogue (every epilogue thread walks every chunk,
+    // so the warp shuffles are convergent), complete sums per CTA (no split-K: statistics taken in the reduction pass were
+    // measured 3.5 ms / step SLOWER than the two-pass GroupNorm on the 8x8 / 16x16 levels that use split-K) and lane quarters
+    // that stay inside one image
     const int G = g->gn_groups;
-    bool ok = G > 0 && (g->N % G) == 0 && !kp.atomic_acc && !a_mn && !b_mn && g->act != 3;
+    bool ok = G > 0 && (g->N % G) == 0 && !kp.atomic_acc && !a_mn && !b_mn && g->act != 3 && kp.split_k == 1 && kp.tma_store != 0;
     const int rpi = kp.conv ? g->H * g->W : g->gn_rows_per_image;
-    if (ok && kp.split_k > 1) ok = (g->N % 32) == 0 && rpi > 0 && (g->M % rpi) == 0;
-    else if (ok) {
-      ok = kp.tma_store != 0;
-      if (ok && kp.conv) ok = kp.TW * kp.TH >= 32;
-      else if (ok) ok = rpi >= 32 && (rpi % 32) == 0 && (g->M % rpi) == 0;
-    }
+    if (ok && kp.conv) ok = kp.TW * kp.TH >= 32;
+    else if (ok) ok = rpi >= 32 && (rpi % 32) == 0 && (g->M % rpi) == 0;
     if (!ok) return COMAT_ERR_UNSUPPORTED;
     kp.gn_sums = g->gn_sums; kp.gn_G = G; kp.gn_cpg = g->N / G;
     kp.gn_rows_per_img = rpi;
@@ -1305,7 +1283,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   if (rc == COMAT_OK && kp.split_k > 1 && !kp.atomic_acc) {
     const long long total = (long long)kp.M * kp.N;
     auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
-    const bool vec4 = kp.gn_sums == nullptr && (kp.N % 4) == 0 && al(kp.splitk_ws, 16) && al(kp.bias, 16) && al(kp.out32, 16) && (kp.out32_ld % 4) == 0 &&
+    const bool vec4 = (kp.N % 4) == 0 && al(kp.splitk_ws, 16) && al(kp.bias, 16) && al(kp.out32, 16) && (kp.out32_ld % 4) == 0 &&
                       al(kp.out16, 8) && (kp.out_ld % 4) == 0 && al(kp.residual, 8) && (kp.res_ld % 4) == 0 &&
                       (kp.rowvec == nullptr || (kp.rowvec_ld % 4) == 0);
     if (vec4) launch_k(splitk_reduce4_kernel, (unsigned)((total / 4 + 255) / 256), 256, 0, st, kp, g->accumulate ? 1 : 0);
@@ -1328,7 +1306,7 @@ extern "C" int comat_gemm_gn_supported(const comat_gemm_params* g) {
   int sk = g->split_k > 1 ? g->split_k : 1;
   if (sk > kb_total) sk = kb_total;
   if (sk > 1) { const int per = (kb_total + sk - 1) / sk; sk = (kb_total + per - 1) / per; }
-  if (sk > 1) return (g->N % 32) == 0 ? 1 : 0;              // statistics in the split-K reduction pass
+  if (sk > 1) return 0;
   if (!g->out16 || g->out32) return 0;
   const char* e = getenv("COMAT_GEMM_EPILOGUE");
   if (e && !strcmp(e, "direct")) return 0;

@@ -153,10 +153,9 @@ typedef struct {
 } comat_gemm_params;
 
 int comat_gemm(const comat_gemm_params* p, void* stream);
-/* 1 if comat_gemm accepts p->gn_sums for this problem, else 0 (p->gn_sums itself is not read).  One-pass problems: 16-bit
- * TMA-store epilogue, no accumulate / GEGLU, and a 32-row accumulator quarter never straddles two images (conv tiles with >= 32
- * pixels per image, plain GEMMs with gn_rows_per_image % 32 == 0).  Split-K problems: N % 32 == 0 (the statistics are taken in
- * the reduction pass). */
+/* 1 if comat_gemm accepts p->gn_sums for this problem, else 0 (p->gn_sums itself is not read): 16-bit TMA-store epilogue, no
+ * split-K / accumulate / GEGLU, and a 32-row accumulator quarter never straddles two images (conv tiles with >= 32 pixels per
+ * image, plain GEMMs with gn_rows_per_image % 32 == 0). */
 int comat_gemm_gn_supported(const comat_gemm_params* p);
 
 /* ------------------------------------------------------------------------------------------------------------

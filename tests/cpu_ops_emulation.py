@@ -47,7 +47,7 @@ def gemm(a_segs, b_segs, *, b_koff=(0, 0), bias=None, rowvec=None, rows_per_grou
     sums = None
     if gn is not None:                         # epilogue statistics: (sum, sum of squares) per (image, group) of the fp32 results
         G, rpi = gn[0], (H * W if conv_taps is not None else gn[1])
-        if M % rpi == 0 and ((split_k <= 1 and rpi % 32 == 0 and not out_fp32) or (split_k > 1 and N % 32 == 0)):
+        if M % rpi == 0 and split_k <= 1 and rpi % 32 == 0 and not out_fp32:
             yg = y.reshape(M // rpi, rpi, G, N // G)
             sums = torch.stack([yg.sum((1, 3)), (yg * yg).sum((1, 3))], -1).float().reshape(-1)
     y = y.to(torch.float32 if (out_fp32 or (out is not None and out.dtype == torch.float32)) else a0.dtype)
