@@ -749,6 +749,17 @@ def main():
     trainer.train_step(dev_batches[0])
     torch.cuda.synchronize()
     ops.PROFILE = None
+    # the same eager step once more under CUPTI (torch.profiler): kernel durations without the event-record gaps that an event pair
+    # around every launch includes (context for `achieved`; the event figure stays the reported one)
+    cupti_s = None
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as kprof:
+            trainer.train_step(dev_batches[1 % len(dev_batches)])
+            torch.cuda.synchronize()
+        cupti_s = sum((e.time_range.end - e.time_range.start) for e in kprof.events() if "gemm_tc_" in e.name) * 1e-6
+    except Exception:                                      # profiler unavailable: the secondary figure is simply omitted
+        cupti_s = None
     pipe.unet.use_graphs, pipe.unet.graph_taped = graphs_were, taped_were
     gemm_s = sum(ev[0].elapsed_time(ev[1]) for ev in prof["events"]) * 1e-3
     sustained, burst, hbm, peak_src = load_peaks()
@@ -759,6 +770,13 @@ def main():
             "launches_per_step": len(prof["events"]), "kernel_seconds_per_step": gemm_s,
             "share_of_step": gemm_s / step_s, "algorithmic_tflop_per_step": prof["flops"] / 1e12,
             "timing": "one CUDA-event pair per launch on the launching stream, eager instrumented step after the timed region",
+            "achieved_cupti": None if not cupti_s else prof["flops"] / cupti_s / 1e12,
+            "frac_cupti": None if not cupti_s else prof["flops"] / cupti_s / 1e12 / sustained,
+            "kernel_seconds_per_step_cupti": cupti_s,
+            "note": "the family's launches also carry work that used to be separate passes: bias / time-embedding / residual adds, "
+                    "torch.cat as K segments, fused GEGLU (no-grad passes) and, since r02, the GroupNorm statistics of their outputs "
+                    "(49 of 61 GroupNorms per UNet call) - their time counts against the GEMM FLOPs here; *_cupti = the same launches' CUPTI "
+                    "kernel durations (an event pair around every launch also measures the ~5-7 us record gap)",
             # DRAM bytes of ONE launch of the family's largest in-step shape from the committed ncu --set full capture
             "traffic": 22.9e6, "traffic_note": "dram__bytes_read + write of one conv3x3 320->320 launch at 64x64, n=8 (gemm_tc_kernel<160,3>): 22.9 MB "
                        "read + 0.006 MB written back at capture time; algorithmic bytes 21.0 MB activations in + 1.8 MB weights + 21.0 MB out (the "
@@ -784,13 +802,14 @@ def main():
                            "library_calls_per_step": lib_calls / a.steps,
                            # second half of BASELINE's metric ("UNet attn tensor-pipe %"): not measurable without a profiler, so the
                            # committed ncu --set full capture is cited, never a number taken in this (unprofiled) run
-                           "unet_attn_tensor_pipe_pct": {"attn_fwd_kernel<40>": 23.0, "attn_bwd_kernel<40,dQ>": 22.9,
-                                                         "attn_bwd_kernel<40,dKdV>": 19.8, "shape": "SD1.5 64^2-latent self-attention, n=8, 8 heads, d=40",
-                                                         "source": "profiles/r01_attn_ncu_v19.md (sm__pipe_tensor cycles active, ncu --set full --clock-control none)"},
+                           "unet_attn_tensor_pipe_pct": {"attn_fwd_long_kernel<40>": 26.2, "attn_bwd_kernel<40,dQ>": 23.2,
+                                                         "attn_bwd_kernel<40,dKdV>": 21.1, "attn_fwd_kernel<40> cross-attention + P export (77 keys)": 5.3,
+                                                         "shape": "SD1.5 64^2-latent self-attention, n=8, 8 heads, d=40",
+                                                         "ceiling": "37 % at d = 40 while every exponential goes through MUFU (512 vs 192 clk per tile; profiles/r02_attn_fwd_analysis.md)",
+                                                         "source": "profiles/r02_ncu_v3.md (sm__pipe_tensor cycles active, ncu --set full --clock-control none)"},
                            "library_note": ("0 = every conv / linear / attention (fwd+bwd) / norm / loss / resize / optimiser launch of the step "
                                             "is a comat_b200 kernel; torch supplies memory, the fp32 latent-chain glue, "
-                                            "embedding gathers, layout permutes and the discriminator's per-pixel Linear(4,1) + BCE head "
-                                            "(2 x B x 64 x 64 logits, fp32 as in gan_sdxl.py:32-34)") if lib_calls == 0 else
+                                            "embedding gathers and layout permutes") if lib_calls == 0 else
                                            "calls that fell back to aten/HF kernels (shapes the native kernels do not cover)"},
                 "e2e": {"value": world * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                         "losses_read_on_host": host_losses[-a.steps:],
