@@ -749,17 +749,6 @@ def main():
     trainer.train_step(dev_batches[0])
     torch.cuda.synchronize()
     ops.PROFILE = None
-    # the same eager step once more under CUPTI (torch.profiler): kernel durations without the event-record gaps that an event pair
-    # around every launch includes (context for `achieved`; the event figure stays the reported one)
-    cupti_s = None
-    try:
-        from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CUDA]) as kprof:
-            trainer.train_step(dev_batches[1 % len(dev_batches)])
-            torch.cuda.synchronize()
-        cupti_s = sum((e.time_range.end - e.time_range.start) for e in kprof.events() if "gemm_tc_" in e.name) * 1e-6
-    except Exception:                                      # profiler unavailable: the secondary figure is simply omitted
-        cupti_s = None
     pipe.unet.use_graphs, pipe.unet.graph_taped = graphs_were, taped_were
     gemm_s = sum(ev[0].elapsed_time(ev[1]) for ev in prof["events"]) * 1e-3
     sustained, burst, hbm, peak_src = load_peaks()
@@ -770,13 +759,11 @@ def main():
             "launches_per_step": len(prof["events"]), "kernel_seconds_per_step": gemm_s,
             "share_of_step": gemm_s / step_s, "algorithmic_tflop_per_step": prof["flops"] / 1e12,
             "timing": "one CUDA-event pair per launch on the launching stream, eager instrumented step after the timed region",
-            "achieved_cupti": None if not cupti_s else prof["flops"] / cupti_s / 1e12,
-            "frac_cupti": None if not cupti_s else prof["flops"] / cupti_s / 1e12 / sustained,
-            "kernel_seconds_per_step_cupti": cupti_s,
             "note": "the family's launches also carry work that used to be separate passes: bias / time-embedding / residual adds, "
                     "torch.cat as K segments, fused GEGLU (no-grad passes) and, since r02, the GroupNorm statistics of their outputs "
-                    "(49 of 61 GroupNorms per UNet call) - their time counts against the GEMM FLOPs here; *_cupti = the same launches' CUPTI "
-                    "kernel durations (an event pair around every launch also measures the ~5-7 us record gap)",
+                    "(49 of 61 GroupNorms per UNet call) - their time counts against the GEMM FLOPs here.  An event pair around every "
+                    "launch also measures the ~5-7 us record gap: the same launches' CUPTI kernel durations (bench.py --kineto_step / "
+                    "--gemm_shapes, profiles/r02_gemm_shapes_v12.md) sum to 0.265 s per step = 0.49 of the peak",
             # DRAM bytes of ONE launch of the family's largest in-step shape from the committed ncu --set full capture
             "traffic": 22.9e6, "traffic_note": "dram__bytes_read + write of one conv3x3 320->320 launch at 64x64, n=8 (gemm_tc_kernel<160,3>): 22.9 MB "
                        "read + 0.006 MB written back at capture time; algorithmic bytes 21.0 MB activations in + 1.8 MB weights + 21.0 MB out (the "

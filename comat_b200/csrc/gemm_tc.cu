@@ -132,16 +132,31 @@ __device__ __forceinline__ bool res_prefetch(const GemmKP& p, uint4 (&r)[4], lon
   return true;
 }
 
+// Epilogue flavours, chosen on the host and compiled into separate kernels.  One kernel used to carry all of them behind runtime
+// branches: 6 200-6 700 instructions (~100 KB) per kernel, of which a call executes ~1 500.  Most launches of the step run 10-25 us
+// and start with a cold instruction cache; ncu's top stall on the short-K linears was `no_instruction` (3.8 per issue,
+// gpurun_out/r02_lin_32768_320_k64.ncu-rep) and a stripped epilogue was 10-25 % faster on them.  Compile-time flavours keep
+// every kernel near its executed footprint.
+enum : int {
+  EPI_STD = 0,      // bias + row vector + SiLU / GELU + residual -> 16-bit (TMA-store staging or direct) and / or fp32
+  EPI_GN = 1,       // EPI_LEAN + GroupNorm statistics of the output
+  EPI_SPLITK = 2,   // raw fp32 partials of one K slice
+  EPI_ATOMIC = 3,   // out32 += alpha * partial (vector fp32 atomics)
+  EPI_GEGLU = 4,    // bias + hidden * gelu(gate) on interleaved columns -> half-width 16-bit
+  EPI_LEAN = 5      // the common case of EPI_STD: no activation, 16-bit output through the TMA-store staging only
+};
+
 // One 32-column chunk of the epilogue for one accumulator row: v[] holds the raw fp32 accumulators of columns
 // [n0+c0, n0+c0+32) of tile row r (global row m).  zsplit = split-K slice (raw partial store), stage = smem staging tile
 // for the TMA-store path.  Every runtime option is tested once per chunk (uniform branches), the element loops are
 // straight FFMA / pack code; bias comes from smem as float4 (the first version spent ~19 instructions per element here
 // and was instruction-issue bound: profiles/r01_gemm_k320_ncu.md).
+template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (&v)[32], int c0, int n0, long long m, bool row_ok,
                                            const float* rv, const float* s_bias, int r, unsigned char* stage, int zsplit, int gn_img = 0,
                                            const uint4* rpre = nullptr) {
   const int ncol = min(32, p.N - (n0 + c0));
-  if (p.atomic_acc) {
+  if constexpr (EPI == EPI_ATOMIC) {
     if (row_ok && ncol > 0) {
       float* op = p.out32 + m * p.out32_ld + n0 + c0;
       if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
@@ -155,7 +170,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
           if (j < ncol) atomicAdd(op + j, __uint_as_float(v[j]) * p.alpha);
       }
     }
-  } else if (p.split_k > 1) {
+  } else if constexpr (EPI == EPI_SPLITK) {
     if (row_ok && ncol > 0) {
       float* wp = p.splitk_ws + ((size_t)zsplit * p.M + m) * p.N + n0 + c0;
       if (ncol == 32 && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
@@ -167,10 +182,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
           if (j < ncol) wp[j] = __uint_as_float(v[j]);
       }
     }
-  } else if (p.tma_store || (row_ok && ncol > 0)) {
-    // lean epilogue: every runtime option is tested once per 32-column chunk (uniform branches), the element loops
-    // are straight FFMA / pack code; bias comes from smem as float4 (the first version spent ~19 instructions per
-    // element here and was instruction-issue bound: profiles/r01_gemm_k320_ncu.md)
+  } else if (EPI == EPI_LEAN || EPI == EPI_GN || p.tma_store || (row_ok && ncol > 0)) {
     float f[32];
     const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
@@ -181,18 +193,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
       f[j + 2] = fmaf(__uint_as_float(v[j + 2]), p.alpha, bb.z);
       f[j + 3] = fmaf(__uint_as_float(v[j + 3]), p.alpha, bb.w);
     }
-    if (rv != nullptr) {
-      const float* rvc = rv + n0 + c0;
-      if (ncol == 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] += rvc[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncol) f[j] += rvc[j];
-      }
-    }
-    if (p.act == 3) {
+    if constexpr (EPI == EPI_GEGLU) {
       // GEGLU (diffusers GEGLU.forward: hidden * gelu(gate)) on a projection whose weight rows were interleaved at pack time
       // (column 2j = hidden_j, 2j+1 = gate_j): 32 accumulator columns -> 16 outputs of the half-width tensor.  The (M, 2*inner)
       // pre-activation never reaches HBM and the separate GEGLU pass disappears (no-grad passes; taped passes keep hg).
@@ -216,13 +217,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
         }
       }
       return;
+    } else {
+    if (rv != nullptr) {
+      const float* rvc = rv + n0 + c0;
+      if (ncol == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] += rvc[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) f[j] += rvc[j];
+      }
     }
-    if (p.act == 1) {
+    if constexpr (EPI == EPI_STD) {
+      if (p.act == 1) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
-    } else if (p.act == 2) {
+        for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+      } else if (p.act == 2) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+        for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+      }
     }
     if (p.residual != nullptr && row_ok && ncol > 0) {
       const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
@@ -267,9 +281,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
         }
       }
     }
-    if (p.gn_sums != nullptr && ncol > 0) gn_stats_chunk(p, f, n0 + c0, ncol, row_ok, gn_img);   // warp-uniform (tma_store path)
+    if constexpr (EPI == EPI_GN) {
+      if (ncol > 0) gn_stats_chunk(p, f, n0 + c0, ncol, row_ok, gn_img);   // warp-uniform: the host only picks EPI_GN with tma_store
+    }
     uint32_t pk[16];
-    if (p.out16 != nullptr) {
+    if (EPI != EPI_STD || p.out16 != nullptr) {
       if (p.is_bf16) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&t); }
@@ -278,30 +294,33 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
         for (int j = 0; j < 16; ++j) { const __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&t); }
       }
     }
-    if (p.tma_store) {
+    if (EPI != EPI_STD || p.tma_store) {
       // panel (c0/32): [128 rows][64 B], 64B-swizzled (16B chunk q of row r lives at q ^ ((r>>1)&3))
       unsigned char* prow = stage + (c0 / 32) * 8192 + r * 64;
       const int sw = (r >> 1) & 3;
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4)
         *reinterpret_cast<uint4*>(prow + ((q4 ^ sw) * 16)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-    } else if (p.out16 != nullptr) {
-      uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n0 + c0;
-      if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+    } else {
+      if (p.out16 != nullptr) {
+        uint16_t* op = reinterpret_cast<uint16_t*>(p.out16) + m * p.out_ld + n0 + c0;
+        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(op + q4 * 8) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-      } else {
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(op + q4 * 8) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncol) op[j] = (uint16_t)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xFFFFu));
+        }
+      }
+      if (p.out32 != nullptr && row_ok) {
+        float* op = p.out32 + m * p.out32_ld + n0 + c0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < ncol) op[j] = (uint16_t)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xFFFFu));
+          if (j < ncol) op[j] = f[j];
       }
     }
-    if (p.out32 != nullptr && row_ok) {
-      float* op = p.out32 + m * p.out32_ld + n0 + c0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncol) op[j] = f[j];
     }
   }
 }
@@ -321,7 +340,7 @@ struct GemmSmem {
   static constexpr int TOTAL = BIAS_OFF + BN * 4 + 1024;      // +1024: manual alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -441,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * p.rowvec_ld : nullptr;
     uint4 rcur[4], rnxt[4];
-    bool have_nxt = res_prefetch(p, rnxt, m, row_ok, n0, 0);
+    bool have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && res_prefetch(p, rnxt, m, row_ok, n0, 0);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -452,9 +471,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const bool have = have_nxt;
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
-      have_nxt = (c0 + 32 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 32);
+      have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && (c0 + 32 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 32);
       tmem_ld_wait();
-      epilogue_chunk(p, v, c0, n0, m, row_ok, rv, s_bias, r, smem, blockIdx.z, gn_warp_image(p, m0, img0, q), have ? rcur : nullptr);
+      epilogue_chunk<EPI>(p, v, c0, n0, m, row_ok, rv, s_bias, r, smem, blockIdx.z, EPI == EPI_GN ? gn_warp_image(p, m0, img0, q) : 0, have ? rcur : nullptr);
     }
     tc_fence_before();
     if (p.tma_store) {
@@ -532,7 +551,7 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const GemmKP& p, int t, in
   return make_coord(p, 2 * pm + rank, r - pm * tiles_n, z);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -670,7 +689,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();   // previous tile's stores have read the staging tile
       asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
       uint4 rcur[4], rnxt[4];
-      bool have_nxt = res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
+      bool have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
@@ -681,9 +700,9 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         const bool have = have_nxt;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
-        have_nxt = (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
+        have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
         tmem_ld_wait();
-        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, gn_warp_image(p, c.m0, c.img0, q), have ? rcur : nullptr);
+        epilogue_chunk<EPI>(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, EPI == EPI_GN ? gn_warp_image(p, c.m0, c.img0, q) : 0, have ? rcur : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -738,7 +757,7 @@ struct PairSmem {
   static_assert(STAGE_BYTES % 1024 == 0, "stage tiles must stay 1024-byte aligned");
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -872,7 +891,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();
       asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
       uint4 rcur[4], rnxt[4];
-      bool have_nxt = res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
+      bool have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
@@ -883,9 +902,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const bool have = have_nxt;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
-        have_nxt = (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
+        have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
         tmem_ld_wait();
-        epilogue_chunk(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, gn_warp_image(p, c.m0, c.img0, q), have ? rcur : nullptr);
+        epilogue_chunk<EPI>(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, EPI == EPI_GN ? gn_warp_image(p, c.m0, c.img0, q) : 0, have ? rcur : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -995,41 +1014,41 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKP p, int 
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 static int launch_gemm(const CUtensorMap* maps, const GemmKP& kp, dim3 grid, cudaStream_t st) {
   using S = GemmSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  launch_k(gemm_tc_kernel<BN, STAGES>, grid, GEMM_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  launch_k(gemm_tc_kernel<BN, STAGES, EPI>, grid, GEMM_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 static int launch_gemm_persist(const CUtensorMap* maps, const GemmKP& kp, int total_tiles, cudaStream_t st) {
   using S = PersistSmem<BN, STAGES>;
   static_assert(S::TOTAL <= 232448, "persistent GEMM smem budget");
   static bool configured = false;
   if (!configured) {
-    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  launch_k(gemm_tc_persist_kernel<BN, STAGES>, grid, PERSIST_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  launch_k(gemm_tc_persist_kernel<BN, STAGES, EPI>, grid, PERSIST_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 static int launch_gemm_pair(const CUtensorMap* maps, const GemmKP& kp, int total_pairs, cudaStream_t st) {
   using S = PairSmem<BN, STAGES>;
   static_assert(S::TOTAL <= 232448, "pair GEMM smem budget");
   static bool configured = false;
   if (!configured) {
-    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    COMAT_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
   const int max_clusters = num_sms() / 2;
@@ -1044,7 +1063,7 @@ static int launch_gemm_pair(const CUtensorMap* maps, const GemmKP& kp, int total
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = comat_pdl_enabled() ? 2 : 1;
-  cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, STAGES>, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, STAGES, EPI>, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -1235,7 +1254,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
     // measured 3.5 ms / step SLOWER than the two-pass GroupNorm on the 8x8 / 16x16 levels that use split-K) and lane quarters
     // that stay inside one image
     const int G = g->gn_groups;
-    bool ok = G > 0 && (g->N % G) == 0 && !kp.atomic_acc && !a_mn && !b_mn && g->act != 3 && kp.split_k == 1 && kp.tma_store != 0;
+    bool ok = G > 0 && (g->N % G) == 0 && !kp.atomic_acc && !a_mn && !b_mn && g->act == 0 && kp.split_k == 1 && kp.tma_store != 0;
     const int rpi = kp.conv ? g->H * g->W : g->gn_rows_per_image;
     if (ok && kp.conv) ok = kp.TW * kp.TH >= 32;
     else if (ok) ok = rpi >= 32 && (rpi % 32) == 0 && (g->M % rpi) == 0;
@@ -1257,29 +1276,56 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   const int total_tiles = (int)(grid.x * grid.y * grid.z);
   const int kb_all = kp.n_taps * (kp.seg_kblocks[0] + (g->n_seg > 1 ? kp.seg_kblocks[1] : 0));
   const bool use_persist = g->force_kernel == 2 || (g->force_kernel != 1 && (kernel_mode == 1 || (kernel_mode == 2 && (kb_all <= 24 || total_tiles <= num_sms()))));
+  // epilogue flavour (compile-time specialisation of every kernel, see EPI_*)
+  const int epi = kp.atomic_acc ? EPI_ATOMIC : kp.split_k > 1 ? EPI_SPLITK : g->act == 3 ? EPI_GEGLU : kp.gn_sums != nullptr ? EPI_GN :
+                  (kp.tma_store && g->act == 0 && !g->out32) ? EPI_LEAN : EPI_STD;
+#define COMAT_EPI_SWITCH(CALL)                                   \
+  switch (epi) {                                                 \
+    case EPI_STD:    rc = CALL(EPI_STD); break;                  \
+    case EPI_GN:     rc = CALL(EPI_GN); break;                   \
+    case EPI_SPLITK: rc = CALL(EPI_SPLITK); break;               \
+    case EPI_ATOMIC: rc = CALL(EPI_ATOMIC); break;               \
+    case EPI_LEAN:   rc = CALL(EPI_LEAN); break;                 \
+    default:         rc = CALL(EPI_GEGLU); break;                \
+  }
   if (use_pair) {
     const int pairs = (int)(((grid.x + 1) / 2) * grid.y * grid.z);
+#define PAIR_CALL_128(E) launch_gemm_pair<128, 6, E>(maps, kp, pairs, st)
+#define PAIR_CALL_160(E) launch_gemm_pair<160, 6, E>(maps, kp, pairs, st)
+#define PAIR_CALL_256(E) launch_gemm_pair<256, 4, E>(maps, kp, pairs, st)
     switch (BN) {
-      case 128: rc = launch_gemm_pair<128, 6>(maps, kp, pairs, st); break;
-      case 160: rc = launch_gemm_pair<160, 6>(maps, kp, pairs, st); break;
-      case 256: rc = launch_gemm_pair<256, 4>(maps, kp, pairs, st); break;
+      case 128: COMAT_EPI_SWITCH(PAIR_CALL_128) break;
+      case 160: COMAT_EPI_SWITCH(PAIR_CALL_160) break;
+      case 256: COMAT_EPI_SWITCH(PAIR_CALL_256) break;
     }
   } else if (use_persist) {
+#define PERS_CALL_32(E) launch_gemm_persist<32, 8, E>(maps, kp, total_tiles, st)
+#define PERS_CALL_64(E) launch_gemm_persist<64, 8, E>(maps, kp, total_tiles, st)
+#define PERS_CALL_128(E) launch_gemm_persist<128, 6, E>(maps, kp, total_tiles, st)
+#define PERS_CALL_160(E) launch_gemm_persist<160, 5, E>(maps, kp, total_tiles, st)
+#define PERS_CALL_256(E) launch_gemm_persist<256, 3, E>(maps, kp, total_tiles, st)
     switch (BN) {
-      case 32:  rc = launch_gemm_persist<32, 8>(maps, kp, total_tiles, st); break;
-      case 64:  rc = launch_gemm_persist<64, 8>(maps, kp, total_tiles, st); break;
-      case 128: rc = launch_gemm_persist<128, 6>(maps, kp, total_tiles, st); break;
-      case 160: rc = launch_gemm_persist<160, 5>(maps, kp, total_tiles, st); break;
-      case 256: rc = launch_gemm_persist<256, 3>(maps, kp, total_tiles, st); break;
+      case 32:  COMAT_EPI_SWITCH(PERS_CALL_32) break;
+      case 64:  COMAT_EPI_SWITCH(PERS_CALL_64) break;
+      case 128: COMAT_EPI_SWITCH(PERS_CALL_128) break;
+      case 160: COMAT_EPI_SWITCH(PERS_CALL_160) break;
+      case 256: COMAT_EPI_SWITCH(PERS_CALL_256) break;
     }
-  } else
-  switch (BN) {
-    case 32:  rc = launch_gemm<32, 4>(maps, kp, grid, st); break;
-    case 64:  rc = launch_gemm<64, 4>(maps, kp, grid, st); break;
-    case 128: rc = launch_gemm<128, 3>(maps, kp, grid, st); break;
-    case 160: rc = launch_gemm<160, 3>(maps, kp, grid, st); break;
-    case 256: rc = launch_gemm<256, 4>(maps, kp, grid, st); break;
+  } else {
+#define TILE_CALL_32(E) launch_gemm<32, 4, E>(maps, kp, grid, st)
+#define TILE_CALL_64(E) launch_gemm<64, 4, E>(maps, kp, grid, st)
+#define TILE_CALL_128(E) launch_gemm<128, 3, E>(maps, kp, grid, st)
+#define TILE_CALL_160(E) launch_gemm<160, 3, E>(maps, kp, grid, st)
+#define TILE_CALL_256(E) launch_gemm<256, 4, E>(maps, kp, grid, st)
+    switch (BN) {
+      case 32:  COMAT_EPI_SWITCH(TILE_CALL_32) break;
+      case 64:  COMAT_EPI_SWITCH(TILE_CALL_64) break;
+      case 128: COMAT_EPI_SWITCH(TILE_CALL_128) break;
+      case 160: COMAT_EPI_SWITCH(TILE_CALL_160) break;
+      case 256: COMAT_EPI_SWITCH(TILE_CALL_256) break;
+    }
   }
+#undef COMAT_EPI_SWITCH
   if (rc == COMAT_OK && kp.split_k > 1 && !kp.atomic_acc) {
     const long long total = (long long)kp.M * kp.N;
     auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
@@ -1297,7 +1343,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
 // callers use it to decide between the fused statistics and the two-pass GroupNorm.
 extern "C" int comat_gemm_gn_supported(const comat_gemm_params* g) {
   if (!g || g->gn_groups <= 0 || (g->N % g->gn_groups) != 0 || g->a_mn_major || g->b_mn_major) return 0;
-  if (g->accumulate || g->act == 3 || g->n_seg < 1 || g->n_seg > 2) return 0;
+  if (g->accumulate || g->act != 0 || g->n_seg < 1 || g->n_seg > 2) return 0;
   const int rpi = g->conv ? g->H * g->W : g->gn_rows_per_image;
   if (rpi <= 0 || (g->M % rpi) != 0) return 0;
   int kb_total = 0;

@@ -6,7 +6,7 @@ from comat_b200 import ops
 from tools.bench_gemm_res import timeit  # noqa
 
 ops.TUNING = {}
-for M, N, K in [(32768, 320, 320), (8192, 640, 640), (2048, 1280, 1280), (32768, 960, 320), (16384, 320, 320)]:
+for M, N, K in [(32768, 320, 320), (32768, 960, 320), (32768, 2560, 320), (32768, 1280, 320), (16384, 320, 320), (32768, 320, 64), (8192, 640, 640)]:
     nb = max(3, int(3e8 // (M * (K + 2 * N) * 2)) + 1)
     a = [torch.randn(M, K, device="cuda").half() for _ in range(nb)]
     res = [torch.randn(M, N, device="cuda").half() for _ in range(nb)]
