@@ -49,6 +49,7 @@ struct GemmKP {
   int tiles_m;                 // number of 128-row (or 128-pixel) output tiles
   int split_k, kb_per_split;   // split-K: blockIdx.z handles k-blocks [z*kb_per_split, ...) and writes raw fp32 partials
   float* splitk_ws;            // [split_k][M][N] fp32
+  int tma_res;       // 1 (persistent / pair kernels, lean flavours): the residual tile arrives in the staging tile through TMA
   int tma_store;     // 1: epilogue stages 16-bit tiles in (free) pipeline smem and writes them with TMA bulk tensor stores
   int atomic_acc;    // 1: out32 += alpha * (this CTA's partial sum) with vector fp32 atomics - gradient accumulation across
                      //    K-splits AND across calls in one kernel (no partial workspace, no reduction pass)
@@ -154,7 +155,7 @@ enum : int {
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (&v)[32], int c0, int n0, long long m, bool row_ok,
                                            const float* rv, const float* s_bias, int r, unsigned char* stage, int zsplit, int gn_img = 0,
-                                           const uint4* rpre = nullptr) {
+                                           const uint4* rpre = nullptr, bool res_staged = false) {
   const int ncol = min(32, p.N - (n0 + c0));
   if constexpr (EPI == EPI_ATOMIC) {
     if (row_ok && ncol > 0) {
@@ -238,11 +239,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, const uint32_t (
         for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
       }
     }
-    if (p.residual != nullptr && row_ok && ncol > 0) {
+    if (p.residual != nullptr && (res_staged || row_ok) && ncol > 0) {
       const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.res_ld + n0 + c0;
-      if (rpre != nullptr || (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0))) {
+      if (res_staged || rpre != nullptr || (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0))) {
         uint4 u[4];
-        if (rpre != nullptr) {
+        if (res_staged) {
+          // the residual tile was bulk-loaded into the staging tile (same 64B-swizzled panels the result is written to): this
+          // thread reads the 64 bytes it is about to overwrite
+          const unsigned char* prow = stage + (c0 / 32) * 8192 + r * 64;
+          const int sw = (r >> 1) & 3;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) u[j4] = *reinterpret_cast<const uint4*>(prow + ((j4 ^ sw) * 16));
+        } else if (rpre != nullptr) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) u[j4] = rpre[j4];          // loaded while the accumulator was still being produced
         } else {
@@ -516,7 +524,7 @@ struct PersistSmem {
   static constexpr int STAGING_OFF = TILES;                         // [(BN+31)/32 panels][128 rows][64 B]
   static constexpr int STAGING_BYTES = ((BN + 31) / 32) * 8192;
   static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;       // full[STAGES], empty[STAGES], tfull[2], tempty[2]
-  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 5) * 8;   // ... + res_full
   static constexpr int BIAS_OFF = (TMEMPTR_OFF + 8 + 15) & ~15;     // [2][BN] floats, float4-aligned
   static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;        // +1024: manual alignment slack
 };
@@ -555,7 +563,7 @@ template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                       const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
+                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmKP p) {
   pdl_trigger();
   using S = PersistSmem<BN, STAGES>;
   constexpr int ACC = tmem_cols<BN>();           // TMEM columns per accumulator buffer
@@ -565,6 +573,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull = empty_bar + STAGES;          // [2] accumulator ready for the epilogue
   uint64_t* tempty = tfull + 2;                  // [2] accumulator drained, MMA may overwrite
+  uint64_t* res_full = tempty + 2;               // residual tile of the current output tile has landed in the staging tile
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::TMEMPTR_OFF);
   float* s_bias = reinterpret_cast<float*>(smem + S::BIAS_OFF);
   unsigned char* staging = smem + S::STAGING_OFF;
@@ -583,6 +592,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], PERSIST_EPI_WARPS); mbar_init(&tempty[1], PERSIST_EPI_WARPS);      // one arrival per epilogue warp
+    mbar_init(res_full, 1);
+    if (p.tma_res) tma_prefetch_desc(&tmR);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -686,11 +697,27 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * p.rowvec_ld : nullptr;
       float* bias_buf = s_bias + (it & 1) * BN;
       for (int i = et; i < BN; i += 32 * PERSIST_EPI_WARPS) bias_buf[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-      if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();   // previous tile's stores have read the staging tile
+      constexpr bool RES_TMA_OK = (EPI == EPI_LEAN || EPI == EPI_GN);
+      const bool res_staged = RES_TMA_OK && p.tma_res != 0;
+      if (p.tma_store && warp == 2 && lane == 0) {
+        bulk_wait_read<0>();                                              // previous tile's stores have read the staging tile
+        if (res_staged) {
+          // residual tile -> staging tile (the panels the result will overwrite): asynchronous, coalesced, no registers; it lands
+          // while this tile's MMAs are still running.  (Per-thread 64-byte row loads cost +10 us on (32768, 320, 320).)
+          int npan = 0;
+          for (int pn = 0; pn < (BN + 31) / 32; ++pn) npan += (n0 + pn * 32 < p.N) ? 1 : 0;
+          mbar_expect_tx(res_full, (uint32_t)npan * 8192u);
+          for (int pn = 0; pn < npan; ++pn) {
+            if (p.conv) tma_load_4d(staging + pn * 8192, &tmR, res_full, n0 + pn * 32, c.w0, c.h0, c.img0);
+            else        tma_load_2d(staging + pn * 8192, &tmR, res_full, n0 + pn * 32, c.m0);
+          }
+        }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
       uint4 rcur[4], rnxt[4];
-      bool have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
+      bool have_nxt = !res_staged && (EPI <= EPI_GN || EPI == EPI_LEAN) && res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
       mbar_wait(&tfull[acc], aph);
+      if (res_staged) mbar_wait(res_full, it & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -700,9 +727,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         const bool have = have_nxt;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
-        have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
+        have_nxt = !res_staged && (EPI <= EPI_GN || EPI == EPI_LEAN) && (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, EPI == EPI_GN ? gn_warp_image(p, c.m0, c.img0, q) : 0, have ? rcur : nullptr);
+        epilogue_chunk<EPI>(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, EPI == EPI_GN ? gn_warp_image(p, c.m0, c.img0, q) : 0, have ? rcur : nullptr,
+                            res_staged);
       }
       tc_fence_before();
       __syncwarp();
@@ -751,7 +779,7 @@ struct PairSmem {
   static constexpr int STAGING_OFF = TILES;
   static constexpr int STAGING_BYTES = ((BN + 31) / 32) * 8192;
   static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;       // full[STAGES], empty[STAGES], tfull[2], tempty[2]
-  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 5) * 8;   // ... + res_full
   static constexpr int BIAS_OFF = (TMEMPTR_OFF + 8 + 15) & ~15;
   static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;
   static_assert(STAGE_BYTES % 1024 == 0, "stage tiles must stay 1024-byte aligned");
@@ -761,7 +789,7 @@ template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                    const __grid_constant__ CUtensorMap tmO, const GemmKP p) {
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmKP p) {
   pdl_trigger();
   using S = PairSmem<BN, STAGES>;
   constexpr int ACC = tmem_cols<BN>();
@@ -772,6 +800,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull = empty_bar + STAGES;
   uint64_t* tempty = tfull + 2;
+  uint64_t* res_full = tempty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::TMEMPTR_OFF);
   float* s_bias = reinterpret_cast<float*>(smem + S::BIAS_OFF);
   unsigned char* staging = smem + S::STAGING_OFF;
@@ -793,6 +822,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], 2 * PERSIST_EPI_WARPS); mbar_init(&tempty[1], 2 * PERSIST_EPI_WARPS);   // epilogue warps of BOTH CTAs
+    mbar_init(res_full, 1);
+    if (p.tma_res) tma_prefetch_desc(&tmR);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -888,11 +919,27 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const float* rv = (p.rowvec != nullptr && row_ok) ? p.rowvec + (m / p.rows_per_group) * p.rowvec_ld : nullptr;
       float* bias_buf = s_bias + (it & 1) * BN;
       for (int i = et; i < BN; i += 32 * PERSIST_EPI_WARPS) bias_buf[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-      if (p.tma_store && warp == 2 && lane == 0) bulk_wait_read<0>();
+      constexpr bool RES_TMA_OK = (EPI == EPI_LEAN || EPI == EPI_GN);
+      const bool res_staged = RES_TMA_OK && p.tma_res != 0;
+      if (p.tma_store && warp == 2 && lane == 0) {
+        bulk_wait_read<0>();                                              // previous tile's stores have read the staging tile
+        if (res_staged) {
+          // residual tile -> staging tile (the panels the result will overwrite): asynchronous, coalesced, no registers; it lands
+          // while this tile's MMAs are still running.  (Per-thread 64-byte row loads cost +10 us on (32768, 320, 320).)
+          int npan = 0;
+          for (int pn = 0; pn < (BN + 31) / 32; ++pn) npan += (n0 + pn * 32 < p.N) ? 1 : 0;
+          mbar_expect_tx(res_full, (uint32_t)npan * 8192u);
+          for (int pn = 0; pn < npan; ++pn) {
+            if (p.conv) tma_load_4d(staging + pn * 8192, &tmR, res_full, n0 + pn * 32, c.w0, c.h0, c.img0);
+            else        tma_load_2d(staging + pn * 8192, &tmR, res_full, n0 + pn * 32, c.m0);
+          }
+        }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * PERSIST_EPI_WARPS) : "memory");
       uint4 rcur[4], rnxt[4];
-      bool have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
+      bool have_nxt = !res_staged && (EPI <= EPI_GN || EPI == EPI_LEAN) && res_prefetch(p, rnxt, m, row_ok, n0, half * 32);
       mbar_wait(&tfull[acc], aph);
+      if (res_staged) mbar_wait(res_full, it & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(acc * ACC) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -902,9 +949,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const bool have = have_nxt;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rnxt[j4];
-        have_nxt = (EPI <= EPI_GN || EPI == EPI_LEAN) && (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
+        have_nxt = !res_staged && (EPI <= EPI_GN || EPI == EPI_LEAN) && (c0 + 64 < BN) && res_prefetch(p, rnxt, m, row_ok, n0, c0 + 64);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, EPI == EPI_GN ? gn_warp_image(p, c.m0, c.img0, q) : 0, have ? rcur : nullptr);
+        epilogue_chunk<EPI>(p, v, c0, n0, m, row_ok, rv, bias_buf, r, staging, c.z, EPI == EPI_GN ? gn_warp_image(p, c.m0, c.img0, q) : 0, have ? rcur : nullptr,
+                            res_staged);
       }
       tc_fence_before();
       __syncwarp();
@@ -1037,7 +1085,7 @@ static int launch_gemm_persist(const CUtensorMap* maps, const GemmKP& kp, int to
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  launch_k(gemm_tc_persist_kernel<BN, STAGES, EPI>, grid, PERSIST_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  launch_k(gemm_tc_persist_kernel<BN, STAGES, EPI>, grid, PERSIST_THREADS, S::TOTAL, st, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -1063,7 +1111,7 @@ static int launch_gemm_pair(const CUtensorMap* maps, const GemmKP& kp, int total
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = comat_pdl_enabled() ? 2 : 1;
-  cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, STAGES, EPI>, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, STAGES, EPI>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], kp);
   COMAT_CHECK_LAUNCH();
   return COMAT_OK;
 }
@@ -1136,7 +1184,7 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
   // fault on sm_100a (measured, profiles/r01_gpu_tests_run13.log), so mixed fp16 x bf16 operands are rejected here
   if (g->b_dtype != 0 && g->b_dtype != g->dtype) return COMAT_ERR_UNSUPPORTED;
   kp.idesc = make_idesc_f16(use_pair ? 2 * BM : BM, BN, kp.is_bf16 ? 1 : 0, a_mn, b_mn);
-  CUtensorMap maps[5];
+  CUtensorMap maps[6];
   memset(maps, 0, sizeof(maps));
   dim3 grid;
   kp.conv = g->conv ? 1 : 0;
@@ -1247,6 +1295,29 @@ extern "C" int comat_gemm(const comat_gemm_params* g, void* stream) {
       ok = make_tmap_16bit(&maps[4], g->out16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
     }
     kp.tma_store = ok ? 1 : 0;
+  }
+  // residual through TMA (persistent / pair kernels, lean flavours): same geometry and panel layout as the output tile.
+  // COMAT_GEMM_TMA_RES=0 keeps the per-thread (prefetched) row loads.
+  {
+    static int res_mode = -1;
+    if (res_mode < 0) { const char* e = getenv("COMAT_GEMM_TMA_RES"); res_mode = (e && e[0] == '0') ? 0 : 1; }
+    kp.tma_res = 0;
+    if (res_mode == 1 && kp.tma_store && g->residual && g->act == 0 && (g->res_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0 &&
+        (!kp.conv || g->res_ld == g->N)) {
+      bool ok;
+      if (kp.conv) {
+        const uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->W, (uint64_t)g->H, (uint64_t)g->n_img};
+        const uint64_t str[3] = {(uint64_t)g->res_ld * 2, (uint64_t)g->res_ld * 2 * g->W, (uint64_t)g->res_ld * 2 * g->W * g->H};
+        const uint32_t box[4] = {32u, (uint32_t)kp.TW, (uint32_t)kp.TH, (uint32_t)kp.TN};
+        ok = make_tmap_16bit(&maps[5], g->residual, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      } else {
+        const uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
+        const uint64_t str[1] = {(uint64_t)g->res_ld * 2};
+        const uint32_t box[2] = {32u, (uint32_t)BM};
+        ok = make_tmap_16bit(&maps[5], g->residual, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      }
+      kp.tma_res = ok ? 1 : 0;
+    }
   }
   if (g->gn_sums != nullptr) {
     // GroupNorm statistics of the output in the epilogue: needs the TMA-store epilogue (every epilogue thread walks every chunk,
