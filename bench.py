@@ -18,6 +18,13 @@ roofline: the tcgen05 GEMM/conv kernel family (dominant), algorithmic FLOPs / pe
 """
 from __future__ import annotations
 
+import os as _os
+# Multi-rank runs: load every CUDA module eagerly.  With the default lazy loading, the first use of a kernel variant inside an optimiser
+# tail (first launches of a GEMM flavour, on the side stream, while the gradient all-reduce of the OTHER optimiser is in flight and
+# waits for the peer) blocked the host in the module load on both ranks and the job dead-locked in its first step
+# (gpurun_out/r02_bench_2gpu_dbg.err: both ranks parked inside comat_gemm).  Must be set before the CUDA context exists.
+if int(_os.environ.get("WORLD_SIZE", "1")) > 1:
+    _os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 import argparse
 import json
 import os
@@ -484,6 +491,10 @@ def main():
     if a.batch == 0:
         a.batch = CONFIGS[a.config]["batch"]
     _claim_stdout()
+    if os.environ.get("COMAT_BENCH_WATCHDOG"):
+        # debugging aid: dump every thread's Python stack to stderr and exit if the run is still going after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["COMAT_BENCH_WATCHDOG"]), exit=True)
     if os.environ.get("COMAT_HOST_ONLY_TIMING"):
         raise SystemExit("bench.py: COMAT_HOST_ONLY_TIMING is set - refusing to emit a bench line (tools/host_issue_time.py is the host-only probe)")
     if a.impl == "reference":

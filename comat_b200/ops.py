@@ -40,7 +40,7 @@ def _load_tuning():
     """measured (tile width, kernel, split-K) choices per GEMM shape of the SD1.5 / SDXL step, written by tools/tune_gemm.py
     on a B200 (comat_b200/gemm_tuning.json).  Shapes that are not in the table use the C side's heuristics."""
     import json, os
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_tuning.json")
+    path = os.environ.get("COMAT_GEMM_TUNING_FILE") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_tuning.json")
     if os.environ.get("COMAT_GEMM_TUNING", "1") == "0" or not os.path.exists(path):
         return {}
     with open(path) as fh:
