@@ -779,7 +779,7 @@ def main():
                     "torch.cat as K segments, fused GEGLU (no-grad passes) and, since r02, the GroupNorm statistics of their outputs "
                     "(49 of 61 GroupNorms per UNet call) - their time counts against the GEMM FLOPs here.  An event pair around every "
                     "launch also measures the ~5-7 us record gap: the same launches' CUPTI kernel durations (bench.py --kineto_step / "
-                    "--gemm_shapes, profiles/r02_gemm_shapes_v12.md) sum to 0.265 s per step = 0.49 of the peak",
+                    "--gemm_shapes, profiles/r02_gemm_shapes_v16.md) sum to 0.238 s per step = 756 TFLOP/s = 0.55 of the peak",
             # DRAM bytes of ONE launch of the family's largest in-step shape from the committed ncu --set full capture
             "traffic": 22.9e6, "traffic_note": "dram__bytes_read + write of one conv3x3 320->320 launch at 64x64, n=8 (gemm_tc_kernel<160,3>): 22.9 MB "
                        "read + 0.006 MB written back at capture time; algorithmic bytes 21.0 MB activations in + 1.8 MB weights + 21.0 MB out (the "
