@@ -366,7 +366,7 @@ class Trainer:
                     self.validate()
             if self.global_step >= a.max_train_steps:
                 break
-        self.core.sync()
+        self.core.close() if hasattr(self.core, "close") else self.core.sync()       # joins the side-stream updates, restores the GC
         self._flush_logs()
         self.save()                                                                   # addition: the reference ends without saving (:720-722)
         if self.device.type == "cuda":

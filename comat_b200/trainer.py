@@ -268,6 +268,14 @@ class CoMatTrainer:
             gc.freeze()          # weights, executors, captured graphs: long-lived, keep them out of every later scan
             gc.disable()
 
+    def close(self):
+        """end of training: join the outstanding updates and give the process its garbage collector back (``_gc_before_step`` froze
+        the long-lived objects and disabled the automatic collector for the duration of the loop)."""
+        self.sync()
+        if self.manual_gc_interval > 0 and not gc.isenabled():
+            gc.unfreeze()
+            gc.enable()
+
     def _gc_after_step(self):
         if self.manual_gc_interval > 0 and self.global_step % self.manual_gc_interval == 0:
             gc.collect()

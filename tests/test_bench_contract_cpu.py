@@ -33,3 +33,17 @@ def test_bench_line_contract(name):
     if line["n_gpus"] == 1:
         c = line["cpu_baseline"]
         assert set(c) >= {"value", "unit", "cores", "kind", "sample"} and c["kind"] in ("reference", "port") and c["cores"] >= 1
+
+
+def test_multi_rank_processes_load_cuda_modules_eagerly(monkeypatch):
+    """WORLD_SIZE > 1: bench.py / the package set CUDA_MODULE_LOADING=EAGER before any CUDA context exists (lazy loading of a kernel
+    variant's first launch inside an optimiser tail dead-locked against the peer-waiting all-reduce); single-rank
+    runs leave the variable alone."""
+    import importlib, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "import os, sys; sys.path.insert(0, %r); import bench; import comat_b200; print(os.environ.get('CUDA_MODULE_LOADING'))" % root
+    for ws, want in (("2", "EAGER"), ("1", "None")):
+        env = dict(os.environ, WORLD_SIZE=ws)
+        env.pop("CUDA_MODULE_LOADING", None)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.stdout.strip().splitlines()[-1] == want, (ws, out.stdout, out.stderr[-500:])
