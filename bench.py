@@ -415,6 +415,7 @@ def run_config5(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))      # torchrun pins OMP_NUM_THREADS=1: model construction crawls
     dt = torch.float16 if a.dtype == "fp16" else torch.bfloat16
     lat, n = (32 if a.tiny else a.latent), a.batch
     unet_p = synthetic.build_sdxl_unet(dev, rank=8 if a.tiny else a.rank_lora, seed=42, tiny=a.tiny)
@@ -521,6 +522,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))      # torchrun pins OMP_NUM_THREADS=1: model construction crawls
     _lib.lib()
     dt = torch.float16 if a.dtype == "fp16" else torch.bfloat16
     gan, attrcon = not a.no_gan, not a.no_attrcon
