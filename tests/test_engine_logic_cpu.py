@@ -188,3 +188,36 @@ def test_engine_unet_module_returns_context_gradient_to_autograd(monkeypatch):
     xr = x.clone().requires_grad_(True)
     (mod(xr, t, encoder_hidden_states=c3)[0] * dy).sum().backward()
     assert c3.grad is None and xr.grad is not None
+
+
+@pytest.mark.parametrize("sdxl", [False, True])
+def test_groupnorm_statistics_routing_over_the_unet_graph(monkeypatch, sdxl):
+    """NS-1 wiring on the executor level (emulated ops, so no split-K refusals): every GroupNorm whose input is the output of ONE GEMM / conv
+    - norm2 of every ResBlock, norm1 of the down / mid ResBlocks, every Transformer2DModel.norm, conv_norm_out - takes the statistics
+    its producer accumulated; exactly the up-path norm1's (input = concatenation with the skip tensor) run the statistics pass.  Turning
+    the routing off changes nothing in the result."""
+    EMU.install(monkeypatch)
+    from comat_b200 import engine as E, ops
+    unet = _tiny(sdxl)
+    eng = E.UNetEngine(unet, torch.float32)
+    g = torch.Generator().manual_seed(1)
+    n, hw = 1, (32 if sdxl else 64)                # every level keeps >= 32 rows per image (the epilogue's condition): 8 x 8 at the bottom
+    x = torch.randn(n, 4, hw, hw, generator=g)
+    ctx = torch.randn(n, 77, 64, generator=g)
+    added = dict(text_embeds=torch.randn(n, 16, generator=g), time_ids=torch.tensor([[512., 512, 0, 0, 512, 512]] * n)) if sdxl else None
+    t = torch.tensor(400)
+    calls = {"fused": 0, "two_pass": 0}
+    f0, f1 = ops.groupnorm_fwd_from_sums, ops.groupnorm_fwd
+    monkeypatch.setattr(ops, "groupnorm_fwd_from_sums", lambda *a, **k: (calls.__setitem__("fused", calls["fused"] + 1), f0(*a, **k))[1])
+    monkeypatch.setattr(ops, "groupnorm_fwd", lambda *a, **k: (calls.__setitem__("two_pass", calls["two_pass"] + 1), f1(*a, **k))[1])
+    out = eng.forward(None, E.Var(ops.latent_to_nhwc(x, torch.float32, 64), False), t, ctx, added_cond=added)
+    n_res = len(eng._res_all)
+    n_up_res = sum(len(rs) for rs, _, _ in eng.up)
+    n_tr = sum(len(a) for _, a, _ in eng.down + eng.up if a is not None) + len(eng.mid[1])
+    assert calls["fused"] + calls["two_pass"] == 2 * n_res + n_tr + 1
+    assert calls["two_pass"] == n_up_res, calls
+    monkeypatch.setattr(E, "FUSE_GN_STATS", False)
+    calls["fused"] = calls["two_pass"] = 0
+    ref = eng.forward(None, E.Var(ops.latent_to_nhwc(x, torch.float32, 64), False), t, ctx, added_cond=added)
+    assert calls["fused"] == 0 and calls["two_pass"] == 2 * n_res + n_tr + 1
+    assert rel(out.v, ref.v) < 1e-5
