@@ -492,10 +492,15 @@ def main():
     if a.batch == 0:
         a.batch = CONFIGS[a.config]["batch"]
     _claim_stdout()
-    if os.environ.get("COMAT_BENCH_WATCHDOG"):
-        # debugging aid: dump every thread's Python stack to stderr and exit if the run is still going after N seconds
+    # watchdog: dump every thread's Python stack to stderr and exit if the run is still going after N seconds.  On by default (30 min)
+    # for multi-rank product runs, where a dead-lock between ranks would otherwise sit until the launcher's own limit
+    # (COMAT_BENCH_WATCHDOG=<seconds> sets it for any run, 0 disables).
+    wd = os.environ.get("COMAT_BENCH_WATCHDOG")
+    if wd is None and a.impl == "comat_b200" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        wd = "1800"
+    if wd and int(wd) > 0:
         import faulthandler
-        faulthandler.dump_traceback_later(int(os.environ["COMAT_BENCH_WATCHDOG"]), exit=True)
+        faulthandler.dump_traceback_later(int(wd), exit=True)
     if os.environ.get("COMAT_HOST_ONLY_TIMING"):
         raise SystemExit("bench.py: COMAT_HOST_ONLY_TIMING is set - refusing to emit a bench line (tools/host_issue_time.py is the host-only probe)")
     if a.impl == "reference":
