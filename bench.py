@@ -788,7 +788,7 @@ def main():
             "timing": "one CUDA-event pair per launch on the launching stream, eager instrumented step after the timed region",
             "note": "the family's launches also carry work that used to be separate passes: bias / time-embedding / residual adds, "
                     "torch.cat as K segments, fused GEGLU (no-grad passes) and, since r02, the GroupNorm statistics of their outputs "
-                    "(49 of 61 GroupNorms per UNet call) - their time counts against the GEMM FLOPs here.  An event pair around every "
+                    "(routed for 49 of 61 GroupNorms per UNet call; 59 % of a step's GroupNorm forwards) - their time counts against the GEMM FLOPs here.  An event pair around every "
                     "launch also measures the ~5-7 us record gap: the same launches' CUPTI kernel durations (bench.py --kineto_step / "
                     "--gemm_shapes, profiles/r02_gemm_shapes_v16.md) sum to 0.238 s per step = 756 TFLOP/s = 0.55 of the peak",
             # DRAM bytes of ONE launch of the family's largest in-step shape from the committed ncu --set full capture
