@@ -142,3 +142,21 @@ def test_dynamic_loss_scale_follows_the_overflow_counter():
     feed[:] = [(2, 8)]
     tr._update_loss_scale()
     assert fp16_a.grad_scale == 1.0                             # floor
+
+
+def test_close_gives_the_garbage_collector_back():
+    """the step freezes the long-lived objects and disables the automatic collector; close() (called by train.py at the end
+    of training) restores both."""
+    import gc
+    from comat_b200.trainer import CoMatTrainer
+    t = object.__new__(CoMatTrainer)
+    t.manual_gc_interval, t._ev_G, t._ev_D = 25, None, None
+    assert gc.isenabled()
+    try:
+        t._gc_before_step()
+        assert not gc.isenabled() and gc.get_freeze_count() > 0
+        t.close()
+        assert gc.isenabled() and gc.get_freeze_count() == 0
+    finally:
+        gc.unfreeze()
+        gc.enable()
