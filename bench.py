@@ -792,9 +792,9 @@ def main():
                     "launch also measures the ~5-7 us record gap: the same launches' CUPTI kernel durations (bench.py --kineto_step / "
                     "--gemm_shapes, profiles/r02_gemm_shapes_v16.md) sum to 0.238 s per step = 756 TFLOP/s = 0.55 of the peak",
             # DRAM bytes of ONE launch of the family's largest in-step shape from the committed ncu --set full capture
-            "traffic": 22.9e6, "traffic_note": "dram__bytes_read + write of one conv3x3 320->320 launch at 64x64, n=8 (gemm_tc_kernel<160,3>): 22.9 MB "
+            "traffic": 22.86e6, "traffic_note": "dram__bytes_read + write of one conv3x3 320->320 launch at 64x64, n=8 (gemm_tc_kernel<160,3,LEAN>): 22.85 MB "
                        "read + 0.006 MB written back at capture time; algorithmic bytes 21.0 MB activations in + 1.8 MB weights + 21.0 MB out (the "
-                       "output is still L2-resident when the kernel ends); profiles/r02_ncu_v4_before_staged_export.md"}
+                       "output is still L2-resident when the kernel ends); profiles/r02_ncu_gemm_final.md"}
 
     if rank == 0:
         # whole-job aggregate (weak scaling): every rank runs K optimiser steps on its own batch of `--batch` prompts, so the job
